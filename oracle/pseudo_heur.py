@@ -1,0 +1,29 @@
+"""Deterministic pseudo-heuristics used to drive reference, oracle and engine with IDENTICAL h-values
+(the "injected-h" parity protocol).  TEST INFRASTRUCTURE ONLY.
+
+Values are multiples of 1/64 in [0, 64) so that float32/float64 representations are exact and f-ties
+are frequent (which stresses the (f, push order) tie-break of OPEN).
+"""
+import numpy as np
+
+
+def _acc(states: np.ndarray) -> np.ndarray:
+    s = np.ascontiguousarray(states, dtype=np.uint8).astype(np.uint64)
+    w = ((np.arange(s.shape[1], dtype=np.uint64) + np.uint64(1)) * np.uint64(2654435761)) & np.uint64(0xFFFFFFFF)
+    return (s * w[None, :]).sum(axis=1) & np.uint64(0xFFFFFFFF)
+
+
+def pseudo_v(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
+    """[N,S] u8 -> float64 [N]"""
+    acc = _acc(states)
+    return (((acc >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.float32) / np.float32(64.0)).astype(np.float64)
+
+
+def make_pseudo_q(num_actions: int):
+    def pseudo_q(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
+        """[N,S] u8 -> float64 [N,A]"""
+        acc = _acc(states)
+        a = (np.arange(num_actions, dtype=np.uint64) * np.uint64(0x9E3779B1))[None, :]
+        v = (acc[:, None] + a) & np.uint64(0xFFFFFFFF)
+        return (((v >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.float32) / np.float32(64.0)).astype(np.float64)
+    return pseudo_q

@@ -1,0 +1,147 @@
+"""Pins the CPU oracle (oracle/) to outputs of the unmodified reference (tests/golden) and to the
+reference's own committed known-answer files.  CPU only."""
+import numpy as np
+import pytest
+
+from oracle.domains_np import OracleDomain, cube3_perm, npuzzle_swap_lut
+from oracle.nnet_torch import resnet_fc_forward, heurv_from_state_dict, heurq_from_state_dict
+from oracle.pseudo_heur import pseudo_v, make_pseudo_q
+from oracle.search import OracleSearch, solve_one
+
+import golden_utils as gu
+
+
+def test_cube3_perm_matches_reference():
+    assert np.array_equal(cube3_perm(), gu.load("domains")["cube3_perm"])
+
+
+@pytest.mark.parametrize("d", [3, 4, 5])
+def test_npuzzle_lut_matches_reference(d):
+    assert np.array_equal(npuzzle_swap_lut(d), gu.load("domains")[f"npuzzle{d}_lut"])
+
+
+@pytest.mark.parametrize("name,dim,key", [("cube3", 0, "cube3"), ("npuzzle", 3, "npuzzle3"), ("npuzzle", 4, "npuzzle4"),
+                                          ("npuzzle", 5, "npuzzle5"), ("grid", 7, "grid7")])
+def test_expand_matches_reference(name, dim, key):
+    z = gu.load("domains")
+    dom = OracleDomain(name, dim)
+    assert np.array_equal(dom.expand(z[key + "_states"]), z[key + "_children"])
+    if key + "_solved" in z:
+        assert np.array_equal(dom.is_solved(z[key + "_states"], z[key + "_goals"]), z[key + "_solved"])
+    if key + "_solved_wild" in z:
+        assert np.array_equal(dom.is_solved(z[key + "_states"], z[key + "_goals_wild"]), z[key + "_solved_wild"])
+
+
+def test_expand_edge_cases():
+    dom = OracleDomain("cube3")
+    assert dom.expand(np.zeros((0, 54), np.uint8)).shape == (0, 54)
+    # every move is a permutation and a^1 is its inverse (ref: cube3.py:560-574)
+    ident = np.arange(54, dtype=np.uint8)[None]
+    for a in range(12):
+        s1 = dom.next_state(ident, np.array([a]))
+        assert sorted(s1[0].tolist()) == list(range(54))
+        assert np.array_equal(dom.next_state(s1, np.array([a ^ 1])), ident)
+
+
+@pytest.mark.parametrize("tag,dname,dim,depth,q", [("cube3v", "cube3", 0, 6, False), ("np4v", "npuzzle", 4, 16, False),
+                                                   ("cube3q", "cube3", 0, 6, True), ("cube3v_nobn", "cube3", 0, 6, False)])
+def test_nnet_matches_reference(tag, dname, dim, depth, q):
+    z = gu.load("nnet")
+    sd = gu.state_dict_torch(tag)
+    fn = (heurq_from_state_dict if q else heurv_from_state_dict)(sd, depth)
+    out = fn(z[tag + "_states"].astype(np.int64))
+    # same torch ops on the same machine class -> expect (near) bit equality; allow fp32 reassociation
+    np.testing.assert_allclose(out, z[tag + "_out"], rtol=0, atol=2e-5)
+    # chunked evaluation (nnet_batch_size) must not change the result materially
+    out2 = (heurq_from_state_dict if q else heurv_from_state_dict)(sd, depth, batch_size=7)(z[tag + "_states"].astype(np.int64))
+    np.testing.assert_allclose(out2, out, rtol=0, atol=2e-5)
+
+
+def test_grid_nets_match_reference():
+    z = gu.load("nnet")
+    dom = OracleDomain("grid", 7)
+    x = dom.nnet_input(z["gridv_states"], z["gridv_goals"])
+    np.testing.assert_allclose(heurv_from_state_dict(gu.state_dict_torch("gridv"), 7)(x), z["gridv_out"], atol=2e-5, rtol=0)
+    np.testing.assert_allclose(heurq_from_state_dict(gu.state_dict_torch("gridq"), 7)(x), z["gridq_out"], atol=2e-5, rtol=0)
+
+
+def _heur_for(cfg, dom):
+    heur = str(cfg[2])
+    if heur in ("v_zero", "q_zero"):
+        return None
+    if heur == "v_pseudo":
+        return pseudo_v
+    if heur == "q_pseudo":
+        return make_pseudo_q(dom.num_actions)
+    prefix = {"v_net": "gridv", "q_net": "gridq"}[heur]
+    depth = dom.input_info()[1]
+    mk = heurq_from_state_dict if heur == "q_net" else heurv_from_state_dict
+    f = mk(gu.state_dict_torch(prefix), depth)
+    return lambda s, g: f(dom.nnet_input(s, g))
+
+
+@pytest.mark.parametrize("tag", gu.trace_tags())
+@pytest.mark.parametrize("kept_only", [False, True])
+def test_search_trace_matches_reference(tag, kept_only):
+    c = gu.trace_case(tag)
+    name, dim = gu.parse_domain(str(c["cfg"][0]))
+    b, w = gu.parse_pathfind(str(c["cfg"][1]))
+    is_q = str(c["cfg"][2]).startswith("q")
+    if is_q and kept_only:
+        pytest.skip("kept-only evaluation is an A* option")
+    dom = OracleDomain(name, dim)
+    srch = OracleSearch(dom, _heur_for(c["cfg"], dom), is_q, b, w, eval_kept_only=kept_only)
+    insts = srch.add_instances(c["states"], c["goals"])
+    n_steps = c["itr"].shape[0]
+    for t in range(n_steps):
+        assert not srch.all_finished()
+        srch.step()
+        for j, inst in enumerate(insts):
+            ids = inst.nodes_curr
+            assert len(ids) == c["n_next"][t, j], (t, j)
+            assert gu.digest(inst.store.state[ids], inst.store.g[ids]) == c["dig_next"][t, j], (t, j)
+            assert len(inst.open) == c["open"][t, j] and len(inst.closed) == c["closed"][t, j], (t, j)
+            if kept_only and str(c["cfg"][2]).endswith("net"):
+                # a different NN batch composition changes MKL's summation order by ~1 ulp (fp32)
+                assert np.isclose(inst.lb, c["lb"][t, j], rtol=1e-6, atol=0) and inst.ub == c["ub"][t, j], (t, j)
+            else:
+                assert inst.lb == c["lb"][t, j] and inst.ub == c["ub"][t, j], (t, j)
+            assert inst.num_nodes_generated == c["gen"][t, j] and inst.itr == c["itr"][t, j], (t, j)
+            assert inst.finished() == c["finished"][t, j], (t, j)
+    off = 0
+    for j, inst in enumerate(insts):
+        assert inst.path_cost() == c["path_cost"][j]
+        ln = int(c["actions_len"][j])
+        if ln >= 0:
+            assert inst.get_path()[1] == c["actions_flat"][off: off + ln].tolist()
+            off += ln
+
+
+def test_kat_brute_easy():
+    """tutorial/cube3/results_brute_easy (zero heuristic, graph.1B_1.0W): committed by the reference authors."""
+    k = gu.load("kat_cube3")
+    dom = OracleDomain("cube3")
+    off = 0
+    for i in range(10):
+        if k["easy_nodes"][i] > 3000:
+            off += int(k["easy_actions_len"][i])
+            continue  # two 12k-node instances: covered by the slower KAT below
+        r = solve_one(dom, k["easy_states"][i], k["easy_goals"][i], None, False, 1, 1.0)
+        ln = int(k["easy_actions_len"][i])
+        assert r["path_cost"] == k["easy_path_costs"][i] and r["num_nodes_generated"] == k["easy_nodes"][i]
+        assert r["iterations"] == k["easy_iterations"][i] and r["actions"] == k["easy_actions_flat"][off: off + ln].tolist()
+        off += ln
+
+
+@pytest.mark.parametrize("idx", [4, 8])
+def test_kat_heur_hard(idx):
+    """tutorial/cube3/results_heur_hard (trained resnet_fc.200H_2B_bn, graph.100B_0.1W)."""
+    k = gu.load("kat_cube3")
+    dom = OracleDomain("cube3")
+    f = heurv_from_state_dict(gu.state_dict_torch("cube3v"), 6)
+    r = solve_one(dom, k["hard_states"][idx], k["hard_goals"][idx], lambda s, g: f(s.astype(np.int64)), False, 100, 0.1)
+    off = int(k["hard_actions_len"][:idx].sum())
+    ln = int(k["hard_actions_len"][idx])
+    assert r["path_cost"] == k["hard_path_costs"][idx]
+    assert r["num_nodes_generated"] == k["hard_nodes"][idx] and r["iterations"] == k["hard_iterations"][idx]
+    assert r["actions"] == k["hard_actions_flat"][off: off + ln].tolist()

@@ -1,0 +1,295 @@
+"""Generate tests/golden/*.npz by running the UNMODIFIED reference (/root/reference) in the build
+container.  The reference cannot travel to the GPU box, so its outputs are committed as fixtures.
+
+    python tools/gen_golden.py            # rewrites tests/golden/
+
+Fixtures (all plain numpy arrays, no pickled reference classes):
+  domains.npz        move tables + expand / is_solved outputs of the reference domains
+  nnet.npz           weights (trained tutorial nets + small random nets) and reference network outputs
+  kat_cube3.npz      tutorial/cube3/{easy,hard}.pkl states and the committed results.pkl of
+                     results_brute_easy / results_heur_hard (costs, nodes, iterations, actions)
+  traces.npz         per-iteration digests of reference graph_v / graph_q runs (zero heuristic,
+                     injected pseudo-heuristic, trained nets), several instances in lock-step
+"""
+import os
+import pickle
+import random
+import sys
+import zlib
+
+import numpy as np
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+
+from oracle.ref_shim import import_reference, REF_ROOT  # noqa: E402
+from oracle.pseudo_heur import pseudo_v, make_pseudo_q  # noqa: E402
+
+import_reference()
+from deepxube.factories.domain_factory import get_domain_from_arg  # noqa: E402
+from deepxube.factories.pathfinding_factory import get_pathfind_from_arg  # noqa: E402
+from deepxube.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict  # noqa: E402
+from deepxube.pathfind_fns.fns_core import PFNsHeurVC, PFNsHeurQC  # noqa: E402
+from deepxube.base.pathfinding import get_path  # noqa: E402
+
+OUT = os.path.join(ROOT, "tests", "golden")
+os.makedirs(OUT, exist_ok=True)
+
+
+def seed_all(s: int) -> None:
+    random.seed(s)
+    np.random.seed(s)
+    torch.manual_seed(s)
+
+
+def state_np(s) -> np.ndarray:
+    if hasattr(s, "colors"):
+        return np.asarray(s.colors, np.uint8)
+    if hasattr(s, "tiles"):
+        return np.asarray(s.tiles, np.uint8)
+    return np.array([s.robot_x, s.robot_y], np.uint8)
+
+
+def states_np(sl) -> np.ndarray:
+    return np.stack([state_np(s) for s in sl]) if len(sl) else np.zeros((0, 1), np.uint8)
+
+
+def digest(states: np.ndarray, g: np.ndarray) -> int:
+    return zlib.crc32(np.ascontiguousarray(g, np.float64).tobytes(), zlib.crc32(np.ascontiguousarray(states, np.uint8).tobytes()))
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_domains() -> None:
+    out = {}
+    seed_all(0)
+    cube, _ = get_domain_from_arg("cube3")
+    from deepxube.domains.cube3 import Cube3State
+    ident = Cube3State(np.arange(54, dtype=np.uint8))
+    out["cube3_perm"] = np.stack([state_np(cube.next_state([ident], [a])[0][0]) for a in cube.get_actions_fixed()]).astype(np.int64)
+    st, goals = cube.sample_problem_instances(list(np.random.randint(0, 40, size=48)))
+    out["cube3_states"] = states_np(st)
+    out["cube3_goals"] = states_np(goals) if hasattr(goals[0], "tiles") else np.stack([g.colors for g in goals]).astype(np.uint8)
+    ch, acts, tcs = cube.expand(st)
+    out["cube3_children"] = np.stack([state_np(c) for row in ch for c in row])
+    assert all(a.action == i for row in acts for i, a in enumerate(row)) and all(t == 1.0 for row in tcs for t in row)
+    out["cube3_solved"] = np.array(cube.is_solved(st, goals))
+
+    for d in (3, 4, 5):
+        dom, _ = get_domain_from_arg(f"npuzzle.{d}")
+        out[f"npuzzle{d}_lut"] = np.asarray(dom.swap_zero_idxs, np.int64)
+        st, goals = dom.sample_problem_instances(list(np.random.randint(0, 60, size=40)))
+        out[f"npuzzle{d}_states"] = states_np(st)
+        out[f"npuzzle{d}_goals"] = np.stack([g.tiles for g in goals]).astype(np.uint8)
+        ch, acts, tcs = dom.expand(st)
+        out[f"npuzzle{d}_children"] = np.stack([state_np(c) for row in ch for c in row])
+        assert all(t == 1.0 for row in tcs for t in row)
+        out[f"npuzzle{d}_solved"] = np.array(dom.is_solved(st, goals))
+        # wildcard goal (npuzzle.py:154-158)
+        from deepxube.domains.npuzzle import NPGoal
+        wg = np.stack([g.tiles for g in goals]).astype(np.uint8)
+        wg[:, ::2] = d * d
+        out[f"npuzzle{d}_goals_wild"] = wg
+        out[f"npuzzle{d}_solved_wild"] = np.array(dom.is_solved(st, [NPGoal(x) for x in wg]))
+
+    grid, _ = get_domain_from_arg("grid.7d")
+    from deepxube.domains.grid import GridState
+    cells = [GridState(x, y) for x in range(7) for y in range(7)]
+    out["grid7_states"] = states_np(cells)
+    ch, acts, tcs = grid.expand(cells)
+    out["grid7_children"] = np.stack([state_np(c) for row in ch for c in row])
+    np.savez_compressed(os.path.join(OUT, "domains.npz"), **out)
+    print("domains.npz", {k: v.shape for k, v in out.items()})
+
+
+# ------------------------------------------------------------------------------------------------
+def sd_to_np(sd, prefix: str) -> dict:
+    return {prefix + k.replace("module.", ""): v.numpy() for k, v in sd.items()}
+
+
+def ref_nnet_raw(domain, domain_name, fn_str, nnet_file, states, goals):
+    """Raw reference network outputs (before clipping) + processed outputs through the reference's
+    own heurv / heurq callable."""
+    pfns, par = get_path_fns_nnet_par_dict(domain, domain_name, [fn_str], torch.device("cpu"), nnet_files=[nnet_file])
+    if hasattr(pfns, "heurv"):
+        vals = np.array(pfns.heurv(states, goals, [None] * len(states)), np.float64)
+    else:
+        acts = domain.get_state_actions(states)
+        vals = np.array(pfns.heurq(states, goals, acts, [None] * len(states)), np.float64)
+    return pfns, vals
+
+
+def gen_nnet() -> None:
+    out = {}
+    seed_all(1)
+    # trained cube3 heurv net (tutorial)
+    cube, _ = get_domain_from_arg("cube3")
+    f = os.path.join(REF_ROOT, "tutorial/cube3/models/heur.pt")
+    out.update(sd_to_np(torch.load(f, map_location="cpu", weights_only=True), "cube3v/"))
+    st, goals = cube.sample_problem_instances(list(np.random.randint(0, 30, size=96)))
+    _, vals = ref_nnet_raw(cube, "cube3", "heurv,resnet_fc.200H_2B_bn", f, st, goals)
+    out["cube3v_states"], out["cube3v_out"] = states_np(st), vals
+
+    # trained grid nets (tutorial/grid_tut == built-in grid semantics)
+    grid, _ = get_domain_from_arg("grid.7d")
+    from deepxube.domains.grid import GridState, GridGoal
+    cells = [GridState(x, y) for x in range(7) for y in range(7)]
+    gl = [GridGoal((3 * i) % 7, (5 * i + 1) % 7) for i in range(len(cells))]
+    fv = os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_v/heur.pt")
+    fq = os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt")
+    out.update(sd_to_np(torch.load(fv, map_location="cpu", weights_only=True), "gridv/"))
+    out.update(sd_to_np(torch.load(fq, map_location="cpu", weights_only=True), "gridq/"))
+    _, vals = ref_nnet_raw(grid, "grid", "heurv,resnet_fc.100H_1B_bn", fv, cells, gl)
+    out["gridv_states"], out["gridv_goals"], out["gridv_out"] = states_np(cells), np.array([[g.robot_x, g.robot_y] for g in gl], np.uint8), vals
+    _, vals = ref_nnet_raw(grid, "grid", "heurq_fixout,resnet_fc.100H_1B_bn", fq, cells, gl)
+    out["gridq_out"] = vals
+
+    # small random nets with non-trivial BN statistics, saved through the reference's own modules
+    import tempfile
+    from oracle.nnet_torch import random_state_dict
+    for tag, dname, dstr, fn, in_dim, depth, odim in (("np4v", "npuzzle", "npuzzle.4", "heurv,resnet_fc.96H_2B_bn", 16, 16, 1),
+                                                        ("cube3q", "cube3", "cube3", "heurq_fixout,resnet_fc.128H_1B_bn", 54, 6, 12),
+                                                        ("cube3v_nobn", "cube3", "cube3", "heurv,resnet_fc.64H_1B", 54, 6, 1)):
+        dom, _ = get_domain_from_arg(dstr)
+        h = int(fn.split("resnet_fc.")[1].split("H")[0])
+        nb = int(fn.split("H_")[1].split("B")[0])
+        sd = random_state_dict(in_dim * depth, h, nb, odim, batch_norm=fn.endswith("bn"), seed=7, randomize_bn=True)
+        with tempfile.NamedTemporaryFile(suffix=".pt") as tf:
+            torch.save(sd, tf.name)
+            st, goals = dom.sample_problem_instances(list(np.random.randint(0, 30, size=64)))
+            _, vals = ref_nnet_raw(dom, dname, fn, tf.name, st, goals)
+        out.update(sd_to_np(sd, tag + "/"))
+        out[tag + "_states"], out[tag + "_out"] = states_np(st), vals
+    np.savez_compressed(os.path.join(OUT, "nnet.npz"), **out)
+    print("nnet.npz", len(out), "arrays")
+
+
+# ------------------------------------------------------------------------------------------------
+def gen_kat() -> None:
+    out = {}
+    for name in ("easy", "hard"):
+        d = pickle.load(open(os.path.join(REF_ROOT, f"tutorial/cube3/{name}.pkl"), "rb"))
+        out[f"{name}_states"] = states_np(d["states"])
+        out[f"{name}_goals"] = np.stack([g.colors for g in d["goals"]]).astype(np.uint8)
+    for name, rdir in (("easy", "results_brute_easy"), ("hard", "results_heur_hard")):
+        r = pickle.load(open(os.path.join(REF_ROOT, f"tutorial/cube3/{rdir}/results.pkl"), "rb"))
+        out[f"{name}_path_costs"] = np.array(r["path_costs"], np.float64)
+        out[f"{name}_nodes"] = np.array(r["num_nodes_generated"], np.int64)
+        out[f"{name}_iterations"] = np.array(r["iterations"], np.int64)
+        out[f"{name}_solved"] = np.array(r["solved"])
+        acts = [[a.action for a in al] for al in r["actions"]]
+        out[f"{name}_actions_flat"] = np.array([x for al in acts for x in al], np.int64)
+        out[f"{name}_actions_len"] = np.array([len(al) for al in acts], np.int64)
+    np.savez_compressed(os.path.join(OUT, "kat_cube3.npz"), **out)
+    print("kat_cube3.npz", {k: v.shape for k, v in out.items()})
+
+
+# ------------------------------------------------------------------------------------------------
+def run_trace(domain, pfns, pathfind_str, states, goals, max_steps):
+    """Runs the reference PathFind on all instances in lock-step and records per-step digests."""
+    pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
+    insts = pathfind.make_instances(states, goals, None, True)
+    pathfind.add_instances(insts)
+    n = len(insts)
+    rec = {k: [] for k in ("n_next", "dig_next", "open", "closed", "lb", "ub", "gen", "itr", "finished")}
+    steps = 0
+    while (not all(i.finished() for i in insts)) and steps < max_steps:
+        pathfind.step()
+        steps += 1
+        for k in rec:
+            rec[k].append([])
+        for inst in insts:
+            nodes = inst._nodes_curr
+            st = states_np([x.state for x in nodes]) if nodes else np.zeros((0, 1), np.uint8)
+            g = np.array([x.path_cost for x in nodes], np.float64)
+            rec["n_next"][-1].append(len(nodes))
+            rec["dig_next"][-1].append(digest(st, g))
+            rec["open"][-1].append(len(inst.open_set))
+            rec["closed"][-1].append(len(inst.closed_dict))
+            rec["lb"][-1].append(inst.lb)
+            rec["ub"][-1].append(inst.ub)
+            rec["gen"][-1].append(inst.num_nodes_generated)
+            rec["itr"][-1].append(inst.itr)
+            rec["finished"][-1].append(inst.finished())
+    res = {k: np.array(v) for k, v in rec.items()}
+    res["path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
+    acts = []
+    for i in insts:
+        acts.append([a.action for a in get_path(i.goal_node)[1]] if i.goal_node is not None else [])
+    res["actions_flat"] = np.array([x for al in acts for x in al], np.int64)
+    res["actions_len"] = np.array([len(al) if i.goal_node is not None else -1 for al, i in zip(acts, insts)], np.int64)
+    res["pathfind_name"] = np.array(name)
+    return res
+
+
+def wrap_v(fn):
+    return PFNsHeurVC(heurv=lambda states, goals, ctxs: fn(states_np(states)).tolist())
+
+
+def wrap_q(fn):
+    return PFNsHeurQC(heurq=lambda states, goals, acts, ctxs: fn(states_np(states)).tolist())
+
+
+def goals_np(goals) -> np.ndarray:
+    g0 = goals[0]
+    if hasattr(g0, "colors"):
+        return np.stack([g.colors for g in goals]).astype(np.uint8)
+    if hasattr(g0, "tiles"):
+        return np.stack([g.tiles for g in goals]).astype(np.uint8)
+    return np.array([[g.robot_x, g.robot_y] for g in goals], np.uint8)
+
+
+def gen_traces() -> None:
+    out = {}
+
+    def add(tag, domain_str, pathfind_str, heur, steps_l, max_steps, nnet=None):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        is_q = heur.startswith("q")
+        if heur in ("v_zero", "q_zero"):
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv" if not is_q else "heurq_fixout"], torch.device("cpu"))
+        elif heur == "v_pseudo":
+            pfns = wrap_v(pseudo_v)
+        elif heur == "q_pseudo":
+            pfns = wrap_q(make_pseudo_q(domain.get_num_acts()))
+        else:
+            fn_str, f = nnet
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, [fn_str], torch.device("cpu"), nnet_files=[f])
+        res = run_trace(domain, pfns, pathfind_str, states, goals, max_steps)
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, "" if nnet is None else nnet[0]])
+        for k, v in res.items():
+            out[tag + "/" + k] = v
+        print(tag, res["pathfind_name"], "steps", res["itr"].shape[0], "cost", res["path_cost"], "gen", res["gen"][-1])
+
+    add("cube3_v_zero_10B", "cube3", "graph.10B", "v_zero", [0, 1, 2] * 3, 200)
+    add("cube3_v_zero_1B", "cube3", "graph", "v_zero", [0, 1, 2, 3], 400)
+    add("cube3_v_pseudo", "cube3", "graph.100B_0.6W", "v_pseudo", [30, 50, 70, 100], 12)
+    add("cube3_v_pseudo_big", "cube3", "graph.1000B_0.3W", "v_pseudo", [40, 60], 8)
+    add("cube3_q_zero_10B", "cube3", "graph.10B", "q_zero", [0, 1, 2] * 2, 200)
+    add("cube3_q_pseudo", "cube3", "graph.50B_0.6W", "q_pseudo", [30, 50, 70], 12)
+    add("np4_v_pseudo", "npuzzle.4", "graph.50B_0.8W", "v_pseudo", [10, 30, 60, 90], 20)
+    add("np4_v_zero", "npuzzle.4", "graph.20B", "v_zero", [0, 3, 6], 300)
+    add("np3_v_zero", "npuzzle.3", "graph.5B", "v_zero", [0, 8, 20], 600)
+    add("grid7_v_zero", "grid.7d", "graph", "v_zero", [0, 3, 9, 20, 50], 400)
+    add("grid7_q_zero", "grid.7d", "graph.2B", "q_zero", [0, 3, 9, 20, 50], 400)
+    add("grid7_v_net", "grid.7d", "graph.1B_1.0W", "v_net", list(np.arange(12) * 7), 400,
+        ("heurv,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_v/heur.pt")))
+    add("grid7_q_net", "grid.7d", "graph.1B_1.0W", "q_net", list(np.arange(12) * 7), 400,
+        ("heurq_fixout,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt")))
+    np.savez_compressed(os.path.join(OUT, "traces.npz"), **out)
+    print("traces.npz", len(out), "arrays")
+
+
+if __name__ == "__main__":
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces"]
+    if "domains" in which:
+        gen_domains()
+    if "nnet" in which:
+        gen_nnet()
+    if "kat" in which:
+        gen_kat()
+    if "traces" in which:
+        gen_traces()

@@ -1,0 +1,229 @@
+// Internal definitions shared by the engine's translation units (not part of the C ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <string>
+
+#include "dxb200.h"
+
+#define DX_NIL 0xFFFFFFFFu
+#define DX_PENDING 0x80000000u          // slot rep points into the child batch, not the node store
+#define DX_EMPTY64 0xFFFFFFFFFFFFFFFFull
+#define DX_SORT_TILE 2048               // elements per radix / merge tile
+#define DX_NUM_DIGITS 12                // 8 bytes of f-key + 4 bytes of instance id
+#define DX_MAX_OUT 32                   // max network outputs (actions) supported
+
+// error bits in Ctl::error (sticky, set on the device)
+#define DX_DEVERR_NODES 1u
+#define DX_DEVERR_OPEN 2u
+#define DX_DEVERR_POP 4u
+
+void dx_set_error(const std::string& msg);
+
+#define DX_CUDA(call)                                                                          \
+    do {                                                                                       \
+        cudaError_t _e = (call);                                                               \
+        if (_e != cudaSuccess) {                                                               \
+            dx_set_error(std::string(#call) + ": " + cudaGetErrorString(_e) + " at " + __FILE__ + ":" + \
+                         std::to_string(__LINE__));                                            \
+            return DX_ERR_CUDA;                                                                \
+        }                                                                                      \
+    } while (0)
+
+// ---------------------------------------------------------------------------------------------
+// Domain description (device copy passed by value to kernels).
+struct DomainDev {
+    int kind;        // enum dx_domain
+    int dim;
+    int S;           // state bytes
+    int SP;          // row bytes: S rounded up so that a 4-byte instance id fits at SP-4, multiple of 16
+    int A;           // actions
+    int in_count;    // NN integer inputs (S, or S + goal bytes for grid)
+    int depth;       // one-hot depth
+    const uint8_t* table;   // cube3: perm [12*54] (next[d] = cur[perm[a*54+d]]); npuzzle: lut [d*d*4]
+};
+
+// Device-resident control block: everything a kernel needs to size its own work, so that the host
+// never has to synchronise inside an iteration.
+struct Ctl {
+    uint32_t n_inst;
+    uint32_t n_pop;        // entries in the current popped list (all instances)
+    uint32_t n_children;   // n_pop * A (A*) ; Q*: number of popped edges
+    uint32_t n_kept;       // nodes appended to the node store this iteration
+    uint32_t node_count;   // nodes in the node store
+    uint32_t node_base;    // node_count at the start of this iteration
+    uint32_t epoch;        // iteration stamp for the per-slot batch lists
+    uint32_t error;
+    uint32_t n_unfinished;
+    uint32_t itr;          // PathFind.itr
+    uint32_t open_total;   // entries in OPEN (all instances) after this iteration
+    uint32_t n_tiles;      // merge tiles this iteration
+    uint32_t nn_row_start; // heuristic job: rows [nn_row_start, nn_row_start + nn_n) of the job's row array
+    uint32_t nn_n;
+    uint32_t sort_final;   // which sort buffer holds the sorted batch
+    uint32_t sort_n;       // elements in the sort batch
+    unsigned long long heur_evals;
+    unsigned long long gen_total;
+    uint32_t pass_src[DX_NUM_DIGITS];
+    uint32_t pass_skip[DX_NUM_DIGITS];
+};
+
+// Per-instance state (structure of arrays, capacity max_instances (+1 for offset arrays)).
+struct InstArrays {
+    int32_t* batch;             // InstanceGraph.batch_size
+    double* weight;             // InstanceGraph.weight
+    double* lb;                 // InstanceGraph.lb
+    unsigned long long* ub_key; // (float bits of g << 32) | pop sequence number of the best solved popped node
+    uint32_t* goal_node;        // node id or DX_NIL
+    uint32_t* itr;              // Instance.itr
+    unsigned long long* gen;    // Instance.num_nodes_generated
+    uint8_t* active;            // not finished() at the start of the current iteration
+    uint32_t* pop_seq_base;     // nodes popped so far (tie-break for "first solved node wins")
+    uint32_t* n_open;           // OPEN entries
+    uint32_t* m_new;            // entries pushed this iteration
+    uint32_t* k_pop;            // entries popped this iteration
+    uint32_t* batch_off;        // [I+1] offsets into the sorted batch
+    uint32_t* tile_off;         // [I+1] merge tile offsets
+    unsigned long long* f_first;// key of the first popped entry this iteration
+    uint8_t* goals;             // [I, SP] goal rows
+};
+
+struct NetDev {
+    int in_count, depth, H, Hp, num_blocks, out_dim, in_dim, in_dim_p;
+    // fp32 parameters (BN folded)
+    float* w0t;      // [in_dim, Hp]  first layer, transposed (row = one-hot feature)
+    float* b0;       // [Hp]
+    float* wres;     // [num_blocks*2, Hp, Hp]  row-major [out, in]
+    float* bres;     // [num_blocks*2, Hp]
+    float* wout;     // [out_dim, Hp]
+    float* bout;     // [out_dim]
+    // bf16 copies for the tensor-core path
+    void* w0_bf16;   // [Hp, in_dim_p]  K-major
+    void* wres_bf16; // [num_blocks*2, Hp, Hp] K-major
+};
+
+static inline int dx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// ---------------------------------------------------------------------------------------------
+// 64-bit hash of a row (state bytes + padding + instance id), 16 bytes at a time.
+__device__ __forceinline__ uint64_t dx_mix64(uint64_t h) {
+    h ^= h >> 33;
+    h *= 0xff51afd7ed558ccdull;
+    h ^= h >> 33;
+    h *= 0xc4ceb9fe1a85ec53ull;
+    h ^= h >> 33;
+    return h;
+}
+
+__device__ __forceinline__ uint64_t dx_hash_row(const uint4* __restrict__ row, int chunks) {
+    uint64_t h = 0x9E3779B97F4A7C15ull;
+    for (int i = 0; i < chunks; ++i) {
+        uint4 v = row[i];
+        uint64_t a = ((uint64_t)v.y << 32) | v.x, b = ((uint64_t)v.w << 32) | v.z;
+        h = dx_mix64(h ^ a) + 0x632BE59BD9B4E019ull;
+        h = dx_mix64(h ^ b) + 0x9E3779B97F4A7C15ull;
+    }
+    return h;
+}
+
+__device__ __forceinline__ bool dx_rows_equal(const uint4* __restrict__ a, const uint4* __restrict__ b, int chunks) {
+    bool eq = true;
+    for (int i = 0; i < chunks; ++i) {
+        uint4 x = a[i], y = b[i];
+        eq = eq && (x.x == y.x) && (x.y == y.y) && (x.z == y.z) && (x.w == y.w);
+    }
+    return eq;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Launchers (each returns the number of kernels it launched).
+struct ScanTemp {
+    uint32_t* block_sums;   // [>= ceil(n_max / 4096) + 1]
+};
+
+struct ClosedDev {
+    unsigned long long* slot_key;   // (tag << 32) | rep ; DX_EMPTY64 when free
+    float* slot_g;                  // CLOSED[state] (inf when new)
+    unsigned long long* slot_head;  // (epoch << 32) | first item of this state in the current batch
+    uint32_t mask;                  // capacity - 1
+};
+
+struct SortBufs {
+    unsigned long long* key[2];
+    uint32_t* inst[2];
+    uint32_t* val[2];
+    uint32_t* hist;       // [256 * max_tiles (+ slack)]
+    uint32_t* ghist;      // [DX_NUM_DIGITS * 256]
+    int max_tiles;
+};
+
+struct MlpBufs {
+    float* x[3];          // fp32 activations [cap, Hp]
+    void* xb[3];          // bf16 activations [cap, Hp]
+    long long cap;        // rows
+};
+
+// k_domain.cu
+int dx_launch_expand(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                     const float* node_g, const uint32_t* popped, const uint32_t* popped_inst, const uint32_t* pop_off,
+                     uint8_t* child_state, float* child_g, uint8_t* pop_solved, int max_pop);
+int dx_launch_goal_resolve(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const uint32_t* popped,
+                           const uint32_t* popped_inst, const uint32_t* pop_off, const uint8_t* pop_solved, int max_pop);
+int dx_launch_check_solved(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                           const float* node_g, const uint32_t* popped, const uint32_t* popped_inst, const uint32_t* pop_off,
+                           uint8_t* pop_solved, int max_pop);
+int dx_launch_expand_edges(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint32_t* edges, uint32_t* popped_out,
+                           uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, int max_pop);
+int dx_launch_standalone_expand(cudaStream_t s, const DomainDev& d, const uint8_t* rows, long long n, const int32_t* actions,
+                                uint8_t* out_rows);
+int dx_launch_standalone_solved(cudaStream_t s, const DomainDev& d, const uint8_t* rows, const uint8_t* goal_rows, long long n,
+                                uint8_t* out);
+
+// k_closed.cu
+int dx_launch_closed_init(cudaStream_t s, const ClosedDev& c);
+int dx_launch_closed_seed(cudaStream_t s, const DomainDev& d, const ClosedDev& c, const uint8_t* node_state, uint32_t first_node,
+                          uint32_t n);
+int dx_launch_closed_filter(cudaStream_t s, const DomainDev& d, const ClosedDev& c, const Ctl* ctl, const InstArrays& ia,
+                            const uint8_t* node_state, const float* node_g, const uint8_t* child_state, const float* child_g,
+                            const uint32_t* item_node, const uint32_t* popped_inst, uint32_t* child_slot, uint32_t* child_next,
+                            uint8_t* child_flags, int max_children, int group);
+int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const uint8_t* child_state,
+                           const float* child_g, const uint32_t* child_slot, const uint8_t* child_flags,
+                           const uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
+                           uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
+                           int max_children);
+int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,
+                            const uint32_t* child_slot, const uint8_t* child_flags, int max_items);
+
+// k_scan.cu
+int dx_launch_scan_flags(cudaStream_t s, const uint8_t* flags, uint32_t* out_prefix, const uint32_t* n_ptr, uint32_t* total_out,
+                         int n_max, const ScanTemp& t);
+int dx_launch_scan_u32(cudaStream_t s, uint32_t* data, int n, const uint32_t* skip_flag, const ScanTemp& t);
+
+// k_open.cu
+int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                   uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
+                   uint32_t max_pop, uint32_t max_open);
+int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
+                        const uint32_t* new_inst, const SortBufs& sb, int max_n);
+int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
+                          const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
+                          const SortBufs& sb, int A, int max_pop);
+int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n);
+int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
+                    const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
+                    unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
+                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles);
+int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
+                       int A, int gen_mode);
+
+// k_mlp_f32.cu / k_mlp_tc.cu
+// rows: [*, SP] row array; the job is ctl->nn_row_start / nn_n.  out_h (nullable) <- max(out0,0) (V) or min_a q (Q);
+// out_q (nullable) [*, out_dim] <- max(out,0).  Outputs are indexed by (nn_row_start + r) when absolute != 0, else r.
+int dx_launch_out_layer(cudaStream_t s, const NetDev& net, const Ctl* ctl, const float* X, float* out_h, float* out_q,
+                        int absolute, long long max_rows);
+int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
+                      const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
+int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
+                       const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);

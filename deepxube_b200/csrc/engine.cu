@@ -1,0 +1,1078 @@
+// Engine: owns device memory + one stream, sequences the kernels of one PathFind.step() and implements
+// the C ABI of include/dxb200.h.  No kernel launch depends on a host-side read of device state: every
+// kernel sizes itself from the device-resident Ctl block, so an iteration is a fixed launch sequence.
+//
+// Iteration order (A*, deepxube/base/pathfinding.py:338-400 + :621-643):
+//   expand + is_solved + record_goal -> CLOSED filter -> compaction (node ids = push order) ->
+//   heuristic of the kept children -> f-keys -> sort -> merge/pop -> lb/finished/itr.
+//   (The reference evaluates the heuristic before filtering; values of filtered children are never
+//    read, so evaluating only the kept ones is observationally identical -- SURVEY.md App. B.6.)
+// Iteration order (Q*, base/pathfinding.py:471-525 + :646-671):
+//   is_solved + record_goal -> CLOSED filter on popped nodes -> edges of kept nodes -> f-keys -> sort ->
+//   merge/pop edges -> next_state per popped edge -> heuristic (all-action q, h = min) -> lb/finished/itr.
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <vector>
+
+#include "dx_internal.cuh"
+
+static thread_local std::string g_last_error;
+void dx_set_error(const std::string& msg) { g_last_error = msg; }
+extern "C" const char* dx_last_error(void) { return g_last_error.c_str(); }
+extern "C" int dx_version(void) { return 100; }
+
+#define DX_FAIL(code, msg) do { dx_set_error(msg); return (code); } while (0)
+
+// cube3 move table: next[d] = cur[perm[a][d]]; the 20 stickers each move displaces, as (dst, src) pairs.
+// Same permutation as the reference's 24 (new, old) index pairs per move (deepxube/domains/cube3.py:598-671,
+// action order :492); pinned against the reference by tests/golden/domains.npz::cube3_perm.
+static const uint8_t kCube3Pairs[12][20][2] = {
+    {{0,2},{1,5},{2,8},{3,1},{5,7},{6,0},{7,3},{8,6},{20,38},{23,41},{26,44},{29,47},{32,50},{35,53},{38,29},{41,32},{44,35},{47,20},{50,23},{53,26}},
+    {{0,6},{1,3},{2,0},{3,7},{5,1},{6,8},{7,5},{8,2},{20,47},{23,50},{26,53},{29,38},{32,41},{35,44},{38,20},{41,23},{44,26},{47,29},{50,32},{53,35}},
+    {{9,11},{10,14},{11,17},{12,10},{14,16},{15,9},{16,12},{17,15},{18,45},{21,48},{24,51},{27,36},{30,39},{33,42},{36,18},{39,21},{42,24},{45,27},{48,30},{51,33}},
+    {{9,15},{10,12},{11,9},{12,16},{14,10},{15,17},{16,14},{17,11},{18,36},{21,39},{24,42},{27,45},{30,48},{33,51},{36,27},{39,30},{42,33},{45,18},{48,21},{51,24}},
+    {{0,45},{1,46},{2,47},{9,44},{10,43},{11,42},{18,20},{19,23},{20,26},{21,19},{23,25},{24,18},{25,21},{26,24},{42,2},{43,1},{44,0},{45,9},{46,10},{47,11}},
+    {{0,44},{1,43},{2,42},{9,45},{10,46},{11,47},{18,24},{19,21},{20,18},{21,25},{23,19},{24,26},{25,23},{26,20},{42,11},{43,10},{44,9},{45,0},{46,1},{47,2}},
+    {{6,38},{7,37},{8,36},{15,51},{16,52},{17,53},{27,29},{28,32},{29,35},{30,28},{32,34},{33,27},{34,30},{35,33},{36,17},{37,16},{38,15},{51,6},{52,7},{53,8}},
+    {{6,51},{7,52},{8,53},{15,38},{16,37},{17,36},{27,33},{28,30},{29,27},{30,34},{32,28},{33,35},{34,32},{35,29},{36,8},{37,7},{38,6},{51,15},{52,16},{53,17}},
+    {{2,18},{5,19},{8,20},{9,33},{12,34},{15,35},{18,15},{19,12},{20,9},{33,8},{34,5},{35,2},{36,38},{37,41},{38,44},{39,37},{41,43},{42,36},{43,39},{44,42}},
+    {{2,35},{5,34},{8,33},{9,20},{12,19},{15,18},{18,2},{19,5},{20,8},{33,9},{34,12},{35,15},{36,42},{37,39},{38,36},{39,43},{41,37},{42,44},{43,41},{44,38}},
+    {{0,29},{3,28},{6,27},{11,26},{14,25},{17,24},{24,0},{25,3},{26,6},{27,11},{28,14},{29,17},{45,47},{46,50},{47,53},{48,46},{50,52},{51,45},{52,48},{53,51}},
+    {{0,24},{3,25},{6,26},{11,27},{14,28},{17,29},{24,17},{25,14},{26,11},{27,6},{28,3},{29,0},{45,51},{46,48},{47,45},{48,52},{50,46},{51,53},{52,50},{53,47}}};
+
+static int make_domain_host(int domain, int dim, DomainDev* d, std::vector<uint8_t>* table) {
+    d->kind = domain;
+    d->dim = dim;
+    d->table = nullptr;
+    table->clear();
+    if (domain == DX_DOMAIN_CUBE3) {
+        d->S = 54; d->A = 12; d->in_count = 54; d->depth = 6; d->dim = 0;
+        table->resize(12 * 54);
+        for (int a = 0; a < 12; ++a) {
+            for (int i = 0; i < 54; ++i) (*table)[a * 54 + i] = (uint8_t)i;
+            for (int p = 0; p < 20; ++p) (*table)[a * 54 + kCube3Pairs[a][p][0]] = kCube3Pairs[a][p][1];
+        }
+    } else if (domain == DX_DOMAIN_NPUZZLE) {
+        if (dim < 2 || dim > 15) DX_FAIL(DX_ERR_ARG, "npuzzle dim must be in 2..15");
+        d->S = dim * dim; d->A = 4; d->in_count = dim * dim; d->depth = dim * dim;
+        table->resize(dim * dim * 4);
+        for (int z = 0; z < dim * dim; ++z) {
+            const int i = z / dim, j = z % dim;
+            // blank moves: U -> row+1, D -> row-1, L -> col+1, R -> col-1; blocked move keeps the blank (npuzzle.py:264-308)
+            (*table)[z * 4 + 0] = (uint8_t)(i < dim - 1 ? (i + 1) * dim + j : z);
+            (*table)[z * 4 + 1] = (uint8_t)(i > 0 ? (i - 1) * dim + j : z);
+            (*table)[z * 4 + 2] = (uint8_t)(j < dim - 1 ? i * dim + j + 1 : z);
+            (*table)[z * 4 + 3] = (uint8_t)(j > 0 ? i * dim + j - 1 : z);
+        }
+    } else if (domain == DX_DOMAIN_GRID) {
+        if (dim < 1 || dim > 255) DX_FAIL(DX_ERR_ARG, "grid dim must be in 1..255");
+        d->S = 2; d->A = 4; d->in_count = 4; d->depth = dim;
+    } else {
+        DX_FAIL(DX_ERR_ARG, "unknown domain");
+    }
+    d->SP = ((d->S + 4 + 15) / 16) * 16;
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+__global__ void k_after_scan_v(Ctl* ctl, uint32_t max_nodes) {
+    if (ctl->error) return;
+    const uint32_t kept = ctl->n_kept;
+    if ((unsigned long long)ctl->node_base + kept > max_nodes) { ctl->error |= DX_DEVERR_NODES; return; }
+    ctl->node_count = ctl->node_base + kept;
+    ctl->nn_row_start = ctl->node_base;
+    ctl->nn_n = kept;
+}
+
+// Q*: after the merge the number of popped edges (= nodes to generate) is pop_off_next[I].
+__global__ void k_after_merge_q(Ctl* ctl, const uint32_t* pop_off_next, uint32_t max_nodes) {
+    if (ctl->error) return;
+    const uint32_t n = pop_off_next[ctl->n_inst];
+    if ((unsigned long long)ctl->node_base + n > max_nodes) { ctl->error |= DX_DEVERR_NODES; return; }
+    ctl->n_kept = n;
+    ctl->node_count = ctl->node_base + n;
+    ctl->nn_row_start = ctl->node_base;
+    ctl->nn_n = n;
+}
+
+__global__ void k_fill_zero_vals(const Ctl* ctl, float* node_h, float* node_q, int A) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        node_h[start + r] = 0.f;
+        if (node_q)
+            for (int a = 0; a < A; ++a) node_q[(size_t)(start + r) * A + a] = 0.f;
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
+}
+
+// HOST mode: values uploaded for rows [nn_row_start, +nn_n): V -> node_h ; Q -> node_q and node_h = min_a q
+__global__ void k_set_host_vals(const Ctl* ctl, const float* vals, float* node_h, float* node_q, int A, int is_q) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (!is_q) {
+            node_h[start + r] = vals[r];
+        } else {
+            float m = __int_as_float(0x7f800000);
+            for (int a = 0; a < A; ++a) {
+                const float v = vals[(size_t)r * A + a];
+                node_q[(size_t)(start + r) * A + a] = v;
+                m = fminf(m, v);
+            }
+            node_h[start + r] = m;
+        }
+    }
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
+}
+
+__global__ void k_set_job(Ctl* ctl, uint32_t start, uint32_t n) { ctl->nn_row_start = start; ctl->nn_n = n; }
+
+// device-side parent walk (base/pathfinding.py:93-120): actions written goal -> root, reversed on the host
+__global__ void k_path_walk(const uint32_t* node_parent, const uint8_t* node_action, uint32_t goal, int32_t* actions,
+                            uint32_t* ids, int cap, int* len_out) {
+    int len = 0;
+    uint32_t id = goal;
+    while (node_parent[id] != DX_NIL) {
+        if (len < cap) { actions[len] = node_action[id]; ids[len] = id; }
+        ++len;
+        id = node_parent[id];
+    }
+    if (len < cap + 1) ids[len <= cap ? len : cap] = id;
+    *len_out = len;
+}
+
+__global__ void k_gather_rows(const uint8_t* node_state, const uint32_t* ids, int n, int SP, uint8_t* out) {
+    const int chunks = SP / 16;
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n * chunks; t += gridDim.x * blockDim.x) {
+        const int r = t / chunks, c = t % chunks;
+        reinterpret_cast<uint4*>(out + (size_t)r * SP)[c] = reinterpret_cast<const uint4*>(node_state + (size_t)ids[r] * SP)[c];
+    }
+}
+
+__global__ void k_gather_f32(const float* src, const uint32_t* ids, int n, float* out) {
+    for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) out[t] = src[ids[t]];
+}
+
+// ---------------------------------------------------------------------------------------------
+enum { ST_EXPAND = 0, ST_CLOSED, ST_SCATTER, ST_HEUR, ST_SORT, ST_MERGE, ST_BOOK, ST_COUNT };
+
+struct dx_engine {
+    dx_config cfg;
+    DomainDev dom;
+    std::vector<uint8_t> table_h;
+    cudaStream_t stream = nullptr;
+    bool is_q = false;
+    int A = 0, SP = 0, S = 0;
+    uint32_t max_nodes = 0, max_open = 0, max_pop = 0, max_children = 0, max_sort = 0;
+    int max_inst = 0;
+    int n_inst = 0;
+    int parity = 0;              // which popped / OPEN buffers are "current"
+    bool pending = false;        // HOST mode: between step_begin and step_end
+    bool weights_loaded = false;
+    long long launches = 0;
+
+    // device memory
+    uint8_t* d_table = nullptr;
+    Ctl* d_ctl = nullptr;
+    Ctl* h_ctl = nullptr;        // pinned
+    uint8_t* node_state = nullptr; float* node_g = nullptr; float* node_h = nullptr; uint32_t* node_parent = nullptr;
+    uint8_t* node_action = nullptr; float* node_q = nullptr;
+    ClosedDev closed{};
+    uint8_t* child_state = nullptr; float* child_g = nullptr; uint32_t* child_slot = nullptr; uint32_t* child_next = nullptr;
+    uint8_t* child_flags = nullptr; uint32_t* child_prefix = nullptr; uint32_t* new_inst = nullptr;
+    uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
+    uint32_t* edge_tmp = nullptr; uint8_t* pop_solved = nullptr;
+    unsigned long long* open_key[2] = {nullptr, nullptr}; uint32_t* open_val[2] = {nullptr, nullptr};
+    uint32_t* open_off[2] = {nullptr, nullptr};
+    SortBufs sort{};
+    ScanTemp scan{};
+    InstArrays ia{};
+    NetDev net{};
+    MlpBufs mlp{};
+    uint8_t* d_stage = nullptr; size_t stage_bytes = 0;     // staging for host<->device transfers
+    float* d_vals = nullptr;                                // HOST-mode value upload / heur_eval output
+    std::vector<void*> allocs;
+
+    // profiling
+    bool profiling = false;
+    std::vector<cudaEvent_t> ev;       // pairs
+    std::vector<int> ev_stage;
+    float stage_ms[ST_COUNT] = {0};
+
+    template <typename T> int alloc(T** p, size_t count) {
+        void* q = nullptr;
+        cudaError_t e = cudaMalloc(&q, std::max<size_t>(count, 1) * sizeof(T));
+        if (e != cudaSuccess) {
+            dx_set_error(std::string("cudaMalloc of ") + std::to_string(count * sizeof(T)) + " bytes failed: " + cudaGetErrorString(e));
+            return DX_ERR_CUDA;
+        }
+        allocs.push_back(q);
+        *p = (T*)q;
+        return DX_OK;
+    }
+};
+
+#define DX_TRY(x) do { int _r = (x); if (_r < 0) return _r; } while (0)
+
+static void stage_begin(dx_engine* e, int st) {
+    if (!e->profiling) return;
+    cudaEvent_t a;
+    cudaEventCreate(&a);
+    cudaEventRecord(a, e->stream);
+    e->ev.push_back(a);
+    e->ev_stage.push_back(st);
+}
+static void stage_end(dx_engine* e) {
+    if (!e->profiling) return;
+    cudaEvent_t b;
+    cudaEventCreate(&b);
+    cudaEventRecord(b, e->stream);
+    e->ev.push_back(b);
+}
+static void stage_collect(dx_engine* e) {
+    if (e->ev.empty()) return;
+    cudaStreamSynchronize(e->stream);
+    for (size_t i = 0; i + 1 < e->ev.size(); i += 2) {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
+        e->stage_ms[e->ev_stage[i / 2]] += ms;
+        cudaEventDestroy(e->ev[i]);
+        cudaEventDestroy(e->ev[i + 1]);
+    }
+    e->ev.clear();
+    e->ev_stage.clear();
+}
+
+static int sync_ctl(dx_engine* e) {
+    DX_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->h_ctl->error) {
+        std::string m = "device capacity exceeded:";
+        if (e->h_ctl->error & DX_DEVERR_NODES) m += " max_nodes";
+        if (e->h_ctl->error & DX_DEVERR_OPEN) m += " max_open";
+        if (e->h_ctl->error & DX_DEVERR_POP) m += " max_pop_total";
+        DX_FAIL(DX_ERR_CAPACITY, m);
+    }
+    return DX_OK;
+}
+
+static int ensure_stage(dx_engine* e, size_t bytes) {
+    if (bytes <= e->stage_bytes) return DX_OK;
+    void* q = nullptr;
+    DX_CUDA(cudaMalloc(&q, bytes));
+    e->allocs.push_back(q);
+    e->d_stage = (uint8_t*)q;
+    e->stage_bytes = bytes;
+    return DX_OK;
+}
+
+static int reset_state(dx_engine* e) {
+    DX_CUDA(cudaMemsetAsync(e->d_ctl, 0, sizeof(Ctl), e->stream));
+    e->launches += dx_launch_closed_init(e->stream, e->closed);
+    DX_CUDA(cudaMemsetAsync(e->sort.ghist, 0, DX_NUM_DIGITS * 256 * sizeof(uint32_t), e->stream));
+    for (int p = 0; p < 2; ++p) {
+        DX_CUDA(cudaMemsetAsync(e->pop_off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream));
+        DX_CUDA(cudaMemsetAsync(e->open_off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream));
+    }
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    e->n_inst = 0;
+    e->parity = 0;
+    e->pending = false;
+    memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    return DX_OK;
+}
+
+extern "C" int dx_domain_info(int32_t domain, int32_t dim, int32_t* state_bytes, int32_t* num_actions, int32_t* in_count,
+                              int32_t* one_hot_depth) {
+    DomainDev d;
+    std::vector<uint8_t> t;
+    DX_TRY(make_domain_host(domain, dim, &d, &t));
+    if (state_bytes) *state_bytes = d.S;
+    if (num_actions) *num_actions = d.A;
+    if (in_count) *in_count = d.in_count;
+    if (one_hot_depth) *one_hot_depth = d.depth;
+    return DX_OK;
+}
+
+extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
+    if (!cfg || !out) DX_FAIL(DX_ERR_ARG, "null argument");
+    if (cfg->max_instances < 1 || cfg->max_pop_total < 1 || cfg->max_nodes < 2) DX_FAIL(DX_ERR_ARG, "capacities must be positive");
+    if (cfg->max_nodes >= 0x7FFFFFF0ll) DX_FAIL(DX_ERR_ARG, "max_nodes must be < 2^31");
+    if (cfg->algo != DX_ALGO_GRAPH_V && cfg->algo != DX_ALGO_GRAPH_Q) DX_FAIL(DX_ERR_ARG, "unknown algo");
+    if (cfg->heur_mode < DX_HEUR_ZERO || cfg->heur_mode > DX_HEUR_NET_BF16) DX_FAIL(DX_ERR_ARG, "unknown heur_mode");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+        DX_FAIL(DX_ERR_CUDA, "no CUDA device: libdxb200 has no CPU fallback");
+    if (cfg->device < 0 || cfg->device >= ndev) DX_FAIL(DX_ERR_ARG, "bad device ordinal");
+    DX_CUDA(cudaSetDevice(cfg->device));
+    dx_engine* e = new dx_engine();
+    e->cfg = *cfg;
+    int r = make_domain_host(cfg->domain, cfg->domain_dim, &e->dom, &e->table_h);
+    if (r < 0) { delete e; return r; }
+    e->is_q = cfg->algo == DX_ALGO_GRAPH_Q;
+    e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
+    e->max_inst = cfg->max_instances;
+    e->max_nodes = (uint32_t)cfg->max_nodes;
+    e->max_pop = (uint32_t)std::max(cfg->max_pop_total, cfg->max_instances);
+    const unsigned long long mc = (unsigned long long)e->max_pop * e->A;
+    if (mc >= 0x7FFFFFF0ull) { delete e; DX_FAIL(DX_ERR_ARG, "max_pop_total * actions must be < 2^31"); }
+    e->max_children = e->is_q ? e->max_pop : (uint32_t)mc;   // items seen by the CLOSED filter
+    e->max_sort = (uint32_t)mc;                               // entries pushed per iteration
+    unsigned long long mo = cfg->max_open > 0 ? (unsigned long long)cfg->max_open
+                                              : (unsigned long long)e->max_nodes * (e->is_q ? e->A : 1);
+    if (mo >= 0xFFFFFFF0ull) mo = 0xFFFFFFF0ull;
+    e->max_open = (uint32_t)mo;
+    if (e->is_q && (unsigned long long)e->max_nodes * e->A >= 0xFFFFFFFFull) { delete e; DX_FAIL(DX_ERR_ARG, "max_nodes * actions must be < 2^32 for graph_q"); }
+
+#define A_(ptr, count) do { int _r = e->alloc(&(ptr), (count)); if (_r < 0) { dx_engine_destroy(e); return _r; } } while (0)
+    if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; DX_FAIL(DX_ERR_CUDA, "stream create failed"); }
+    if (cudaMallocHost((void**)&e->h_ctl, sizeof(Ctl)) != cudaSuccess) { delete e; DX_FAIL(DX_ERR_CUDA, "pinned alloc failed"); }
+    A_(e->d_ctl, 1);
+    A_(e->d_table, std::max<size_t>(e->table_h.size(), 16));
+    if (!e->table_h.empty()) cudaMemcpy(e->d_table, e->table_h.data(), e->table_h.size(), cudaMemcpyHostToDevice);
+    e->dom.table = e->d_table;
+    const size_t N = e->max_nodes, C = e->max_children, P = e->max_pop, I = e->max_inst;
+    A_(e->node_state, N * e->SP); A_(e->node_g, N); A_(e->node_h, N); A_(e->node_parent, N); A_(e->node_action, N);
+    if (e->is_q) A_(e->node_q, N * e->A);
+    size_t hcap = 1024;
+    while (hcap < 2 * N) hcap <<= 1;
+    e->closed.mask = (uint32_t)(hcap - 1);
+    A_(e->closed.slot_key, hcap); A_(e->closed.slot_g, hcap); A_(e->closed.slot_head, hcap);
+    if (!e->is_q) { A_(e->child_state, C * e->SP); A_(e->child_g, C); }
+    A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
+    for (int p = 0; p < 2; ++p) {
+        A_(e->popped[p], P); A_(e->popped_inst[p], P); A_(e->pop_off[p], I + 1);
+        A_(e->open_key[p], (size_t)e->max_open); A_(e->open_val[p], (size_t)e->max_open); A_(e->open_off[p], I + 1);
+        A_(e->sort.key[p], (size_t)e->max_sort); A_(e->sort.inst[p], (size_t)e->max_sort); A_(e->sort.val[p], (size_t)e->max_sort);
+    }
+    A_(e->edge_tmp, P); A_(e->pop_solved, P);
+    e->sort.max_tiles = dx_div_up(e->max_sort, DX_SORT_TILE);
+    A_(e->sort.hist, (size_t)256 * e->sort.max_tiles + 4096); A_(e->sort.ghist, DX_NUM_DIGITS * 256);
+    A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
+    A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
+    A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);
+    A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP);
+    A_(e->d_vals, std::max<size_t>((size_t)e->max_sort, P * e->A) + I * e->A);
+#undef A_
+    r = reset_state(e);
+    if (r < 0) { dx_engine_destroy(e); return r; }
+    *out = e;
+    return DX_OK;
+}
+
+extern "C" int dx_engine_destroy(dx_engine* e) {
+    if (!e) return DX_OK;
+    cudaSetDevice(e->cfg.device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    for (void* p : e->allocs) cudaFree(p);
+    if (e->h_ctl) cudaFreeHost(e->h_ctl);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+    return DX_OK;
+}
+
+extern "C" int dx_engine_reset(dx_engine* e) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    return reset_state(e);
+}
+
+// ---------------------------------------------------------------------------------------------
+static int need_net(dx_engine* e) {
+    if ((e->cfg.heur_mode == DX_HEUR_NET_FP32 || e->cfg.heur_mode == DX_HEUR_NET_BF16) && !e->weights_loaded)
+        DX_FAIL(DX_ERR_STATE, "heur_mode is NET_* but dx_load_weights has not been called");
+    return DX_OK;
+}
+
+int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats);   // net_load.cu
+
+// heuristic for the current job (ctl->nn_row_start / nn_n) over node-store rows
+static int launch_heur_nodes(dx_engine* e, long long max_rows) {
+    const int mode = e->cfg.heur_mode;
+    if (mode == DX_HEUR_ZERO) {
+        k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->node_h, e->node_q, e->A);
+        e->launches += 1;
+    } else if (mode == DX_HEUR_NET_FP32) {
+        e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, e->node_h,
+                                         e->node_q, 1, max_rows);
+    } else if (mode == DX_HEUR_NET_BF16) {
+        e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, e->node_h,
+                                          e->node_q, 1, max_rows);
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
+                                const int32_t* batch_sizes, const double* weights, const float* root_vals) {
+    if (!e || (n > 0 && (!states || !goals))) DX_FAIL(DX_ERR_ARG, "null argument");
+    if (n <= 0) return DX_OK;
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "dx_add_instances between dx_step_begin and dx_step_end");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(need_net(e));
+    if (e->n_inst + n > e->max_inst) DX_FAIL(DX_ERR_CAPACITY, "max_instances exceeded");
+    if (e->cfg.heur_mode == DX_HEUR_HOST && e->is_q && !root_vals) DX_FAIL(DX_ERR_ARG, "graph_q in HOST mode needs root_vals");
+    DX_TRY(sync_ctl(e));
+    const Ctl c = *e->h_ctl;
+    if ((unsigned long long)c.node_count + n > e->max_nodes) DX_FAIL(DX_ERR_CAPACITY, "max_nodes exceeded");
+    if ((unsigned long long)c.n_pop + n > e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "max_pop_total exceeded");
+    long long bsum = 0;
+    for (int i = 0; i < n; ++i) {
+        const int b = batch_sizes ? batch_sizes[i] : 1;
+        if (b < 1) DX_FAIL(DX_ERR_ARG, "batch size must be >= 1");
+        bsum += b;
+    }
+    {   // total batch of live instances must fit max_pop_total
+        std::vector<int32_t> hb(e->n_inst);
+        if (e->n_inst) DX_CUDA(cudaMemcpy(hb.data(), e->ia.batch, e->n_inst * sizeof(int32_t), cudaMemcpyDeviceToHost));
+        for (int b : hb) bsum += b;
+        if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of batch sizes exceeds max_pop_total");
+    }
+    const int SP = e->SP, S = e->S, I0 = e->n_inst, p = e->parity;
+    std::vector<uint8_t> rows((size_t)n * SP, 0), grow((size_t)n * SP, 0);
+    std::vector<int32_t> hb(n);
+    std::vector<double> hw(n), hlb(n, 0.0);
+    std::vector<unsigned long long> hub(n, DX_EMPTY64), hgen(n, 0ull);
+    std::vector<uint32_t> hgoal(n, DX_NIL), hz(n, 0u), hpar(n, DX_NIL), hpop(n), hpinst(n), hoff(n + 1), hooff(n + 1);
+    std::vector<uint8_t> hact(n, 1), hacn(n, 0);
+    std::vector<float> hg(n, 0.f);
+    for (int i = 0; i < n; ++i) {
+        memcpy(&rows[(size_t)i * SP], states + (size_t)i * S, S);
+        const uint32_t inst = I0 + i;
+        memcpy(&rows[(size_t)i * SP + SP - 4], &inst, 4);
+        memcpy(&grow[(size_t)i * SP], goals + (size_t)i * S, S);
+        hb[i] = batch_sizes ? batch_sizes[i] : 1;
+        hw[i] = weights ? weights[i] : 1.0;
+        hpop[i] = c.node_count + i;
+        hpinst[i] = inst;
+        hoff[i] = c.n_pop + i;
+        hooff[i] = c.open_total;
+    }
+    hoff[n] = c.n_pop + n;
+    hooff[n] = c.open_total;
+    cudaStream_t s = e->stream;
+    const uint32_t first = c.node_count;
+    DX_CUDA(cudaMemcpyAsync(e->node_state + (size_t)first * SP, rows.data(), rows.size(), cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.goals + (size_t)I0 * SP, grow.data(), grow.size(), cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->node_g + first, hg.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->node_h + first, hg.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->node_parent + first, hpar.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->node_action + first, hacn.data(), n, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.batch + I0, hb.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.weight + I0, hw.data(), n * 8, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.lb + I0, hlb.data(), n * 8, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.ub_key + I0, hub.data(), n * 8, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.goal_node + I0, hgoal.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.itr + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.gen + I0, hgen.data(), n * 8, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.active + I0, hact.data(), n, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.pop_seq_base + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.n_open + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->popped[p] + c.n_pop, hpop.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->popped_inst[p] + c.n_pop, hpinst.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->pop_off[p] + I0, hoff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->open_off[p] + I0, hooff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    // control block
+    Ctl nc = c;
+    nc.n_inst = I0 + n;
+    nc.n_pop = c.n_pop + n;
+    nc.n_children = nc.n_pop * (e->is_q ? 1 : e->A);
+    nc.node_count = c.node_count + n;
+    nc.node_base = nc.node_count;
+    nc.n_unfinished = c.n_unfinished + n;
+    if (nc.epoch == 0) nc.epoch = 1;
+    nc.nn_row_start = first;
+    nc.nn_n = n;
+    *e->h_ctl = nc;
+    DX_CUDA(cudaMemcpyAsync(e->d_ctl, e->h_ctl, sizeof(Ctl), cudaMemcpyHostToDevice, s));
+    if (!e->is_q) e->launches += dx_launch_closed_seed(s, e->dom, e->closed, e->node_state, first, n);   // graph_search.py:119-121
+    // root values (graph_search.py:103-107): one heuristic call over the new roots
+    if (e->cfg.heur_mode == DX_HEUR_HOST) {
+        if (root_vals) {
+            const size_t cnt = (size_t)n * (e->is_q ? e->A : 1);
+            DX_CUDA(cudaMemcpyAsync(e->d_vals, root_vals, cnt * 4, cudaMemcpyHostToDevice, s));
+            k_set_host_vals<<<dx_div_up(n, 128), 128, 0, s>>>(e->d_ctl, e->d_vals, e->node_h, e->node_q, e->A, e->is_q ? 1 : 0);
+            e->launches += 1;
+        }
+    } else {
+        DX_TRY(launch_heur_nodes(e, n));
+    }
+    DX_CUDA(cudaStreamSynchronize(s));
+    e->n_inst += n;
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// A* phase A: everything up to (and including) storing the kept children.
+static int step_v_a(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity;
+    stage_begin(e, ST_EXPAND);
+    e->launches += dx_launch_expand(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
+                                    e->pop_off[p], e->child_state, e->child_g, e->pop_solved, e->max_pop);
+    e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
+                                          e->pop_solved, e->max_pop);
+    stage_end(e);
+    stage_begin(e, ST_CLOSED);
+    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
+                                           e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                           e->max_children, e->A);
+    stage_end(e);
+    stage_begin(e, ST_SCATTER);
+    e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
+                                        e->max_children, e->scan);
+    k_after_scan_v<<<1, 1, 0, s>>>(e->d_ctl, e->max_nodes);
+    e->launches += 1;
+    e->launches += dx_launch_scatter_kept(s, e->dom, e->closed, e->d_ctl, e->child_state, e->child_g, e->child_slot,
+                                          e->child_flags, e->child_prefix, e->popped[p], e->popped_inst[p], e->node_state,
+                                          e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children);
+    stage_end(e);
+    return DX_OK;
+}
+
+static int step_v_b(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity, q = p ^ 1;
+    stage_begin(e, ST_SORT);
+    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open);
+    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    stage_end(e);
+    stage_begin(e, ST_MERGE);
+    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles);
+    stage_end(e);
+    stage_begin(e, ST_BOOK);
+    e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, 0);
+    stage_end(e);
+    e->parity = q;
+    return DX_OK;
+}
+
+// Q* phase A: up to (and including) generating the children of the popped edges.
+static int step_q_a(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity, q = p ^ 1;
+    stage_begin(e, ST_EXPAND);
+    e->launches += dx_launch_check_solved(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
+                                          e->pop_off[p], e->pop_solved, e->max_pop);
+    e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
+                                          e->pop_solved, e->max_pop);
+    stage_end(e);
+    stage_begin(e, ST_CLOSED);
+    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, nullptr, nullptr,
+                                           e->popped[p], e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                           e->max_children, 1);
+    stage_end(e);
+    stage_begin(e, ST_SCATTER);
+    e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
+                                        e->max_children, e->scan);
+    e->launches += dx_launch_closed_commit(s, e->closed, e->d_ctl, e->node_g, e->popped[p], e->child_slot, e->child_flags,
+                                           e->max_children);
+    stage_end(e);
+    stage_begin(e, ST_SORT);
+    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                  e->open_off[q], 1, e->A, e->max_pop, e->max_open);
+    e->launches += dx_launch_make_keys_q(s, e->d_ctl, e->ia, e->node_g, e->node_q, e->popped[p], e->popped_inst[p],
+                                         e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    stage_end(e);
+    stage_begin(e, ST_MERGE);
+    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                   e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles);
+    k_after_merge_q<<<1, 1, 0, s>>>(e->d_ctl, e->pop_off[q], e->max_nodes);
+    e->launches += 1;
+    e->launches += dx_launch_expand_edges(s, e->dom, e->d_ctl, e->edge_tmp, e->popped[q], e->node_state, e->node_g,
+                                          e->node_parent, e->node_action, e->max_pop);
+    stage_end(e);
+    return DX_OK;
+}
+
+static int step_q_b(dx_engine* e) {
+    const int p = e->parity, q = p ^ 1;
+    stage_begin(e, ST_BOOK);
+    e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, 1);
+    stage_end(e);
+    e->parity = q;
+    return DX_OK;
+}
+
+static int full_step(dx_engine* e) {
+    if (e->is_q) {
+        DX_TRY(step_q_a(e));
+        stage_begin(e, ST_HEUR);
+        DX_TRY(launch_heur_nodes(e, e->max_pop));
+        stage_end(e);
+        DX_TRY(step_q_b(e));
+    } else {
+        DX_TRY(step_v_a(e));
+        stage_begin(e, ST_HEUR);
+        DX_TRY(launch_heur_nodes(e, e->max_children));
+        stage_end(e);
+        DX_TRY(step_v_b(e));
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    if (e->cfg.heur_mode == DX_HEUR_HOST) DX_FAIL(DX_ERR_STATE, "dx_run needs a device heuristic (use dx_step_begin/end in HOST mode)");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(need_net(e));
+    int done = 0;
+    DX_TRY(sync_ctl(e));
+    while (done < max_iters && e->h_ctl->n_unfinished > 0) {
+        DX_TRY(full_step(e));
+        ++done;
+        DX_TRY(sync_ctl(e));
+    }
+    stage_collect(e);
+    DX_CUDA(cudaGetLastError());
+    if (iters_done) *iters_done = done;
+    return DX_OK;
+}
+
+extern "C" int dx_step_begin(dx_engine* e, int64_t* n_pending) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    if (e->cfg.heur_mode != DX_HEUR_HOST) DX_FAIL(DX_ERR_STATE, "dx_step_begin is for HOST heuristic mode");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step already pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    if (e->is_q) DX_TRY(step_q_a(e)); else DX_TRY(step_v_a(e));
+    DX_TRY(sync_ctl(e));
+    e->pending = true;
+    if (n_pending) *n_pending = e->h_ctl->nn_n;
+    return DX_OK;
+}
+
+extern "C" int dx_get_pending(dx_engine* e, uint8_t* states, uint8_t* goals, int64_t cap) {
+    if (!e || !e->pending) DX_FAIL(DX_ERR_STATE, "no step pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    const uint32_t n = e->h_ctl->nn_n, start = e->h_ctl->nn_row_start;
+    if ((int64_t)n > cap) DX_FAIL(DX_ERR_ARG, "buffer too small");
+    if (n == 0) return DX_OK;
+    const int SP = e->SP, S = e->S;
+    std::vector<uint8_t> rows((size_t)n * SP), grows((size_t)e->n_inst * SP);
+    DX_CUDA(cudaMemcpyAsync(rows.data(), e->node_state + (size_t)start * SP, rows.size(), cudaMemcpyDeviceToHost, e->stream));
+    DX_CUDA(cudaMemcpyAsync(grows.data(), e->ia.goals, grows.size(), cudaMemcpyDeviceToHost, e->stream));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    for (uint32_t r = 0; r < n; ++r) {
+        if (states) memcpy(states + (size_t)r * S, &rows[(size_t)r * SP], S);
+        if (goals) {
+            uint32_t inst;
+            memcpy(&inst, &rows[(size_t)r * SP + SP - 4], 4);
+            memcpy(goals + (size_t)r * S, &grows[(size_t)inst * SP], S);
+        }
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_step_end(dx_engine* e, const float* vals, int64_t n) {
+    if (!e || !e->pending) DX_FAIL(DX_ERR_STATE, "no step pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    const uint32_t want = e->h_ctl->nn_n;
+    if ((int64_t)want != n) DX_FAIL(DX_ERR_ARG, "dx_step_end: value count does not match pending states");
+    if (n > 0) {
+        if (!vals) DX_FAIL(DX_ERR_ARG, "null values");
+        const size_t cnt = (size_t)n * (e->is_q ? e->A : 1);
+        DX_CUDA(cudaMemcpyAsync(e->d_vals, vals, cnt * 4, cudaMemcpyHostToDevice, e->stream));
+        k_set_host_vals<<<std::min(dx_div_up(n, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->d_vals, e->node_h, e->node_q,
+                                                                                    e->A, e->is_q ? 1 : 0);
+        e->launches += 1;
+    }
+    if (e->is_q) DX_TRY(step_q_b(e)); else DX_TRY(step_v_b(e));
+    e->pending = false;
+    DX_TRY(sync_ctl(e));
+    stage_collect(e);
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int dx_num_instances(dx_engine* e) { return e ? e->n_inst : 0; }
+
+extern "C" int dx_all_finished(dx_engine* e, int32_t* out) {
+    if (!e || !out) DX_FAIL(DX_ERR_ARG, "null argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    *out = e->h_ctl->n_unfinished == 0 ? 1 : 0;
+    return DX_OK;
+}
+
+extern "C" int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap) {
+    if (!e || !out) DX_FAIL(DX_ERR_ARG, "null argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    const int n = std::min(cap, e->n_inst);
+    if (n <= 0) return DX_OK;
+    std::vector<double> lb(n);
+    std::vector<unsigned long long> ub(n), gen(n);
+    std::vector<uint32_t> goal(n), itr(n), nopen(n), off(e->n_inst + 1);
+    std::vector<uint8_t> act(n);
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    DX_CUDA(cudaMemcpy(lb.data(), e->ia.lb, n * 8, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(ub.data(), e->ia.ub_key, n * 8, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(gen.data(), e->ia.gen, n * 8, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(goal.data(), e->ia.goal_node, n * 4, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(itr.data(), e->ia.itr, n * 4, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(nopen.data(), e->ia.n_open, n * 4, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(act.data(), e->ia.active, n, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(off.data(), e->pop_off[e->parity], (e->n_inst + 1) * 4, cudaMemcpyDeviceToHost));
+    for (int i = 0; i < n; ++i) {
+        out[i].lb = lb[i];
+        if (ub[i] == DX_EMPTY64) out[i].ub = INFINITY;
+        else { uint32_t b = (uint32_t)(ub[i] >> 32); float f; memcpy(&f, &b, 4); out[i].ub = (double)f; }
+        out[i].num_nodes_generated = (int64_t)gen[i];
+        out[i].open_size = nopen[i];
+        out[i].goal_node = goal[i] == DX_NIL ? -1 : (int64_t)goal[i];
+        out[i].itr = (int32_t)itr[i];
+        out[i].finished = act[i] ? 0 : 1;
+        out[i].num_curr = (int32_t)(off[i + 1] - off[i]);
+        out[i].reserved = 0;
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_get_counters(dx_engine* e, dx_counters* out) {
+    if (!e || !out) DX_FAIL(DX_ERR_ARG, "null argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    memset(out, 0, sizeof(*out));
+    out->nodes_stored = e->h_ctl->node_count;
+    out->heur_evals = (int64_t)e->h_ctl->heur_evals;
+    out->children_generated = (int64_t)e->h_ctl->gen_total;
+    out->iterations = e->h_ctl->itr;
+    out->kernel_launches = e->launches;
+    return DX_OK;
+}
+
+extern "C" int dx_get_path(dx_engine* e, int32_t inst, int32_t* actions, uint8_t* states_on_path, int32_t cap, int32_t* len) {
+    if (!e || !len || inst < 0 || inst >= e->n_inst) DX_FAIL(DX_ERR_ARG, "bad argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    uint32_t goal;
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    DX_CUDA(cudaMemcpy(&goal, e->ia.goal_node + inst, 4, cudaMemcpyDeviceToHost));
+    if (goal == DX_NIL) { *len = -1; return DX_OK; }
+    const size_t need = (size_t)cap * 4 + (size_t)(cap + 1) * 4 + 16 + (size_t)(cap + 1) * e->SP;
+    DX_TRY(ensure_stage(e, need));
+    int32_t* d_act = (int32_t*)e->d_stage;
+    uint32_t* d_ids = (uint32_t*)(e->d_stage + (size_t)cap * 4);
+    int* d_len = (int*)(e->d_stage + (size_t)cap * 4 + (size_t)(cap + 1) * 4);
+    uint8_t* d_rows = e->d_stage + (((size_t)cap * 8 + 4 + 16 + 15) / 16) * 16;
+    k_path_walk<<<1, 1, 0, e->stream>>>(e->node_parent, e->node_action, goal, d_act, d_ids, cap, d_len);
+    e->launches += 1;
+    int hlen = 0;
+    DX_CUDA(cudaMemcpyAsync(&hlen, d_len, 4, cudaMemcpyDeviceToHost, e->stream));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    *len = hlen;
+    if (hlen > cap) DX_FAIL(DX_ERR_ARG, "path longer than cap");
+    std::vector<int32_t> a(std::max(hlen, 1));
+    if (hlen && actions) {
+        DX_CUDA(cudaMemcpy(a.data(), d_act, (size_t)hlen * 4, cudaMemcpyDeviceToHost));
+        for (int i = 0; i < hlen; ++i) actions[i] = a[hlen - 1 - i];
+    }
+    if (states_on_path) {
+        k_gather_rows<<<dx_div_up((long long)(hlen + 1) * (e->SP / 16), 128), 128, 0, e->stream>>>(e->node_state, d_ids, hlen + 1, e->SP, d_rows);
+        e->launches += 1;
+        std::vector<uint8_t> rows((size_t)(hlen + 1) * e->SP);
+        DX_CUDA(cudaMemcpyAsync(rows.data(), d_rows, rows.size(), cudaMemcpyDeviceToHost, e->stream));
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+        for (int i = 0; i <= hlen; ++i) memcpy(states_on_path + (size_t)i * e->S, &rows[(size_t)(hlen - i) * e->SP], e->S);
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_get_curr_nodes(dx_engine* e, int32_t inst, uint8_t* states, float* g, float* h, int32_t cap, int32_t* n) {
+    if (!e || !n || inst < 0 || inst >= e->n_inst) DX_FAIL(DX_ERR_ARG, "bad argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    uint32_t off[2];
+    DX_CUDA(cudaMemcpy(off, e->pop_off[e->parity] + inst, 8, cudaMemcpyDeviceToHost));
+    const int cnt = (int)(off[1] - off[0]);
+    *n = cnt;
+    if (cnt > cap) DX_FAIL(DX_ERR_ARG, "buffer too small");
+    if (cnt == 0) return DX_OK;
+    const size_t need = (size_t)cnt * e->SP + (size_t)cnt * 8 + 64;
+    DX_TRY(ensure_stage(e, need));
+    uint8_t* d_rows = e->d_stage;
+    float* d_g = (float*)(e->d_stage + (((size_t)cnt * e->SP + 15) / 16) * 16);
+    float* d_h = d_g + cnt;
+    const uint32_t* ids = e->popped[e->parity] + off[0];
+    k_gather_rows<<<dx_div_up((long long)cnt * (e->SP / 16), 128), 128, 0, e->stream>>>(e->node_state, ids, cnt, e->SP, d_rows);
+    k_gather_f32<<<dx_div_up(cnt, 128), 128, 0, e->stream>>>(e->node_g, ids, cnt, d_g);
+    k_gather_f32<<<dx_div_up(cnt, 128), 128, 0, e->stream>>>(e->node_h, ids, cnt, d_h);
+    e->launches += 3;
+    std::vector<uint8_t> rows((size_t)cnt * e->SP);
+    DX_CUDA(cudaMemcpyAsync(rows.data(), d_rows, rows.size(), cudaMemcpyDeviceToHost, e->stream));
+    if (g) DX_CUDA(cudaMemcpyAsync(g, d_g, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->stream));
+    if (h) DX_CUDA(cudaMemcpyAsync(h, d_h, (size_t)cnt * 4, cudaMemcpyDeviceToHost, e->stream));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    if (states)
+        for (int i = 0; i < cnt; ++i) memcpy(states + (size_t)i * e->S, &rows[(size_t)i * e->SP], e->S);
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone domain API on host buffers.
+static int domain_call(int device, int domain, int dim, const uint8_t* states, const uint8_t* goals, const int32_t* actions,
+                       long long n, uint8_t* out, int what) {   // what: 0 expand, 1 next_state, 2 is_solved
+    if (n < 0 || (n > 0 && (!states || !out))) DX_FAIL(DX_ERR_ARG, "bad argument");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) DX_FAIL(DX_ERR_CUDA, "no CUDA device: libdxb200 has no CPU fallback");
+    DX_CUDA(cudaSetDevice(device));
+    DomainDev d;
+    std::vector<uint8_t> table;
+    DX_TRY(make_domain_host(domain, dim, &d, &table));
+    if (n == 0) return DX_OK;
+    const int SP = d.SP, S = d.S;
+    const long long n_out = what == 0 ? n * d.A : n;
+    std::vector<uint8_t> rows((size_t)n * SP, 0);
+    for (long long i = 0; i < n; ++i) memcpy(&rows[(size_t)i * SP], states + (size_t)i * S, S);
+    uint8_t *d_rows = nullptr, *d_out = nullptr, *d_table = nullptr, *d_goals = nullptr;
+    int32_t* d_act = nullptr;
+    int rc = DX_OK;
+    auto cleanup = [&]() { cudaFree(d_rows); cudaFree(d_out); cudaFree(d_table); cudaFree(d_goals); cudaFree(d_act); };
+#define C_(x) do { if ((x) != cudaSuccess) { dx_set_error(std::string(#x) + ": " + cudaGetErrorString(cudaGetLastError())); cleanup(); return DX_ERR_CUDA; } } while (0)
+    C_(cudaMalloc(&d_rows, rows.size()));
+    C_(cudaMalloc(&d_table, std::max<size_t>(table.size(), 16)));
+    C_(cudaMemcpy(d_rows, rows.data(), rows.size(), cudaMemcpyHostToDevice));
+    if (!table.empty()) C_(cudaMemcpy(d_table, table.data(), table.size(), cudaMemcpyHostToDevice));
+    d.table = d_table;
+    if (what == 2) {
+        std::vector<uint8_t> grows((size_t)n * SP, 0);
+        for (long long i = 0; i < n; ++i) memcpy(&grows[(size_t)i * SP], goals + (size_t)i * S, S);
+        C_(cudaMalloc(&d_goals, grows.size()));
+        C_(cudaMemcpy(d_goals, grows.data(), grows.size(), cudaMemcpyHostToDevice));
+        C_(cudaMalloc(&d_out, (size_t)n));
+        dx_launch_standalone_solved(0, d, d_rows, d_goals, n, d_out);
+        C_(cudaMemcpy(out, d_out, (size_t)n, cudaMemcpyDeviceToHost));
+    } else {
+        if (what == 1) {
+            if (!actions) { cleanup(); DX_FAIL(DX_ERR_ARG, "null actions"); }
+            for (long long i = 0; i < n; ++i)
+                if (actions[i] < 0 || actions[i] >= d.A) { cleanup(); DX_FAIL(DX_ERR_ARG, "action out of range"); }
+            C_(cudaMalloc(&d_act, (size_t)n * 4));
+            C_(cudaMemcpy(d_act, actions, (size_t)n * 4, cudaMemcpyHostToDevice));
+        }
+        C_(cudaMalloc(&d_out, (size_t)n_out * SP));
+        dx_launch_standalone_expand(0, d, d_rows, n, what == 1 ? d_act : nullptr, d_out);
+        std::vector<uint8_t> orows((size_t)n_out * SP);
+        C_(cudaMemcpy(orows.data(), d_out, orows.size(), cudaMemcpyDeviceToHost));
+        for (long long i = 0; i < n_out; ++i) memcpy(out + (size_t)i * S, &orows[(size_t)i * SP], S);
+    }
+    C_(cudaGetLastError());
+#undef C_
+    cleanup();
+    return rc;
+}
+
+extern "C" int dx_expand(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, int64_t n, uint8_t* children) {
+    return domain_call(device, domain, dim, states, nullptr, nullptr, n, children, 0);
+}
+extern "C" int dx_next_state(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, const int32_t* actions,
+                             int64_t n, uint8_t* next) {
+    return domain_call(device, domain, dim, states, nullptr, actions, n, next, 1);
+}
+extern "C" int dx_is_solved(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, const uint8_t* goals, int64_t n,
+                            uint8_t* solved) {
+    if (n > 0 && !goals) DX_FAIL(DX_ERR_ARG, "null goals");
+    return domain_call(device, domain, dim, states, goals, nullptr, n, solved, 2);
+}
+
+// ---------------------------------------------------------------------------------------------
+extern "C" int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats) {
+    if (!e || !desc || !blob) DX_FAIL(DX_ERR_ARG, "null argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    if (desc->in_count != e->dom.in_count || desc->one_hot_depth != e->dom.depth)
+        DX_FAIL(DX_ERR_ARG, "network input shape does not match the domain's NN input");
+    const int want_out = e->is_q ? e->A : 1;
+    if (desc->out_dim != want_out) DX_FAIL(DX_ERR_ARG, "network out_dim must be 1 for graph_v and num_actions for graph_q");
+    DX_TRY(dx_upload_net(e, desc, blob, n_floats));
+    e->weights_loaded = true;
+    return DX_OK;
+}
+
+// Evaluate the loaded network on host-provided states: rows are staged in a scratch area with a private
+// goal table (row r uses goal r), so it does not disturb the search state.
+extern "C" int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* goals, int64_t n, float* out) {
+    if (!e || n < 0 || (n > 0 && (!states || !out))) DX_FAIL(DX_ERR_ARG, "bad argument");
+    if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    if (n == 0) return DX_OK;
+    const int SP = e->SP, S = e->S, od = e->net.out_dim;
+    const long long chunk = std::min<long long>(e->mlp.cap, 1 << 16);
+    DX_TRY(ensure_stage(e, (size_t)chunk * SP * 2 + (size_t)chunk * od * 4 + 64));
+    uint8_t* d_rows = e->d_stage;
+    uint8_t* d_goals = e->d_stage + (size_t)chunk * SP;
+    float* d_out = (float*)(e->d_stage + (size_t)chunk * SP * 2);
+    std::vector<uint8_t> rows((size_t)chunk * SP), grows((size_t)chunk * SP);
+    DX_TRY(sync_ctl(e));
+    const Ctl saved = *e->h_ctl;
+    for (long long s0 = 0; s0 < n; s0 += chunk) {
+        const long long m = std::min(chunk, n - s0);
+        std::fill(rows.begin(), rows.end(), 0);
+        std::fill(grows.begin(), grows.end(), 0);
+        for (long long r = 0; r < m; ++r) {
+            memcpy(&rows[(size_t)r * SP], states + (size_t)(s0 + r) * S, S);
+            const uint32_t gi = (uint32_t)r;
+            memcpy(&rows[(size_t)r * SP + SP - 4], &gi, 4);
+            if (goals) memcpy(&grows[(size_t)r * SP], goals + (size_t)(s0 + r) * S, S);
+        }
+        DX_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)m * SP, cudaMemcpyHostToDevice, e->stream));
+        DX_CUDA(cudaMemcpyAsync(d_goals, grows.data(), (size_t)m * SP, cudaMemcpyHostToDevice, e->stream));
+        k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, 0, (uint32_t)m);
+        e->launches += 1;
+        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
+            e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, d_rows, d_goals, nullptr, d_out, 0, m);
+        else
+            e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, d_rows, d_goals, nullptr, d_out, 0, m);
+        DX_CUDA(cudaMemcpyAsync(out + (size_t)s0 * od, d_out, (size_t)m * od * 4, cudaMemcpyDeviceToHost, e->stream));
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    // restore the job fields / counters the evaluation touched
+    k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, saved.nn_row_start, saved.nn_n);
+    e->launches += 1;
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    DX_CUDA(cudaGetLastError());
+    return DX_OK;
+}
+
+extern "C" int dx_row_bytes(dx_engine* e, int32_t* row_bytes) {
+    if (!e || !row_bytes) DX_FAIL(DX_ERR_ARG, "null argument");
+    *row_bytes = e->SP;
+    return DX_OK;
+}
+
+// Times `reps` network evaluations over n node-store rows already resident on the device
+// (rows [0, n) of the node store; whatever states are there -- the arithmetic does not depend on them).
+extern "C" int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_total) {
+    if (!e || !ms_total || n < 1 || reps < 1) DX_FAIL(DX_ERR_ARG, "bad argument");
+    if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
+    if (n > (int64_t)e->max_nodes || n > e->mlp.cap) DX_FAIL(DX_ERR_ARG, "n exceeds node store / activation capacity");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    const Ctl saved = *e->h_ctl;
+    DX_TRY(ensure_stage(e, (size_t)n * e->net.out_dim * 4 + 64));
+    float* d_out = (float*)e->d_stage;
+    k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, 0, (uint32_t)n);
+    cudaEvent_t a, b;
+    cudaEventCreate(&a);
+    cudaEventCreate(&b);
+    cudaEventRecord(a, e->stream);
+    for (int r = 0; r < reps; ++r) {
+        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
+            e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, nullptr, d_out, 0, n);
+        else
+            e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, nullptr, d_out, 0, n);
+    }
+    cudaEventRecord(b, e->stream);
+    k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, saved.nn_row_start, saved.nn_n);
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    cudaEventElapsedTime(ms_total, a, b);
+    cudaEventDestroy(a);
+    cudaEventDestroy(b);
+    DX_CUDA(cudaGetLastError());
+    return DX_OK;
+}
+
+extern "C" int dx_set_profiling(dx_engine* e, int32_t on) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    stage_collect(e);
+    e->profiling = on != 0;
+    memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    return DX_OK;
+}
+
+extern "C" int dx_get_stage_ms(dx_engine* e, float* ms, int32_t cap) {
+    if (!e || !ms) DX_FAIL(DX_ERR_ARG, "null argument");
+    stage_collect(e);
+    for (int i = 0; i < std::min<int>(cap, ST_COUNT); ++i) ms[i] = e->stage_ms[i];
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Weight ingest: parse the blob (layout in dxb200.h), fold eval-mode BN into the preceding Linear
+// (y = (Wx + b - mu) * gamma / sqrt(var + 1e-5) + beta, deepxube/pytorch/pytorch_models.py:188 ->
+//  W' = s * W, b' = s * (b - mu) + beta with s computed in double), pad H to a multiple of 128 with zeros.
+__global__ void k_f32_to_bf16(const float* __restrict__ src, uint16_t* __restrict__ dst, size_t n) {
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t u = __float_as_uint(src[i]);
+        // round to nearest even
+        const uint32_t r = u + 0x7FFFu + ((u >> 16) & 1u);
+        dst[i] = (uint16_t)(r >> 16);
+    }
+}
+
+int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats) {
+    if (e->weights_loaded) DX_FAIL(DX_ERR_STATE, "weights already loaded for this engine");
+    const int H = desc->res_dim, nb = desc->num_blocks, od = desc->out_dim, bn = desc->batch_norm;
+    const int in_dim = desc->in_count * desc->one_hot_depth;
+    if (H < 1 || nb < 0 || od < 1 || od > DX_MAX_OUT || desc->in_count > 256) DX_FAIL(DX_ERR_ARG, "unsupported network shape");
+    const int64_t per_layer = (int64_t)H * H + H + (bn ? 4 * H : 0);
+    const int64_t want = (int64_t)H * in_dim + H + 2 * nb * per_layer + (int64_t)od * H + od;
+    if (n_floats != want) DX_FAIL(DX_ERR_ARG, "weight blob has " + std::to_string(n_floats) + " floats, expected " + std::to_string(want));
+    const int Hp = ((H + 127) / 128) * 128;
+    const int in_dim_p = ((in_dim + 63) / 64) * 64;
+    NetDev& net = e->net;
+    net.in_count = desc->in_count; net.depth = desc->one_hot_depth; net.H = H; net.Hp = Hp; net.num_blocks = nb;
+    net.out_dim = od; net.in_dim = in_dim; net.in_dim_p = in_dim_p;
+    std::vector<float> w0t((size_t)in_dim * Hp, 0.f), b0(Hp, 0.f), w0p((size_t)Hp * in_dim_p, 0.f);
+    std::vector<float> wres((size_t)2 * nb * Hp * Hp, 0.f), bres((size_t)2 * nb * Hp, 0.f), wout((size_t)od * Hp, 0.f), bout(od, 0.f);
+    const float* p = blob;
+    for (int o = 0; o < H; ++o)
+        for (int i = 0; i < in_dim; ++i) {
+            w0t[(size_t)i * Hp + o] = p[(size_t)o * in_dim + i];
+            w0p[(size_t)o * in_dim_p + i] = p[(size_t)o * in_dim + i];
+        }
+    p += (size_t)H * in_dim;
+    for (int o = 0; o < H; ++o) b0[o] = p[o];
+    p += H;
+    for (int l = 0; l < 2 * nb; ++l) {
+        const float* W = p; p += (size_t)H * H;
+        const float* b = p; p += H;
+        const float *gam = nullptr, *bet = nullptr, *mu = nullptr, *var = nullptr;
+        if (bn) { gam = p; bet = p + H; mu = p + 2 * H; var = p + 3 * H; p += 4 * H; }
+        float* Wd = &wres[(size_t)l * Hp * Hp];
+        float* bd = &bres[(size_t)l * Hp];
+        for (int o = 0; o < H; ++o) {
+            double s = 1.0, sh = 0.0, mo = 0.0;
+            if (bn) { s = (double)gam[o] / sqrt((double)var[o] + 1e-5); sh = bet[o]; mo = mu[o]; }
+            for (int i = 0; i < H; ++i) Wd[(size_t)o * Hp + i] = (float)((double)W[(size_t)o * H + i] * s);
+            bd[o] = (float)(((double)b[o] - mo) * s + sh);
+        }
+    }
+    for (int o = 0; o < od; ++o)
+        for (int i = 0; i < H; ++i) wout[(size_t)o * Hp + i] = p[(size_t)o * H + i];
+    p += (size_t)od * H;
+    for (int o = 0; o < od; ++o) bout[o] = p[o];
+
+#define UP_(dst, vec) do { DX_TRY(e->alloc(&(dst), (vec).size())); \
+        DX_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(float), cudaMemcpyHostToDevice)); } while (0)
+    UP_(net.w0t, w0t); UP_(net.b0, b0); UP_(net.wres, wres); UP_(net.bres, bres); UP_(net.wout, wout); UP_(net.bout, bout);
+    // bf16 copies for the tensor-core path (first layer K-major [Hp, in_dim_p]; residual layers [l, Hp, Hp])
+    float* d_w0p = nullptr;
+    UP_(d_w0p, w0p);
+#undef UP_
+    uint16_t *w0b = nullptr, *wrb = nullptr;
+    DX_TRY(e->alloc(&w0b, w0p.size()));
+    DX_TRY(e->alloc(&wrb, wres.size()));
+    k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(d_w0p, w0b, w0p.size());
+    if (!wres.empty()) k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(net.wres, wrb, wres.size());
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    net.w0_bf16 = w0b;
+    net.wres_bf16 = wrb;
+    // activation buffers
+    const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst);
+    e->mlp.cap = cap;
+    if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
+        for (int i = 0; i < 3; ++i) { uint16_t* q = nullptr; DX_TRY(e->alloc(&q, (size_t)cap * Hp)); e->mlp.xb[i] = q; }
+        DX_TRY(e->alloc(&e->mlp.x[0], (size_t)cap * Hp));     // fp32 copy of the last activation for the output layer
+    } else {
+        for (int i = 0; i < 3; ++i) DX_TRY(e->alloc(&e->mlp.x[i], (size_t)cap * Hp));
+    }
+    return DX_OK;
+}

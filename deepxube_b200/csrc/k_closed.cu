@@ -1,0 +1,227 @@
+// CLOSED: open-addressing hash set keyed on (instance, state) with a full-row compare, storing the best
+// path cost g per state, plus the exact *sequential* filter semantics of the reference.
+//
+// Reference (deepxube/pathfinding/graph_search.py:73-80): children are visited one by one, in order;
+//     keep child iff state not in CLOSED or CLOSED[state] > g;  then CLOSED[state] = g.
+// So inside one batch a child is kept iff its g is strictly below CLOSED-before-the-batch AND strictly
+// below the g of every EARLIER same-state child of the batch (a later, strictly cheaper duplicate is kept
+// too).  A plain atomic-min insert is not equivalent.  Parallel formulation used here:
+//   1. k_closed_link    every item finds / claims its slot (64-bit CAS on (tag | rep)), then pushes
+//                       itself onto the slot's per-iteration list ((epoch | head) CAS, child_next links).
+//   2. k_closed_decide  every item walks its slot's list (the same-state items of this batch, usually
+//                       1-3) and evaluates the sequential rule directly from (g, batch position).
+//                       The kept item with the lexicographically smallest (g, position) is "final": it
+//                       is the value CLOSED holds after the batch.
+//   3. the final item writes CLOSED[state] = g and, for a slot claimed in this batch, replaces the
+//      pending batch reference by its node id (k_scatter_kept for A*, k_closed_commit for Q*).
+// A slot's representative row is either a node-store row (rep = node id) or, while the batch that
+// created it is in flight, a row of the child batch (rep = DX_PENDING | child index): a state that is new
+// always has a kept child (its first occurrence beats CLOSED = +inf), so the pending reference is
+// always resolved before the next iteration.
+//
+// Two uses: A* filters generated children (item rows = child batch, group = A items per popped node);
+// Q* filters popped nodes (item rows = node-store rows of the popped list, group = 1; graph_search.py:132-133).
+#include "dx_internal.cuh"
+
+#define CL_THREADS 256
+
+__global__ void k_closed_init(ClosedDev c) {
+    const size_t cap = (size_t)c.mask + 1;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
+        c.slot_key[i] = DX_EMPTY64;
+        c.slot_g[i] = __int_as_float(0x7f800000);
+        c.slot_head[i] = 0ull;
+    }
+}
+
+int dx_launch_closed_init(cudaStream_t s, const ClosedDev& c) {
+    k_closed_init<<<148 * 8, 256, 0, s>>>(c);
+    return 1;
+}
+
+__device__ __forceinline__ uint32_t closed_find_or_claim(const ClosedDev& c, const uint4* __restrict__ row, int chunks,
+                                                         uint32_t claim_rep, const uint8_t* __restrict__ node_state,
+                                                         const uint8_t* __restrict__ batch_rows, int SP) {
+    const uint64_t h = dx_hash_row(row, chunks);
+    const uint32_t tag = (uint32_t)(h >> 32);
+    uint32_t i = (uint32_t)h & c.mask;
+    const unsigned long long mine = ((unsigned long long)tag << 32) | claim_rep;
+    while (true) {
+        unsigned long long k = *((volatile unsigned long long*)&c.slot_key[i]);
+        if (k == DX_EMPTY64) {
+            unsigned long long old = atomicCAS(&c.slot_key[i], DX_EMPTY64, mine);
+            if (old == DX_EMPTY64) return i;
+            k = old;
+        }
+        if ((uint32_t)(k >> 32) == tag) {
+            const uint32_t rep = (uint32_t)k;
+            const uint8_t* other = (rep & DX_PENDING) ? (batch_rows + (size_t)(rep & ~DX_PENDING) * SP)
+                                                      : (node_state + (size_t)rep * SP);
+            if (dx_rows_equal(row, reinterpret_cast<const uint4*>(other), chunks)) return i;
+        }
+        i = (i + 1) & c.mask;
+    }
+}
+
+// Root of an A* instance: CLOSED[root] = 0.0 (graph_search.py:119-121).
+__global__ void k_closed_seed(DomainDev d, ClosedDev c, const uint8_t* __restrict__ node_state, uint32_t first, uint32_t n) {
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t id = first + t;
+        const uint4* row = reinterpret_cast<const uint4*>(node_state + (size_t)id * d.SP);
+        uint32_t i = closed_find_or_claim(c, row, d.SP / 16, id, node_state, node_state, d.SP);
+        c.slot_g[i] = 0.0f;
+    }
+}
+
+int dx_launch_closed_seed(cudaStream_t s, const DomainDev& d, const ClosedDev& c, const uint8_t* node_state, uint32_t first_node,
+                          uint32_t n) {
+    if (n == 0) return 0;
+    k_closed_seed<<<dx_div_up(n, 128), 128, 0, s>>>(d, c, node_state, first_node, n);
+    return 1;
+}
+
+// item -> (row pointer, g, owning instance active?)
+struct ItemView {
+    const uint8_t* batch_rows;    // A*: child rows ; Q*: unused
+    const float* batch_g;         // A*: child g (NaN = dead)
+    const uint32_t* item_node;    // Q*: popped node ids (nullptr for A*)
+    const uint8_t* node_state;
+    const float* node_g;
+    const uint32_t* popped_inst;
+    const uint8_t* active;
+    int group;
+    int SP;
+};
+
+__device__ __forceinline__ const uint8_t* item_row(const ItemView& v, uint32_t c) {
+    return v.item_node ? v.node_state + (size_t)v.item_node[c] * v.SP : v.batch_rows + (size_t)c * v.SP;
+}
+__device__ __forceinline__ float item_g(const ItemView& v, uint32_t c) {
+    if (v.item_node) return v.active[v.popped_inst[c]] ? v.node_g[v.item_node[c]] : __int_as_float(0x7fc00000);
+    return v.batch_g[c];
+}
+
+__global__ void __launch_bounds__(CL_THREADS)
+k_closed_link(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, uint32_t* __restrict__ child_slot,
+              uint32_t* __restrict__ child_next) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    const uint32_t epoch = ctl->epoch;
+    const int chunks = v.SP / 16;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
+        const float g = item_g(v, ci);
+        if (g != g) { child_slot[ci] = DX_NIL; continue; }      // item of a finished instance
+        const uint4* row = reinterpret_cast<const uint4*>(item_row(v, ci));
+        const uint32_t claim = v.item_node ? v.item_node[ci] : (DX_PENDING | ci);
+        const uint32_t i = closed_find_or_claim(c, row, chunks, claim, v.node_state, v.batch_rows, v.SP);
+        child_slot[ci] = i;
+        unsigned long long old = *((volatile unsigned long long*)&c.slot_head[i]);
+        while (true) {
+            const uint32_t next = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
+            child_next[ci] = next;
+            const unsigned long long want = ((unsigned long long)epoch << 32) | ci;
+            const unsigned long long got = atomicCAS(&c.slot_head[i], old, want);
+            if (got == old) break;
+            old = got;
+        }
+    }
+}
+
+// flags: bit0 = keep, bit1 = final (this item's g becomes CLOSED[state])
+__global__ void __launch_bounds__(CL_THREADS)
+k_closed_decide(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, const uint32_t* __restrict__ child_slot,
+                const uint32_t* __restrict__ child_next, uint8_t* __restrict__ child_flags) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
+        const uint32_t i = child_slot[ci];
+        if (i == DX_NIL) { child_flags[ci] = 0; continue; }
+        const float g = item_g(v, ci);
+        bool keep = g < c.slot_g[i];
+        bool fin = keep;
+        uint32_t c2 = (uint32_t)c.slot_head[i];
+        while (c2 != DX_NIL) {
+            if (c2 != ci) {
+                const float g2 = item_g(v, c2);
+                if (c2 < ci && g2 <= g) keep = false;                    // an earlier duplicate already set CLOSED <= g
+                if (g2 < g || (g2 == g && c2 < ci)) fin = false;
+            }
+            c2 = child_next[c2];
+        }
+        child_flags[ci] = (keep ? 1 : 0) | ((keep && fin) ? 2 : 0);
+    }
+}
+
+int dx_launch_closed_filter(cudaStream_t s, const DomainDev& d, const ClosedDev& c, const Ctl* ctl, const InstArrays& ia,
+                            const uint8_t* node_state, const float* node_g, const uint8_t* child_state, const float* child_g,
+                            const uint32_t* item_node, const uint32_t* popped_inst, uint32_t* child_slot, uint32_t* child_next,
+                            uint8_t* child_flags, int max_children, int group) {
+    ItemView v{child_state, child_g, item_node, node_state, node_g, popped_inst, ia.active, group, d.SP};
+    int blocks = min(dx_div_up(max_children, CL_THREADS), 148 * 8);
+    k_closed_link<<<blocks, CL_THREADS, 0, s>>>(c, ctl, v, child_slot, child_next);
+    k_closed_decide<<<blocks, CL_THREADS, 0, s>>>(c, ctl, v, child_slot, child_next, child_flags);
+    return 2;
+}
+
+// A*: kept children become nodes (ids in flat child order = push order); final items commit CLOSED.
+__global__ void __launch_bounds__(CL_THREADS)
+k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, const uint8_t* __restrict__ child_state,
+               const float* __restrict__ child_g, const uint32_t* __restrict__ child_slot,
+               const uint8_t* __restrict__ child_flags, const uint32_t* __restrict__ child_prefix,
+               const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst, uint8_t* __restrict__ node_state,
+               float* __restrict__ node_g, uint32_t* __restrict__ node_parent, uint8_t* __restrict__ node_action,
+               uint32_t* __restrict__ new_inst) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    const uint32_t base = ctl->node_base;
+    const int chunks = d.SP / 16;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
+        const uint8_t f = child_flags[ci];
+        if (!(f & 1)) continue;
+        const uint32_t k = child_prefix[ci];
+        const uint32_t id = base + k;
+        const uint4* src = reinterpret_cast<const uint4*>(child_state + (size_t)ci * d.SP);
+        uint4* dst = reinterpret_cast<uint4*>(node_state + (size_t)id * d.SP);
+        for (int q = 0; q < chunks; ++q) dst[q] = src[q];
+        const float g = child_g[ci];
+        const uint32_t j = ci / d.A;
+        node_g[id] = g;
+        node_parent[id] = popped[j];
+        node_action[id] = (uint8_t)(ci % d.A);
+        new_inst[k] = popped_inst[j];
+        if (f & 2) {
+            const uint32_t i = child_slot[ci];
+            c.slot_g[i] = g;
+            const unsigned long long key = c.slot_key[i];
+            if ((uint32_t)key & DX_PENDING) c.slot_key[i] = (key & 0xFFFFFFFF00000000ull) | id;
+        }
+    }
+}
+
+int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const uint8_t* child_state,
+                           const float* child_g, const uint32_t* child_slot, const uint8_t* child_flags,
+                           const uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
+                           uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
+                           int max_children) {
+    int blocks = min(dx_div_up(max_children, CL_THREADS), 148 * 8);
+    k_scatter_kept<<<blocks, CL_THREADS, 0, s>>>(d, c, ctl, child_state, child_g, child_slot, child_flags, child_prefix, popped,
+                                                 popped_inst, node_state, node_g, node_parent, node_action, new_inst);
+    return 1;
+}
+
+// Q*: popped nodes that pass the filter only need CLOSED committed (they already are nodes).
+__global__ void k_closed_commit(ClosedDev c, const Ctl* __restrict__ ctl, const float* __restrict__ node_g,
+                                const uint32_t* __restrict__ item_node, const uint32_t* __restrict__ child_slot,
+                                const uint8_t* __restrict__ child_flags) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
+        if (child_flags[ci] & 2) c.slot_g[child_slot[ci]] = node_g[item_node[ci]];
+}
+
+int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,
+                            const uint32_t* child_slot, const uint8_t* child_flags, int max_items) {
+    int blocks = min(dx_div_up(max_items, 256), 148 * 8);
+    k_closed_commit<<<blocks, 256, 0, s>>>(c, ctl, node_g, item_node, child_slot, child_flags);
+    return 1;
+}

@@ -1,0 +1,322 @@
+// State expansion / next_state / is_solved for cube3, npuzzle and grid over packed uint8 rows.
+//
+// Reference behaviour reproduced (children are state-major / action-minor, child = j*A + a):
+//   ActsEnum.expand                      deepxube/base/domain.py:288-312
+//   Cube3._next_state_np                 deepxube/domains/cube3.py:583-596  (next[new] = cur[old], table :598-671)
+//   NPuzzle._move_np / swap_zero_idxs    deepxube/domains/npuzzle.py:264-321 (blocked move = no-op, cost still 1.0)
+//   Grid.next_state                      deepxube/domains/grid.py:74-86
+//   is_solved                            cube3.py:514-517, npuzzle.py:154-158 (goal byte d*d = wildcard), grid.py:68-69
+//   goal test on POPPED nodes + record_goal (ub = min g, first seen wins)
+//                                        deepxube/base/pathfinding.py:353-359, pathfinding/graph_search.py:35-41
+//
+// Layout: a row is SP bytes = S state bytes, zero padding, and the owning instance id in the last 4
+// bytes (so that hashing / comparing whole rows keys CLOSED by (instance, state)).  One block stages
+// PB parent rows in shared memory and its threads emit the children one 32-bit word at a time, so
+// global stores are fully coalesced (consecutive threads -> consecutive words of consecutive children).
+#include "dx_internal.cuh"
+
+#define EXP_THREADS 256
+#define EXP_PB 16          // parents per block pass
+#define MAX_SP 240         // npuzzle.15: 225 + 4 -> 240
+
+__device__ __forceinline__ uint32_t child_byte(int kind, int dim, int S, const uint8_t* __restrict__ row,
+                                               const uint8_t* __restrict__ table, int a, int i, int z) {
+    if (i >= S) return 0u;
+    if (kind == DX_DOMAIN_CUBE3) {
+        return row[table[a * 54 + i]];
+    } else if (kind == DX_DOMAIN_NPUZZLE) {
+        int sw = table[z * 4 + a];
+        if (i == z) return row[sw];          // sw == z (blocked): row[z] == 0, unchanged
+        if (i == sw) return 0u;
+        return row[i];
+    } else {
+        int v = row[i];
+        if (i == 0) {
+            if (a == 0) v = max(v - 1, 0);
+            else if (a == 1) v = min(v + 1, dim - 1);
+        } else {
+            if (a == 2) v = max(v - 1, 0);
+            else if (a == 3) v = min(v + 1, dim - 1);
+        }
+        return (uint32_t)v;
+    }
+}
+
+__device__ __forceinline__ bool row_solved(int kind, int dim, int S, const uint8_t* __restrict__ row,
+                                           const uint8_t* __restrict__ goal) {
+    bool ok = true;
+    const int wild = dim * dim;
+    for (int i = 0; i < S; ++i) {
+        uint8_t g = goal[i];
+        bool e = (row[i] == g);
+        if (kind == DX_DOMAIN_NPUZZLE) e = e || (g == wild);
+        ok = ok && e;
+    }
+    return ok;
+}
+
+__device__ __forceinline__ int find_blank(const uint8_t* row, int S) {
+    int z = 0;
+    for (int i = 0; i < S; ++i)
+        if (row[i] == 0) { z = i; break; }
+    return z;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Search-time expansion of the popped list.
+__global__ void __launch_bounds__(EXP_THREADS)
+k_expand(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
+         const float* __restrict__ node_g, const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
+         const uint32_t* __restrict__ pop_off, uint8_t* __restrict__ child_state, float* __restrict__ child_g,
+         uint8_t* __restrict__ pop_solved) {
+    __shared__ __align__(16) uint8_t s_rows[EXP_PB * MAX_SP];
+    __shared__ uint8_t s_table[12 * 54 > 225 * 4 ? 12 * 54 : 225 * 4];
+    __shared__ int s_z[EXP_PB];
+    __shared__ uint32_t s_inst[EXP_PB];
+    __shared__ float s_g[EXP_PB];       // NaN marks a parent of an inactive (finished) instance
+
+    if (ctl->error) return;
+    const int n_pop = ctl->n_pop;
+    const int SP = d.SP, S = d.S, A = d.A, words = SP / 4;
+    const int tsz = d.kind == DX_DOMAIN_CUBE3 ? 12 * 54 : (d.kind == DX_DOMAIN_NPUZZLE ? d.dim * d.dim * 4 : 0);
+    for (int i = threadIdx.x; i < tsz; i += EXP_THREADS) s_table[i] = d.table[i];
+
+    for (int base = blockIdx.x * EXP_PB; base < n_pop; base += gridDim.x * EXP_PB) {
+        const int np = min(EXP_PB, n_pop - base);
+        __syncthreads();
+        // stage parent rows (16-byte chunks)
+        const int chunks = SP / 16;
+        for (int t = threadIdx.x; t < np * chunks; t += EXP_THREADS) {
+            int p = t / chunks, c = t % chunks;
+            uint32_t id = popped[base + p];
+            reinterpret_cast<uint4*>(s_rows + p * SP)[c] = reinterpret_cast<const uint4*>(node_state + (size_t)id * SP)[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < np) {
+            const int p = threadIdx.x, j = base + p;
+            const uint8_t* row = s_rows + p * SP;
+            const uint32_t inst = popped_inst[j];
+            const uint32_t id = popped[j];
+            const bool act = ia.active[inst] != 0;
+            const float g = node_g[id];
+            s_inst[p] = inst;
+            s_g[p] = act ? g : __int_as_float(0x7fc00000);
+            s_z[p] = (d.kind == DX_DOMAIN_NPUZZLE) ? find_blank(row, S) : 0;
+            bool solved = false;
+            if (act) {
+                solved = row_solved(d.kind, d.dim, S, row, ia.goals + (size_t)inst * SP);
+                if (solved) {
+                    // lexicographic min over (g, pop order): strict '>' in record_goal == first seen wins
+                    unsigned long long key = ((unsigned long long)__float_as_uint(g) << 32) |
+                                             (unsigned long long)(ia.pop_seq_base[inst] + (uint32_t)j - pop_off[inst]);
+                    atomicMin(&ia.ub_key[inst], key);
+                }
+            }
+            pop_solved[j] = solved ? 1 : 0;
+        }
+        __syncthreads();
+        // children, one 32-bit word per thread step
+        const int total_words = np * A * words;
+        for (int t = threadIdx.x; t < total_words; t += EXP_THREADS) {
+            const int cl = t / words, w = t % words;
+            const int p = cl / A, a = cl % A;
+            const uint8_t* row = s_rows + p * SP;
+            uint32_t v;
+            if (w == words - 1) {
+                v = s_inst[p];
+            } else {
+                const int i0 = w * 4;
+                v = child_byte(d.kind, d.dim, S, row, s_table, a, i0, s_z[p]) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 1, s_z[p]) << 8) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 2, s_z[p]) << 16) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 3, s_z[p]) << 24);
+            }
+            reinterpret_cast<uint32_t*>(child_state + ((size_t)(base * A + cl)) * SP)[w] = v;
+        }
+        for (int t = threadIdx.x; t < np * A; t += EXP_THREADS) {
+            float g = s_g[t / A];
+            child_g[(size_t)base * A + t] = g + 1.0f;     // transition cost 1.0 in all three domains; NaN stays NaN
+        }
+    }
+}
+
+int dx_launch_expand(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                     const float* node_g, const uint32_t* popped, const uint32_t* popped_inst, const uint32_t* pop_off,
+                     uint8_t* child_state, float* child_g, uint8_t* pop_solved, int max_pop) {
+    int blocks = min(dx_div_up(max_pop, EXP_PB), 148 * 8);
+    k_expand<<<blocks, EXP_THREADS, 0, s>>>(d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, child_state,
+                                            child_g, pop_solved);
+    return 1;
+}
+
+// goal_node = the popped node whose (g, sequence) key won the atomicMin.
+__global__ void k_goal_resolve(const Ctl* __restrict__ ctl, InstArrays ia, const float* __restrict__ node_g,
+                               const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
+                               const uint32_t* __restrict__ pop_off, const uint8_t* __restrict__ pop_solved) {
+    if (ctl->error) return;
+    const int n = ctl->n_pop;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        if (!pop_solved[j]) continue;
+        uint32_t inst = popped_inst[j], id = popped[j];
+        unsigned long long key = ((unsigned long long)__float_as_uint(node_g[id]) << 32) |
+                                 (unsigned long long)(ia.pop_seq_base[inst] + (uint32_t)j - pop_off[inst]);
+        if (ia.ub_key[inst] == key) ia.goal_node[inst] = id;
+    }
+}
+
+int dx_launch_goal_resolve(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const uint32_t* popped,
+                           const uint32_t* popped_inst, const uint32_t* pop_off, const uint8_t* pop_solved, int max_pop) {
+    int blocks = min(dx_div_up(max_pop, 256), 148 * 4);
+    k_goal_resolve<<<blocks, 256, 0, s>>>(ctl, ia, node_g, popped, popped_inst, pop_off, pop_solved);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Stand-alone domain API (expand / next_state / is_solved on caller-provided rows).
+// actions == nullptr: all A children per row (out rows = n*A); else one child per row.
+__global__ void __launch_bounds__(EXP_THREADS)
+k_standalone_expand(DomainDev d, const uint8_t* __restrict__ rows, long long n, const int32_t* __restrict__ actions,
+                    uint8_t* __restrict__ out_rows) {
+    __shared__ __align__(16) uint8_t s_rows[EXP_PB * MAX_SP];
+    __shared__ uint8_t s_table[12 * 54 > 225 * 4 ? 12 * 54 : 225 * 4];
+    __shared__ int s_z[EXP_PB];
+    __shared__ int s_act[EXP_PB];
+    const int SP = d.SP, S = d.S, words = SP / 4;
+    const int A = actions ? 1 : d.A;
+    const int tsz = d.kind == DX_DOMAIN_CUBE3 ? 12 * 54 : (d.kind == DX_DOMAIN_NPUZZLE ? d.dim * d.dim * 4 : 0);
+    for (int i = threadIdx.x; i < tsz; i += EXP_THREADS) s_table[i] = d.table[i];
+    for (long long base = (long long)blockIdx.x * EXP_PB; base < n; base += (long long)gridDim.x * EXP_PB) {
+        const int np = (int)min((long long)EXP_PB, n - base);
+        __syncthreads();
+        const int chunks = SP / 16;
+        for (int t = threadIdx.x; t < np * chunks; t += EXP_THREADS) {
+            int p = t / chunks, c = t % chunks;
+            reinterpret_cast<uint4*>(s_rows + p * SP)[c] = reinterpret_cast<const uint4*>(rows + (size_t)(base + p) * SP)[c];
+        }
+        __syncthreads();
+        if (threadIdx.x < np) {
+            const uint8_t* row = s_rows + threadIdx.x * SP;
+            s_z[threadIdx.x] = (d.kind == DX_DOMAIN_NPUZZLE) ? find_blank(row, S) : 0;
+            s_act[threadIdx.x] = actions ? actions[base + threadIdx.x] : 0;
+        }
+        __syncthreads();
+        const int total_words = np * A * words;
+        for (int t = threadIdx.x; t < total_words; t += EXP_THREADS) {
+            const int cl = t / words, w = t % words;
+            const int p = cl / A, a = actions ? s_act[p] : (cl % A);
+            const uint8_t* row = s_rows + p * SP;
+            uint32_t v;
+            if (w == words - 1) {
+                v = reinterpret_cast<const uint32_t*>(row)[w];
+            } else {
+                const int i0 = w * 4;
+                v = child_byte(d.kind, d.dim, S, row, s_table, a, i0, s_z[p]) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 1, s_z[p]) << 8) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 2, s_z[p]) << 16) |
+                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 3, s_z[p]) << 24);
+            }
+            reinterpret_cast<uint32_t*>(out_rows + ((size_t)(base * A + cl)) * SP)[w] = v;
+        }
+    }
+}
+
+int dx_launch_standalone_expand(cudaStream_t s, const DomainDev& d, const uint8_t* rows, long long n, const int32_t* actions,
+                                uint8_t* out_rows) {
+    if (n <= 0) return 0;
+    int blocks = (int)min((long long)dx_div_up(n, EXP_PB), (long long)148 * 8);
+    k_standalone_expand<<<blocks, EXP_THREADS, 0, s>>>(d, rows, n, actions, out_rows);
+    return 1;
+}
+
+__global__ void k_standalone_solved(DomainDev d, const uint8_t* __restrict__ rows, const uint8_t* __restrict__ goal_rows,
+                                    long long n, uint8_t* __restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x)
+        out[i] = row_solved(d.kind, d.dim, d.S, rows + (size_t)i * d.SP, goal_rows + (size_t)i * d.SP) ? 1 : 0;
+}
+
+int dx_launch_standalone_solved(cudaStream_t s, const DomainDev& d, const uint8_t* rows, const uint8_t* goal_rows, long long n,
+                                uint8_t* out) {
+    if (n <= 0) return 0;
+    int blocks = (int)min((long long)dx_div_up(n, 256), (long long)148 * 8);
+    k_standalone_solved<<<blocks, 256, 0, s>>>(d, rows, goal_rows, n, out);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Q*: goal test of the popped nodes only (no expansion at this point; base/pathfinding.py:486-492).
+__global__ void k_check_solved(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
+                               const float* __restrict__ node_g, const uint32_t* __restrict__ popped,
+                               const uint32_t* __restrict__ popped_inst, const uint32_t* __restrict__ pop_off,
+                               uint8_t* __restrict__ pop_solved) {
+    if (ctl->error) return;
+    const int n = ctl->n_pop;
+    for (int j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t inst = popped_inst[j], id = popped[j];
+        bool solved = false;
+        if (ia.active[inst]) {
+            solved = row_solved(d.kind, d.dim, d.S, node_state + (size_t)id * d.SP, ia.goals + (size_t)inst * d.SP);
+            if (solved) {
+                unsigned long long key = ((unsigned long long)__float_as_uint(node_g[id]) << 32) |
+                                         (unsigned long long)(ia.pop_seq_base[inst] + (uint32_t)j - pop_off[inst]);
+                atomicMin(&ia.ub_key[inst], key);
+            }
+        }
+        pop_solved[j] = solved ? 1 : 0;
+    }
+}
+
+int dx_launch_check_solved(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                           const float* node_g, const uint32_t* popped, const uint32_t* popped_inst, const uint32_t* pop_off,
+                           uint8_t* pop_solved, int max_pop) {
+    int blocks = min(dx_div_up(max_pop, 128), 148 * 8);
+    k_check_solved<<<blocks, 128, 0, s>>>(d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, pop_solved);
+    return 1;
+}
+
+// Q*: one child per popped edge (base/pathfinding.py:527-566).  edges[r] = parent * A + action;
+// popped_out[r] = id of the generated node (= node_base + r, creation order): the next popped-node list.
+__global__ void __launch_bounds__(128)
+k_expand_edges(DomainDev d, const Ctl* __restrict__ ctl, const uint32_t* __restrict__ edges, uint32_t* __restrict__ popped_out,
+               uint8_t* __restrict__ node_state, float* __restrict__ node_g, uint32_t* __restrict__ node_parent,
+               uint8_t* __restrict__ node_action) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_kept, base = ctl->node_base;
+    const int SP = d.SP, S = d.S, words = SP / 4;
+    // 4 lanes cooperate on one edge: coalesced 16-byte pieces of the parent row, word-wise stores
+    const uint32_t gt = blockIdx.x * blockDim.x + threadIdx.x;
+    const uint32_t sub = gt & 3;
+    for (uint32_t r = gt >> 2; r < n; r += (gridDim.x * blockDim.x) >> 2) {
+        const uint32_t code = edges[r];
+        const uint32_t parent = code / d.A, a = code % d.A;
+        const uint8_t* prow = node_state + (size_t)parent * SP;
+        const int z = (d.kind == DX_DOMAIN_NPUZZLE) ? find_blank(prow, S) : 0;
+        const uint32_t id = base + r;
+        uint32_t* out = reinterpret_cast<uint32_t*>(node_state + (size_t)id * SP);
+        for (int w = sub; w < words; w += 4) {
+            uint32_t v;
+            if (w == words - 1) {
+                v = reinterpret_cast<const uint32_t*>(prow)[w];
+            } else {
+                const int i0 = w * 4;
+                v = child_byte(d.kind, d.dim, S, prow, d.table, a, i0, z) |
+                    (child_byte(d.kind, d.dim, S, prow, d.table, a, i0 + 1, z) << 8) |
+                    (child_byte(d.kind, d.dim, S, prow, d.table, a, i0 + 2, z) << 16) |
+                    (child_byte(d.kind, d.dim, S, prow, d.table, a, i0 + 3, z) << 24);
+            }
+            out[w] = v;
+        }
+        if (sub == 0) {
+            node_g[id] = node_g[parent] + 1.0f;
+            node_parent[id] = parent;
+            node_action[id] = (uint8_t)a;
+            popped_out[r] = id;
+        }
+    }
+}
+
+int dx_launch_expand_edges(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint32_t* edges, uint32_t* popped_out,
+                           uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, int max_pop) {
+    int blocks = min(dx_div_up((long long)max_pop * 4, 128), 148 * 8);
+    k_expand_edges<<<blocks, 128, 0, s>>>(d, ctl, edges, popped_out, node_state, node_g, node_parent, node_action);
+    return 1;
+}

@@ -1,0 +1,433 @@
+// OPEN: device-resident batched priority structure.
+//
+// Reference semantics (deepxube/pathfinding/graph_search.py:48-71): a binary heap of
+// (f, push_count, item); every iteration pushes the kept items in order and pops min(B, |OPEN|) items,
+// i.e. the B smallest by (f, push order), returned in ascending order; lb = max(lb, f of first popped).
+// f = float64(w) * float64(g) + float64(h), two separately rounded float64 operations
+// (graph_search.py:153, :175).
+//
+// Device formulation: per instance, OPEN is one run sorted by (f-key, item), where f-key is the bit
+// pattern of the float64 f (f >= 0, so unsigned order == numeric order) and items are numbered in push
+// order (A*: node id; Q*: node id * A + action), so the pair order IS the heap's (f, push_count) order.
+// One iteration =
+//   k_plan        per-instance sizes and offsets of this iteration (pushed m, popped k, new |OPEN|),
+//   k_make_keys   f-keys of the pushed batch (__dmul_rn/__dadd_rn: no FMA contraction),
+//   radix sort    stable LSD sort of the batch by (instance, f-key) -- 8-bit digits, digit passes whose
+//                 byte is constant over the batch are skipped (flags computed on the device),
+//   k_merge       merge-path merge of each instance's run with its sorted batch; the first k outputs
+//                 become the next popped list (already in pop order), the rest the new run (ping-pong),
+//   k_end_iter    lb / ub / finished() / itr bookkeeping (graph_search.py:43-46, 67-69).
+// Every kernel sizes itself from the device-side control block; the host never synchronises.
+#include "dx_internal.cuh"
+
+#define OPEN_THREADS 256
+#define ITEMS 8   // DX_SORT_TILE / OPEN_THREADS
+
+static_assert(OPEN_THREADS * ITEMS == DX_SORT_TILE, "tile size");
+
+// ---------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(1024)
+k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+       uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
+       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open) {
+    __shared__ uint32_t s_tot[4][1024];
+    if (ctl->error) return;
+    const int I = ctl->n_inst;
+    const int per = (I + 1023) / 1024;
+    const int lo = min(I, (int)threadIdx.x * per), hi = min(I, lo + per);
+    uint32_t sm = 0, sk = 0, sn = 0, st = 0;
+    for (int i = lo; i < hi; ++i) {
+        const bool act = ia.active[i] != 0;
+        const uint32_t kept = prefix[pop_off_cur[i + 1] * child_mult] - prefix[pop_off_cur[i] * child_mult];
+        const uint32_t m = act ? kept * push_mult : 0;
+        const uint32_t n = act ? (open_off_cur[i + 1] - open_off_cur[i]) : 0;   // OPEN of a finished instance is dropped
+        const uint32_t t = n + m;
+        const uint32_t k = act ? min((uint32_t)ia.batch[i], t) : 0;
+        ia.m_new[i] = m;
+        ia.k_pop[i] = k;
+        ia.n_open[i] = t - k;
+        sm += m; sk += k; sn += t - k; st += (t + DX_SORT_TILE - 1) / DX_SORT_TILE;
+    }
+    s_tot[0][threadIdx.x] = sm; s_tot[1][threadIdx.x] = sk; s_tot[2][threadIdx.x] = sn; s_tot[3][threadIdx.x] = st;
+    __syncthreads();
+    if (threadIdx.x < 4) {        // tiny serial scan over 1024 partials per quantity
+        uint32_t acc = 0;
+        for (int t = 0; t < 1024; ++t) { uint32_t v = s_tot[threadIdx.x][t]; s_tot[threadIdx.x][t] = acc; acc += v; }
+        if (threadIdx.x == 0) { ia.batch_off[I] = acc; ctl->sort_n = acc; }
+        if (threadIdx.x == 1) { pop_off_next[I] = acc; if (acc > max_pop) atomicOr(&ctl->error, DX_DEVERR_POP); }
+        if (threadIdx.x == 2) { open_off_next[I] = acc; ctl->open_total = acc; if (acc > max_open) atomicOr(&ctl->error, DX_DEVERR_OPEN); }
+        if (threadIdx.x == 3) { ia.tile_off[I] = acc; ctl->n_tiles = acc; }
+    }
+    __syncthreads();
+    uint32_t om = s_tot[0][threadIdx.x], ok = s_tot[1][threadIdx.x], on = s_tot[2][threadIdx.x], ot = s_tot[3][threadIdx.x];
+    for (int i = lo; i < hi; ++i) {
+        ia.batch_off[i] = om; pop_off_next[i] = ok; open_off_next[i] = on; ia.tile_off[i] = ot;
+        const uint32_t m = ia.m_new[i], k = ia.k_pop[i], n = ia.n_open[i];
+        om += m; ok += k; on += n; ot += (n + k + DX_SORT_TILE - 1) / DX_SORT_TILE;
+    }
+}
+
+int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                   uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
+                   uint32_t max_pop, uint32_t max_open) {
+    k_plan<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, child_mult,
+                              push_mult, max_pop, max_open);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned long long f_key(double w, float g, float h) {
+    // float64(w) * float64(g) + float64(h), each rounded once (no FMA) -- graph_search.py:153
+    const double f = __dadd_rn(__dmul_rn(w, (double)g), (double)h);
+    return (unsigned long long)__double_as_longlong(f);
+}
+
+// A*: batch element k is new node (node_base + k).
+__global__ void k_make_keys_v(const Ctl* __restrict__ ctl, InstArrays ia, const float* __restrict__ node_g,
+                              const float* __restrict__ node_h, const uint32_t* __restrict__ new_inst, SortBufs sb) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->sort_n, base = ctl->node_base;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t id = base + k, inst = new_inst[k];
+        sb.key[0][k] = f_key(ia.weight[inst], node_g[id], node_h[id]);
+        sb.inst[0][k] = inst;
+        sb.val[0][k] = id;
+    }
+}
+
+// Q*: batch element (r*A + a) is edge (kept popped node r, action a); f = w * g(node) + q(node, a)
+// (graph_search.py:168-179; edge order = kept-node order x action id, base/pathfinding.py:568-588).
+__global__ void k_make_keys_q(const Ctl* __restrict__ ctl, InstArrays ia, const float* __restrict__ node_g,
+                              const float* __restrict__ node_q, const uint32_t* __restrict__ popped,
+                              const uint32_t* __restrict__ popped_inst, const uint8_t* __restrict__ flags,
+                              const uint32_t* __restrict__ prefix, SortBufs sb, int A) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_pop * A;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
+        const uint32_t j = t / A, a = t % A;
+        if (!(flags[j] & 1)) continue;
+        const uint32_t node = popped[j], inst = popped_inst[j];
+        const uint32_t k = prefix[j] * A + a;
+        sb.key[0][k] = f_key(ia.weight[inst], node_g[node], node_q[(size_t)node * A + a]);
+        sb.inst[0][k] = inst;
+        sb.val[0][k] = node * A + a;
+    }
+}
+
+int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
+                        const uint32_t* new_inst, const SortBufs& sb, int max_n) {
+    int blocks = min(dx_div_up(max_n, 256), 148 * 8);
+    k_make_keys_v<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_h, new_inst, sb);
+    return 1;
+}
+
+int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
+                          const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
+                          const SortBufs& sb, int A, int max_pop) {
+    int blocks = min(dx_div_up((long long)max_pop * A, 256), 148 * 8);
+    k_make_keys_q<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_q, popped, popped_inst, flags, prefix, sb, A);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Radix sort (LSD, 8-bit digits, stable).  Digit d < 8: byte d of the f-key; d >= 8: byte d-8 of the
+// instance id.
+__device__ __forceinline__ uint32_t digit_of(unsigned long long key, uint32_t inst, int d) {
+    return d < 8 ? (uint32_t)(key >> (8 * d)) & 255u : (inst >> (8 * (d - 8))) & 255u;
+}
+
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_radix_prepass(const Ctl* __restrict__ ctl, SortBufs sb) {
+    __shared__ uint32_t s_h[DX_NUM_DIGITS * 256];
+    if (ctl->error) return;
+    const uint32_t n = ctl->sort_n;
+    if (blockIdx.x * OPEN_THREADS >= n && blockIdx.x > 0) return;
+    for (int i = threadIdx.x; i < DX_NUM_DIGITS * 256; i += OPEN_THREADS) s_h[i] = 0;
+    __syncthreads();
+    for (uint32_t k = blockIdx.x * OPEN_THREADS + threadIdx.x; k < n; k += gridDim.x * OPEN_THREADS) {
+        const unsigned long long key = sb.key[0][k];
+        const uint32_t inst = sb.inst[0][k];
+#pragma unroll
+        for (int d = 0; d < DX_NUM_DIGITS; ++d) atomicAdd(&s_h[d * 256 + digit_of(key, inst, d)], 1u);
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < DX_NUM_DIGITS * 256; i += OPEN_THREADS)
+        if (s_h[i]) atomicAdd(&sb.ghist[i], s_h[i]);
+}
+
+// skip a pass when one bin holds every element; assign ping-pong sources to the remaining passes.
+__global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
+    __shared__ uint32_t s_skip[DX_NUM_DIGITS];
+    if (ctl->error) return;
+    const uint32_t n = ctl->sort_n;
+    if (threadIdx.x < DX_NUM_DIGITS) s_skip[threadIdx.x] = (n == 0) ? 1u : 0u;
+    __syncthreads();
+    for (int i = threadIdx.x; i < DX_NUM_DIGITS * 256; i += blockDim.x) {
+        if (n != 0 && sb.ghist[i] == n) s_skip[i / 256] = 1u;
+        sb.ghist[i] = 0;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        uint32_t src = 0;
+        for (int d = 0; d < DX_NUM_DIGITS; ++d) {
+            ctl->pass_skip[d] = s_skip[d];
+            ctl->pass_src[d] = src;
+            if (!s_skip[d]) src ^= 1u;
+        }
+        ctl->sort_final = src;
+    }
+}
+
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_radix_hist(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
+    __shared__ uint32_t s_h[256];
+    if (ctl->error || ctl->pass_skip[d]) return;
+    const uint32_t n = ctl->sort_n;
+    const uint32_t src = ctl->pass_src[d];
+    const uint32_t tile = blockIdx.x;
+    s_h[threadIdx.x] = 0;
+    __syncthreads();
+    const uint32_t base = tile * DX_SORT_TILE;
+    if (base < n) {
+        const unsigned long long* __restrict__ keys = sb.key[src];
+        const uint32_t* __restrict__ insts = sb.inst[src];
+#pragma unroll
+        for (int r = 0; r < ITEMS; ++r) {
+            const uint32_t e = base + r * OPEN_THREADS + threadIdx.x;
+            if (e < n) atomicAdd(&s_h[digit_of(keys[e], insts[e], d)], 1u);
+        }
+    }
+    __syncthreads();
+    sb.hist[(size_t)threadIdx.x * sb.max_tiles + tile] = s_h[threadIdx.x];
+}
+
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
+    __shared__ uint32_t s_cnt[OPEN_THREADS / 32][256];
+    if (ctl->error || ctl->pass_skip[d]) return;
+    const uint32_t n = ctl->sort_n;
+    const uint32_t src = ctl->pass_src[d], dst = src ^ 1u;
+    const uint32_t tile = blockIdx.x;
+    const uint32_t base = tile * DX_SORT_TILE;
+    if (base >= n) return;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (int i = threadIdx.x; i < (OPEN_THREADS / 32) * 256; i += OPEN_THREADS) (&s_cnt[0][0])[i] = 0;
+    __syncthreads();
+
+    unsigned long long key[ITEMS];
+    uint32_t inst[ITEMS], val[ITEMS], rank[ITEMS], dig[ITEMS];
+    const unsigned long long* __restrict__ keys = sb.key[src];
+    const uint32_t* __restrict__ insts = sb.inst[src];
+    const uint32_t* __restrict__ vals = sb.val[src];
+    // warp w owns the contiguous elements [w*256, (w+1)*256) of the tile, 32 per round: stability = (warp, round, lane)
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        const uint32_t e = base + warp * (32 * ITEMS) + r * 32 + lane;
+        const bool valid = e < n;
+        key[r] = valid ? keys[e] : 0ull;
+        inst[r] = valid ? insts[e] : 0u;
+        val[r] = valid ? vals[e] : 0u;
+        dig[r] = valid ? digit_of(key[r], inst[r], d) : (256u + lane);
+        const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
+        const int leader = __ffs(peers) - 1;
+        const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+        uint32_t old = 0;
+        if (valid && lane == leader) {
+            old = s_cnt[warp][dig[r]];
+            s_cnt[warp][dig[r]] = old + __popc(peers);
+        }
+        old = __shfl_sync(0xffffffffu, old, leader);
+        rank[r] = old + before;
+        __syncwarp();
+    }
+    __syncthreads();
+    {   // per digit: exclusive offsets over warps, on top of the global (digit, tile) offset
+        const uint32_t dg = threadIdx.x;
+        uint32_t acc = sb.hist[(size_t)dg * sb.max_tiles + tile];
+#pragma unroll
+        for (int w = 0; w < OPEN_THREADS / 32; ++w) {
+            const uint32_t c = s_cnt[w][dg];
+            s_cnt[w][dg] = acc;
+            acc += c;
+        }
+    }
+    __syncthreads();
+    unsigned long long* __restrict__ okeys = sb.key[dst];
+    uint32_t* __restrict__ oinsts = sb.inst[dst];
+    uint32_t* __restrict__ ovals = sb.val[dst];
+#pragma unroll
+    for (int r = 0; r < ITEMS; ++r) {
+        if (dig[r] < 256u) {
+            const uint32_t pos = s_cnt[warp][dig[r]] + rank[r];
+            okeys[pos] = key[r];
+            oinsts[pos] = inst[r];
+            ovals[pos] = val[r];
+        }
+    }
+}
+
+int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n) {
+    int launches = 0;
+    const int pre_blocks = min(dx_div_up(max_n, OPEN_THREADS), 148 * 4);
+    k_radix_prepass<<<pre_blocks, OPEN_THREADS, 0, s>>>(ctl, sb);
+    k_radix_flags<<<1, 256, 0, s>>>(ctl, sb);
+    launches += 2;
+    for (int d = 0; d < DX_NUM_DIGITS; ++d) {
+        k_radix_hist<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
+        launches += 1 + dx_launch_scan_u32(s, sb.hist, 256 * sb.max_tiles, &ctl->pass_skip[d], t);
+        k_radix_scatter<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
+        launches += 1;
+    }
+    return launches;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Merge-path merge of OPEN run (A) and sorted batch (B) per instance; ties take A first (older push).
+__device__ __forceinline__ uint32_t merge_path(const unsigned long long* __restrict__ a, uint32_t na,
+                                               const unsigned long long* __restrict__ b, uint32_t nb, uint32_t diag) {
+    uint32_t lo = diag > nb ? diag - nb : 0, hi = min(diag, na);
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        if (a[mid] <= b[diag - 1 - mid]) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
+        const uint32_t* __restrict__ open_val_cur, const uint32_t* __restrict__ open_off_cur,
+        unsigned long long* __restrict__ open_key_next, uint32_t* __restrict__ open_val_next,
+        const uint32_t* __restrict__ open_off_next, uint32_t* __restrict__ popped_next, uint32_t* __restrict__ popped_inst_next,
+        const uint32_t* __restrict__ pop_off_next) {
+    __shared__ unsigned long long s_key[DX_SORT_TILE];
+    __shared__ uint32_t s_val[DX_SORT_TILE];
+    __shared__ uint32_t s_part[4];   // a0, a1, inst
+    if (ctl->error) return;
+    const uint32_t n_tiles = ctl->n_tiles;
+    const int I = ctl->n_inst;
+    const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
+    const uint32_t* __restrict__ bvals = sb.val[ctl->sort_final];
+    for (uint32_t T = blockIdx.x; T < n_tiles; T += gridDim.x) {
+        __syncthreads();
+        if (threadIdx.x < 2) {
+            // instance of this tile: last i with tile_off[i] <= T
+            int lo = 0, hi = I - 1;
+            while (lo < hi) {
+                const int mid = (lo + hi + 1) >> 1;
+                if (ia.tile_off[mid] <= T) lo = mid; else hi = mid - 1;
+            }
+            const int i = lo;
+            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
+            const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
+            const uint32_t diag = threadIdx.x == 0 ? d0 : min(d0 + DX_SORT_TILE, na + nb);
+            s_part[threadIdx.x] = merge_path(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, diag);
+            if (threadIdx.x == 0) s_part[2] = i;
+        }
+        __syncthreads();
+        const int i = s_part[2];
+        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
+        const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE, d1 = min(d0 + DX_SORT_TILE, na + nb);
+        const uint32_t a0 = s_part[0], a1 = s_part[1], b0 = d0 - a0, b1 = d1 - a1;
+        const uint32_t ca = a1 - a0, cb = b1 - b0;
+        const unsigned long long* __restrict__ ak = open_key_cur + open_off_cur[i] + a0;
+        const uint32_t* __restrict__ av = open_val_cur + open_off_cur[i] + a0;
+        const unsigned long long* __restrict__ bk = bkeys + ia.batch_off[i] + b0;
+        const uint32_t* __restrict__ bv = bvals + ia.batch_off[i] + b0;
+        for (uint32_t t = threadIdx.x; t < ca; t += OPEN_THREADS) { s_key[t] = ak[t]; s_val[t] = av[t]; }
+        for (uint32_t t = threadIdx.x; t < cb; t += OPEN_THREADS) { s_key[ca + t] = bk[t]; s_val[ca + t] = bv[t]; }
+        __syncthreads();
+        const uint32_t cnt = ca + cb;
+        const uint32_t my0 = min(threadIdx.x * ITEMS, cnt), my1 = min(my0 + ITEMS, cnt);
+        uint32_t pa = merge_path(s_key, ca, s_key + ca, cb, my0);
+        uint32_t pb = my0 - pa;
+        const uint32_t k = ia.k_pop[i];
+        const uint32_t pop_base = pop_off_next[i], open_base = open_off_next[i];
+        for (uint32_t o = my0; o < my1; ++o) {
+            bool take_a;
+            if (pa >= ca) take_a = false;
+            else if (pb >= cb) take_a = true;
+            else take_a = s_key[pa] <= s_key[ca + pb];
+            const uint32_t idx = take_a ? pa : ca + pb;
+            const unsigned long long key = s_key[idx];
+            const uint32_t val = s_val[idx];
+            if (take_a) ++pa; else ++pb;
+            const uint32_t r = d0 + o;
+            if (r < k) {
+                popped_next[pop_base + r] = val;
+                popped_inst_next[pop_base + r] = i;
+                if (r == 0) ia.f_first[i] = key;
+            } else {
+                open_key_next[open_base + r - k] = key;
+                open_val_next[open_base + r - k] = val;
+            }
+        }
+    }
+}
+
+int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
+                    const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
+                    unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
+                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles) {
+    int blocks = min(max_tiles, 148 * 4);
+    k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
+                                            open_off_next, popped_next, popped_inst_next, pop_off_next);
+    return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// End of PathFind.step(): lb, counters, finished(), next iteration's sizes.
+//   gen_mode 0 (A*): num_nodes_generated += popped nodes * A   (base/pathfinding.py:458-459)
+//   gen_mode 1 (Q*): num_nodes_generated += popped edges       (base/pathfinding.py:562-563)
+__global__ void __launch_bounds__(1024)
+k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ pop_off_cur,
+           const uint32_t* __restrict__ pop_off_next, int A, int gen_mode) {
+    __shared__ uint32_t s_unfinished;
+    __shared__ unsigned long long s_gen;
+    if (ctl->error) return;
+    if (threadIdx.x == 0) { s_unfinished = 0; s_gen = 0; }
+    __syncthreads();
+    const int I = ctl->n_inst;
+    uint32_t unfin = 0;
+    unsigned long long gen = 0;
+    for (int i = threadIdx.x; i < I; i += blockDim.x) {
+        if (!ia.active[i]) continue;
+        const uint32_t n_pop = pop_off_cur[i + 1] - pop_off_cur[i];
+        const uint32_t k = ia.k_pop[i];
+        double lb = ia.lb[i];
+        if (k > 0) lb = fmax(__longlong_as_double((long long)ia.f_first[i]), lb);   // graph_search.py:67-69
+        ia.lb[i] = lb;
+        const unsigned long long g_add = gen_mode == 0 ? (unsigned long long)n_pop * A : (unsigned long long)k;
+        ia.gen[i] += g_add;
+        gen += g_add;
+        ia.pop_seq_base[i] += n_pop;
+        const uint32_t itr = ia.itr[i] + 1;
+        ia.itr[i] = itr;
+        const unsigned long long ubk = ia.ub_key[i];
+        bool fin = false;
+        if (ubk != DX_EMPTY64) {
+            const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
+            fin = lb >= __dmul_rn(ia.weight[i], ub);                                // graph_search.py:44
+        }
+        fin = fin || (k == 0);                                                       // itr > 0 holds here (graph_search.py:45)
+        ia.active[i] = fin ? 0 : 1;
+        if (!fin) ++unfin;
+    }
+    atomicAdd(&s_unfinished, unfin);
+    atomicAdd(&s_gen, gen);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        ctl->n_unfinished = s_unfinished;
+        ctl->gen_total += s_gen;
+        ctl->n_pop = pop_off_next[I];
+        ctl->n_children = pop_off_next[I] * (gen_mode == 0 ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
+        ctl->itr += 1;
+        ctl->epoch += 1;
+        ctl->node_base = ctl->node_count;
+    }
+}
+
+int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
+                       int A, int gen_mode) {
+    k_end_iter<<<1, 1024, 0, s>>>(ctl, ia, pop_off_cur, pop_off_next, A, gen_mode);
+    return 1;
+}

@@ -1,0 +1,186 @@
+/*
+ * dxb200.h -- C ABI of libdxb200.so, the B200 (sm_100a) batched heuristic-search engine.
+ *
+ * The reference (forestagostinelli/deepxube) is 100% Python and has no FFI boundary; its boundary for
+ * this path is a set of Python protocols.  Each entry point below names the reference interface it
+ * stands behind (file:line relative to the reference root).  The Python layer in deepxube_b200/
+ * binds these with ctypes (see INTEGRATION.md for the stub a reference maintainer would add).
+ *
+ * Conventions: every function returns DX_OK (0) or a negative error code; dx_last_error() gives the
+ * message for the calling thread's last failure.  All pointers are HOST pointers to caller-owned
+ * memory unless the name ends in _dev.  The engine owns all device memory and one CUDA stream; calls
+ * on one engine must not overlap (the reference's PathFind objects are single-threaded too).
+ *
+ * State rows are packed uint8:
+ *   cube3      54 bytes, sticker colours 0..5          (deepxube/domains/cube3.py:14-29, 502-503)
+ *   npuzzle.d  d*d bytes, tile numbers, 0 = blank      (deepxube/domains/npuzzle.py:18-33, 63-73)
+ *   grid.d     2 bytes (robot_x, robot_y)              (deepxube/domains/grid.py:24-35)
+ * Goal rows have the same layout as state rows (for npuzzle a goal byte equal to d*d is a wildcard,
+ * npuzzle.py:154-158).
+ */
+#ifndef DXB200_H
+#define DXB200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define DX_OK 0
+#define DX_ERR_ARG (-1)        /* bad argument                                   */
+#define DX_ERR_CUDA (-2)       /* CUDA runtime failure                           */
+#define DX_ERR_CAPACITY (-3)   /* node store / OPEN / batch capacity exceeded    */
+#define DX_ERR_STATE (-4)      /* call not valid in the engine's current state   */
+#define DX_ERR_UNSUPPORTED (-5)
+
+enum dx_domain { DX_DOMAIN_CUBE3 = 0, DX_DOMAIN_NPUZZLE = 1, DX_DOMAIN_GRID = 2 };
+
+/* graph_v = batch weighted A* (deepxube/pathfinding/graph_search.py:182-194),
+ * graph_q = batch weighted Q* (graph_search.py:197-209). */
+enum dx_algo { DX_ALGO_GRAPH_V = 0, DX_ALGO_GRAPH_Q = 1 };
+
+/* Where heuristic values come from:
+ *   ZERO      the all-zero default functions (deepxube/base/pathfind_fns.py:205-210, 235-243)
+ *   HOST      any HeurVFn / HeurQFn callable on the host (base/pathfind_fns.py:20-31): the iteration is
+ *             split in dx_step_begin / dx_step_end around the host call
+ *   NET_FP32  resnet_fc on the device, fp32 CUDA-core GEMMs (parity mode)
+ *   NET_BF16  resnet_fc on the device, tcgen05 bf16 tensor-core GEMMs with fp32 accumulation */
+enum dx_heur_mode { DX_HEUR_ZERO = 0, DX_HEUR_HOST = 1, DX_HEUR_NET_FP32 = 2, DX_HEUR_NET_BF16 = 3 };
+
+typedef struct dx_engine dx_engine;
+
+typedef struct dx_config {
+    int32_t device;          /* CUDA device ordinal                                                      */
+    int32_t domain;          /* enum dx_domain                                                           */
+    int32_t domain_dim;      /* npuzzle: side d (2..15); grid: side d (1..255); cube3: ignored           */
+    int32_t algo;            /* enum dx_algo                                                             */
+    int32_t heur_mode;       /* enum dx_heur_mode                                                        */
+    int32_t max_instances;   /* capacity: instances alive in the engine at once                          */
+    int32_t max_pop_total;   /* capacity: sum over instances of their batch sizes (nodes popped / iter)  */
+    int32_t reserved0;
+    int64_t max_nodes;       /* capacity: nodes stored (A*: kept children; Q*: all generated children)   */
+    int64_t max_open;        /* capacity: OPEN entries (A*: <= max_nodes; Q*: edges); 0 = derive         */
+    int32_t reserved[8];
+} dx_config;
+
+/* resnet_fc.<H>H_<B>B[_bn] (deepxube/nnets/resnet_fc.py:19-52).  The weight blob is float32, in this
+ * order (all nn.Linear weights row-major [out, in] exactly as in the state_dict):
+ *   heur.0.weight [H, in_count*one_hot_depth], heur.0.bias [H],
+ *   for each block b, for each layer j in {0,1}:
+ *       ...layers.j.0.weight [H,H], ...layers.j.0.bias [H],
+ *       if batch_norm: ...layers.j.1.weight(gamma) [H], .bias(beta) [H], .running_mean [H], .running_var [H]
+ *   heur.2.weight [out_dim, H], heur.2.bias [out_dim]
+ * Eval-mode batch norm (eps 1e-5) is folded into the preceding Linear at load time. */
+typedef struct dx_net_desc {
+    int32_t in_count;        /* integer inputs per state (cube3 54, npuzzle d*d, grid 4)                 */
+    int32_t one_hot_depth;   /* cube3 6, npuzzle d*d, grid d                                             */
+    int32_t res_dim;         /* H                                                                        */
+    int32_t num_blocks;      /* B                                                                        */
+    int32_t out_dim;         /* 1 (heurv) or number of actions (heurq_fixout)                            */
+    int32_t batch_norm;      /* 0 / 1                                                                    */
+} dx_net_desc;
+
+/* Per-instance view, the fields of Instance / InstanceGraph the callers read
+ * (deepxube/base/pathfinding.py:132-184, pathfinding/graph_search.py:20-46). */
+typedef struct dx_inst_status {
+    double lb;                    /* InstanceGraph.lb                                                    */
+    double ub;                    /* InstanceGraph.ub (inf while no goal node)                           */
+    int64_t num_nodes_generated;  /* Instance.num_nodes_generated                                        */
+    int64_t open_size;            /* frontier_size()                                                     */
+    int64_t goal_node;            /* node id of goal_node, -1 if none                                    */
+    int32_t itr;                  /* Instance.itr                                                        */
+    int32_t finished;             /* Instance.finished()                                                 */
+    int32_t num_curr;             /* len(_nodes_curr): nodes that the next step will pop/expand          */
+    int32_t reserved;
+} dx_inst_status;
+
+/* Device-side counters of the last dx_run / step, for bench.py's accounting. */
+typedef struct dx_counters {
+    int64_t nodes_stored;         /* nodes in the node store                                             */
+    int64_t heur_evals;           /* states evaluated by the heuristic (device net or host callback)     */
+    int64_t children_generated;   /* sum of num_nodes_generated over all instances                       */
+    int64_t iterations;           /* PathFind.itr                                                        */
+    int64_t kernel_launches;      /* CUDA kernels launched by the engine since creation                  */
+    int64_t reserved[3];
+} dx_counters;
+
+const char* dx_last_error(void);
+int dx_version(void);
+
+/* PathFind.__init__ (deepxube/base/pathfinding.py:219-228) + GraphSearch.__init__ (graph_search.py:87-92). */
+int dx_engine_create(const dx_config* cfg, dx_engine** out);
+int dx_engine_destroy(dx_engine* e);
+/* Drops all instances and search state; keeps buffers and loaded weights (a fresh PathFind per
+ * problem instance, deepxube/_solve.py:146-147, without re-allocating). */
+int dx_engine_reset(dx_engine* e);
+
+/* load_nnet + nnet.eval() (deepxube/pytorch/nnet_utils.py:44-62, factories/pathfind_fns_factory.py:98-104). */
+int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats);
+
+/* make_instances + add_instances (graph_search.py:94-109,142-145,161-166; base/pathfinding.py:242-243).
+ * states [n, state_bytes], goals [n, state_bytes]; batch_sizes / weights per instance (may be NULL:
+ * 1 / 1.0).  Root values are computed on the device for ZERO / NET modes; in HOST mode the caller
+ * passes them in root_vals ([n] for graph_v, [n, A] for graph_q; may be NULL for graph_v). */
+int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
+                     const int32_t* batch_sizes, const double* weights, const float* root_vals);
+
+/* PathFind.step() repeated (base/pathfinding.py:338-400, 471-525): runs until every instance is
+ * finished() or max_iters steps were taken.  ZERO / NET modes only.  *iters_done = steps taken. */
+int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done);
+
+/* HOST heuristic mode: one step() split around the host callable.
+ *   dx_step_begin   pop/is_solved/record_goal/expand/closed filter (A*) or filter/edges/push/pop/next_state (Q*);
+ *                   *n_pending = number of states that need values
+ *   dx_get_pending  copies those states [n_pending, state_bytes] and their goals to the host
+ *   dx_step_end     takes h [n_pending] (graph_v) or q [n_pending, A] (graph_q), float32, already clipped,
+ *                   and finishes the step (costs, push, pop, lb, finished, itr) */
+int dx_step_begin(dx_engine* e, int64_t* n_pending);
+int dx_get_pending(dx_engine* e, uint8_t* states, uint8_t* goals, int64_t cap);
+int dx_step_end(dx_engine* e, const float* vals, int64_t n);
+
+int dx_num_instances(dx_engine* e);
+int dx_all_finished(dx_engine* e, int32_t* out);
+int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap);
+int dx_get_counters(dx_engine* e, dx_counters* out);
+
+/* get_path (base/pathfinding.py:93-120): device-side parent walk from goal_node.  actions [cap],
+ * states_on_path [(cap+1), state_bytes] (may be NULL).  *len = number of actions (path length). */
+int dx_get_path(dx_engine* e, int32_t inst, int32_t* actions, uint8_t* states_on_path, int32_t cap, int32_t* len);
+
+/* Instance.get_nodes() (base/pathfinding.py:147-148): the nodes the next step will expand, in pop order.
+ * states [cap, state_bytes], g [cap], h [cap]; *n = count. */
+int dx_get_curr_nodes(dx_engine* e, int32_t inst, uint8_t* states, float* g, float* h, int32_t cap, int32_t* n);
+
+/* Stand-alone domain kernels on host buffers (the domain mixin API):
+ *   ActsEnum.expand (base/domain.py:288-312): children [n*A, state_bytes], child i*A+a
+ *   Domain.next_state (cube3.py:583-596, npuzzle.py:87-110, grid.py:74-86)
+ *   Domain.is_solved (cube3.py:514-517, npuzzle.py:154-158, grid.py:68-69) */
+int dx_domain_info(int32_t domain, int32_t dim, int32_t* state_bytes, int32_t* num_actions, int32_t* in_count,
+                   int32_t* one_hot_depth);
+int dx_expand(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, int64_t n, uint8_t* children);
+int dx_next_state(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, const int32_t* actions, int64_t n,
+                  uint8_t* next);
+int dx_is_solved(int32_t device, int32_t domain, int32_t dim, const uint8_t* states, const uint8_t* goals, int64_t n,
+                 uint8_t* solved);
+
+/* HeurVFn / HeurQFn with the loaded network (base/pathfind_fns.py:196-227, pathfind_fns/fns_core.py:60-90,
+ * pytorch/nnet_utils.py:73-111): out [n, out_dim] float32, clipped at 0.  Uses the engine's heur_mode
+ * precision (NET_FP32 or NET_BF16). */
+int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* goals, int64_t n, float* out);
+
+/* Bench / profiling helpers: same network evaluation with inputs and outputs resident on the device.
+ * dev_states: [n, row_bytes] engine row layout (see dx_row_bytes); returns milliseconds of device time
+ * measured with CUDA events on the engine's stream over `reps` back-to-back evaluations. */
+int dx_row_bytes(dx_engine* e, int32_t* row_bytes);
+int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_total);
+/* Device time (ms, CUDA events on the engine stream) spent per pipeline stage since the last reset:
+ * [0] expand, [1] closed filter, [2] scan+scatter, [3] heuristic, [4] sort, [5] merge/pop, [6] bookkeeping.
+ * Only collected when dx_set_profiling(e, 1) was called (adds event records, no syncs). */
+int dx_set_profiling(dx_engine* e, int32_t on);
+int dx_get_stage_ms(dx_engine* e, float* ms, int32_t cap);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DXB200_H */

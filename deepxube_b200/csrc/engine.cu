@@ -338,7 +338,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     A_(e->node_state, N * e->SP); A_(e->node_g, N); A_(e->node_h, N); A_(e->node_parent, N); A_(e->node_action, N);
     if (e->is_q) A_(e->node_q, N * e->A);
     size_t hcap = 1024;
-    while (hcap < 2 * N) hcap <<= 1;
+    while (hcap < 2 * (N + C)) hcap <<= 1;   // load factor <= 0.5 even with a full node store and a full batch in flight
     e->closed.mask = (uint32_t)(hcap - 1);
     A_(e->closed.slot_key, hcap); A_(e->closed.slot_g, hcap); A_(e->closed.slot_head, hcap);
     if (!e->is_q) { A_(e->child_state, C * e->SP); A_(e->child_g, C); }

@@ -46,7 +46,9 @@ __device__ __forceinline__ uint32_t closed_find_or_claim(const ClosedDev& c, con
     const uint32_t tag = (uint32_t)(h >> 32);
     uint32_t i = (uint32_t)h & c.mask;
     const unsigned long long mine = ((unsigned long long)tag << 32) | claim_rep;
-    while (true) {
+    // the table holds >= 2x (max_nodes + max items per batch) slots, so a probe sequence always ends;
+    // the bound only guards against a corrupted table (never spin forever on the device)
+    for (uint32_t probes = 0; probes <= c.mask; ++probes) {
         unsigned long long k = *((volatile unsigned long long*)&c.slot_key[i]);
         if (k == DX_EMPTY64) {
             unsigned long long old = atomicCAS(&c.slot_key[i], DX_EMPTY64, mine);
@@ -61,6 +63,7 @@ __device__ __forceinline__ uint32_t closed_find_or_claim(const ClosedDev& c, con
         }
         i = (i + 1) & c.mask;
     }
+    return DX_NIL;
 }
 
 // Root of an A* instance: CLOSED[root] = 0.0 (graph_search.py:119-121).
@@ -69,7 +72,7 @@ __global__ void k_closed_seed(DomainDev d, ClosedDev c, const uint8_t* __restric
         const uint32_t id = first + t;
         const uint4* row = reinterpret_cast<const uint4*>(node_state + (size_t)id * d.SP);
         uint32_t i = closed_find_or_claim(c, row, d.SP / 16, id, node_state, node_state, d.SP);
-        c.slot_g[i] = 0.0f;
+        if (i != DX_NIL) c.slot_g[i] = 0.0f;
     }
 }
 
@@ -115,6 +118,7 @@ k_closed_link(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, uint32_t* __
         const uint32_t claim = v.item_node ? v.item_node[ci] : (DX_PENDING | ci);
         const uint32_t i = closed_find_or_claim(c, row, chunks, claim, v.node_state, v.batch_rows, v.SP);
         child_slot[ci] = i;
+        if (i == DX_NIL) { atomicOr((uint32_t*)&ctl->error, DX_DEVERR_NODES); continue; }
         unsigned long long old = *((volatile unsigned long long*)&c.slot_head[i]);
         while (true) {
             const uint32_t next = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;

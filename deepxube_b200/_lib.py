@@ -16,7 +16,7 @@ LIB_PATH = os.path.join(HERE, "libdxb200.so")
 DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2}
 DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q = 0, 1
 DX_HEUR_ZERO, DX_HEUR_HOST, DX_HEUR_NET_FP32, DX_HEUR_NET_BF16 = 0, 1, 2, 3
-STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book"]
+STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book", "gemm_hidden", "gemm_input"]
 
 
 class DxError(RuntimeError):
@@ -79,6 +79,8 @@ SIGNATURES = {
     "dx_bench_heur": (C.c_int, [_engp, C.c_int64, C.c_int32, _f32p]),
     "dx_set_profiling": (C.c_int, [_engp, C.c_int32]),
     "dx_get_stage_ms": (C.c_int, [_engp, _f32p, C.c_int32]),
+    "dx_get_stage_calls": (C.c_int, [_engp, C.POINTER(C.c_int64), C.c_int32]),
+    "dx_last_run_ms": (C.c_int, [_engp, _f32p]),
 }
 
 _lib = None
@@ -277,9 +279,19 @@ class Engine:
         check(self._lib.dx_set_profiling(self._h, 1 if on else 0))
 
     def stage_ms(self) -> dict:
-        arr = (C.c_float * 8)()
-        check(self._lib.dx_get_stage_ms(self._h, arr, 8))
+        arr = (C.c_float * 16)()
+        check(self._lib.dx_get_stage_ms(self._h, arr, 16))
         return {k: arr[i] for i, k in enumerate(STAGE_NAMES)}
+
+    def stage_calls(self) -> dict:
+        arr = (C.c_int64 * 16)()
+        check(self._lib.dx_get_stage_calls(self._h, arr, 16))
+        return {k: arr[i] for i, k in enumerate(STAGE_NAMES)}
+
+    def last_run_ms(self) -> float:
+        ms = C.c_float()
+        check(self._lib.dx_last_run_ms(self._h, C.byref(ms)))
+        return ms.value
 
 
 def pack_state_dict(sd: dict) -> Tuple[np.ndarray, dict]:

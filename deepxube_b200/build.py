@@ -54,7 +54,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         failed = failed or pr.returncode != 0
     if failed:
         raise RuntimeError("nvcc failed")
-    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart", "-lcuda"]
+    cmd = [_nvcc(), "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a", "-lcudart"]
     subprocess.check_call(cmd)
     with open(stamp_file, "w") as f:
         f.write(stamp)

@@ -21,6 +21,12 @@
 
 void dx_set_error(const std::string& msg);
 
+// optional per-kernel timing (CUDA events on the engine stream); no-ops unless profiling is on
+#define DX_ST_GEMM_RES 7     // hidden-layer tensor-core / fp32 GEMM launches
+#define DX_ST_GEMM_IN 8      // input-layer launches (one-hot + first GEMM, or the gather kernel)
+void dx_prof_begin(int stage);
+void dx_prof_end();
+
 #define DX_CUDA(call)                                                                          \
     do {                                                                                       \
         cudaError_t _e = (call);                                                               \
@@ -101,6 +107,7 @@ struct NetDev {
     // bf16 copies for the tensor-core path
     void* w0_bf16;   // [Hp, in_dim_p]  K-major
     void* wres_bf16; // [num_blocks*2, Hp, Hp] K-major
+    void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16
 };
 
 static inline int dx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -227,3 +234,4 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
                       const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
                        const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
+int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, void** plan_out);

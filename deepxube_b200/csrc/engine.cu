@@ -157,7 +157,7 @@ __global__ void k_gather_f32(const float* src, const uint32_t* ids, int n, float
 }
 
 // ---------------------------------------------------------------------------------------------
-enum { ST_EXPAND = 0, ST_CLOSED, ST_SCATTER, ST_HEUR, ST_SORT, ST_MERGE, ST_BOOK, ST_COUNT };
+enum { ST_EXPAND = 0, ST_CLOSED, ST_SCATTER, ST_HEUR, ST_SORT, ST_MERGE, ST_BOOK, ST_GEMM_RES = DX_ST_GEMM_RES, ST_GEMM_IN = DX_ST_GEMM_IN, ST_COUNT };
 
 struct dx_engine {
     dx_config cfg;
@@ -201,6 +201,9 @@ struct dx_engine {
     std::vector<cudaEvent_t> ev;       // pairs
     std::vector<int> ev_stage;
     float stage_ms[ST_COUNT] = {0};
+    long long stage_calls[ST_COUNT] = {0};
+    cudaEvent_t run_ev[2] = {nullptr, nullptr};
+    float last_run_ms = 0.f;
 
     template <typename T> int alloc(T** p, size_t count) {
         void* q = nullptr;
@@ -239,12 +242,18 @@ static void stage_collect(dx_engine* e) {
         float ms = 0;
         cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
         e->stage_ms[e->ev_stage[i / 2]] += ms;
+        e->stage_calls[e->ev_stage[i / 2]] += 1;
         cudaEventDestroy(e->ev[i]);
         cudaEventDestroy(e->ev[i + 1]);
     }
     e->ev.clear();
     e->ev_stage.clear();
 }
+
+// kernel-level timing hooks used by the network launchers (nested inside the ST_HEUR stage)
+static thread_local dx_engine* g_prof_engine = nullptr;
+void dx_prof_begin(int stage) { if (g_prof_engine) stage_begin(g_prof_engine, stage); }
+void dx_prof_end() { if (g_prof_engine) stage_end(g_prof_engine); }
 
 static int sync_ctl(dx_engine* e) {
     DX_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
@@ -282,6 +291,7 @@ static int reset_state(dx_engine* e) {
     e->parity = 0;
     e->pending = false;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    memset(e->stage_calls, 0, sizeof(e->stage_calls));
     return DX_OK;
 }
 
@@ -392,6 +402,7 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
 // heuristic for the current job (ctl->nn_row_start / nn_n) over node-store rows
 static int launch_heur_nodes(dx_engine* e, long long max_rows) {
     const int mode = e->cfg.heur_mode;
+    g_prof_engine = e->profiling ? e : nullptr;
     if (mode == DX_HEUR_ZERO) {
         k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->node_h, e->node_q, e->A);
         e->launches += 1;
@@ -627,11 +638,16 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     DX_TRY(need_net(e));
     int done = 0;
     DX_TRY(sync_ctl(e));
+    if (!e->run_ev[0]) { cudaEventCreate(&e->run_ev[0]); cudaEventCreate(&e->run_ev[1]); }
+    cudaEventRecord(e->run_ev[0], e->stream);
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         DX_TRY(full_step(e));
         ++done;
         DX_TRY(sync_ctl(e));
     }
+    cudaEventRecord(e->run_ev[1], e->stream);
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    cudaEventElapsedTime(&e->last_run_ms, e->run_ev[0], e->run_ev[1]);
     stage_collect(e);
     DX_CUDA(cudaGetLastError());
     if (iters_done) *iters_done = done;
@@ -984,6 +1000,7 @@ extern "C" int dx_set_profiling(dx_engine* e, int32_t on) {
     stage_collect(e);
     e->profiling = on != 0;
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
+    memset(e->stage_calls, 0, sizeof(e->stage_calls));
     return DX_OK;
 }
 
@@ -991,6 +1008,19 @@ extern "C" int dx_get_stage_ms(dx_engine* e, float* ms, int32_t cap) {
     if (!e || !ms) DX_FAIL(DX_ERR_ARG, "null argument");
     stage_collect(e);
     for (int i = 0; i < std::min<int>(cap, ST_COUNT); ++i) ms[i] = e->stage_ms[i];
+    return DX_OK;
+}
+
+extern "C" int dx_get_stage_calls(dx_engine* e, int64_t* calls, int32_t cap) {
+    if (!e || !calls) DX_FAIL(DX_ERR_ARG, "null argument");
+    stage_collect(e);
+    for (int i = 0; i < std::min<int>(cap, ST_COUNT); ++i) calls[i] = e->stage_calls[i];
+    return DX_OK;
+}
+
+extern "C" int dx_last_run_ms(dx_engine* e, float* ms) {
+    if (!e || !ms) DX_FAIL(DX_ERR_ARG, "null argument");
+    *ms = e->last_run_ms;
     return DX_OK;
 }
 
@@ -1070,7 +1100,9 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     e->mlp.cap = cap;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
         for (int i = 0; i < 3; ++i) { uint16_t* q = nullptr; DX_TRY(e->alloc(&q, (size_t)cap * Hp)); e->mlp.xb[i] = q; }
-        DX_TRY(e->alloc(&e->mlp.x[0], (size_t)cap * Hp));     // fp32 copy of the last activation for the output layer
+        uint16_t* onehot = nullptr;
+        DX_TRY(e->alloc(&onehot, (size_t)cap * in_dim_p));
+        DX_TRY(dx_mlp_bf16_prepare(net, e->mlp, onehot, &net.tc_plan));
     } else {
         for (int i = 0; i < 3; ++i) DX_TRY(e->alloc(&e->mlp.x[i], (size_t)cap * Hp));
     }

@@ -195,8 +195,12 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
     for (int b = 0; b < net.num_blocks; ++b) {
         const float* w1 = net.wres + (size_t)(2 * b) * Hp * Hp;
         const float* w2 = net.wres + (size_t)(2 * b + 1) * Hp * Hp;
+        dx_prof_begin(DX_ST_GEMM_RES);
         k_sgemm_bias_act<<<grid, 256, 0, s>>>(x, w1, net.bres + (size_t)(2 * b) * Hp, nullptr, y, ctl, Hp, Hp, 1);
+        dx_prof_end();
+        dx_prof_begin(DX_ST_GEMM_RES);
         k_sgemm_bias_act<<<grid, 256, 0, s>>>(y, w2, net.bres + (size_t)(2 * b + 1) * Hp, x, z, ctl, Hp, Hp, 1);
+        dx_prof_end();
         float* t = x; x = z; z = t;
         launches += 2;
     }

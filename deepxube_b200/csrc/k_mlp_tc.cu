@@ -385,6 +385,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     if (max_rows > mb.cap) max_rows = mb.cap;
     int launches = 0;
     const int oh_blocks = (int)min((long long)dx_div_up(max_rows * (net.in_dim_p / 8), 256), (long long)148 * 16);
+    dx_prof_begin(DX_ST_GEMM_IN);
     k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ctl, rows, goals, p->onehot);
     ++launches;
     __nv_bfloat16* x = (__nv_bfloat16*)mb.xb[0];
@@ -394,9 +395,14 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const int Hp = net.Hp;
     launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, net.b0, nullptr, x, 0);
     ++launches;
+    dx_prof_end();
     for (int b = 0; b < net.num_blocks; ++b) {
+        dx_prof_begin(DX_ST_GEMM_RES);
         launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, net.bres + (size_t)(2 * b) * Hp, nullptr, y, 1);
+        dx_prof_end();
+        dx_prof_begin(DX_ST_GEMM_RES);
         launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, x, z, 1);
+        dx_prof_end();
         launches += 2;
         __nv_bfloat16* tp = x; x = z; z = tp;
         int ti = ix; ix = iz; iz = ti;

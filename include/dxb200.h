@@ -179,6 +179,11 @@ int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_total);
  * Only collected when dx_set_profiling(e, 1) was called (adds event records, no syncs). */
 int dx_set_profiling(dx_engine* e, int32_t on);
 int dx_get_stage_ms(dx_engine* e, float* ms, int32_t cap);
+/* Same indexing plus [7] hidden-layer GEMM launches and [8] input-layer launches (both nested inside [3]):
+ * number of timed intervals per entry, so that ms / calls = average launch duration. */
+int dx_get_stage_calls(dx_engine* e, int64_t* calls, int32_t cap);
+/* Device time (ms, CUDA events on the engine stream) of the last dx_run call. */
+int dx_last_run_ms(dx_engine* e, float* ms);
 
 #ifdef __cplusplus
 }

@@ -1,0 +1,203 @@
+"""GPU tests through the reference-facing Python API (registries -> PathFind -> libdxb200).
+Mirrors of the reference's own tests: tests/test_bruteforce.py (search correctness with the zero
+heuristic, several instances in one PathFind), tests/test_domains.py (expand == next_state over the
+actions; reverse actions), plus the `solve` entry point on the tutorial known-answer set."""
+import os
+import pickle
+import random
+import sys
+
+import numpy as np
+import pytest
+
+import deepxube_b200  # noqa: F401
+from deepxube_b200 import compat_pickle
+from deepxube_b200.base.pathfind_fns import PFNsHeurQ, PFNsHeurV
+from deepxube_b200.base.pathfinding import get_path
+from deepxube_b200.factories.domain_factory import get_domain_from_arg
+from deepxube_b200.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict
+from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+from deepxube_b200.pathfind_fns.fns_core import PFNsHeurQC, PFNsHeurVC
+from deepxube_b200.pathfinding.utils import is_valid_soln
+
+import golden_utils as gu
+from oracle.pseudo_heur import make_pseudo_q, pseudo_v
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("fn_name", ["heurv", "heurq_fixout"])
+@pytest.mark.parametrize("pathfind_arg", ["graph", "graph.10B"])
+def test_bruteforce(fn_name, pathfind_arg):
+    """reference tests/test_bruteforce.py:26-58"""
+    random.seed(0)
+    dom, name = get_domain_from_arg("cube3")
+    states, goals = dom.sample_problem_instances([0, 1, 2] * 3)
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [fn_name])
+    pathfind, _, _ = get_pathfind_from_arg(dom, pfns, pathfind_arg)
+    pathfind.add_instances(pathfind.make_instances(states, goals, None, True))
+    for _ in range(200):
+        pathfind.step()
+    solved = []
+    for inst, s, g in zip(pathfind.instances, states, goals):
+        if inst.goal_node is not None:
+            _, actions, _, cost = get_path(inst.goal_node)
+            solved.append(is_valid_soln(s, g, actions, dom))
+            assert cost == len(actions) <= 2
+        else:
+            solved.append(False)
+    assert 100 * np.mean(solved) == 100
+    pathfind.close()
+
+
+@pytest.mark.parametrize("domain_str", ["cube3", "npuzzle.4", "npuzzle.3", "grid.7d"])
+def test_expand_equals_next_state(domain_str):
+    """reference tests/test_domains.py::test_expand"""
+    random.seed(1)
+    dom, _ = get_domain_from_arg(domain_str)
+    states, goals = dom.sample_problem_instances(list(range(0, 20)))
+    children, actions_l, tcs_l = dom.expand(states)
+    assert dom.is_solved(states[:1], goals[:1]) == [True]
+    for s, ch, acts, tcs in zip(states, children, actions_l, tcs_l):
+        nxt, tc2 = dom.next_state([s] * len(acts), acts)
+        assert {c: t for c, t in zip(ch, tcs)} == {c: t for c, t in zip(nxt, tc2)}
+        assert all(a == b for a, b in zip(ch, nxt))
+
+
+def test_actsrev_cube3():
+    """reference tests/test_domains.py::test_actsrev: next_state(sample_rev_state(s)) == s"""
+    random.seed(2)
+    dom, _ = get_domain_from_arg("cube3")
+    states, _ = dom.sample_problem_instances([10] * 20)
+    prev, acts_rev, tcs = dom.sample_rev_state(states)
+    back, _ = dom.next_state(prev, acts_rev)
+    assert all(a == b for a, b in zip(back, states)) and tcs == [1.0] * 20
+
+
+def test_user_callable_heuristic_host_mode():
+    """Any HeurVFn / HeurQFn callable is accepted (base/pathfind_fns.py:20-31): user lambdas go through the
+    host-callback mode and must give the oracle's results for the same function."""
+    from oracle.domains_np import OracleDomain
+    from oracle.search import OracleSearch
+    random.seed(3)
+    dom, _ = get_domain_from_arg("cube3")
+    states, goals = dom.sample_problem_instances([20, 40, 60])
+    rows, grows = dom.states_to_rows(states), dom.goals_to_rows(goals)
+    for is_q in (False, True):
+        if is_q:
+            fq = make_pseudo_q(12)
+            pfns = PFNsHeurQC(heurq=lambda s, g, a, c: fq(dom.states_to_rows(s)).tolist())
+        else:
+            pfns = PFNsHeurVC(heurv=lambda s, g, c: pseudo_v(dom.states_to_rows(s)).tolist())
+        pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.200B_0.6W")
+        assert pname == ("graph_q" if is_q else "graph_v")
+        pathfind.add_instances(pathfind.make_instances(states, goals))
+        orc = OracleSearch(OracleDomain("cube3"), make_pseudo_q(12) if is_q else pseudo_v, is_q, 200, 0.6)
+        oi = orc.add_instances(rows, grows)
+        for _ in range(6):
+            pathfind.step()
+            orc.step()
+        for inst, o in zip(pathfind.instances, oi):
+            assert (inst.num_nodes_generated, inst.itr, inst.lb, inst.ub) == (o.num_nodes_generated, o.itr, o.lb, o.ub)
+            got = dom.states_to_rows([n.state for n in inst.get_nodes()])
+            assert np.array_equal(got, o.store.state[o.nodes_curr])
+        pathfind.close()
+
+
+def test_solve_cli_reproduces_tutorial_kat(tmp_path):
+    """`solve --domain cube3 --fn heurv,resnet_fc.200H_2B_bn,<heur.pt> --pathfind graph.100B_0.1W --file hard.pkl`
+    (the exact command of tutorial/cube3/results_heur_hard/output.txt:1) against the reference's results.pkl."""
+    from deepxube_b200 import _cli
+    dom, name = get_domain_from_arg("cube3")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.200H_2B_bn"])
+    pfns.heurv.nnet.load_state_dict(gu.state_dict_np("cube3v"))
+    pt = str(tmp_path / "heur.pt")
+    pfns.heurv.nnet.save(pt)
+    res_dir = str(tmp_path / "results")
+    argv, stdout = sys.argv, sys.stdout
+    sys.argv = ["deepxube_b200", "solve", "--domain", "cube3", "--fn", f"heurv,resnet_fc.200H_2B_bn,{pt}", "--pathfind",
+                "graph.100B_0.1W", "--file", os.path.join(gu.GOLDEN, "ref_cube3_hard.pkl"), "--results", res_dir, "--redo"]
+    try:
+        _cli.main()
+    finally:
+        sys.argv, sys.stdout = argv, stdout
+    mine = pickle.load(open(os.path.join(res_dir, "results.pkl"), "rb"))
+    ref = compat_pickle.load(os.path.join(gu.GOLDEN, "ref_cube3_results_heur_hard.pkl"))
+    assert mine["path_costs"] == ref["path_costs"] and mine["num_nodes_generated"] == ref["num_nodes_generated"]
+    assert mine["iterations"] == ref["iterations"] and mine["solved"] == ref["solved"]
+    assert [[a.action for a in al] for al in mine["actions"]] == [[a.action for a in al] for al in ref["actions"]]
+    assert all(np.array_equal(np.stack([s.colors for s in m]), np.stack([s.colors for s in r]))
+               for m, r in zip(mine["states_on_path"], ref["states_on_path"]))
+    out = open(os.path.join(res_dir, "output.txt")).read()
+    assert "State: 9, SolnCost: 48.00, # Nodes Gen: 93,756, Itrs: 80" in out and "Means - SolnCost: 56.70" in out
+    # resume: a second run without --redo has nothing left to do and keeps the results
+    sys.argv = [a for a in sys.argv if a != "--redo"]
+    argv2 = ["deepxube_b200", "solve", "--domain", "cube3", "--fn", f"heurv,resnet_fc.200H_2B_bn,{pt}", "--pathfind",
+             "graph.100B_0.1W", "--file", os.path.join(gu.GOLDEN, "ref_cube3_hard.pkl"), "--results", res_dir]
+    sys.argv = argv2
+    try:
+        _cli.main()
+    finally:
+        sys.argv, sys.stdout = argv, stdout
+    again = pickle.load(open(os.path.join(res_dir, "results.pkl"), "rb"))
+    assert again["path_costs"] == ref["path_costs"] and len(again["actions"]) == 10
+
+
+def test_device_heur_callable_matches_reference_values():
+    """The heurv callable built by `--fn heurv,resnet_fc...` is usable on its own (HeurVFn protocol)."""
+    dom, name = get_domain_from_arg("grid.7d")
+    z = gu.load("nnet")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, ["heurq_fixout,resnet_fc.100H_1B_bn"], nnet_batch_size=17)
+    pfns.heurq.nnet.load_state_dict(gu.state_dict_np("gridq"))
+    states = dom.rows_to_states(z["gridv_states"])
+    from deepxube_b200.domains.grid import GridGoal
+    goals = [GridGoal(int(r[0]), int(r[1])) for r in z["gridv_goals"]]
+    q = np.array(pfns.heurq(states, goals, dom.get_state_actions(states), [None] * len(states)))
+    np.testing.assert_allclose(q, z["gridq_out"], rtol=0, atol=2e-4)
+
+
+@pytest.mark.parametrize("tag,dname,dim,q,atol", [("cube3v", "cube3", 0, False, 0.08), ("gridv", "grid", 7, False, 0.05),
+                                                  ("gridq", "grid", 7, True, 0.05), ("np4v", "npuzzle", 4, False, 0.02),
+                                                  ("cube3q", "cube3", 0, True, 0.01)])
+def test_bf16_network_within_tolerance(tag, dname, dim, q, atol):
+    """tcgen05 bf16 path vs the reference's fp32 outputs.  Stated tolerance: |h_bf16 - h_ref| <= 0.08 for the
+    trained cube3 network (outputs up to ~25, i.e. ~0.3 % relative; bf16 has an 8-bit mantissa and the residual
+    stream is kept in bf16)."""
+    from deepxube_b200 import _lib as L
+    z = gu.load("nnet")
+    eng = L.Engine(dname, dim, "graph_q" if q else "graph_v", L.DX_HEUR_NET_BF16, max_instances=4, max_pop_total=256, max_nodes=4096)
+    blob, info = L.pack_state_dict(gu.state_dict_np(tag))
+    eng.load_weights(eng.in_count, eng.depth, info["res_dim"], info["num_blocks"], info["out_dim"], info["batch_norm"], blob)
+    skey = "gridv" if tag.startswith("grid") else tag
+    out = eng.heur_eval(z[skey + "_states"], z["gridv_goals"] if tag.startswith("grid") else None, info["out_dim"])
+    ref = z[tag + "_out"]
+    np.testing.assert_allclose(out if q else out[:, 0], ref, rtol=0, atol=atol)
+    eng.close()
+
+
+def test_bf16_search_deviation_is_reported():
+    """bf16 heuristics cannot promise identical node counts: solutions must stay valid and the
+    deviation of cost / nodes from the fp32 KAT is bounded and printed."""
+    from deepxube_b200 import _lib as L
+    from oracle.domains_np import OracleDomain
+    k = gu.load("kat_cube3")
+    dom = OracleDomain("cube3")
+    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_BF16, max_instances=1, max_pop_total=100, max_nodes=600000)
+    blob, info = L.pack_state_dict(gu.state_dict_np("cube3v"))
+    eng.load_weights(54, 6, info["res_dim"], info["num_blocks"], 1, True, blob)
+    dc, dn = [], []
+    for i in range(10):
+        eng.reset()
+        eng.add_instances(k["hard_states"][i:i + 1], k["hard_goals"][i:i + 1], 100, 0.1)
+        eng.run(100000)
+        s = eng.status()[0]
+        acts, _ = eng.get_path(0)
+        cur = k["hard_states"][i:i + 1]
+        for a in acts:
+            cur = dom.next_state(cur, np.array([a]))
+        assert s.finished and dom.is_solved(cur, k["hard_goals"][i:i + 1])[0]
+        dc.append(len(acts) - k["hard_path_costs"][i])
+        dn.append(s.num_nodes_generated / k["hard_nodes"][i] - 1.0)
+    print(f"bf16 vs fp32 KAT: cost deviation {dc}, nodes-generated deviation {[round(100 * x, 1) for x in dn]} %")
+    assert max(abs(x) for x in dc) <= 6 and max(abs(x) for x in dn) <= 0.35
+    eng.close()

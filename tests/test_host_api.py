@@ -1,0 +1,156 @@
+"""CPU tests of the host-side mirror of the reference's registries / parsers / protocols (no GPU needed).
+Mirrors tests/test_defaults.py and tests/test_compat.py of the reference for the in-scope names."""
+import os
+
+import numpy as np
+import pytest
+
+import deepxube_b200  # noqa: F401
+from deepxube_b200 import compat_pickle
+from deepxube_b200.base.factory import DelimParser, Factory
+from deepxube_b200.factories.domain_factory import domain_factory, get_domain_from_arg
+from deepxube_b200.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict
+from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg, pathfinding_factory
+from deepxube_b200.utils.command_line_utils import get_name_args
+from deepxube_b200.utils.misc_utils import flatten, unflatten
+from deepxube_b200.utils.timing_utils import Times
+
+import golden_utils as gu
+
+
+def test_name_args_split():
+    assert get_name_args("cube3") == ("cube3", None)
+    assert get_name_args("graph.10B_0.5W") == ("graph", "10B_0.5W")
+    assert get_name_args("resnet_fc.1000H_4B_bn") == ("resnet_fc", "1000H_4B_bn")
+
+
+def test_registries_hold_the_hot_path_names():
+    assert set(domain_factory.get_all_class_names()) == {"cube3", "npuzzle", "grid"}
+    assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q"}
+    with pytest.raises(ValueError, match="Unknown domain"):
+        get_domain_from_arg("sokoban")
+    with pytest.raises(ValueError, match="already registered"):
+        domain_factory.register_class("cube3")(object)
+
+
+def test_domain_parsers():
+    d, n = get_domain_from_arg("npuzzle.5")
+    assert n == "npuzzle" and d.dim == 5 and d.get_num_acts() == 4
+    d, n = get_domain_from_arg("grid.7d")
+    assert n == "grid" and d.dim == 7
+    with pytest.raises(ValueError):
+        get_domain_from_arg("grid.7x")
+    d, _ = get_domain_from_arg("cube3")
+    assert d.get_num_acts() == 12 and [repr(a) for a in d.get_actions_fixed()][:4] == ["U-1", "U1", "D-1", "D1"]
+
+
+def test_graph_search_parser_and_defaults():
+    dom, name = get_domain_from_arg("cube3")
+    pfv, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv"])
+    pfq, _ = get_path_fns_nnet_par_dict(dom, name, ["heurq_fixout"])
+    p, pname, full = get_pathfind_from_arg(dom, pfv, "graph.100B_0.1W")
+    assert pname == "graph_v" and full == "graph_v.100B_0.1W" and p.batch_size_default == 100 and p.weight_default == 0.1
+    p, pname, _ = get_pathfind_from_arg(dom, pfq, "graph")
+    assert pname == "graph_q" and (p.batch_size_default, p.weight_default, p.eps_default) == (1, 1.0, 0.0)   # test_defaults.py
+    insts = p.make_instances(*dom.sample_problem_instances([0]))
+    assert (insts[0].batch_size, insts[0].weight, insts[0].eps) == (1, 1.0, 0.0) and insts[0].lb == 0.0 and insts[0].ub == np.inf
+    with pytest.raises(ValueError):
+        get_pathfind_from_arg(dom, pfv, "graph.10X")
+    with pytest.raises(ValueError, match="eps"):
+        get_pathfind_from_arg(dom, pfv, "graph.10B_0.1E")
+    with pytest.raises(ValueError, match="Could not find any compatible"):
+        get_pathfind_from_arg(dom, pfv, "beam.10B")
+    with pytest.raises(TypeError):
+        pathfinding_factory.get_type("graph_q")(dom, pfv)      # PFNsHeurV given to the Q* search
+
+
+@pytest.mark.parametrize("domain_str,fn,ok", [("cube3", "heurv,resnet_fc.100H_1B_bn", True), ("cube3", "heurq_fixout,resnet_fc.100H_1B_bn", True),
+                                              ("grid.7d", "heurv,resnet_fc.100H_1B_bn", True), ("grid.7d", "heurq_fixout,resnet_fc.100H_1B_bn", True),
+                                              ("npuzzle.4", "heurv,resnet_fc.100H_1B_bn", True), ("npuzzle.4", "heurq_fixout,resnet_fc.100H_1B_bn", False)])
+def test_fn_resolution(domain_str, fn, ok):
+    """test_compat.py: every (fn x graph) string combination resolves; npuzzle has no fixed-action input."""
+    dom, name = get_domain_from_arg(domain_str)
+    if not ok:
+        with pytest.raises(ValueError, match="Cannot build fn"):
+            get_path_fns_nnet_par_dict(dom, name, [fn])
+        return
+    pfns, pars = get_path_fns_nnet_par_dict(dom, name, [fn])
+    p, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.10B")
+    assert pname == ("graph_q" if fn.startswith("heurq") else "graph_v")
+    nnet = (pfns.heurq if fn.startswith("heurq") else pfns.heurv).nnet
+    assert nnet.res_dim == 100 and nnet.num_blocks == 1 and nnet.batch_norm
+    assert nnet.out_dim == (dom.get_num_acts() if fn.startswith("heurq") else 1)
+
+
+def test_resnet_fc_state_dict_roundtrip(tmp_path):
+    dom, name = get_domain_from_arg("cube3")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.200H_2B_bn"])
+    nnet = pfns.heurv.nnet
+    nnet.load_state_dict({"module." + k: v for k, v in gu.state_dict_np("cube3v").items()})    # tutorial weights, `module.` prefix
+    f = str(tmp_path / "heur.pt")
+    nnet.save(f)
+    pf2, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.200H_2B_bn"], nnet_files=[f])
+    for k, v in nnet.state_dict().items():
+        assert np.array_equal(pf2.heurv.nnet.state_dict()[k], v)
+    with pytest.raises(RuntimeError, match="size mismatch|missing"):
+        get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.100H_2B_bn"], nnet_files=[f])
+    with pytest.raises(NotImplementedError):
+        get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.100H_2B_wn"])
+
+
+def test_delim_parser_longest_suffix_case_insensitive():
+    class P(DelimParser):
+        def __init__(self):
+            super().__init__()
+            self.add_argument("H", "h", int, "hidden")
+            self.add_argument("bn", "bn", None, "batch norm")
+            self.add_argument("n", "n", int, "n")
+
+        @property
+        def delim(self):
+            return "_"
+    assert P().parse("1000h_BN_3n") == {"h": 1000, "bn": True, "n": 3}
+    with pytest.raises(ValueError):
+        P().parse("12q")
+    assert P().parse("") == {}
+
+
+def test_times_and_flatten():
+    t = Times()
+    t.record_time("heur", 1.5)
+    t.record_time("heur", 0.5)
+    t.record_time("expand", 0.25, path=["sub"])
+    assert t.get_time_str().startswith("heur: 2.00, ->sub: 0.25, Tot: 2.25")
+    flat, split = flatten([[1, 2], [], [3]])
+    assert flat == [1, 2, 3] and split == [2, 2] and unflatten(flat, split) == [[1, 2], [], [3]]
+
+
+def test_reads_reference_pickles():
+    d = compat_pickle.load(os.path.join(gu.GOLDEN, "ref_cube3_hard.pkl"))
+    k = gu.load("kat_cube3")
+    assert type(d["states"][0]).__module__ == "deepxube_b200.domains.cube3"
+    assert np.array_equal(np.stack([s.colors for s in d["states"]]), k["hard_states"])
+    g = compat_pickle.load(os.path.join(gu.GOLDEN, "ref_grid_custom_insts.pkl"))
+    assert type(g["states"][0]).__name__ == "GridState" and hasattr(g["goals"][0], "robot_x")
+    r = compat_pickle.load(os.path.join(gu.GOLDEN, "ref_cube3_results_heur_hard.pkl"))
+    assert r["path_costs"] == k["hard_path_costs"].tolist() and [a.action for a in r["actions"][0]][:3] == [1, 8, 1]
+
+
+def test_problem_instance_generation_is_host_side():
+    """sample_problem_instances only produces INPUTS for the search and runs from the host move tables."""
+    import random
+    random.seed(0)
+    from oracle.domains_np import OracleDomain
+    for dstr, oname, dim in (("cube3", "cube3", 0), ("npuzzle.4", "npuzzle", 4), ("grid.7d", "grid", 7)):
+        dom, _ = get_domain_from_arg(dstr)
+        states, goals = dom.sample_problem_instances([0, 1, 7, 30])
+        assert len(states) == len(goals) == 4
+        rows, grows = dom.states_to_rows(states), dom.goals_to_rows(goals)
+        assert OracleDomain(oname, dim).is_solved(rows[:1], grows[:1])[0]          # 0 steps -> solved
+        walked, acts, costs = dom.random_walk(states[:2], [5, 3])
+        o = OracleDomain(oname, dim)
+        cur = rows[:2].copy()
+        for i, al in enumerate(acts):
+            for a in al:
+                cur[i:i + 1] = o.next_state(cur[i:i + 1], np.array([dom.action_index(a)]))
+        assert np.array_equal(dom.states_to_rows(walked), cur) and costs == [5.0, 3.0]

@@ -200,6 +200,7 @@ struct dx_engine {
     bool profiling = false;
     std::vector<cudaEvent_t> ev;       // pairs
     std::vector<int> ev_stage;
+    std::vector<int> ev_open;
     float stage_ms[ST_COUNT] = {0};
     long long stage_calls[ST_COUNT] = {0};
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
@@ -220,34 +221,42 @@ struct dx_engine {
 
 #define DX_TRY(x) do { int _r = (x); if (_r < 0) return _r; } while (0)
 
+// Timed intervals may nest (kernel-level intervals inside the heuristic stage): begin pushes on a stack,
+// end closes the innermost open interval.
 static void stage_begin(dx_engine* e, int st) {
     if (!e->profiling) return;
     cudaEvent_t a;
     cudaEventCreate(&a);
     cudaEventRecord(a, e->stream);
+    e->ev_open.push_back((int)e->ev.size());
     e->ev.push_back(a);
+    e->ev.push_back(nullptr);
     e->ev_stage.push_back(st);
 }
 static void stage_end(dx_engine* e) {
-    if (!e->profiling) return;
+    if (!e->profiling || e->ev_open.empty()) return;
     cudaEvent_t b;
     cudaEventCreate(&b);
     cudaEventRecord(b, e->stream);
-    e->ev.push_back(b);
+    e->ev[e->ev_open.back() + 1] = b;
+    e->ev_open.pop_back();
 }
 static void stage_collect(dx_engine* e) {
     if (e->ev.empty()) return;
     cudaStreamSynchronize(e->stream);
     for (size_t i = 0; i + 1 < e->ev.size(); i += 2) {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
-        e->stage_ms[e->ev_stage[i / 2]] += ms;
-        e->stage_calls[e->ev_stage[i / 2]] += 1;
+        if (e->ev[i + 1]) {
+            float ms = 0;
+            cudaEventElapsedTime(&ms, e->ev[i], e->ev[i + 1]);
+            e->stage_ms[e->ev_stage[i / 2]] += ms;
+            e->stage_calls[e->ev_stage[i / 2]] += 1;
+            cudaEventDestroy(e->ev[i + 1]);
+        }
         cudaEventDestroy(e->ev[i]);
-        cudaEventDestroy(e->ev[i + 1]);
     }
     e->ev.clear();
     e->ev_stage.clear();
+    e->ev_open.clear();
 }
 
 // kernel-level timing hooks used by the network launchers (nested inside the ST_HEUR stage)
@@ -290,9 +299,7 @@ static int reset_state(dx_engine* e) {
     e->n_inst = 0;
     e->parity = 0;
     e->pending = false;
-    memset(e->stage_ms, 0, sizeof(e->stage_ms));
-    memset(e->stage_calls, 0, sizeof(e->stage_calls));
-    return DX_OK;
+    return DX_OK;      // stage timers are cumulative across resets; dx_set_profiling() clears them
 }
 
 extern "C" int dx_domain_info(int32_t domain, int32_t dim, int32_t* state_bytes, int32_t* num_actions, int32_t* in_count,

@@ -8,7 +8,10 @@
 //   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, into one
 //     of two TMEM accumulator stages (2 x BN columns),
 //   * four epilogue warps drain the other accumulator stage with tcgen05.ld (32 lanes x 32 columns per
-//     instruction), add bias / residual, apply ReLU, and store bf16 rows,
+//     instruction, software-pipelined one chunk ahead), add bias / residual, apply ReLU, and write bf16.
+//     Each warp stages its 32 x 32 chunk in a private, 64-byte-swizzled shared-memory buffer and moves it
+//     with TMA (bulk tensor store; the residual chunk arrives by TMA load two chunks ahead), so every
+//     global access of the epilogue is a full-line transfer instead of 32 strided row accesses,
 //   * persistent CTAs (one per SM) walk the (m, n) tiles; M is read from the device control block.
 // The one-hot input layer is a K = in_dim (padded to 64) GEMM over a bf16 one-hot matrix written by
 // k_onehot_bf16 (exact: the entries are 0 / 1).
@@ -28,6 +31,7 @@ struct TcPlan {
     CUtensorMap a_x[3];
     CUtensorMap b_w0;
     CUtensorMap b_res;
+    CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
     int BN;
     int num_sms;
@@ -60,6 +64,11 @@ __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
@@ -96,15 +105,18 @@ struct TcSmem {
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
     static constexpr int B_BYTES = BN * TC_BK * 2;
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int BAR_OFF = TC_STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFF = TC_STAGES * STAGE_BYTES;
+    static constexpr int EPI_BUF = 32 * 64;              // one 32-row x 32-column bf16 chunk
+    static constexpr int EPI_WARP_BYTES = 4 * EPI_BUF;   // per epilogue warp: 2 output + 2 residual buffers
+    static constexpr int BAR_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
 
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
-k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB, const Ctl* __restrict__ ctl,
-               int w_row0, int K, int N, const float* __restrict__ bias, const __nv_bfloat16* __restrict__ R,
-               __nv_bfloat16* __restrict__ C, int relu) {
+k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
+               const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
+               int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu) {
     extern __shared__ uint8_t smem_raw[];
     using SM = TcSmem<BN>;
     if (ctl->error) return;
@@ -117,7 +129,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4);
+    auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + 2 * q + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 8);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -125,6 +138,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
+        for (int q = 0; q < 4; ++q) { mbar_init(res_bar(q, 0), 1); mbar_init(res_bar(q, 1), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -184,58 +198,97 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     } else if (warp >= 4) {
         // ---------------- epilogue (warps 4..7 <-> TMEM lane quarters 0..3) ----------------
         const int q = warp - 4;
+        const uint32_t epi_base = smem_base + SM::EPI_OFF + q * SM::EPI_WARP_BYTES;
+        uint8_t* epi_ptr = smem_raw + (epi_base - smem_u32(smem_raw));
+        // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
+        const uint32_t sw = (uint32_t)((lane >> 1) & 3);
+        constexpr int NCH = BN / 32;
+        uint32_t rphase0 = 0, rphase1 = 0;
         uint32_t lt = 0;
         for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
             const int as = lt & 1;
             const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            const int row0 = m0 + q * 32;
+            if (has_res && lane == 0) {          // residual chunks 0 and 1 of this tile
+#pragma unroll
+                for (int b = 0; b < 2; ++b) {
+                    mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
+                    tma_load_2d(epi_base + (2 + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + b * 32, row0);
+                }
+            }
             mbar_wait(tfull_bar(as), (lt >> 1) & 1u);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-            const int row = m0 + q * 32 + lane;
-            const bool row_ok = row < M;
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
-#pragma unroll 1
-            for (int c = 0; c < BN / 32; ++c) {
-                uint32_t v[32];
-                tmem_ld32(t_row + (uint32_t)(c * 32), v);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+
+            auto process = [&](const uint32_t* v, int c) {
+                const int b = c & 1;
                 const int col = n0 + c * 32;
-                if (row_ok) {
-                    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-                    const uint4* r4 = R ? reinterpret_cast<const uint4*>(R + (size_t)row * N + col) : nullptr;
-                    uint4* c4 = reinterpret_cast<uint4*>(C + (size_t)row * N + col);
+                if (has_res) {
+                    mbar_wait(res_bar(q, b), b ? rphase1 : rphase0);
+                    if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+                }
+                // the TMA store that last read output buffer b (two chunks ago) must be done with it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                __syncwarp();
+                const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+                const uint8_t* rrow = epi_ptr + (2 + b) * SM::EPI_BUF + lane * 64;
+                uint8_t* crow = epi_ptr + b * SM::EPI_BUF + lane * 64;
 #pragma unroll
-                    for (int g = 0; g < 4; ++g) {      // 8 columns per group
-                        float f[8];
-                        const float4 ba = b4[2 * g], bb = b4[2 * g + 1];
-                        f[0] = __uint_as_float(v[8 * g + 0]) + ba.x; f[1] = __uint_as_float(v[8 * g + 1]) + ba.y;
-                        f[2] = __uint_as_float(v[8 * g + 2]) + ba.z; f[3] = __uint_as_float(v[8 * g + 3]) + ba.w;
-                        f[4] = __uint_as_float(v[8 * g + 4]) + bb.x; f[5] = __uint_as_float(v[8 * g + 5]) + bb.y;
-                        f[6] = __uint_as_float(v[8 * g + 6]) + bb.z; f[7] = __uint_as_float(v[8 * g + 7]) + bb.w;
-                        if (r4) {
-                            const uint4 rr = r4[g];
-                            const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr);
+                for (int g = 0; g < 4; ++g) {      // 8 columns = one 16-byte chunk per group
+                    float f[8];
+                    const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+                    f[0] = __uint_as_float(v[8 * g + 0]) + ba.x; f[1] = __uint_as_float(v[8 * g + 1]) + ba.y;
+                    f[2] = __uint_as_float(v[8 * g + 2]) + ba.z; f[3] = __uint_as_float(v[8 * g + 3]) + ba.w;
+                    f[4] = __uint_as_float(v[8 * g + 4]) + bb.x; f[5] = __uint_as_float(v[8 * g + 5]) + bb.y;
+                    f[6] = __uint_as_float(v[8 * g + 6]) + bb.z; f[7] = __uint_as_float(v[8 * g + 7]) + bb.w;
+                    const uint32_t pos = ((uint32_t)g ^ sw) << 4;
+                    if (has_res) {
+                        const uint4 rr = *reinterpret_cast<const uint4*>(rrow + pos);
+                        const __nv_bfloat162* rb = reinterpret_cast<const __nv_bfloat162*>(&rr);
 #pragma unroll
-                            for (int e = 0; e < 4; ++e) {
-                                const float2 rf = __bfloat1622float2(rb[e]);
-                                f[2 * e] += rf.x; f[2 * e + 1] += rf.y;
-                            }
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 rf = __bfloat1622float2(rb[e]);
+                            f[2 * e] += rf.x; f[2 * e + 1] += rf.y;
                         }
-                        if (relu) {
+                    }
+                    if (relu) {
 #pragma unroll
-                            for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
-                        }
-                        uint4 o;
-                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+                    uint4 o;
+                    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                        for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                        c4[g] = o;
+                    for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                    *reinterpret_cast<uint4*>(crow + pos) = o;
+                }
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
+                __syncwarp();
+                if (lane == 0) {
+                    tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
+                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (has_res && c + 2 < NCH) {      // all lanes are past their reads of residual buffer b
+                        mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
+                        tma_load_2d(epi_base + (2 + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + (c + 2) * 32, row0);
                     }
                 }
+            };
+
+            uint32_t va[32], vb[32];
+            tmem_ld32(t_row, va);
+#pragma unroll 1
+            for (int c = 0; c < NCH; c += 2) {
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                tmem_ld32(t_row + (uint32_t)((c + 1) * 32), vb);
+                process(va, c);
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (c + 2 < NCH) tmem_ld32(t_row + (uint32_t)((c + 2) * 32), va);
+                process(vb, c + 1);
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) mbar_arrive(tempty_bar(as));
         }
+        if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
@@ -320,13 +373,14 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
-static int make_map(EncodeTiledFn enc, CUtensorMap* map, void* base, uint64_t cols, uint64_t rows, uint32_t box_rows) {
+static int make_map(EncodeTiledFn enc, CUtensorMap* map, void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
+                    uint32_t box_cols = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
     cuuint64_t dims[2] = {cols, rows};
     cuuint64_t strides[1] = {cols * 2};
-    cuuint32_t box[2] = {TC_BK, box_rows};
+    cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
-                     CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+                     swz, CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) {
         dx_set_error("cuTensorMapEncodeTiled failed with code " + std::to_string((int)r));
         return DX_ERR_CUDA;
@@ -355,6 +409,8 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     int rc = make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM);
     for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i)
+        rc = make_map(enc, &p->c_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN);
     if (rc == DX_OK && net.num_blocks > 0)
         rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN);
@@ -370,12 +426,15 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     return DX_OK;
 }
 
+// c: output buffer index, r: residual buffer index or -1
 static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
-                        int K, int N, const float* bias, const __nv_bfloat16* R, __nv_bfloat16* C, int relu) {
+                        int K, int N, const float* bias, int r, int c, int relu) {
+    const CUtensorMap& tc = p->c_x[c];
+    const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     if (p->BN == 256)
-        k_gemm_bf16_tc<256><<<p->num_sms, TC_THREADS, TcSmem<256>::TOTAL, s>>>(a, b, ctl, w_row0, K, N, bias, R, C, relu);
+        k_gemm_bf16_tc<256><<<p->num_sms, TC_THREADS, TcSmem<256>::TOTAL, s>>>(a, b, tc, tr, ctl, w_row0, K, N, bias, r >= 0, relu);
     else
-        k_gemm_bf16_tc<128><<<p->num_sms, TC_THREADS, TcSmem<128>::TOTAL, s>>>(a, b, ctl, w_row0, K, N, bias, R, C, relu);
+        k_gemm_bf16_tc<128><<<p->num_sms, TC_THREADS, TcSmem<128>::TOTAL, s>>>(a, b, tc, tr, ctl, w_row0, K, N, bias, r >= 0, relu);
 }
 
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
@@ -388,26 +447,22 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     dx_prof_begin(DX_ST_GEMM_IN);
     k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ctl, rows, goals, p->onehot);
     ++launches;
-    __nv_bfloat16* x = (__nv_bfloat16*)mb.xb[0];
-    __nv_bfloat16* y = (__nv_bfloat16*)mb.xb[1];
-    __nv_bfloat16* z = (__nv_bfloat16*)mb.xb[2];
     int ix = 0, iy = 1, iz = 2;
     const int Hp = net.Hp;
-    launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, net.b0, nullptr, x, 0);
+    launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, net.b0, -1, ix, 0);
     ++launches;
     dx_prof_end();
     for (int b = 0; b < net.num_blocks; ++b) {
         dx_prof_begin(DX_ST_GEMM_RES);
-        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, net.bres + (size_t)(2 * b) * Hp, nullptr, y, 1);
+        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
         dx_prof_end();
         dx_prof_begin(DX_ST_GEMM_RES);
-        launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, x, z, 1);
+        launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
         dx_prof_end();
         launches += 2;
-        __nv_bfloat16* tp = x; x = z; z = tp;
         int ti = ix; ix = iz; iz = ti;
     }
-    (void)y; (void)iy;
+    const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
     const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);
     k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, out_h, out_q, absolute);
     ++launches;

@@ -161,7 +161,8 @@ struct SortBufs {
     uint32_t* inst[2];
     uint32_t* val[2];
     uint32_t* hist;       // [256 * max_tiles (+ slack)]
-    uint32_t* ghist;      // [DX_NUM_DIGITS * 256]
+    uint32_t* ghist;      // [DX_NUM_DIGITS * 256] global digit histograms of the batch
+    uint32_t* gbase;      // [DX_NUM_DIGITS * 256] exclusive bin offsets per digit position
     int max_tiles;
 };
 

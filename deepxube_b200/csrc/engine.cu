@@ -11,6 +11,7 @@
 //   is_solved + record_goal -> CLOSED filter on popped nodes -> edges of kept nodes -> f-keys -> sort ->
 //   merge/pop edges -> next_state per popped edge -> heuristic (all-action q, h = min) -> lb/finished/itr.
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -204,6 +205,9 @@ struct dx_engine {
     float stage_ms[ST_COUNT] = {0};
     long long stage_calls[ST_COUNT] = {0};
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
+    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one captured iteration per buffer parity
+    int graph_launches = 0;
+    bool use_graphs = true;
     float last_run_ms = 0.f;
 
     template <typename T> int alloc(T** p, size_t count) {
@@ -330,6 +334,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     int r = make_domain_host(cfg->domain, cfg->domain_dim, &e->dom, &e->table_h);
     if (r < 0) { delete e; return r; }
     e->is_q = cfg->algo == DX_ALGO_GRAPH_Q;
+    if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -367,7 +372,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     }
     A_(e->edge_tmp, P); A_(e->pop_solved, P);
     e->sort.max_tiles = dx_div_up(e->max_sort, DX_SORT_TILE);
-    A_(e->sort.hist, (size_t)256 * e->sort.max_tiles + 4096); A_(e->sort.ghist, DX_NUM_DIGITS * 256);
+    A_(e->sort.hist, (size_t)256 * e->sort.max_tiles + 4096); A_(e->sort.ghist, DX_NUM_DIGITS * 256); A_(e->sort.gbase, DX_NUM_DIGITS * 256);
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
     A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);
@@ -384,6 +389,7 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
     if (!e) return DX_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
+    for (int k = 0; k < 2; ++k) if (e->graph_exec[k]) cudaGraphExecDestroy(e->graph_exec[k]);
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -637,6 +643,27 @@ static int full_step(dx_engine* e) {
     return DX_OK;
 }
 
+static int build_step_graphs(dx_engine* e) {
+    const int p0 = e->parity;
+    const long long l0 = e->launches;
+    for (int k = 0; k < 2; ++k) {
+        const int p = e->parity;
+        cudaGraph_t g = nullptr;
+        DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        const int rc = full_step(e);                 // flips e->parity
+        cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
+        if (rc < 0) { if (g) cudaGraphDestroy(g); return rc; }
+        if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
+        ce = cudaGraphInstantiate(&e->graph_exec[p], g, 0);
+        cudaGraphDestroy(g);
+        if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
+    }
+    e->graph_launches = (int)((e->launches - l0) / 2);
+    e->launches = l0;
+    e->parity = p0;
+    return DX_OK;
+}
+
 extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
     if (e->cfg.heur_mode == DX_HEUR_HOST) DX_FAIL(DX_ERR_STATE, "dx_run needs a device heuristic (use dx_step_begin/end in HOST mode)");
@@ -646,9 +673,19 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     int done = 0;
     DX_TRY(sync_ctl(e));
     if (!e->run_ev[0]) { cudaEventCreate(&e->run_ev[0]); cudaEventCreate(&e->run_ev[1]); }
+    // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
+    // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
+    const bool use_graph = !e->profiling && e->use_graphs;
+    if (use_graph && !e->graph_exec[0]) DX_TRY(build_step_graphs(e));
     cudaEventRecord(e->run_ev[0], e->stream);
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
-        DX_TRY(full_step(e));
+        if (use_graph) {
+            DX_CUDA(cudaGraphLaunch(e->graph_exec[e->parity], e->stream));
+            e->launches += e->graph_launches;
+            e->parity ^= 1;
+        } else {
+            DX_TRY(full_step(e));
+        }
         ++done;
         DX_TRY(sync_ctl(e));
     }

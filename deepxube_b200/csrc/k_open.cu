@@ -156,17 +156,30 @@ k_radix_prepass(const Ctl* __restrict__ ctl, SortBufs sb) {
 }
 
 // skip a pass when one bin holds every element; assign ping-pong sources to the remaining passes.
+// Also turns each digit position's global histogram into exclusive bin offsets (gbase), the starting
+// output position of every digit value in that pass.
 __global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
     __shared__ uint32_t s_skip[DX_NUM_DIGITS];
+    __shared__ uint32_t s_cnt[DX_NUM_DIGITS * 256];
     if (ctl->error) return;
     const uint32_t n = ctl->sort_n;
     if (threadIdx.x < DX_NUM_DIGITS) s_skip[threadIdx.x] = (n == 0) ? 1u : 0u;
     __syncthreads();
     for (int i = threadIdx.x; i < DX_NUM_DIGITS * 256; i += blockDim.x) {
-        if (n != 0 && sb.ghist[i] == n) s_skip[i / 256] = 1u;
+        const uint32_t c = sb.ghist[i];
+        s_cnt[i] = c;
+        if (n != 0 && c == n) s_skip[i / 256] = 1u;
         sb.ghist[i] = 0;
     }
     __syncthreads();
+    if (threadIdx.x < DX_NUM_DIGITS) {
+        uint32_t acc = 0;
+        for (int b = 0; b < 256; ++b) {
+            const uint32_t c = s_cnt[threadIdx.x * 256 + b];
+            sb.gbase[threadIdx.x * 256 + b] = acc;
+            acc += c;
+        }
+    }
     if (threadIdx.x == 0) {
         uint32_t src = 0;
         for (int d = 0; d < DX_NUM_DIGITS; ++d) {
@@ -188,7 +201,8 @@ k_radix_hist(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
     s_h[threadIdx.x] = 0;
     __syncthreads();
     const uint32_t base = tile * DX_SORT_TILE;
-    if (base < n) {
+    if (base >= n) return;                 // tiles past the end are never read by the tile scan
+    {
         const unsigned long long* __restrict__ keys = sb.key[src];
         const uint32_t* __restrict__ insts = sb.inst[src];
 #pragma unroll
@@ -199,6 +213,41 @@ k_radix_hist(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
     }
     __syncthreads();
     sb.hist[(size_t)threadIdx.x * sb.max_tiles + tile] = s_h[threadIdx.x];
+}
+
+// One block per digit value: exclusive scan of that value's per-tile counts, offset by the value's global base.
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_radix_tilescan(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
+    __shared__ uint32_t s_warp[OPEN_THREADS / 32];
+    if (ctl->error || ctl->pass_skip[d]) return;
+    const uint32_t n = ctl->sort_n;
+    const uint32_t ntiles = (n + DX_SORT_TILE - 1) / DX_SORT_TILE;
+    const uint32_t digit = blockIdx.x;
+    uint32_t* __restrict__ h = sb.hist + (size_t)digit * sb.max_tiles;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    uint32_t carry = sb.gbase[d * 256 + digit];
+    for (uint32_t base = 0; base < ntiles; base += OPEN_THREADS) {
+        const uint32_t i = base + threadIdx.x;
+        const uint32_t v = i < ntiles ? h[i] : 0u;
+        uint32_t x = v;
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, o);
+            if (lane >= o) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        uint32_t woff = 0, total = 0;
+#pragma unroll
+        for (int w = 0; w < OPEN_THREADS / 32; ++w) {
+            const uint32_t c = s_warp[w];
+            if (w < warp) woff += c;
+            total += c;
+        }
+        if (i < ntiles) h[i] = carry + woff + x - v;
+        carry += total;
+        __syncthreads();
+    }
 }
 
 __global__ void __launch_bounds__(OPEN_THREADS)
@@ -274,9 +323,9 @@ int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp&
     launches += 2;
     for (int d = 0; d < DX_NUM_DIGITS; ++d) {
         k_radix_hist<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
-        launches += 1 + dx_launch_scan_u32(s, sb.hist, 256 * sb.max_tiles, &ctl->pass_skip[d], t);
+        k_radix_tilescan<<<256, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_scatter<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
-        launches += 1;
+        launches += 3;
     }
     return launches;
 }

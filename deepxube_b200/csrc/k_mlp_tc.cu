@@ -16,6 +16,7 @@
 // The one-hot input layer is a K = in_dim (padded to 64) GEMM over a bf16 one-hot matrix written by
 // k_onehot_bf16 (exact: the entries are 0 / 1).
 #include <cuda.h>
+#include <stdlib.h>
 #include <cuda_bf16.h>
 
 #include "dx_internal.cuh"
@@ -34,6 +35,7 @@ struct TcPlan {
     CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
     int BN;
+    int CL;                      // CTAs per cluster (B tile multicast)
     int num_sms;
 };
 
@@ -70,6 +72,19 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
+}
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
+                 "[%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
+                 : "memory");
+}
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                 ::"r"(bar), "h"(mask) : "memory");
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
@@ -112,7 +127,11 @@ struct TcSmem {
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
 
-template <int BN>
+// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent tiles
+// (same n, rows m and m+1): each loads its own A tile and HALF of the shared B (weight) tile, multicast into
+// both CTAs' shared memory, which cuts the L2 -> SM operand traffic per CTA from 48 KB to 32 KB per k-block.
+// A stage is reusable only when BOTH CTAs' MMAs have read it (empty barrier count 2, multicast commits).
+template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
@@ -135,8 +154,11 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    uint32_t cta_rank = 0;
+    if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
         for (int q = 0; q < 4; ++q) { mbar_init(res_bar(q, 0), 1); mbar_init(res_bar(q, 1), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -148,25 +170,31 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (CL > 1) cluster_sync_all();          // peer barriers are initialised before any multicast lands
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
-    const int total = m_tiles * n_tiles;
+    const int total = ((m_tiles + CL - 1) / CL) * n_tiles;       // tile groups of CL vertically adjacent tiles
     const int kblocks = K / TC_BK;
+    const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer ----------------
             uint32_t it = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x) {
-                const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            for (int t = cl_id; t < total; t += n_cl) {
+                const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % TC_STAGES;
                     mbar_wait(empty_bar(s), ((it / TC_STAGES) & 1u) ^ 1u);
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
                     mbar_arrive_expect_tx(full_bar(s), SM::STAGE_BYTES);
                     tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
-                    tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
+                    if (CL == 1)
+                        tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
+                    else
+                        tma_load_2d_mc(b_dst + cta_rank * (SM::B_BYTES / CL), &tmB, full_bar(s), kb * TC_BK,
+                                       w_row0 + n0 + (int)cta_rank * (BN / CL), MC_MASK);
                 }
             }
         }
@@ -176,7 +204,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t it = 0, lt = 0;
-            for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+            for (int t = cl_id; t < total; t += n_cl, ++lt) {
                 const int as = lt & 1;
                 mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -190,7 +218,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
                         umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit(empty_bar(s));          // smem slot reusable once these MMAs have read it
+                    if (CL == 1) umma_commit(empty_bar(s));        // smem slot reusable once these MMAs have read it
+                    else umma_commit_mc(empty_bar(s), MC_MASK);    // ... in both CTAs of the cluster
                 }
                 umma_commit(tfull_bar(as));             // accumulator complete
             }
@@ -205,9 +234,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NCH = BN / 32;
         uint32_t rphase0 = 0, rphase1 = 0;
         uint32_t lt = 0;
-        for (int t = blockIdx.x; t < total; t += gridDim.x, ++lt) {
+        for (int t = cl_id; t < total; t += n_cl, ++lt) {
             const int as = lt & 1;
-            const int m0 = (t / n_tiles) * TC_BM, n0 = (t % n_tiles) * BN;
+            const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + q * 32;
             if (has_res && lane == 0) {          // residual chunks 0 and 1 of this tile
 #pragma unroll
@@ -292,6 +321,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // no CTA exits while its peer may still multicast into it / signal it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
@@ -403,6 +433,8 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     TcPlan* p = new TcPlan();
     p->BN = net.Hp >= 256 ? 256 : 128;
+    p->CL = 2;
+    if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : 2;
     p->onehot = (__nv_bfloat16*)onehot_buf;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -411,13 +443,20 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM);
     for (int i = 0; i < 3 && rc == DX_OK; ++i)
         rc = make_map(enc, &p->c_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN);
+    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN / p->CL);
     if (rc == DX_OK && net.num_blocks > 0)
-        rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN);
+        rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / p->CL);
     if (rc == DX_OK) {
-        if (cudaFuncSetAttribute(k_gemm_bf16_tc<256>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<256>::TOTAL) != cudaSuccess ||
-            cudaFuncSetAttribute(k_gemm_bf16_tc<128>, cudaFuncAttributeMaxDynamicSharedMemorySize, TcSmem<128>::TOTAL) != cudaSuccess) {
-            dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(cudaGetLastError()));
+        cudaError_t ce = cudaSuccess;
+        auto set_attr = [&](const void* f, int bytes) {
+            if (ce == cudaSuccess) ce = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        };
+        set_attr((const void*)k_gemm_bf16_tc<256, 1>, TcSmem<256>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2>, TcSmem<256>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1>, TcSmem<128>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2>, TcSmem<128>::TOTAL);
+        if (ce != cudaSuccess) {
+            dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(ce));
             rc = DX_ERR_CUDA;
         }
     }
@@ -431,10 +470,23 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, c
                         int K, int N, const float* bias, int r, int c, int relu) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
-    if (p->BN == 256)
-        k_gemm_bf16_tc<256><<<p->num_sms, TC_THREADS, TcSmem<256>::TOTAL, s>>>(a, b, tc, tr, ctl, w_row0, K, N, bias, r >= 0, relu);
-    else
-        k_gemm_bf16_tc<128><<<p->num_sms, TC_THREADS, TcSmem<128>::TOTAL, s>>>(a, b, tc, tr, ctl, w_row0, K, N, bias, r >= 0, relu);
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3((unsigned)(p->num_sms / p->CL * p->CL));
+    cfg.blockDim = dim3(TC_THREADS);
+    cfg.dynamicSmemBytes = p->BN == 256 ? TcSmem<256>::TOTAL : TcSmem<128>::TOTAL;
+    cfg.stream = s;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeClusterDimension;
+    attr[0].val.clusterDim.x = (unsigned)p->CL;
+    attr[0].val.clusterDim.y = 1;
+    attr[0].val.clusterDim.z = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    const int has_res = r >= 0 ? 1 : 0;
+    if (p->BN == 256 && p->CL == 2) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<256, 2>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
+    else if (p->BN == 256) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<256, 1>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
+    else if (p->CL == 2) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<128, 2>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
+    else cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<128, 1>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
 }
 
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,

@@ -33,11 +33,6 @@ FLOP_PER_STATE = 2.0 * (IN_COUNT * DEPTH * H + 2 * NB * H * H + H * 1)      # SU
 FLOP_PER_STATE_HIDDEN_LAYER = 2.0 * H * H                                    # one hidden-layer GEMM launch, per state
 
 
-def cube3_perm() -> np.ndarray:
-    from deepxube_b200.domains.cube3 import CUBE3_PERM
-    return CUBE3_PERM
-
-
 def make_scrambles(n: int, seed: int = 0):
     """n cube3 start states: solved cube + random walk of U{1000..10000} moves (host-side input generation)."""
     from deepxube_b200.domains.tables import cube3_perm_table
@@ -303,9 +298,17 @@ def main() -> None:
         hidden_flop = FLOP_PER_STATE_HIDDEN_LAYER * 2 * NB * evals
         achieved = hidden_flop / (stage["gemm_hidden"] / 1e3) / 1e12 if stage["gemm_hidden"] > 0 else None
         peak = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else None
-        roof = {"kernel": "k_gemm_bf16_tc<256> (hidden layers, 1000x1000 per state)" if args.precision == "bf16" else "k_sgemm_bias_act",
+        traffic, traffic_note = None, None
+        tf = os.path.join(ROOT, "profiles", "r1_gemm_traffic.json")
+        if args.precision == "bf16" and os.path.exists(tf):
+            tj = json.load(open(tf))
+            traffic = tj["traffic_per_launch_avg_bytes"]
+            traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture of a "
+                            f"{tj['rows_in_launch']}-state launch (profiles/r1_gemm_traffic.json); algorithmic bytes of that launch: "
+                            f"{tj['algorithmic_bytes']['hidden']} (plain) / {tj['algorithmic_bytes']['hidden_residual']} (with residual)")
+        roof = {"kernel": "k_gemm_bf16_tc<256,2> (hidden layers, 1000x1000 per state)" if args.precision == "bf16" else "k_sgemm_bias_act",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": None,
+                "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["_source"] + " (sustained bf16, kernel timed inside a long step)",
                 "launches_timed": calls["gemm_hidden"], "avg_launch_ms": stage["gemm_hidden"] / max(calls["gemm_hidden"], 1),
                 "network_tflops_dense_equiv": FLOP_PER_STATE * evals / (stage["heur"] / 1e3) / 1e12 if stage["heur"] > 0 else None,

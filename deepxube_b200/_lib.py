@@ -40,6 +40,11 @@ class dx_inst_status(C.Structure):
                 ("reserved", C.c_int32)]
 
 
+class dx_hda_local(C.Structure):
+    _fields_ = [("k_popped", C.c_int64), ("f_first", C.c_double), ("ub", C.c_double), ("goal_local", C.c_int64),
+                ("n_kept", C.c_int64), ("open_size", C.c_int64), ("children_sent", C.c_int64)]
+
+
 class dx_counters(C.Structure):
     _fields_ = [("nodes_stored", C.c_int64), ("heur_evals", C.c_int64), ("children_generated", C.c_int64),
                 ("iterations", C.c_int64), ("kernel_launches", C.c_int64), ("reserved", C.c_int64 * 3)]
@@ -81,6 +86,14 @@ SIGNATURES = {
     "dx_get_stage_ms": (C.c_int, [_engp, _f32p, C.c_int32]),
     "dx_get_stage_calls": (C.c_int, [_engp, C.POINTER(C.c_int64), C.c_int32]),
     "dx_last_run_ms": (C.c_int, [_engp, _f32p]),
+    "dx_hda_config": (C.c_int, [_engp, C.c_int32, C.c_int32]),
+    "dx_hda_record_bytes": (C.c_int, [_engp, _i32p]),
+    "dx_hda_owner": (C.c_int, [_engp, _u8p, _i32p]),
+    "dx_hda_add_instance": (C.c_int, [_engp, _u8p, _u8p, C.c_int32, C.c_double]),
+    "dx_hda_expand": (C.c_int, [_engp, C.c_void_p, C.c_int64, C.POINTER(C.c_int64)]),
+    "dx_hda_absorb": (C.c_int, [_engp, C.c_void_p, C.c_int64, C.POINTER(dx_hda_local)]),
+    "dx_hda_finish": (C.c_int, [_engp, C.c_int64, C.c_double, C.c_double, C.c_int64, _i32p]),
+    "dx_hda_node": (C.c_int, [_engp, C.c_int64, _u8p, C.POINTER(C.c_uint32), _i32p, _f32p]),
 }
 
 _lib = None
@@ -269,6 +282,47 @@ class Engine:
         out = np.empty((states.shape[0], out_dim), np.float32)
         check(self._lib.dx_heur_eval(self._h, _p(states, _u8p), _p(goals, _u8p), states.shape[0], _p(out, _f32p)))
         return out
+
+    # ---- HDA* (hash-distributed single search) ----------------------------------------------------------
+    def hda_config(self, rank: int, world: int) -> None:
+        check(self._lib.dx_hda_config(self._h, rank, world))
+
+    def hda_record_bytes(self) -> int:
+        n = C.c_int32()
+        check(self._lib.dx_hda_record_bytes(self._h, C.byref(n)))
+        return n.value
+
+    def hda_owner(self, state: np.ndarray) -> int:
+        st = _u8(state)
+        o = C.c_int32()
+        check(self._lib.dx_hda_owner(self._h, _p(st, _u8p), C.byref(o)))
+        return o.value
+
+    def hda_add_instance(self, state: np.ndarray, goal: np.ndarray, batch_local: int, weight: float) -> None:
+        st, gl = _u8(state), _u8(goal)
+        check(self._lib.dx_hda_add_instance(self._h, _p(st, _u8p), _p(gl, _u8p), batch_local, weight))
+
+    def hda_expand(self, send_ptr: int, send_cap_bytes: int, world: int) -> np.ndarray:
+        counts = (C.c_int64 * 16)()
+        check(self._lib.dx_hda_expand(self._h, C.c_void_p(send_ptr), send_cap_bytes, counts))
+        return np.array(counts[:world], dtype=np.int64)
+
+    def hda_absorb(self, recv_ptr: int, n_records: int) -> dx_hda_local:
+        out = dx_hda_local()
+        check(self._lib.dx_hda_absorb(self._h, C.c_void_p(recv_ptr), n_records, C.byref(out)))
+        return out
+
+    def hda_finish(self, k_total: int, f_first_min: float, ub_min: float, children_total: int) -> bool:
+        fin = C.c_int32()
+        check(self._lib.dx_hda_finish(self._h, k_total, f_first_min, ub_min, children_total, C.byref(fin)))
+        return bool(fin.value)
+
+    def hda_node(self, local_id: int):
+        """-> (state [S], parent global id or None for the root, action, g)"""
+        st = np.empty(self.state_bytes, np.uint8)
+        par, act, g = C.c_uint32(), C.c_int32(), C.c_float()
+        check(self._lib.dx_hda_node(self._h, local_id, _p(st, _u8p), C.byref(par), C.byref(act), C.byref(g)))
+        return st, (None if par.value == 0xFFFFFFFF else par.value), act.value, g.value
 
     def bench_heur(self, n: int, reps: int) -> float:
         ms = C.c_float()

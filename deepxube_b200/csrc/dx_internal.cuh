@@ -114,7 +114,7 @@ static inline int dx_div_up(long long a, long long b) { return (int)((a + b - 1)
 
 // ---------------------------------------------------------------------------------------------
 // 64-bit hash of a row (state bytes + padding + instance id), 16 bytes at a time.
-__device__ __forceinline__ uint64_t dx_mix64(uint64_t h) {
+__host__ __device__ __forceinline__ uint64_t dx_mix64(uint64_t h) {
     h ^= h >> 33;
     h *= 0xff51afd7ed558ccdull;
     h ^= h >> 33;
@@ -123,7 +123,7 @@ __device__ __forceinline__ uint64_t dx_mix64(uint64_t h) {
     return h;
 }
 
-__device__ __forceinline__ uint64_t dx_hash_row(const uint4* __restrict__ row, int chunks) {
+__host__ __device__ __forceinline__ uint64_t dx_hash_row(const uint4* __restrict__ row, int chunks) {
     uint64_t h = 0x9E3779B97F4A7C15ull;
     for (int i = 0; i < chunks; ++i) {
         uint4 v = row[i];
@@ -212,7 +212,24 @@ int dx_launch_scan_u32(cudaStream_t s, uint32_t* data, int n, const uint32_t* sk
 // k_open.cu
 int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                    uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
-                   uint32_t max_pop, uint32_t max_open);
+                   uint32_t max_pop, uint32_t max_open, int kept_is_total = 0);
+
+// k_hda.cu (hash-distributed single search)
+int dx_launch_hda_bucket(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortBufs& sb, const ScanTemp& t,
+                         const uint8_t* child_state, const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world,
+                         uint32_t* counts, uint8_t* send, int max_children);
+int dx_launch_hda_unpack(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* recv, uint32_t n, uint8_t* child_state,
+                         float* child_g, uint32_t* child_parent, uint8_t* child_action);
+int dx_launch_scatter_kept_hda(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const uint8_t* child_state,
+                               const float* child_g, const uint32_t* child_slot, const uint8_t* child_flags,
+                               const uint32_t* child_prefix, const uint32_t* child_parent, const uint8_t* child_action,
+                               uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action,
+                               uint32_t* new_inst, int max_children);
+int dx_launch_hda_finish(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
+                         int A, unsigned long long k_total, unsigned long long f_first_min_bits, uint32_t ub_g_bits, int has_ub,
+                         unsigned long long gen_add);
+int dx_launch_hda_drop_root(cudaStream_t s, Ctl* ctl, uint32_t* pop_off);
+uint32_t dx_hda_owner_host(const uint8_t* row, int SP, uint32_t world);
 int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
                         const uint32_t* new_inst, const SortBufs& sb, int max_n);
 int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,

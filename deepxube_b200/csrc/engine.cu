@@ -11,6 +11,7 @@
 //   is_solved + record_goal -> CLOSED filter on popped nodes -> edges of kept nodes -> f-keys -> sort ->
 //   merge/pop edges -> next_state per popped edge -> heuristic (all-action q, h = min) -> lb/finished/itr.
 #include <math.h>
+#include <cmath>
 #include <stdlib.h>
 #include <string.h>
 
@@ -186,6 +187,10 @@ struct dx_engine {
     uint8_t* child_flags = nullptr; uint32_t* child_prefix = nullptr; uint32_t* new_inst = nullptr;
     uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
     uint32_t* edge_tmp = nullptr; uint8_t* pop_solved = nullptr;
+    // HDA* mode (hash-distributed single search)
+    int hda_rank = 0, hda_world = 0;
+    uint32_t* hda_counts = nullptr; uint32_t* child_parent = nullptr; uint8_t* child_action = nullptr;
+    int64_t hda_children_sent = 0;
     unsigned long long* open_key[2] = {nullptr, nullptr}; uint32_t* open_val[2] = {nullptr, nullptr};
     uint32_t* open_off[2] = {nullptr, nullptr};
     SortBufs sort{};
@@ -1150,5 +1155,171 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     } else {
         for (int i = 0; i < 3; ++i) DX_TRY(e->alloc(&e->mlp.x[i], (size_t)cap * Hp));
     }
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// HDA*-style hash-distributed single search (BASELINE config 5).  The exchange itself is done by
+// the host layer (NCCL all-to-all through torch.distributed, or an in-process copy when several ranks are
+// emulated on one GPU); the engine produces / consumes the per-destination record buffers.
+extern "C" int dx_hda_config(dx_engine* e, int32_t rank, int32_t world) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    if (world < 1 || world > 16 || rank < 0 || rank >= world) DX_FAIL(DX_ERR_ARG, "bad rank / world (world <= 16)");
+    if (e->is_q) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode is implemented for graph_v");
+    if (e->cfg.heur_mode == DX_HEUR_HOST) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode needs a device heuristic");
+    if (e->n_inst != 0) DX_FAIL(DX_ERR_STATE, "dx_hda_config must precede dx_hda_add_instance");
+    if (e->max_nodes >= (1u << 28)) DX_FAIL(DX_ERR_ARG, "HDA* mode: max_nodes must be < 2^28 per rank (global node id = rank << 28 | id)");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    e->hda_rank = rank;
+    e->hda_world = world;
+    if (!e->hda_counts) {
+        DX_TRY(e->alloc(&e->hda_counts, 16));
+        DX_TRY(e->alloc(&e->child_parent, (size_t)e->max_children + 1));
+        DX_TRY(e->alloc(&e->child_action, (size_t)e->max_children + 1));
+    }
+    return DX_OK;
+}
+
+extern "C" int dx_hda_record_bytes(dx_engine* e, int32_t* rec_bytes) {
+    if (!e || !rec_bytes) DX_FAIL(DX_ERR_ARG, "null argument");
+    *rec_bytes = e->SP + 16;
+    return DX_OK;
+}
+
+extern "C" int dx_hda_owner(dx_engine* e, const uint8_t* state, int32_t* owner) {
+    if (!e || !state || !owner || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    std::vector<uint8_t> row(e->SP, 0);            // instance id field = 0 (single instance)
+    memcpy(row.data(), state, e->S);
+    uint4 tmp[16];
+    memcpy(tmp, row.data(), e->SP);
+    *owner = (int32_t)dx_hda_owner_host(reinterpret_cast<const uint8_t*>(tmp), e->SP, (uint32_t)e->hda_world);
+    return DX_OK;
+}
+
+extern "C" int dx_hda_add_instance(dx_engine* e, const uint8_t* state, const uint8_t* goal, int32_t batch_local, double weight) {
+    if (!e || e->hda_world < 1) DX_FAIL(DX_ERR_STATE, "HDA* mode not configured");
+    if (e->n_inst != 0) DX_FAIL(DX_ERR_STATE, "HDA* mode holds exactly one instance (dx_engine_reset first)");
+    int32_t owner = 0;
+    DX_TRY(dx_hda_owner(e, state, &owner));
+    DX_TRY(dx_add_instances(e, state, goal, 1, &batch_local, &weight, nullptr));
+    if (owner != e->hda_rank) {
+        // this rank knows the instance (goal, weight, batch) but does not own the root
+        e->launches += dx_launch_hda_drop_root(e->stream, e->d_ctl, e->pop_off[e->parity]);
+        e->launches += dx_launch_closed_init(e->stream, e->closed);
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    return DX_OK;
+}
+
+// Phase 1: expand the local popped list, group the children by owner rank, write the records into send_dev
+// (device pointer, >= n_children * rec_bytes).  counts[world] = records per destination, in rank order.
+extern "C" int dx_hda_expand(dx_engine* e, void* send_dev, int64_t send_cap_bytes, int64_t* counts) {
+    if (!e || !send_dev || !counts || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    if ((int64_t)e->h_ctl->n_children * (e->SP + 16) > send_cap_bytes) DX_FAIL(DX_ERR_CAPACITY, "HDA* send buffer too small");
+    cudaStream_t s = e->stream;
+    const int p = e->parity;
+    DX_CUDA(cudaMemsetAsync(e->hda_counts, 0, 16 * sizeof(uint32_t), s));
+    e->launches += dx_launch_expand(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
+                                    e->pop_off[p], e->child_state, e->child_g, e->pop_solved, e->max_pop);
+    e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
+                                          e->pop_solved, e->max_pop);
+    e->launches += dx_launch_hda_bucket(s, e->dom, e->d_ctl, e->sort, e->scan, e->child_state, e->child_g, e->popped[p],
+                                        (uint32_t)e->hda_rank, (uint32_t)e->hda_world, e->hda_counts, (uint8_t*)send_dev,
+                                        e->max_children);
+    uint32_t hc[16];
+    DX_CUDA(cudaMemcpyAsync(hc, e->hda_counts, 16 * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+    DX_CUDA(cudaStreamSynchronize(s));
+    for (int r = 0; r < e->hda_world; ++r) counts[r] = hc[r];
+    e->hda_children_sent = e->h_ctl->n_children;
+    return DX_OK;
+}
+
+
+
+// Phase 2: filter the n_records received children against the local CLOSED shard, store / evaluate / push the
+// survivors, pop the local top batch.  Reports the local quantities the host reduces over ranks.
+extern "C" int dx_hda_absorb(dx_engine* e, const void* recv_dev, int64_t n_records, dx_hda_local* out) {
+    if (!e || !out || (n_records > 0 && !recv_dev) || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    if (n_records > (int64_t)e->max_children) DX_FAIL(DX_ERR_CAPACITY, "HDA*: received more children than max_pop_total * actions (raise max_pop_total)");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int p = e->parity, q = p ^ 1;
+    e->launches += dx_launch_hda_unpack(s, e->dom, e->d_ctl, (const uint8_t*)recv_dev, (uint32_t)n_records, e->child_state,
+                                        e->child_g, e->child_parent, e->child_action);
+    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
+                                           e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                           e->max_children, e->A);
+    e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
+                                        e->max_children, e->scan);
+    k_after_scan_v<<<1, 1, 0, s>>>(e->d_ctl, e->max_nodes);
+    e->launches += 1;
+    e->launches += dx_launch_scatter_kept_hda(s, e->dom, e->closed, e->d_ctl, e->child_state, e->child_g, e->child_slot,
+                                              e->child_flags, e->child_prefix, e->child_parent, e->child_action, e->node_state,
+                                              e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children);
+    DX_TRY(launch_heur_nodes(e, e->max_children));
+    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open, 1);
+    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles);
+    DX_TRY(sync_ctl(e));
+    uint32_t k = 0, goal = DX_NIL, nopen = 0;
+    unsigned long long ff = 0, ubk = DX_EMPTY64;
+    DX_CUDA(cudaMemcpy(&k, e->ia.k_pop, 4, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(&ff, e->ia.f_first, 8, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(&ubk, e->ia.ub_key, 8, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(&goal, e->ia.goal_node, 4, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(&nopen, e->ia.n_open, 4, cudaMemcpyDeviceToHost));
+    struct Local { int64_t k_popped; double f_first; double ub; int64_t goal_local; int64_t n_kept; int64_t open_size; int64_t children_sent; };
+    Local* o = reinterpret_cast<Local*>(out);
+    o->k_popped = k;
+    memcpy(&o->f_first, &ff, 8);
+    if (k == 0) o->f_first = INFINITY;
+    if (ubk == DX_EMPTY64) o->ub = INFINITY;
+    else { uint32_t b = (uint32_t)(ubk >> 32); float f; memcpy(&f, &b, 4); o->ub = (double)f; }
+    o->goal_local = goal == DX_NIL ? -1 : (int64_t)goal;
+    o->n_kept = e->h_ctl->n_kept;
+    o->open_size = nopen;
+    o->children_sent = e->hda_children_sent;
+    return DX_OK;
+}
+
+// Phase 3: identical bookkeeping on every rank from the reduced quantities.
+extern "C" int dx_hda_finish(dx_engine* e, int64_t k_total, double f_first_min, double ub_min, int64_t children_total,
+                             int32_t* finished) {
+    if (!e || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    const int p = e->parity, q = p ^ 1;
+    unsigned long long fbits = 0;
+    memcpy(&fbits, &f_first_min, 8);
+    const int has_ub = std::isfinite(ub_min) ? 1 : 0;
+    const float ubf = has_ub ? (float)ub_min : 0.f;
+    uint32_t ubits;
+    memcpy(&ubits, &ubf, 4);
+    e->launches += dx_launch_hda_finish(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, (unsigned long long)k_total,
+                                        fbits, ubits, has_ub, (unsigned long long)children_total);
+    e->parity = q;
+    DX_TRY(sync_ctl(e));
+    if (finished) *finished = e->h_ctl->n_unfinished == 0 ? 1 : 0;
+    return DX_OK;
+}
+
+// One node of the local shard: state row, global parent id (0xFFFFFFFF for the root), action, g.
+extern "C" int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint32_t* parent_global, int32_t* action, float* g) {
+    if (!e || local_id < 0) DX_FAIL(DX_ERR_ARG, "bad argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    if (local_id >= (int64_t)e->h_ctl->node_count) DX_FAIL(DX_ERR_ARG, "node id out of range");
+    std::vector<uint8_t> row(e->SP);
+    uint8_t act = 0;
+    DX_CUDA(cudaMemcpy(row.data(), e->node_state + (size_t)local_id * e->SP, e->SP, cudaMemcpyDeviceToHost));
+    if (state) memcpy(state, row.data(), e->S);
+    if (parent_global) DX_CUDA(cudaMemcpy(parent_global, e->node_parent + local_id, 4, cudaMemcpyDeviceToHost));
+    if (action) { DX_CUDA(cudaMemcpy(&act, e->node_action + local_id, 1, cudaMemcpyDeviceToHost)); *action = act; }
+    if (g) DX_CUDA(cudaMemcpy(g, e->node_g + local_id, 4, cudaMemcpyDeviceToHost));
     return DX_OK;
 }

@@ -29,7 +29,7 @@ static_assert(OPEN_THREADS * ITEMS == DX_SORT_TILE, "tile size");
 __global__ void __launch_bounds__(1024)
 k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
        uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
-       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open) {
+       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open, int kept_is_total) {
     __shared__ uint32_t s_tot[4][1024];
     if (ctl->error) return;
     const int I = ctl->n_inst;
@@ -38,7 +38,9 @@ k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix
     uint32_t sm = 0, sk = 0, sn = 0, st = 0;
     for (int i = lo; i < hi; ++i) {
         const bool act = ia.active[i] != 0;
-        const uint32_t kept = prefix[pop_off_cur[i + 1] * child_mult] - prefix[pop_off_cur[i] * child_mult];
+        // HDA*: the filtered batch is what this rank RECEIVED, unrelated to its popped list (single instance)
+        const uint32_t kept = kept_is_total ? ctl->n_kept
+                                            : prefix[pop_off_cur[i + 1] * child_mult] - prefix[pop_off_cur[i] * child_mult];
         const uint32_t m = act ? kept * push_mult : 0;
         const uint32_t n = act ? (open_off_cur[i + 1] - open_off_cur[i]) : 0;   // OPEN of a finished instance is dropped
         const uint32_t t = n + m;
@@ -69,9 +71,9 @@ k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix
 
 int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                    uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
-                   uint32_t max_pop, uint32_t max_open) {
+                   uint32_t max_pop, uint32_t max_open, int kept_is_total) {
     k_plan<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, child_mult,
-                              push_mult, max_pop, max_open);
+                              push_mult, max_pop, max_open, kept_is_total);
     return 1;
 }
 

@@ -1,0 +1,169 @@
+"""HDA*-style hash-distributed batch weighted A*: ONE search instance over W GPUs (BASELINE config 5).
+
+Not in the reference (its search is single-process Python); semantics follow graph_search.py with the
+distribution rules of SURVEY.md 8e: owner(state) = hash(state) mod W owns the state's CLOSED entry, node and
+OPEN entry; per iteration every rank pops its local top-(B/W), expands, and routes each child record to its
+owner with one all-to-all; lb / ub / finished() are evaluated on globally reduced quantities so every rank
+takes the same decision in the same iteration.  Local top-(B/W) per shard is not the global top-B, so costs /
+node counts are compared with the single-GPU engine statistically, not bit-for-bit (W = 1 IS bit-identical).
+
+Two transports with identical engine calls:
+  * `dist` given       one process per GPU, `torch.distributed` (NCCL): `all_to_all_single` moves the records,
+                       `all_gather` the per-rank scalars
+  * `dist` is None     W ranks emulated in one process on one GPU (the engines run one after the other, so
+                       nothing ever waits on a concurrently running kernel); used by the single-GPU tests
+"""
+from typing import Any, List, Optional
+
+import numpy as np
+import torch
+
+from deepxube_b200 import _lib
+from deepxube_b200.base.pathfind_fns import load_nnet_into_engine
+
+
+class HdaSearch:
+    def __init__(self, domain_name: str, dim: int, world: int, batch_size: int, weight: float, nnet: Any = None,
+                 precision: str = "fp32", max_nodes_per_rank: int = 1 << 22, dist: Optional[Any] = None,
+                 device: Optional[int] = None, capacity_slack: float = 2.0):
+        self.dist = dist
+        self.world = world
+        self.weight = weight
+        self.batch_local = max(1, -(-batch_size // world))
+        if dist is not None:
+            assert dist.get_world_size() == world
+            self.local_ranks = [dist.get_rank()]
+        else:
+            self.local_ranks = list(range(world))
+        dev = _lib.current_device() if device is None else device
+        self.tdev = torch.device("cuda", dev)
+        mode = _lib.DX_HEUR_ZERO if nnet is None else (_lib.DX_HEUR_NET_BF16 if precision == "bf16" else _lib.DX_HEUR_NET_FP32)
+        self.engines: List[_lib.Engine] = []
+        for r in self.local_ranks:
+            eng = _lib.Engine(domain_name, dim, "graph_v", mode, max_instances=1,
+                              max_pop_total=int(np.ceil(self.batch_local * capacity_slack)) + 64,
+                              max_nodes=min(max_nodes_per_rank, (1 << 28) - 1), device=dev)
+            if nnet is not None:
+                load_nnet_into_engine(eng, nnet)
+            eng.hda_config(r, world)
+            self.engines.append(eng)
+        e0 = self.engines[0]
+        self.rec = e0.hda_record_bytes()
+        self.num_actions = e0.num_actions
+        self.cap_records = (int(np.ceil(self.batch_local * capacity_slack)) + 64) * self.num_actions
+        self.send = [torch.empty(self.cap_records * self.rec, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
+        self.recv = [torch.empty(self.cap_records * self.rec, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
+        self.itr = 0
+        self.num_nodes_generated = 0
+        self.goal = None          # (ub, rank, local id)
+        self.finished = False
+
+    # ---- transports --------------------------------------------------------------------------------------
+    def _exchange(self, counts: List[np.ndarray]) -> List[int]:
+        """counts[i][dst] = records local rank i sends to dst.  Fills self.recv, returns records received."""
+        rec = self.rec
+        if self.dist is None:
+            n_recv = []
+            for di, dst in enumerate(self.local_ranks):
+                off = 0
+                for si, _ in enumerate(self.local_ranks):
+                    c = int(counts[si][dst])
+                    s0 = int(counts[si][:dst].sum())
+                    if c:
+                        self.recv[di][off * rec:(off + c) * rec].copy_(self.send[si][s0 * rec:(s0 + c) * rec])
+                    off += c
+                if off > self.cap_records:
+                    raise _lib.DxError("HDA*: receive buffer too small (raise capacity_slack)")
+                n_recv.append(off)
+            torch.cuda.synchronize(self.tdev)
+            return n_recv
+        dist = self.dist
+        mine = torch.tensor(counts[0], dtype=torch.int64, device=self.tdev)
+        allc = [torch.empty_like(mine) for _ in range(self.world)]
+        dist.all_gather(allc, mine)
+        allc = torch.stack(allc).cpu().numpy()                     # allc[src][dst]
+        r = self.local_ranks[0]
+        in_split = [int(c) * rec for c in counts[0]]
+        out_split = [int(allc[src][r]) * rec for src in range(self.world)]
+        n = sum(out_split) // rec
+        if n > self.cap_records:
+            raise _lib.DxError("HDA*: receive buffer too small (raise capacity_slack)")
+        dist.all_to_all_single(self.recv[0][: n * rec], self.send[0][: int(counts[0].sum()) * rec], out_split, in_split)
+        torch.cuda.synchronize(self.tdev)
+        return [n]
+
+    def _gather_locals(self, locs: List[Any]) -> List[Any]:
+        """Per-rank scalars of every rank, in rank order: rows of (k, f_first, ub, goal_local, children_sent)."""
+        rows = [[float(l.k_popped), l.f_first, l.ub, float(l.goal_local), float(l.children_sent)] for l in locs]
+        if self.dist is None:
+            return rows
+        t = torch.tensor(rows[0], dtype=torch.float64, device=self.tdev)
+        out = [torch.empty_like(t) for _ in range(self.world)]
+        self.dist.all_gather(out, t)
+        return [o.cpu().tolist() for o in out]
+
+    # ---- search ---------------------------------------------------------------------------------------------
+    def start(self, state: np.ndarray, goal: np.ndarray) -> None:
+        for eng in self.engines:
+            eng.reset()
+            eng.hda_add_instance(state, goal, self.batch_local, self.weight)
+        self.itr, self.num_nodes_generated, self.goal, self.finished = 0, 0, None, False
+
+    def step(self) -> bool:
+        counts = [eng.hda_expand(self.send[i].data_ptr(), self.send[i].numel(), self.world) for i, eng in enumerate(self.engines)]
+        n_recv = self._exchange(counts)
+        locs = [eng.hda_absorb(self.recv[i].data_ptr(), n_recv[i]) for i, eng in enumerate(self.engines)]
+        rows = self._gather_locals(locs)
+        k_total = int(sum(r[0] for r in rows))
+        f_first_min = min(r[1] for r in rows)
+        children = int(sum(r[4] for r in rows))
+        best = min(((r[2], rank, int(r[3])) for rank, r in enumerate(rows) if r[3] >= 0), default=None)
+        ub_min = best[0] if best is not None else float("inf")
+        self.goal = best
+        fins = [eng.hda_finish(k_total, f_first_min, ub_min, children) for eng in self.engines]
+        self.itr += 1
+        self.num_nodes_generated += children
+        self.finished = fins[0]
+        return self.finished
+
+    def solve(self, state: np.ndarray, goal: np.ndarray, max_itrs: Optional[int] = None) -> dict:
+        self.start(state, goal)
+        while not self.finished and (max_itrs is None or self.itr < max_itrs):
+            self.step()
+        out = dict(iterations=self.itr, num_nodes_generated=self.num_nodes_generated, solved=self.goal is not None,
+                   path_cost=float("inf"), actions=None)
+        if self.goal is not None:
+            out["path_cost"] = float(self.goal[0])
+            out["actions"] = self.get_path()
+        return out
+
+    def _node(self, rank: int, local_id: int):
+        """(parent global id or None, action) of node `local_id` on `rank`, known to every rank."""
+        if self.dist is None:
+            _, par, act, _ = self.engines[self.local_ranks.index(rank)].hda_node(local_id)
+            return par, act
+        obj = [None]
+        if self.local_ranks[0] == rank:
+            _, par, act, _ = self.engines[0].hda_node(local_id)
+            obj = [(par, act)]
+        self.dist.broadcast_object_list(obj, src=rank)
+        return obj[0]
+
+    def get_path(self) -> List[int]:
+        """Parent walk across shards (deepxube/base/pathfinding.py:93-120 with global node ids)."""
+        assert self.goal is not None
+        _, rank, nid = self.goal
+        acts: List[int] = []
+        while True:
+            par, act = self._node(rank, nid)
+            if par is None:
+                break
+            acts.append(act)
+            rank, nid = par >> 28, par & ((1 << 28) - 1)
+        acts.reverse()
+        return acts
+
+    def close(self) -> None:
+        for eng in self.engines:
+            eng.close()
+        self.engines = []

@@ -185,6 +185,31 @@ int dx_get_stage_calls(dx_engine* e, int64_t* calls, int32_t cap);
 /* Device time (ms, CUDA events on the engine stream) of the last dx_run call. */
 int dx_last_run_ms(dx_engine* e, float* ms);
 
+/* ---- HDA*-style hash-distributed single search (one instance over `world` ranks, graph_v, device heuristic) ----
+ * Not present in the reference (its only multi-GPU mechanism is nn.DataParallel,
+ * deepxube/factories/pathfind_fns_factory.py:99-104); semantics per rank are those of graph_search.py with
+ * lb / ub / finished() evaluated on globally reduced quantities.  owner(state) = hash(state) mod world.
+ * Per iteration:  dx_hda_expand -> all-to-all of the record buffers (host layer: NCCL) -> dx_hda_absorb ->
+ * reduce {sum k_popped, min f_first, min ub, sum children_sent} over ranks -> dx_hda_finish.
+ * Record = state row + g + parent global id ((rank << 28) | local id) + action; dx_hda_record_bytes gives its size. */
+typedef struct dx_hda_local {
+    int64_t k_popped;        /* nodes this rank popped for the next iteration                     */
+    double f_first;          /* f of its first popped node (inf if none)                          */
+    double ub;               /* g of the best solved node this rank has popped so far (inf if none) */
+    int64_t goal_local;      /* local id of that node, -1 if none                                 */
+    int64_t n_kept;          /* received children that passed the CLOSED filter                   */
+    int64_t open_size;       /* local OPEN entries                                                */
+    int64_t children_sent;   /* children this rank generated this iteration                       */
+} dx_hda_local;
+int dx_hda_config(dx_engine* e, int32_t rank, int32_t world);
+int dx_hda_record_bytes(dx_engine* e, int32_t* rec_bytes);
+int dx_hda_owner(dx_engine* e, const uint8_t* state, int32_t* owner);
+int dx_hda_add_instance(dx_engine* e, const uint8_t* state, const uint8_t* goal, int32_t batch_local, double weight);
+int dx_hda_expand(dx_engine* e, void* send_dev, int64_t send_cap_bytes, int64_t* counts);
+int dx_hda_absorb(dx_engine* e, const void* recv_dev, int64_t n_records, dx_hda_local* out);
+int dx_hda_finish(dx_engine* e, int64_t k_total, double f_first_min, double ub_min, int64_t children_total, int32_t* finished);
+int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint32_t* parent_global, int32_t* action, float* g);
+
 #ifdef __cplusplus
 }
 #endif

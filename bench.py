@@ -219,7 +219,6 @@ def main() -> None:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
     from deepxube_b200 import _lib as L
-    from deepxube_b200.search_api import solve_batch_e2e  # reference-facing API (PathFind mirror)
     G, ITERS, B = args.insts_per_step, args.max_itrs, 10000
     mode = L.DX_HEUR_NET_BF16 if args.precision == "bf16" else L.DX_HEUR_NET_FP32
     sd = random_weights(0)
@@ -269,17 +268,43 @@ def main() -> None:
     calls = eng.stage_calls()
     eng.set_profiling(False)
 
-    # ---- pass 2: end-to-end through the reference-facing API with host buffers ---------------------------
+    # ---- pass 2: end-to-end through the reference-facing API (registries -> PathFind -> C ABI), host objects ----
+    # the `solve` loop of the reference (deepxube/_solve.py:146-160) with G instances per PathFind: make_instances
+    # from host State/Goal objects (H2D inside), one Python-level step() per iteration (status D2H inside).
+    eng.close()
+    import deepxube_b200  # noqa: F401
+    from deepxube_b200.domains.cube3 import Cube3Goal
+    from deepxube_b200.factories.domain_factory import get_domain_from_arg
+    from deepxube_b200.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict
+    from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+    domain, dname = get_domain_from_arg("cube3")
+    pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv,resnet_fc.1000H_4B_bn"], precision=args.precision)
+    pfns.heurv.nnet.load_state_dict(sd)
+    pathfind = get_pathfind_from_arg(domain, pfns, "graph.10000B_0.6W")[0]
+    pathfind._max_nodes = int(G * B * ACTS * (ITERS + 1) * 0.95) + 1024
+
+    def e2e_step(step_idx: int) -> int:
+        s, g = pick(step_idx)
+        pathfind.reset()
+        insts = pathfind.make_instances(domain.rows_to_states(s), [Cube3Goal(x) for x in g], None, True)
+        pathfind.add_instances(insts)
+        itrs = 0
+        while not min(x.finished() for x in pathfind.instances) and itrs < ITERS:
+            pathfind.step()
+            itrs += 1
+        return int(sum(x.num_nodes_generated for x in pathfind.instances))
+
+    e2e_step(0)                                   # engine creation + graph capture outside the timed region
     barrier()
     t0 = time.perf_counter()
-    e2e_nodes, h2d, d2h = 0, 0, 0
+    e2e_nodes = 0
     for k in range(args.steps):
-        s, g = pick(args.warmup + k)
-        n_k, h2d_k, d2h_k = solve_batch_e2e(eng, s, g, B, 0.6, ITERS)
-        e2e_nodes += n_k
-        h2d, d2h = h2d_k, d2h_k
+        e2e_nodes += e2e_step(args.warmup + k)
     barrier()
     e2e_s = time.perf_counter() - t0
+    h2d = int(G * 54 * 2 + G * 12)                # start + goal rows, batch sizes and weights
+    d2h = int(ITERS * G * 56)                     # dx_inst_status of every instance after every step()
+    pathfind.close()
 
     # ---- reduce over ranks: max time, sum of work -----------------------------------------------------------
     tot = torch.tensor([float(nodes), float(e2e_nodes), float(evals), float(launches)], device="cuda", dtype=torch.float64)
@@ -318,7 +343,7 @@ def main() -> None:
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),
                 "clocks": clocks,
                 "e2e": {"value": e2e_val, "unit": "nodes/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
-                        "api": "GraphSearch make_instances/step/status via libdxb200 C ABI, host buffers"},
+                        "api": "get_pathfind_from_arg('graph.10000B_0.6W') -> make_instances/add_instances/step() per iteration from host State objects"},
                 "gpu_launches": int(tot[3]), "roofline": roof,
                 "heur_evals": int(tot[2]), "nodes_generated": int(tot[0]), "wall_s_value_pass": wall_value_pass}
         if not args.no_cpu_baseline:
@@ -329,7 +354,6 @@ def main() -> None:
             line["cpu_baseline"] = {"value": n_cpu / s_cpu, "unit": "nodes/s", "cores": threads, "kind": "port",
                                     "sample": f"1 instance x {args.ref_itrs} iterations ({n_cpu} nodes, {s_cpu:.1f} s) of the same workload"}
         print(json.dumps(line), flush=True)
-    eng.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()

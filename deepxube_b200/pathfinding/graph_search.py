@@ -246,6 +246,14 @@ class GraphSearch(PathFind):
     def stage_times(self) -> Dict[str, float]:
         return self._engine.stage_ms() if self._engine is not None else {}
 
+    def reset(self) -> None:
+        """Extension: drop all instances but keep the engine (buffers, loaded weights, captured graphs) --
+        what `solve` gets in the reference by constructing a fresh, cheap PathFind per instance."""
+        if self._engine is not None:
+            self._engine.reset()
+        self.instances = []
+        self.itr = 0
+
     def close(self) -> None:
         if self._engine is not None:
             self._engine.close()

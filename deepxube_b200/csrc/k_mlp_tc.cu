@@ -23,7 +23,19 @@
 
 #define TC_BM 128
 #define TC_BK 64
-#define TC_STAGES 4
+#ifndef TC_STAGES
+#define TC_STAGES 4          // operand ring depth (48 KB per stage at BN = 256)
+#endif
+#ifndef TC_NBUF
+#define TC_NBUF 2            // epilogue staging buffers per warp, for outputs and for residual chunks (power of 2)
+#endif
+#if TC_NBUF == 2
+#define TC_NBUF_M1 "1"
+#elif TC_NBUF == 4
+#define TC_NBUF_M1 "3"
+#else
+#error "TC_NBUF must be 2 or 4"
+#endif
 #define TC_THREADS 256
 #define TC_UMMA_K 16
 
@@ -86,6 +98,10 @@ __device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
+__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
+    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
+                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
+}
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
 }
@@ -122,7 +138,7 @@ struct TcSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFF = TC_STAGES * STAGE_BYTES;
     static constexpr int EPI_BUF = 32 * 64;              // one 32-row x 32-column bf16 chunk
-    static constexpr int EPI_WARP_BYTES = 4 * EPI_BUF;   // per epilogue warp: 2 output + 2 residual buffers
+    static constexpr int EPI_WARP_BYTES = 2 * TC_NBUF * EPI_BUF;   // per epilogue warp: TC_NBUF output + TC_NBUF residual buffers
     static constexpr int BAR_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
     static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
@@ -148,8 +164,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
     auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-    auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + 2 * q + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 8);
+    auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + TC_NBUF * q + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 4 * TC_NBUF);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -160,7 +176,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (threadIdx.x == 0) {
         for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-        for (int q = 0; q < 4; ++q) { mbar_init(res_bar(q, 0), 1); mbar_init(res_bar(q, 1), 1); }
+        for (int q = 0; q < 4; ++q)
+            for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(q, b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {
@@ -232,17 +249,17 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);
         constexpr int NCH = BN / 32;
-        uint32_t rphase0 = 0, rphase1 = 0;
+        uint32_t rphase = 0;                     // bit b = parity the next wait on residual buffer b expects
         uint32_t lt = 0;
         for (int t = cl_id; t < total; t += n_cl, ++lt) {
             const int as = lt & 1;
             const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + q * 32;
-            if (has_res && lane == 0) {          // residual chunks 0 and 1 of this tile
+            if (has_res && lane == 0) {          // the first TC_NBUF residual chunks of this tile
 #pragma unroll
-                for (int b = 0; b < 2; ++b) {
+                for (int b = 0; b < TC_NBUF && b < NCH; ++b) {
                     mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
-                    tma_load_2d(epi_base + (2 + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + b * 32, row0);
+                    tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + b * 32, row0);
                 }
             }
             mbar_wait(tfull_bar(as), (lt >> 1) & 1u);
@@ -250,17 +267,17 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
             auto process = [&](const uint32_t* v, int c) {
-                const int b = c & 1;
+                const int b = c & (TC_NBUF - 1);
                 const int col = n0 + c * 32;
                 if (has_res) {
-                    mbar_wait(res_bar(q, b), b ? rphase1 : rphase0);
-                    if (b) rphase1 ^= 1u; else rphase0 ^= 1u;
+                    mbar_wait(res_bar(q, b), (rphase >> b) & 1u);
+                    rphase ^= 1u << b;
                 }
-                // the TMA store that last read output buffer b (two chunks ago) must be done with it
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 1;" ::: "memory");
+                // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
+                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read " TC_NBUF_M1 ";" ::: "memory");
                 __syncwarp();
                 const float4* b4 = reinterpret_cast<const float4*>(bias + col);
-                const uint8_t* rrow = epi_ptr + (2 + b) * SM::EPI_BUF + lane * 64;
+                const uint8_t* rrow = epi_ptr + (TC_NBUF + b) * SM::EPI_BUF + lane * 64;
                 uint8_t* crow = epi_ptr + b * SM::EPI_BUF + lane * 64;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {      // 8 columns = one 16-byte chunk per group
@@ -295,9 +312,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 if (lane == 0) {
                     tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    if (has_res && c + 2 < NCH) {      // all lanes are past their reads of residual buffer b
+                    if (has_res && c + TC_NBUF < NCH) {      // all lanes are past their reads of residual buffer b
                         mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
-                        tma_load_2d(epi_base + (2 + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + (c + 2) * 32, row0);
+                        tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + (c + TC_NBUF) * 32, row0);
                     }
                 }
             };

@@ -86,6 +86,7 @@ SIGNATURES = {
     "dx_get_stage_ms": (C.c_int, [_engp, _f32p, C.c_int32]),
     "dx_get_stage_calls": (C.c_int, [_engp, C.POINTER(C.c_int64), C.c_int32]),
     "dx_last_run_ms": (C.c_int, [_engp, _f32p]),
+    "dx_debug_tc_profile": (C.c_int, [_engp, C.POINTER(C.c_uint64)]),
     "dx_hda_config": (C.c_int, [_engp, C.c_int32, C.c_int32]),
     "dx_hda_record_bytes": (C.c_int, [_engp, _i32p]),
     "dx_hda_owner": (C.c_int, [_engp, _u8p, _i32p]),
@@ -323,6 +324,11 @@ class Engine:
         par, act, g = C.c_uint32(), C.c_int32(), C.c_float()
         check(self._lib.dx_hda_node(self._h, local_id, _p(st, _u8p), C.byref(par), C.byref(act), C.byref(g)))
         return st, (None if par.value == 0xFFFFFFFF else par.value), act.value, g.value
+
+    def tc_profile(self) -> list:
+        arr = (C.c_uint64 * 16)()
+        check(self._lib.dx_debug_tc_profile(self._h, arr))
+        return [int(x) for x in arr]
 
     def bench_heur(self, n: int, reps: int) -> float:
         ms = C.c_float()

@@ -1323,3 +1323,11 @@ extern "C" int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint3
     if (g) DX_CUDA(cudaMemcpy(g, e->node_g + local_id, 4, cudaMemcpyDeviceToHost));
     return DX_OK;
 }
+
+int dx_tc_profile_read(unsigned long long* out16);   // k_mlp_tc.cu
+extern "C" int dx_debug_tc_profile(dx_engine* e, uint64_t* out8) {   /* out8: 16 entries */
+    if (!e || !out8) DX_FAIL(DX_ERR_ARG, "null argument");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    return dx_tc_profile_read(reinterpret_cast<unsigned long long*>(out8));
+}

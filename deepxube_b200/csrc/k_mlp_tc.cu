@@ -3,16 +3,19 @@
 // folded at load time); only the arithmetic type of the H x H contractions changes.
 //
 // One GEMM kernel, launched once per layer:  C[M, N] = act(A[M, K] . W[N, K]^T + bias (+ R))
-//   * A (activations, row-major = K-major) and W (nn.Linear weight [out, in] = K-major) are streamed by
-//     TMA (cp.async.bulk.tensor, 128-byte swizzle) into a 4-stage shared-memory ring,
-//   * one elected thread issues tcgen05.mma.cta_group::1.kind::f16, 128 x BN x 16 per instruction, into one
-//     of two TMEM accumulator stages (2 x BN columns),
-//   * four epilogue warps drain the other accumulator stage with tcgen05.ld (32 lanes x 32 columns per
-//     instruction, software-pipelined one chunk ahead), add bias / residual, apply ReLU, and write bf16.
-//     Each warp stages its 32 x 32 chunk in a private, 64-byte-swizzled shared-memory buffer and moves it
-//     with TMA (bulk tensor store; the residual chunk arrives by TMA load two chunks ahead), so every
-//     global access of the epilogue is a full-line transfer instead of 32 strided row accesses,
-//   * persistent CTAs (one per SM) walk the (m, n) tiles; M is read from the device control block.
+//   * CTA pairs (cluster of 2, `tcgen05.mma.cta_group::2`): a pair owns a 256 x BN output tile; each CTA holds its
+//     128 A rows and HALF of the weight tile (BN/2 rows) in shared memory, so a k-block costs each SM 32 KB of TMA
+//     writes and 8 KB of operand reads per MMA instead of 48 KB / 12 KB -- shared-memory bandwidth, not L2 or
+//     HBM, is what capped the single-CTA version (measured: DESIGN.md section 5),
+//   * A (activations, K-major) and W (nn.Linear weight [out, in] = K-major) are streamed by TMA (128-byte swizzle)
+//     into a 5-stage shared-memory ring; both CTAs' loads complete on the LEADER's barrier,
+//   * one thread of the leader CTA issues the MMAs (256 x BN x 16 per instruction) into one of two TMEM
+//     accumulator stages; commits are multicast to both CTAs' barriers,
+//   * eight epilogue warps per CTA (two per TMEM lane quarter, alternating 32-column chunks) drain their CTA's 128
+//     accumulator rows with tcgen05.ld (pipelined one chunk ahead), add bias / residual, apply ReLU and write bf16 through 64-byte-swizzled staging buffers and TMA
+//     (bulk tensor store; residual chunks arrive by TMA load TC_NBUF chunks ahead),
+//   * persistent clusters walk the tiles; M is read from the device control block.
+// CL = 1 keeps the single-CTA variant (128 x BN tiles, cta_group::1) for A/B measurements.
 // The one-hot input layer is a K = in_dim (padded to 64) GEMM over a bf16 one-hot matrix written by
 // k_onehot_bf16 (exact: the entries are 0 / 1).
 #include <cuda.h>
@@ -23,9 +26,6 @@
 
 #define TC_BM 128
 #define TC_BK 64
-#ifndef TC_STAGES
-#define TC_STAGES 4          // operand ring depth (48 KB per stage at BN = 256)
-#endif
 #ifndef TC_NBUF
 #define TC_NBUF 2            // epilogue staging buffers per warp, for outputs and for residual chunks (power of 2)
 #endif
@@ -36,8 +36,10 @@
 #else
 #error "TC_NBUF must be 2 or 4"
 #endif
-#define TC_THREADS 256
+#define TC_THREADS 384         // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+#define TC_EPI_WARPS 8
 #define TC_UMMA_K 16
+#define TC_PEER_MASK 0xFEFFFFFFu     // clears the CTA-rank bit of a shared::cluster address -> the leader CTA's copy
 
 struct TcPlan {
     CUtensorMap a_onehot;
@@ -47,9 +49,22 @@ struct TcPlan {
     CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
     int BN;
-    int CL;                      // CTAs per cluster (B tile multicast)
+    int CL;                      // CTAs per cluster: 2 = cta_group::2 pairs, 1 = single-CTA tiles
     int num_sms;
 };
+
+// Optional in-kernel wait accounting (build with -DTC_PROFILE): cycles the role threads spend blocked on each
+// barrier, summed over CTAs.  [0] MMA waits operands (full), [1] MMA waits accumulator (tmem empty),
+// [2] producer waits slot (empty), [3] epilogue waits accumulator (tmem full), [4] epilogue waits residual,
+// [5] epilogue waits TMA-store drain, [6] epilogue total, [7] MMA total.
+__device__ unsigned long long g_tc_prof[16];   // [8] epi tmem-load wait, [9] epi math+smem, [10] epi fence+sync, [11] epi TMA issue
+#ifdef TC_PROFILE
+#define TC_T0() const long long _t0 = clock64()
+#define TC_ACC(var) var += clock64() - _t0
+#else
+#define TC_T0()
+#define TC_ACC(var)
+#endif
 
 // ---------------------------------------------------------------------------------------------
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
@@ -57,17 +72,21 @@ __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)_
 __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) {
     asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
 }
+// Bounded wait: try_wait suspends up to ~10 ms per attempt; a barrier that does not complete within ~4 s is a
+// protocol bug, and the kernel traps (CUDA error on the host) instead of hanging the GPU.
 __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred P1;\n\t"
-        "LAB_WAIT:\n\t"
-        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1, %2;\n\t"
-        "@P1 bra DONE;\n\t"
-        "bra LAB_WAIT;\n\t"
-        "DONE:\n\t"
-        "}" ::"r"(bar), "r"(parity), "r"(0x989680u)
-        : "memory");
+    for (int attempt = 0; attempt < 400; ++attempt) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -75,9 +94,25 @@ __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t byt
 __device__ __forceinline__ void mbar_arrive(uint32_t bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
 }
+// arrive on the barrier at the same shared-memory offset in CTA `cta` of the cluster
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta)
+        : "memory");
+}
 __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1)
+                 : "memory");
+}
+// 2-CTA load: data lands in THIS CTA's shared memory, the bytes are counted on the LEADER CTA's barrier
+__device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & TC_PEER_MASK), "r"(c0), "r"(c1)
                  : "memory");
 }
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
@@ -85,34 +120,35 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
                  : "memory");
 }
-__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
-    asm volatile("cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster "
-                 "[%0], [%1, {%3, %4}], [%2], %5;"
-                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar), "r"(c0), "r"(c1), "h"(mask)
-                 : "memory");
-}
-__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t mask) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                 ::"r"(bar), "h"(mask) : "memory");
-}
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-__device__ __forceinline__ void tma_prefetch_l2_2d(const CUtensorMap* map, int c0, int c1) {
-    asm volatile("cp.async.bulk.prefetch.tensor.2d.L2.global [%0, {%1, %2}];"
-                 ::"l"(reinterpret_cast<uint64_t>(map)), "r"(c0), "r"(c1) : "memory");
-}
+template <int CL>
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
-    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    if (CL == 1)
+        asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
+    else       // arrives on the barrier at this offset in BOTH CTAs of the pair
+        asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+                     ::"r"(bar), "h"((uint16_t)3) : "memory");
 }
+template <int CL>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    asm volatile(
-        "{\n\t"
-        ".reg .pred p;\n\t"
-        "setp.ne.b32 p, %4, 0;\n\t"
-        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
-        "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
-        : "memory");
+    if (CL == 1)
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
+    else
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "setp.ne.b32 p, %4, 0;\n\t"
+            "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t"
+            "}" ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+            : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t* v) {
     asm volatile(
@@ -131,158 +167,197 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
     return (uint64_t)((smem_addr >> 4) & 0x3FFFu) | (1ull << 16) | (64ull << 32) | (1ull << 46) | (2ull << 61);
 }
 
-template <int BN>
+template <int BN, int CL>
 struct TcSmem {
+    static constexpr int STAGES = CL == 2 ? 5 : 3;
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-    static constexpr int B_BYTES = BN * TC_BK * 2;
+    static constexpr int B_BYTES = (BN / CL) * TC_BK * 2;          // a pair CTA holds half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-    static constexpr int EPI_OFF = TC_STAGES * STAGE_BYTES;
+    static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int EPI_BUF = 32 * 64;              // one 32-row x 32-column bf16 chunk
     static constexpr int EPI_WARP_BYTES = 2 * TC_NBUF * EPI_BUF;   // per epilogue warp: TC_NBUF output + TC_NBUF residual buffers
-    static constexpr int BAR_OFF = EPI_OFF + 4 * EPI_WARP_BYTES;
-    static constexpr int TOTAL = BAR_OFF + 256 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
+    static constexpr int BAR_OFF = EPI_OFF + TC_EPI_WARPS * EPI_WARP_BYTES;
+    static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
 
-// CL = CTAs per cluster (1 or 2).  With CL = 2 the two CTAs of a cluster work on vertically adjacent tiles
-// (same n, rows m and m+1): each loads its own A tile and HALF of the shared B (weight) tile, multicast into
-// both CTAs' shared memory, which cuts the L2 -> SM operand traffic per CTA from 48 KB to 32 KB per k-block.
-// A stage is reusable only when BOTH CTAs' MMAs have read it (empty barrier count 2, multicast commits).
 template <int BN, int CL>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
                int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu) {
     extern __shared__ uint8_t smem_raw[];
-    using SM = TcSmem<BN>;
+    using SM = TcSmem<BN, CL>;
+    constexpr int STAGES = SM::STAGES;
     if (ctl->error) return;
     const int M = (int)ctl->nn_n;
     if (M == 0) return;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + SM::BAR_OFF;
-    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2]; then the TMEM base address
+    // barriers: full[STAGES], empty[STAGES], tmem_full[2], tmem_empty[2], residual[4][TC_NBUF]; then the TMEM base address
     auto full_bar = [&](int s) { return bar_base + 8u * s; };
-    auto empty_bar = [&](int s) { return bar_base + 8u * (TC_STAGES + s); };
-    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + a); };
-    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * TC_STAGES + 2 + a); };
-    auto res_bar = [&](int q, int b) { return bar_base + 8u * (2 * TC_STAGES + 4 + TC_NBUF * q + b); };
-    const uint32_t tmem_slot = bar_base + 8u * (2 * TC_STAGES + 4 + 4 * TC_NBUF);
+    auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+    auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+    auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+    auto res_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 4 + TC_NBUF * ew + b); };
+    const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + TC_EPI_WARPS * TC_NBUF);
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t cta_rank = 0;
     if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
-    constexpr uint16_t MC_MASK = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), CL); }
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 4); }
-        for (int q = 0; q < 4; ++q)
-            for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(q, b), 1);
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // tmem_empty (leader's copy is the one the MMA thread waits on): one arrival per epilogue warp of the pair
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * CL); }
+        for (int ew = 0; ew < TC_EPI_WARPS; ++ew)
+            for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(ew, b), 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 2) {
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN));
-        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    if (warp == 2) {      // the same warp in both CTAs of a pair
+        if (CL == 1) {
+            asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+        } else {
+            asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN));
+            asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+        }
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
+    if (CL > 1) cluster_sync_all();          // peer barriers / TMEM exist before anything is signalled across CTAs
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    if (CL > 1) cluster_sync_all();          // peer barriers are initialised before any multicast lands
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
-    const int total = ((m_tiles + CL - 1) / CL) * n_tiles;       // tile groups of CL vertically adjacent tiles
+    const int total = ((m_tiles + CL - 1) / CL) * n_tiles;       // tile groups of CL vertically adjacent 128-row tiles
     const int kblocks = K / TC_BK;
     const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
 
     if (warp == 0) {
         if (lane == 0) {
-            // ---------------- TMA producer ----------------
+            // ---------------- TMA producer (every CTA: its A rows, its share of the weight tile) ----------------
             uint32_t it = 0;
+            long long w_empty = 0;
             for (int t = cl_id; t < total; t += n_cl) {
                 const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    mbar_wait(empty_bar(s), ((it / TC_STAGES) & 1u) ^ 1u);
+                    const int s = it % STAGES;
+                    { TC_T0(); mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u); TC_ACC(w_empty); }
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
-                    mbar_arrive_expect_tx(full_bar(s), SM::STAGE_BYTES);
-                    tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
-                    if (CL == 1)
+                    if (CL == 1) {
+                        mbar_arrive_expect_tx(full_bar(s), SM::STAGE_BYTES);
+                        tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
-                    else
-                        tma_load_2d_mc(b_dst + cta_rank * (SM::B_BYTES / CL), &tmB, full_bar(s), kb * TC_BK,
-                                       w_row0 + n0 + (int)cta_rank * (BN / CL), MC_MASK);
+                    } else {
+                        // the leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SM::STAGE_BYTES);
+                        tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                        tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)cta_rank * (BN / CL));
+                    }
                 }
             }
+#ifdef TC_PROFILE
+            atomicAdd(&g_tc_prof[2], (unsigned long long)w_empty);
+#endif
         }
     } else if (warp == 1) {
-        if (lane == 0) {
-            // ---------------- MMA issuer ----------------
-            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)(TC_BM >> 4) << 24);
+        if (lane == 0 && cta_rank == 0) {
+            // ---------------- MMA issuer (leader CTA only) ----------------
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128 * CL
+            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
+                                   ((uint32_t)((TC_BM * CL) >> 4) << 24);
             uint32_t it = 0, lt = 0;
+            long long w_full = 0, w_tempty = 0;
+#ifdef TC_PROFILE
+            const long long t_mma0 = clock64();
+#endif
             for (int t = cl_id; t < total; t += n_cl, ++lt) {
                 const int as = lt & 1;
-                mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u);
+                { TC_T0(); mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u); TC_ACC(w_tempty); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                    const int s = it % TC_STAGES;
-                    mbar_wait(full_bar(s), (it / TC_STAGES) & 1u);
+                    const int s = it % STAGES;
+                    { TC_T0(); mbar_wait(full_bar(s), (it / STAGES) & 1u); TC_ACC(w_full); }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t a_src = smem_base + s * SM::STAGE_BYTES, b_src = a_src + SM::A_BYTES;
                     const uint64_t adesc = make_sw128_desc(a_src), bdesc = make_sw128_desc(b_src);
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-                        umma_bf16(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    if (CL == 1) umma_commit(empty_bar(s));        // smem slot reusable once these MMAs have read it
-                    else umma_commit_mc(empty_bar(s), MC_MASK);    // ... in both CTAs of the cluster
+                        umma_bf16<CL>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit<CL>(empty_bar(s));        // slot reusable (in every CTA of the pair) once these MMAs have read it
                 }
-                umma_commit(tfull_bar(as));             // accumulator complete
+                umma_commit<CL>(tfull_bar(as));           // accumulator complete (signalled to every CTA of the pair)
             }
+#ifdef TC_PROFILE
+            atomicAdd(&g_tc_prof[0], (unsigned long long)w_full);
+            atomicAdd(&g_tc_prof[1], (unsigned long long)w_tempty);
+            atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - t_mma0));
+#endif
         }
     } else if (warp >= 4) {
-        // ---------------- epilogue (warps 4..7 <-> TMEM lane quarters 0..3) ----------------
-        const int q = warp - 4;
-        const uint32_t epi_base = smem_base + SM::EPI_OFF + q * SM::EPI_WARP_BYTES;
+        // ---------------- epilogue: 8 warps; warp 4 + ew drains TMEM lane quarter (ew & 3) -- a warp may only touch
+        // lanes 32 * (warp % 4) .. + 31 -- and the 32-column chunks c with (c & 1) == ew >> 2 ----------------
+        const int ew = warp - 4, q = ew & 3, h = ew >> 2;
+        const uint32_t epi_base = smem_base + SM::EPI_OFF + ew * SM::EPI_WARP_BYTES;
         uint8_t* epi_ptr = smem_raw + (epi_base - smem_u32(smem_raw));
         // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);
         constexpr int NCH = BN / 32;
         uint32_t rphase = 0;                     // bit b = parity the next wait on residual buffer b expects
         uint32_t lt = 0;
+        long long w_tfull = 0, w_res = 0, w_store = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0;
+#ifdef TC_PROFILE
+        const long long t_epi0 = clock64();
+#endif
         for (int t = cl_id; t < total; t += n_cl, ++lt) {
             const int as = lt & 1;
             const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
             const int row0 = m0 + q * 32;
-            if (has_res && lane == 0) {          // the first TC_NBUF residual chunks of this tile
+            if (has_res && lane == 0) {          // this warp's first TC_NBUF residual chunks of the tile
 #pragma unroll
-                for (int b = 0; b < TC_NBUF && b < NCH; ++b) {
-                    mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
-                    tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + b * 32, row0);
+                for (int b = 0; b < TC_NBUF && h + 2 * b < NCH; ++b) {
+                    mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
+                    tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (h + 2 * b) * 32, row0);
                 }
             }
-            mbar_wait(tfull_bar(as), (lt >> 1) & 1u);
+            { TC_T0(); mbar_wait(tfull_bar(as), (lt >> 1) & 1u); TC_ACC(w_tfull); }
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
             auto process = [&](const uint32_t* v, int c) {
-                const int b = c & (TC_NBUF - 1);
+                const int b = (c >> 1) & (TC_NBUF - 1);       // this warp's chunks are c = h, h + 2, ...
                 const int col = n0 + c * 32;
+                // bias first: with ~225 KB of shared memory in use the L1 keeps almost nothing, so these are L2 round
+                // trips; issued here, their latency overlaps the barrier waits below instead of stalling the math
+                float4 bv[8];
+                {
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
+                }
                 if (has_res) {
-                    mbar_wait(res_bar(q, b), (rphase >> b) & 1u);
+                    TC_T0();
+                    mbar_wait(res_bar(ew, b), (rphase >> b) & 1u);
+                    TC_ACC(w_res);
                     rphase ^= 1u << b;
                 }
-                // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
-                if (lane == 0) asm volatile("cp.async.bulk.wait_group.read " TC_NBUF_M1 ";" ::: "memory");
-                __syncwarp();
-                const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+                {   // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
+                    TC_T0();
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read " TC_NBUF_M1 ";" ::: "memory");
+                    __syncwarp();
+                    TC_ACC(w_store);
+                }
+#ifdef TC_PROFILE
+                const long long _tm0 = clock64();
+#endif
                 const uint8_t* rrow = epi_ptr + (TC_NBUF + b) * SM::EPI_BUF + lane * 64;
                 uint8_t* crow = epi_ptr + b * SM::EPI_BUF + lane * 64;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {      // 8 columns = one 16-byte chunk per group
                     float f[8];
-                    const float4 ba = __ldg(b4 + 2 * g), bb = __ldg(b4 + 2 * g + 1);
+                    const float4 ba = bv[2 * g], bb = bv[2 * g + 1];
                     f[0] = __uint_as_float(v[8 * g + 0]) + ba.x; f[1] = __uint_as_float(v[8 * g + 1]) + ba.y;
                     f[2] = __uint_as_float(v[8 * g + 2]) + ba.z; f[3] = __uint_as_float(v[8 * g + 3]) + ba.w;
                     f[4] = __uint_as_float(v[8 * g + 4]) + bb.x; f[5] = __uint_as_float(v[8 * g + 5]) + bb.y;
@@ -307,41 +382,70 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
                     *reinterpret_cast<uint4*>(crow + pos) = o;
                 }
+#ifdef TC_PROFILE
+                const long long _tm1 = clock64();
+                w_math += _tm1 - _tm0;
+#endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
                 __syncwarp();
+#ifdef TC_PROFILE
+                const long long _tm2 = clock64();
+                w_fence += _tm2 - _tm1;
+#endif
                 if (lane == 0) {
                     tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
                     asm volatile("cp.async.bulk.commit_group;" ::: "memory");
-                    if (has_res && c + TC_NBUF < NCH) {      // all lanes are past their reads of residual buffer b
-                        mbar_arrive_expect_tx(res_bar(q, b), SM::EPI_BUF);
-                        tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(q, b), n0 + (c + TC_NBUF) * 32, row0);
+                    if (has_res && c + 2 * TC_NBUF < NCH) {      // all lanes are past their reads of residual buffer b
+                        mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
+                        tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (c + 2 * TC_NBUF) * 32, row0);
                     }
                 }
+#ifdef TC_PROFILE
+                w_issue += clock64() - _tm2;
+#endif
             };
 
             uint32_t va[32], vb[32];
-            tmem_ld32(t_row, va);
+            tmem_ld32(t_row + (uint32_t)(h * 32), va);
 #pragma unroll 1
-            for (int c = 0; c < NCH; c += 2) {
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                tmem_ld32(t_row + (uint32_t)((c + 1) * 32), vb);
+            for (int c = h; c < NCH; c += 4) {
+                { TC_T0(); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); TC_ACC(w_ld); }
+                if (c + 2 < NCH) tmem_ld32(t_row + (uint32_t)((c + 2) * 32), vb);
                 process(va, c);
-                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (c + 2 < NCH) tmem_ld32(t_row + (uint32_t)((c + 2) * 32), va);
-                process(vb, c + 1);
+                if (c + 2 < NCH) {
+                    { TC_T0(); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); TC_ACC(w_ld); }
+                    if (c + 4 < NCH) tmem_ld32(t_row + (uint32_t)((c + 4) * 32), va);
+                    process(vb, c + 2);
+                }
             }
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
-            if (lane == 0) mbar_arrive(tempty_bar(as));
+            if (lane == 0) {                      // this warp's quarter of the accumulator stage is free again
+                if (CL == 1) mbar_arrive(tempty_bar(as));
+                else mbar_arrive_cluster(tempty_bar(as), 0);       // the MMA thread lives in the leader CTA
+            }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+#ifdef TC_PROFILE
+        if (lane == 0 && ew == 0) {
+            atomicAdd(&g_tc_prof[3], (unsigned long long)w_tfull);
+            atomicAdd(&g_tc_prof[4], (unsigned long long)w_res);
+            atomicAdd(&g_tc_prof[5], (unsigned long long)w_store);
+            atomicAdd(&g_tc_prof[6], (unsigned long long)(clock64() - t_epi0));
+            atomicAdd(&g_tc_prof[8], (unsigned long long)w_ld);
+            atomicAdd(&g_tc_prof[9], (unsigned long long)w_math);
+            atomicAdd(&g_tc_prof[10], (unsigned long long)w_fence);
+            atomicAdd(&g_tc_prof[11], (unsigned long long)w_issue);
+        }
+#endif
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (CL > 1) cluster_sync_all();          // no CTA exits while its peer may still multicast into it / signal it
+    if (CL > 1) cluster_sync_all();          // no CTA exits (or frees TMEM) while its peer may still use / signal it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+        if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+        else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
 
@@ -468,10 +572,10 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
         auto set_attr = [&](const void* f, int bytes) {
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         };
-        set_attr((const void*)k_gemm_bf16_tc<256, 1>, TcSmem<256>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2>, TcSmem<256>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1>, TcSmem<128>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2>, TcSmem<128>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2>, TcSmem<128, 2>::TOTAL);
         if (ce != cudaSuccess) {
             dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(ce));
             rc = DX_ERR_CUDA;
@@ -490,7 +594,8 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, c
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p->num_sms / p->CL * p->CL));
     cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = p->BN == 256 ? TcSmem<256>::TOTAL : TcSmem<128>::TOTAL;
+    cfg.dynamicSmemBytes = p->BN == 256 ? (p->CL == 2 ? TcSmem<256, 2>::TOTAL : TcSmem<256, 1>::TOTAL)
+                                        : (p->CL == 2 ? TcSmem<128, 2>::TOTAL : TcSmem<128, 1>::TOTAL);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -536,4 +641,12 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, out_h, out_q, absolute);
     ++launches;
     return launches;
+}
+
+// debug: read and clear the TC_PROFILE counters (zeros unless built with -DTC_PROFILE)
+int dx_tc_profile_read(unsigned long long* out16) {
+    if (cudaMemcpyFromSymbol(out16, g_tc_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return DX_ERR_CUDA;
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_tc_prof, z, sizeof(z)) != cudaSuccess) return DX_ERR_CUDA;
+    return DX_OK;
 }

@@ -185,6 +185,13 @@ int dx_get_stage_calls(dx_engine* e, int64_t* calls, int32_t cap);
 /* Device time (ms, CUDA events on the engine stream) of the last dx_run call. */
 int dx_last_run_ms(dx_engine* e, float* ms);
 
+/* Debug: per-role barrier-wait cycle counters of the tensor-core GEMM, summed over CTAs since the last call
+ * (all zero unless the library was built with -DTC_PROFILE): [0] MMA<-operands, [1] MMA<-accumulator free,
+ * [2] TMA producer<-slot free, [3] epilogue<-accumulator ready, [4] epilogue<-residual, [5] epilogue<-store drain,
+ * [6] epilogue warp total, [7] MMA thread total, [8] epilogue<-tcgen05.ld, [9] epilogue math + staging,
+ * [10] epilogue proxy fence + warp sync, [11] epilogue TMA issue; out8 must hold 16 entries. */
+int dx_debug_tc_profile(dx_engine* e, uint64_t* out8);
+
 /* ---- HDA*-style hash-distributed single search (one instance over `world` ranks, graph_v, device heuristic) ----
  * Not present in the reference (its only multi-GPU mechanism is nn.DataParallel,
  * deepxube/factories/pathfind_fns_factory.py:99-104); semantics per rank are those of graph_search.py with

@@ -335,7 +335,9 @@ def main() -> None:
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": (achieved / peak) if (achieved and peak) else None, "traffic": traffic, "traffic_note": traffic_note,
                 "peak_source": peaks["_source"] + " (sustained bf16, kernel timed inside a long step)",
-                "launches_timed": calls["gemm_hidden"], "avg_launch_ms": stage["gemm_hidden"] / max(calls["gemm_hidden"], 1),
+                # one CUDA-event interval brackets the 2*NB back-to-back hidden-layer launches of a network evaluation
+                "launches_timed": calls["gemm_hidden"] * (2 * NB if args.precision == "bf16" else 1),
+                "avg_launch_ms": stage["gemm_hidden"] / max(calls["gemm_hidden"] * (2 * NB if args.precision == "bf16" else 1), 1),
                 "network_tflops_dense_equiv": FLOP_PER_STATE * evals / (stage["heur"] / 1e3) / 1e12 if stage["heur"] > 0 else None,
                 "stage_ms_rank0": {k: round(v, 3) for k, v in stage.items()}}
         line = {"metric": "nodes_generated_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,

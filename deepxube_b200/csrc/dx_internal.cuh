@@ -164,6 +164,7 @@ struct SortBufs {
     uint32_t* ghist;      // [DX_NUM_DIGITS * 256] global digit histograms of the batch
     uint32_t* gbase;      // [DX_NUM_DIGITS * 256] exclusive bin offsets per digit position
     int max_tiles;
+    int num_digits;       // digit positions that can vary: 8 key bytes + the bytes max_instances - 1 occupies
 };
 
 struct MlpBufs {

@@ -211,6 +211,11 @@ struct dx_engine {
     long long stage_calls[ST_COUNT] = {0};
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
     cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one captured iteration per buffer parity
+    // the same iteration captured with the stage timers as event-record nodes (used while profiling is on)
+    cudaGraphExec_t graph_prof_exec[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> gev[2];   // begin/end pairs of the captured timers, per parity
+    std::vector<int> gev_stage[2];
+    int cap_prof = -1;                 // parity whose profiling graph is being captured, else -1
     int graph_launches = 0;
     bool use_graphs = true;
     float last_run_ms = 0.f;
@@ -236,6 +241,15 @@ static void stage_begin(dx_engine* e, int st) {
     if (!e->profiling) return;
     cudaEvent_t a;
     cudaEventCreate(&a);
+    if (e->cap_prof >= 0) {            // inside stream capture: a real event-record node, kept for every replay
+        cudaEventRecordWithFlags(a, e->stream, cudaEventRecordExternal);
+        auto& v = e->gev[e->cap_prof];
+        e->ev_open.push_back((int)v.size());
+        v.push_back(a);
+        v.push_back(nullptr);
+        e->gev_stage[e->cap_prof].push_back(st);
+        return;
+    }
     cudaEventRecord(a, e->stream);
     e->ev_open.push_back((int)e->ev.size());
     e->ev.push_back(a);
@@ -246,6 +260,12 @@ static void stage_end(dx_engine* e) {
     if (!e->profiling || e->ev_open.empty()) return;
     cudaEvent_t b;
     cudaEventCreate(&b);
+    if (e->cap_prof >= 0) {
+        cudaEventRecordWithFlags(b, e->stream, cudaEventRecordExternal);
+        e->gev[e->cap_prof][e->ev_open.back() + 1] = b;
+        e->ev_open.pop_back();
+        return;
+    }
     cudaEventRecord(b, e->stream);
     e->ev[e->ev_open.back() + 1] = b;
     e->ev_open.pop_back();
@@ -266,6 +286,18 @@ static void stage_collect(dx_engine* e) {
     e->ev.clear();
     e->ev_stage.clear();
     e->ev_open.clear();
+}
+
+// after a replay of the profiling graph of parity p has completed: add its captured intervals
+static void stage_collect_graph(dx_engine* e, int p) {
+    const auto& v = e->gev[p];
+    for (size_t i = 0; i + 1 < v.size(); i += 2) {
+        if (!v[i + 1]) continue;
+        float ms = 0;
+        if (cudaEventElapsedTime(&ms, v[i], v[i + 1]) != cudaSuccess) { cudaGetLastError(); continue; }
+        e->stage_ms[e->gev_stage[p][i / 2]] += ms;
+        e->stage_calls[e->gev_stage[p][i / 2]] += 1;
+    }
 }
 
 // kernel-level timing hooks used by the network launchers (nested inside the ST_HEUR stage)
@@ -377,6 +409,8 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     }
     A_(e->edge_tmp, P); A_(e->pop_solved, P);
     e->sort.max_tiles = dx_div_up(e->max_sort, DX_SORT_TILE);
+    e->sort.num_digits = 8;
+    for (uint32_t m = (uint32_t)(e->max_inst - 1); m && e->sort.num_digits < DX_NUM_DIGITS; m >>= 8) e->sort.num_digits += 1;
     A_(e->sort.hist, (size_t)256 * e->sort.max_tiles + 4096); A_(e->sort.ghist, DX_NUM_DIGITS * 256); A_(e->sort.gbase, DX_NUM_DIGITS * 256);
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
@@ -394,7 +428,11 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
     if (!e) return DX_OK;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (int k = 0; k < 2; ++k) if (e->graph_exec[k]) cudaGraphExecDestroy(e->graph_exec[k]);
+    for (int k = 0; k < 2; ++k) {
+        if (e->graph_exec[k]) cudaGraphExecDestroy(e->graph_exec[k]);
+        if (e->graph_prof_exec[k]) cudaGraphExecDestroy(e->graph_prof_exec[k]);
+        for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
+    }
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->stream) cudaStreamDestroy(e->stream);
@@ -648,18 +686,21 @@ static int full_step(dx_engine* e) {
     return DX_OK;
 }
 
-static int build_step_graphs(dx_engine* e) {
+static int build_step_graphs(dx_engine* e, bool prof) {
     const int p0 = e->parity;
     const long long l0 = e->launches;
     for (int k = 0; k < 2; ++k) {
         const int p = e->parity;
         cudaGraph_t g = nullptr;
         DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
+        e->cap_prof = prof ? p : -1;
         const int rc = full_step(e);                 // flips e->parity
+        e->cap_prof = -1;
+        e->ev_open.clear();
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         if (rc < 0) { if (g) cudaGraphDestroy(g); return rc; }
         if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        ce = cudaGraphInstantiate(&e->graph_exec[p], g, 0);
+        ce = cudaGraphInstantiate(prof ? &e->graph_prof_exec[p] : &e->graph_exec[p], g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
     }
@@ -680,19 +721,21 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     if (!e->run_ev[0]) { cudaEventCreate(&e->run_ev[0]); cudaEventCreate(&e->run_ev[1]); }
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
-    const bool use_graph = !e->profiling && e->use_graphs;
-    if (use_graph && !e->graph_exec[0]) DX_TRY(build_step_graphs(e));
+    const bool use_graph = e->use_graphs, prof = e->profiling;
+    if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
+    if (use_graph && prof && !e->graph_prof_exec[0]) { stage_collect(e); DX_TRY(build_step_graphs(e, true)); }
     cudaEventRecord(e->run_ev[0], e->stream);
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         if (use_graph) {
-            DX_CUDA(cudaGraphLaunch(e->graph_exec[e->parity], e->stream));
+            DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[e->parity] : e->graph_exec[e->parity], e->stream));
             e->launches += e->graph_launches;
             e->parity ^= 1;
         } else {
             DX_TRY(full_step(e));
         }
         ++done;
-        DX_TRY(sync_ctl(e));
+        DX_TRY(sync_ctl(e));                         // synchronises the stream
+        if (use_graph && prof) stage_collect_graph(e, e->parity ^ 1);
     }
     cudaEventRecord(e->run_ev[1], e->stream);
     DX_CUDA(cudaStreamSynchronize(e->stream));

@@ -50,6 +50,7 @@ struct TcPlan {
     __nv_bfloat16* onehot;
     int BN;
     int CL;                      // CTAs per cluster: 2 = cta_group::2 pairs, 1 = single-CTA tiles
+    int fuse_out;                // fold a scalar output layer into the last hidden GEMM (DXB200_FUSE_OUT=0 disables)
     int num_sms;
 };
 
@@ -180,11 +181,15 @@ struct TcSmem {
     static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
 
-template <int BN, int CL>
+// FUSE_OUT = true (last hidden layer of a scalar-output network): the epilogue does not store the activations; every
+// thread dots its row's 128 activated columns with the output layer's weight row and writes one fp32 partial
+// (partial[(2 * n_tile + h) * pstride + row]); k_out_final_bf16 adds the partials in a fixed order.
+template <int BN, int CL, bool FUSE_OUT>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
-               int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu) {
+               int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu,
+               const float* __restrict__ wout, float* __restrict__ partial, long long pstride) {
     extern __shared__ uint8_t smem_raw[];
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
@@ -326,6 +331,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
+            float oacc = 0.f;                     // FUSE_OUT: this row's partial output-layer dot product
             auto process = [&](const uint32_t* v, int c) {
                 const int b = (c >> 1) & (TC_NBUF - 1);       // this warp's chunks are c = h, h + 2, ...
                 const int col = n0 + c * 32;
@@ -337,13 +343,19 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                     for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
                 }
+                float4 wv[FUSE_OUT ? 8 : 1];
+                if (FUSE_OUT) {
+                    const float4* w4 = reinterpret_cast<const float4*>(wout + col);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) wv[g] = __ldg(w4 + g);
+                }
                 if (has_res) {
                     TC_T0();
                     mbar_wait(res_bar(ew, b), (rphase >> b) & 1u);
                     TC_ACC(w_res);
                     rphase ^= 1u << b;
                 }
-                {   // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
+                if (!FUSE_OUT) {   // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
                     TC_T0();
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read " TC_NBUF_M1 ";" ::: "memory");
                     __syncwarp();
@@ -376,25 +388,35 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
                     }
-                    uint4 o;
-                    __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
+                    if (FUSE_OUT) {
+                        const float4 wa = wv[FUSE_OUT ? 2 * g : 0], wb = wv[FUSE_OUT ? 2 * g + 1 : 0];
+                        oacc = fmaf(f[0], wa.x, oacc); oacc = fmaf(f[1], wa.y, oacc);
+                        oacc = fmaf(f[2], wa.z, oacc); oacc = fmaf(f[3], wa.w, oacc);
+                        oacc = fmaf(f[4], wb.x, oacc); oacc = fmaf(f[5], wb.y, oacc);
+                        oacc = fmaf(f[6], wb.z, oacc); oacc = fmaf(f[7], wb.w, oacc);
+                    } else {
+                        uint4 o;
+                        __nv_bfloat162* ob = reinterpret_cast<__nv_bfloat162*>(&o);
 #pragma unroll
-                    for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
-                    *reinterpret_cast<uint4*>(crow + pos) = o;
+                        for (int e = 0; e < 4; ++e) ob[e] = __floats2bfloat162_rn(f[2 * e], f[2 * e + 1]);
+                        *reinterpret_cast<uint4*>(crow + pos) = o;
+                    }
                 }
 #ifdef TC_PROFILE
                 const long long _tm1 = clock64();
                 w_math += _tm1 - _tm0;
 #endif
-                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
+                if (!FUSE_OUT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
                 __syncwarp();
 #ifdef TC_PROFILE
                 const long long _tm2 = clock64();
                 w_fence += _tm2 - _tm1;
 #endif
                 if (lane == 0) {
-                    tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
-                    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    if (!FUSE_OUT) {
+                        tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
                     if (has_res && c + 2 * TC_NBUF < NCH) {      // all lanes are past their reads of residual buffer b
                         mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
                         tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (c + 2 * TC_NBUF) * 32, row0);
@@ -418,6 +440,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     process(vb, c + 2);
                 }
             }
+            if (FUSE_OUT && row0 + lane < M) partial[(size_t)((n0 / BN) * 2 + h) * (size_t)pstride + (size_t)(row0 + lane)] = oacc;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {                      // this warp's quarter of the accumulator stage is free again
@@ -519,6 +542,25 @@ k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* _
     }
 }
 
+// Scalar-output networks: the last hidden GEMM wrote P = 2 * Hp / BN fp32 partial dot products per row
+// (partial[p * pstride + row]); out = max(sum_p partial + bias, 0), partials added in index order.
+__global__ void __launch_bounds__(256)
+k_out_final_bf16(NetDev net, const Ctl* __restrict__ ctl, const float* __restrict__ partial, long long pstride, int P,
+                 float* __restrict__ out_h, float* __restrict__ out_q, int absolute) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
+    if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
+    const float b = net.bout[0];
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        float acc = 0.f;
+        for (int p = 0; p < P; ++p) acc += partial[(size_t)p * (size_t)pstride + r];
+        const float v = fmaxf(acc + b, 0.f);
+        const size_t oi = absolute ? (size_t)(start + r) : (size_t)r;
+        if (out_q) out_q[oi] = v;
+        if (out_h) out_h[oi] = v;
+    }
+}
+
 // ---------------------------------------------------------------------------------------------
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
@@ -556,6 +598,8 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     p->BN = net.Hp >= 256 ? 256 : 128;
     p->CL = 2;
     if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : 2;
+    p->fuse_out = 1;
+    if (const char* c = getenv("DXB200_FUSE_OUT")) p->fuse_out = (c[0] == '0') ? 0 : 1;
     p->onehot = (__nv_bfloat16*)onehot_buf;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -572,10 +616,14 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
         auto set_attr = [&](const void* f, int bytes) {
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         };
-        set_attr((const void*)k_gemm_bf16_tc<256, 1>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, false>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, false>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, true>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, true>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, true>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, true>, TcSmem<128, 2>::TOTAL);
         if (ce != cudaSuccess) {
             dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(ce));
             rc = DX_ERR_CUDA;
@@ -586,16 +634,25 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     return DX_OK;
 }
 
-// c: output buffer index, r: residual buffer index or -1
+template <int BN, int CL, bool FUSE>
+static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& tc,
+                          const CUtensorMap& tr, const Ctl* ctl, int w_row0, int K, int N, const float* bias, int has_res,
+                          int relu, const float* wout, float* partial, long long pstride) {
+    cfg->dynamicSmemBytes = TcSmem<BN, CL>::TOTAL;
+    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, FUSE>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
+                       pstride);
+}
+
+// c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
+// (no activation store; buffer c is not written)
 static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
-                        int K, int N, const float* bias, int r, int c, int relu) {
+                        int K, int N, const float* bias, int r, int c, int relu, const float* wout = nullptr,
+                        float* partial = nullptr, long long pstride = 0) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
     cfg.gridDim = dim3((unsigned)(p->num_sms / p->CL * p->CL));
     cfg.blockDim = dim3(TC_THREADS);
-    cfg.dynamicSmemBytes = p->BN == 256 ? (p->CL == 2 ? TcSmem<256, 2>::TOTAL : TcSmem<256, 1>::TOTAL)
-                                        : (p->CL == 2 ? TcSmem<128, 2>::TOTAL : TcSmem<128, 1>::TOTAL);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
@@ -605,10 +662,19 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int has_res = r >= 0 ? 1 : 0;
-    if (p->BN == 256 && p->CL == 2) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<256, 2>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
-    else if (p->BN == 256) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<256, 1>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
-    else if (p->CL == 2) cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<128, 2>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
-    else cudaLaunchKernelEx(&cfg, k_gemm_bf16_tc<128, 1>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu);
+    const int sel = (p->BN == 256 ? 4 : 0) | (p->CL == 2 ? 2 : 0) | (partial ? 1 : 0);
+#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride
+    switch (sel) {
+        case 7: launch_gemm_t<256, 2, true>(DX_TC_ARGS); break;
+        case 6: launch_gemm_t<256, 2, false>(DX_TC_ARGS); break;
+        case 5: launch_gemm_t<256, 1, true>(DX_TC_ARGS); break;
+        case 4: launch_gemm_t<256, 1, false>(DX_TC_ARGS); break;
+        case 3: launch_gemm_t<128, 2, true>(DX_TC_ARGS); break;
+        case 2: launch_gemm_t<128, 2, false>(DX_TC_ARGS); break;
+        case 1: launch_gemm_t<128, 1, true>(DX_TC_ARGS); break;
+        default: launch_gemm_t<128, 1, false>(DX_TC_ARGS); break;
+    }
+#undef DX_TC_ARGS
 }
 
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
@@ -626,19 +692,32 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, net.b0, -1, ix, 0);
     ++launches;
     dx_prof_end();
+    // one timed interval around the 2 * num_blocks back-to-back hidden-layer launches (an event between
+    // every pair of launches costs ~3 % of the step; the average launch duration is interval / launches)
+    // scalar output (heurv): the H -> 1 output layer is folded into the epilogue of the last hidden GEMM, which then
+    // writes 2 * Hp / BN fp32 partials per row into the (otherwise unused) third activation buffer
+    const bool fuse = net.out_dim == 1 && net.num_blocks > 0 && p->fuse_out;
+    const int P = 2 * (Hp / p->BN);
+    dx_prof_begin(DX_ST_GEMM_RES);
     for (int b = 0; b < net.num_blocks; ++b) {
-        dx_prof_begin(DX_ST_GEMM_RES);
         launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
-        dx_prof_end();
-        dx_prof_begin(DX_ST_GEMM_RES);
-        launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
-        dx_prof_end();
+        if (fuse && b == net.num_blocks - 1)
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+                        net.wout, (float*)mb.xb[iz], mb.cap);
+        else
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
         launches += 2;
         int ti = ix; ix = iz; iz = ti;
     }
-    const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
-    const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);
-    k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, out_h, out_q, absolute);
+    dx_prof_end();
+    if (fuse) {
+        const int blocks = (int)min((long long)dx_div_up(max_rows, 256), (long long)148 * 8);
+        k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, (const float*)mb.xb[ix], mb.cap, P, out_h, out_q, absolute);
+    } else {
+        const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
+        const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);
+        k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, out_h, out_q, absolute);
+    }
     ++launches;
     return launches;
 }

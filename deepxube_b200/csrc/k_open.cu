@@ -323,7 +323,7 @@ int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp&
     k_radix_prepass<<<pre_blocks, OPEN_THREADS, 0, s>>>(ctl, sb);
     k_radix_flags<<<1, 256, 0, s>>>(ctl, sb);
     launches += 2;
-    for (int d = 0; d < DX_NUM_DIGITS; ++d) {
+    for (int d = 0; d < sb.num_digits; ++d) {      // higher instance-id bytes are constant zero: never launched
         k_radix_hist<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_tilescan<<<256, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_scatter<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);

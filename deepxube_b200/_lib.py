@@ -11,7 +11,7 @@ from typing import List, Optional, Tuple
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libdxb200.so")
+LIB_PATH = os.environ.get("DXB200_LIB") or os.path.join(HERE, "libdxb200.so")   # DXB200_LIB: A/B builds
 
 DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2}
 DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q = 0, 1

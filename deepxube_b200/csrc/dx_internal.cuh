@@ -107,6 +107,10 @@ struct NetDev {
     // bf16 copies for the tensor-core path
     void* w0_bf16;   // [Hp, in_dim_p]  K-major
     void* wres_bf16; // [num_blocks*2, Hp, Hp] K-major
+    // Bias folding of the tensor-core path: when H < Hp, activation columns H..H+2 hold 1.0 and weight columns
+    // H..H+2 hold a 3-piece bf16 split of the fp32 bias (hi + mid + lo == bias exactly), so the GEMM adds the bias.
+    int tc_fold;     // bit 0: hidden layers folded, bit 1: input layer folded
+    float* b0_tc;    // [Hp] first-layer bias for the unfolded input layer (carries the 1.0 of the ones columns), else nullptr
     void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16
 };
 

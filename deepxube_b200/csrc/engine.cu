@@ -418,6 +418,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP);
     A_(e->d_vals, std::max<size_t>((size_t)e->max_sort, P * e->A) + I * e->A);
 #undef A_
+    cudaDeviceSynchronize();                 // the legacy-stream table upload has landed before the engine stream runs
     r = reset_state(e);
     if (r < 0) { dx_engine_destroy(e); return r; }
     *out = e;
@@ -1175,29 +1176,87 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
 #define UP_(dst, vec) do { DX_TRY(e->alloc(&(dst), (vec).size())); \
         DX_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(float), cudaMemcpyHostToDevice)); } while (0)
     UP_(net.w0t, w0t); UP_(net.b0, b0); UP_(net.wres, wres); UP_(net.bres, bres); UP_(net.wout, wout); UP_(net.bout, bout);
-    // bf16 copies for the tensor-core path (first layer K-major [Hp, in_dim_p]; residual layers [l, Hp, Hp])
-    float* d_w0p = nullptr;
-    UP_(d_w0p, w0p);
 #undef UP_
-    uint16_t *w0b = nullptr, *wrb = nullptr;
-    DX_TRY(e->alloc(&w0b, w0p.size()));
-    DX_TRY(e->alloc(&wrb, wres.size()));
-    k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(d_w0p, w0b, w0p.size());
-    if (!wres.empty()) k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(net.wres, wrb, wres.size());
-    DX_CUDA(cudaStreamSynchronize(e->stream));
-    net.w0_bf16 = w0b;
-    net.wres_bf16 = wrb;
+    // bf16 copies for the tensor-core path (first layer K-major [Hp, in_dim_p]; residual layers [l, Hp, Hp]).
+    // Bias folding (NetDev::tc_fold): spare padding columns carry the bias through the GEMM itself.
+    net.tc_fold = 0;
+    net.b0_tc = nullptr;
+    if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
+        auto bf16r = [](float x) {                 // round to nearest even, as k_f32_to_bf16
+            uint32_t u; memcpy(&u, &x, 4);
+            u = (u + 0x7FFFu + ((u >> 16) & 1u)) & 0xFFFF0000u;
+            float y; memcpy(&y, &u, 4);
+            return y;
+        };
+        auto split3 = [&](float b, float* out3) {
+            out3[0] = bf16r(b);
+            out3[1] = bf16r(b - out3[0]);
+            out3[2] = bf16r(b - out3[0] - out3[1]);
+        };
+        const char* fenv = getenv("DXB200_FOLD_BIAS");            // =0: keep the explicit bias adds (A/B measurements)
+        const bool fold_h = Hp - H >= 3 && nb > 0 && !(fenv && fenv[0] == '0');
+        const bool fold_in = fold_h && in_dim_p - in_dim >= 3;
+        std::vector<float> wres_tc(wres);
+        if (fold_h) {
+            net.tc_fold |= 1;
+            for (int l = 0; l < 2 * nb; ++l) {
+                float* Wd = &wres_tc[(size_t)l * Hp * Hp];
+                for (int o = 0; o < H; ++o) split3(bres[(size_t)l * Hp + o], &Wd[(size_t)o * Hp + H]);
+                // ones columns of the output: produced by the GEMM in the plain layer, carried by the residual otherwise
+                if ((l & 1) == 0) for (int j = 0; j < 3; ++j) Wd[(size_t)(H + j) * Hp + H + j] = 1.f;
+            }
+            if (fold_in) {
+                net.tc_fold |= 2;
+                for (int o = 0; o < H; ++o) split3(b0[o], &w0p[(size_t)o * in_dim_p + in_dim]);
+                for (int j = 0; j < 3; ++j) w0p[(size_t)(H + j) * in_dim_p + in_dim + j] = 1.f;
+            } else {
+                std::vector<float> b0tc(b0);
+                for (int j = 0; j < 3; ++j) b0tc[H + j] = 1.f;
+                DX_TRY(e->alloc(&net.b0_tc, b0tc.size()));
+                DX_CUDA(cudaMemcpy(net.b0_tc, b0tc.data(), b0tc.size() * sizeof(float), cudaMemcpyHostToDevice));
+            }
+        }
+        uint16_t *w0b = nullptr, *wrb = nullptr;
+        DX_TRY(e->alloc(&w0b, w0p.size()));
+        DX_TRY(e->alloc(&wrb, wres_tc.size()));
+        float* tmp = nullptr;
+        const size_t tmp_n = std::max(w0p.size(), std::max<size_t>(wres_tc.size(), 1));
+        DX_CUDA(cudaMalloc(&tmp, tmp_n * sizeof(float)));
+        // copies go through the engine's (non-blocking) stream: a legacy-stream cudaMemcpy from pageable memory may
+        // return before its DMA has landed, and nothing would order the conversion kernel after it
+        cudaMemcpyAsync(tmp, w0p.data(), w0p.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+        k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, w0b, w0p.size());
+        cudaStreamSynchronize(e->stream);
+        if (!wres_tc.empty()) {
+            cudaMemcpyAsync(tmp, wres_tc.data(), wres_tc.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+            k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, wrb, wres_tc.size());
+        }
+        cudaError_t ce = cudaStreamSynchronize(e->stream);
+        cudaFree(tmp);
+        DX_CUDA(ce);
+        net.w0_bf16 = w0b;
+        net.wres_bf16 = wrb;
+    }
     // activation buffers
     const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst);
     e->mlp.cap = cap;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
-        for (int i = 0; i < 3; ++i) { uint16_t* q = nullptr; DX_TRY(e->alloc(&q, (size_t)cap * Hp)); e->mlp.xb[i] = q; }
+        int fill = 0;
+        if (const char* f = getenv("DXB200_DEBUG_FILL")) fill = atoi(f);      // debug: poison value of never-written rows
+        for (int i = 0; i < 3; ++i) {
+            uint16_t* q = nullptr;
+            DX_TRY(e->alloc(&q, (size_t)cap * Hp));
+            DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 2));
+            e->mlp.xb[i] = q;
+        }
         uint16_t* onehot = nullptr;
         DX_TRY(e->alloc(&onehot, (size_t)cap * in_dim_p));
+        DX_CUDA(cudaMemset(onehot, fill, (size_t)cap * in_dim_p * 2));
         DX_TRY(dx_mlp_bf16_prepare(net, e->mlp, onehot, &net.tc_plan));
     } else {
         for (int i = 0; i < 3; ++i) DX_TRY(e->alloc(&e->mlp.x[i], (size_t)cap * Hp));
     }
+    DX_CUDA(cudaDeviceSynchronize());        // every legacy-stream upload above has landed before the engine stream uses it
     return DX_OK;
 }
 

@@ -337,11 +337,15 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const int col = n0 + c * 32;
                 // bias first: with ~225 KB of shared memory in use the L1 keeps almost nothing, so these are L2 round
                 // trips; issued here, their latency overlaps the barrier waits below instead of stalling the math
+                // (bias == nullptr: the bias is folded into the GEMM through the ones columns, NetDev::tc_fold)
                 float4 bv[8];
-                {
+                if (bias) {
                     const float4* b4 = reinterpret_cast<const float4*>(bias + col);
 #pragma unroll
                     for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) bv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
                 }
                 float4 wv[FUSE_OUT ? 8 : 1];
                 if (FUSE_OUT) {
@@ -474,7 +478,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 
 // ---------------------------------------------------------------------------------------------
 // bf16 one-hot input matrix [n, in_dim_p] (OneHot.forward, deepxube/pytorch/pytorch_models.py:15-24)
-__global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p, const Ctl* __restrict__ ctl,
+// ones_col >= 0: columns ones_col .. ones_col + 2 are set to 1.0 (they multiply the folded bias columns of W0)
+__global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p, int ones_col, const Ctl* __restrict__ ctl,
                               const uint8_t* __restrict__ rows, const uint8_t* __restrict__ goals,
                               __nv_bfloat16* __restrict__ out) {
     if (ctl->error) return;
@@ -497,6 +502,13 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
             v = min(v, depth - 1);
             const int f = i * depth + v - c0;
             if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 = 0x3F80
+        }
+        if (ones_col >= 0) {
+#pragma unroll
+            for (int j = 0; j < 3; ++j) {
+                const int f = ones_col + j - c0;
+                if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;
+            }
         }
         reinterpret_cast<uint4*>(out + (size_t)r * in_dim_p)[c0 / 8] = make_uint4(w[0], w[1], w[2], w[3]);
     }
@@ -685,11 +697,14 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     int launches = 0;
     const int oh_blocks = (int)min((long long)dx_div_up(max_rows * (net.in_dim_p / 8), 256), (long long)148 * 16);
     dx_prof_begin(DX_ST_GEMM_IN);
-    k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ctl, rows, goals, p->onehot);
+    k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, (net.tc_fold & 2) ? net.in_dim : -1, ctl, rows,
+                                            goals, p->onehot);
     ++launches;
     int ix = 0, iy = 1, iz = 2;
     const int Hp = net.Hp;
-    launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, net.b0, -1, ix, 0);
+    const bool fold_h = (net.tc_fold & 1) != 0;
+    launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, (net.tc_fold & 2) ? nullptr : (fold_h ? net.b0_tc : net.b0), -1,
+                ix, 0);
     ++launches;
     dx_prof_end();
     // one timed interval around the 2 * num_blocks back-to-back hidden-layer launches (an event between
@@ -700,12 +715,12 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const int P = 2 * (Hp / p->BN);
     dx_prof_begin(DX_ST_GEMM_RES);
     for (int b = 0; b < net.num_blocks; ++b) {
-        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
+        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
         if (fuse && b == net.num_blocks - 1)
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
                         net.wout, (float*)mb.xb[iz], mb.cap);
         else
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
         launches += 2;
         int ti = ix; ix = iz; iz = ti;
     }

@@ -5,16 +5,17 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 from deepxube_b200 import _lib as L
 from oracle.nnet_torch import random_state_dict
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 600000
-sd = random_state_dict(324, 1000, 4, 1, True, seed=0)
+NB = int(sys.argv[2]) if len(sys.argv) > 2 else 4      # 0 blocks: only the input-layer GEMM runs
+sd = random_state_dict(324, 1000, NB, 1, True, seed=0)
 blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
 eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_BF16, max_instances=8, max_pop_total=80000, max_nodes=n + 1024)
-eng.load_weights(54, 6, 1000, 4, 1, True, blob)
+eng.load_weights(54, 6, 1000, NB, 1, True, blob)
 eng.bench_heur(n, 2)
 eng.tc_profile()
 ms = eng.bench_heur(n, 3)
 p = eng.tc_profile()
 names = ["mma<-operands", "mma<-tmem_free", "producer<-slot", "epi<-tmem_full", "epi<-residual", "epi<-store_drain", "epi_total", "mma_total", "epi<-tmem_ld", "epi math+stage", "epi fence+sync", "epi tma issue"]
-print(f"n={n} {ms/3:.3f} ms per eval (profiling build)")
+print(f"n={n} blocks={NB} {ms/3:.3f} ms per eval (profiling build)")
 for k, v in zip(names, p):
     base = p[7] if k.startswith(("mma", "producer")) else p[6]
     print(f"  {k:18s} {v/1e6:10.1f} Mcycles  {100.0*v/max(base,1):5.1f}% of role total")

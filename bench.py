@@ -239,12 +239,15 @@ def main() -> None:
         torch.cuda.synchronize()
 
     # ---- pass 1: device-resident metric ("value") + kernel timing for the roofline --------------------
+    # Profiling level 2 brackets only the dominant kernel group (the 2*NB back-to-back hidden-layer GEMM launches of every
+    # network evaluation) with CUDA events recorded inside the captured step graph; every other launch runs untimed.
+    eng.set_profiling(2)
     for w in range(args.warmup):
         s, g = pick(w)
         eng.reset()
         eng.add_instances(s, g, B, 0.6)
         eng.run(ITERS)
-    eng.set_profiling(True)
+    eng.set_profiling(2)                          # clears the timers; the captured graphs stay
     sampler = ClockSampler(physical_gpu_index(local))
     sampler.start()
     launches0 = eng.counters().kernel_launches
@@ -266,7 +269,14 @@ def main() -> None:
     launches = eng.counters().kernel_launches - launches0
     stage = eng.stage_ms()
     calls = eng.stage_calls()
-    eng.set_profiling(False)
+    # informational stage split: ONE extra step with every stage timed (outside both timed regions)
+    eng.set_profiling(1)
+    s, g = pick(args.warmup + args.steps)
+    eng.reset()
+    eng.add_instances(s, g, B, 0.6)
+    eng.run(ITERS)
+    stage_split = eng.stage_ms()
+    eng.set_profiling(0)
 
     # ---- pass 2: end-to-end through the reference-facing API (registries -> PathFind -> C ABI), host objects ----
     # the `solve` loop of the reference (deepxube/_solve.py:146-160) with G instances per PathFind: make_instances
@@ -338,8 +348,7 @@ def main() -> None:
                 # one CUDA-event interval brackets the 2*NB back-to-back hidden-layer launches of a network evaluation
                 "launches_timed": calls["gemm_hidden"] * (2 * NB if args.precision == "bf16" else 1),
                 "avg_launch_ms": stage["gemm_hidden"] / max(calls["gemm_hidden"] * (2 * NB if args.precision == "bf16" else 1), 1),
-                "network_tflops_dense_equiv": FLOP_PER_STATE * evals / (stage["heur"] / 1e3) / 1e12 if stage["heur"] > 0 else None,
-                "stage_ms_rank0": {k: round(v, 3) for k, v in stage.items()}}
+                "stage_ms_one_extra_step_rank0": {k: round(v, 3) for k, v in stage_split.items()}}
         line = {"metric": "nodes_generated_per_sec", "value": value, "unit": "nodes/s", "n_gpus": world, "steps": args.steps,
                 "warmup": args.warmup, "ms_per_step": tmax[0] / max(args.steps, 1), "higher_is_better": True, "scaling": "weak",
                 "vs_baseline": None, "dtype": args.precision, "data": "synthetic", "config": workload_config(args, world),

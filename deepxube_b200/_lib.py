@@ -335,8 +335,9 @@ class Engine:
         check(self._lib.dx_bench_heur(self._h, n, reps, C.byref(ms)))
         return ms.value
 
-    def set_profiling(self, on: bool) -> None:
-        check(self._lib.dx_set_profiling(self._h, 1 if on else 0))
+    def set_profiling(self, level) -> None:
+        """0 / False: off; 1 / True: every stage + GEMM groups; 2: only the hidden-layer GEMM group (lowest overhead)."""
+        check(self._lib.dx_set_profiling(self._h, int(level)))
 
     def stage_ms(self) -> dict:
         arr = (C.c_float * 16)()

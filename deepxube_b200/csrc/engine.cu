@@ -203,7 +203,8 @@ struct dx_engine {
     std::vector<void*> allocs;
 
     // profiling
-    bool profiling = false;
+    int profiling = 0;                 // 0 off, 1 every stage + GEMM intervals, 2 only the hidden-layer GEMM interval
+    int prof_graph_level = 0;          // level the profiling graphs were captured at
     std::vector<cudaEvent_t> ev;       // pairs
     std::vector<int> ev_stage;
     std::vector<int> ev_open;
@@ -239,6 +240,7 @@ struct dx_engine {
 // end closes the innermost open interval.
 static void stage_begin(dx_engine* e, int st) {
     if (!e->profiling) return;
+    if (e->profiling == 2 && st != ST_GEMM_RES) { e->ev_open.push_back(-1); return; }   // not timed at this level
     cudaEvent_t a;
     cudaEventCreate(&a);
     if (e->cap_prof >= 0) {            // inside stream capture: a real event-record node, kept for every replay
@@ -258,6 +260,7 @@ static void stage_begin(dx_engine* e, int st) {
 }
 static void stage_end(dx_engine* e) {
     if (!e->profiling || e->ev_open.empty()) return;
+    if (e->ev_open.back() < 0) { e->ev_open.pop_back(); return; }
     cudaEvent_t b;
     cudaEventCreate(&b);
     if (e->cap_prof >= 0) {
@@ -722,9 +725,22 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     if (!e->run_ev[0]) { cudaEventCreate(&e->run_ev[0]); cudaEventCreate(&e->run_ev[1]); }
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
-    const bool use_graph = e->use_graphs, prof = e->profiling;
+    const bool use_graph = e->use_graphs, prof = e->profiling != 0;
     if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
-    if (use_graph && prof && !e->graph_prof_exec[0]) { stage_collect(e); DX_TRY(build_step_graphs(e, true)); }
+    if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level
+        for (int k = 0; k < 2; ++k) {
+            cudaGraphExecDestroy(e->graph_prof_exec[k]);
+            e->graph_prof_exec[k] = nullptr;
+            for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
+            e->gev[k].clear();
+            e->gev_stage[k].clear();
+        }
+    }
+    if (use_graph && prof && !e->graph_prof_exec[0]) {
+        stage_collect(e);
+        DX_TRY(build_step_graphs(e, true));
+        e->prof_graph_level = e->profiling;
+    }
     cudaEventRecord(e->run_ev[0], e->stream);
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         if (use_graph) {
@@ -1091,7 +1107,7 @@ extern "C" int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_to
 extern "C" int dx_set_profiling(dx_engine* e, int32_t on) {
     if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
     stage_collect(e);
-    e->profiling = on != 0;
+    e->profiling = on < 0 ? 0 : (on > 2 ? 2 : on);
     memset(e->stage_ms, 0, sizeof(e->stage_ms));
     memset(e->stage_calls, 0, sizeof(e->stage_calls));
     return DX_OK;

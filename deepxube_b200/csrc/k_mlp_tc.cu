@@ -37,6 +37,7 @@
 #error "TC_NBUF must be 2 or 4"
 #endif
 #define TC_THREADS 384         // 4 control warps (TMA, MMA, TMEM alloc, spare) + 8 epilogue warps
+#define TC_THREADS_GEN 448     // fused input layer: + 2 warps; warps 2, 3, 12, 13 generate the one-hot A tiles
 #define TC_EPI_WARPS 8
 #define TC_UMMA_K 16
 #define TC_PEER_MASK 0xFEFFFFFFu     // clears the CTA-rank bit of a shared::cluster address -> the leader CTA's copy
@@ -51,7 +52,18 @@ struct TcPlan {
     int BN;
     int CL;                      // CTAs per cluster: 2 = cta_group::2 pairs, 1 = single-CTA tiles
     int fuse_out;                // fold a scalar output layer into the last hidden GEMM (DXB200_FUSE_OUT=0 disables)
+    int fuse_in;                 // generate the one-hot input inside the first GEMM (DXB200_FUSE_IN=0 disables)
     int num_sms;
+};
+
+// Fused input layer (GEN_A): the A operand is the one-hot encoding of the state rows
+// (OneHot.forward, deepxube/pytorch/pytorch_models.py:15-24), written straight into the swizzled operand slots by
+// two generator warps -- the one-hot matrix never exists in HBM.
+struct TcGen {
+    const uint8_t* rows;         // node-store rows (state + pad + instance id), row stride SP
+    const uint8_t* goals;        // [instances, SP] goal rows (inputs S .. in_count - 1 come from the goal)
+    int S, SP, in_count, depth;
+    int ones_col;                // >= 0: columns ones_col .. +2 are 1.0 (folded bias), else -1
 };
 
 // Optional in-kernel wait accounting (build with -DTC_PROFILE): cycles the role threads spend blocked on each
@@ -88,6 +100,30 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
         if (done) return;
     }
     __trap();
+}
+// same, cluster-scope acquire: the data the barrier guards was written by threads of the peer CTA
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    for (int attempt = 0; attempt < 400; ++attempt) {
+        uint32_t done;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred P1;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 P1, [%1], %2, %3;\n\t"
+            "selp.u32 %0, 1, 0, P1;\n\t"
+            "}" : "=r"(done) : "r"(bar), "r"(parity), "r"(0x989680u)
+            : "memory");
+        if (done) return;
+    }
+    __trap();
+}
+__device__ __forceinline__ void mbar_arrive_release_cluster(uint32_t bar, uint32_t cta) {
+    asm volatile(
+        "{\n\t"
+        ".reg .b32 ra;\n\t"
+        "mapa.shared::cluster.u32 ra, %0, %1;\n\t"
+        "mbarrier.arrive.release.cluster.shared::cluster.b64 _, [ra];\n\t"
+        "}" ::"r"(bar), "r"(cta)
+        : "memory");
 }
 __device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes) {
     asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
@@ -176,20 +212,25 @@ struct TcSmem {
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int EPI_BUF = 32 * 64;              // one 32-row x 32-column bf16 chunk
-    static constexpr int EPI_WARP_BYTES = 2 * TC_NBUF * EPI_BUF;   // per epilogue warp: TC_NBUF output + TC_NBUF residual buffers
-    static constexpr int BAR_OFF = EPI_OFF + TC_EPI_WARPS * EPI_WARP_BYTES;
+    // epilogue staging: TC_NBUF output buffers per warp, then (contiguous, 32 KB) TC_NBUF residual buffers per warp;
+    // the fused input layer has no residual and keeps its tile's state rows in the residual region instead
+    static constexpr int EPI_OUT_BYTES = TC_EPI_WARPS * TC_NBUF * EPI_BUF;
+    static constexpr int RES_OFF = EPI_OFF + EPI_OUT_BYTES;
+    static constexpr int RES_BYTES = TC_EPI_WARPS * TC_NBUF * EPI_BUF;
+    static constexpr int BAR_OFF = RES_OFF + RES_BYTES;
     static constexpr int TOTAL = BAR_OFF + 512 + 1024;   // barriers + tmem ptr, + slack for 1024-byte alignment
 };
 
 // FUSE_OUT = true (last hidden layer of a scalar-output network): the epilogue does not store the activations; every
 // thread dots its row's 128 activated columns with the output layer's weight row and writes one fp32 partial
 // (partial[(2 * n_tile + h) * pstride + row]); k_out_final_bf16 adds the partials in a fixed order.
-template <int BN, int CL, bool FUSE_OUT>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+// GEN_A = true (input layer): no A tensor map is read; four generator warps write the one-hot A tiles (TcGen).
+template <int BN, int CL, bool FUSE_OUT, bool GEN_A>
+__global__ void __launch_bounds__(GEN_A ? TC_THREADS_GEN : TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
                int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu,
-               const float* __restrict__ wout, float* __restrict__ partial, long long pstride) {
+               const float* __restrict__ wout, float* __restrict__ partial, long long pstride, const TcGen gen) {
     extern __shared__ uint8_t smem_raw[];
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
@@ -205,6 +246,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
     auto res_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 4 + TC_NBUF * ew + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + TC_EPI_WARPS * TC_NBUF);
+    auto rows_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + TC_EPI_WARPS * TC_NBUF + b); };   // GEN_A: state rows landed
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -212,11 +254,13 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     uint32_t cta_rank = 0;
     if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
     if (threadIdx.x == 0) {
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+        // full: the leader's expect_tx arrival (+ one arrival per generator warp of the pair when A is generated)
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), GEN_A ? 1 + 4 * CL : 1); mbar_init(empty_bar(s), 1); }
         // tmem_empty (leader's copy is the one the MMA thread waits on): one arrival per epilogue warp of the pair
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * CL); }
         for (int ew = 0; ew < TC_EPI_WARPS; ++ew)
             for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(ew, b), 1);
+        if (GEN_A) { mbar_init(rows_bar(0), 1); mbar_init(rows_bar(1), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {      // the same warp in both CTAs of a pair
@@ -250,14 +294,15 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const int s = it % STAGES;
                     { TC_T0(); mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u); TC_ACC(w_empty); }
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
+                    constexpr int TX = GEN_A ? SM::B_BYTES : SM::STAGE_BYTES;     // generated A tiles carry no TMA bytes
                     if (CL == 1) {
-                        mbar_arrive_expect_tx(full_bar(s), SM::STAGE_BYTES);
-                        tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                        mbar_arrive_expect_tx(full_bar(s), TX);
+                        if (!GEN_A) tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
                     } else {
                         // the leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
-                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SM::STAGE_BYTES);
-                        tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * TX);
+                        if (!GEN_A) tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)cta_rank * (BN / CL));
                     }
                 }
@@ -301,12 +346,138 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             atomicAdd(&g_tc_prof[7], (unsigned long long)(clock64() - t_mma0));
 #endif
         }
-    } else if (warp >= 4) {
+    } else if (GEN_A && (warp == 2 || warp == 3 || warp >= 12)) {
+        // ---------------- A generator (4 warps, 128 threads): thread gt writes the one-hot encoding of row gt ----------------
+        // Residual region (unused by this layer): [256-entry LUT: byte -> 8 bf16 0/1 values][rows of tile t][rows of t+1][ranges].
+        // A row's 64 features of a k-block are collected into a 64-bit mask, then expanded 8 features at a time through
+        // the LUT: one 16-byte load + one 16-byte store per swizzled operand chunk, no zero-fill pass.
+        const int gt = (warp >= 12 ? (warp - 10) : (warp - 2)) * 32 + lane;
+        uint8_t* res_sm = smem_raw + (smem_base + SM::RES_OFF - smem_u32(smem_raw));
+        uint4* lut = reinterpret_cast<uint4*>(res_sm);
+        // LUT slot of byte e: low 3 bits permuted so that the few byte values a one-hot code produces spread over banks
+        auto lut_slot = [](uint32_t e) { return e ^ (((e >> 3) ^ (e >> 6)) & 7u); };
+        const int SP = gen.SP, depth = gen.depth;
+        uint8_t* rows_buf0 = res_sm + 4096;                              // buffer b at rows_buf0 + b * TC_BM * SP
+        const uint32_t row_start = ctl->nn_row_start;
+        // input range [i_lo, i_hi] whose features fall into k-block kb (kblocks <= 64), computed once: no divisions in the loop
+        int* irange = reinterpret_cast<int*>(rows_buf0 + 2 * TC_BM * SP);
+        for (int kb = gt; kb < kblocks; kb += 128) {
+            irange[2 * kb] = (kb * TC_BK) / depth;
+            irange[2 * kb + 1] = min(gen.in_count - 1, (kb * TC_BK + TC_BK - 1) / depth);
+        }
+        for (uint32_t e = gt; e < 256; e += 128) {
+            uint32_t w[4];
+#pragma unroll
+            for (int k = 0; k < 4; ++k) w[k] = (((e >> (2 * k)) & 1) ? 0x00003F80u : 0u) | (((e >> (2 * k + 1)) & 1) ? 0x3F800000u : 0u);
+            lut[lut_slot(e)] = make_uint4(w[0], w[1], w[2], w[3]);
+        }
+        // One bulk copy (TMA, completes on rows_bar) brings a tile's rows -- contiguous in the node store -- into buffer b.
+        // It is tracked by the barrier, not by this thread's memory-operation scoreboard, so the proxy fences below do
+        // not wait for it (a cp.async / ld.global prefetch would stall every fence until the rows arrived).
+        auto prefetch_rows = [&](int t, int b) {
+            const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM;
+            const int nrows = min(TC_BM, M - m0);                      // rows past M keep stale bytes: their outputs are unused
+            if (gt == 0) {
+                if (nrows > 0) {
+                    const uint32_t bytes = (uint32_t)nrows * (uint32_t)SP;
+                    mbar_arrive_expect_tx(rows_bar(b), bytes);
+                    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                                 ::"r"(smem_u32(rows_buf0 + b * TC_BM * SP)), "l"(gen.rows + (size_t)(row_start + m0) * SP), "r"(bytes),
+                                   "r"(rows_bar(b)) : "memory");
+                } else {
+                    mbar_arrive(rows_bar(b));
+                }
+            }
+        };
+        if (cl_id < total) prefetch_rows(cl_id, 0);
+        uint32_t it = 0, lt = 0;
+        long long w_gslot = 0, w_gmask = 0, w_gexp = 0, w_gsync = 0;
+#ifdef TC_PROFILE
+        const long long t_gen0 = clock64();
+#endif
+        const int r = gt;
+        const uint32_t arow_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);      // SW128: chunk j of row r at j ^ (r & 7)
+        for (int t = cl_id; t < total; t += n_cl, ++lt) {
+            asm volatile("bar.sync 1, 128;" ::: "memory");         // everyone is done with the other buffer (and the LUT is written)
+            if (t + n_cl < total) prefetch_rows(t + n_cl, (lt + 1) & 1);
+            mbar_wait(rows_bar(lt & 1), (lt >> 1) & 1u);           // this tile's rows have landed
+            const uint8_t* srow = rows_buf0 + (lt & 1) * TC_BM * SP + r * SP;
+            for (int kb = 0; kb < kblocks; ++kb, ++it) {
+                const int s = it % STAGES;
+                const int f0 = kb * TC_BK;
+                const int i_lo = irange[2 * kb], i_hi = irange[2 * kb + 1];
+#ifdef TC_PROFILE
+                const long long _g0 = clock64();
+#endif
+                // Feature mask of this row's 64 columns as two 32-bit halves.  Four inputs per shared-memory word; input i
+                // sets bit i * depth + v - f0.  shl.b32 clamps: a shift amount outside [0, 32) (as unsigned) gives 0, so
+                // inputs of the neighbouring k-blocks drop out without range tests.  Row bytes past in_count are zero padding /
+                // the instance id and only reach columns >= in_dim, whose weights are zero (or the always-one bias columns).
+                uint32_t mlo = 0u, mhi = 0u;
+                auto shl1 = [](int sh) { uint32_t o; asm("shl.b32 %0, %1, %2;" : "=r"(o) : "r"(1u), "r"((uint32_t)sh)); return o; };
+#pragma unroll 2
+                for (int i4 = i_lo & ~3; i4 <= i_hi; i4 += 4) {
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(srow + i4);
+                    const int fb = i4 * depth - f0;
+#pragma unroll
+                    for (int j = 0; j < 4; ++j) {
+                        const int f = fb + j * depth + min((int)((w >> (8 * j)) & 0xFFu), depth - 1);
+                        mlo |= shl1(f);
+                        mhi |= shl1(f - 32);
+                    }
+                }
+                if (gen.ones_col >= 0) {
+#pragma unroll
+                    for (int j = 0; j < 3; ++j) {
+                        const int f = gen.ones_col + j - f0;
+                        mlo |= shl1(f);
+                        mhi |= shl1(f - 32);
+                    }
+                }
+#ifdef TC_PROFILE
+                const long long _g1 = clock64();
+                w_gmask += _g1 - _g0;
+#endif
+                mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);          // the mask is ready before the slot is needed
+#ifdef TC_PROFILE
+                const long long _g2 = clock64();
+                w_gslot += _g2 - _g1;
+#endif
+                uint8_t* arow = smem_raw + (smem_base + s * SM::STAGE_BYTES - smem_u32(smem_raw)) + arow_off;
+                uint4 ch[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) ch[j] = lut[lut_slot(((j < 4 ? mlo : mhi) >> (8 * (j & 3))) & 0xFFu)];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) *reinterpret_cast<uint4*>(arow + ((j ^ (r & 7)) << 4)) = ch[j];
+#ifdef TC_PROFILE
+                const long long _g3 = clock64();
+                w_gexp += _g3 - _g2;
+#endif
+                asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
+                __syncwarp();
+                if (lane == 0) mbar_arrive_cluster(full_bar(s), 0);              // the leader's barrier (rank 0 of the pair)
+#ifdef TC_PROFILE
+                w_gsync += clock64() - _g3;
+#endif
+            }
+        }
+#ifdef TC_PROFILE
+        if (gt == 0) {
+            atomicAdd(&g_tc_prof[12], (unsigned long long)w_gslot);
+            atomicAdd(&g_tc_prof[13], (unsigned long long)w_gmask);
+            atomicAdd(&g_tc_prof[14], (unsigned long long)w_gexp);
+            atomicAdd(&g_tc_prof[15], (unsigned long long)(clock64() - t_gen0));
+            atomicAdd(&g_tc_prof[2], (unsigned long long)w_gsync);     // (slot [2] doubles as generator fence+sync+arrive)
+        }
+#endif
+    } else if (warp >= 4 && warp < 4 + TC_EPI_WARPS) {
         // ---------------- epilogue: 8 warps; warp 4 + ew drains TMEM lane quarter (ew & 3) -- a warp may only touch
         // lanes 32 * (warp % 4) .. + 31 -- and the 32-column chunks c with (c & 1) == ew >> 2 ----------------
         const int ew = warp - 4, q = ew & 3, h = ew >> 2;
-        const uint32_t epi_base = smem_base + SM::EPI_OFF + ew * SM::EPI_WARP_BYTES;
+        const uint32_t epi_base = smem_base + SM::EPI_OFF + ew * (TC_NBUF * SM::EPI_BUF);      // this warp's output buffers
+        const uint32_t res_base = smem_base + SM::RES_OFF + ew * (TC_NBUF * SM::EPI_BUF);      // ... residual buffers
         uint8_t* epi_ptr = smem_raw + (epi_base - smem_u32(smem_raw));
+        const uint8_t* res_ptr = smem_raw + (res_base - smem_u32(smem_raw));
         // 64-byte swizzle (Swizzle<2,4,3>): 16-byte chunk j of row r lives at chunk j ^ ((r >> 1) & 3)
         const uint32_t sw = (uint32_t)((lane >> 1) & 3);
         constexpr int NCH = BN / 32;
@@ -324,7 +495,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                 for (int b = 0; b < TC_NBUF && h + 2 * b < NCH; ++b) {
                     mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
-                    tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (h + 2 * b) * 32, row0);
+                    tma_load_2d(res_base + b * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (h + 2 * b) * 32, row0);
                 }
             }
             { TC_T0(); mbar_wait(tfull_bar(as), (lt >> 1) & 1u); TC_ACC(w_tfull); }
@@ -368,7 +539,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef TC_PROFILE
                 const long long _tm0 = clock64();
 #endif
-                const uint8_t* rrow = epi_ptr + (TC_NBUF + b) * SM::EPI_BUF + lane * 64;
+                const uint8_t* rrow = res_ptr + b * SM::EPI_BUF + lane * 64;
                 uint8_t* crow = epi_ptr + b * SM::EPI_BUF + lane * 64;
 #pragma unroll
                 for (int g = 0; g < 4; ++g) {      // 8 columns = one 16-byte chunk per group
@@ -423,7 +594,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     }
                     if (has_res && c + 2 * TC_NBUF < NCH) {      // all lanes are past their reads of residual buffer b
                         mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
-                        tma_load_2d(epi_base + (TC_NBUF + b) * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (c + 2 * TC_NBUF) * 32, row0);
+                        tma_load_2d(res_base + b * SM::EPI_BUF, &tmR, res_bar(ew, b), n0 + (c + 2 * TC_NBUF) * 32, row0);
                     }
                 }
 #ifdef TC_PROFILE
@@ -516,8 +687,8 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
 
 // Final Linear(H, out_dim) + clipping on bf16 activations; one warp per row (see k_out_layer in k_mlp_f32.cu).
 __global__ void __launch_bounds__(256)
-k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* __restrict__ X, float* __restrict__ out_h,
-                 float* __restrict__ out_q, int absolute) {
+k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* __restrict__ X, int kmax, float* __restrict__ out_h,
+                 float* __restrict__ out_q, int absolute) {      // kmax: columns of X the last GEMM wrote (the rest is never read)
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     const int lane = threadIdx.x & 31;
@@ -529,7 +700,7 @@ k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* _
         float hmin = __int_as_float(0x7f800000);
         for (int o0 = 0; o0 < od; o0 += 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
-            for (int k2 = lane; k2 < Hp / 2; k2 += 32) {
+            for (int k2 = lane; k2 < kmax / 2; k2 += 32) {
                 const float2 xv = __bfloat1622float2(x2[k2]);
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
@@ -607,11 +778,13 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     }
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     TcPlan* p = new TcPlan();
-    p->BN = net.Hp >= 256 ? 256 : 128;
+    p->BN = (net.Hp % 256 == 0) ? 256 : 128;      // n-tiles must divide the padded width (Hp is a multiple of 128)
     p->CL = 2;
     if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : 2;
     p->fuse_out = 1;
     if (const char* c = getenv("DXB200_FUSE_OUT")) p->fuse_out = (c[0] == '0') ? 0 : 1;
+    p->fuse_in = 1;
+    if (const char* c = getenv("DXB200_FUSE_IN")) p->fuse_in = (c[0] == '0') ? 0 : 1;
     p->onehot = (__nv_bfloat16*)onehot_buf;
     int dev = 0;
     cudaGetDevice(&dev);
@@ -628,14 +801,18 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
         auto set_attr = [&](const void* f, int bytes) {
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         };
-        set_attr((const void*)k_gemm_bf16_tc<256, 1, false>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2, false>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1, false>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2, false>, TcSmem<128, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 1, true>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2, true>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1, true>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2, true>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, false, false>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, false, false>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, false, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, false, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, true, false>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, true, false>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, true, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, true, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, false, true>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, false, true>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, false, true>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, false, true>, TcSmem<128, 2>::TOTAL);
         if (ce != cudaSuccess) {
             dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(ce));
             rc = DX_ERR_CUDA;
@@ -646,20 +823,21 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     return DX_OK;
 }
 
-template <int BN, int CL, bool FUSE>
+template <int BN, int CL, bool FUSE, bool GEN>
 static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& tc,
                           const CUtensorMap& tr, const Ctl* ctl, int w_row0, int K, int N, const float* bias, int has_res,
-                          int relu, const float* wout, float* partial, long long pstride) {
+                          int relu, const float* wout, float* partial, long long pstride, const TcGen& gen) {
     cfg->dynamicSmemBytes = TcSmem<BN, CL>::TOTAL;
-    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, FUSE>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
-                       pstride);
+    cfg->blockDim = dim3(GEN ? TC_THREADS_GEN : TC_THREADS);
+    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, FUSE, GEN>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
+                       pstride, gen);
 }
 
 // c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
-// (no activation store; buffer c is not written)
+// (no activation store; buffer c is not written); gen != nullptr selects the fused one-hot input (a is not read)
 static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
                         int K, int N, const float* bias, int r, int c, int relu, const float* wout = nullptr,
-                        float* partial = nullptr, long long pstride = 0) {
+                        float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
@@ -674,17 +852,27 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, c
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int has_res = r >= 0 ? 1 : 0;
+    const TcGen g = gen ? *gen : TcGen{};
     const int sel = (p->BN == 256 ? 4 : 0) | (p->CL == 2 ? 2 : 0) | (partial ? 1 : 0);
-#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride
-    switch (sel) {
-        case 7: launch_gemm_t<256, 2, true>(DX_TC_ARGS); break;
-        case 6: launch_gemm_t<256, 2, false>(DX_TC_ARGS); break;
-        case 5: launch_gemm_t<256, 1, true>(DX_TC_ARGS); break;
-        case 4: launch_gemm_t<256, 1, false>(DX_TC_ARGS); break;
-        case 3: launch_gemm_t<128, 2, true>(DX_TC_ARGS); break;
-        case 2: launch_gemm_t<128, 2, false>(DX_TC_ARGS); break;
-        case 1: launch_gemm_t<128, 1, true>(DX_TC_ARGS); break;
-        default: launch_gemm_t<128, 1, false>(DX_TC_ARGS); break;
+#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g
+    if (gen) {
+        switch (sel >> 1) {
+            case 3: launch_gemm_t<256, 2, false, true>(DX_TC_ARGS); break;
+            case 2: launch_gemm_t<256, 1, false, true>(DX_TC_ARGS); break;
+            case 1: launch_gemm_t<128, 2, false, true>(DX_TC_ARGS); break;
+            default: launch_gemm_t<128, 1, false, true>(DX_TC_ARGS); break;
+        }
+    } else {
+        switch (sel) {
+            case 7: launch_gemm_t<256, 2, true, false>(DX_TC_ARGS); break;
+            case 6: launch_gemm_t<256, 2, false, false>(DX_TC_ARGS); break;
+            case 5: launch_gemm_t<256, 1, true, false>(DX_TC_ARGS); break;
+            case 4: launch_gemm_t<256, 1, false, false>(DX_TC_ARGS); break;
+            case 3: launch_gemm_t<128, 2, true, false>(DX_TC_ARGS); break;
+            case 2: launch_gemm_t<128, 2, false, false>(DX_TC_ARGS); break;
+            case 1: launch_gemm_t<128, 1, true, false>(DX_TC_ARGS); break;
+            default: launch_gemm_t<128, 1, false, false>(DX_TC_ARGS); break;
+        }
     }
 #undef DX_TC_ARGS
 }
@@ -696,16 +884,26 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     if (max_rows > mb.cap) max_rows = mb.cap;
     int launches = 0;
     const int oh_blocks = (int)min((long long)dx_div_up(max_rows * (net.in_dim_p / 8), 256), (long long)148 * 16);
-    dx_prof_begin(DX_ST_GEMM_IN);
-    k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, (net.tc_fold & 2) ? net.in_dim : -1, ctl, rows,
-                                            goals, p->onehot);
-    ++launches;
     int ix = 0, iy = 1, iz = 2;
     const int Hp = net.Hp;
     const bool fold_h = (net.tc_fold & 1) != 0;
-    launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, net.in_dim_p, Hp, (net.tc_fold & 2) ? nullptr : (fold_h ? net.b0_tc : net.b0), -1,
-                ix, 0);
-    ++launches;
+    const float* bias0 = (net.tc_fold & 2) ? nullptr : (fold_h ? net.b0_tc : net.b0);
+    const int ones_col = (net.tc_fold & 2) ? net.in_dim : -1;
+    const int kv_in = net.in_dim_p, kv_h = Hp, nv = Hp;      // padded shapes (trimming the padding measured no gain)
+    dx_prof_begin(DX_ST_GEMM_IN);
+    // (networks that also read the goal keep the separate one-hot kernel: the goal row is a dependent gather)
+    if (p->fuse_in && net.in_count <= d.S && d.SP % 16 == 0 && net.in_dim_p <= 4096 &&
+        4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64) {
+        // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
+        TcGen g;
+        g.rows = rows; g.goals = goals; g.S = d.S; g.SP = d.SP; g.in_count = net.in_count; g.depth = net.depth; g.ones_col = ones_col;
+        launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
+        ++launches;
+    } else {
+        k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, ctl, rows, goals, p->onehot);
+        launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0);
+        launches += 2;
+    }
     dx_prof_end();
     // one timed interval around the 2 * num_blocks back-to-back hidden-layer launches (an event between
     // every pair of launches costs ~3 % of the step; the average launch duration is interval / launches)
@@ -715,12 +913,12 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const int P = 2 * (Hp / p->BN);
     dx_prof_begin(DX_ST_GEMM_RES);
     for (int b = 0; b < net.num_blocks; ++b) {
-        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
+        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
         if (fuse && b == net.num_blocks - 1)
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
                         net.wout, (float*)mb.xb[iz], mb.cap);
         else
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, Hp, Hp, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
+            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
         launches += 2;
         int ti = ix; ix = iz; iz = ti;
     }
@@ -731,7 +929,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     } else {
         const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
         const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);
-        k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, out_h, out_q, absolute);
+        k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, Hp, out_h, out_q, absolute);
     }
     ++launches;
     return launches;

@@ -176,8 +176,9 @@ int dx_row_bytes(dx_engine* e, int32_t* row_bytes);
 int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_total);
 /* Device time (ms, CUDA events on the engine stream) spent per pipeline stage since the last reset:
  * [0] expand, [1] closed filter, [2] scan+scatter, [3] heuristic, [4] sort, [5] merge/pop, [6] bookkeeping.
- * Only collected when dx_set_profiling(e, 1) was called (adds event records, no syncs). */
-int dx_set_profiling(dx_engine* e, int32_t on);
+ * Only collected while profiling is on (event records, no syncs): level 1 times every stage and the GEMM groups,
+ * level 2 only the hidden-layer GEMM group ([7]; one interval per network evaluation, lowest overhead), 0 turns it off. */
+int dx_set_profiling(dx_engine* e, int32_t level);
 int dx_get_stage_ms(dx_engine* e, float* ms, int32_t cap);
 /* Same indexing plus [7] hidden-layer GEMM launches and [8] input-layer launches (both nested inside [3]):
  * number of timed intervals per entry, so that ms / calls = average launch duration. */

@@ -45,12 +45,16 @@
 struct TcPlan {
     CUtensorMap a_onehot;
     CUtensorMap a_x[3];
+    CUtensorMap a_xh[3];         // the same buffers in 64-row boxes (clusters of two pairs: each CTA fetches half of an A tile)
     CUtensorMap b_w0;
     CUtensorMap b_res;
     CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
     int BN;
-    int CL;                      // CTAs per cluster: 2 = cta_group::2 pairs, 1 = single-CTA tiles
+    int CL;                      // CTAs per cluster of the hidden layers: 1 = single-CTA tiles, 2 = cta_group::2 pairs,
+                                 // 4 = two pairs sharing their A tiles by TMA multicast (DXB200_GEMM_CLUSTER)
+    int CL_in;                   // ... of the input layer (min(CL, 2))
+    int grid4;                   // CTAs launched with clusters of 4 (4 x the co-resident clusters the device reports)
     int fuse_out;                // fold a scalar output layer into the last hidden GEMM (DXB200_FUSE_OUT=0 disables)
     int fuse_in;                 // generate the one-hot input inside the first GEMM (DXB200_FUSE_IN=0 disables)
     int num_sms;
@@ -152,6 +156,13 @@ __device__ __forceinline__ void tma_load_2d_2sm(uint32_t dst, const CUtensorMap*
                  ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & TC_PEER_MASK), "r"(c0), "r"(c1)
                  : "memory");
 }
+// 2-CTA load multicast to the CTAs in `mask` (same shared-memory offset in each); every destination counts its bytes on
+// the barrier at this offset in the leader of ITS pair
+__device__ __forceinline__ void tma_load_2d_2sm_mc(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, uint16_t mask) {
+    asm volatile("cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes.multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+                 ::"r"(dst), "l"(reinterpret_cast<uint64_t>(map)), "r"(bar & TC_PEER_MASK), "r"(c0), "r"(c1), "h"(mask)
+                 : "memory");
+}
 __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t src, int c0, int c1) {
     asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%2, %3}], [%1];"
                  ::"l"(reinterpret_cast<uint64_t>(map)), "r"(src), "r"(c0), "r"(c1)
@@ -160,17 +171,17 @@ __device__ __forceinline__ void tma_store_2d(const CUtensorMap* map, uint32_t sr
 __device__ __forceinline__ void cluster_sync_all() {
     asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-template <int CL>
-__device__ __forceinline__ void umma_commit(uint32_t bar) {
-    if (CL == 1)
+template <int PAIR>
+__device__ __forceinline__ void umma_commit(uint32_t bar, uint16_t mask) {
+    if (PAIR == 1)
         asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(bar) : "memory");
-    else       // arrives on the barrier at this offset in BOTH CTAs of the pair
+    else       // arrives on the barrier at this offset in every CTA of `mask`
         asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
-                     ::"r"(bar), "h"((uint16_t)3) : "memory");
+                     ::"r"(bar), "h"(mask) : "memory");
 }
-template <int CL>
+template <int PAIR>
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
-    if (CL == 1)
+    if (PAIR == 1)
         asm volatile(
             "{\n\t"
             ".reg .pred p;\n\t"
@@ -206,9 +217,10 @@ __device__ __forceinline__ uint64_t make_sw128_desc(uint32_t smem_addr) {
 
 template <int BN, int CL>
 struct TcSmem {
-    static constexpr int STAGES = CL == 2 ? 5 : 3;
+    static constexpr int PAIR = CL >= 2 ? 2 : 1;          // CTAs per MMA (cta_group)
+    static constexpr int STAGES = CL >= 2 ? 5 : 3;
     static constexpr int A_BYTES = TC_BM * TC_BK * 2;
-    static constexpr int B_BYTES = (BN / CL) * TC_BK * 2;          // a pair CTA holds half of the weight tile
+    static constexpr int B_BYTES = (BN / PAIR) * TC_BK * 2;        // a pair CTA holds half of the weight tile
     static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
     static constexpr int EPI_OFF = STAGES * STAGE_BYTES;
     static constexpr int EPI_BUF = 32 * 64;              // one 32-row x 32-column bf16 chunk
@@ -234,6 +246,10 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     extern __shared__ uint8_t smem_raw[];
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
+    constexpr int PAIR = SM::PAIR;           // CTAs per MMA
+    constexpr int NP = CL / PAIR;            // pairs per cluster; NP = 2: two pairs work on adjacent n-tiles of the same rows
+                                             // and fetch their common A tiles once, by TMA multicast
+    static_assert(!(GEN_A && CL > 2), "the generated input layer runs in single CTAs or pairs");
     if (ctl->error) return;
     const int M = (int)ctl->nn_n;
     if (M == 0) return;
@@ -253,18 +269,23 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     uint32_t cta_rank = 0;
     if (CL > 1) asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(cta_rank));
+    const uint32_t hr = cta_rank & (PAIR - 1);        // which 128-row half of the pair's tile
+    const uint32_t pr = cta_rank / PAIR;              // which pair of the cluster
+    const uint32_t leader = cta_rank - hr;            // the pair's MMA-issuing CTA
+    const uint16_t pair_mask = (uint16_t)(((1u << PAIR) - 1u) << leader), all_mask = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
         // full: the leader's expect_tx arrival (+ one arrival per generator warp of the pair when A is generated)
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), GEN_A ? 1 + 4 * CL : 1); mbar_init(empty_bar(s), 1); }
+        // empty: one MMA commit per pair of the cluster (a multicast A tile lands in the shared memory of both pairs)
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), GEN_A ? 1 + 4 * PAIR : 1); mbar_init(empty_bar(s), NP); }
         // tmem_empty (leader's copy is the one the MMA thread waits on): one arrival per epilogue warp of the pair
-        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * CL); }
+        for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * PAIR); }
         for (int ew = 0; ew < TC_EPI_WARPS; ++ew)
             for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(ew, b), 1);
         if (GEN_A) { mbar_init(rows_bar(0), 1); mbar_init(rows_bar(1), 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {      // the same warp in both CTAs of a pair
-        if (CL == 1) {
+        if (PAIR == 1) {
             asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "r"(2 * BN));
             asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
         } else {
@@ -279,7 +300,10 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t tmem_base = *tmem_slot_ptr;
 
     const int m_tiles = (M + TC_BM - 1) / TC_BM, n_tiles = N / BN;
-    const int total = ((m_tiles + CL - 1) / CL) * n_tiles;       // tile groups of CL vertically adjacent 128-row tiles
+    const int nq = n_tiles / NP;                                   // work items per row group: NP adjacent n-tiles each
+    const int total = ((m_tiles + PAIR - 1) / PAIR) * nq;          // row groups of PAIR vertically adjacent 128-row tiles
+    auto tile_m0 = [&](int t) { return ((t / nq) * PAIR + (int)hr) * TC_BM; };
+    auto tile_n0 = [&](int t) { return ((t % nq) * NP + (int)pr) * BN; };
     const int kblocks = K / TC_BK;
     const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
 
@@ -289,21 +313,28 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             uint32_t it = 0;
             long long w_empty = 0;
             for (int t = cl_id; t < total; t += n_cl) {
-                const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
+                const int m0 = tile_m0(t), n0 = tile_n0(t);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     { TC_T0(); mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u); TC_ACC(w_empty); }
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
                     constexpr int TX = GEN_A ? SM::B_BYTES : SM::STAGE_BYTES;     // generated A tiles carry no TMA bytes
-                    if (CL == 1) {
+                    if (PAIR == 1) {
                         mbar_arrive_expect_tx(full_bar(s), TX);
                         if (!GEN_A) tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
                     } else {
-                        // the leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
-                        if (cta_rank == 0) mbar_arrive_expect_tx(full_bar(s), 2 * TX);
-                        if (!GEN_A) tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
-                        tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)cta_rank * (BN / CL));
+                        // the pair leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
+                        if (hr == 0) mbar_arrive_expect_tx(full_bar(s), 2 * TX);
+                        if (NP == 2) {
+                            // CTAs hr and hr + 2 hold the same 128 A rows: each fetches 64 of them (tmA has 64-row boxes here)
+                            // and multicasts them into both
+                            tma_load_2d_2sm_mc(a_dst + pr * (SM::A_BYTES / 2), &tmA, full_bar(s), kb * TC_BK, m0 + (int)pr * (TC_BM / 2),
+                                               (uint16_t)((1u << hr) | (1u << (hr + 2))));
+                        } else if (!GEN_A) {
+                            tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                        }
+                        tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)hr * (BN / PAIR));
                     }
                 }
             }
@@ -312,11 +343,11 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         }
     } else if (warp == 1) {
-        if (lane == 0 && cta_rank == 0) {
-            // ---------------- MMA issuer (leader CTA only) ----------------
-            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128 * CL
+        if (lane == 0 && hr == 0) {
+            // ---------------- MMA issuer (the leader CTA of each pair) ----------------
+            // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128 * PAIR
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)((TC_BM * CL) >> 4) << 24);
+                                   ((uint32_t)((TC_BM * PAIR) >> 4) << 24);
             uint32_t it = 0, lt = 0;
             long long w_full = 0, w_tempty = 0;
 #ifdef TC_PROFILE
@@ -335,10 +366,10 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t adesc = make_sw128_desc(a_src), bdesc = make_sw128_desc(b_src);
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-                        umma_bf16<CL>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
-                    umma_commit<CL>(empty_bar(s));        // slot reusable (in every CTA of the pair) once these MMAs have read it
+                        umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                    umma_commit<PAIR>(empty_bar(s), all_mask);    // slot reusable (told to every CTA of the cluster) once these MMAs have read it
                 }
-                umma_commit<CL>(tfull_bar(as));           // accumulator complete (signalled to every CTA of the pair)
+                umma_commit<PAIR>(tfull_bar(as), pair_mask);      // accumulator complete (signalled to both CTAs of the pair)
             }
 #ifdef TC_PROFILE
             atomicAdd(&g_tc_prof[0], (unsigned long long)w_full);
@@ -375,7 +406,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // It is tracked by the barrier, not by this thread's memory-operation scoreboard, so the proxy fences below do
         // not wait for it (a cp.async / ld.global prefetch would stall every fence until the rows arrived).
         auto prefetch_rows = [&](int t, int b) {
-            const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM;
+            const int m0 = tile_m0(t);
             const int nrows = min(TC_BM, M - m0);                      // rows past M keep stale bytes: their outputs are unused
             if (gt == 0) {
                 if (nrows > 0) {
@@ -455,7 +486,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(full_bar(s), 0);              // the leader's barrier (rank 0 of the pair)
+                if (lane == 0) mbar_arrive_cluster(full_bar(s), leader);         // the pair leader's barrier
 #ifdef TC_PROFILE
                 w_gsync += clock64() - _g3;
 #endif
@@ -489,7 +520,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
         for (int t = cl_id; t < total; t += n_cl, ++lt) {
             const int as = lt & 1;
-            const int m0 = ((t / n_tiles) * CL + (int)cta_rank) * TC_BM, n0 = (t % n_tiles) * BN;
+            const int m0 = tile_m0(t), n0 = tile_n0(t);
             const int row0 = m0 + q * 32;
             if (has_res && lane == 0) {          // this warp's first TC_NBUF residual chunks of the tile
 #pragma unroll
@@ -619,8 +650,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
             if (lane == 0) {                      // this warp's quarter of the accumulator stage is free again
-                if (CL == 1) mbar_arrive(tempty_bar(as));
-                else mbar_arrive_cluster(tempty_bar(as), 0);       // the MMA thread lives in the leader CTA
+                if (PAIR == 1) mbar_arrive(tempty_bar(as));
+                else mbar_arrive_cluster(tempty_bar(as), leader);  // the MMA thread lives in the pair's leader CTA
             }
         }
         if (lane == 0) asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
@@ -642,7 +673,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     if (CL > 1) cluster_sync_all();          // no CTA exits (or frees TMEM) while its peer may still use / signal it
     if (warp == 2) {
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-        if (CL == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
+        if (PAIR == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
         else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(2 * BN));
     }
 }
@@ -780,7 +811,10 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     TcPlan* p = new TcPlan();
     p->BN = (net.Hp % 256 == 0) ? 256 : 128;      // n-tiles must divide the padded width (Hp is a multiple of 128)
     p->CL = 2;
-    if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : 2;
+    if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : (c[0] == '4' ? 4 : 2);
+    if (p->CL == 4 && (p->BN != 256 || net.Hp % 512 != 0)) p->CL = 2;      // pairs of n-tiles must tile the width
+    p->CL_in = p->CL == 4 ? 2 : p->CL;
+    p->grid4 = 0;
     p->fuse_out = 1;
     if (const char* c = getenv("DXB200_FUSE_OUT")) p->fuse_out = (c[0] == '0') ? 0 : 1;
     p->fuse_in = 1;
@@ -791,11 +825,13 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     int rc = make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM);
     for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_xh[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM / 2);
     for (int i = 0; i < 3 && rc == DX_OK; ++i)
         rc = make_map(enc, &p->c_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
-    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN / p->CL);
+    const int pair = p->CL >= 2 ? 2 : 1;
+    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN / pair);
     if (rc == DX_OK && net.num_blocks > 0)
-        rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / p->CL);
+        rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / pair);
     if (rc == DX_OK) {
         cudaError_t ce = cudaSuccess;
         auto set_attr = [&](const void* f, int bytes) {
@@ -813,6 +849,26 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
         set_attr((const void*)k_gemm_bf16_tc<256, 2, false, true>, TcSmem<256, 2>::TOTAL);
         set_attr((const void*)k_gemm_bf16_tc<128, 1, false, true>, TcSmem<128, 1>::TOTAL);
         set_attr((const void*)k_gemm_bf16_tc<128, 2, false, true>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 4, false, false>, TcSmem<256, 4>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 4, true, false>, TcSmem<256, 4>::TOTAL);
+        if (ce == cudaSuccess && p->CL == 4) {
+            // clusters of 4 do not fill every GPC: launch exactly as many as can be co-resident (persistent tiles)
+            cudaLaunchConfig_t cfg = {};
+            cfg.gridDim = dim3((unsigned)(p->num_sms / 4 * 4));
+            cfg.blockDim = dim3(TC_THREADS);
+            cfg.dynamicSmemBytes = TcSmem<256, 4>::TOTAL;
+            cudaLaunchAttribute attr[1];
+            attr[0].id = cudaLaunchAttributeClusterDimension;
+            attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+            cfg.attrs = attr; cfg.numAttrs = 1;
+            int ncl = 0;
+            if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)k_gemm_bf16_tc<256, 4, false, false>, &cfg) != cudaSuccess || ncl < 1) {
+                cudaGetLastError();
+                p->CL = 2;
+            } else {
+                p->grid4 = ncl * 4;
+            }
+        }
         if (ce != cudaSuccess) {
             dx_set_error(std::string("cudaFuncSetAttribute(max dynamic smem) failed: ") + cudaGetErrorString(ce));
             rc = DX_ERR_CUDA;
@@ -834,46 +890,40 @@ static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const C
 }
 
 // c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
-// (no activation store; buffer c is not written); gen != nullptr selects the fused one-hot input (a is not read)
-static void launch_gemm(cudaStream_t s, const TcPlan* p, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
+// (no activation store; buffer c is not written); gen != nullptr selects the fused one-hot input (a is not read);
+// cl: CTAs per cluster of this launch
+static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
                         int K, int N, const float* bias, int r, int c, int relu, const float* wout = nullptr,
                         float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(p->num_sms / p->CL * p->CL));
+    cfg.gridDim = dim3((unsigned)(cl == 4 ? p->grid4 : p->num_sms / cl * cl));
     cfg.blockDim = dim3(TC_THREADS);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];
     attr[0].id = cudaLaunchAttributeClusterDimension;
-    attr[0].val.clusterDim.x = (unsigned)p->CL;
+    attr[0].val.clusterDim.x = (unsigned)cl;
     attr[0].val.clusterDim.y = 1;
     attr[0].val.clusterDim.z = 1;
     cfg.attrs = attr;
     cfg.numAttrs = 1;
     const int has_res = r >= 0 ? 1 : 0;
     const TcGen g = gen ? *gen : TcGen{};
-    const int sel = (p->BN == 256 ? 4 : 0) | (p->CL == 2 ? 2 : 0) | (partial ? 1 : 0);
+    const bool big = p->BN == 256, fuse = partial != nullptr;
 #define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g
+#define DX_TC_PICK(CLV, FUSEV, GENV) do { if (big) launch_gemm_t<256, CLV, FUSEV, GENV>(DX_TC_ARGS); \
+                                          else launch_gemm_t<128, CLV, FUSEV, GENV>(DX_TC_ARGS); } while (0)
     if (gen) {
-        switch (sel >> 1) {
-            case 3: launch_gemm_t<256, 2, false, true>(DX_TC_ARGS); break;
-            case 2: launch_gemm_t<256, 1, false, true>(DX_TC_ARGS); break;
-            case 1: launch_gemm_t<128, 2, false, true>(DX_TC_ARGS); break;
-            default: launch_gemm_t<128, 1, false, true>(DX_TC_ARGS); break;
-        }
+        if (cl == 2) DX_TC_PICK(2, false, true); else DX_TC_PICK(1, false, true);
+    } else if (cl == 4) {
+        if (fuse) launch_gemm_t<256, 4, true, false>(DX_TC_ARGS); else launch_gemm_t<256, 4, false, false>(DX_TC_ARGS);
+    } else if (cl == 2) {
+        if (fuse) DX_TC_PICK(2, true, false); else DX_TC_PICK(2, false, false);
     } else {
-        switch (sel) {
-            case 7: launch_gemm_t<256, 2, true, false>(DX_TC_ARGS); break;
-            case 6: launch_gemm_t<256, 2, false, false>(DX_TC_ARGS); break;
-            case 5: launch_gemm_t<256, 1, true, false>(DX_TC_ARGS); break;
-            case 4: launch_gemm_t<256, 1, false, false>(DX_TC_ARGS); break;
-            case 3: launch_gemm_t<128, 2, true, false>(DX_TC_ARGS); break;
-            case 2: launch_gemm_t<128, 2, false, false>(DX_TC_ARGS); break;
-            case 1: launch_gemm_t<128, 1, true, false>(DX_TC_ARGS); break;
-            default: launch_gemm_t<128, 1, false, false>(DX_TC_ARGS); break;
-        }
+        if (fuse) DX_TC_PICK(1, true, false); else DX_TC_PICK(1, false, false);
     }
+#undef DX_TC_PICK
 #undef DX_TC_ARGS
 }
 
@@ -897,11 +947,11 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
         TcGen g;
         g.rows = rows; g.goals = goals; g.S = d.S; g.SP = d.SP; g.in_count = net.in_count; g.depth = net.depth; g.ones_col = ones_col;
-        launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
+        launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
         ++launches;
     } else {
         k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, ctl, rows, goals, p->onehot);
-        launch_gemm(s, p, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0);
+        launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0);
         launches += 2;
     }
     dx_prof_end();
@@ -911,14 +961,15 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     // writes 2 * Hp / BN fp32 partials per row into the (otherwise unused) third activation buffer
     const bool fuse = net.out_dim == 1 && net.num_blocks > 0 && p->fuse_out;
     const int P = 2 * (Hp / p->BN);
+    const CUtensorMap* ax = p->CL == 4 ? p->a_xh : p->a_x;
     dx_prof_begin(DX_ST_GEMM_RES);
     for (int b = 0; b < net.num_blocks; ++b) {
-        launch_gemm(s, p, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
+        launch_gemm(s, p, p->CL, ax[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
         if (fuse && b == net.num_blocks - 1)
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+            launch_gemm(s, p, p->CL, ax[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
                         net.wout, (float*)mb.xb[iz], mb.cap);
         else
-            launch_gemm(s, p, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
+            launch_gemm(s, p, p->CL, ax[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
         launches += 2;
         int ti = ix; ix = iz; iz = ti;
     }

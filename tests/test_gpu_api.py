@@ -175,6 +175,34 @@ def test_bf16_network_within_tolerance(tag, dname, dim, q, atol):
     eng.close()
 
 
+@pytest.mark.parametrize("switch", [{}, {"DXB200_FUSE_IN": "0"}, {"DXB200_FOLD_BIAS": "0"}, {"DXB200_FUSE_OUT": "0"},
+                                    {"DXB200_GEMM_CLUSTER": "1"}, {"DXB200_GEMM_CLUSTER": "4"},
+                                    {"DXB200_FUSE_IN": "0", "DXB200_FOLD_BIAS": "0", "DXB200_FUSE_OUT": "0"}])
+def test_bf16_kernel_variants_agree(switch, monkeypatch):
+    """Every variant of the tensor-core path (one-hot generated inside the first GEMM or read from a one-hot matrix, bias
+    folded into the GEMM or added in the epilogue, output layer folded into the last GEMM or separate, single CTAs /
+    CTA pairs / clusters of two pairs with multicast A tiles) computes the same network: each stays within the bf16
+    tolerance of the fp32 torch reference on 3000 random states (DeepCubeA-sized resnet_fc.1000H_4B_bn), on 5000 rows so
+    that several row tiles and every cluster rank are exercised."""
+    import torch
+    from deepxube_b200 import _lib as L
+    from oracle.nnet_torch import random_state_dict, resnet_fc_forward
+    for k, v in switch.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(5)
+    st = rng.integers(0, 6, size=(5000, 54), dtype=np.uint8)
+    sd = random_state_dict(324, 1000, 4, 1, True, seed=3, randomize_bn=True)
+    ref = np.maximum(np.asarray(resnet_fc_forward(sd, st.astype(np.int64), 6)).ravel(), 0)
+    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_BF16, max_instances=4, max_pop_total=512, max_nodes=8192)
+    blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    eng.load_weights(54, 6, 1000, 4, 1, True, blob)
+    out = eng.heur_eval(st, None, 1).ravel()
+    out2 = eng.heur_eval(st, None, 1).ravel()
+    eng.close()
+    assert np.array_equal(out, out2), "evaluation is not repeatable"
+    np.testing.assert_allclose(out, ref, rtol=0, atol=0.01)
+
+
 def test_bf16_search_deviation_is_reported():
     """bf16 heuristics cannot promise identical node counts: solutions must stay valid and the
     deviation of cost / nodes from the fp32 KAT is bounded and printed."""

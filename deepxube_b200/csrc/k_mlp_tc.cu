@@ -263,6 +263,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto res_bar = [&](int ew, int b) { return bar_base + 8u * (2 * STAGES + 4 + TC_NBUF * ew + b); };
     const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4 + TC_EPI_WARPS * TC_NBUF);
     auto rows_bar = [&](int b) { return bar_base + 8u * (2 * STAGES + 5 + TC_EPI_WARPS * TC_NBUF + b); };   // GEN_A: state rows landed
+    // GEN_A: the generated A tile of k-block kb (kb < 8) is complete / has been read by the MMAs of the row group's last n-tile
+    auto afull_bar = [&](int kb) { return bar_base + 8u * (2 * STAGES + 7 + TC_EPI_WARPS * TC_NBUF + kb); };
+    auto aempty_bar = [&](int kb) { return bar_base + 8u * (2 * STAGES + 15 + TC_EPI_WARPS * TC_NBUF + kb); };
     volatile uint32_t* tmem_slot_ptr =
         reinterpret_cast<volatile uint32_t*>(smem_raw + (tmem_slot - smem_u32(smem_raw)));
 
@@ -274,14 +277,17 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     const uint32_t leader = cta_rank - hr;            // the pair's MMA-issuing CTA
     const uint16_t pair_mask = (uint16_t)(((1u << PAIR) - 1u) << leader), all_mask = (uint16_t)((1u << CL) - 1u);
     if (threadIdx.x == 0) {
-        // full: the leader's expect_tx arrival (+ one arrival per generator warp of the pair when A is generated)
+        // full: the leader's expect_tx arrival
         // empty: one MMA commit per pair of the cluster (a multicast A tile lands in the shared memory of both pairs)
-        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), GEN_A ? 1 + 4 * PAIR : 1); mbar_init(empty_bar(s), NP); }
+        for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), NP); }
         // tmem_empty (leader's copy is the one the MMA thread waits on): one arrival per epilogue warp of the pair
         for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), TC_EPI_WARPS * PAIR); }
         for (int ew = 0; ew < TC_EPI_WARPS; ++ew)
             for (int b = 0; b < TC_NBUF; ++b) mbar_init(res_bar(ew, b), 1);
-        if (GEN_A) { mbar_init(rows_bar(0), 1); mbar_init(rows_bar(1), 1); }
+        if (GEN_A) {
+            mbar_init(rows_bar(0), 1); mbar_init(rows_bar(1), 1);
+            for (int kb = 0; kb < 8; ++kb) { mbar_init(afull_bar(kb), 4 * PAIR); mbar_init(aempty_bar(kb), 1); }   // one arrival per generator warp
+        }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 2) {      // the same warp in both CTAs of a pair
@@ -306,22 +312,59 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
     auto tile_n0 = [&](int t) { return ((t % nq) * NP + (int)pr) * BN; };
     const int kblocks = K / TC_BK;
     const int cl_id = blockIdx.x / CL, n_cl = gridDim.x / CL;
+    // GEN_A (input layer): a cluster takes whole row groups; the generated A tiles of a group (kblocks x 16 KB) stay resident
+    // in the operand region for all n-tiles of the group, and what is left of the region is the ring of weight tiles.
+    const int groups = (m_tiles + PAIR - 1) / PAIR;
+    const int a_res_bytes = GEN_A ? kblocks * SM::A_BYTES : 0;
+    const int nb_st = GEN_A ? min(STAGES, (STAGES * SM::STAGE_BYTES - a_res_bytes) / SM::B_BYTES) : STAGES;
+    // k-th tile of this cluster, in the order every role walks them
+    auto seq_tile = [&](int k, int& m0, int& n0) -> bool {
+        if (GEN_A) {
+            const int g = cl_id + (k / n_tiles) * n_cl;
+            if (g >= groups) return false;
+            m0 = (g * PAIR + (int)hr) * TC_BM;
+            n0 = (k % n_tiles) * BN;
+            return true;
+        }
+        const int t = cl_id + k * n_cl;
+        if (t >= total) return false;
+        m0 = tile_m0(t);
+        n0 = tile_n0(t);
+        return true;
+    };
 
     if (warp == 0) {
         if (lane == 0) {
             // ---------------- TMA producer (every CTA: its A rows, its share of the weight tile) ----------------
             uint32_t it = 0;
             long long w_empty = 0;
-            for (int t = cl_id; t < total; t += n_cl) {
+            if (GEN_A) {       // weight tiles only: ring of nb_st slots behind the resident A tiles
+                uint32_t s = 0, ph = 0;
+                int m0, n0;
+                for (int k = 0; seq_tile(k, m0, n0); ++k)
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        mbar_wait(empty_bar(s), ph ^ 1u);
+                        const uint32_t b_dst = smem_base + a_res_bytes + s * SM::B_BYTES;
+                        if (PAIR == 1) {
+                            mbar_arrive_expect_tx(full_bar(s), SM::B_BYTES);
+                            tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
+                        } else {
+                            if (hr == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SM::B_BYTES);
+                            tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)hr * (BN / PAIR));
+                        }
+                        if (++s == (uint32_t)nb_st) { s = 0; ph ^= 1u; }
+                    }
+            }
+            for (int t = cl_id; !GEN_A && t < total; t += n_cl) {
                 const int m0 = tile_m0(t), n0 = tile_n0(t);
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     { TC_T0(); mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u); TC_ACC(w_empty); }
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
-                    constexpr int TX = GEN_A ? SM::B_BYTES : SM::STAGE_BYTES;     // generated A tiles carry no TMA bytes
+                    constexpr int TX = SM::STAGE_BYTES;
                     if (PAIR == 1) {
                         mbar_arrive_expect_tx(full_bar(s), TX);
-                        if (!GEN_A) tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                        tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
                     } else {
                         // the pair leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
@@ -331,7 +374,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                             // and multicasts them into both
                             tma_load_2d_2sm_mc(a_dst + pr * (SM::A_BYTES / 2), &tmA, full_bar(s), kb * TC_BK, m0 + (int)pr * (TC_BM / 2),
                                                (uint16_t)((1u << hr) | (1u << (hr + 2))));
-                        } else if (!GEN_A) {
+                        } else {
                             tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
                         }
                         tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)hr * (BN / PAIR));
@@ -353,7 +396,31 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef TC_PROFILE
             const long long t_mma0 = clock64();
 #endif
-            for (int t = cl_id; t < total; t += n_cl, ++lt) {
+            if (GEN_A) {
+                uint32_t s = 0, ph = 0;
+                int m0, n0;
+                for (int k = 0; seq_tile(k, m0, n0); ++k, ++lt) {
+                    const int as = lt & 1, nt = k % n_tiles;
+                    const uint32_t gph = (uint32_t)(k / n_tiles) & 1u;          // phase of the row group's A barriers
+                    { TC_T0(); mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u); TC_ACC(w_tempty); }
+                    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                    const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                    for (int kb = 0; kb < kblocks; ++kb) {
+                        { TC_T0(); mbar_wait(full_bar(s), ph); if (nt == 0) mbar_wait(afull_bar(kb), gph); TC_ACC(w_full); }
+                        asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                        const uint64_t adesc = make_sw128_desc(smem_base + kb * SM::A_BYTES);
+                        const uint64_t bdesc = make_sw128_desc(smem_base + a_res_bytes + s * SM::B_BYTES);
+#pragma unroll
+                        for (int q = 0; q < TC_BK / TC_UMMA_K; ++q)
+                            umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(q * 2), bdesc + (uint64_t)(q * 2), idesc, (kb | q) ? 1u : 0u);
+                        umma_commit<PAIR>(empty_bar(s), all_mask);
+                        if (nt == n_tiles - 1) umma_commit<PAIR>(aempty_bar(kb), pair_mask);   // the group's A tile kb may be overwritten
+                        if (++s == (uint32_t)nb_st) { s = 0; ph ^= 1u; }
+                    }
+                    umma_commit<PAIR>(tfull_bar(as), pair_mask);
+                }
+            }
+            for (int t = cl_id; !GEN_A && t < total; t += n_cl, ++lt) {
                 const int as = lt & 1;
                 { TC_T0(); mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u); TC_ACC(w_tempty); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -405,8 +472,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         // One bulk copy (TMA, completes on rows_bar) brings a tile's rows -- contiguous in the node store -- into buffer b.
         // It is tracked by the barrier, not by this thread's memory-operation scoreboard, so the proxy fences below do
         // not wait for it (a cp.async / ld.global prefetch would stall every fence until the rows arrived).
-        auto prefetch_rows = [&](int t, int b) {
-            const int m0 = tile_m0(t);
+        auto prefetch_rows = [&](int g, int b) {       // rows of row group g (this CTA's half)
+            const int m0 = (g * PAIR + (int)hr) * TC_BM;
             const int nrows = min(TC_BM, M - m0);                      // rows past M keep stale bytes: their outputs are unused
             if (gt == 0) {
                 if (nrows > 0) {
@@ -420,21 +487,20 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 }
             }
         };
-        if (cl_id < total) prefetch_rows(cl_id, 0);
-        uint32_t it = 0, lt = 0;
+        if (cl_id < groups) prefetch_rows(cl_id, 0);
+        uint32_t lt = 0;                                 // row groups done by this cluster
         long long w_gslot = 0, w_gmask = 0, w_gexp = 0, w_gsync = 0;
 #ifdef TC_PROFILE
         const long long t_gen0 = clock64();
 #endif
         const int r = gt;
         const uint32_t arow_off = (uint32_t)((r >> 3) * 1024 + (r & 7) * 128);      // SW128: chunk j of row r at j ^ (r & 7)
-        for (int t = cl_id; t < total; t += n_cl, ++lt) {
+        for (int g = cl_id; g < groups; g += n_cl, ++lt) {
             asm volatile("bar.sync 1, 128;" ::: "memory");         // everyone is done with the other buffer (and the LUT is written)
-            if (t + n_cl < total) prefetch_rows(t + n_cl, (lt + 1) & 1);
-            mbar_wait(rows_bar(lt & 1), (lt >> 1) & 1u);           // this tile's rows have landed
+            if (g + n_cl < groups) prefetch_rows(g + n_cl, (lt + 1) & 1);
+            mbar_wait(rows_bar(lt & 1), (lt >> 1) & 1u);           // this group's rows have landed
             const uint8_t* srow = rows_buf0 + (lt & 1) * TC_BM * SP + r * SP;
-            for (int kb = 0; kb < kblocks; ++kb, ++it) {
-                const int s = it % STAGES;
+            for (int kb = 0; kb < kblocks; ++kb) {
                 const int f0 = kb * TC_BK;
                 const int i_lo = irange[2 * kb], i_hi = irange[2 * kb + 1];
 #ifdef TC_PROFILE
@@ -469,12 +535,12 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const long long _g1 = clock64();
                 w_gmask += _g1 - _g0;
 #endif
-                mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u);          // the mask is ready before the slot is needed
+                mbar_wait(aempty_bar(kb), (lt & 1u) ^ 1u);      // the previous group's MMAs have read this resident tile
 #ifdef TC_PROFILE
                 const long long _g2 = clock64();
                 w_gslot += _g2 - _g1;
 #endif
-                uint8_t* arow = smem_raw + (smem_base + s * SM::STAGE_BYTES - smem_u32(smem_raw)) + arow_off;
+                uint8_t* arow = smem_raw + (smem_base + kb * SM::A_BYTES - smem_u32(smem_raw)) + arow_off;
                 uint4 ch[8];
 #pragma unroll
                 for (int j = 0; j < 8; ++j) ch[j] = lut[lut_slot(((j < 4 ? mlo : mhi) >> (8 * (j & 3))) & 0xFFu)];
@@ -486,7 +552,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
                 asm volatile("fence.proxy.async.shared::cta;" ::: "memory");     // generic-proxy writes -> visible to the MMA
                 __syncwarp();
-                if (lane == 0) mbar_arrive_cluster(full_bar(s), leader);         // the pair leader's barrier
+                if (lane == 0) mbar_arrive_cluster(afull_bar(kb), leader);       // the pair leader's barrier
 #ifdef TC_PROFILE
                 w_gsync += clock64() - _g3;
 #endif
@@ -518,9 +584,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #ifdef TC_PROFILE
         const long long t_epi0 = clock64();
 #endif
-        for (int t = cl_id; t < total; t += n_cl, ++lt) {
+        int m0, n0;
+        for (int k = 0; seq_tile(k, m0, n0); ++k, ++lt) {
             const int as = lt & 1;
-            const int m0 = tile_m0(t), n0 = tile_n0(t);
             const int row0 = m0 + q * 32;
             if (has_res && lane == 0) {          // this warp's first TC_NBUF residual chunks of the tile
 #pragma unroll
@@ -942,7 +1008,11 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const int kv_in = net.in_dim_p, kv_h = Hp, nv = Hp;      // padded shapes (trimming the padding measured no gain)
     dx_prof_begin(DX_ST_GEMM_IN);
     // (networks that also read the goal keep the separate one-hot kernel: the goal row is a dependent gather)
-    if (p->fuse_in && net.in_count <= d.S && d.SP % 16 == 0 && net.in_dim_p <= 4096 &&
+    // ... and the generated A tiles of a row group (in_dim_p / 64 tiles of 16 KB, at most 8) stay resident next to a ring of
+    // at least 3 weight tiles, which needs CTA pairs (half-size weight tiles)
+    const int kb_in = net.in_dim_p / TC_BK;
+    const int ring_in = (5 * (TC_BM * TC_BK * 2 + (p->BN / 2) * TC_BK * 2) - kb_in * TC_BM * TC_BK * 2) / ((p->BN / 2) * TC_BK * 2);
+    if (p->fuse_in && p->CL_in == 2 && kb_in <= 8 && ring_in >= 3 && net.in_count <= d.S && d.SP % 16 == 0 &&
         4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64) {
         // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
         TcGen g;

@@ -177,6 +177,42 @@ def run_reference(args, rank: int, world: int) -> None:
     print(json.dumps(line), flush=True)
 
 
+def kat_solve_times(L, device: int) -> dict:
+    """Solve time / instance (the second half of BASELINE's metric) on the reference's own known-answer set:
+    tutorial/cube3 `hard` instances with the trained resnet_fc.200H_2B_bn heuristic, graph.100B_0.1W
+    (fixtures under tests/golden/, generated from the unmodified reference by tools/gen_golden.py).  Timed like
+    deepxube/_solve.py:150-161 (instance creation + every step), one instance at a time, fp32 network (bit-exact path)."""
+    g = os.path.join(ROOT, "tests", "golden")
+    k = np.load(os.path.join(g, "kat_cube3.npz"))
+    z = np.load(os.path.join(g, "nnet.npz"))
+    sd = {key[len("cube3v/"):]: z[key] for key in z.files if key.startswith("cube3v/")}
+    out = {}
+    for prec, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16)):
+        eng = L.Engine("cube3", 0, "graph_v", mode, max_instances=1, max_pop_total=100, max_nodes=600000, device=device)
+        blob, info = L.pack_state_dict(sd)
+        eng.load_weights(IN_COUNT, DEPTH, info["res_dim"], info["num_blocks"], 1, True, blob)
+        eng.add_instances(k["hard_states"][:1], k["hard_goals"][:1], 100, 0.1)      # warm-up: graph capture
+        eng.run(100000)
+        secs, nodes, costs = [], [], []
+        for i in range(10):
+            t0 = time.perf_counter()
+            eng.reset()
+            eng.add_instances(k["hard_states"][i:i + 1], k["hard_goals"][i:i + 1], 100, 0.1)
+            eng.run(100000)
+            stt = eng.status()[0]
+            secs.append(time.perf_counter() - t0)
+            nodes.append(int(stt.num_nodes_generated))
+            costs.append(float(stt.ub))              # path cost of the goal node = ub
+        eng.close()
+        out[prec] = {"instances": 10, "mean_solve_time_s": float(np.mean(secs)), "max_solve_time_s": float(np.max(secs)),
+                     "nodes_per_s": float(np.sum(nodes) / np.sum(secs)), "mean_path_cost": float(np.mean(costs)),
+                     "path_costs_equal_reference": bool(np.array_equal(np.array(costs), k["hard_path_costs"])),
+                     "nodes_generated_equal_reference": bool(np.array_equal(np.array(nodes), k["hard_nodes"]))}
+    out["workload"] = "tutorial/cube3 hard set (10 instances), heurv resnet_fc.200H_2B_bn trained weights, graph.100B_0.1W"
+    out["reference_mean_path_cost"] = float(np.mean(k["hard_path_costs"]))
+    return out
+
+
 def workload_config(args, world: int) -> dict:
     return {"workload": "cube3 batch weighted A* graph.10000B_0.6W, heurv resnet_fc.1000H_4B_bn random-init, "
                         "1000 synthetic scrambles (BASELINE.json configs[1])",
@@ -198,6 +234,7 @@ def main() -> None:
     ap.add_argument("--ref-itrs", type=int, default=5, help="iterations per bounded CPU sample")
     ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-kat", action="store_true", help="skip the solve-time-per-instance report on the trained-net KAT set")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
 
@@ -357,6 +394,11 @@ def main() -> None:
                         "api": "get_pathfind_from_arg('graph.10000B_0.6W') -> make_instances/add_instances/step() per iteration from host State objects"},
                 "gpu_launches": int(tot[3]), "roofline": roof,
                 "heur_evals": int(tot[2]), "nodes_generated": int(tot[0]), "wall_s_value_pass": wall_value_pass}
+        if world == 1 and not args.no_kat:
+            try:
+                line["kat_solve"] = kat_solve_times(L, local)
+            except Exception as e:  # noqa: BLE001  (extra information only; never fails the bench line)
+                line["kat_solve"] = {"error": str(e)}
         if not args.no_cpu_baseline:
             import torch as _t
             threads = os.cpu_count() or 8

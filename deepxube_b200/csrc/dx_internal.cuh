@@ -111,6 +111,8 @@ struct NetDev {
     // H..H+2 hold a 3-piece bf16 split of the fp32 bias (hi + mid + lo == bias exactly), so the GEMM adds the bias.
     int tc_fold;     // bit 0: hidden layers folded, bit 1: input layer folded
     float* b0_tc;    // [Hp] first-layer bias for the unfolded input layer (carries the 1.0 of the ones columns), else nullptr
+    void* wout_bf16; // [128, Hp] zero-padded bf16 output-layer weights (multi-output networks with out_dim <= 32), else nullptr
+    float* bout_pad; // [128] output bias, zero-padded
     void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16
 };
 

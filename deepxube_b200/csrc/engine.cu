@@ -1197,6 +1197,8 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     // Bias folding (NetDev::tc_fold): spare padding columns carry the bias through the GEMM itself.
     net.tc_fold = 0;
     net.b0_tc = nullptr;
+    net.wout_bf16 = nullptr;
+    net.bout_pad = nullptr;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
         auto bf16r = [](float x) {                 // round to nearest even, as k_f32_to_bf16
             uint32_t u; memcpy(&u, &x, 4);
@@ -1236,7 +1238,7 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
         DX_TRY(e->alloc(&w0b, w0p.size()));
         DX_TRY(e->alloc(&wrb, wres_tc.size()));
         float* tmp = nullptr;
-        const size_t tmp_n = std::max(w0p.size(), std::max<size_t>(wres_tc.size(), 1));
+        const size_t tmp_n = std::max(std::max(w0p.size(), (size_t)128 * Hp), std::max<size_t>(wres_tc.size(), 1));
         DX_CUDA(cudaMalloc(&tmp, tmp_n * sizeof(float)));
         // copies go through the engine's (non-blocking) stream: a legacy-stream cudaMemcpy from pageable memory may
         // return before its DMA has landed, and nothing would order the conversion kernel after it
@@ -1248,6 +1250,24 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, wrb, wres_tc.size());
         }
         cudaError_t ce = cudaStreamSynchronize(e->stream);
+        net.wout_bf16 = nullptr;
+        net.bout_pad = nullptr;
+        if (ce == cudaSuccess && od > 1 && od <= 32 && tmp_n >= (size_t)128 * Hp) {
+            // multi-output layer on the tensor cores: weight rows zero-padded to one 128-wide n-tile
+            std::vector<float> wpad((size_t)128 * Hp, 0.f), bpad(128, 0.f);
+            for (int o = 0; o < od; ++o) {
+                memcpy(&wpad[(size_t)o * Hp], &wout[(size_t)o * Hp], (size_t)Hp * sizeof(float));
+                bpad[o] = bout[o];
+            }
+            uint16_t* wob = nullptr;
+            DX_TRY(e->alloc(&wob, wpad.size()));
+            DX_TRY(e->alloc(&net.bout_pad, bpad.size()));
+            cudaMemcpyAsync(net.bout_pad, bpad.data(), bpad.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+            cudaMemcpyAsync(tmp, wpad.data(), wpad.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+            k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, wob, wpad.size());
+            ce = cudaStreamSynchronize(e->stream);
+            net.wout_bf16 = wob;
+        }
         cudaFree(tmp);
         DX_CUDA(ce);
         net.w0_bf16 = w0b;

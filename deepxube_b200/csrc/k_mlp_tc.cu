@@ -48,6 +48,8 @@ struct TcPlan {
     CUtensorMap a_xh[3];         // the same buffers in 64-row boxes (clusters of two pairs: each CTA fetches half of an A tile)
     CUtensorMap b_w0;
     CUtensorMap b_res;
+    CUtensorMap b_out;           // zero-padded output-layer weights [128, Hp] (multi-output networks), boxes of 128 / pair rows
+    int q_out;                   // the multi-output layer runs on the tensor cores (DXB200_QOUT=0: warp-per-state kernel)
     CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
     int BN;
@@ -237,21 +239,29 @@ struct TcSmem {
 // thread dots its row's 128 activated columns with the output layer's weight row and writes one fp32 partial
 // (partial[(2 * n_tile + h) * pstride + row]); k_out_final_bf16 adds the partials in a fixed order.
 // GEN_A = true (input layer): no A tensor map is read; four generator warps write the one-hot A tiles (TcGen).
-template <int BN, int CL, bool FUSE_OUT, bool GEN_A>
+// OUT_MODE 0: store the bf16 activations; 1 (= FUSE_OUT, above); 2 (= Q_OUT): the launch IS the output layer of a
+// multi-output network (Q*: out_dim = #actions <= 32, weight rows zero-padded to the n-tile): the epilogue adds the fp32
+// bias, clips at 0 and writes the first qdim columns as fp32 q-values plus their minimum (node.heuristic) -- no bf16
+// rounding of the outputs, no activation store.
+template <int BN, int CL, int OUT_MODE, bool GEN_A>
 __global__ void __launch_bounds__(GEN_A ? TC_THREADS_GEN : TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
                int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu,
-               const float* __restrict__ wout, float* __restrict__ partial, long long pstride, const TcGen gen) {
+               const float* __restrict__ wout, float* __restrict__ partial, long long pstride, const TcGen gen,
+               float* __restrict__ out_h, int qdim, int absolute) {
     extern __shared__ uint8_t smem_raw[];
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
+    constexpr bool FUSE_OUT = OUT_MODE == 1, Q_OUT = OUT_MODE == 2;
     constexpr int PAIR = SM::PAIR;           // CTAs per MMA
     constexpr int NP = CL / PAIR;            // pairs per cluster; NP = 2: two pairs work on adjacent n-tiles of the same rows
                                              // and fetch their common A tiles once, by TMA multicast
     static_assert(!(GEN_A && CL > 2), "the generated input layer runs in single CTAs or pairs");
     if (ctl->error) return;
     const int M = (int)ctl->nn_n;
+    if (Q_OUT && blockIdx.x == 0 && threadIdx.x == 0)
+        atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)M);
     if (M == 0) return;
     const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
     const uint32_t bar_base = smem_base + SM::BAR_OFF;
@@ -600,6 +610,8 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(as * BN);
 
             float oacc = 0.f;                     // FUSE_OUT: this row's partial output-layer dot product
+            float hmin = __int_as_float(0x7f800000);      // Q_OUT: min over the row's q-values
+            const size_t orow = (size_t)(absolute ? ctl->nn_row_start : 0u) + (size_t)(row0 + lane);   // Q_OUT: output row
             auto process = [&](const uint32_t* v, int c) {
                 const int b = (c >> 1) & (TC_NBUF - 1);       // this warp's chunks are c = h, h + 2, ...
                 const int col = n0 + c * 32;
@@ -627,7 +639,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     TC_ACC(w_res);
                     rphase ^= 1u << b;
                 }
-                if (!FUSE_OUT) {   // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
+                if (OUT_MODE == 0) {   // the TMA store that last read output buffer b (TC_NBUF chunks ago) must be done with it
                     TC_T0();
                     if (lane == 0) asm volatile("cp.async.bulk.wait_group.read " TC_NBUF_M1 ";" ::: "memory");
                     __syncwarp();
@@ -660,7 +672,16 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #pragma unroll
                         for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
                     }
-                    if (FUSE_OUT) {
+                    if (Q_OUT) {
+                        if (row0 + lane < M) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (8 * g + e < qdim) {
+                                    hmin = fminf(hmin, f[e]);
+                                    partial[orow * (size_t)qdim + (size_t)(8 * g + e)] = f[e];
+                                }
+                        }
+                    } else if (FUSE_OUT) {
                         const float4 wa = wv[FUSE_OUT ? 2 * g : 0], wb = wv[FUSE_OUT ? 2 * g + 1 : 0];
                         oacc = fmaf(f[0], wa.x, oacc); oacc = fmaf(f[1], wa.y, oacc);
                         oacc = fmaf(f[2], wa.z, oacc); oacc = fmaf(f[3], wa.w, oacc);
@@ -678,14 +699,14 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 const long long _tm1 = clock64();
                 w_math += _tm1 - _tm0;
 #endif
-                if (!FUSE_OUT) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
+                if (OUT_MODE == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // generic-proxy writes -> visible to TMA
                 __syncwarp();
 #ifdef TC_PROFILE
                 const long long _tm2 = clock64();
                 w_fence += _tm2 - _tm1;
 #endif
                 if (lane == 0) {
-                    if (!FUSE_OUT) {
+                    if (OUT_MODE == 0) {
                         tma_store_2d(&tmC, epi_base + b * SM::EPI_BUF, col, row0);
                         asm volatile("cp.async.bulk.commit_group;" ::: "memory");
                     }
@@ -700,6 +721,14 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             };
 
             uint32_t va[32], vb[32];
+            if (Q_OUT) {                                   // the q-values live in the first 32 columns: one chunk, by the h = 0 warps
+                if (h == 0) {
+                    tmem_ld32(t_row, va);
+                    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                    process(va, 0);
+                    if (out_h && row0 + lane < M) out_h[orow] = hmin;
+                }
+            } else {
             tmem_ld32(t_row + (uint32_t)(h * 32), va);
 #pragma unroll 1
             for (int c = h; c < NCH; c += 4) {
@@ -711,6 +740,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     if (c + 4 < NCH) tmem_ld32(t_row + (uint32_t)((c + 4) * 32), va);
                     process(vb, c + 2);
                 }
+            }
             }
             if (FUSE_OUT && row0 + lane < M) partial[(size_t)((n0 / BN) * 2 + h) * (size_t)pstride + (size_t)(row0 + lane)] = oacc;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -898,25 +928,33 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN / pair);
     if (rc == DX_OK && net.num_blocks > 0)
         rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / pair);
+    p->q_out = 0;
+    if (rc == DX_OK && net.wout_bf16) {
+        const char* c = getenv("DXB200_QOUT");
+        p->q_out = (c && c[0] == '0') ? 0 : 1;
+        rc = make_map(enc, &p->b_out, net.wout_bf16, net.Hp, 128, 128 / pair);
+    }
     if (rc == DX_OK) {
         cudaError_t ce = cudaSuccess;
         auto set_attr = [&](const void* f, int bytes) {
             if (ce == cudaSuccess) ce = cudaFuncSetAttribute(f, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
         };
-        set_attr((const void*)k_gemm_bf16_tc<256, 1, false, false>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2, false, false>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1, false, false>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2, false, false>, TcSmem<128, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 1, true, false>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2, true, false>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1, true, false>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2, true, false>, TcSmem<128, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 1, false, true>, TcSmem<256, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 2, false, true>, TcSmem<256, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 1, false, true>, TcSmem<128, 1>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<128, 2, false, true>, TcSmem<128, 2>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 4, false, false>, TcSmem<256, 4>::TOTAL);
-        set_attr((const void*)k_gemm_bf16_tc<256, 4, true, false>, TcSmem<256, 4>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, 0, false>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, 0, false>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, 0, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 0, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, 1, false>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, 1, false>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, 1, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 1, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 1, 0, true>, TcSmem<256, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, 0, true>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, 0, true>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 0, true>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 1, 2, false>, TcSmem<128, 1>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 2, false>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 4, 0, false>, TcSmem<256, 4>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 4, 1, false>, TcSmem<256, 4>::TOTAL);
         if (ce == cudaSuccess && p->CL == 4) {
             // clusters of 4 do not fill every GPC: launch exactly as many as can be co-resident (persistent tiles)
             cudaLaunchConfig_t cfg = {};
@@ -928,7 +966,7 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
             attr[0].val.clusterDim.x = 4; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
             cfg.attrs = attr; cfg.numAttrs = 1;
             int ncl = 0;
-            if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)k_gemm_bf16_tc<256, 4, false, false>, &cfg) != cudaSuccess || ncl < 1) {
+            if (cudaOccupancyMaxActiveClusters(&ncl, (const void*)k_gemm_bf16_tc<256, 4, 0, false>, &cfg) != cudaSuccess || ncl < 1) {
                 cudaGetLastError();
                 p->CL = 2;
             } else {
@@ -945,22 +983,25 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     return DX_OK;
 }
 
-template <int BN, int CL, bool FUSE, bool GEN>
+struct TcQOut { float* out_h; int qdim; int absolute; };       // Q_OUT launches: where the fp32 q-values / minima go
+
+template <int BN, int CL, int MODE, bool GEN>
 static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& tc,
                           const CUtensorMap& tr, const Ctl* ctl, int w_row0, int K, int N, const float* bias, int has_res,
-                          int relu, const float* wout, float* partial, long long pstride, const TcGen& gen) {
+                          int relu, const float* wout, float* partial, long long pstride, const TcGen& gen, const TcQOut& qo) {
     cfg->dynamicSmemBytes = TcSmem<BN, CL>::TOTAL;
     cfg->blockDim = dim3(GEN ? TC_THREADS_GEN : TC_THREADS);
-    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, FUSE, GEN>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
-                       pstride, gen);
+    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, MODE, GEN>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
+                       pstride, gen, qo.out_h, qo.qdim, qo.absolute);
 }
 
 // c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
 // (no activation store; buffer c is not written); gen != nullptr selects the fused one-hot input (a is not read);
+// qo != nullptr: this launch is the multi-output layer itself (128-wide n-tile, partial = q-value array);
 // cl: CTAs per cluster of this launch
 static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
                         int K, int N, const float* bias, int r, int c, int relu, const float* wout = nullptr,
-                        float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr) {
+                        float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr, const TcQOut* qo = nullptr) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
@@ -976,18 +1017,21 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorM
     cfg.numAttrs = 1;
     const int has_res = r >= 0 ? 1 : 0;
     const TcGen g = gen ? *gen : TcGen{};
+    const TcQOut q = qo ? *qo : TcQOut{nullptr, 0, 0};
     const bool big = p->BN == 256, fuse = partial != nullptr;
-#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g
-#define DX_TC_PICK(CLV, FUSEV, GENV) do { if (big) launch_gemm_t<256, CLV, FUSEV, GENV>(DX_TC_ARGS); \
-                                          else launch_gemm_t<128, CLV, FUSEV, GENV>(DX_TC_ARGS); } while (0)
-    if (gen) {
-        if (cl == 2) DX_TC_PICK(2, false, true); else DX_TC_PICK(1, false, true);
+#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g, q
+#define DX_TC_PICK(CLV, MODEV, GENV) do { if (big) launch_gemm_t<256, CLV, MODEV, GENV>(DX_TC_ARGS); \
+                                          else launch_gemm_t<128, CLV, MODEV, GENV>(DX_TC_ARGS); } while (0)
+    if (qo) {
+        if (cl == 2) launch_gemm_t<128, 2, 2, false>(DX_TC_ARGS); else launch_gemm_t<128, 1, 2, false>(DX_TC_ARGS);
+    } else if (gen) {
+        if (cl == 2) DX_TC_PICK(2, 0, true); else DX_TC_PICK(1, 0, true);
     } else if (cl == 4) {
-        if (fuse) launch_gemm_t<256, 4, true, false>(DX_TC_ARGS); else launch_gemm_t<256, 4, false, false>(DX_TC_ARGS);
+        if (fuse) launch_gemm_t<256, 4, 1, false>(DX_TC_ARGS); else launch_gemm_t<256, 4, 0, false>(DX_TC_ARGS);
     } else if (cl == 2) {
-        if (fuse) DX_TC_PICK(2, true, false); else DX_TC_PICK(2, false, false);
+        if (fuse) DX_TC_PICK(2, 1, false); else DX_TC_PICK(2, 0, false);
     } else {
-        if (fuse) DX_TC_PICK(1, true, false); else DX_TC_PICK(1, false, false);
+        if (fuse) DX_TC_PICK(1, 1, false); else DX_TC_PICK(1, 0, false);
     }
 #undef DX_TC_PICK
 #undef DX_TC_ARGS
@@ -1047,6 +1091,10 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     if (fuse) {
         const int blocks = (int)min((long long)dx_div_up(max_rows, 256), (long long)148 * 8);
         k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, (const float*)mb.xb[ix], mb.cap, P, out_h, out_q, absolute);
+    } else if (p->q_out && out_q) {
+        // multi-output layer as one more GEMM (128-wide n-tile of zero-padded weight rows), fp32 q-values from the epilogue
+        TcQOut qo{out_h, net.out_dim, absolute};
+        launch_gemm(s, p, p->CL_in, p->a_x[ix], p->b_out, ctl, 0, Hp, 128, net.bout_pad, -1, iz, 1, nullptr, out_q, 0, nullptr, &qo);
     } else {
         const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
         const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);

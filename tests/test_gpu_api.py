@@ -203,6 +203,28 @@ def test_bf16_kernel_variants_agree(switch, monkeypatch):
     np.testing.assert_allclose(out, ref, rtol=0, atol=0.01)
 
 
+@pytest.mark.parametrize("switch", [{}, {"DXB200_QOUT": "0"}, {"DXB200_GEMM_CLUSTER": "1"}])
+def test_bf16_q_output_layer_variants_agree(switch, monkeypatch):
+    """Q* network (out_dim = 12): the output layer as one more tensor-core GEMM with fp32 q-values written by the
+    epilogue, or the warp-per-state kernel -- both within the bf16 tolerance of the fp32 torch reference, and
+    node.heuristic = min_a q (deepxube/base/pathfinding.py:722-744)."""
+    from deepxube_b200 import _lib as L
+    from oracle.nnet_torch import random_state_dict, resnet_fc_forward
+    for k, v in switch.items():
+        monkeypatch.setenv(k, v)
+    rng = np.random.default_rng(6)
+    st = rng.integers(0, 6, size=(3000, 54), dtype=np.uint8)
+    sd = random_state_dict(324, 1000, 4, 12, True, seed=4, randomize_bn=True)
+    ref = np.maximum(np.asarray(resnet_fc_forward(sd, st.astype(np.int64), 6)), 0)
+    eng = L.Engine("cube3", 0, "graph_q", L.DX_HEUR_NET_BF16, max_instances=4, max_pop_total=4096, max_nodes=8192)
+    blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    eng.load_weights(54, 6, 1000, 4, 12, True, blob)
+    out = eng.heur_eval(st, None, 12)
+    eng.close()
+    assert out.shape == (3000, 12)
+    np.testing.assert_allclose(out, ref, rtol=0, atol=0.01)
+
+
 def test_bf16_search_deviation_is_reported():
     """bf16 heuristics cannot promise identical node counts: solutions must stay valid and the
     deviation of cost / nodes from the fp32 KAT is bounded and printed."""

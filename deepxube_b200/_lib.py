@@ -95,6 +95,10 @@ SIGNATURES = {
     "dx_hda_absorb": (C.c_int, [_engp, C.c_void_p, C.c_int64, C.POINTER(dx_hda_local)]),
     "dx_hda_finish": (C.c_int, [_engp, C.c_int64, C.c_double, C.c_double, C.c_int64, _i32p]),
     "dx_hda_node": (C.c_int, [_engp, C.c_int64, _u8p, C.POINTER(C.c_uint32), _i32p, _f32p]),
+    "dx_engine_set_stream": (C.c_int, [_engp, C.c_void_p]),
+    "dx_hda_send": (C.c_int, [_engp, C.c_void_p, C.c_int64]),
+    "dx_hda_receive": (C.c_int, [_engp, C.c_void_p, C.c_int64, C.c_void_p]),
+    "dx_hda_reduce": (C.c_int, [_engp, C.c_void_p, C.c_void_p]),
 }
 
 _lib = None
@@ -317,6 +321,19 @@ class Engine:
         fin = C.c_int32()
         check(self._lib.dx_hda_finish(self._h, k_total, f_first_min, ub_min, children_total, C.byref(fin)))
         return bool(fin.value)
+
+    def set_stream(self, cuda_stream: int) -> None:
+        """Run every launch of this engine on the caller's CUDA stream (0 / None: back to the engine's own stream)."""
+        check(self._lib.dx_engine_set_stream(self._h, C.c_void_p(cuda_stream or None)))
+
+    def hda_send(self, send_ptr: int, seg_records: int) -> None:
+        check(self._lib.dx_hda_send(self._h, C.c_void_p(send_ptr), seg_records))
+
+    def hda_receive(self, recv_ptr: int, seg_records: int, local_ptr: int) -> None:
+        check(self._lib.dx_hda_receive(self._h, C.c_void_p(recv_ptr), seg_records, C.c_void_p(local_ptr)))
+
+    def hda_reduce(self, all_ptr: int, summary_ptr: int) -> None:
+        check(self._lib.dx_hda_reduce(self._h, C.c_void_p(all_ptr), C.c_void_p(summary_ptr)))
 
     def hda_node(self, local_id: int):
         """-> (state [S], parent global id or None for the root, action, g)"""

@@ -18,6 +18,7 @@
 #define DX_DEVERR_NODES 1u
 #define DX_DEVERR_OPEN 2u
 #define DX_DEVERR_POP 4u
+#define DX_DEVERR_HDA 8u      // HDA*: an exchange segment / the receive capacity overflowed
 
 void dx_set_error(const std::string& msg);
 
@@ -236,6 +237,15 @@ int dx_launch_hda_finish(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const u
                          int A, unsigned long long k_total, unsigned long long f_first_min_bits, uint32_t ub_g_bits, int has_ub,
                          unsigned long long gen_add);
 int dx_launch_hda_drop_root(cudaStream_t s, Ctl* ctl, uint32_t* pop_off);
+int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, const uint8_t* child_state,
+                       const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world, uint32_t* counts, uint8_t* send,
+                       uint32_t seg_records, uint32_t* aux, int max_children);
+int dx_launch_hda_recv(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* recv, uint32_t world, uint32_t seg_records,
+                       uint32_t max_children, uint32_t* src_off, uint8_t* child_state, float* child_g, uint32_t* child_parent,
+                       uint8_t* child_action);
+int dx_launch_hda_locals(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const uint32_t* aux, double* loc);
+int dx_launch_hda_reduce(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
+                         int A, int world, const double* all, double* summary);
 uint32_t dx_hda_owner_host(const uint8_t* row, int SP, uint32_t world);
 int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
                         const uint32_t* new_inst, const SortBufs& sb, int max_n);

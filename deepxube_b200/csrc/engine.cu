@@ -190,6 +190,8 @@ struct dx_engine {
     // HDA* mode (hash-distributed single search)
     int hda_rank = 0, hda_world = 0;
     uint32_t* hda_counts = nullptr; uint32_t* child_parent = nullptr; uint8_t* child_action = nullptr;
+    uint32_t* hda_src_off = nullptr; uint32_t* hda_aux = nullptr;     // device-resident exchange: per-source offsets, children sent
+    cudaStream_t own_stream = nullptr;                                 // the stream the engine created (e->stream may be a caller's)
     int64_t hda_children_sent = 0;
     unsigned long long* open_key[2] = {nullptr, nullptr}; uint32_t* open_val[2] = {nullptr, nullptr};
     uint32_t* open_off[2] = {nullptr, nullptr};
@@ -316,6 +318,7 @@ static int sync_ctl(dx_engine* e) {
         if (e->h_ctl->error & DX_DEVERR_NODES) m += " max_nodes";
         if (e->h_ctl->error & DX_DEVERR_OPEN) m += " max_open";
         if (e->h_ctl->error & DX_DEVERR_POP) m += " max_pop_total";
+        if (e->h_ctl->error & DX_DEVERR_HDA) m += " HDA* exchange segment / receive capacity";
         DX_FAIL(DX_ERR_CAPACITY, m);
     }
     return DX_OK;
@@ -391,6 +394,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
 
 #define A_(ptr, count) do { int _r = e->alloc(&(ptr), (count)); if (_r < 0) { dx_engine_destroy(e); return _r; } } while (0)
     if (cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) != cudaSuccess) { delete e; DX_FAIL(DX_ERR_CUDA, "stream create failed"); }
+    e->own_stream = e->stream;
     if (cudaMallocHost((void**)&e->h_ctl, sizeof(Ctl)) != cudaSuccess) { delete e; DX_FAIL(DX_ERR_CUDA, "pinned alloc failed"); }
     A_(e->d_ctl, 1);
     A_(e->d_table, std::max<size_t>(e->table_h.size(), 16));
@@ -439,7 +443,7 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
     }
     for (void* p : e->allocs) cudaFree(p);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
-    if (e->stream) cudaStreamDestroy(e->stream);
+    if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
     return DX_OK;
 }
@@ -1312,6 +1316,9 @@ extern "C" int dx_hda_config(dx_engine* e, int32_t rank, int32_t world) {
     e->hda_world = world;
     if (!e->hda_counts) {
         DX_TRY(e->alloc(&e->hda_counts, 16));
+        DX_TRY(e->alloc(&e->hda_src_off, 32));
+        DX_TRY(e->alloc(&e->hda_aux, 4));
+        DX_CUDA(cudaMemset(e->hda_aux, 0, 4 * sizeof(uint32_t)));
         DX_TRY(e->alloc(&e->child_parent, (size_t)e->max_children + 1));
         DX_TRY(e->alloc(&e->child_action, (size_t)e->max_children + 1));
     }
@@ -1443,6 +1450,74 @@ extern "C" int dx_hda_finish(dx_engine* e, int64_t k_total, double f_first_min, 
     e->parity = q;
     DX_TRY(sync_ctl(e));
     if (finished) *finished = e->h_ctl->n_unfinished == 0 ? 1 : 0;
+    return DX_OK;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Device-resident HDA* iteration: send -> (all-to-all, equal splits) -> receive -> (all-gather of 5 doubles) -> reduce.
+// Nothing here synchronises with the host; the caller orders its collectives on the engine's stream
+// (dx_engine_set_stream) and polls summary_dev when it wants to know whether the search has finished.
+extern "C" int dx_engine_set_stream(dx_engine* e, void* cuda_stream) {
+    if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    e->stream = cuda_stream ? (cudaStream_t)cuda_stream : e->own_stream;
+    return DX_OK;
+}
+
+extern "C" int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records) {
+    if (!e || !send_dev || seg_records < 1 || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int p = e->parity;
+    DX_CUDA(cudaMemsetAsync(e->hda_counts, 0, 16 * sizeof(uint32_t), s));
+    e->launches += dx_launch_expand(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
+                                    e->pop_off[p], e->child_state, e->child_g, e->pop_solved, e->max_pop);
+    e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
+                                          e->pop_solved, e->max_pop);
+    e->launches += dx_launch_hda_send(s, e->dom, e->d_ctl, e->sort, e->scan, e->child_state, e->child_g, e->popped[p],
+                                      (uint32_t)e->hda_rank, (uint32_t)e->hda_world, e->hda_counts, (uint8_t*)send_dev,
+                                      (uint32_t)seg_records, e->hda_aux, e->max_children);
+    return DX_OK;
+}
+
+extern "C" int dx_hda_receive(dx_engine* e, const void* recv_dev, int64_t seg_records, double* local_dev) {
+    if (!e || !recv_dev || !local_dev || seg_records < 1 || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    cudaStream_t s = e->stream;
+    const int p = e->parity, q = p ^ 1;
+    e->launches += dx_launch_hda_recv(s, e->dom, e->d_ctl, (const uint8_t*)recv_dev, (uint32_t)e->hda_world, (uint32_t)seg_records,
+                                      (uint32_t)e->max_children, e->hda_src_off, e->child_state, e->child_g, e->child_parent,
+                                      e->child_action);
+    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
+                                           e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                           e->max_children, e->A);
+    e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
+                                        e->max_children, e->scan);
+    k_after_scan_v<<<1, 1, 0, s>>>(e->d_ctl, e->max_nodes);
+    e->launches += 1;
+    e->launches += dx_launch_scatter_kept_hda(s, e->dom, e->closed, e->d_ctl, e->child_state, e->child_g, e->child_slot,
+                                              e->child_flags, e->child_prefix, e->child_parent, e->child_action, e->node_state,
+                                              e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children);
+    DX_TRY(launch_heur_nodes(e, e->max_children));
+    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open, 1);
+    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles);
+    e->launches += dx_launch_hda_locals(s, e->d_ctl, e->ia, e->hda_aux, local_dev);
+    return DX_OK;
+}
+
+extern "C" int dx_hda_reduce(dx_engine* e, const double* all_dev, double* summary_dev) {
+    if (!e || !all_dev || !summary_dev || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    const int p = e->parity, q = p ^ 1;
+    e->launches += dx_launch_hda_reduce(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, e->hda_world, all_dev,
+                                        summary_dev);
+    e->parity = q;
     return DX_OK;
 }
 

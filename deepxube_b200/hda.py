@@ -12,6 +12,15 @@ Two transports with identical engine calls:
                        `all_gather` the per-rank scalars
   * `dist` is None     W ranks emulated in one process on one GPU (the engines run one after the other, so
                        nothing ever waits on a concurrently running kernel); used by the single-GPU tests
+
+Two drivers of the iteration:
+  * device-resident (default): the engine kernels and the collectives are ordered on ONE CUDA stream and nothing inside
+    an iteration synchronises with the host -- fixed-size per-destination segments carry their record count in a
+    header, so the all-to-all needs no counts on the host; per-rank scalars are all-gathered as a device tensor and
+    reduced by a kernel on every rank; the host reads one 64-byte summary per iteration
+  * host-driven (`device_resident=False`): variable-size all-to-all with the counts exchanged through the host
+    (the first implementation, kept for A/B measurements; ~8 device-to-host reads per iteration)
+Both produce the same received-children order (source-major, sender's order), hence identical searches.
 """
 from typing import Any, List, Optional
 
@@ -25,8 +34,9 @@ from deepxube_b200.base.pathfind_fns import load_nnet_into_engine
 class HdaSearch:
     def __init__(self, domain_name: str, dim: int, world: int, batch_size: int, weight: float, nnet: Any = None,
                  precision: str = "fp32", max_nodes_per_rank: int = 1 << 22, dist: Optional[Any] = None,
-                 device: Optional[int] = None, capacity_slack: float = 2.0):
+                 device: Optional[int] = None, capacity_slack: float = 2.0, device_resident: bool = True):
         self.dist = dist
+        self.device_resident = device_resident
         self.world = world
         self.weight = weight
         self.batch_local = max(1, -(-batch_size // world))
@@ -57,6 +67,20 @@ class HdaSearch:
         self.num_nodes_generated = 0
         self.goal = None          # (ub, rank, local id)
         self.finished = False
+        if device_resident:
+            # expected records per destination = batch_local * actions / world; the slack covers the hash imbalance
+            self.seg_records = int(np.ceil(self.batch_local * self.num_actions / world * max(capacity_slack, 1.0) * 1.25)) + 64
+            self.seg_bytes = 16 + self.seg_records * self.rec
+            self.stream = torch.cuda.Stream(device=self.tdev)
+            with torch.cuda.stream(self.stream):
+                self.send = [torch.zeros(world * self.seg_bytes, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
+                self.recv = [torch.zeros(world * self.seg_bytes, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
+                self.loc = [torch.zeros(5, dtype=torch.float64, device=self.tdev) for _ in self.local_ranks]
+                self.loc_all = torch.zeros(world * 5, dtype=torch.float64, device=self.tdev)
+                self.summary = [torch.zeros(8, dtype=torch.float64, device=self.tdev) for _ in self.local_ranks]
+            self.stream.synchronize()
+            for eng in self.engines:
+                eng.set_stream(self.stream.cuda_stream)
 
     # ---- transports --------------------------------------------------------------------------------------
     def _exchange(self, counts: List[np.ndarray]) -> List[int]:
@@ -109,7 +133,38 @@ class HdaSearch:
             eng.hda_add_instance(state, goal, self.batch_local, self.weight)
         self.itr, self.num_nodes_generated, self.goal, self.finished = 0, 0, None, False
 
+    def _step_device(self) -> bool:
+        """One iteration with every launch and collective on self.stream; the only host read is the summary."""
+        W, seg = self.world, self.seg_bytes
+        with torch.cuda.stream(self.stream):
+            for i, eng in enumerate(self.engines):
+                eng.hda_send(self.send[i].data_ptr(), self.seg_records)
+            if self.dist is not None:
+                self.dist.all_to_all_single(self.recv[0], self.send[0])                 # equal splits of seg_bytes
+            else:
+                for di in range(W):
+                    for si in range(W):
+                        self.recv[di][si * seg:(si + 1) * seg].copy_(self.send[si][di * seg:(di + 1) * seg], non_blocking=True)
+            for i, eng in enumerate(self.engines):
+                eng.hda_receive(self.recv[i].data_ptr(), self.seg_records, self.loc[i].data_ptr())
+            if self.dist is not None:
+                self.dist.all_gather_into_tensor(self.loc_all, self.loc[0])
+            else:
+                torch.cat(self.loc, out=self.loc_all)
+            for i, eng in enumerate(self.engines):
+                eng.hda_reduce(self.loc_all.data_ptr(), self.summary[i].data_ptr())
+            sm = self.summary[0].cpu().tolist()                                          # the iteration's one synchronisation
+        if sm[6] != 0:
+            raise _lib.DxError(f"HDA*: device capacity exceeded (flags {int(sm[6])}): raise capacity_slack / max_nodes_per_rank")
+        self.finished = sm[0] != 0
+        self.itr = int(sm[1])
+        self.num_nodes_generated = int(sm[2])
+        self.goal = (sm[3], int(sm[4]), int(sm[5])) if sm[4] >= 0 else None
+        return self.finished
+
     def step(self) -> bool:
+        if self.device_resident:
+            return self._step_device()
         counts = [eng.hda_expand(self.send[i].data_ptr(), self.send[i].numel(), self.world) for i, eng in enumerate(self.engines)]
         n_recv = self._exchange(counts)
         locs = [eng.hda_absorb(self.recv[i].data_ptr(), n_recv[i]) for i, eng in enumerate(self.engines)]

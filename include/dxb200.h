@@ -217,6 +217,21 @@ int dx_hda_expand(dx_engine* e, void* send_dev, int64_t send_cap_bytes, int64_t*
 int dx_hda_absorb(dx_engine* e, const void* recv_dev, int64_t n_records, dx_hda_local* out);
 int dx_hda_finish(dx_engine* e, int64_t k_total, double f_first_min, double ub_min, int64_t children_total, int32_t* finished);
 int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint32_t* parent_global, int32_t* action, float* g);
+/* Device-resident form of the same iteration -- no host synchronisation inside, every launch on the engine's stream
+ * (dx_engine_set_stream lets the caller's collectives share it):
+ *   dx_hda_send(e, send_dev, seg_records)        expand the local popped list, group the children by owner and write W fixed-size
+ *                                                segments [u32 count, 12 B pad, seg_records records] (segment d is for rank d)
+ *   -- all-to-all of the segments with EQUAL splits (16 + seg_records * record_bytes each) --
+ *   dx_hda_receive(e, recv_dev, seg_records, local_dev)   unpack the W received segments (source-major), CLOSED filter, heuristic,
+ *                                                push / pop; local_dev[5] (device doubles) = {k_popped, f_first, ub, goal_local, children}
+ *   -- all-gather of local_dev over the ranks --
+ *   dx_hda_reduce(e, all_dev, summary_dev)       lb / ub / finished() from all_dev[5 * W] on every rank; summary_dev[8] (device doubles)
+ *                                                = {finished, iterations, nodes generated, ub, goal rank, goal local id, device error flags, 0}
+ * A segment or receive-capacity overflow raises the device error flag (reported in the summary and by the next synchronising call). */
+int dx_engine_set_stream(dx_engine* e, void* cuda_stream);   /* NULL: back to the engine's own stream */
+int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records);
+int dx_hda_receive(dx_engine* e, const void* recv_dev, int64_t seg_records, double* local_dev);
+int dx_hda_reduce(dx_engine* e, const double* all_dev, double* summary_dev);
 
 #ifdef __cplusplus
 }

@@ -61,6 +61,23 @@ def test_zero_heuristic_is_optimal_and_deterministic(world):
     assert _valid(dom, st, goal, runs[0]["actions"])
 
 
+@pytest.mark.parametrize("world", [1, 4])
+def test_device_resident_driver_equals_host_driven(world):
+    """The device-resident iteration (fixed-size segments with count headers, scalars reduced by a kernel, one host
+    read per iteration) and the host-driven one (variable-size exchange, counts through the host) are the same search."""
+    from deepxube_b200.hda import HdaSearch
+    dom = OracleDomain("cube3")
+    goal = dom.canonical_goal()
+    st = _scramble(dom, 30, 3)
+    out = []
+    for dev in (True, False):
+        h = HdaSearch("cube3", 0, world, batch_size=400, weight=0.8, max_nodes_per_rank=400000, device_resident=dev)
+        out.append(h.solve(st, goal, max_itrs=6))
+        h.close()
+    assert out[0] == out[1]
+    assert out[0]["iterations"] == 6 and out[0]["num_nodes_generated"] > 10000
+
+
 def test_trained_net_hard_instance_world4():
     """Trained tutorial network, fp32: the distributed search must solve the KAT instance with a valid path;
     its cost / nodes generated are reported next to the single-GPU KAT values."""

@@ -50,18 +50,20 @@ if args.bench:
     for a in rng.integers(0, 12, size=2000):
         st = st[cube3_perm_table()[a]]
     B = args.batch_per_gpu * world
-    h = HdaSearch("cube3", 0, world, B, 0.6, nnet=pfns.heurv.nnet, precision="bf16",
-                  max_nodes_per_rank=int(args.batch_per_gpu * 12 * (args.iters + 2) * 1.5), dist=dist, device=local)
-    for rep in range(2):
-        dist.barrier(); torch.cuda.synchronize()
-        t0 = time.perf_counter()
-        r = h.solve(st, goal, max_itrs=args.iters)
-        torch.cuda.synchronize(); dist.barrier()
-        dt = time.perf_counter() - t0
-        if rank == 0:
-            print(json.dumps({"config": "C5 HDA* cube3", "n_gpus": world, "global_batch": B, "iters": r["iterations"],
-                              "nodes_generated": r["num_nodes_generated"], "seconds": dt, "nodes_per_sec": r["num_nodes_generated"] / dt,
-                              "rep": rep}))
-    h.close()
+    for dev_res in (True, False):
+        h = HdaSearch("cube3", 0, world, B, 0.6, nnet=pfns.heurv.nnet, precision="bf16",
+                      max_nodes_per_rank=int(args.batch_per_gpu * 12 * (args.iters + 2) * 1.5), dist=dist, device=local,
+                      device_resident=dev_res)
+        for rep in range(3):
+            dist.barrier(); torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            r = h.solve(st, goal, max_itrs=args.iters)
+            torch.cuda.synchronize(); dist.barrier()
+            dt = time.perf_counter() - t0
+            if rank == 0:
+                print(json.dumps({"config": "C5 HDA* cube3", "driver": "device-resident" if dev_res else "host-driven", "n_gpus": world,
+                                  "global_batch": B, "iters": r["iterations"], "nodes_generated": r["num_nodes_generated"], "seconds": dt,
+                                  "nodes_per_sec": r["num_nodes_generated"] / dt, "rep": rep}))
+        h.close()
 dist.barrier()
 dist.destroy_process_group()

@@ -97,6 +97,7 @@ SIGNATURES = {
     "dx_hda_node": (C.c_int, [_engp, C.c_int64, _u8p, C.POINTER(C.c_uint32), _i32p, _f32p]),
     "dx_engine_set_stream": (C.c_int, [_engp, C.c_void_p]),
     "dx_hda_send": (C.c_int, [_engp, C.c_void_p, C.c_int64]),
+    "dx_hda_send_peers": (C.c_int, [_engp, C.POINTER(C.c_uint64), C.c_int64]),
     "dx_hda_receive": (C.c_int, [_engp, C.c_void_p, C.c_int64, C.c_void_p]),
     "dx_hda_reduce": (C.c_int, [_engp, C.c_void_p, C.c_void_p]),
 }
@@ -328,6 +329,10 @@ class Engine:
 
     def hda_send(self, send_ptr: int, seg_records: int) -> None:
         check(self._lib.dx_hda_send(self._h, C.c_void_p(send_ptr), seg_records))
+
+    def hda_send_peers(self, peer_recv_ptrs, seg_records: int) -> None:
+        arr = (C.c_uint64 * len(peer_recv_ptrs))(*[int(x) for x in peer_recv_ptrs])
+        check(self._lib.dx_hda_send_peers(self._h, arr, seg_records))
 
     def hda_receive(self, recv_ptr: int, seg_records: int, local_ptr: int) -> None:
         check(self._lib.dx_hda_receive(self._h, C.c_void_p(recv_ptr), seg_records, C.c_void_p(local_ptr)))

@@ -237,8 +237,9 @@ int dx_launch_hda_finish(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const u
                          int A, unsigned long long k_total, unsigned long long f_first_min_bits, uint32_t ub_g_bits, int has_ub,
                          unsigned long long gen_add);
 int dx_launch_hda_drop_root(cudaStream_t s, Ctl* ctl, uint32_t* pop_off);
+struct HdaDst { uint8_t* seg[16]; };     // destination of the exchange segment for each rank (local send buffer or peer memory)
 int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, const uint8_t* child_state,
-                       const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world, uint32_t* counts, uint8_t* send,
+                       const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world, uint32_t* counts, const HdaDst& dst,
                        uint32_t seg_records, uint32_t* aux, int max_children);
 int dx_launch_hda_recv(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* recv, uint32_t world, uint32_t seg_records,
                        uint32_t max_children, uint32_t* src_off, uint8_t* child_state, float* child_g, uint32_t* child_parent,

@@ -1465,8 +1465,31 @@ extern "C" int dx_engine_set_stream(dx_engine* e, void* cuda_stream) {
     return DX_OK;
 }
 
+static int hda_send_impl(dx_engine* e, const HdaDst& dst, int64_t seg_records);
+
 extern "C" int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records) {
     if (!e || !send_dev || seg_records < 1 || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    HdaDst dst = {};
+    const size_t seg_bytes = 16 + (size_t)seg_records * (size_t)(e->SP + 16);
+    for (int r = 0; r < e->hda_world; ++r) dst.seg[r] = (uint8_t*)send_dev + (size_t)r * seg_bytes;
+    return hda_send_impl(e, dst, seg_records);
+}
+
+// Peer-memory exchange: peer_recv[r] = device address (valid in THIS process: symmetric / IPC-mapped memory) of rank r's
+// receive buffer; the pack kernel stores this rank's segment for r directly into slot hda_rank of that buffer over NVLink.
+// The caller places a cross-rank barrier between this call and dx_hda_receive.
+extern "C" int dx_hda_send_peers(dx_engine* e, const uint64_t* peer_recv, int64_t seg_records) {
+    if (!e || !peer_recv || seg_records < 1 || e->hda_world < 1) DX_FAIL(DX_ERR_ARG, "bad argument / HDA* mode not configured");
+    HdaDst dst = {};
+    const size_t seg_bytes = 16 + (size_t)seg_records * (size_t)(e->SP + 16);
+    for (int r = 0; r < e->hda_world; ++r) {
+        if (!peer_recv[r]) DX_FAIL(DX_ERR_ARG, "null peer receive buffer");
+        dst.seg[r] = (uint8_t*)(uintptr_t)peer_recv[r] + (size_t)e->hda_rank * seg_bytes;
+    }
+    return hda_send_impl(e, dst, seg_records);
+}
+
+static int hda_send_impl(dx_engine* e, const HdaDst& dst, int64_t seg_records) {
     DX_CUDA(cudaSetDevice(e->cfg.device));
     cudaStream_t s = e->stream;
     const int p = e->parity;
@@ -1476,7 +1499,7 @@ extern "C" int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records) {
     e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
                                           e->pop_solved, e->max_pop);
     e->launches += dx_launch_hda_send(s, e->dom, e->d_ctl, e->sort, e->scan, e->child_state, e->child_g, e->popped[p],
-                                      (uint32_t)e->hda_rank, (uint32_t)e->hda_world, e->hda_counts, (uint8_t*)send_dev,
+                                      (uint32_t)e->hda_rank, (uint32_t)e->hda_world, e->hda_counts, dst,
                                       (uint32_t)seg_records, e->hda_aux, e->max_children);
     return DX_OK;
 }

@@ -137,16 +137,17 @@ __global__ void k_hda_finish(Ctl* __restrict__ ctl, InstArrays ia, const uint32_
 // Received children are numbered source-major, in the sender's order (the sender's stable sort by owner keeps its
 // child order), exactly the order the variable-size all-to-all of the host-driven version produced.
 
-// after the stable sort by owner: records -> segments; aux[0] = children this rank generated
+// after the stable sort by owner: records -> segments; aux[0] = children this rank generated.
+// dst.seg[o] is where the segment for rank o goes: a slice of the local send buffer (NCCL all-to-all follows), or --
+// peer-memory exchange -- slot `rank` of rank o's receive buffer, written straight over NVLink by this kernel.
 __global__ void k_hda_pack_seg(DomainDev d, Ctl* __restrict__ ctl, SortBufs sb, const uint8_t* __restrict__ child_state,
                                const float* __restrict__ child_g, const uint32_t* __restrict__ popped, uint32_t rank, uint32_t world,
-                               const uint32_t* __restrict__ counts, uint8_t* __restrict__ send, uint32_t seg_records,
+                               const uint32_t* __restrict__ counts, HdaDst dst, uint32_t seg_records,
                                uint32_t* __restrict__ aux) {
     __shared__ uint32_t s_pref[17];
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;
     const int words = d.SP / 4, rw = words + 4;
-    const size_t seg_bytes = 16 + (size_t)seg_records * (size_t)(rw * 4);
     if (threadIdx.x == 0) {
         uint32_t acc = 0;
         for (uint32_t o = 0; o < world; ++o) { s_pref[o] = acc; acc += counts[o]; }
@@ -156,7 +157,7 @@ __global__ void k_hda_pack_seg(DomainDev d, Ctl* __restrict__ ctl, SortBufs sb, 
     if (blockIdx.x == 0 && threadIdx.x < world) {
         uint32_t c = counts[threadIdx.x];
         if (c > seg_records) { atomicOr(&ctl->error, DX_DEVERR_HDA); c = seg_records; }
-        *reinterpret_cast<uint4*>(send + (size_t)threadIdx.x * seg_bytes) = make_uint4(c, 0u, 0u, 0u);
+        *reinterpret_cast<uint4*>(dst.seg[threadIdx.x]) = make_uint4(c, 0u, 0u, 0u);
     }
     if (blockIdx.x == 0 && threadIdx.x == 0) aux[0] = n;
     const unsigned long long* __restrict__ keys = sb.key[ctl->sort_final];
@@ -174,7 +175,7 @@ __global__ void k_hda_pack_seg(DomainDev d, Ctl* __restrict__ ctl, SortBufs sb, 
         else if (w == (uint32_t)words + 1) v = (rank << 28) | popped[c / d.A];
         else if (w == (uint32_t)words + 2) v = c % d.A;
         else v = 0u;
-        reinterpret_cast<uint32_t*>(send + (size_t)o * seg_bytes + 16 + (size_t)pos * (rw * 4))[w] = v;
+        reinterpret_cast<uint32_t*>(dst.seg[o] + 16 + (size_t)pos * (rw * 4))[w] = v;
     }
 }
 
@@ -321,14 +322,14 @@ int dx_launch_hda_finish(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const u
 }
 
 int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, const uint8_t* child_state,
-                       const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world, uint32_t* counts, uint8_t* send,
+                       const float* child_g, const uint32_t* popped, uint32_t rank, uint32_t world, uint32_t* counts, const HdaDst& dst,
                        uint32_t seg_records, uint32_t* aux, int max_children) {
     int launches = 0;
     const int blocks = min(dx_div_up(max_children, 256), 148 * 8);
     k_hda_owner_keys<<<blocks, 256, 0, s>>>(d, ctl, child_state, child_g, sb, world, counts);
     launches += 1 + dx_launch_sort(s, ctl, sb, t, max_children);
     const int pblocks = (int)min((long long)dx_div_up((long long)max_children * (d.SP / 4 + 4), 256), (long long)148 * 16);
-    k_hda_pack_seg<<<pblocks, 256, 0, s>>>(d, ctl, sb, child_state, child_g, popped, rank, world, counts, send, seg_records, aux);
+    k_hda_pack_seg<<<pblocks, 256, 0, s>>>(d, ctl, sb, child_state, child_g, popped, rank, world, counts, dst, seg_records, aux);
     return launches + 1;
 }
 

@@ -16,8 +16,10 @@ Two transports with identical engine calls:
 Two drivers of the iteration:
   * device-resident (default): the engine kernels and the collectives are ordered on ONE CUDA stream and nothing inside
     an iteration synchronises with the host -- fixed-size per-destination segments carry their record count in a
-    header, so the all-to-all needs no counts on the host; per-rank scalars are all-gathered as a device tensor and
-    reduced by a kernel on every rank; the host reads one 64-byte summary per iteration
+    header, so the exchange needs no counts on the host; with `exchange="p2p"` (default) the pack kernel itself stores
+    the segments into the owners' receive buffers over NVLink peer memory (symmetric memory) and one device-side
+    barrier follows, with `exchange="nccl"` an equal-split all-to-all moves them; per-rank scalars are all-gathered as
+    a device tensor and reduced by a kernel on every rank; the host reads one 64-byte summary per iteration
   * host-driven (`device_resident=False`): variable-size all-to-all with the counts exchanged through the host
     (the first implementation, kept for A/B measurements; ~8 device-to-host reads per iteration)
 Both produce the same received-children order (source-major, sender's order), hence identical searches.
@@ -34,7 +36,8 @@ from deepxube_b200.base.pathfind_fns import load_nnet_into_engine
 class HdaSearch:
     def __init__(self, domain_name: str, dim: int, world: int, batch_size: int, weight: float, nnet: Any = None,
                  precision: str = "fp32", max_nodes_per_rank: int = 1 << 22, dist: Optional[Any] = None,
-                 device: Optional[int] = None, capacity_slack: float = 2.0, device_resident: bool = True):
+                 device: Optional[int] = None, capacity_slack: float = 2.0, device_resident: bool = True,
+                 exchange: str = "p2p"):
         self.dist = dist
         self.device_resident = device_resident
         self.world = world
@@ -81,6 +84,27 @@ class HdaSearch:
             self.stream.synchronize()
             for eng in self.engines:
                 eng.set_stream(self.stream.cuda_stream)
+            # Record exchange.  "p2p": the pack kernel stores every segment straight into the owner's receive buffer over
+            # peer memory (torch symmetric memory maps the W receive buffers into every process), followed by one
+            # symmetric-memory barrier -- no collective moves the records.  "nccl": pack locally, all_to_all_single.
+            self.exchange = exchange
+            self.symm = None
+            if exchange == "p2p":
+                if dist is None:
+                    self.peer_ptrs = [[self.recv[d].data_ptr() for d in range(world)] for _ in self.local_ranks]
+                else:
+                    try:
+                        import torch.distributed._symmetric_memory as symm_mem
+                        buf = symm_mem.empty(world * self.seg_bytes, dtype=torch.uint8, device=self.tdev)
+                        self.symm = symm_mem.rendezvous(buf, dist.group.WORLD)
+                        buf.zero_()
+                        self.recv = [buf]
+                        self.peer_ptrs = [[int(p) for p in self.symm.buffer_ptrs]]
+                        torch.cuda.synchronize(self.tdev)
+                        dist.barrier()
+                    except Exception as ex:  # noqa: BLE001  (no peer access on this machine: keep the NCCL exchange)
+                        print(f"HDA*: peer-memory exchange unavailable ({ex}); using the NCCL all-to-all", flush=True)
+                        self.exchange, self.symm = "nccl", None
 
     # ---- transports --------------------------------------------------------------------------------------
     def _exchange(self, counts: List[np.ndarray]) -> List[int]:
@@ -137,14 +161,20 @@ class HdaSearch:
         """One iteration with every launch and collective on self.stream; the only host read is the summary."""
         W, seg = self.world, self.seg_bytes
         with torch.cuda.stream(self.stream):
-            for i, eng in enumerate(self.engines):
-                eng.hda_send(self.send[i].data_ptr(), self.seg_records)
-            if self.dist is not None:
-                self.dist.all_to_all_single(self.recv[0], self.send[0])                 # equal splits of seg_bytes
+            if self.exchange == "p2p":
+                for i, eng in enumerate(self.engines):
+                    eng.hda_send_peers(self.peer_ptrs[i], self.seg_records)               # pack + store into the owners' buffers
+                if self.symm is not None:
+                    self.symm.barrier(channel=0)                                          # every rank's segments have landed
             else:
-                for di in range(W):
-                    for si in range(W):
-                        self.recv[di][si * seg:(si + 1) * seg].copy_(self.send[si][di * seg:(di + 1) * seg], non_blocking=True)
+                for i, eng in enumerate(self.engines):
+                    eng.hda_send(self.send[i].data_ptr(), self.seg_records)
+                if self.dist is not None:
+                    self.dist.all_to_all_single(self.recv[0], self.send[0])             # equal splits of seg_bytes
+                else:
+                    for di in range(W):
+                        for si in range(W):
+                            self.recv[di][si * seg:(si + 1) * seg].copy_(self.send[si][di * seg:(di + 1) * seg], non_blocking=True)
             for i, eng in enumerate(self.engines):
                 eng.hda_receive(self.recv[i].data_ptr(), self.seg_records, self.loc[i].data_ptr())
             if self.dist is not None:

@@ -230,6 +230,10 @@ int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint32_t* parent
  * A segment or receive-capacity overflow raises the device error flag (reported in the summary and by the next synchronising call). */
 int dx_engine_set_stream(dx_engine* e, void* cuda_stream);   /* NULL: back to the engine's own stream */
 int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records);
+/* Fused pack + exchange over peer memory: peer_recv[r] is rank r's receive buffer mapped into this process (symmetric /
+ * IPC memory); the pack kernel stores the segment for rank r into slot <this rank> of that buffer over NVLink, so no
+ * collective moves the records.  The caller puts a cross-rank barrier between this call and dx_hda_receive. */
+int dx_hda_send_peers(dx_engine* e, const uint64_t* peer_recv, int64_t seg_records);
 int dx_hda_receive(dx_engine* e, const void* recv_dev, int64_t seg_records, double* local_dev);
 int dx_hda_reduce(dx_engine* e, const double* all_dev, double* summary_dev);
 

@@ -70,11 +70,11 @@ def test_device_resident_driver_equals_host_driven(world):
     goal = dom.canonical_goal()
     st = _scramble(dom, 30, 3)
     out = []
-    for dev in (True, False):
-        h = HdaSearch("cube3", 0, world, batch_size=400, weight=0.8, max_nodes_per_rank=400000, device_resident=dev)
+    for dev, exch in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
+        h = HdaSearch("cube3", 0, world, batch_size=400, weight=0.8, max_nodes_per_rank=400000, device_resident=dev, exchange=exch)
         out.append(h.solve(st, goal, max_itrs=6))
         h.close()
-    assert out[0] == out[1]
+    assert out[0] == out[1] == out[2]
     assert out[0]["iterations"] == 6 and out[0]["num_nodes_generated"] > 10000
 
 

@@ -35,10 +35,10 @@ if args.check:
         e = HdaSearch("cube3", 0, world, 100, 0.1, nnet=pfns.heurv.nnet, precision="fp32", max_nodes_per_rank=1 << 20, device=local)
         emu = [e.solve(k["hard_states"][i], k["hard_goals"][i], max_itrs=3000) for i in (4, 8)]
         e.close()
-        print("NCCL    :", [(r["path_cost"], r["num_nodes_generated"], r["iterations"]) for r in res])
+        print("W ranks :", [(r["path_cost"], r["num_nodes_generated"], r["iterations"]) for r in res])
         print("emulated:", [(r["path_cost"], r["num_nodes_generated"], r["iterations"]) for r in emu])
-        assert res == emu, "NCCL transport and in-process emulation disagree"
-        print("HDA* check OK: NCCL == emulation")
+        assert res == emu, "distributed run and in-process emulation disagree"
+        print(f"HDA* check OK: {world} processes ({h.exchange} exchange) == emulation")
 
 if args.bench:
     pfns, _ = get_path_fns_nnet_par_dict(domain, name, ["heurv,resnet_fc.1000H_4B_bn"])
@@ -50,10 +50,10 @@ if args.bench:
     for a in rng.integers(0, 12, size=2000):
         st = st[cube3_perm_table()[a]]
     B = args.batch_per_gpu * world
-    for dev_res in (True, False):
+    for dev_res, exch in ((True, "p2p"), (True, "nccl"), (False, "nccl")):
         h = HdaSearch("cube3", 0, world, B, 0.6, nnet=pfns.heurv.nnet, precision="bf16",
                       max_nodes_per_rank=int(args.batch_per_gpu * 12 * (args.iters + 2) * 1.5), dist=dist, device=local,
-                      device_resident=dev_res)
+                      device_resident=dev_res, exchange=exch)
         for rep in range(3):
             dist.barrier(); torch.cuda.synchronize()
             t0 = time.perf_counter()
@@ -61,7 +61,7 @@ if args.bench:
             torch.cuda.synchronize(); dist.barrier()
             dt = time.perf_counter() - t0
             if rank == 0:
-                print(json.dumps({"config": "C5 HDA* cube3", "driver": "device-resident" if dev_res else "host-driven", "n_gpus": world,
+                print(json.dumps({"config": "C5 HDA* cube3", "driver": (f"device-resident/{h.exchange}" if dev_res else "host-driven"), "n_gpus": world,
                                   "global_batch": B, "iters": r["iterations"], "nodes_generated": r["num_nodes_generated"], "seconds": dt,
                                   "nodes_per_sec": r["num_nodes_generated"] / dt, "rep": rep}))
         h.close()

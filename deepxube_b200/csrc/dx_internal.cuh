@@ -253,7 +253,8 @@ int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, co
 int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
                           const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
                           const SortBufs& sb, int A, int max_pop);
-int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n);
+#define DX_SMALL_SORT 2048     // batches up to this many entries are sorted by one block (k_sort_small)
+int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n, bool small = false);
 int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,

@@ -220,6 +220,8 @@ struct dx_engine {
     std::vector<int> gev_stage[2];
     int cap_prof = -1;                 // parity whose profiling graph is being captured, else -1
     int graph_launches = 0;
+    long long sort_bound = 0;          // sum of batch_size * actions over the instances: no iteration pushes more entries
+    bool graph_small = false;          // whether the captured graphs use the single-block sort
     bool use_graphs = true;
     float last_run_ms = 0.f;
 
@@ -324,6 +326,22 @@ static int sync_ctl(dx_engine* e) {
     return DX_OK;
 }
 
+// single-block sort instead of the radix passes: only when the host can bound the pushed batch (never in HDA* mode,
+// where the received children are not bounded by the local batch)
+static bool small_sort(const dx_engine* e) {
+    return e->hda_world < 1 && e->sort_bound > 0 && e->sort_bound <= DX_SMALL_SORT;
+}
+
+static void drop_graphs(dx_engine* e) {
+    for (int k = 0; k < 2; ++k) {
+        if (e->graph_exec[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_exec[k] = nullptr; }
+        if (e->graph_prof_exec[k]) { cudaGraphExecDestroy(e->graph_prof_exec[k]); e->graph_prof_exec[k] = nullptr; }
+        for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
+        e->gev[k].clear();
+        e->gev_stage[k].clear();
+    }
+}
+
 static int ensure_stage(dx_engine* e, size_t bytes) {
     if (bytes <= e->stage_bytes) return DX_OK;
     void* q = nullptr;
@@ -346,6 +364,7 @@ static int reset_state(dx_engine* e) {
     e->n_inst = 0;
     e->parity = 0;
     e->pending = false;
+    e->sort_bound = 0;
     return DX_OK;      // stage timers are cumulative across resets; dx_set_profiling() clears them
 }
 
@@ -505,6 +524,7 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
         for (int b : hb) bsum += b;
         if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of batch sizes exceeds max_pop_total");
     }
+    e->sort_bound = bsum * e->A;             // no iteration can push more entries than every instance's full batch expanded
     const int SP = e->SP, S = e->S, I0 = e->n_inst, p = e->parity;
     std::vector<uint8_t> rows((size_t)n * SP, 0), grow((size_t)n * SP, 0);
     std::vector<int32_t> hb(n);
@@ -614,7 +634,7 @@ static int step_v_b(dx_engine* e) {
     e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
                                   e->open_off[q], e->A, 1, e->max_pop, e->max_open);
     e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort);
-    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     stage_end(e);
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
@@ -654,7 +674,7 @@ static int step_q_a(dx_engine* e) {
                                   e->open_off[q], 1, e->A, e->max_pop, e->max_open);
     e->launches += dx_launch_make_keys_q(s, e->d_ctl, e->ia, e->node_g, e->node_q, e->popped[p], e->popped_inst[p],
                                          e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop);
-    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort);
+    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     stage_end(e);
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
@@ -695,6 +715,7 @@ static int full_step(dx_engine* e) {
 }
 
 static int build_step_graphs(dx_engine* e, bool prof) {
+    e->graph_small = small_sort(e);
     const int p0 = e->parity;
     const long long l0 = e->launches;
     for (int k = 0; k < 2; ++k) {
@@ -730,6 +751,7 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
     const bool use_graph = e->use_graphs, prof = e->profiling != 0;
+    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && e->graph_small != small_sort(e)) drop_graphs(e);   // captured with the other sort
     if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
     if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level
         for (int k = 0; k < 2; ++k) {

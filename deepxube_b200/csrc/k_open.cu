@@ -317,7 +317,61 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
     }
 }
 
-int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n) {
+// Small batches (<= DX_SMALL_SORT entries, known on the host from the instances' batch sizes): the whole sort is ONE
+// block -- a bitonic network in shared memory on (instance, f-key, original position), the position making it the same
+// stable order as the radix sort -- instead of 2 + 3 launches per digit pass, which at these sizes are pure launch latency
+// (26 of the 40 launches of an iteration).  Output goes to buffer 1, like an odd number of radix passes.
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
+    __shared__ unsigned long long s_key[DX_SMALL_SORT];
+    __shared__ uint32_t s_inst[DX_SMALL_SORT];
+    __shared__ uint32_t s_idx[DX_SMALL_SORT];
+    if (ctl->error) return;
+    const uint32_t n = ctl->sort_n;
+    if (n > DX_SMALL_SORT) {                 // the host's bound was wrong: fail loudly instead of sorting a prefix
+        if (threadIdx.x == 0) atomicOr(&ctl->error, DX_DEVERR_POP);
+        return;
+    }
+    if (threadIdx.x == 0) ctl->sort_final = 1;
+    if (n == 0) return;
+    uint32_t m = 1;
+    while (m < n) m <<= 1;
+    for (uint32_t i = threadIdx.x; i < m; i += OPEN_THREADS) {
+        const bool in = i < n;
+        s_key[i] = in ? sb.key[0][i] : ~0ull;
+        s_inst[i] = in ? sb.inst[0][i] : 0xFFFFFFFFu;
+        s_idx[i] = i;
+    }
+    for (uint32_t k = 2; k <= m; k <<= 1)
+        for (uint32_t j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (uint32_t i = threadIdx.x; i < m; i += OPEN_THREADS) {
+                const uint32_t p = i ^ j;
+                if (p > i) {
+                    const unsigned long long ka = s_key[i], kb = s_key[p];
+                    const uint32_t ia = s_inst[i], ib = s_inst[p], xa = s_idx[i], xb = s_idx[p];
+                    const bool a_gt_b = ia != ib ? ia > ib : (ka != kb ? ka > kb : xa > xb);
+                    if (a_gt_b == ((i & k) == 0)) {
+                        s_key[i] = kb; s_key[p] = ka;
+                        s_inst[i] = ib; s_inst[p] = ia;
+                        s_idx[i] = xb; s_idx[p] = xa;
+                    }
+                }
+            }
+        }
+    __syncthreads();
+    for (uint32_t i = threadIdx.x; i < n; i += OPEN_THREADS) {
+        sb.key[1][i] = s_key[i];
+        sb.inst[1][i] = s_inst[i];
+        sb.val[1][i] = sb.val[0][s_idx[i]];
+    }
+}
+
+int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n, bool small) {
+    if (small) {
+        k_sort_small<<<1, OPEN_THREADS, 0, s>>>(ctl, sb);
+        return 1;
+    }
     int launches = 0;
     const int pre_blocks = min(dx_div_up(max_n, OPEN_THREADS), 148 * 4);
     k_radix_prepass<<<pre_blocks, OPEN_THREADS, 0, s>>>(ctl, sb);

@@ -63,78 +63,138 @@ __device__ __forceinline__ int find_blank(const uint8_t* row, int S) {
 }
 
 // ---------------------------------------------------------------------------------------------
-// Search-time expansion of the popped list.
+// Search-time expansion of the popped list, one instantiation per domain.
+//   * a block pass stages EXP_SP parents (16-byte loads); eight threads share a parent's goal test / blank search
+//     (strided over the state bytes, combined with three shuffles), thread 0 of the group records it;
+//   * the children are written 16 bytes per thread (consecutive threads -> consecutive chunks of consecutive children:
+//     512 contiguous bytes per warp).  cube3: a shared-memory table holds, per (action, output word), the four source byte
+//     indices packed in one word (indices >= S point at the row's zero padding), so a chunk costs 4 table loads + 16 byte
+//     loads; npuzzle: a child is the parent with two bytes exchanged; grid: one clamped coordinate.
+#define EXP_SP 32          // parents per block pass (8 threads each)
+
+template <int KIND>
 __global__ void __launch_bounds__(EXP_THREADS)
-k_expand(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
-         const float* __restrict__ node_g, const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
-         const uint32_t* __restrict__ pop_off, uint8_t* __restrict__ child_state, float* __restrict__ child_g,
-         uint8_t* __restrict__ pop_solved) {
-    __shared__ __align__(16) uint8_t s_rows[EXP_PB * MAX_SP];
-    __shared__ uint8_t s_table[12 * 54 > 225 * 4 ? 12 * 54 : 225 * 4];
-    __shared__ int s_z[EXP_PB];
-    __shared__ uint32_t s_inst[EXP_PB];
-    __shared__ float s_g[EXP_PB];       // NaN marks a parent of an inactive (finished) instance
+k_expand_t(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
+           const float* __restrict__ node_g, const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
+           const uint32_t* __restrict__ pop_off, uint8_t* __restrict__ child_state, float* __restrict__ child_g,
+           uint8_t* __restrict__ pop_solved) {
+    __shared__ __align__(16) uint8_t s_rows[EXP_SP * MAX_SP];
+    __shared__ uint32_t s_src4[12 * 16];                 // cube3: source bytes of output word w under action a
+    __shared__ uint8_t s_lut[225 * 4];                   // npuzzle: swap partner of blank position z under action a
+    __shared__ int s_z[EXP_SP];
+    __shared__ uint32_t s_inst[EXP_SP];
+    __shared__ float s_g[EXP_SP];       // NaN marks a parent of an inactive (finished) instance
 
     if (ctl->error) return;
     const int n_pop = ctl->n_pop;
-    const int SP = d.SP, S = d.S, A = d.A, words = SP / 4;
-    const int tsz = d.kind == DX_DOMAIN_CUBE3 ? 12 * 54 : (d.kind == DX_DOMAIN_NPUZZLE ? d.dim * d.dim * 4 : 0);
-    for (int i = threadIdx.x; i < tsz; i += EXP_THREADS) s_table[i] = d.table[i];
+    const int SP = d.SP, S = d.S, A = d.A, chunks = SP / 16;
+    if (KIND == DX_DOMAIN_CUBE3) {
+        for (int t = threadIdx.x; t < 12 * 16; t += EXP_THREADS) {
+            const int a = t >> 4, w = t & 15;
+            uint32_t v = 0;
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                const int i = 4 * w + j;
+                v |= (uint32_t)(i < 54 ? d.table[a * 54 + i] : 54) << (8 * j);     // byte 54 of a row is zero padding
+            }
+            s_src4[t] = v;
+        }
+    } else if (KIND == DX_DOMAIN_NPUZZLE) {
+        for (int i = threadIdx.x; i < d.dim * d.dim * 4; i += EXP_THREADS) s_lut[i] = d.table[i];
+    }
 
-    for (int base = blockIdx.x * EXP_PB; base < n_pop; base += gridDim.x * EXP_PB) {
-        const int np = min(EXP_PB, n_pop - base);
+    for (int base = blockIdx.x * EXP_SP; base < n_pop; base += gridDim.x * EXP_SP) {
+        const int np = min(EXP_SP, n_pop - base);
         __syncthreads();
-        // stage parent rows (16-byte chunks)
-        const int chunks = SP / 16;
         for (int t = threadIdx.x; t < np * chunks; t += EXP_THREADS) {
-            int p = t / chunks, c = t % chunks;
-            uint32_t id = popped[base + p];
+            const int p = t / chunks, c = t - p * chunks;
+            const uint32_t id = popped[base + p];
             reinterpret_cast<uint4*>(s_rows + p * SP)[c] = reinterpret_cast<const uint4*>(node_state + (size_t)id * SP)[c];
         }
         __syncthreads();
-        if (threadIdx.x < np) {
-            const int p = threadIdx.x, j = base + p;
-            const uint8_t* row = s_rows + p * SP;
+        {   // parent phase: 8 threads per parent (EXP_THREADS == 8 * EXP_SP)
+            const int p = threadIdx.x >> 3, sub = threadIdx.x & 7;
+            const bool live = p < np;
+            const int j = base + (live ? p : 0);
+            const uint8_t* row = s_rows + (live ? p : 0) * SP;
             const uint32_t inst = popped_inst[j];
-            const uint32_t id = popped[j];
             const bool act = ia.active[inst] != 0;
-            const float g = node_g[id];
-            s_inst[p] = inst;
-            s_g[p] = act ? g : __int_as_float(0x7fc00000);
-            s_z[p] = (d.kind == DX_DOMAIN_NPUZZLE) ? find_blank(row, S) : 0;
-            bool solved = false;
-            if (act) {
-                solved = row_solved(d.kind, d.dim, S, row, ia.goals + (size_t)inst * SP);
+            const uint8_t* goal = ia.goals + (size_t)inst * SP;
+            const int wild = d.dim * d.dim;
+            bool ok = true;
+            int z = 0x7fffffff;
+            for (int i = sub; i < S; i += 8) {
+                const uint8_t v = row[i], g = goal[i];
+                bool e = v == g;
+                if (KIND == DX_DOMAIN_NPUZZLE) {
+                    e = e || (g == wild);
+                    if (v == 0) z = min(z, i);
+                }
+                ok = ok && e;
+            }
+#pragma unroll
+            for (int sh = 1; sh < 8; sh <<= 1) {
+                const int ok_other = __shfl_xor_sync(0xffffffffu, (int)ok, sh);       // (never inside a short-circuit: every
+                const int z_other = __shfl_xor_sync(0xffffffffu, z, sh);              //  lane must execute the shuffle)
+                ok = ok && (ok_other != 0);
+                z = min(z, z_other);
+            }
+            if (live && sub == 0) {
+                const uint32_t id = popped[j];
+                const float g = node_g[id];
+                s_inst[p] = inst;
+                s_g[p] = act ? g : __int_as_float(0x7fc00000);
+                s_z[p] = (KIND == DX_DOMAIN_NPUZZLE && z != 0x7fffffff) ? z : 0;
+                const bool solved = act && ok;
                 if (solved) {
                     // lexicographic min over (g, pop order): strict '>' in record_goal == first seen wins
-                    unsigned long long key = ((unsigned long long)__float_as_uint(g) << 32) |
-                                             (unsigned long long)(ia.pop_seq_base[inst] + (uint32_t)j - pop_off[inst]);
+                    const unsigned long long key = ((unsigned long long)__float_as_uint(g) << 32) |
+                                                   (unsigned long long)(ia.pop_seq_base[inst] + (uint32_t)j - pop_off[inst]);
                     atomicMin(&ia.ub_key[inst], key);
                 }
+                pop_solved[j] = solved ? 1 : 0;
             }
-            pop_solved[j] = solved ? 1 : 0;
         }
         __syncthreads();
-        // children, one 32-bit word per thread step
-        const int total_words = np * A * words;
-        for (int t = threadIdx.x; t < total_words; t += EXP_THREADS) {
-            const int cl = t / words, w = t % words;
-            const int p = cl / A, a = cl % A;
+        // children: one 16-byte chunk per thread step
+        const int total = np * A * chunks;
+        for (int t = threadIdx.x; t < total; t += EXP_THREADS) {
+            const int cl = t / chunks, c = t - cl * chunks;
+            const int p = cl / A, a = cl - p * A;
             const uint8_t* row = s_rows + p * SP;
-            uint32_t v;
-            if (w == words - 1) {
-                v = s_inst[p];
+            uint32_t v[4];
+            if (KIND == DX_DOMAIN_CUBE3) {
+#pragma unroll
+                for (int q = 0; q < 4; ++q) {
+                    const uint32_t s4 = s_src4[a * 16 + 4 * c + q];
+                    v[q] = (uint32_t)row[s4 & 0xFF] | ((uint32_t)row[(s4 >> 8) & 0xFF] << 8) |
+                           ((uint32_t)row[(s4 >> 16) & 0xFF] << 16) | ((uint32_t)row[s4 >> 24] << 24);
+                }
             } else {
-                const int i0 = w * 4;
-                v = child_byte(d.kind, d.dim, S, row, s_table, a, i0, s_z[p]) |
-                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 1, s_z[p]) << 8) |
-                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 2, s_z[p]) << 16) |
-                    (child_byte(d.kind, d.dim, S, row, s_table, a, i0 + 3, s_z[p]) << 24);
+                const uint4 pv = reinterpret_cast<const uint4*>(row)[c];
+                v[0] = pv.x; v[1] = pv.y; v[2] = pv.z; v[3] = pv.w;
+                if (KIND == DX_DOMAIN_NPUZZLE) {
+                    const int z = s_z[p], sw = s_lut[z * 4 + a];
+                    if (sw != z) {                        // a blocked move leaves the state unchanged
+                        const uint32_t tile = row[sw];
+                        const int lo = 16 * c;
+                        if (z >= lo && z < lo + 16) { const int k = z - lo; v[k >> 2] = (v[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (tile << (8 * (k & 3))); }
+                        if (sw >= lo && sw < lo + 16) { const int k = sw - lo; v[k >> 2] &= ~(0xFFu << (8 * (k & 3))); }
+                    }
+                } else if (c == 0) {                      // grid: byte 0 = x (actions 0 / 1), byte 1 = y (actions 2 / 3)
+                    int x = (int)(v[0] & 0xFF), y = (int)((v[0] >> 8) & 0xFF);
+                    if (a == 0) x = max(x - 1, 0);
+                    else if (a == 1) x = min(x + 1, d.dim - 1);
+                    else if (a == 2) y = max(y - 1, 0);
+                    else y = min(y + 1, d.dim - 1);
+                    v[0] = (v[0] & 0xFFFF0000u) | (uint32_t)x | ((uint32_t)y << 8);
+                }
             }
-            reinterpret_cast<uint32_t*>(child_state + ((size_t)(base * A + cl)) * SP)[w] = v;
+            if (c == chunks - 1) v[3] = s_inst[p];        // the row's last word is the owning instance
+            reinterpret_cast<uint4*>(child_state + ((size_t)(base * A + cl)) * SP)[c] = make_uint4(v[0], v[1], v[2], v[3]);
         }
         for (int t = threadIdx.x; t < np * A; t += EXP_THREADS) {
-            float g = s_g[t / A];
+            const float g = s_g[t / A];
             child_g[(size_t)base * A + t] = g + 1.0f;     // transition cost 1.0 in all three domains; NaN stays NaN
         }
     }
@@ -143,9 +203,13 @@ k_expand(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_t*
 int dx_launch_expand(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
                      const float* node_g, const uint32_t* popped, const uint32_t* popped_inst, const uint32_t* pop_off,
                      uint8_t* child_state, float* child_g, uint8_t* pop_solved, int max_pop) {
-    int blocks = min(dx_div_up(max_pop, EXP_PB), 148 * 8);
-    k_expand<<<blocks, EXP_THREADS, 0, s>>>(d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, child_state,
-                                            child_g, pop_solved);
+    static_assert(EXP_THREADS == 8 * EXP_SP, "eight threads per staged parent");
+    const int blocks = min(dx_div_up(max_pop, EXP_SP), 148 * 8);
+#define DX_EXPAND_ARGS d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, child_state, child_g, pop_solved
+    if (d.kind == DX_DOMAIN_CUBE3) k_expand_t<DX_DOMAIN_CUBE3><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
+    else if (d.kind == DX_DOMAIN_NPUZZLE) k_expand_t<DX_DOMAIN_NPUZZLE><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
+    else k_expand_t<DX_DOMAIN_GRID><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
+#undef DX_EXPAND_ARGS
     return 1;
 }
 

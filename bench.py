@@ -371,12 +371,12 @@ def main() -> None:
         achieved = hidden_flop / (stage["gemm_hidden"] / 1e3) / 1e12 if stage["gemm_hidden"] > 0 else None
         peak = peaks["bf16_tflops_sustained"] if args.precision == "bf16" else None
         traffic, traffic_note = None, None
-        tf = os.path.join(ROOT, "profiles", "r1g_gemm_traffic.json")
+        tf = os.path.join(ROOT, "profiles", "r1i_gemm_traffic.json")
         if args.precision == "bf16" and os.path.exists(tf):
             tj = json.load(open(tf))
             traffic = tj["traffic_per_launch_avg_bytes"]
             traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture of a "
-                            f"{tj['rows_in_launch']}-state launch (profiles/r1g_gemm_traffic.json); algorithmic bytes of that launch: "
+                            f"{tj['rows_in_launch']}-state launch (profiles/r1i_gemm_traffic.json); algorithmic bytes of that launch: "
                             f"{tj['algorithmic_bytes']['hidden']} (plain) / {tj['algorithmic_bytes']['hidden_residual']} (with residual)")
         roof = {"kernel": "k_gemm_bf16_tc<256,2> (hidden layers, 1000x1000 per state)" if args.precision == "bf16" else "k_sgemm_bias_act",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -271,4 +271,5 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
                       const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
                        const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
-int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, void** plan_out);
+bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d);
+int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out);

@@ -1312,9 +1312,12 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             e->mlp.xb[i] = q;
         }
         uint16_t* onehot = nullptr;
-        DX_TRY(e->alloc(&onehot, (size_t)cap * in_dim_p));
-        DX_CUDA(cudaMemset(onehot, fill, (size_t)cap * in_dim_p * 2));
-        DX_TRY(dx_mlp_bf16_prepare(net, e->mlp, onehot, &net.tc_plan));
+        const bool gen_input = dx_mlp_bf16_gen_input(net, e->dom);
+        if (!gen_input) {                   // the one-hot matrix exists only for networks whose input layer is not fused
+            DX_TRY(e->alloc(&onehot, (size_t)cap * in_dim_p));
+            DX_CUDA(cudaMemset(onehot, fill, (size_t)cap * in_dim_p * 2));
+        }
+        DX_TRY(dx_mlp_bf16_prepare(net, e->mlp, onehot, gen_input, &net.tc_plan));
     } else {
         for (int i = 0; i < 3; ++i) DX_TRY(e->alloc(&e->mlp.x[i], (size_t)cap * Hp));
     }

@@ -58,7 +58,7 @@ struct TcPlan {
     int CL_in;                   // ... of the input layer (min(CL, 2))
     int grid4;                   // CTAs launched with clusters of 4 (4 x the co-resident clusters the device reports)
     int fuse_out;                // fold a scalar output layer into the last hidden GEMM (DXB200_FUSE_OUT=0 disables)
-    int fuse_in;                 // generate the one-hot input inside the first GEMM (DXB200_FUSE_IN=0 disables)
+    int fuse_in;                 // the one-hot input is generated inside the first GEMM (dx_mlp_bf16_gen_input; DXB200_FUSE_IN=0 disables)
     int num_sms;
 };
 
@@ -891,8 +891,25 @@ static int make_map(EncodeTiledFn enc, CUtensorMap* map, void* base, uint64_t co
     return DX_OK;
 }
 
+// Whether the input layer of this network / domain runs with the one-hot encoding generated inside the GEMM (then no one-hot
+// matrix is needed at all).  Networks that also read the goal keep the separate one-hot kernel (the goal row is a dependent
+// gather); the generated A tiles of a row group (in_dim_p / 64 tiles of 16 KB, at most 8) must fit next to a ring of at least
+// 3 weight tiles, which needs CTA pairs (half-size weight tiles).
+bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d) {
+    if (const char* c = getenv("DXB200_FUSE_IN")) if (c[0] == '0') return false;
+    if (const char* c = getenv("DXB200_GEMM_CLUSTER")) if (c[0] == '1') return false;
+    const int BN = (net.Hp % 256 == 0) ? 256 : 128;
+    const int kb_in = net.in_dim_p / TC_BK;
+    const int b_bytes = (BN / 2) * TC_BK * 2, a_bytes = TC_BM * TC_BK * 2;
+    const int ring_in = (5 * (a_bytes + b_bytes) - kb_in * a_bytes) / b_bytes;
+    return kb_in <= 8 && ring_in >= 3 && net.in_count <= d.S && d.SP % 16 == 0 &&
+           4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64;
+}
+
 // Called once after the weights and activation buffers exist.  Returns a heap TcPlan in *plan_out.
-int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, void** plan_out) {
+// onehot_buf may be nullptr when dx_mlp_bf16_gen_input() holds (gen_input then tells the launcher).
+int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out) {
+    if (!gen_input && !onehot_buf) { dx_set_error("NET_BF16: one-hot buffer missing"); return DX_ERR_ARG; }
     if (net.in_dim_p > 4096) {
         dx_set_error("NET_BF16: one-hot input wider than 4096 features is not supported (use NET_FP32)");
         return DX_ERR_UNSUPPORTED;
@@ -913,13 +930,14 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     p->grid4 = 0;
     p->fuse_out = 1;
     if (const char* c = getenv("DXB200_FUSE_OUT")) p->fuse_out = (c[0] == '0') ? 0 : 1;
-    p->fuse_in = 1;
-    if (const char* c = getenv("DXB200_FUSE_IN")) p->fuse_in = (c[0] == '0') ? 0 : 1;
+    p->fuse_in = gen_input ? 1 : 0;
     p->onehot = (__nv_bfloat16*)onehot_buf;
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
-    int rc = make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM);
+    // (with a generated input the A map of the first launch is never read: any valid map will do)
+    int rc = onehot_buf ? make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM)
+                        : make_map(enc, &p->a_onehot, mb.xb[0], net.Hp, (uint64_t)mb.cap, TC_BM);
     for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM);
     for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_xh[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM / 2);
     for (int i = 0; i < 3 && rc == DX_OK; ++i)
@@ -1051,13 +1069,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const int ones_col = (net.tc_fold & 2) ? net.in_dim : -1;
     const int kv_in = net.in_dim_p, kv_h = Hp, nv = Hp;      // padded shapes (trimming the padding measured no gain)
     dx_prof_begin(DX_ST_GEMM_IN);
-    // (networks that also read the goal keep the separate one-hot kernel: the goal row is a dependent gather)
-    // ... and the generated A tiles of a row group (in_dim_p / 64 tiles of 16 KB, at most 8) stay resident next to a ring of
-    // at least 3 weight tiles, which needs CTA pairs (half-size weight tiles)
-    const int kb_in = net.in_dim_p / TC_BK;
-    const int ring_in = (5 * (TC_BM * TC_BK * 2 + (p->BN / 2) * TC_BK * 2) - kb_in * TC_BM * TC_BK * 2) / ((p->BN / 2) * TC_BK * 2);
-    if (p->fuse_in && p->CL_in == 2 && kb_in <= 8 && ring_in >= 3 && net.in_count <= d.S && d.SP % 16 == 0 &&
-        4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64) {
+    if (p->fuse_in && p->CL_in == 2) {
         // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
         TcGen g;
         g.rows = rows; g.goals = goals; g.S = d.S; g.SP = d.SP; g.in_count = net.in_count; g.depth = net.depth; g.ones_col = ones_col;

@@ -225,6 +225,28 @@ def test_bf16_q_output_layer_variants_agree(switch, monkeypatch):
     np.testing.assert_allclose(out, ref, rtol=0, atol=0.01)
 
 
+@pytest.mark.parametrize("out_dim", [1, 12])
+def test_bf16_odd_row_counts(out_dim):
+    """Row counts around the 128 / 256-row tile and CTA-pair boundaries (1, 127, 129, 255, 257, 1000 states): every row of
+    the tensor-core path must agree with the fp32 device path, and a row's value must not depend on what else is in the batch."""
+    from deepxube_b200 import _lib as L
+    from oracle.nnet_torch import random_state_dict
+    rng = np.random.default_rng(9)
+    st = rng.integers(0, 6, size=(1000, 54), dtype=np.uint8)
+    sd = random_state_dict(324, 1000, 4, out_dim, True, seed=8, randomize_bn=True)
+    blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    outs = {}
+    for mode in (L.DX_HEUR_NET_FP32, L.DX_HEUR_NET_BF16):
+        eng = L.Engine("cube3", 0, "graph_q" if out_dim > 1 else "graph_v", mode, max_instances=2, max_pop_total=1024, max_nodes=4096)
+        eng.load_weights(54, 6, 1000, 4, out_dim, True, blob)
+        outs[mode] = {n: eng.heur_eval(st[:n], None, out_dim) for n in (1, 127, 129, 255, 257, 1000)}
+        eng.close()
+    full = outs[L.DX_HEUR_NET_BF16][1000]
+    for n, o in outs[L.DX_HEUR_NET_BF16].items():
+        assert np.array_equal(o, full[:n]), n                                  # batch-independent, bit for bit
+        np.testing.assert_allclose(o, outs[L.DX_HEUR_NET_FP32][n], rtol=0, atol=0.01)
+
+
 def test_bf16_search_deviation_is_reported():
     """bf16 heuristics cannot promise identical node counts: solutions must stay valid and the
     deviation of cost / nodes from the fp32 KAT is bounded and printed."""

@@ -8,7 +8,7 @@ The compute path is libdxb200.so (hand-written sm_100a CUDA, include/dxb200.h); 
 __version__ = "0.1.0"
 
 from . import domains  # noqa: F401,E402
-from .domains import cube3, grid, npuzzle  # noqa: F401,E402
+from .domains import cube3, grid, lightsout, npuzzle  # noqa: F401,E402
 from .nnets import resnet_fc  # noqa: F401,E402
 from .pathfind_fns import fns_core  # noqa: F401,E402
 from .pathfinding import graph_search  # noqa: F401,E402

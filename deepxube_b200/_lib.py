@@ -13,7 +13,7 @@ import numpy as np
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DXB200_LIB") or os.path.join(HERE, "libdxb200.so")   # DXB200_LIB: A/B builds
 
-DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2}
+DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2, "lightsout": 3}
 DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q = 0, 1
 DX_HEUR_ZERO, DX_HEUR_HOST, DX_HEUR_NET_FP32, DX_HEUR_NET_BF16 = 0, 1, 2, 3
 STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book", "gemm_hidden", "gemm_input"]

@@ -12,6 +12,7 @@ _MODULE_MAP = {
     "deepxube.domains.cube3": "deepxube_b200.domains.cube3",
     "deepxube.domains.npuzzle": "deepxube_b200.domains.npuzzle",
     "deepxube.domains.grid": "deepxube_b200.domains.grid",
+    "deepxube.domains.lightsout": "deepxube_b200.domains.lightsout",
     "domains.grid_tutorial": "deepxube_b200.domains.grid",      # tutorial copy of the grid domain, same classes
 }
 

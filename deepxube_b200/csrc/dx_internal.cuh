@@ -12,7 +12,7 @@
 #define DX_EMPTY64 0xFFFFFFFFFFFFFFFFull
 #define DX_SORT_TILE 2048               // elements per radix / merge tile
 #define DX_NUM_DIGITS 12                // 8 bytes of f-key + 4 bytes of instance id
-#define DX_MAX_OUT 32                   // max network outputs (actions) supported
+#define DX_MAX_OUT 256                  // max network outputs (actions) supported (lightsout.15: 225)
 
 // error bits in Ctl::error (sticky, set on the device)
 #define DX_DEVERR_NODES 1u

@@ -71,6 +71,20 @@ static int make_domain_host(int domain, int dim, DomainDev* d, std::vector<uint8
     } else if (domain == DX_DOMAIN_GRID) {
         if (dim < 1 || dim > 255) DX_FAIL(DX_ERR_ARG, "grid dim must be in 1..255");
         d->S = 2; d->A = 4; d->in_count = 4; d->depth = dim;
+    } else if (domain == DX_DOMAIN_LIGHTSOUT) {
+        if (dim < 2 || dim > 15) DX_FAIL(DX_ERR_ARG, "lightsout dim must be in 2..15");
+        // action a toggles [a, a+dim, a-dim, a+1, a-1], an off-board neighbour replaced by a (lightsout.py:69-78); one-hot
+        // depth 1 = the 0 / 1 tile value is the network input itself (lightsout.py:107-108, pytorch_models.py:15-24)
+        d->S = dim * dim; d->A = dim * dim; d->in_count = dim * dim; d->depth = 1;
+        table->resize(dim * dim * 5);
+        for (int a = 0; a < dim * dim; ++a) {
+            const int x = a / dim, y = a % dim;
+            (*table)[a * 5 + 0] = (uint8_t)a;
+            (*table)[a * 5 + 1] = (uint8_t)(x < dim - 1 ? a + dim : a);
+            (*table)[a * 5 + 2] = (uint8_t)(x > 0 ? a - dim : a);
+            (*table)[a * 5 + 3] = (uint8_t)(y < dim - 1 ? a + 1 : a);
+            (*table)[a * 5 + 4] = (uint8_t)(y > 0 ? a - 1 : a);
+        }
     } else {
         DX_FAIL(DX_ERR_ARG, "unknown domain");
     }

@@ -29,6 +29,11 @@ __device__ __forceinline__ uint32_t child_byte(int kind, int dim, int S, const u
         if (i == z) return row[sw];          // sw == z (blocked): row[z] == 0, unchanged
         if (i == sw) return 0u;
         return row[i];
+    } else if (kind == DX_DOMAIN_LIGHTSOUT) {
+        // toggled once even when the border lists the pressed cell several times (lightsout.py:186)
+        const uint8_t* m = table + a * 5;
+        const bool hit = i == m[0] || i == m[1] || i == m[2] || i == m[3] || i == m[4];
+        return (uint32_t)row[i] ^ (hit ? 1u : 0u);
     } else {
         int v = row[i];
         if (i == 0) {
@@ -80,7 +85,7 @@ k_expand_t(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_
            uint8_t* __restrict__ pop_solved) {
     __shared__ __align__(16) uint8_t s_rows[EXP_SP * MAX_SP];
     __shared__ uint32_t s_src4[12 * 16];                 // cube3: source bytes of output word w under action a
-    __shared__ uint8_t s_lut[225 * 4];                   // npuzzle: swap partner of blank position z under action a
+    __shared__ uint8_t s_lut[225 * 5];                   // npuzzle: swap partner of blank z under action a; lightsout: toggled cells
     __shared__ int s_z[EXP_SP];
     __shared__ uint32_t s_inst[EXP_SP];
     __shared__ float s_g[EXP_SP];       // NaN marks a parent of an inactive (finished) instance
@@ -101,6 +106,8 @@ k_expand_t(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_
         }
     } else if (KIND == DX_DOMAIN_NPUZZLE) {
         for (int i = threadIdx.x; i < d.dim * d.dim * 4; i += EXP_THREADS) s_lut[i] = d.table[i];
+    } else if (KIND == DX_DOMAIN_LIGHTSOUT) {
+        for (int i = threadIdx.x; i < d.dim * d.dim * 5; i += EXP_THREADS) s_lut[i] = d.table[i];
     }
 
     for (int base = blockIdx.x * EXP_SP; base < n_pop; base += gridDim.x * EXP_SP) {
@@ -181,6 +188,13 @@ k_expand_t(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_
                         if (z >= lo && z < lo + 16) { const int k = z - lo; v[k >> 2] = (v[k >> 2] & ~(0xFFu << (8 * (k & 3)))) | (tile << (8 * (k & 3))); }
                         if (sw >= lo && sw < lo + 16) { const int k = sw - lo; v[k >> 2] &= ~(0xFFu << (8 * (k & 3))); }
                     }
+                } else if (KIND == DX_DOMAIN_LIGHTSOUT) {  // the pressed cell and its on-board neighbours flip, each once
+                    const int lo = 16 * c;
+#pragma unroll
+                    for (int q = 0; q < 5; ++q) {
+                        const int m = s_lut[a * 5 + q];
+                        if ((q == 0 || m != a) && m >= lo && m < lo + 16) { const int k = m - lo; v[k >> 2] ^= 1u << (8 * (k & 3)); }
+                    }
                 } else if (c == 0) {                      // grid: byte 0 = x (actions 0 / 1), byte 1 = y (actions 2 / 3)
                     int x = (int)(v[0] & 0xFF), y = (int)((v[0] >> 8) & 0xFF);
                     if (a == 0) x = max(x - 1, 0);
@@ -208,6 +222,7 @@ int dx_launch_expand(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const I
 #define DX_EXPAND_ARGS d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, child_state, child_g, pop_solved
     if (d.kind == DX_DOMAIN_CUBE3) k_expand_t<DX_DOMAIN_CUBE3><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
     else if (d.kind == DX_DOMAIN_NPUZZLE) k_expand_t<DX_DOMAIN_NPUZZLE><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
+    else if (d.kind == DX_DOMAIN_LIGHTSOUT) k_expand_t<DX_DOMAIN_LIGHTSOUT><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
     else k_expand_t<DX_DOMAIN_GRID><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
 #undef DX_EXPAND_ARGS
     return 1;
@@ -242,12 +257,13 @@ __global__ void __launch_bounds__(EXP_THREADS)
 k_standalone_expand(DomainDev d, const uint8_t* __restrict__ rows, long long n, const int32_t* __restrict__ actions,
                     uint8_t* __restrict__ out_rows) {
     __shared__ __align__(16) uint8_t s_rows[EXP_PB * MAX_SP];
-    __shared__ uint8_t s_table[12 * 54 > 225 * 4 ? 12 * 54 : 225 * 4];
+    __shared__ uint8_t s_table[225 * 5];          // cube3 12*54, npuzzle dim*dim*4, lightsout dim*dim*5
     __shared__ int s_z[EXP_PB];
     __shared__ int s_act[EXP_PB];
     const int SP = d.SP, S = d.S, words = SP / 4;
     const int A = actions ? 1 : d.A;
-    const int tsz = d.kind == DX_DOMAIN_CUBE3 ? 12 * 54 : (d.kind == DX_DOMAIN_NPUZZLE ? d.dim * d.dim * 4 : 0);
+    const int tsz = d.kind == DX_DOMAIN_CUBE3 ? 12 * 54 : (d.kind == DX_DOMAIN_NPUZZLE ? d.dim * d.dim * 4
+                    : (d.kind == DX_DOMAIN_LIGHTSOUT ? d.dim * d.dim * 5 : 0));
     for (int i = threadIdx.x; i < tsz; i += EXP_THREADS) s_table[i] = d.table[i];
     for (long long base = (long long)blockIdx.x * EXP_PB; base < n; base += (long long)gridDim.x * EXP_PB) {
         const int np = (int)min((long long)EXP_PB, n - base);

@@ -22,6 +22,7 @@ __global__ void __launch_bounds__(FL_THREADS)
 k_first_layer_f32(DomainDev d, NetDev net, const Ctl* __restrict__ ctl, const uint8_t* __restrict__ rows,
                   const uint8_t* __restrict__ goals, float* __restrict__ X) {
     __shared__ int s_feat[FL_ROWS][256];     // in_count <= 256 (npuzzle.15 has 225)
+    __shared__ float s_mul[FL_ROWS][256];    // 1 for one-hot inputs; the input value itself when one_hot_depth == 1
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     const int Hp = net.Hp, ic = net.in_count;
@@ -32,8 +33,14 @@ k_first_layer_f32(DomainDev d, NetDev net, const Ctl* __restrict__ ctl, const ui
             const int r = t / ic, i = t % ic;
             const uint8_t* row = rows + (size_t)(start + base + r) * d.SP;
             int v = nn_input_value(d, row, goals, i);
-            v = min(v, net.depth - 1);                     // one_hot would raise on out-of-range input; clamp instead
-            s_feat[r][i] = (i * net.depth + v) * Hp;
+            if (net.depth > 1) {
+                v = min(v, net.depth - 1);                 // one_hot would raise on out-of-range input; clamp instead
+                s_feat[r][i] = (i * net.depth + v) * Hp;
+                s_mul[r][i] = 1.f;
+            } else {                                       // OneHot with depth 1 is x.float() (pytorch_models.py:24)
+                s_feat[r][i] = i * Hp;
+                s_mul[r][i] = (float)v;
+            }
         }
         __syncthreads();
         for (int c = threadIdx.x; c < Hp; c += FL_THREADS) {
@@ -44,7 +51,7 @@ k_first_layer_f32(DomainDev d, NetDev net, const Ctl* __restrict__ ctl, const ui
             for (int i = 0; i < ic; ++i) {
 #pragma unroll
                 for (int r = 0; r < FL_ROWS; ++r)
-                    if (r < nr) acc[r] += net.w0t[s_feat[r][i] + c];
+                    if (r < nr) acc[r] += s_mul[r][i] * net.w0t[s_feat[r][i] + c];     // (1.0f * w is exact: one-hot sums unchanged)
             }
 #pragma unroll
             for (int r = 0; r < FL_ROWS; ++r)

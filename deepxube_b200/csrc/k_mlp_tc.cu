@@ -797,6 +797,12 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
                 const uint32_t inst = *reinterpret_cast<const uint32_t*>(row + d.SP - 4);
                 v = goals[(size_t)inst * d.SP + (i - d.S)];
             }
+            if (depth == 1) {                       // OneHot with depth 1 is x.float(): feature i = the value (exact in bf16 up to 256)
+                const int f = i - c0;
+                const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)v));
+                w[f >> 1] |= (f & 1) ? (bits << 16) : bits;
+                continue;
+            }
             v = min(v, depth - 1);
             const int f = i * depth + v - c0;
             if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 = 0x3F80
@@ -902,6 +908,7 @@ bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d) {
     const int kb_in = net.in_dim_p / TC_BK;
     const int b_bytes = (BN / 2) * TC_BK * 2, a_bytes = TC_BM * TC_BK * 2;
     const int ring_in = (5 * (a_bytes + b_bytes) - kb_in * a_bytes) / b_bytes;
+    if (net.depth < 2) return false;          // depth-1 inputs are raw values, not one-hot codes: separate input kernel
     return kb_in <= 8 && ring_in >= 3 && net.in_count <= d.S && d.SP % 16 == 0 &&
            4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64;
 }

@@ -49,3 +49,15 @@ def npuzzle_swap_table(dim: int) -> np.ndarray:
                     np.where(j < dim - 1, z + 1, z), np.where(j > 0, z - 1, z)], axis=1).astype(np.int64)
     lut.setflags(write=False)
     return lut
+
+
+@lru_cache(maxsize=None)
+def lightsout_move_table(dim: int) -> np.ndarray:
+    """[d*d, 5] int64: the cells action a flips = [a, a+d, a-d, a+1, a-1], a neighbour that would leave the board replaced
+    by a itself (deepxube/domains/lightsout.py:69-78)."""
+    a = np.arange(dim * dim)
+    x, y = a // dim, a % dim
+    mm = np.stack([a, np.where(x < dim - 1, a + dim, a), np.where(x > 0, a - dim, a),
+                   np.where(y < dim - 1, a + 1, a), np.where(y > 0, a - 1, a)], axis=1).astype(np.int64)
+    mm.setflags(write=False)
+    return mm

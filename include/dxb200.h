@@ -34,7 +34,8 @@ extern "C" {
 #define DX_ERR_STATE (-4)      /* call not valid in the engine's current state   */
 #define DX_ERR_UNSUPPORTED (-5)
 
-enum dx_domain { DX_DOMAIN_CUBE3 = 0, DX_DOMAIN_NPUZZLE = 1, DX_DOMAIN_GRID = 2 };
+enum dx_domain { DX_DOMAIN_CUBE3 = 0, DX_DOMAIN_NPUZZLE = 1, DX_DOMAIN_GRID = 2,
+                 DX_DOMAIN_LIGHTSOUT = 3 /* deepxube/domains/lightsout.py: dim*dim 0/1 tiles, dim*dim actions */ };
 
 /* graph_v = batch weighted A* (deepxube/pathfinding/graph_search.py:182-194),
  * graph_q = batch weighted Q* (graph_search.py:197-209). */

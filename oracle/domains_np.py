@@ -6,6 +6,7 @@ State rows:
   cube3     54 x u8 sticker colours, goal = arange(54)//9          (ref: deepxube/domains/cube3.py:502-503)
   npuzzle.d d*d x u8 tiles, 0 = blank, goal = [1..d*d-1, 0]         (ref: deepxube/domains/npuzzle.py:63-73)
   grid.d    2 x u8 (robot_x, robot_y); goal row 2 x u8             (ref: deepxube/domains/grid.py:24-35)
+  lightsout.d  d*d x u8 lights (0 / 1), goal = all off              (ref: deepxube/domains/lightsout.py:16-24, :79)
 
 Children are produced state-major / action-minor, child index = i*A + a
 (ref: deepxube/base/domain.py:288-312).  Every transition costs 1.0.
@@ -60,8 +61,19 @@ def npuzzle_swap_lut(dim: int) -> np.ndarray:
     return lut
 
 
+def lightsout_moves(dim: int) -> np.ndarray:
+    """[d*d, 5] int64: the cells action a toggles = [a, a+d, a-d, a+1, a-1], an out-of-board neighbour replaced by a
+    itself (ref: lightsout.py:69-78).  The reference toggles through one fancy-index assignment
+    `t[i, mm] = (t[i, mm] + 1) % 2` (:186), so a cell listed twice is still toggled ONCE."""
+    mm = np.zeros((dim * dim, 5), dtype=np.int64)
+    for a in range(dim * dim):
+        x, y = a // dim, a % dim
+        mm[a] = [a, a + dim if x < dim - 1 else a, a - dim if x > 0 else a, a + 1 if y < dim - 1 else a, a - 1 if y > 0 else a]
+    return mm
+
+
 class OracleDomain:
-    """name in {"cube3", "npuzzle", "grid"}; dim is the puzzle / grid side (ignored for cube3)."""
+    """name in {"cube3", "npuzzle", "grid", "lightsout"}; dim is the puzzle / grid side (ignored for cube3)."""
 
     def __init__(self, name: str, dim: int = 0):
         self.name = name
@@ -79,6 +91,11 @@ class OracleDomain:
             assert 1 <= dim <= 255
             self.state_len, self.num_actions = 2, 4
             self.goal_len = 2
+        elif name == "lightsout":
+            assert 2 <= dim <= 15
+            self.state_len, self.num_actions = dim * dim, dim * dim
+            self.moves = lightsout_moves(dim)
+            self.goal_len = dim * dim
         else:
             raise ValueError(name)
 
@@ -89,6 +106,8 @@ class OracleDomain:
         if self.name == "npuzzle":
             n = self.dim * self.dim
             return np.concatenate((np.arange(1, n), [0])).astype(np.uint8)
+        if self.name == "lightsout":
+            return np.zeros(self.dim * self.dim, np.uint8)
         raise ValueError("grid has no canonical goal")
 
     def input_info(self) -> Tuple[int, int]:
@@ -98,6 +117,8 @@ class OracleDomain:
             return 54, 6
         if self.name == "npuzzle":
             return self.dim * self.dim, self.dim * self.dim
+        if self.name == "lightsout":
+            return self.dim * self.dim, 1          # depth 1: the 0 / 1 value itself is the feature (pytorch_models.py:15-24)
         return 4, self.dim
 
     def nnet_input(self, states: np.ndarray, goals: np.ndarray) -> np.ndarray:
@@ -123,6 +144,12 @@ class OracleDomain:
             rows = np.arange(n)
             out[rows, z] = states[rows, sw]
             out[rows, sw] = 0
+            return out
+        if self.name == "lightsout":
+            out = states.copy()
+            for k in range(n):
+                cells = np.unique(self.moves[actions[k]])
+                out[k, cells] ^= 1
             return out
         out = states.astype(np.int64)
         d = self.dim

@@ -50,7 +50,7 @@ def test_bruteforce(fn_name, pathfind_arg):
     pathfind.close()
 
 
-@pytest.mark.parametrize("domain_str", ["cube3", "npuzzle.4", "npuzzle.3", "grid.7d"])
+@pytest.mark.parametrize("domain_str", ["cube3", "npuzzle.4", "npuzzle.3", "grid.7d", "lightsout.5"])
 def test_expand_equals_next_state(domain_str):
     """reference tests/test_domains.py::test_expand"""
     random.seed(1)

@@ -25,7 +25,7 @@ def test_name_args_split():
 
 
 def test_registries_hold_the_hot_path_names():
-    assert set(domain_factory.get_all_class_names()) == {"cube3", "npuzzle", "grid"}
+    assert set(domain_factory.get_all_class_names()) == {"cube3", "npuzzle", "grid", "lightsout"}
     assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q"}
     with pytest.raises(ValueError, match="Unknown domain"):
         get_domain_from_arg("sokoban")

@@ -32,6 +32,27 @@ def test_expand_matches_reference(name, dim, key):
         assert np.array_equal(dom.is_solved(z[key + "_states"], z[key + "_goals_wild"]), z[key + "_solved_wild"])
 
 
+@pytest.mark.parametrize("d", [3, 5, 7])
+def test_lightsout_matches_reference(d):
+    """move matrix, expand (a border move lists its own cell twice but toggles it once, lightsout.py:186), is_solved"""
+    z = gu.load("lightsout")
+    dom = OracleDomain("lightsout", d)
+    assert np.array_equal(dom.moves, z[f"lo{d}_moves"])
+    assert np.array_equal(dom.expand(z[f"lo{d}_states"]), z[f"lo{d}_children"])
+    assert np.array_equal(dom.is_solved(z[f"lo{d}_states"], z[f"lo{d}_goals"]), z[f"lo{d}_solved"])
+    assert dom.input_info() == (d * d, 1)
+
+
+@pytest.mark.parametrize("tag,q", [("lo5v", False), ("lo5q", True)])
+def test_lightsout_nnet_matches_reference(tag, q):
+    """one-hot depth 1: the tile values themselves are the network input (pytorch_models.py:15-24)"""
+    from oracle.nnet_torch import heurq_from_state_dict, heurv_from_state_dict
+    z = gu.load("lightsout")
+    sd = gu.state_dict_torch(tag)
+    fn = (heurq_from_state_dict if q else heurv_from_state_dict)(sd, 1)
+    np.testing.assert_allclose(fn(z[tag + "_states"].astype(np.int64)), z[tag + "_out"], rtol=0, atol=2e-5)
+
+
 def test_expand_edge_cases():
     dom = OracleDomain("cube3")
     assert dom.expand(np.zeros((0, 54), np.uint8)).shape == (0, 54)

@@ -283,8 +283,68 @@ def gen_traces() -> None:
     print("traces.npz", len(out), "arrays")
 
 
+def gen_lightsout() -> None:
+    """lightsout.npz: the fourth domain, everything in one file so that the other fixtures stay untouched:
+    move matrices, expand / is_solved outputs, a random-BN network through the reference's own modules (one-hot depth 1:
+    the 0 / 1 tile value is the feature), and search traces with the zero / pseudo heuristics."""
+    out = {}
+    seed_all(3)
+    for d in (3, 5, 7):
+        dom, _ = get_domain_from_arg(f"lightsout.{d}")
+        out[f"lo{d}_moves"] = np.asarray(dom.move_matrix, np.int64)
+        st, goals = dom.sample_problem_instances(list(np.random.randint(0, 30, size=40)))
+        out[f"lo{d}_states"] = states_np(st)
+        out[f"lo{d}_goals"] = np.stack([g.tiles for g in goals]).astype(np.uint8)
+        ch, acts, tcs = dom.expand(st)
+        out[f"lo{d}_children"] = np.stack([state_np(c) for row in ch for c in row])
+        assert all(a.action == i for row in acts for i, a in enumerate(row)) and all(t == 1.0 for row in tcs for t in row)
+        out[f"lo{d}_solved"] = np.array(dom.is_solved(st, goals))
+    # networks (random weights, non-trivial BN statistics) evaluated by the reference
+    import tempfile
+    from oracle.nnet_torch import random_state_dict
+    dom, _ = get_domain_from_arg("lightsout.5")
+    for tag, fn, odim in (("lo5v", "heurv,resnet_fc.96H_2B_bn", 1), ("lo5q", "heurq_fixout,resnet_fc.128H_1B_bn", 25)):
+        h = int(fn.split("resnet_fc.")[1].split("H")[0])
+        nb = int(fn.split("H_")[1].split("B")[0])
+        sd = random_state_dict(25, h, nb, odim, batch_norm=True, seed=9, randomize_bn=True)
+        with tempfile.NamedTemporaryFile(suffix=".pt") as tf:
+            torch.save(sd, tf.name)
+            st, goals = dom.sample_problem_instances(list(np.random.randint(0, 30, size=64)))
+            _, vals = ref_nnet_raw(dom, "lightsout", fn, tf.name, st, goals)
+        out.update(sd_to_np(sd, tag + "/"))
+        out[tag + "_states"], out[tag + "_out"] = states_np(st), vals
+
+    def add(tag, domain_str, pathfind_str, heur, steps_l, max_steps):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        is_q = heur.startswith("q")
+        if heur in ("v_zero", "q_zero"):
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv" if not is_q else "heurq_fixout"], torch.device("cpu"))
+        elif heur == "v_pseudo":
+            pfns = wrap_v(pseudo_v)
+        else:
+            pfns = wrap_q(make_pseudo_q(domain.get_num_acts()))
+        res = run_trace(domain, pfns, pathfind_str, states, goals, max_steps)
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, ""])
+        for k, v in res.items():
+            out[tag + "/" + k] = v
+        print(tag, res["pathfind_name"], "steps", res["itr"].shape[0], "cost", res["path_cost"], "gen", res["gen"][-1])
+
+    add("lo3_v_zero", "lightsout.3", "graph.4B", "v_zero", [0, 2, 5, 9], 300)
+    add("lo5_v_pseudo", "lightsout.5", "graph.40B_0.7W", "v_pseudo", [3, 8, 15, 30], 10)
+    add("lo5_q_zero", "lightsout.5", "graph.20B", "q_zero", [0, 1, 2, 3], 60)
+    add("lo7_q_pseudo", "lightsout.7", "graph.30B_0.6W", "q_pseudo", [5, 12, 25], 8)
+    np.savez_compressed(os.path.join(OUT, "lightsout.npz"), **out)
+    print("lightsout.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout"]
+    if "lightsout" in which:
+        gen_lightsout()
     if "domains" in which:
         gen_domains()
     if "nnet" in which:

@@ -39,6 +39,7 @@ _NNET_INPUTS = {
     "cube3": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn},
     "npuzzle": {"flat_sg": StateGoalIn},                      # no fixed-action input: heurq_fixout unavailable (npuzzle.py:55)
     "grid": {"grid_flat_in": StateGoalIn, "grid_flat_in_qfix": StateGoalActFixIn},
+    "lightsout": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn},      # lightsout.py:60-64
 }
 
 

@@ -225,6 +225,38 @@ def test_bf16_q_output_layer_variants_agree(switch, monkeypatch):
     np.testing.assert_allclose(out, ref, rtol=0, atol=0.01)
 
 
+@pytest.mark.parametrize("fn,tag,q", [("heurv,resnet_fc.96H_2B_bn", "lo5v", False), ("heurq_fixout,resnet_fc.128H_1B_bn", "lo5q", True)])
+def test_lightsout_through_the_registries(fn, tag, q):
+    """`--domain lightsout.5 --fn heurv|heurq_fixout,resnet_fc...` resolves like in the reference (flat_sg / flat_sg_actfix
+    inputs with one-hot depth 1) and the device network reproduces the reference's outputs; a short search runs through
+    the PathFind API."""
+    z = gu.load("lightsout")
+    dom, name = get_domain_from_arg("lightsout.5")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [fn])
+    heur = pfns.heurq if q else pfns.heurv
+    heur.nnet.load_state_dict(gu.state_dict_np(tag))
+    states = dom.rows_to_states(z[tag + "_states"])
+    goals = dom.sample_goalstate_goal_pairs(len(states))[1]
+    if q:
+        out = np.array(heur(states, goals, dom.get_state_actions(states), [None] * len(states)))
+    else:
+        out = np.array(heur(states, goals, [None] * len(states)))
+    np.testing.assert_allclose(out, z[tag + "_out"], rtol=0, atol=2e-4)
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.50B_0.8W")
+    assert pname == ("graph_q" if q else "graph_v")
+    random.seed(4)
+    st, gl = dom.sample_problem_instances([3, 6, 9])
+    pathfind.add_instances(pathfind.make_instances(st, gl))
+    for _ in range(8):
+        pathfind.step()
+    assert all(i.num_nodes_generated > 0 for i in pathfind.instances)
+    for inst, s0, g0 in zip(pathfind.instances, st, gl):
+        if inst.goal_node is not None:
+            _, actions, _, cost = get_path(inst.goal_node)
+            assert is_valid_soln(s0, g0, actions, dom) and cost == len(actions)
+    pathfind.close()
+
+
 @pytest.mark.parametrize("out_dim", [1, 12])
 def test_bf16_odd_row_counts(out_dim):
     """Row counts around the 128 / 256-row tile and CTA-pair boundaries (1, 127, 129, 255, 257, 1000 states): every row of

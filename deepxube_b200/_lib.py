@@ -31,7 +31,7 @@ class dx_config(C.Structure):
 
 class dx_net_desc(C.Structure):
     _fields_ = [("in_count", C.c_int32), ("one_hot_depth", C.c_int32), ("res_dim", C.c_int32), ("num_blocks", C.c_int32),
-                ("out_dim", C.c_int32), ("batch_norm", C.c_int32)]
+                ("out_dim", C.c_int32), ("batch_norm", C.c_int32), ("act_depth", C.c_int32)]
 
 
 class dx_inst_status(C.Structure):
@@ -209,9 +209,10 @@ class Engine:
         check(self._lib.dx_engine_reset(self._h))
 
     def load_weights(self, in_count: int, depth: int, res_dim: int, num_blocks: int, out_dim: int, batch_norm: bool,
-                     blob: np.ndarray) -> None:
+                     blob: np.ndarray, act_depth: int = 0) -> None:
+        """act_depth > 0: action-as-input Q network (heurq_in): the action index is one more input of that one-hot depth"""
         blob = np.ascontiguousarray(blob, dtype=np.float32)
-        desc = dx_net_desc(in_count, depth, res_dim, num_blocks, out_dim, 1 if batch_norm else 0)
+        desc = dx_net_desc(in_count, depth, res_dim, num_blocks, out_dim, 1 if batch_norm else 0, act_depth)
         check(self._lib.dx_load_weights(self._h, C.byref(desc), _p(blob, _f32p), blob.size))
 
     def add_instances(self, states: np.ndarray, goals: np.ndarray, batch_sizes=None, weights=None, root_vals=None) -> None:

@@ -27,6 +27,20 @@ class StateGoalIn(FlatIn):
         return self.domain.to_np_flat_sg(states, goals)
 
 
+class StateGoalActIn(FlatIn):
+    """action-as-input Q networks (`heurq_in`): the flat state-goal input plus ONE action index per row whose one-hot
+    depth is the number of actions (deepxube/base/nnet_input.py:283-296, `flat_sga`; grid: `grid_flat_in_actin`,
+    deepxube/domains/grid.py:147-155)."""
+
+    def get_input_info(self) -> Tuple[List[int], List[int]]:
+        dims, depths = self.domain.get_input_info_flat_sg()
+        return list(dims) + [1], list(depths) + [self.domain.get_num_acts()]
+
+    def to_np(self, states: List[Any], goals: List[Any], actions: List[Any]) -> List[np.ndarray]:
+        acts = np.expand_dims(np.array([self.domain.action_index(a) for a in actions]), 1)
+        return self.domain.to_np_flat_sg(states, goals) + [acts]
+
+
 class StateGoalActFixIn(FlatIn):
     def to_np(self, states: List[Any], goals: List[Any], actions_l: List[List[Any]]) -> List[np.ndarray]:
         acts = np.array([[self.domain.action_index(a) for a in al] for al in actions_l])
@@ -36,10 +50,10 @@ class StateGoalActFixIn(FlatIn):
 # domain name -> {nnet input name: class}; order matters: the first compatible one is picked
 # (deepxube/factories/pathfind_fns_factory.py:23-39)
 _NNET_INPUTS = {
-    "cube3": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn},
+    "cube3": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn, "flat_sga": StateGoalActIn},
     "npuzzle": {"flat_sg": StateGoalIn},                      # no fixed-action input: heurq_fixout unavailable (npuzzle.py:55)
-    "grid": {"grid_flat_in": StateGoalIn, "grid_flat_in_qfix": StateGoalActFixIn},
-    "lightsout": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn},      # lightsout.py:60-64
+    "grid": {"grid_flat_in": StateGoalIn, "grid_flat_in_qfix": StateGoalActFixIn, "grid_flat_in_actin": StateGoalActIn},
+    "lightsout": {"flat_sg": StateGoalIn, "flat_sg_actfix": StateGoalActFixIn, "flat_sga": StateGoalActIn},      # lightsout.py:60-64
 }
 
 

@@ -77,7 +77,8 @@ class _DeviceHeur:
             from deepxube_b200 import _lib
             mode = _lib.DX_HEUR_NET_BF16 if self.precision == "bf16" else _lib.DX_HEUR_NET_FP32
             a = self.domain.get_num_acts()
-            eng = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, "graph_q" if self.nnet.q_fix else "graph_v", mode,
+            is_q = self.nnet.q_fix or getattr(self.nnet, "act_depth", 0) > 0
+            eng = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, "graph_q" if is_q else "graph_v", mode,
                               max_instances=1, max_pop_total=max(1, 16384 // (1 if self.nnet.q_fix else a)), max_nodes=1024)
             load_nnet_into_engine(eng, self.nnet)
             self._eng = eng
@@ -86,10 +87,11 @@ class _DeviceHeur:
     def _eval(self, states: List[Any], goals: List[Any]) -> np.ndarray:
         n = len(states)
         if n == 0:
-            return np.zeros((0, self.nnet.out_dim), np.float32)
+            return np.zeros((0, self.nnet.out_dim * max(getattr(self.nnet, "act_depth", 0), 1)), np.float32)
         rows, grows = self.domain.states_to_rows(states), self.domain.goals_to_rows(goals)
         step = self.nnet_batch_size or n
-        outs = [self._engine().heur_eval(rows[s:s + step], grows[s:s + step], self.nnet.out_dim) for s in range(0, n, step)]
+        od = self.nnet.out_dim * max(getattr(self.nnet, "act_depth", 0), 1)          # action-as-input: one value per action
+        outs = [self._engine().heur_eval(rows[s:s + step], grows[s:s + step], od) for s in range(0, n, step)]
         return np.concatenate(outs, axis=0)
 
 
@@ -107,4 +109,5 @@ class DeviceHeurQ(_DeviceHeur):
 def load_nnet_into_engine(eng: Any, nnet: Any) -> None:
     from deepxube_b200 import _lib
     blob, info = _lib.pack_state_dict(nnet.state_dict())
-    eng.load_weights(nnet.in_count, nnet.one_hot_depth, info["res_dim"], info["num_blocks"], info["out_dim"], info["batch_norm"], blob)
+    eng.load_weights(nnet.in_count, nnet.one_hot_depth, info["res_dim"], info["num_blocks"], info["out_dim"], info["batch_norm"], blob,
+                     act_depth=getattr(nnet, "act_depth", 0))

@@ -98,6 +98,7 @@ struct InstArrays {
 
 struct NetDev {
     int in_count, depth, H, Hp, num_blocks, out_dim, in_dim, in_dim_p;
+    int act_depth;   // > 0: action-as-input Q network -- rows are (node, action) pairs, feature in_dim - act_depth + a is the action
     // fp32 parameters (BN folded)
     float* w0t;      // [in_dim, Hp]  first layer, transposed (row = one-hot feature)
     float* b0;       // [Hp]
@@ -271,5 +272,7 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
                       const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
 int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
                        const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);
+int dx_launch_act_begin(cudaStream_t s, const NetDev& net, Ctl* ctl);
+int dx_launch_act_end(cudaStream_t s, const NetDev& net, Ctl* ctl, const float* q, float* out_h, int absolute, long long max_nodes);
 bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d);
 int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out);

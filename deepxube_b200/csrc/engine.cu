@@ -1053,8 +1053,9 @@ extern "C" int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const floa
     DX_CUDA(cudaSetDevice(e->cfg.device));
     if (desc->in_count != e->dom.in_count || desc->one_hot_depth != e->dom.depth)
         DX_FAIL(DX_ERR_ARG, "network input shape does not match the domain's NN input");
-    const int want_out = e->is_q ? e->A : 1;
-    if (desc->out_dim != want_out) DX_FAIL(DX_ERR_ARG, "network out_dim must be 1 for graph_v and num_actions for graph_q");
+    const int want_out = (e->is_q && desc->act_depth == 0) ? e->A : 1;       // an action-as-input Q network has one output
+    if (desc->out_dim != want_out)
+        DX_FAIL(DX_ERR_ARG, "network out_dim must be 1 for graph_v / action-as-input networks and num_actions for graph_q");
     DX_TRY(dx_upload_net(e, desc, blob, n_floats));
     e->weights_loaded = true;
     return DX_OK;
@@ -1068,8 +1069,9 @@ extern "C" int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* 
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     if (n == 0) return DX_OK;
-    const int SP = e->SP, S = e->S, od = e->net.out_dim;
-    const long long chunk = std::min<long long>(e->mlp.cap, 1 << 16);
+    const int amul = e->net.act_depth > 0 ? e->net.act_depth : 1;
+    const int SP = e->SP, S = e->S, od = e->net.out_dim * amul;        // action-as-input: one value per (state, action)
+    const long long chunk = std::min<long long>(e->mlp.cap / amul, 1 << 16);
     DX_TRY(ensure_stage(e, (size_t)chunk * SP * 2 + (size_t)chunk * od * 4 + 64));
     uint8_t* d_rows = e->d_stage;
     uint8_t* d_goals = e->d_stage + (size_t)chunk * SP;
@@ -1117,11 +1119,12 @@ extern "C" int dx_row_bytes(dx_engine* e, int32_t* row_bytes) {
 extern "C" int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_total) {
     if (!e || !ms_total || n < 1 || reps < 1) DX_FAIL(DX_ERR_ARG, "bad argument");
     if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
-    if (n > (int64_t)e->max_nodes || n > e->mlp.cap) DX_FAIL(DX_ERR_ARG, "n exceeds node store / activation capacity");
+    if (n > (int64_t)e->max_nodes || n * (e->net.act_depth > 0 ? e->net.act_depth : 1) > e->mlp.cap)
+        DX_FAIL(DX_ERR_ARG, "n exceeds node store / activation capacity");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_TRY(sync_ctl(e));
     const Ctl saved = *e->h_ctl;
-    DX_TRY(ensure_stage(e, (size_t)n * e->net.out_dim * 4 + 64));
+    DX_TRY(ensure_stage(e, (size_t)n * e->net.out_dim * (e->net.act_depth > 0 ? e->net.act_depth : 1) * 4 + 64));
     float* d_out = (float*)e->d_stage;
     k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, 0, (uint32_t)n);
     cudaEvent_t a, b;
@@ -1189,7 +1192,10 @@ __global__ void k_f32_to_bf16(const float* __restrict__ src, uint16_t* __restric
 int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats) {
     if (e->weights_loaded) DX_FAIL(DX_ERR_STATE, "weights already loaded for this engine");
     const int H = desc->res_dim, nb = desc->num_blocks, od = desc->out_dim, bn = desc->batch_norm;
-    const int in_dim = desc->in_count * desc->one_hot_depth;
+    const int act_depth = desc->act_depth;
+    if (act_depth < 0 || (act_depth > 0 && (od != 1 || !e->is_q || act_depth != e->A)))
+        DX_FAIL(DX_ERR_ARG, "action-as-input network: needs a graph_q engine, out_dim 1 and act_depth == number of actions");
+    const int in_dim = desc->in_count * desc->one_hot_depth + act_depth;
     if (H < 1 || nb < 0 || od < 1 || od > DX_MAX_OUT || desc->in_count > 256) DX_FAIL(DX_ERR_ARG, "unsupported network shape");
     const int64_t per_layer = (int64_t)H * H + H + (bn ? 4 * H : 0);
     const int64_t want = (int64_t)H * in_dim + H + 2 * nb * per_layer + (int64_t)od * H + od;
@@ -1198,7 +1204,7 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     const int in_dim_p = ((in_dim + 63) / 64) * 64;
     NetDev& net = e->net;
     net.in_count = desc->in_count; net.depth = desc->one_hot_depth; net.H = H; net.Hp = Hp; net.num_blocks = nb;
-    net.out_dim = od; net.in_dim = in_dim; net.in_dim_p = in_dim_p;
+    net.out_dim = od; net.in_dim = in_dim; net.in_dim_p = in_dim_p; net.act_depth = act_depth;
     std::vector<float> w0t((size_t)in_dim * Hp, 0.f), b0(Hp, 0.f), w0p((size_t)Hp * in_dim_p, 0.f);
     std::vector<float> wres((size_t)2 * nb * Hp * Hp, 0.f), bres((size_t)2 * nb * Hp, 0.f), wout((size_t)od * Hp, 0.f), bout(od, 0.f);
     const float* p = blob;
@@ -1314,7 +1320,8 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
         net.wres_bf16 = wrb;
     }
     // activation buffers
-    const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst);
+    // rows one evaluation can hold: popped nodes (Q*) or children (A*); x actions for an action-as-input network
+    const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst) * (act_depth > 0 ? act_depth : 1);
     e->mlp.cap = cap;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
         int fill = 0;

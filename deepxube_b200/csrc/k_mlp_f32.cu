@@ -21,17 +21,24 @@ __device__ __forceinline__ int nn_input_value(const DomainDev& d, const uint8_t*
 __global__ void __launch_bounds__(FL_THREADS)
 k_first_layer_f32(DomainDev d, NetDev net, const Ctl* __restrict__ ctl, const uint8_t* __restrict__ rows,
                   const uint8_t* __restrict__ goals, float* __restrict__ X) {
-    __shared__ int s_feat[FL_ROWS][256];     // in_count <= 256 (npuzzle.15 has 225)
-    __shared__ float s_mul[FL_ROWS][256];    // 1 for one-hot inputs; the input value itself when one_hot_depth == 1
+    __shared__ int s_feat[FL_ROWS][257];     // in_count <= 256 (npuzzle.15 has 225) + the action feature of heurq_in networks
+    __shared__ float s_mul[FL_ROWS][257];    // 1 for one-hot inputs; the input value itself when one_hot_depth == 1
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
-    const int Hp = net.Hp, ic = net.in_count;
+    const int Hp = net.Hp, ic0 = net.in_count, amul = net.act_depth > 0 ? net.act_depth : 1;
+    const int ic = ic0 + (net.act_depth > 0 ? 1 : 0);          // inputs per row incl. the action of a heurq_in network
     for (uint32_t base = blockIdx.x * FL_ROWS; base < n; base += gridDim.x * FL_ROWS) {
         const int nr = min((uint32_t)FL_ROWS, n - base);
         __syncthreads();
         for (int t = threadIdx.x; t < nr * ic; t += FL_THREADS) {
             const int r = t / ic, i = t % ic;
-            const uint8_t* row = rows + (size_t)(start + base + r) * d.SP;
+            // action-as-input networks: row (base + r) is node (base + r) / A with action (base + r) % A
+            const uint8_t* row = rows + (size_t)(start + (base + r) / amul) * d.SP;
+            if (i == ic0) {
+                s_feat[r][i] = (net.in_dim - amul + (int)((base + r) % amul)) * Hp;
+                s_mul[r][i] = 1.f;
+                continue;
+            }
             int v = nn_input_value(d, row, goals, i);
             if (net.depth > 1) {
                 v = min(v, net.depth - 1);                 // one_hot would raise on out-of-range input; clamp instead
@@ -155,7 +162,7 @@ k_out_layer(NetDev net, const Ctl* __restrict__ ctl, const float* __restrict__ X
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
     for (uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
         const float* x = X + (size_t)r * Hp;
-        const size_t oi = absolute ? (size_t)(start + r) : (size_t)r;
+        const size_t oi = absolute ? (size_t)start * (net.act_depth > 0 ? net.act_depth : 1) + r : (size_t)r;   // (node, action) rows
         float hmin = __int_as_float(0x7f800000);
         for (int o0 = 0; o0 < od; o0 += 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -187,10 +194,49 @@ int dx_launch_out_layer(cudaStream_t s, const NetDev& net, const Ctl* ctl, const
     return 1;
 }
 
+// action-as-input Q networks (heurq_in): the job's node count becomes a (node, action) row count for the duration of the
+// evaluation (factor > 0: multiply, < 0: divide back)
+__global__ void k_nn_scale_rows(Ctl* ctl, int factor) {
+    if (factor > 0) ctl->nn_n *= (uint32_t)factor;
+    else ctl->nn_n /= (uint32_t)(-factor);
+}
+
+// heuristic of a node = min over its per-action q-values (deepxube/base/pathfinding.py:722-744); ctl->nn_n holds ROWS here
+__global__ void k_act_hmin(const Ctl* __restrict__ ctl, int A, const float* __restrict__ q, float* __restrict__ out_h, int absolute) {
+    if (ctl->error) return;
+    const uint32_t nodes = ctl->nn_n / (uint32_t)A, start = ctl->nn_row_start;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < nodes; j += gridDim.x * blockDim.x) {
+        const size_t o = absolute ? (size_t)(start + j) : (size_t)j;
+        float h = __int_as_float(0x7f800000);
+        for (int a = 0; a < A; ++a) h = fminf(h, q[o * A + a]);
+        out_h[o] = h;
+    }
+}
+
+int dx_launch_act_begin(cudaStream_t s, const NetDev& net, Ctl* ctl) {
+    if (net.act_depth <= 0) return 0;
+    k_nn_scale_rows<<<1, 1, 0, s>>>(ctl, net.act_depth);
+    return 1;
+}
+
+int dx_launch_act_end(cudaStream_t s, const NetDev& net, Ctl* ctl, const float* q, float* out_h, int absolute, long long max_nodes) {
+    if (net.act_depth <= 0) return 0;
+    int launches = 1;
+    if (out_h) {
+        k_act_hmin<<<(int)min((long long)dx_div_up(max_nodes, 256), (long long)148 * 4), 256, 0, s>>>(ctl, net.act_depth, q, out_h, absolute);
+        ++launches;
+    }
+    k_nn_scale_rows<<<1, 1, 0, s>>>(ctl, -net.act_depth);
+    return launches;
+}
+
 int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, const MlpBufs& mb, const Ctl* ctl,
                       const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows) {
+    const long long max_nodes = max_rows;
+    const bool act = net.act_depth > 0;
+    if (act) max_rows *= net.act_depth;
     if (max_rows > mb.cap) max_rows = mb.cap;
-    int launches = 0;
+    int launches = dx_launch_act_begin(s, net, const_cast<Ctl*>(ctl));
     const int fl_blocks = (int)min((long long)dx_div_up(max_rows, FL_ROWS), (long long)148 * 8);
     k_first_layer_f32<<<fl_blocks, FL_THREADS, 0, s>>>(d, net, ctl, rows, goals, mb.x[0]);
     ++launches;
@@ -211,6 +257,8 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
         float* t = x; x = z; z = t;
         launches += 2;
     }
-    launches += dx_launch_out_layer(s, net, ctl, x, out_h, out_q, absolute, max_rows);
+    // action-as-input networks: the scalar outputs ARE the q-values, written flat [(node, action)] into the q array
+    launches += dx_launch_out_layer(s, net, ctl, x, act ? out_q : out_h, act ? nullptr : out_q, absolute, max_rows);
+    launches += dx_launch_act_end(s, net, const_cast<Ctl*>(ctl), out_q, out_h, absolute, max_nodes);
     return launches;
 }

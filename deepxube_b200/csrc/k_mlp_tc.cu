@@ -777,8 +777,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // ---------------------------------------------------------------------------------------------
 // bf16 one-hot input matrix [n, in_dim_p] (OneHot.forward, deepxube/pytorch/pytorch_models.py:15-24)
 // ones_col >= 0: columns ones_col .. ones_col + 2 are set to 1.0 (they multiply the folded bias columns of W0)
-__global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p, int ones_col, const Ctl* __restrict__ ctl,
-                              const uint8_t* __restrict__ rows, const uint8_t* __restrict__ goals,
+// act_depth > 0 (heurq_in): row r is node r / act_depth with action r % act_depth; column act_col0 + action is 1.0
+__global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p, int ones_col, int act_depth, int act_col0,
+                              const Ctl* __restrict__ ctl, const uint8_t* __restrict__ rows, const uint8_t* __restrict__ goals,
                               __nv_bfloat16* __restrict__ out) {
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
@@ -787,8 +788,13 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
     for (size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (size_t)gridDim.x * blockDim.x) {
         const uint32_t r = (uint32_t)(t / chunks);
         const int c0 = (int)(t % chunks) * 8;
-        const uint8_t* row = rows + (size_t)(start + r) * d.SP;
+        const uint32_t node = act_depth > 0 ? r / (uint32_t)act_depth : r;
+        const uint8_t* row = rows + (size_t)(start + node) * d.SP;
         uint32_t w[4] = {0u, 0u, 0u, 0u};
+        if (act_depth > 0) {
+            const int f = act_col0 + (int)(r % (uint32_t)act_depth) - c0;
+            if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;
+        }
         const int i_lo = c0 / depth, i_hi = min(in_count - 1, (c0 + 7) / depth);
         for (int i = i_lo; i <= i_hi; ++i) {
             int v;
@@ -829,7 +835,7 @@ k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* _
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
     for (uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
         const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(X + (size_t)r * Hp);
-        const size_t oi = absolute ? (size_t)(start + r) : (size_t)r;
+        const size_t oi = absolute ? (size_t)start * (net.act_depth > 0 ? net.act_depth : 1) + r : (size_t)r;
         float hmin = __int_as_float(0x7f800000);
         for (int o0 = 0; o0 < od; o0 += 4) {
             float acc[4] = {0.f, 0.f, 0.f, 0.f};
@@ -871,7 +877,7 @@ k_out_final_bf16(NetDev net, const Ctl* __restrict__ ctl, const float* __restric
         float acc = 0.f;
         for (int p = 0; p < P; ++p) acc += partial[(size_t)p * (size_t)pstride + r];
         const float v = fmaxf(acc + b, 0.f);
-        const size_t oi = absolute ? (size_t)(start + r) : (size_t)r;
+        const size_t oi = absolute ? (size_t)start * (net.act_depth > 0 ? net.act_depth : 1) + r : (size_t)r;
         if (out_q) out_q[oi] = v;
         if (out_h) out_h[oi] = v;
     }
@@ -909,6 +915,7 @@ bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d) {
     const int b_bytes = (BN / 2) * TC_BK * 2, a_bytes = TC_BM * TC_BK * 2;
     const int ring_in = (5 * (a_bytes + b_bytes) - kb_in * a_bytes) / b_bytes;
     if (net.depth < 2) return false;          // depth-1 inputs are raw values, not one-hot codes: separate input kernel
+    if (net.act_depth > 0) return false;      // (node, action) rows: separate input kernel
     return kb_in <= 8 && ring_in >= 3 && net.in_count <= d.S && d.SP % 16 == 0 &&
            4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64;
 }
@@ -1066,8 +1073,15 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
                        const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows) {
     const TcPlan* p = (const TcPlan*)net.tc_plan;
     if (!p) { dx_set_error("NET_BF16 plan missing"); return 0; }
+    // action-as-input Q networks (heurq_in): one row per (node, action); the scalar outputs are the q-values
+    const bool act = net.act_depth > 0;
+    const long long max_nodes = max_rows;
+    if (act) max_rows *= net.act_depth;
     if (max_rows > mb.cap) max_rows = mb.cap;
-    int launches = 0;
+    int launches = dx_launch_act_begin(s, net, const_cast<Ctl*>(ctl));
+    float* const q_dst = out_q;
+    float* const h_dst = out_h;
+    if (act) { out_h = q_dst; out_q = nullptr; }
     const int oh_blocks = (int)min((long long)dx_div_up(max_rows * (net.in_dim_p / 8), 256), (long long)148 * 16);
     int ix = 0, iy = 1, iz = 2;
     const int Hp = net.Hp;
@@ -1083,7 +1097,8 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
         ++launches;
     } else {
-        k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, ctl, rows, goals, p->onehot);
+        k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, net.act_depth,
+                                                net.in_dim - net.act_depth, ctl, rows, goals, p->onehot);
         launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0);
         launches += 2;
     }
@@ -1120,6 +1135,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, Hp, out_h, out_q, absolute);
     }
     ++launches;
+    launches += dx_launch_act_end(s, net, const_cast<Ctl*>(ctl), q_dst, h_dst, absolute, max_nodes);
     return launches;
 }
 

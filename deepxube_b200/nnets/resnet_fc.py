@@ -29,9 +29,15 @@ class ResnetFCHeur:
         self.out_dim, self.q_fix = int(out_dim), bool(q_fix)
         self.res_dim, self.num_blocks, self.batch_norm = int(res_dim), int(num_blocks), bool(batch_norm)
         dims, depths = nnet_input.get_input_info()
-        assert len(dims) == 1 and len(depths) == 1, "flat one-hot input with a single block expected"
+        # one flat one-hot block, optionally followed by the action index of an action-as-input Q network
+        # (deepxube/nnets/resnet_fc.py:23-30: every input is one-hot encoded with its own depth and concatenated)
+        assert len(dims) == len(depths) and len(dims) in (1, 2), "flat one-hot input (+ one action input) expected"
         self.in_count, self.one_hot_depth = int(dims[0]), int(depths[0])
-        self.in_dim = self.in_count * self.one_hot_depth
+        self.act_depth = 0
+        if len(dims) == 2:
+            assert int(dims[1]) == 1 and not q_fix, "second input must be a single action index"
+            self.act_depth = int(depths[1])
+        self.in_dim = self.in_count * self.one_hot_depth + self.act_depth
         self._sd: Optional[Dict[str, np.ndarray]] = None
 
     # ---- weights -------------------------------------------------------------------------------------

@@ -4,7 +4,7 @@ from dataclasses import dataclass
 from typing import Any, Optional
 
 from deepxube_b200.base.domain import ActsEnumFixed, Domain
-from deepxube_b200.base.nnet_input import StateGoalActFixIn, StateGoalIn, get_nnet_input_from_arg, get_nnet_input_t
+from deepxube_b200.base.nnet_input import StateGoalActFixIn, StateGoalActIn, StateGoalIn, get_nnet_input_from_arg, get_nnet_input_t
 from deepxube_b200.base.pathfind_fns import (DeviceHeurQ, DeviceHeurV, HeurZerosQFn, HeurZerosVFn, PFNsHeurQ, PFNsHeurV)
 from deepxube_b200.factories.nnet_factory import deepxube_nnet_factory
 from deepxube_b200.factories.pathfind_fns_factory import deepxube_nnet_par_factory, pathfind_fns_factory
@@ -105,6 +105,30 @@ class HeurQNNetParFixOut(_HeurNNetPar):
 
     def _out_dim(self) -> int:
         return self.domain.get_num_acts()
+
+    def get_default_fn(self):
+        return HeurZerosQFn()
+
+    def get_nnet_fn(self, nnet: Any, batch_size: Optional[int], precision: Optional[str] = None):
+        return DeviceHeurQ(self.domain, nnet, precision, batch_size)
+
+
+@deepxube_nnet_par_factory.register_class("heurq_in")
+class HeurQNNetParIn(_HeurNNetPar):
+    """Action-as-input Q function (fns_core.py:99-133): the network takes (state, goal, action) and returns ONE value; it is
+    evaluated once per (state, action) -- every state repeated for each of its actions -- and the values are regrouped per
+    state.  On the device the (node, action) rows are never materialised: the input kernels read node r / A and set
+    the action feature r % A.  The engine needs a fixed action set (the reference accepts any Domain)."""
+    field_name = "heurq"
+    q_fix = False
+
+    @staticmethod
+    def domain_type():
+        return ActsEnumFixed
+
+    @staticmethod
+    def nnet_input_type():
+        return StateGoalActIn
 
     def get_default_fn(self):
         return HeurZerosQFn()

@@ -80,6 +80,9 @@ typedef struct dx_net_desc {
     int32_t num_blocks;      /* B                                                                        */
     int32_t out_dim;         /* 1 (heurv) or number of actions (heurq_fixout)                            */
     int32_t batch_norm;      /* 0 / 1                                                                    */
+    int32_t act_depth;       /* 0, or the number of actions for an action-as-input Q network (heurq_in,
+                                deepxube/pathfind_fns/fns_core.py:99-133): the action index is one more input with this
+                                one-hot depth, out_dim is 1 and the network runs once per (state, action)         */
 } dx_net_desc;
 
 /* Per-instance view, the fields of Instance / InstanceGraph the callers read

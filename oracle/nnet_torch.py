@@ -79,9 +79,11 @@ def random_state_dict(in_dim: int, res_dim: int, num_blocks: int, out_dim: int, 
 
 @torch.no_grad()
 def resnet_fc_forward(sd: Dict[str, torch.Tensor], x_int: np.ndarray, one_hot_depth: int,
-                      batch_size: Optional[int] = None) -> np.ndarray:
+                      batch_size: Optional[int] = None, act_depth: int = 0) -> np.ndarray:
     """x_int [N, D] integer inputs -> raw network output [N, out_dim] float32.
-    Chunked like nnet_batched (ref: deepxube/pytorch/nnet_utils.py:73-111)."""
+    Chunked like nnet_batched (ref: deepxube/pytorch/nnet_utils.py:73-111).
+    act_depth > 0: the LAST column of x_int is an action index with its own one-hot depth, encoded separately and
+    concatenated (ref: deepxube/nnets/resnet_fc.py:23-30, :49-51; action-as-input Q networks)."""
     sd = strip_module_prefix(sd)
     nb, bn = num_blocks_of(sd), has_bn(sd)
     n = x_int.shape[0]
@@ -89,11 +91,17 @@ def resnet_fc_forward(sd: Dict[str, torch.Tensor], x_int: np.ndarray, one_hot_de
     step = n if not batch_size else batch_size
     for s in range(0, max(n, 1), max(step, 1)):
         xi = torch.as_tensor(np.ascontiguousarray(x_int[s:s + step]))
+        xa = None
+        if act_depth > 0:
+            xa = F.one_hot(xi[:, -1].long(), act_depth).float()
+            xi = xi[:, :-1]
         if one_hot_depth > 1:
             x = F.one_hot(xi.long(), one_hot_depth).float()
             x = x.reshape(x.shape[0], -1)
         else:
             x = xi.float()
+        if xa is not None:
+            x = torch.cat([x, xa], dim=1)
         x = F.linear(x, sd["heur.0.weight"], sd["heur.0.bias"])
         for b in range(nb):
             res = x
@@ -124,4 +132,16 @@ def heurq_from_state_dict(sd: Dict[str, torch.Tensor], one_hot_depth: int, batch
     def fn(x_int: np.ndarray) -> np.ndarray:
         out = resnet_fc_forward(sd, x_int, one_hot_depth, batch_size)
         return np.maximum(out, 0).astype(np.float64)
+    return fn
+
+
+def heurq_in_from_state_dict(sd: Dict[str, torch.Tensor], one_hot_depth: int, num_actions: int, batch_size: Optional[int] = None):
+    """Action-as-input Q function (ref: deepxube/pathfind_fns/fns_core.py:99-133): every state is repeated once per action,
+    the action index is the extra input; returns fn(x_int [N, D]) -> float64 [N, A] (clipped at 0)."""
+    def fn(x_int: np.ndarray) -> np.ndarray:
+        n = x_int.shape[0]
+        rep = np.repeat(np.asarray(x_int, np.int64), num_actions, axis=0)
+        acts = np.tile(np.arange(num_actions, dtype=np.int64), n)[:, None]
+        out = resnet_fc_forward(sd, np.concatenate([rep, acts], axis=1), one_hot_depth, batch_size, act_depth=num_actions)
+        return np.maximum(out[:, 0], 0).astype(np.float64).reshape(n, num_actions)
     return fn

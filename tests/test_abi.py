@@ -36,7 +36,7 @@ def test_header_symbols_exported_and_bound(lib):
 def test_struct_sizes_match_header():
     from deepxube_b200 import _lib
     assert ctypes.sizeof(_lib.dx_config) == 4 * 8 + 8 * 2 + 4 * 8
-    assert ctypes.sizeof(_lib.dx_net_desc) == 24
+    assert ctypes.sizeof(_lib.dx_net_desc) == 28          # 7 x int32 (act_depth added for heurq_in networks)
     assert ctypes.sizeof(_lib.dx_inst_status) == 8 * 5 + 4 * 4
     assert ctypes.sizeof(_lib.dx_counters) == 64
 
@@ -47,6 +47,7 @@ def test_domain_info_is_host_side(lib):
     assert _lib.domain_info("npuzzle", 4) == (16, 4, 16, 16)
     assert _lib.domain_info("npuzzle", 5) == (25, 4, 25, 25)
     assert _lib.domain_info("grid", 7) == (2, 4, 4, 7)
+    assert _lib.domain_info("lightsout", 7) == (49, 49, 49, 1)
     with pytest.raises(_lib.DxError):
         _lib.domain_info("npuzzle", 16)
 

@@ -257,6 +257,36 @@ def test_lightsout_through_the_registries(fn, tag, q):
     pathfind.close()
 
 
+@pytest.mark.parametrize("domain_str,tag", [("cube3", "qin_cube3"), ("lightsout.5", "qin_lo5"), ("grid.7d", "qin_grid7")])
+def test_heurq_in_through_the_registries(domain_str, tag):
+    """`--fn heurq_in,resnet_fc...` (action-as-input Q network, fns_core.py:99-133) resolves to the `flat_sga` /
+    `grid_flat_in_actin` input, reproduces the reference's q-values and drives graph_q."""
+    z = gu.load("heurq_in")
+    dom, name = get_domain_from_arg(domain_str)
+    sd = gu.state_dict_np(tag)
+    h, nb = sd["heur.0.weight"].shape[0], sum(1 for k in sd if k.endswith("layers.0.0.weight"))
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [f"heurq_in,resnet_fc.{h}H_{nb}B_bn"])
+    assert isinstance(pfns, PFNsHeurQ) and pfns.heurq.nnet.act_depth == dom.get_num_acts() and pfns.heurq.nnet.out_dim == 1
+    pfns.heurq.nnet.load_state_dict(sd)
+    states = dom.rows_to_states(z[tag + "_states"])
+    if domain_str.startswith("grid"):
+        from deepxube_b200.domains.grid import GridGoal
+        goals = [GridGoal(int(r[0]), int(r[1])) for r in z[tag + "_goals"]]
+    else:
+        goals = dom.sample_goalstate_goal_pairs(len(states))[1]
+    q = np.array(pfns.heurq(states, goals, dom.get_state_actions(states), [None] * len(states)))
+    np.testing.assert_allclose(q, z[tag + "_out"], rtol=0, atol=2e-4)
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.20B_0.7W")
+    assert pname == "graph_q"
+    random.seed(5)
+    st, gl = dom.sample_problem_instances([2, 5, 9])
+    pathfind.add_instances(pathfind.make_instances(st, gl))
+    for _ in range(6):
+        pathfind.step()
+    assert all(i.num_nodes_generated > 0 for i in pathfind.instances)
+    pathfind.close()
+
+
 @pytest.mark.parametrize("out_dim", [1, 12])
 def test_bf16_odd_row_counts(out_dim):
     """Row counts around the 128 / 256-row tile and CTA-pair boundaries (1, 127, 129, 255, 257, 1000 states): every row of

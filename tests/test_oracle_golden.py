@@ -53,6 +53,17 @@ def test_lightsout_nnet_matches_reference(tag, q):
     np.testing.assert_allclose(fn(z[tag + "_states"].astype(np.int64)), z[tag + "_out"], rtol=0, atol=2e-5)
 
 
+@pytest.mark.parametrize("tag,dname,dim", [("qin_cube3", "cube3", 0), ("qin_lo5", "lightsout", 5), ("qin_grid7", "grid", 7)])
+def test_heurq_in_nnet_matches_reference(tag, dname, dim):
+    """action-as-input Q networks: one forward per (state, action), the action index one-hot encoded with depth A"""
+    from oracle.nnet_torch import heurq_in_from_state_dict
+    z = gu.load("heurq_in")
+    dom = OracleDomain(dname, dim)
+    fn = heurq_in_from_state_dict(gu.state_dict_torch(tag), dom.input_info()[1], dom.num_actions)
+    x = dom.nnet_input(z[tag + "_states"], z[tag + "_goals"])
+    np.testing.assert_allclose(fn(x), z[tag + "_out"], rtol=0, atol=2e-5)
+
+
 def test_expand_edge_cases():
     dom = OracleDomain("cube3")
     assert dom.expand(np.zeros((0, 54), np.uint8)).shape == (0, 54)
@@ -94,6 +105,10 @@ def _heur_for(cfg, dom):
         return pseudo_v
     if heur == "q_pseudo":
         return make_pseudo_q(dom.num_actions)
+    if heur == "q_in_net":          # action-as-input Q network of the heurq_in trace
+        from oracle.nnet_torch import heurq_in_from_state_dict
+        f = heurq_in_from_state_dict(gu.state_dict_torch("qin_cube3"), dom.input_info()[1], dom.num_actions)
+        return lambda s, g: f(dom.nnet_input(s, g))
     prefix = {"v_net": "gridv", "q_net": "gridq"}[heur]
     depth = dom.input_info()[1]
     mk = heurq_from_state_dict if heur == "q_net" else heurv_from_state_dict

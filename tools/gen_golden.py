@@ -341,8 +341,48 @@ def gen_lightsout() -> None:
     print("lightsout.npz", len(out), "arrays")
 
 
+def gen_qin() -> None:
+    """heurq_in.npz: action-as-input Q networks (heurq_in, fns_core.py:99-133) evaluated by the reference -- random weights
+    with non-trivial BN statistics -- and one reference graph_q search driven by such a network."""
+    import tempfile
+    from oracle.nnet_torch import random_state_dict
+    out = {}
+    seed_all(5)
+    files = {}
+    for tag, dstr, dname, in_dim, h, nb in (("qin_cube3", "cube3", "cube3", 324 + 12, 64, 1), ("qin_lo5", "lightsout.5", "lightsout", 25 + 25, 96, 2),
+                                            ("qin_grid7", "grid.7d", "grid", 28 + 4, 48, 1)):
+        dom, _ = get_domain_from_arg(dstr)
+        fn = f"heurq_in,resnet_fc.{h}H_{nb}B_bn"
+        sd = random_state_dict(in_dim, h, nb, 1, batch_norm=True, seed=11, randomize_bn=True)
+        tf = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
+        torch.save(sd, tf.name)
+        files[tag] = (fn, tf.name)
+        st, goals = dom.sample_problem_instances(list(np.random.randint(0, 30, size=48)))
+        _, vals = ref_nnet_raw(dom, dname, fn, tf.name, st, goals)
+        out.update(sd_to_np(sd, tag + "/"))
+        out[tag + "_states"], out[tag + "_goals"], out[tag + "_out"] = states_np(st), goals_np(goals), vals
+        print(tag, vals.shape)
+
+    seed_all(6)
+    domain, dname = get_domain_from_arg("cube3")
+    states, goals = domain.sample_problem_instances([3, 20, 50])
+    fn, f = files["qin_cube3"]
+    pfns, _ = get_path_fns_nnet_par_dict(domain, dname, [fn], torch.device("cpu"), nnet_files=[f])
+    res = run_trace(domain, pfns, "graph.30B_0.7W", states, goals, 8)
+    tag = "qin_cube3_trace"
+    out[tag + "/states"], out[tag + "/goals"] = states_np(states), goals_np(goals)
+    out[tag + "/cfg"] = np.array(["cube3", "graph.30B_0.7W", "q_in_net", fn])
+    for k, v in res.items():
+        out[tag + "/" + k] = v
+    print(tag, res["pathfind_name"], "steps", res["itr"].shape[0], "cost", res["path_cost"], "gen", res["gen"][-1])
+    np.savez_compressed(os.path.join(OUT, "heurq_in.npz"), **out)
+    print("heurq_in.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin"]
+    if "qin" in which:
+        gen_qin()
     if "lightsout" in which:
         gen_lightsout()
     if "domains" in which:

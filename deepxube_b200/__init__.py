@@ -11,4 +11,4 @@ from . import domains  # noqa: F401,E402
 from .domains import cube3, grid, lightsout, npuzzle  # noqa: F401,E402
 from .nnets import resnet_fc  # noqa: F401,E402
 from .pathfind_fns import fns_core  # noqa: F401,E402
-from .pathfinding import graph_search  # noqa: F401,E402
+from .pathfinding import graph_search, beam_search  # noqa: F401,E402

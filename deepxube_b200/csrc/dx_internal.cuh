@@ -221,7 +221,7 @@ int dx_launch_scan_u32(cudaStream_t s, uint32_t* data, int n, const uint32_t* sk
 // k_open.cu
 int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                    uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
-                   uint32_t max_pop, uint32_t max_open, int kept_is_total = 0);
+                   uint32_t max_pop, uint32_t max_open, int kept_is_total = 0, int beam = 0);
 
 // k_hda.cu (hash-distributed single search)
 int dx_launch_hda_bucket(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortBufs& sb, const ScanTemp& t,
@@ -250,7 +250,7 @@ int dx_launch_hda_reduce(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const u
                          int A, int world, const double* all, double* summary);
 uint32_t dx_hda_owner_host(const uint8_t* row, int SP, uint32_t world);
 int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
-                        const uint32_t* new_inst, const SortBufs& sb, int max_n);
+                        const uint32_t* new_inst, const SortBufs& sb, int max_n, int beam = 0);
 int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
                           const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
                           const SortBufs& sb, int A, int max_pop);
@@ -259,9 +259,11 @@ int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp&
 int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
-                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles);
+                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open = 1);
+// gen_mode: 0 graph_v (A children per popped node), 1 graph_q (one node per popped edge), 2 beam_v (as 0, finished on a goal)
 int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
                        int A, int gen_mode);
+int dx_launch_beam_keep(cudaStream_t s, const Ctl* ctl, const float* child_g, uint8_t* child_flags, int max_children);
 
 // k_mlp_f32.cu / k_mlp_tc.cu
 // rows: [*, SP] row array; the job is ctl->nn_row_start / nn_n.  out_h (nullable) <- max(out0,0) (V) or min_a q (Q);

@@ -181,6 +181,7 @@ struct dx_engine {
     std::vector<uint8_t> table_h;
     cudaStream_t stream = nullptr;
     bool is_q = false;
+    bool is_beam = false;              // beam_v: graph_v pipeline without CLOSED and without a persistent OPEN
     int A = 0, SP = 0, S = 0;
     uint32_t max_nodes = 0, max_open = 0, max_pop = 0, max_children = 0, max_sort = 0;
     int max_inst = 0;
@@ -398,7 +399,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (!cfg || !out) DX_FAIL(DX_ERR_ARG, "null argument");
     if (cfg->max_instances < 1 || cfg->max_pop_total < 1 || cfg->max_nodes < 2) DX_FAIL(DX_ERR_ARG, "capacities must be positive");
     if (cfg->max_nodes >= 0x7FFFFFF0ll) DX_FAIL(DX_ERR_ARG, "max_nodes must be < 2^31");
-    if (cfg->algo != DX_ALGO_GRAPH_V && cfg->algo != DX_ALGO_GRAPH_Q) DX_FAIL(DX_ERR_ARG, "unknown algo");
+    if (cfg->algo != DX_ALGO_GRAPH_V && cfg->algo != DX_ALGO_GRAPH_Q && cfg->algo != DX_ALGO_BEAM_V) DX_FAIL(DX_ERR_ARG, "unknown algo");
     if (cfg->heur_mode < DX_HEUR_ZERO || cfg->heur_mode > DX_HEUR_NET_BF16) DX_FAIL(DX_ERR_ARG, "unknown heur_mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -410,6 +411,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     int r = make_domain_host(cfg->domain, cfg->domain_dim, &e->dom, &e->table_h);
     if (r < 0) { delete e; return r; }
     e->is_q = cfg->algo == DX_ALGO_GRAPH_Q;
+    e->is_beam = cfg->algo == DX_ALGO_BEAM_V;
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
@@ -625,9 +627,12 @@ static int step_v_a(dx_engine* e) {
                                           e->pop_solved, e->max_pop);
     stage_end(e);
     stage_begin(e, ST_CLOSED);
-    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
-                                           e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
-                                           e->max_children, e->A);
+    if (e->is_beam)
+        e->launches += dx_launch_beam_keep(s, e->d_ctl, e->child_g, e->child_flags, e->max_children);
+    else
+        e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
+                                               e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                               e->max_children, e->A);
     stage_end(e);
     stage_begin(e, ST_SCATTER);
     e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
@@ -645,18 +650,19 @@ static int step_v_b(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity, q = p ^ 1;
     stage_begin(e, ST_SORT);
+    const int beam = e->is_beam ? 1 : 0;
     e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
-                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open);
-    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort);
+                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open, 0, beam);
+    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort, beam);
     e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     stage_end(e);
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
     e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
-                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles);
+                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
     stage_end(e);
     stage_begin(e, ST_BOOK);
-    e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, 0);
+    e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, beam ? 2 : 0);
     stage_end(e);
     e->parity = q;
     return DX_OK;
@@ -1353,7 +1359,7 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
 extern "C" int dx_hda_config(dx_engine* e, int32_t rank, int32_t world) {
     if (!e) DX_FAIL(DX_ERR_ARG, "null engine");
     if (world < 1 || world > 16 || rank < 0 || rank >= world) DX_FAIL(DX_ERR_ARG, "bad rank / world (world <= 16)");
-    if (e->is_q) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode is implemented for graph_v");
+    if (e->is_q || e->is_beam) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode is implemented for graph_v");
     if (e->cfg.heur_mode == DX_HEUR_HOST) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode needs a device heuristic");
     if (e->n_inst != 0) DX_FAIL(DX_ERR_STATE, "dx_hda_config must precede dx_hda_add_instance");
     if (e->max_nodes >= (1u << 28)) DX_FAIL(DX_ERR_ARG, "HDA* mode: max_nodes must be < 2^28 per rank (global node id = rank << 28 | id)");

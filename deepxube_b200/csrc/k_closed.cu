@@ -229,3 +229,19 @@ int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, 
     k_closed_commit<<<blocks, 256, 0, s>>>(c, ctl, node_g, item_node, child_slot, child_flags);
     return 1;
 }
+
+// Beam search has no CLOSED list (InstanceNodeBeam.filter_expanded_nodes returns every child, beam_search.py:108-109):
+// every child of an active instance is kept (flag 1, never the "commits CLOSED" flag 2).
+__global__ void k_beam_keep(const Ctl* __restrict__ ctl, const float* __restrict__ child_g, uint8_t* __restrict__ child_flags) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
+        const float g = child_g[ci];
+        child_flags[ci] = (g == g) ? 1 : 0;          // NaN g = child of a finished instance
+    }
+}
+
+int dx_launch_beam_keep(cudaStream_t s, const Ctl* ctl, const float* child_g, uint8_t* child_flags, int max_children) {
+    k_beam_keep<<<min(dx_div_up(max_children, 256), 148 * 8), 256, 0, s>>>(ctl, child_g, child_flags);
+    return 1;
+}

@@ -29,7 +29,7 @@ static_assert(OPEN_THREADS * ITEMS == DX_SORT_TILE, "tile size");
 __global__ void __launch_bounds__(1024)
 k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
        uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
-       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open, int kept_is_total) {
+       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open, int kept_is_total, int beam) {
     __shared__ uint32_t s_tot[4][1024];
     if (ctl->error) return;
     const int I = ctl->n_inst;
@@ -47,8 +47,9 @@ k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix
         const uint32_t k = act ? min((uint32_t)ia.batch[i], t) : 0;
         ia.m_new[i] = m;
         ia.k_pop[i] = k;
-        ia.n_open[i] = t - k;
-        sm += m; sk += k; sn += t - k; st += (t + DX_SORT_TILE - 1) / DX_SORT_TILE;
+        // beam search keeps nothing but the selected nodes (beam_search.py:113-115): OPEN stays empty
+        ia.n_open[i] = beam ? 0u : t - k;
+        sm += m; sk += k; sn += ia.n_open[i]; st += (t + DX_SORT_TILE - 1) / DX_SORT_TILE;
     }
     s_tot[0][threadIdx.x] = sm; s_tot[1][threadIdx.x] = sk; s_tot[2][threadIdx.x] = sn; s_tot[3][threadIdx.x] = st;
     __syncthreads();
@@ -65,15 +66,16 @@ k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix
     for (int i = lo; i < hi; ++i) {
         ia.batch_off[i] = om; pop_off_next[i] = ok; open_off_next[i] = on; ia.tile_off[i] = ot;
         const uint32_t m = ia.m_new[i], k = ia.k_pop[i], n = ia.n_open[i];
-        om += m; ok += k; on += n; ot += (n + k + DX_SORT_TILE - 1) / DX_SORT_TILE;
+        const uint32_t t = beam ? m : n + k;          // elements the merge of this instance walks
+        om += m; ok += k; on += n; ot += (t + DX_SORT_TILE - 1) / DX_SORT_TILE;
     }
 }
 
 int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                    uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int child_mult, int push_mult,
-                   uint32_t max_pop, uint32_t max_open, int kept_is_total) {
+                   uint32_t max_pop, uint32_t max_open, int kept_is_total, int beam) {
     k_plan<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, child_mult,
-                              push_mult, max_pop, max_open, kept_is_total);
+                              push_mult, max_pop, max_open, kept_is_total, beam);
     return 1;
 }
 
@@ -85,13 +87,16 @@ __device__ __forceinline__ unsigned long long f_key(double w, float g, float h) 
 }
 
 // A*: batch element k is new node (node_base + k).
+// beam: the selection cost of a child is parent_t_cost + heuristic = 1.0 + h (beam_search.py:183-187; the reference takes
+// the beam_size LARGEST logits = -(cost), i.e. the smallest costs)
 __global__ void k_make_keys_v(const Ctl* __restrict__ ctl, InstArrays ia, const float* __restrict__ node_g,
-                              const float* __restrict__ node_h, const uint32_t* __restrict__ new_inst, SortBufs sb) {
+                              const float* __restrict__ node_h, const uint32_t* __restrict__ new_inst, SortBufs sb, int beam) {
     if (ctl->error) return;
     const uint32_t n = ctl->sort_n, base = ctl->node_base;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t id = base + k, inst = new_inst[k];
-        sb.key[0][k] = f_key(ia.weight[inst], node_g[id], node_h[id]);
+        sb.key[0][k] = beam ? (unsigned long long)__double_as_longlong(__dadd_rn(1.0, (double)node_h[id]))
+                            : f_key(ia.weight[inst], node_g[id], node_h[id]);
         sb.inst[0][k] = inst;
         sb.val[0][k] = id;
     }
@@ -117,9 +122,9 @@ __global__ void k_make_keys_q(const Ctl* __restrict__ ctl, InstArrays ia, const 
 }
 
 int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_h,
-                        const uint32_t* new_inst, const SortBufs& sb, int max_n) {
+                        const uint32_t* new_inst, const SortBufs& sb, int max_n, int beam) {
     int blocks = min(dx_div_up(max_n, 256), 148 * 8);
-    k_make_keys_v<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_h, new_inst, sb);
+    k_make_keys_v<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_h, new_inst, sb, beam);
     return 1;
 }
 
@@ -403,7 +408,7 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
         const uint32_t* __restrict__ open_val_cur, const uint32_t* __restrict__ open_off_cur,
         unsigned long long* __restrict__ open_key_next, uint32_t* __restrict__ open_val_next,
         const uint32_t* __restrict__ open_off_next, uint32_t* __restrict__ popped_next, uint32_t* __restrict__ popped_inst_next,
-        const uint32_t* __restrict__ pop_off_next) {
+        const uint32_t* __restrict__ pop_off_next, int keep_open) {
     __shared__ unsigned long long s_key[DX_SORT_TILE];
     __shared__ uint32_t s_val[DX_SORT_TILE];
     __shared__ uint32_t s_part[4];   // a0, a1, inst
@@ -461,7 +466,7 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
                 popped_next[pop_base + r] = val;
                 popped_inst_next[pop_base + r] = i;
                 if (r == 0) ia.f_first[i] = key;
-            } else {
+            } else if (keep_open) {            // (beam search drops what it does not select)
                 open_key_next[open_base + r - k] = key;
                 open_val_next[open_base + r - k] = val;
             }
@@ -472,10 +477,10 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
 int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
-                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles) {
+                    uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open) {
     int blocks = min(max_tiles, 148 * 4);
     k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
-                                            open_off_next, popped_next, popped_inst_next, pop_off_next);
+                                            open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open);
     return 1;
 }
 
@@ -501,7 +506,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         double lb = ia.lb[i];
         if (k > 0) lb = fmax(__longlong_as_double((long long)ia.f_first[i]), lb);   // graph_search.py:67-69
         ia.lb[i] = lb;
-        const unsigned long long g_add = gen_mode == 0 ? (unsigned long long)n_pop * A : (unsigned long long)k;
+        const unsigned long long g_add = gen_mode != 1 ? (unsigned long long)n_pop * A : (unsigned long long)k;
         ia.gen[i] += g_add;
         gen += g_add;
         ia.pop_seq_base[i] += n_pop;
@@ -511,7 +516,8 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         bool fin = false;
         if (ubk != DX_EMPTY64) {
             const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
-            fin = lb >= __dmul_rn(ia.weight[i], ub);                                // graph_search.py:44
+            fin = gen_mode == 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
+                                : lb >= __dmul_rn(ia.weight[i], ub);                // graph_search.py:44
         }
         fin = fin || (k == 0);                                                       // itr > 0 holds here (graph_search.py:45)
         ia.active[i] = fin ? 0 : 1;
@@ -524,7 +530,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         ctl->n_unfinished = s_unfinished;
         ctl->gen_total += s_gen;
         ctl->n_pop = pop_off_next[I];
-        ctl->n_children = pop_off_next[I] * (gen_mode == 0 ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
+        ctl->n_children = pop_off_next[I] * (gen_mode != 1 ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
         ctl->itr += 1;
         ctl->epoch += 1;
         ctl->node_base = ctl->node_count;

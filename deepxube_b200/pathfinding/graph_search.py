@@ -81,6 +81,7 @@ class InstanceGraph(Instance):
 
 class GraphSearch(PathFind):
     is_q = False
+    dx_algo: Optional[str] = None        # engine algorithm name; None: graph_q / graph_v from is_q
 
     def __init__(self, domain: Any, pathfind_fns: Any, batch_size: int = 1, weight: float = 1.0, eps: float = 0.0,
                  max_nodes: Optional[int] = None, max_instances: Optional[int] = None, precision: Optional[str] = None):
@@ -120,7 +121,7 @@ class GraphSearch(PathFind):
             pop_total += (self._max_instances - len(new_insts)) * self.batch_size_default
         max_nodes = self._max_nodes or max(1 << 18, min(pop_total * a * 256, 48_000_000))
         mode = self._heur_mode()
-        self._engine = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, "graph_q" if self.is_q else "graph_v", mode,
+        self._engine = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, self.dx_algo or ("graph_q" if self.is_q else "graph_v"), mode,
                                    max_instances=n_inst, max_pop_total=max(pop_total, n_inst), max_nodes=max_nodes)
         if mode in (_lib.DX_HEUR_NET_FP32, _lib.DX_HEUR_NET_BF16):
             load_nnet_into_engine(self._engine, self._fn.nnet)

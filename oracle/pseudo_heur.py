@@ -19,6 +19,20 @@ def pseudo_v(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
     return (((acc >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.float32) / np.float32(64.0)).astype(np.float64)
 
 
+def pseudo_v_fine(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
+    """[N,S] u8 -> float64 [N]: 24-bit values (multiples of 2^-18 in [0, 64), exact in float32) from an FNV-1a hash of the
+    row -- non-linear, so different states practically never tie (the linear _acc collides on states related by commuting
+    moves).  For selections whose choice among exact ties is implementation-defined (beam search's np.argpartition)."""
+    s = np.ascontiguousarray(states, dtype=np.uint8).astype(np.uint64)
+    h = np.full(s.shape[0], 2166136261, dtype=np.uint64)
+    for i in range(s.shape[1]):
+        h = ((h ^ s[:, i]) * np.uint64(16777619)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(15)
+    h = (h * np.uint64(2246822519)) & np.uint64(0xFFFFFFFF)
+    h ^= h >> np.uint64(13)
+    return ((h >> np.uint64(8)).astype(np.float64) / 262144.0)
+
+
 def make_pseudo_q(num_actions: int):
     def pseudo_q(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
         """[N,S] u8 -> float64 [N,A]"""

@@ -287,6 +287,32 @@ def test_heurq_in_through_the_registries(domain_str, tag):
     pathfind.close()
 
 
+def test_beam_v_through_the_registries():
+    """`--pathfind beam_v.<B>B` (beam_search.py:202-214) through the PathFind API with a device network: instances finish as
+    soon as a goal is popped, returned paths are valid, and nothing but the beam survives an iteration."""
+    random.seed(7)
+    dom, name = get_domain_from_arg("cube3")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.200H_2B_bn"])
+    pfns.heurv.nnet.load_state_dict(gu.state_dict_np("cube3v"))
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "beam_v.100B")
+    assert pname == "beam_v"
+    states, goals = dom.sample_problem_instances([3, 6, 9, 12])
+    pathfind.add_instances(pathfind.make_instances(states, goals))
+    for _ in range(40):
+        if all(i.finished() for i in pathfind.instances):
+            break
+        pathfind.step()
+    solved = 0
+    for inst, s0, g0 in zip(pathfind.instances, states, goals):
+        assert inst.frontier_size() <= 100
+        if inst.goal_node is not None:
+            _, actions, _, cost = get_path(inst.goal_node)
+            assert is_valid_soln(s0, g0, actions, dom) and cost == len(actions) and inst.finished()
+            solved += 1
+    assert solved >= 3          # the trained tutorial network solves short scrambles greedily
+    pathfind.close()
+
+
 @pytest.mark.parametrize("out_dim", [1, 12])
 def test_bf16_odd_row_counts(out_dim):
     """Row counts around the 128 / 256-row tile and CTA-pair boundaries (1, 127, 129, 255, 257, 1000 states): every row of

@@ -26,7 +26,7 @@ def test_name_args_split():
 
 def test_registries_hold_the_hot_path_names():
     assert set(domain_factory.get_all_class_names()) == {"cube3", "npuzzle", "grid", "lightsout"}
-    assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q"}
+    assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q", "beam_v"}
     with pytest.raises(ValueError, match="Unknown domain"):
         get_domain_from_arg("sokoban")
     with pytest.raises(ValueError, match="already registered"):
@@ -58,8 +58,12 @@ def test_graph_search_parser_and_defaults():
         get_pathfind_from_arg(dom, pfv, "graph.10X")
     with pytest.raises(ValueError, match="eps"):
         get_pathfind_from_arg(dom, pfv, "graph.10B_0.1E")
+    pb, pname, _ = get_pathfind_from_arg(dom, pfv, "beam.10B")           # prefix resolution, like `graph` (pathfinding_factory.py:27-66)
+    assert pname == "beam_v" and pb.beam_size_default == 10
     with pytest.raises(ValueError, match="Could not find any compatible"):
-        get_pathfind_from_arg(dom, pfv, "beam.10B")
+        get_pathfind_from_arg(dom, pfq, "beam.10B")                      # beam_q is not built
+    with pytest.raises(ValueError, match="Could not find any compatible"):
+        get_pathfind_from_arg(dom, pfv, "rollout.1.0T")
     with pytest.raises(TypeError):
         pathfinding_factory.get_type("graph_q")(dom, pfv)      # PFNsHeurV given to the Q* search
 
@@ -154,3 +158,19 @@ def test_problem_instance_generation_is_host_side():
             for a in al:
                 cur[i:i + 1] = o.next_state(cur[i:i + 1], np.array([dom.action_index(a)]))
         assert np.array_equal(dom.states_to_rows(walked), cur) and costs == [5.0, 3.0]
+
+
+def test_beam_v_parser_and_rejections():
+    """beam_v.<int>B (deepxube/pathfinding/beam_search.py:256-283); the sampling options are rejected, not ignored"""
+    from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+    from deepxube_b200.pathfind_fns.fns_core import PFNsHeurVC
+    dom, _ = get_domain_from_arg("cube3")
+    pfns = PFNsHeurVC(heurv=lambda s, g, c: [0.0] * len(s))
+    pathfind, name, _ = get_pathfind_from_arg(dom, pfns, "beam_v.25B")
+    assert name == "beam_v" and pathfind.beam_size_default == 25 and pathfind.dx_algo == "beam_v"
+    assert repr(pathfind) == "BeamSearchHeurNodeActsEnum(beam_size=25, temp=0.0, eps=0.0, rollout=False)"
+    for bad in ("beam_v.10B_1.0T", "beam_v.10B_0.1E"):
+        with pytest.raises(ValueError, match="not supported"):
+            get_pathfind_from_arg(dom, pfns, bad)
+    with pytest.raises(ValueError, match="Error parsing 10X"):
+        get_pathfind_from_arg(dom, pfns, "beam_v.10X")

@@ -5,7 +5,7 @@ import pytest
 
 from oracle.domains_np import OracleDomain, cube3_perm, npuzzle_swap_lut
 from oracle.nnet_torch import resnet_fc_forward, heurv_from_state_dict, heurq_from_state_dict
-from oracle.pseudo_heur import pseudo_v, make_pseudo_q
+from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q
 from oracle.search import OracleSearch, solve_one
 
 import golden_utils as gu
@@ -142,6 +142,36 @@ def test_search_trace_matches_reference(tag, kept_only):
                 assert np.isclose(inst.lb, c["lb"][t, j], rtol=1e-6, atol=0) and inst.ub == c["ub"][t, j], (t, j)
             else:
                 assert inst.lb == c["lb"][t, j] and inst.ub == c["ub"][t, j], (t, j)
+            assert inst.num_nodes_generated == c["gen"][t, j] and inst.itr == c["itr"][t, j], (t, j)
+            assert inst.finished() == c["finished"][t, j], (t, j)
+    off = 0
+    for j, inst in enumerate(insts):
+        assert inst.path_cost() == c["path_cost"][j]
+        ln = int(c["actions_len"][j])
+        if ln >= 0:
+            assert inst.get_path()[1] == c["actions_flat"][off: off + ln].tolist()
+            off += ln
+
+
+@pytest.mark.parametrize("tag", gu.beam_tags())
+def test_beam_v_matches_reference(tag):
+    """beam_v: the oracle calls the same np.argpartition as the reference, so even the order of the selected
+    nodes is reproduced."""
+    from oracle.beam import OracleBeamV
+    c = gu.beam_case(tag)
+    name, dim = gu.parse_domain(str(c["cfg"][0]))
+    b, _ = gu.parse_pathfind(str(c["cfg"][1]))
+    dom = OracleDomain(name, dim)
+    srch = OracleBeamV(dom, pseudo_v_fine, b)
+    insts = srch.add_instances(c["states"], c["goals"])
+    for t in range(c["itr"].shape[0]):
+        srch.step()
+        for j, inst in enumerate(insts):
+            ids = inst.nodes_curr
+            if t == 0 or not c["finished"][t - 1, j]:
+                assert len(ids) == c["n_next"][t, j], (t, j)
+                assert gu.digest(inst.store.state[ids], inst.store.g[ids]) == c["dig_next"][t, j], (t, j)
+                assert gu.sorted_digest(inst.store.state[ids], inst.store.g[ids]) == c["setdig_next"][t, j], (t, j)
             assert inst.num_nodes_generated == c["gen"][t, j] and inst.itr == c["itr"][t, j], (t, j)
             assert inst.finished() == c["finished"][t, j], (t, j)
     off = 0

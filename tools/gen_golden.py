@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle.ref_shim import import_reference, REF_ROOT  # noqa: E402
-from oracle.pseudo_heur import pseudo_v, make_pseudo_q  # noqa: E402
+from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q  # noqa: E402
 
 import_reference()
 from deepxube.factories.domain_factory import get_domain_from_arg  # noqa: E402
@@ -379,8 +379,68 @@ def gen_qin() -> None:
     print("heurq_in.npz", len(out), "arrays")
 
 
+def sorted_digest(states: np.ndarray, g: np.ndarray) -> int:
+    """order-insensitive digest of a node set: rows sorted lexicographically together with their path costs"""
+    if len(states) == 0:
+        return digest(states, g)
+    key = np.concatenate([np.asarray(states, np.uint8), np.asarray(g, np.float64)[:, None].astype(np.uint8)], axis=1)
+    order = np.lexsort(key.T[::-1])
+    return digest(np.asarray(states)[order], np.asarray(g)[order])
+
+
+def gen_beam() -> None:
+    """beam.npz: reference beam_v runs (beam_search.py) with the 24-bit pseudo heuristic (practically no exact cost ties between different states): per step the
+    selected nodes as an ordered digest (the oracle calls the same np.argpartition) and as a set digest (the engine orders
+    its selection by cost), counters, and the final solution."""
+    out = {}
+
+    def add(tag, domain_str, pathfind_str, steps_l, max_steps):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        pfns = wrap_v(pseudo_v_fine)
+        pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
+        insts = pathfind.make_instances(states, goals, None, True)
+        pathfind.add_instances(insts)
+        rec = {k: [] for k in ("n_next", "dig_next", "setdig_next", "gen", "itr", "finished")}
+        steps = 0
+        while (not all(i.finished() for i in insts)) and steps < max_steps:
+            pathfind.step()
+            steps += 1
+            for k in rec:
+                rec[k].append([])
+            for inst in insts:
+                nodes = inst._nodes_curr
+                st = states_np([x.state for x in nodes]) if nodes else np.zeros((0, 1), np.uint8)
+                g = np.array([x.path_cost for x in nodes], np.float64)
+                rec["n_next"][-1].append(len(nodes))
+                rec["dig_next"][-1].append(digest(st, g))
+                rec["setdig_next"][-1].append(sorted_digest(st, g))
+                rec["gen"][-1].append(inst.num_nodes_generated)
+                rec["itr"][-1].append(inst.itr)
+                rec["finished"][-1].append(inst.finished())
+        for k, v in rec.items():
+            out[tag + "/" + k] = np.array(v)
+        out[tag + "/states"], out[tag + "/goals"] = states_np(states), goals_np(goals)
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, "v_pseudo_fine", name])
+        out[tag + "/path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
+        acts = [[a.action for a in get_path(i.goal_node)[1]] if i.goal_node is not None else [] for i in insts]
+        out[tag + "/actions_flat"] = np.array([x for al in acts for x in al], np.int64)
+        out[tag + "/actions_len"] = np.array([len(al) if i.goal_node is not None else -1 for al, i in zip(acts, insts)], np.int64)
+        print(tag, name, "steps", steps, "cost", out[tag + "/path_cost"], "gen", rec["gen"][-1])
+
+    add("beam_cube3_20B", "cube3", "beam_v.20B", [2, 4, 30, 60], 12)
+    add("beam_cube3_500B", "cube3", "beam_v.500B", [5, 40], 8)
+    add("beam_np4_30B", "npuzzle.4", "beam_v.30B", [4, 20, 60], 25)
+    add("beam_lo5_10B", "lightsout.5", "beam_v.10B", [1, 3, 12], 10)
+    np.savez_compressed(os.path.join(OUT, "beam.npz"), **out)
+    print("beam.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam"]
+    if "beam" in which:
+        gen_beam()
     if "qin" in which:
         gen_qin()
     if "lightsout" in which:

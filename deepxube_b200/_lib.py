@@ -14,8 +14,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("DXB200_LIB") or os.path.join(HERE, "libdxb200.so")   # DXB200_LIB: A/B builds
 
 DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2, "lightsout": 3}
-DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q, DX_ALGO_BEAM_V = 0, 1, 2
-DX_ALGO = {"graph_v": DX_ALGO_GRAPH_V, "graph_q": DX_ALGO_GRAPH_Q, "beam_v": DX_ALGO_BEAM_V}
+DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q, DX_ALGO_BEAM_V, DX_ALGO_BEAM_Q = 0, 1, 2, 3
+DX_ALGO = {"graph_v": DX_ALGO_GRAPH_V, "graph_q": DX_ALGO_GRAPH_Q, "beam_v": DX_ALGO_BEAM_V, "beam_q": DX_ALGO_BEAM_Q}
 DX_HEUR_ZERO, DX_HEUR_HOST, DX_HEUR_NET_FP32, DX_HEUR_NET_BF16 = 0, 1, 2, 3
 STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book", "gemm_hidden", "gemm_input"]
 
@@ -186,7 +186,7 @@ class Engine:
         lib = load()
         self.domain, self.dim = domain, dim
         self.state_bytes, self.num_actions, self.in_count, self.depth = domain_info(domain, dim)
-        self.is_q = algo == "graph_q"
+        self.is_q = algo in ("graph_q", "beam_q")
         self.algo = algo
         self.heur_mode = heur_mode
         cfg = dx_config(device=current_device() if device is None else device, domain=DX_DOMAIN[domain], domain_dim=dim,

@@ -253,17 +253,19 @@ int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, co
                         const uint32_t* new_inst, const SortBufs& sb, int max_n, int beam = 0);
 int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
                           const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
-                          const SortBufs& sb, int A, int max_pop);
+                          const SortBufs& sb, int A, int max_pop, int beam = 0);
 #define DX_SMALL_SORT 2048     // batches up to this many entries are sorted by one block (k_sort_small)
 int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n, bool small = false);
 int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const SortBufs& sb,
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open = 1);
-// gen_mode: 0 graph_v (A children per popped node), 1 graph_q (one node per popped edge), 2 beam_v (as 0, finished on a goal)
+// gen_mode: 0 graph_v (A children per popped node), 1 graph_q (one node per popped edge), 2 beam_v / 3 beam_q (as 0 / 1,
+// finished on a goal)
 int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
                        int A, int gen_mode);
 int dx_launch_beam_keep(cudaStream_t s, const Ctl* ctl, const float* child_g, uint8_t* child_flags, int max_children);
+int dx_launch_beam_keep_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const uint32_t* popped_inst, uint8_t* flags, int max_items);
 
 // k_mlp_f32.cu / k_mlp_tc.cu
 // rows: [*, SP] row array; the job is ctl->nn_row_start / nn_n.  out_h (nullable) <- max(out0,0) (V) or min_a q (Q);

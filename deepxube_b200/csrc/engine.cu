@@ -399,7 +399,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (!cfg || !out) DX_FAIL(DX_ERR_ARG, "null argument");
     if (cfg->max_instances < 1 || cfg->max_pop_total < 1 || cfg->max_nodes < 2) DX_FAIL(DX_ERR_ARG, "capacities must be positive");
     if (cfg->max_nodes >= 0x7FFFFFF0ll) DX_FAIL(DX_ERR_ARG, "max_nodes must be < 2^31");
-    if (cfg->algo != DX_ALGO_GRAPH_V && cfg->algo != DX_ALGO_GRAPH_Q && cfg->algo != DX_ALGO_BEAM_V) DX_FAIL(DX_ERR_ARG, "unknown algo");
+    if (cfg->algo < DX_ALGO_GRAPH_V || cfg->algo > DX_ALGO_BEAM_Q) DX_FAIL(DX_ERR_ARG, "unknown algo");
     if (cfg->heur_mode < DX_HEUR_ZERO || cfg->heur_mode > DX_HEUR_NET_BF16) DX_FAIL(DX_ERR_ARG, "unknown heur_mode");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
@@ -410,8 +410,8 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->cfg = *cfg;
     int r = make_domain_host(cfg->domain, cfg->domain_dim, &e->dom, &e->table_h);
     if (r < 0) { delete e; return r; }
-    e->is_q = cfg->algo == DX_ALGO_GRAPH_Q;
-    e->is_beam = cfg->algo == DX_ALGO_BEAM_V;
+    e->is_q = cfg->algo == DX_ALGO_GRAPH_Q || cfg->algo == DX_ALGO_BEAM_Q;
+    e->is_beam = cfg->algo == DX_ALGO_BEAM_V || cfg->algo == DX_ALGO_BEAM_Q;
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
@@ -678,28 +678,33 @@ static int step_q_a(dx_engine* e) {
     e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
                                           e->pop_solved, e->max_pop);
     stage_end(e);
+    const int beam = e->is_beam ? 1 : 0;
     stage_begin(e, ST_CLOSED);
-    e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, nullptr, nullptr,
-                                           e->popped[p], e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
-                                           e->max_children, 1);
+    if (beam)
+        e->launches += dx_launch_beam_keep_q(s, e->d_ctl, e->ia, e->popped_inst[p], e->child_flags, e->max_children);
+    else
+        e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, nullptr, nullptr,
+                                               e->popped[p], e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
+                                               e->max_children, 1);
     stage_end(e);
     stage_begin(e, ST_SCATTER);
     e->launches += dx_launch_scan_flags(s, e->child_flags, e->child_prefix, &e->d_ctl->n_children, &e->d_ctl->n_kept,
                                         e->max_children, e->scan);
-    e->launches += dx_launch_closed_commit(s, e->closed, e->d_ctl, e->node_g, e->popped[p], e->child_slot, e->child_flags,
-                                           e->max_children);
+    if (!beam)
+        e->launches += dx_launch_closed_commit(s, e->closed, e->d_ctl, e->node_g, e->popped[p], e->child_slot, e->child_flags,
+                                               e->max_children);
     stage_end(e);
     stage_begin(e, ST_SORT);
     e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
-                                  e->open_off[q], 1, e->A, e->max_pop, e->max_open);
+                                  e->open_off[q], 1, e->A, e->max_pop, e->max_open, 0, beam);
     e->launches += dx_launch_make_keys_q(s, e->d_ctl, e->ia, e->node_g, e->node_q, e->popped[p], e->popped_inst[p],
-                                         e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop);
+                                         e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop, beam);
     e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     stage_end(e);
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
     e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
-                                   e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles);
+                                   e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
     k_after_merge_q<<<1, 1, 0, s>>>(e->d_ctl, e->pop_off[q], e->max_nodes);
     e->launches += 1;
     e->launches += dx_launch_expand_edges(s, e->dom, e->d_ctl, e->edge_tmp, e->popped[q], e->node_state, e->node_g,
@@ -711,7 +716,7 @@ static int step_q_a(dx_engine* e) {
 static int step_q_b(dx_engine* e) {
     const int p = e->parity, q = p ^ 1;
     stage_begin(e, ST_BOOK);
-    e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, 1);
+    e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, e->is_beam ? 3 : 1);
     stage_end(e);
     e->parity = q;
     return DX_OK;

@@ -245,3 +245,17 @@ int dx_launch_beam_keep(cudaStream_t s, const Ctl* ctl, const float* child_g, ui
     k_beam_keep<<<min(dx_div_up(max_children, 256), 148 * 8), 256, 0, s>>>(ctl, child_g, child_flags);
     return 1;
 }
+
+// beam_q: every popped node of an active instance keeps its edges (InstanceEdgeBeam.filter_popped_nodes, beam_search.py:122-123)
+__global__ void k_beam_keep_q(const Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ popped_inst,
+                              uint8_t* __restrict__ flags) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        flags[j] = ia.active[popped_inst[j]] ? 1 : 0;
+}
+
+int dx_launch_beam_keep_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const uint32_t* popped_inst, uint8_t* flags, int max_items) {
+    k_beam_keep_q<<<min(dx_div_up(max_items, 256), 148 * 8), 256, 0, s>>>(ctl, ia, popped_inst, flags);
+    return 1;
+}

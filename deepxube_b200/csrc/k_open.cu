@@ -107,7 +107,7 @@ __global__ void k_make_keys_v(const Ctl* __restrict__ ctl, InstArrays ia, const 
 __global__ void k_make_keys_q(const Ctl* __restrict__ ctl, InstArrays ia, const float* __restrict__ node_g,
                               const float* __restrict__ node_q, const uint32_t* __restrict__ popped,
                               const uint32_t* __restrict__ popped_inst, const uint8_t* __restrict__ flags,
-                              const uint32_t* __restrict__ prefix, SortBufs sb, int A) {
+                              const uint32_t* __restrict__ prefix, SortBufs sb, int A, int beam) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_pop * A;
     for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) {
@@ -115,7 +115,9 @@ __global__ void k_make_keys_q(const Ctl* __restrict__ ctl, InstArrays ia, const 
         if (!(flags[j] & 1)) continue;
         const uint32_t node = popped[j], inst = popped_inst[j];
         const uint32_t k = prefix[j] * A + a;
-        sb.key[0][k] = f_key(ia.weight[inst], node_g[node], node_q[(size_t)node * A + a]);
+        // beam_q ranks an edge by its q-value alone (logits = -q_val, beam_search.py:206-212)
+        sb.key[0][k] = beam ? (unsigned long long)__double_as_longlong((double)node_q[(size_t)node * A + a])
+                            : f_key(ia.weight[inst], node_g[node], node_q[(size_t)node * A + a]);
         sb.inst[0][k] = inst;
         sb.val[0][k] = node * A + a;
     }
@@ -130,9 +132,9 @@ int dx_launch_make_keys(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, co
 
 int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const float* node_g, const float* node_q,
                           const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* flags, const uint32_t* prefix,
-                          const SortBufs& sb, int A, int max_pop) {
+                          const SortBufs& sb, int A, int max_pop, int beam) {
     int blocks = min(dx_div_up((long long)max_pop * A, 256), 148 * 8);
-    k_make_keys_q<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_q, popped, popped_inst, flags, prefix, sb, A);
+    k_make_keys_q<<<blocks, 256, 0, s>>>(ctl, ia, node_g, node_q, popped, popped_inst, flags, prefix, sb, A, beam);
     return 1;
 }
 
@@ -506,7 +508,8 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         double lb = ia.lb[i];
         if (k > 0) lb = fmax(__longlong_as_double((long long)ia.f_first[i]), lb);   // graph_search.py:67-69
         ia.lb[i] = lb;
-        const unsigned long long g_add = gen_mode != 1 ? (unsigned long long)n_pop * A : (unsigned long long)k;
+        const bool edge_mode = gen_mode == 1 || gen_mode == 3;
+        const unsigned long long g_add = !edge_mode ? (unsigned long long)n_pop * A : (unsigned long long)k;
         ia.gen[i] += g_add;
         gen += g_add;
         ia.pop_seq_base[i] += n_pop;
@@ -516,7 +519,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         bool fin = false;
         if (ubk != DX_EMPTY64) {
             const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
-            fin = gen_mode == 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
+            fin = gen_mode >= 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
                                 : lb >= __dmul_rn(ia.weight[i], ub);                // graph_search.py:44
         }
         fin = fin || (k == 0);                                                       // itr > 0 holds here (graph_search.py:45)
@@ -530,7 +533,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         ctl->n_unfinished = s_unfinished;
         ctl->gen_total += s_gen;
         ctl->n_pop = pop_off_next[I];
-        ctl->n_children = pop_off_next[I] * (gen_mode != 1 ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
+        ctl->n_children = pop_off_next[I] * ((gen_mode == 0 || gen_mode == 2) ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
         ctl->itr += 1;
         ctl->epoch += 1;
         ctl->node_base = ctl->node_count;

@@ -1,10 +1,12 @@
-"""`beam_v`: beam search with a heuristic that prioritises nodes (deepxube/pathfinding/beam_search.py:17-125, 175-196, 202-214).
+"""`beam_v` / `beam_q`: beam search with a heuristic that prioritises nodes / edges
+(deepxube/pathfinding/beam_search.py:17-125, 175-229).
 
 Every iteration expands the current beam, evaluates ALL children (no CLOSED list), and keeps the `beam_size` children with
 the smallest `parent_t_cost + heuristic` (the reference takes the beam_size largest logits = -(cost) with
 np.argpartition); an instance is finished as soon as a popped node is a goal.  On the device this is the graph_v pipeline
 with the CLOSED filter replaced by keep-all, an OPEN list that is emptied every iteration and the selection key 1 + h
-(`DX_ALGO_BEAM_V`).  The selected nodes come out ordered by cost; the reference keeps np.argpartition's
+(`DX_ALGO_BEAM_V`); `beam_q` is the graph_q pipeline with the same three changes and the key q(node, action)
+(`DX_ALGO_BEAM_Q`): the beam_size edges with the smallest q-values are followed.  The selected nodes come out ordered by cost; the reference keeps np.argpartition's
 (implementation-defined) order, so the two agree as SETS; with exact cost ties between different states at the selection
 boundary the reference's pick is arbitrary and may differ.  temp > 0 (Boltzmann sampling) and eps > 0 (random
 replacements) are rejected, `rollout` is not offered.
@@ -14,7 +16,7 @@ from typing import Any, Dict, List, Optional, Type
 
 from deepxube_b200.base.domain import ActsEnum
 from deepxube_b200.base.factory import Parser
-from deepxube_b200.base.pathfind_fns import PFNsHeurV
+from deepxube_b200.base.pathfind_fns import PFNsHeurQ, PFNsHeurV
 from deepxube_b200.factories.pathfinding_factory import pathfinding_factory
 from deepxube_b200.pathfinding.graph_search import GraphSearch
 
@@ -58,6 +60,20 @@ class BeamSearchHeurNodeActsEnum(GraphSearch):
         return f"{type(self).__name__}(beam_size={self.beam_size_default}, temp=0.0, eps=0.0, rollout=False)"
 
 
+@pathfinding_factory.register_class("beam_q")
+class BeamSearchHeurEdgeActsEnum(BeamSearchHeurNodeActsEnum):
+    is_q = True
+    dx_algo = "beam_q"
+
+    @staticmethod
+    def pathfind_functions_type() -> Type:
+        return PFNsHeurQ
+
+    @staticmethod
+    def description() -> str:
+        return "Beam search with heuristic that prioritizes edges"
+
+
 @pathfinding_factory.register_parser("beam_v")
 class BeamSearchNodeParser(Parser):
     def parse(self, args_str: str) -> Dict[str, Any]:
@@ -78,3 +94,9 @@ class BeamSearchNodeParser(Parser):
     def help(self) -> str:
         return ("<int>B (beam size), <float>T (temperature; must be 0 here), <float>E (epsilon; must be 0 here).\n"
                 "E.g. beam_v.10B")
+
+
+@pathfinding_factory.register_parser("beam_q")
+class BeamSearchEdgeParser(BeamSearchNodeParser):
+    def help(self) -> str:
+        return super().help().replace("beam_v", "beam_q")

@@ -40,7 +40,8 @@ enum dx_domain { DX_DOMAIN_CUBE3 = 0, DX_DOMAIN_NPUZZLE = 1, DX_DOMAIN_GRID = 2,
 /* graph_v = batch weighted A* (deepxube/pathfinding/graph_search.py:182-194),
  * graph_q = batch weighted Q* (graph_search.py:197-209). */
 enum dx_algo { DX_ALGO_GRAPH_V = 0, DX_ALGO_GRAPH_Q = 1,
-               DX_ALGO_BEAM_V = 2 /* beam_v (deepxube/pathfinding/beam_search.py:106-125, 175-196): batch_size = beam size */ };
+               DX_ALGO_BEAM_V = 2 /* beam_v (deepxube/pathfinding/beam_search.py:106-125, 175-196): batch_size = beam size */,
+               DX_ALGO_BEAM_Q = 3 /* beam_q (beam_search.py:117-125, 199-214, 217-229): edges ranked by their q-value */ };
 
 /* Where heuristic values come from:
  *   ZERO      the all-zero default functions (deepxube/base/pathfind_fns.py:205-210, 235-243)

@@ -12,6 +12,10 @@ TEST INFRASTRUCTURE ONLY (see oracle/__init__.py).
       selection including its (implementation-defined) order and its choice among exact ties
   driver                               deepxube/base/pathfinding.py:338-400 (PathFindNode.step)
 
+  beam_q: InstanceEdgeBeam / BeamSearchHeurEdge     beam_search.py:117-125, 199-214; driver pathfinding.py:471-525
+      every (popped node, action) is an edge with cost q(node, action); the beam_size edges with the smallest q are followed
+      (logits = -q_val), their child nodes are generated, evaluated, and become the next popped nodes
+
 temp > 0 (Boltzmann sampling) and eps > 0 (random replacements) are not restated.
 """
 from typing import Callable, List, Optional
@@ -94,4 +98,65 @@ class OracleBeamV:
             else:
                 nxt = np.argpartition(logits, -inst.beam_size)[-inst.beam_size:].tolist()
             inst.nodes_curr = [int(ids[k]) for k in nxt]
+            inst.itr += 1
+
+
+class OracleBeamQ:
+    """heur_fn(states, goals) -> float64 [N, A] (q-values of every action)."""
+
+    def __init__(self, domain: OracleDomain, heur_fn: Optional[HeurFn], beam_size: int = 1):
+        self.domain, self.heur_fn, self.beam_size = domain, heur_fn, beam_size
+        self.instances: List[_BeamInst] = []
+
+    def _q(self, states: np.ndarray, goals: np.ndarray) -> np.ndarray:
+        if self.heur_fn is None:
+            return np.zeros((len(states), self.domain.num_actions))
+        return np.asarray(self.heur_fn(states, goals), np.float64)
+
+    def add_instances(self, states: np.ndarray, goals: np.ndarray) -> List[_BeamInst]:
+        new = [_BeamInst(self.domain, s, g, self.beam_size) for s, g in zip(states, goals)]
+        q = self._q(np.asarray(states), np.asarray(goals))          # root values (make_instances, beam_search.py:203-204)
+        for inst, qi in zip(new, q):
+            inst.q = {0: qi}
+        self.instances.extend(new)
+        return new
+
+    def all_finished(self) -> bool:
+        return all(i.finished() for i in self.instances)
+
+    def step(self) -> None:
+        dom, a = self.domain, self.domain.num_actions
+        insts = [i for i in self.instances if not i.finished()]
+        if not insts:
+            return
+        new_by_inst = []
+        for inst in insts:
+            popped = np.array(inst.nodes_curr, np.int64)
+            st, g = inst.store.state[popped], inst.store.g[popped]
+            solved = dom.is_solved(st, np.tile(inst.goal, (len(popped), 1)))
+            for n, ok in zip(popped.tolist(), solved.tolist()):
+                if ok and (inst.goal_node is None or inst.store.g[inst.goal_node] > inst.store.g[n]):
+                    inst.goal_node = n
+            # edges in (node, action) order with their q-values; select by the largest logits = -q
+            nodes_e = np.repeat(popped, a)
+            acts_e = np.tile(np.arange(a), len(popped))
+            logits = [-float(inst.q[int(n)][int(k)]) for n, k in zip(nodes_e, acts_e)]
+            if len(logits) <= inst.beam_size:
+                nxt = list(range(len(logits)))
+            else:
+                nxt = np.argpartition(logits, -inst.beam_size)[-inst.beam_size:].tolist()
+            pn, pa = nodes_e[nxt], acts_e[nxt]
+            children = dom.next_state(inst.store.state[pn], pa)
+            ids = inst.store.append(children, inst.store.g[pn] + 1.0, pn, pa)
+            inst.num_nodes_generated += len(ids)
+            new_by_inst.append(ids)
+        all_states = np.concatenate([inst.store.state[ids] for inst, ids in zip(insts, new_by_inst)])
+        all_goals = np.concatenate([np.tile(inst.goal, (len(ids), 1)) for inst, ids in zip(insts, new_by_inst)])
+        q = self._q(all_states, all_goals)
+        off = 0
+        for inst, ids in zip(insts, new_by_inst):
+            inst.q = {int(n): q[off + k] for k, n in enumerate(ids)}
+            inst.store.h[ids] = q[off: off + len(ids)].min(axis=1)
+            off += len(ids)
+            inst.nodes_curr = [int(n) for n in ids]
             inst.itr += 1

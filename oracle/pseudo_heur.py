@@ -41,3 +41,14 @@ def make_pseudo_q(num_actions: int):
         v = (acc[:, None] + a) & np.uint64(0xFFFFFFFF)
         return (((v >> np.uint64(20)) & np.uint64(0xFFF)).astype(np.float32) / np.float32(64.0)).astype(np.float64)
     return pseudo_q
+
+
+def make_pseudo_q_fine(num_actions: int):
+    """Tie-free counterpart of make_pseudo_q: q[state, a] = 24-bit FNV hash of (state bytes, a)."""
+    def pseudo_q_fine(states: np.ndarray, goals: np.ndarray = None) -> np.ndarray:
+        s = np.ascontiguousarray(states, dtype=np.uint8)
+        out = np.empty((s.shape[0], num_actions), np.float64)
+        for a in range(num_actions):
+            out[:, a] = pseudo_v_fine(np.concatenate([s, np.full((s.shape[0], 1), a, np.uint8)], axis=1))
+        return out
+    return pseudo_q_fine

@@ -26,7 +26,7 @@ def test_name_args_split():
 
 def test_registries_hold_the_hot_path_names():
     assert set(domain_factory.get_all_class_names()) == {"cube3", "npuzzle", "grid", "lightsout"}
-    assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q", "beam_v"}
+    assert set(pathfinding_factory.get_all_class_names()) == {"graph_v", "graph_q", "beam_v", "beam_q"}
     with pytest.raises(ValueError, match="Unknown domain"):
         get_domain_from_arg("sokoban")
     with pytest.raises(ValueError, match="already registered"):
@@ -60,8 +60,8 @@ def test_graph_search_parser_and_defaults():
         get_pathfind_from_arg(dom, pfv, "graph.10B_0.1E")
     pb, pname, _ = get_pathfind_from_arg(dom, pfv, "beam.10B")           # prefix resolution, like `graph` (pathfinding_factory.py:27-66)
     assert pname == "beam_v" and pb.beam_size_default == 10
-    with pytest.raises(ValueError, match="Could not find any compatible"):
-        get_pathfind_from_arg(dom, pfq, "beam.10B")                      # beam_q is not built
+    pb, pname, _ = get_pathfind_from_arg(dom, pfq, "beam.10B")
+    assert pname == "beam_q" and pb.is_q and pb.dx_algo == "beam_q"
     with pytest.raises(ValueError, match="Could not find any compatible"):
         get_pathfind_from_arg(dom, pfv, "rollout.1.0T")
     with pytest.raises(TypeError):

@@ -5,7 +5,7 @@ import pytest
 
 from oracle.domains_np import OracleDomain, cube3_perm, npuzzle_swap_lut
 from oracle.nnet_torch import resnet_fc_forward, heurv_from_state_dict, heurq_from_state_dict
-from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q
+from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q, make_pseudo_q_fine
 from oracle.search import OracleSearch, solve_one
 
 import golden_utils as gu
@@ -154,15 +154,16 @@ def test_search_trace_matches_reference(tag, kept_only):
 
 
 @pytest.mark.parametrize("tag", gu.beam_tags())
-def test_beam_v_matches_reference(tag):
-    """beam_v: the oracle calls the same np.argpartition as the reference, so even the order of the selected
-    nodes is reproduced."""
-    from oracle.beam import OracleBeamV
+def test_beam_search_matches_reference(tag):
+    """beam_v / beam_q: the oracle calls the same np.argpartition as the reference, so even the order of the
+    selected nodes is reproduced."""
+    from oracle.beam import OracleBeamQ, OracleBeamV
     c = gu.beam_case(tag)
     name, dim = gu.parse_domain(str(c["cfg"][0]))
     b, _ = gu.parse_pathfind(str(c["cfg"][1]))
     dom = OracleDomain(name, dim)
-    srch = OracleBeamV(dom, pseudo_v_fine, b)
+    is_q = str(c["cfg"][1]).startswith("beam_q")
+    srch = OracleBeamQ(dom, make_pseudo_q_fine(dom.num_actions), b) if is_q else OracleBeamV(dom, pseudo_v_fine, b)
     insts = srch.add_instances(c["states"], c["goals"])
     for t in range(c["itr"].shape[0]):
         srch.step()

@@ -1,5 +1,5 @@
 """GPU probe for the other BASELINE configs (C3 npuzzle A*, C4 cube3 Q*): nodes/s + stage breakdown.
-usage: config_probe.py <domain> <dim> <algo v|q> <B> <I> <iters> [bf16|fp32|zero]"""
+usage: config_probe.py <domain> <dim> <algo v|q|b (beam_v)> <B> <I> <iters> [bf16|fp32|zero]"""
 import sys, os, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -24,7 +24,7 @@ out_dim = A if is_q else 1
 sd = random_state_dict(in_count * depth, 1000, 4, out_dim, True, seed=0)
 blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
 per_iter_nodes = B if is_q else B * A
-eng = L.Engine(dname, dim, "graph_q" if is_q else "graph_v", MODE, max_instances=I, max_pop_total=I * B,
+eng = L.Engine(dname, dim, "graph_q" if is_q else ("beam_v" if algo == "b" else "graph_v"), MODE, max_instances=I, max_pop_total=I * B,
                max_nodes=int(I * per_iter_nodes * (ITERS + 2)) + 4096)
 if MODE != L.DX_HEUR_ZERO:
     eng.load_weights(in_count, depth, 1000, 4, out_dim, True, blob)
@@ -37,7 +37,7 @@ for rep in range(2):
     dt = time.time() - t0
     c = eng.counters()
     gen = sum(s.num_nodes_generated for s in eng.status())
-    print(f"{dname}.{dim} {'Q*' if is_q else 'A*'} B={B} I={I} {mode_s} rep{rep}: iters={done} gen={gen} evals={c.heur_evals} "
+    print(f"{dname}.{dim} {'Q*' if is_q else ('beam' if algo == 'b' else 'A*')} B={B} I={I} {mode_s} rep{rep}: iters={done} gen={gen} evals={c.heur_evals} "
           f"open={sum(s.open_size for s in eng.status())} time={dt:.3f}s nodes/s={gen/dt:.3e} dev_ms={eng.last_run_ms():.1f}", flush=True)
     if rep == 1:
         print("  stage ms:", {k: round(v, 2) for k, v in eng.stage_ms().items()}, flush=True)

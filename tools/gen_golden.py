@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, ROOT)
 
 from oracle.ref_shim import import_reference, REF_ROOT  # noqa: E402
-from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q  # noqa: E402
+from oracle.pseudo_heur import pseudo_v, pseudo_v_fine, make_pseudo_q, make_pseudo_q_fine  # noqa: E402
 
 import_reference()
 from deepxube.factories.domain_factory import get_domain_from_arg  # noqa: E402
@@ -398,7 +398,7 @@ def gen_beam() -> None:
         seed_all(zlib.crc32(tag.encode()) % 1000)
         domain, dname = get_domain_from_arg(domain_str)
         states, goals = domain.sample_problem_instances(list(steps_l))
-        pfns = wrap_v(pseudo_v_fine)
+        pfns = wrap_q(make_pseudo_q_fine(domain.get_num_acts())) if pathfind_str.startswith("beam_q") else wrap_v(pseudo_v_fine)
         pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
         insts = pathfind.make_instances(states, goals, None, True)
         pathfind.add_instances(insts)
@@ -433,6 +433,9 @@ def gen_beam() -> None:
     add("beam_cube3_500B", "cube3", "beam_v.500B", [5, 40], 8)
     add("beam_np4_30B", "npuzzle.4", "beam_v.30B", [4, 20, 60], 25)
     add("beam_lo5_10B", "lightsout.5", "beam_v.10B", [1, 3, 12], 10)
+    add("beamq_cube3_20B", "cube3", "beam_q.20B", [2, 4, 30, 60], 12)
+    add("beamq_cube3_400B", "cube3", "beam_q.400B", [5, 40], 8)
+    add("beamq_lo5_15B", "lightsout.5", "beam_q.15B", [1, 3, 12], 10)
     np.savez_compressed(os.path.join(OUT, "beam.npz"), **out)
     print("beam.npz", len(out), "arrays")
 

@@ -27,7 +27,7 @@ class DxError(RuntimeError):
 class dx_config(C.Structure):
     _fields_ = [("device", C.c_int32), ("domain", C.c_int32), ("domain_dim", C.c_int32), ("algo", C.c_int32),
                 ("heur_mode", C.c_int32), ("max_instances", C.c_int32), ("max_pop_total", C.c_int32),
-                ("reserved0", C.c_int32), ("max_nodes", C.c_int64), ("max_open", C.c_int64), ("reserved", C.c_int32 * 8)]
+                ("max_backups", C.c_int32), ("max_nodes", C.c_int64), ("max_open", C.c_int64), ("reserved", C.c_int32 * 8)]
 
 
 class dx_net_desc(C.Structure):
@@ -74,6 +74,7 @@ SIGNATURES = {
     "dx_all_finished": (C.c_int, [_engp, _i32p]),
     "dx_get_status": (C.c_int, [_engp, C.POINTER(dx_inst_status), C.c_int32]),
     "dx_get_counters": (C.c_int, [_engp, C.POINTER(dx_counters)]),
+    "dx_drain_backups": (C.c_int, [_engp, _u8p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
     "dx_get_path": (C.c_int, [_engp, C.c_int32, _i32p, _u8p, C.c_int32, _i32p]),
     "dx_get_curr_nodes": (C.c_int, [_engp, C.c_int32, _u8p, _f32p, _f32p, C.c_int32, _i32p]),
     "dx_domain_info": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
@@ -182,16 +183,20 @@ class Engine:
 
     def __init__(self, domain: str, dim: int = 0, algo: str = "graph_v", heur_mode: int = DX_HEUR_ZERO,
                  max_instances: int = 1, max_pop_total: int = 1, max_nodes: int = 1 << 20, max_open: int = 0,
-                 device: Optional[int] = None):
+                 device: Optional[int] = None, max_backups: int = 0):
+        """max_backups > 0 (graph_v): evaluate every generated child before the CLOSED filter and log the Bellman backup of
+        every expanded node (see drain_backups)"""
         lib = load()
         self.domain, self.dim = domain, dim
+        self.max_backups = max_backups
         self.state_bytes, self.num_actions, self.in_count, self.depth = domain_info(domain, dim)
         self.is_q = algo in ("graph_q", "beam_q")
         self.algo = algo
         self.heur_mode = heur_mode
         cfg = dx_config(device=current_device() if device is None else device, domain=DX_DOMAIN[domain], domain_dim=dim,
                         algo=DX_ALGO[algo], heur_mode=heur_mode,
-                        max_instances=max_instances, max_pop_total=max_pop_total, max_nodes=max_nodes, max_open=max_open)
+                        max_instances=max_instances, max_pop_total=max_pop_total, max_nodes=max_nodes, max_open=max_open,
+                        max_backups=max_backups)
         self._h = _engp()
         check(lib.dx_engine_create(C.byref(cfg), C.byref(self._h)))
         self._lib = lib
@@ -265,6 +270,18 @@ class Engine:
         c = dx_counters()
         check(self._lib.dx_get_counters(self._h, C.byref(c)))
         return c
+
+    def drain_backups(self):
+        """-> (states [n, S] uint8, backups [n] float64, insts [n] int32): Node.bellman_backup() of every node expanded since
+        the last drain, in the reference's `popped` order (updaters/updater_rl.py:143-158); empties the log"""
+        cap = self.max_backups
+        st = np.empty((cap, self.state_bytes), np.uint8)
+        bk = np.empty(cap, np.float64)
+        ins = np.empty(cap, np.int32)
+        n = C.c_int64()
+        check(self._lib.dx_drain_backups(self._h, _p(st, _u8p), bk.ctypes.data_as(C.POINTER(C.c_double)), _p(ins, _i32p), cap,
+                                         C.byref(n)))
+        return st[:n.value].copy(), bk[:n.value].copy(), ins[:n.value].copy()
 
     def get_path(self, inst: int, cap: int = 4096, with_states: bool = False):
         """-> (actions list or None, states_on_path [len+1, S] or None)"""

@@ -19,6 +19,7 @@
 #define DX_DEVERR_OPEN 2u
 #define DX_DEVERR_POP 4u
 #define DX_DEVERR_HDA 8u      // HDA*: an exchange segment / the receive capacity overflowed
+#define DX_DEVERR_BACKUPS 16u // the Bellman-backup log is full (dx_config.max_backups); drain it more often
 
 void dx_set_error(const std::string& msg);
 
@@ -74,6 +75,8 @@ struct Ctl {
     unsigned long long gen_total;
     uint32_t pass_src[DX_NUM_DIGITS];
     uint32_t pass_skip[DX_NUM_DIGITS];
+    uint32_t n_backups;    // records in the Bellman-backup log (evaluate-all engines)
+    uint32_t backup_overflow;
 };
 
 // Per-instance state (structure of arrays, capacity max_instances (+1 for offset arrays)).
@@ -209,7 +212,10 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
                            const float* child_g, const uint32_t* child_slot, const uint8_t* child_flags,
                            const uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
                            uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
-                           int max_children);
+                           int max_children, const float* child_h = nullptr, float* node_h = nullptr);
+int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                             const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
+                             uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint32_t bk_cap, int max_pop);
 int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,
                             const uint32_t* child_slot, const uint8_t* child_flags, int max_items);
 

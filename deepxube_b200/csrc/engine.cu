@@ -145,6 +145,8 @@ __global__ void k_set_host_vals(const Ctl* ctl, const float* vals, float* node_h
 }
 
 __global__ void k_set_job(Ctl* ctl, uint32_t start, uint32_t n) { ctl->nn_row_start = start; ctl->nn_n = n; }
+__global__ void k_reset_backups(Ctl* ctl) { ctl->n_backups = 0; }
+__global__ void k_set_job_children(Ctl* ctl) { ctl->nn_row_start = 0; ctl->nn_n = ctl->error ? 0 : ctl->n_children; }
 
 // device-side parent walk (base/pathfinding.py:93-120): actions written goal -> root, reversed on the host
 __global__ void k_path_walk(const uint32_t* node_parent, const uint8_t* node_action, uint32_t goal, int32_t* actions,
@@ -200,6 +202,10 @@ struct dx_engine {
     ClosedDev closed{};
     uint8_t* child_state = nullptr; float* child_g = nullptr; uint32_t* child_slot = nullptr; uint32_t* child_next = nullptr;
     uint8_t* child_flags = nullptr; uint32_t* child_prefix = nullptr; uint32_t* new_inst = nullptr;
+    // evaluate-all engines (dx_config.max_backups > 0): the heuristic of EVERY generated child, before the CLOSED filter,
+    // and the Bellman-backup log of the expanded nodes
+    bool eval_all = false;
+    float* child_h = nullptr; uint8_t* bk_state = nullptr; double* bk_val = nullptr; uint32_t* bk_inst = nullptr;
     uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
     uint32_t* edge_tmp = nullptr; uint8_t* pop_solved = nullptr;
     // HDA* mode (hash-distributed single search)
@@ -336,6 +342,7 @@ static int sync_ctl(dx_engine* e) {
         if (e->h_ctl->error & DX_DEVERR_OPEN) m += " max_open";
         if (e->h_ctl->error & DX_DEVERR_POP) m += " max_pop_total";
         if (e->h_ctl->error & DX_DEVERR_HDA) m += " HDA* exchange segment / receive capacity";
+        if (e->h_ctl->error & DX_DEVERR_BACKUPS) m += " max_backups (drain the backup log with dx_drain_backups)";
         DX_FAIL(DX_ERR_CAPACITY, m);
     }
     return DX_OK;
@@ -401,6 +408,9 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (cfg->max_nodes >= 0x7FFFFFF0ll) DX_FAIL(DX_ERR_ARG, "max_nodes must be < 2^31");
     if (cfg->algo < DX_ALGO_GRAPH_V || cfg->algo > DX_ALGO_BEAM_Q) DX_FAIL(DX_ERR_ARG, "unknown algo");
     if (cfg->heur_mode < DX_HEUR_ZERO || cfg->heur_mode > DX_HEUR_NET_BF16) DX_FAIL(DX_ERR_ARG, "unknown heur_mode");
+    if (cfg->max_backups < 0) DX_FAIL(DX_ERR_ARG, "max_backups must be >= 0");
+    if (cfg->max_backups > 0 && cfg->algo != DX_ALGO_GRAPH_V)
+        DX_FAIL(DX_ERR_UNSUPPORTED, "Bellman backups (max_backups > 0) are implemented for graph_v only");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         DX_FAIL(DX_ERR_CUDA, "no CUDA device: libdxb200 has no CPU fallback");
@@ -443,6 +453,11 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->closed.mask = (uint32_t)(hcap - 1);
     A_(e->closed.slot_key, hcap); A_(e->closed.slot_g, hcap); A_(e->closed.slot_head, hcap);
     if (!e->is_q) { A_(e->child_state, C * e->SP); A_(e->child_g, C); }
+    e->eval_all = cfg->max_backups > 0;
+    if (e->eval_all) {
+        const size_t K = (size_t)cfg->max_backups;
+        A_(e->child_h, C + 1); A_(e->bk_state, K * e->SP); A_(e->bk_val, K); A_(e->bk_inst, K);
+    }
     A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
     for (int p = 0; p < 2; ++p) {
         A_(e->popped[p], P); A_(e->popped_inst[p], P); A_(e->pop_off[p], I + 1);
@@ -499,20 +514,27 @@ static int need_net(dx_engine* e) {
 int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats);   // net_load.cu
 
 // heuristic for the current job (ctl->nn_row_start / nn_n) over node-store rows
-static int launch_heur_nodes(dx_engine* e, long long max_rows) {
+static int launch_heur_rows(dx_engine* e, const uint8_t* rows, float* out_h, float* out_q, long long max_rows) {
     const int mode = e->cfg.heur_mode;
     g_prof_engine = e->profiling ? e : nullptr;
     if (mode == DX_HEUR_ZERO) {
-        k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->node_h, e->node_q, e->A);
+        k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, out_h, out_q, e->A);
         e->launches += 1;
     } else if (mode == DX_HEUR_NET_FP32) {
-        e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, e->node_h,
-                                         e->node_q, 1, max_rows);
+        e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, e->ia.goals, out_h, out_q, 1, max_rows);
     } else if (mode == DX_HEUR_NET_BF16) {
-        e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, e->node_h,
-                                          e->node_q, 1, max_rows);
+        e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, e->ia.goals, out_h, out_q, 1, max_rows);
     }
     return DX_OK;
+}
+static int launch_heur_nodes(dx_engine* e, long long max_rows) {
+    return launch_heur_rows(e, e->node_state, e->node_h, e->node_q, max_rows);
+}
+// the heuristic job of an iteration: the stored kept children / generated nodes, or -- evaluate-all engines -- every generated
+// child in flat child order (rows [0, n_children) of child_state; the job was set by step_v_a)
+static int launch_heur_step(dx_engine* e, long long max_rows) {
+    if (e->eval_all) return launch_heur_rows(e, e->child_state, e->child_h, nullptr, max_rows);
+    return launch_heur_nodes(e, max_rows);
 }
 
 extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
@@ -616,6 +638,7 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
 }
 
 // ---------------------------------------------------------------------------------------------
+static int step_v_filter(dx_engine* e);
 // A* phase A: everything up to (and including) storing the kept children.
 static int step_v_a(dx_engine* e) {
     cudaStream_t s = e->stream;
@@ -626,6 +649,25 @@ static int step_v_a(dx_engine* e) {
     e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
                                           e->pop_solved, e->max_pop);
     stage_end(e);
+    if (e->eval_all) {                 // the reference order (base/pathfinding.py:362-371): evaluate all children, then filter
+        k_set_job_children<<<1, 1, 0, s>>>(e->d_ctl);
+        e->launches += 1;
+        return DX_OK;
+    }
+    return step_v_filter(e);
+}
+
+// A*: CLOSED filter + storing the kept children (phase A; evaluate-all engines run it after the heuristic, in phase B)
+static int step_v_filter(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity;
+    if (e->eval_all) {
+        stage_begin(e, ST_BOOK);
+        e->launches += dx_launch_bellman_backup(s, e->dom, e->d_ctl, e->ia, e->node_state, e->popped[p], e->popped_inst[p],
+                                                e->pop_solved, e->child_h, e->bk_state, e->bk_val, e->bk_inst,
+                                                (uint32_t)e->cfg.max_backups, e->max_pop);
+        stage_end(e);
+    }
     stage_begin(e, ST_CLOSED);
     if (e->is_beam)
         e->launches += dx_launch_beam_keep(s, e->d_ctl, e->child_g, e->child_flags, e->max_children);
@@ -641,7 +683,8 @@ static int step_v_a(dx_engine* e) {
     e->launches += 1;
     e->launches += dx_launch_scatter_kept(s, e->dom, e->closed, e->d_ctl, e->child_state, e->child_g, e->child_slot,
                                           e->child_flags, e->child_prefix, e->popped[p], e->popped_inst[p], e->node_state,
-                                          e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children);
+                                          e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children,
+                                          e->eval_all ? e->child_h : nullptr, e->node_h);
     stage_end(e);
     return DX_OK;
 }
@@ -649,6 +692,7 @@ static int step_v_a(dx_engine* e) {
 static int step_v_b(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity, q = p ^ 1;
+    if (e->eval_all) DX_TRY(step_v_filter(e));
     stage_begin(e, ST_SORT);
     const int beam = e->is_beam ? 1 : 0;
     e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
@@ -732,7 +776,7 @@ static int full_step(dx_engine* e) {
     } else {
         DX_TRY(step_v_a(e));
         stage_begin(e, ST_HEUR);
-        DX_TRY(launch_heur_nodes(e, e->max_children));
+        DX_TRY(launch_heur_step(e, e->max_children));
         stage_end(e);
         DX_TRY(step_v_b(e));
     }
@@ -834,7 +878,8 @@ extern "C" int dx_get_pending(dx_engine* e, uint8_t* states, uint8_t* goals, int
     if (n == 0) return DX_OK;
     const int SP = e->SP, S = e->S;
     std::vector<uint8_t> rows((size_t)n * SP), grows((size_t)e->n_inst * SP);
-    DX_CUDA(cudaMemcpyAsync(rows.data(), e->node_state + (size_t)start * SP, rows.size(), cudaMemcpyDeviceToHost, e->stream));
+    const uint8_t* src = e->eval_all ? e->child_state : e->node_state;
+    DX_CUDA(cudaMemcpyAsync(rows.data(), src + (size_t)start * SP, rows.size(), cudaMemcpyDeviceToHost, e->stream));
     DX_CUDA(cudaMemcpyAsync(grows.data(), e->ia.goals, grows.size(), cudaMemcpyDeviceToHost, e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
     for (uint32_t r = 0; r < n; ++r) {
@@ -857,8 +902,9 @@ extern "C" int dx_step_end(dx_engine* e, const float* vals, int64_t n) {
         if (!vals) DX_FAIL(DX_ERR_ARG, "null values");
         const size_t cnt = (size_t)n * (e->is_q ? e->A : 1);
         DX_CUDA(cudaMemcpyAsync(e->d_vals, vals, cnt * 4, cudaMemcpyHostToDevice, e->stream));
-        k_set_host_vals<<<std::min(dx_div_up(n, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->d_vals, e->node_h, e->node_q,
-                                                                                    e->A, e->is_q ? 1 : 0);
+        k_set_host_vals<<<std::min(dx_div_up(n, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, e->d_vals,
+                                                                                    e->eval_all ? e->child_h : e->node_h,
+                                                                                    e->node_q, e->A, e->is_q ? 1 : 0);
         e->launches += 1;
     }
     if (e->is_q) DX_TRY(step_q_b(e)); else DX_TRY(step_v_b(e));
@@ -909,6 +955,44 @@ extern "C" int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap) {
         out[i].num_curr = (int32_t)(off[i + 1] - off[i]);
         out[i].reserved = 0;
     }
+    return DX_OK;
+}
+
+// Bellman-backup log (evaluate-all engines): one record per node expanded since the last drain, in expansion order
+// (iteration, then instance, then pop order -- the order of the `popped` lists PathFind.step() returns,
+// base/pathfinding.py:349,399) -> the (state, target) pairs of UpdateHeurVRLKeepGoalABC (updaters/updater_rl.py:143-158).
+extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, double* backups, int32_t* insts, int64_t cap, int64_t* n_out) {
+    if (!e || !n_out) DX_FAIL(DX_ERR_ARG, "null argument");
+    if (!e->eval_all) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(sync_ctl(e));
+    const size_t n = e->h_ctl->n_backups;
+    const int SP = e->SP, S = e->S;
+    std::vector<uint8_t> rows(n * SP);
+    std::vector<double> vals(n);
+    std::vector<uint32_t> inst(n);
+    if (n) {
+        DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk_state, rows.size(), cudaMemcpyDeviceToHost, e->stream));
+        DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk_val, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
+        DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk_inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    int64_t m = 0;
+    for (size_t r = 0; r < n; ++r) m += vals[r] == vals[r] ? 1 : 0;        // NaN: popped by an instance that had finished
+    *n_out = m;
+    if (m > cap) DX_FAIL(DX_ERR_ARG, "buffer too small (n_out holds the record count; the log was not drained)");
+    int64_t k = 0;
+    for (size_t r = 0; r < n; ++r) {
+        if (vals[r] != vals[r]) continue;
+        if (states) memcpy(states + (size_t)k * S, &rows[r * SP], S);
+        if (backups) backups[k] = vals[r];
+        if (insts) insts[k] = (int32_t)inst[r];
+        ++k;
+    }
+    k_reset_backups<<<1, 1, 0, e->stream>>>(e->d_ctl);
+    e->launches += 1;
+    DX_CUDA(cudaStreamSynchronize(e->stream));
     return DX_OK;
 }
 
@@ -1366,6 +1450,7 @@ extern "C" int dx_hda_config(dx_engine* e, int32_t rank, int32_t world) {
     if (world < 1 || world > 16 || rank < 0 || rank >= world) DX_FAIL(DX_ERR_ARG, "bad rank / world (world <= 16)");
     if (e->is_q || e->is_beam) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode is implemented for graph_v");
     if (e->cfg.heur_mode == DX_HEUR_HOST) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode needs a device heuristic");
+    if (e->eval_all) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode does not keep a Bellman-backup log (max_backups must be 0)");
     if (e->n_inst != 0) DX_FAIL(DX_ERR_STATE, "dx_hda_config must precede dx_hda_add_instance");
     if (e->max_nodes >= (1u << 28)) DX_FAIL(DX_ERR_ARG, "HDA* mode: max_nodes must be < 2^28 per rank (global node id = rank << 28 | id)");
     DX_CUDA(cudaSetDevice(e->cfg.device));

@@ -174,7 +174,7 @@ k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, const uint8_t* _
                const uint8_t* __restrict__ child_flags, const uint32_t* __restrict__ child_prefix,
                const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst, uint8_t* __restrict__ node_state,
                float* __restrict__ node_g, uint32_t* __restrict__ node_parent, uint8_t* __restrict__ node_action,
-               uint32_t* __restrict__ new_inst) {
+               uint32_t* __restrict__ new_inst, const float* __restrict__ child_h, float* __restrict__ node_h) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;
     const uint32_t base = ctl->node_base;
@@ -193,6 +193,7 @@ k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, const uint8_t* _
         node_parent[id] = popped[j];
         node_action[id] = (uint8_t)(ci % d.A);
         new_inst[k] = popped_inst[j];
+        if (child_h) node_h[id] = child_h[ci];       // evaluate-all engines: the value was computed before the filter
         if (f & 2) {
             const uint32_t i = child_slot[ci];
             c.slot_g[i] = g;
@@ -206,11 +207,69 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
                            const float* child_g, const uint32_t* child_slot, const uint8_t* child_flags,
                            const uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
                            uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
-                           int max_children) {
+                           int max_children, const float* child_h, float* node_h) {
     int blocks = min(dx_div_up(max_children, CL_THREADS), 148 * 8);
     k_scatter_kept<<<blocks, CL_THREADS, 0, s>>>(d, c, ctl, child_state, child_g, child_slot, child_flags, child_prefix, popped,
-                                                 popped_inst, node_state, node_g, node_parent, node_action, new_inst);
+                                                 popped_inst, node_state, node_g, node_parent, node_action, new_inst, child_h,
+                                                 node_h);
     return 1;
+}
+
+// Bellman backup of every node expanded this iteration (deepxube/base/pathfinding.py:41-47, called on the popped nodes by
+// UpdateHeurVRLKeepGoalABC._get_labels_no_rb, updaters/updater_rl.py:143-158):
+//     backup = 0 if the node is solved else min over its children of (transition cost 1.0 + heuristic(child)),
+// in float64 like the reference's Python floats.  One record per popped node is appended, in pop order, to the engine's
+// backup log (state row, instance id, value); the nodes an instance popped in the iteration it finished are never expanded by
+// the reference (pathfinding.py:339) -- their records carry NaN and are dropped when the log is drained, and their children
+// do not count as heuristic evaluations.
+__global__ void __launch_bounds__(256)
+k_bellman_backup(DomainDev d, Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
+                 const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
+                 const uint8_t* __restrict__ pop_solved, const float* __restrict__ child_h, uint8_t* __restrict__ bk_state,
+                 double* __restrict__ bk_val, uint32_t* __restrict__ bk_inst, uint32_t bk_cap) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children / (uint32_t)d.A, at = ctl->n_backups;
+    if ((unsigned long long)at + n > bk_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->backup_overflow = 1;     // turned into ctl->error by k_backup_commit
+        return;
+    }
+    const int chunks = d.SP / 16;
+    unsigned long long skipped = 0;
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
+        const uint32_t inst = popped_inst[j];
+        double v;
+        if (!ia.active[inst]) {
+            v = __longlong_as_double(0x7ff8000000000000ll);
+            skipped += (unsigned long long)d.A;
+        } else if (pop_solved[j]) {
+            v = 0.0;
+        } else {
+            v = __longlong_as_double(0x7ff0000000000000ll);
+            for (int a = 0; a < d.A; ++a) v = fmin(v, 1.0 + (double)child_h[(size_t)j * d.A + a]);
+        }
+        bk_val[at + j] = v;
+        bk_inst[at + j] = inst;
+        const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)popped[j] * d.SP);
+        uint4* dst = reinterpret_cast<uint4*>(bk_state + (size_t)(at + j) * d.SP);
+        for (int q = 0; q < chunks; ++q) dst[q] = src[q];
+    }
+    if (skipped) atomicAdd(&ctl->heur_evals, 0ull - skipped);
+}
+
+__global__ void k_backup_commit(Ctl* ctl, int A) {
+    if (ctl->error) return;
+    if (ctl->backup_overflow) { ctl->error |= DX_DEVERR_BACKUPS; return; }
+    ctl->n_backups += ctl->n_children / (uint32_t)A;
+}
+
+int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
+                             const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
+                             uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint32_t bk_cap, int max_pop) {
+    k_bellman_backup<<<min(dx_div_up(max_pop, 256), 148 * 4), 256, 0, s>>>(d, ctl, ia, node_state, popped, popped_inst,
+                                                                                pop_solved, child_h, bk_state, bk_val, bk_inst,
+                                                                                bk_cap);
+    k_backup_commit<<<1, 1, 0, s>>>(ctl, d.A);
+    return 2;
 }
 
 // Q*: popped nodes that pass the filter only need CLOSED committed (they already are nodes).

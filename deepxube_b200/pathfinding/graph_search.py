@@ -97,6 +97,7 @@ class GraphSearch(PathFind):
         self._engine: Optional[_lib.Engine] = None
         self._fn = pathfind_fns.heurq if self.is_q else pathfind_fns.heurv
         self._pending: List[InstanceGraph] = []
+        self._max_backups = 0
 
     @staticmethod
     def _check_eps(eps: float) -> None:
@@ -122,9 +123,25 @@ class GraphSearch(PathFind):
         max_nodes = self._max_nodes or max(1 << 18, min(pop_total * a * 256, 48_000_000))
         mode = self._heur_mode()
         self._engine = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, self.dx_algo or ("graph_q" if self.is_q else "graph_v"), mode,
-                                   max_instances=n_inst, max_pop_total=max(pop_total, n_inst), max_nodes=max_nodes)
+                                   max_instances=n_inst, max_pop_total=max(pop_total, n_inst), max_nodes=max_nodes,
+                                   max_backups=self._max_backups)
         if mode in (_lib.DX_HEUR_NET_FP32, _lib.DX_HEUR_NET_BF16):
             load_nnet_into_engine(self._engine, self._fn.nnet)
+
+    def enable_backups(self, max_backups: int, max_instances: Optional[int] = None) -> None:
+        """Extension (training-data generation, deepxube_b200/updaters/updater_rl.py): the engine evaluates every generated
+        child before the CLOSED filter, as the reference does, and logs Node.bellman_backup() of every expanded node."""
+        if self._engine is not None:
+            raise RuntimeError("enable_backups must precede the first add_instances")
+        if self.is_q or self.dx_algo not in (None, "graph_v"):
+            raise TypeError("Bellman backups are implemented for graph_v")
+        self._max_backups = int(max_backups)
+        if max_instances:
+            self._max_instances = max(self._max_instances or 0, int(max_instances))
+
+    def drain_backups(self):
+        """-> (state rows [n, S], backups float64 [n], instance slots [n]) since the last drain"""
+        return self._engine.drain_backups()
 
     # ---- PathFind protocol -----------------------------------------------------------------------------
     def make_instances(self, states: List[Any], goals: List[Any], inst_infos: Optional[List[Any]] = None,

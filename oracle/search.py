@@ -157,6 +157,9 @@ class OracleSearch:
         self.trace_on = trace
         self.trace: List[List[dict]] = []
         self.num_heur_evals = 0
+        # Bellman backups of the popped nodes, per step: (states, backup values float64, instance index) -- what
+        # UpdateHeurVRLKeepGoalABC._get_labels_no_rb (updaters/updater_rl.py:143-158) reads after each PathFind.step()
+        self.backup_log: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = []
 
     # zero heuristic defaults (ref: base/pathfind_fns.py:205-210, 235-243)
     def _heur(self, states: np.ndarray, goals: np.ndarray) -> np.ndarray:
@@ -227,6 +230,18 @@ class OracleSearch:
             for p in per:
                 p[5] = h_all[off: off + p[1].shape[0]]
                 off += p[1].shape[0]
+            # Node.bellman_backup (base/pathfinding.py:41-47): 0 if solved else min_a (tc + heuristic(child_a)), tc = 1.0
+            bst, bval, bidx = [], [], []
+            for p in per:
+                inst = p[0]
+                ids = inst.nodes_curr
+                pst = inst.store.state[ids]
+                solved = dom.is_solved(pst, np.broadcast_to(inst.goal, (len(ids), dom.goal_len)))
+                mins = (1.0 + np.asarray(p[5], np.float64)).reshape(len(ids), a).min(axis=1) if len(ids) else np.zeros(0)
+                bst.append(pst.copy())
+                bval.append(np.where(solved, 0.0, mins))
+                bidx.append(np.full(len(ids), self.instances.index(inst), np.int32))
+            self.backup_log.append((np.concatenate(bst), np.concatenate(bval), np.concatenate(bidx)))
         keeps = []
         for p in per:
             inst, cst, cg = p[0], p[1], p[2]

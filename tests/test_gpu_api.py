@@ -363,3 +363,55 @@ def test_bf16_search_deviation_is_reported():
     # makes the termination iteration very sensitive to h).  The bound below is what the test enforces.
     assert max(abs(x) for x in dc) <= 2 and max(abs(x) for x in dn) <= 0.75
     eng.close()
+
+
+def test_updater_rl_bellman_targets_vs_oracle():
+    """SURVEY 8f.1 slice: one runner of the heurv RL updater (instances with batch size 1, replaced when they finish,
+    base/updater.py:343-400) -- emitted (state, goal, backup) triples equal the oracle's for the same instances."""
+    from deepxube_b200.updaters.updater_rl import UpdateHeurVRLKeepGoal
+    from oracle.domains_np import OracleDomain
+    from oracle.pseudo_heur import pseudo_v_fine
+    from oracle.search import OracleSearch
+    random.seed(5)
+    dom, _ = get_domain_from_arg("cube3")
+    pfns = PFNsHeurVC(heurv=lambda s, g, c: pseudo_v_fine(dom.states_to_rows(s)).tolist())
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph_v.1B_0.8W")
+    made = []
+
+    class Rec(UpdateHeurVRLKeepGoal):
+        def _make_instances(self, steps_gen):
+            insts = super()._make_instances(steps_gen)
+            made.append(insts)
+            return insts
+
+    steps_gen = [0, 1, 2, 1, 0, 3, 30, 40, 2, 1, 0, 25]
+    search_itrs = 6
+    up = Rec(dom, pathfind, search_itrs)
+    states, goals, ctgs = up.get_instance_data(steps_gen)
+    assert len(made) >= 2 and [len(m) for m in made][0] == len(steps_gen)          # finished instances were replaced
+
+    orc = OracleSearch(OracleDomain("cube3"), pseudo_v_fine, False, 1, 0.8)
+    groups, live = [], []
+    it_made = iter(made)
+    removed = None
+    for it in range(search_itrs):
+        batch = next(it_made) if (it == 0 or removed) else []
+        if batch:
+            live += orc.add_instances(dom.states_to_rows([i.root_node.state for i in batch]),
+                                      dom.goals_to_rows([i.root_node.goal for i in batch]))
+        orc.step()
+        removed = [i for i in live if i.finished() or i.itr >= search_itrs]
+        live = [i for i in live if not (i.finished() or i.itr >= search_itrs)]
+        if removed:
+            groups.append(removed)
+    if live:
+        groups.append(live)
+    st = np.concatenate([x[0] for x in orc.backup_log]); val = np.concatenate([x[1] for x in orc.backup_log])
+    idx = np.concatenate([x[2] for x in orc.backup_log])
+    order = np.concatenate([np.flatnonzero(idx == orc.instances.index(i)) for g in groups for i in g])
+    assert np.array_equal(dom.states_to_rows(states), st[order])
+    assert np.array_equal(ctgs, val[order]) and (ctgs[:1] == 0.0).all()            # first emitted: a solved root
+    exp_goals = np.stack([orc.instances[k].goal for k in idx[order]])
+    assert np.array_equal(dom.goals_to_rows(goals)[:, :exp_goals.shape[1]], exp_goals)
+    assert len(ctgs) == sum(i.itr for i in orc.instances)                          # batch size 1: one popped node per step
+    pathfind.close()

@@ -174,3 +174,22 @@ def test_beam_v_parser_and_rejections():
             get_pathfind_from_arg(dom, pfns, bad)
     with pytest.raises(ValueError, match="Error parsing 10X"):
         get_pathfind_from_arg(dom, pfns, "beam_v.10X")
+
+
+def test_updater_rl_rejects_what_it_does_not_implement():
+    """the training-data slice covers heurv + graph_v only"""
+    from deepxube_b200.updaters.updater_rl import UpdateHeurVRLKeepGoal
+    dom, name = get_domain_from_arg("cube3")
+    pfq, _ = get_path_fns_nnet_par_dict(dom, name, ["heurq_fixout"])
+    pq, _, _ = get_pathfind_from_arg(dom, pfq, "graph.1B")
+    with pytest.raises(TypeError, match="graph_v"):
+        UpdateHeurVRLKeepGoal(dom, pq, 5)
+    with pytest.raises(TypeError, match="graph_v"):
+        pq.enable_backups(10)
+    pfv, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv"])
+    pb, _, _ = get_pathfind_from_arg(dom, pfv, "beam_v.4B")
+    with pytest.raises(TypeError, match="graph_v"):
+        UpdateHeurVRLKeepGoal(dom, pb, 5)
+    pv, _, _ = get_pathfind_from_arg(dom, pfv, "graph.1B_0.8W")
+    up = UpdateHeurVRLKeepGoal(dom, pv, 5)
+    assert up.search_itrs == 5 and pv._max_backups == 0

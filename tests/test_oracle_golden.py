@@ -103,6 +103,8 @@ def _heur_for(cfg, dom):
         return None
     if heur == "v_pseudo":
         return pseudo_v
+    if heur == "v_pseudo_fine":
+        return pseudo_v_fine
     if heur == "q_pseudo":
         return make_pseudo_q(dom.num_actions)
     if heur == "q_in_net":          # action-as-input Q network of the heurq_in trace
@@ -212,3 +214,26 @@ def test_kat_heur_hard(idx):
     assert r["path_cost"] == k["hard_path_costs"][idx]
     assert r["num_nodes_generated"] == k["hard_nodes"][idx] and r["iterations"] == k["hard_iterations"][idx]
     assert r["actions"] == k["hard_actions_flat"][off: off + ln].tolist()
+
+
+@pytest.mark.parametrize("tag", gu.backup_tags())
+def test_bellman_backups_match_reference(tag):
+    """SURVEY 8f.1 slice: Node.bellman_backup() of the popped nodes of every step (updaters/updater_rl.py:143-158)."""
+    c = gu.backup_case(tag)
+    name, dim = gu.parse_domain(str(c["cfg"][0]))
+    b, w = gu.parse_pathfind(str(c["cfg"][1]))
+    dom = OracleDomain(name, dim)
+    srch = OracleSearch(dom, _heur_for(c["cfg"], dom), False, b, w)
+    insts = srch.add_instances(c["states"], c["goals"])
+    for _ in range(len(c["bk_counts"])):
+        srch.step()
+    assert [len(x[1]) for x in srch.backup_log] == c["bk_counts"].tolist()
+    st = np.concatenate([x[0] for x in srch.backup_log])
+    val = np.concatenate([x[1] for x in srch.backup_log])
+    idx = np.concatenate([x[2] for x in srch.backup_log])
+    assert np.array_equal(st, c["bk_states"]) and np.array_equal(idx, c["bk_inst"])
+    if str(c["cfg"][2]).endswith("net"):
+        np.testing.assert_allclose(val, c["bk_vals"], rtol=0, atol=2e-5)
+    else:
+        assert np.array_equal(val, c["bk_vals"])
+    assert [i.finished() for i in insts] == c["finished"].tolist()

@@ -440,8 +440,65 @@ def gen_beam() -> None:
     print("beam.npz", len(out), "arrays")
 
 
+def gen_backup() -> None:
+    """backup.npz (the training-time slice): the labels UpdateHeurVRLKeepGoalABC._get_labels_no_rb
+    (updaters/updater_rl.py:143-158, non-LHBL, no ub_heur_solns) reads off a graph_v search -- after every PathFind.step()
+    the popped nodes it returns get node.bellman_backup() (base/pathfinding.py:41-47).  Stored flat: the popped states, the
+    backup values (float64), the index of the owning instance and the number of records per step."""
+    out = {}
+
+    def add(tag, domain_str, pathfind_str, heur, steps_l, max_steps, nnet=None):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        if heur == "v_zero":
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv"], torch.device("cpu"))
+        elif heur == "v_pseudo_fine":
+            pfns = wrap_v(pseudo_v_fine)
+        else:
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, [nnet[0]], torch.device("cpu"), nnet_files=[nnet[1]])
+        pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
+        insts = pathfind.make_instances(states, goals, None, True)
+        pathfind.add_instances(insts)
+        st_l, val_l, idx_l, cnt_l = [], [], [], []
+        steps = 0
+        while (not all(i.finished() for i in insts)) and steps < max_steps:
+            owners = [k for k, inst in enumerate(insts) if not inst.finished() for _ in inst._nodes_curr]
+            popped, _ = pathfind.step()
+            assert len(popped) == len(owners)
+            steps += 1
+            vals = [node.bellman_backup() for node in popped]
+            assert all(isinstance(v, float) for v in vals), set(type(v) for v in vals)
+            st_l.append(states_np([n.state for n in popped]) if popped else np.zeros((0, states_np(states).shape[1]), np.uint8))
+            val_l.append(np.array(vals, np.float64))
+            idx_l.append(np.array(owners, np.int32))
+            cnt_l.append(len(popped))
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, "" if nnet is None else nnet[0]])
+        out[tag + "/bk_states"] = np.concatenate(st_l)
+        out[tag + "/bk_vals"] = np.concatenate(val_l)
+        out[tag + "/bk_inst"] = np.concatenate(idx_l)
+        out[tag + "/bk_counts"] = np.array(cnt_l, np.int64)
+        out[tag + "/finished"] = np.array([i.finished() for i in insts])
+        out[tag + "/path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
+        print(tag, name, "steps", steps, "records", int(sum(cnt_l)), "finished", out[tag + "/finished"].astype(int),
+              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()))
+
+    add("cube3_zero", "cube3", "graph.10B", "v_zero", [0, 1, 2, 3, 1, 2], 100)
+    add("cube3_fine", "cube3", "graph.20B_0.6W", "v_pseudo_fine", [20, 40, 3, 60], 10)
+    add("np4_fine", "npuzzle.4", "graph.30B_0.8W", "v_pseudo_fine", [10, 30, 2, 60, 90], 12)
+    add("lo5_fine", "lightsout.5", "graph.8B_0.5W", "v_pseudo_fine", [3, 8, 15], 10)
+    add("grid7_net", "grid.7d", "graph.3B_1.0W", "v_net", list(np.arange(8) * 5), 60,
+        ("heurv,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_v/heur.pt")))
+    np.savez_compressed(os.path.join(OUT, "backup.npz"), **out)
+    print("backup.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam", "backup"]
+    if "backup" in which:
+        gen_backup()
     if "beam" in which:
         gen_beam()
     if "qin" in which:

@@ -74,7 +74,7 @@ SIGNATURES = {
     "dx_all_finished": (C.c_int, [_engp, _i32p]),
     "dx_get_status": (C.c_int, [_engp, C.POINTER(dx_inst_status), C.c_int32]),
     "dx_get_counters": (C.c_int, [_engp, C.POINTER(dx_counters)]),
-    "dx_drain_backups": (C.c_int, [_engp, _u8p, C.POINTER(C.c_double), C.POINTER(C.c_int32), C.c_int64, C.POINTER(C.c_int64)]),
+    "dx_drain_backups": (C.c_int, [_engp, _u8p, _i32p, C.POINTER(C.c_double), _i32p, C.c_int64, C.POINTER(C.c_int64)]),
     "dx_get_path": (C.c_int, [_engp, C.c_int32, _i32p, _u8p, C.c_int32, _i32p]),
     "dx_get_curr_nodes": (C.c_int, [_engp, C.c_int32, _u8p, _f32p, _f32p, C.c_int32, _i32p]),
     "dx_domain_info": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
@@ -272,16 +272,22 @@ class Engine:
         return c
 
     def drain_backups(self):
-        """-> (states [n, S] uint8, backups [n] float64, insts [n] int32): Node.bellman_backup() of every node expanded since
-        the last drain, in the reference's `popped` order (updaters/updater_rl.py:143-158); empties the log"""
+        """graph_v -> (states [n, S] uint8, backups [n] float64, insts [n] int32): Node.bellman_backup() of every node expanded
+        since the last drain, in the reference's `popped` order (updaters/updater_rl.py:143-158);
+        graph_q -> (states, actions [n] int32, backups, insts): Node.backup_act(action) of every popped edge (:169-189).
+        Empties the log."""
         cap = self.max_backups
         st = np.empty((cap, self.state_bytes), np.uint8)
         bk = np.empty(cap, np.float64)
         ins = np.empty(cap, np.int32)
+        act = np.empty(cap, np.int32)
         n = C.c_int64()
-        check(self._lib.dx_drain_backups(self._h, _p(st, _u8p), bk.ctypes.data_as(C.POINTER(C.c_double)), _p(ins, _i32p), cap,
-                                         C.byref(n)))
-        return st[:n.value].copy(), bk[:n.value].copy(), ins[:n.value].copy()
+        check(self._lib.dx_drain_backups(self._h, _p(st, _u8p), _p(act, _i32p), bk.ctypes.data_as(C.POINTER(C.c_double)),
+                                         _p(ins, _i32p), cap, C.byref(n)))
+        k = n.value
+        if self.is_q:
+            return st[:k].copy(), act[:k].copy(), bk[:k].copy(), ins[:k].copy()
+        return st[:k].copy(), bk[:k].copy(), ins[:k].copy()
 
     def get_path(self, inst: int, cap: int = 4096, with_states: bool = False):
         """-> (actions list or None, states_on_path [len+1, S] or None)"""

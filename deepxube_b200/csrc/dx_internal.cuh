@@ -216,6 +216,12 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
 int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
                              const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
                              uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint32_t bk_cap, int max_pop);
+int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped, const uint32_t* pop_off,
+                          const uint8_t* pop_solved, uint8_t* node_solved, int max_pop);
+int dx_launch_bellman_backup_q(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* node_state, const uint32_t* node_parent,
+                               const uint8_t* node_action, const float* node_h, const uint8_t* node_solved,
+                               const uint32_t* edge_inst, uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint8_t* bk_act,
+                               uint32_t bk_cap, int max_pop);
 int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,
                             const uint32_t* child_slot, const uint8_t* child_flags, int max_items);
 

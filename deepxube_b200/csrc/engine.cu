@@ -206,6 +206,8 @@ struct dx_engine {
     // and the Bellman-backup log of the expanded nodes
     bool eval_all = false;
     float* child_h = nullptr; uint8_t* bk_state = nullptr; double* bk_val = nullptr; uint32_t* bk_inst = nullptr;
+    bool backups_q = false;          // graph_q with a backup log: labels of the popped edges
+    uint8_t* bk_act = nullptr; uint8_t* node_solved = nullptr;
     uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
     uint32_t* edge_tmp = nullptr; uint8_t* pop_solved = nullptr;
     // HDA* mode (hash-distributed single search)
@@ -382,6 +384,7 @@ static int reset_state(dx_engine* e) {
         DX_CUDA(cudaMemsetAsync(e->pop_off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream));
         DX_CUDA(cudaMemsetAsync(e->open_off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream));
     }
+    if (e->node_solved) DX_CUDA(cudaMemsetAsync(e->node_solved, 0, e->max_nodes, e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
     e->n_inst = 0;
     e->parity = 0;
@@ -409,8 +412,8 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (cfg->algo < DX_ALGO_GRAPH_V || cfg->algo > DX_ALGO_BEAM_Q) DX_FAIL(DX_ERR_ARG, "unknown algo");
     if (cfg->heur_mode < DX_HEUR_ZERO || cfg->heur_mode > DX_HEUR_NET_BF16) DX_FAIL(DX_ERR_ARG, "unknown heur_mode");
     if (cfg->max_backups < 0) DX_FAIL(DX_ERR_ARG, "max_backups must be >= 0");
-    if (cfg->max_backups > 0 && cfg->algo != DX_ALGO_GRAPH_V)
-        DX_FAIL(DX_ERR_UNSUPPORTED, "Bellman backups (max_backups > 0) are implemented for graph_v only");
+    if (cfg->max_backups > 0 && cfg->algo != DX_ALGO_GRAPH_V && cfg->algo != DX_ALGO_GRAPH_Q)
+        DX_FAIL(DX_ERR_UNSUPPORTED, "Bellman backups (max_backups > 0) are implemented for graph_v and graph_q only");
     int ndev = 0;
     if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
         DX_FAIL(DX_ERR_CUDA, "no CUDA device: libdxb200 has no CPU fallback");
@@ -453,10 +456,13 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->closed.mask = (uint32_t)(hcap - 1);
     A_(e->closed.slot_key, hcap); A_(e->closed.slot_g, hcap); A_(e->closed.slot_head, hcap);
     if (!e->is_q) { A_(e->child_state, C * e->SP); A_(e->child_g, C); }
-    e->eval_all = cfg->max_backups > 0;
-    if (e->eval_all) {
+    e->eval_all = cfg->max_backups > 0 && !e->is_q;
+    e->backups_q = cfg->max_backups > 0 && e->is_q;
+    if (cfg->max_backups > 0) {
         const size_t K = (size_t)cfg->max_backups;
-        A_(e->child_h, C + 1); A_(e->bk_state, K * e->SP); A_(e->bk_val, K); A_(e->bk_inst, K);
+        A_(e->bk_state, K * e->SP); A_(e->bk_val, K); A_(e->bk_inst, K); A_(e->bk_act, K);
+        if (e->eval_all) A_(e->child_h, C + 1);
+        if (e->backups_q) A_(e->node_solved, N);
     }
     A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
     for (int p = 0; p < 2; ++p) {
@@ -721,6 +727,8 @@ static int step_q_a(dx_engine* e) {
                                           e->pop_off[p], e->pop_solved, e->max_pop);
     e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
                                           e->pop_solved, e->max_pop);
+    if (e->backups_q)
+        e->launches += dx_launch_mark_solved(s, e->d_ctl, e->popped[p], e->pop_off[p], e->pop_solved, e->node_solved, e->max_pop);
     stage_end(e);
     const int beam = e->is_beam ? 1 : 0;
     stage_begin(e, ST_CLOSED);
@@ -760,6 +768,10 @@ static int step_q_a(dx_engine* e) {
 static int step_q_b(dx_engine* e) {
     const int p = e->parity, q = p ^ 1;
     stage_begin(e, ST_BOOK);
+    if (e->backups_q)
+        e->launches += dx_launch_bellman_backup_q(e->stream, e->dom, e->d_ctl, e->node_state, e->node_parent, e->node_action,
+                                                  e->node_h, e->node_solved, e->popped_inst[q], e->bk_state, e->bk_val,
+                                                  e->bk_inst, e->bk_act, (uint32_t)e->cfg.max_backups, e->max_pop);
     e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, e->is_beam ? 3 : 1);
     stage_end(e);
     e->parity = q;
@@ -961,9 +973,10 @@ extern "C" int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap) {
 // Bellman-backup log (evaluate-all engines): one record per node expanded since the last drain, in expansion order
 // (iteration, then instance, then pop order -- the order of the `popped` lists PathFind.step() returns,
 // base/pathfinding.py:349,399) -> the (state, target) pairs of UpdateHeurVRLKeepGoalABC (updaters/updater_rl.py:143-158).
-extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, double* backups, int32_t* insts, int64_t cap, int64_t* n_out) {
+extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap,
+                                int64_t* n_out) {
     if (!e || !n_out) DX_FAIL(DX_ERR_ARG, "null argument");
-    if (!e->eval_all) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
+    if (!e->eval_all && !e->backups_q) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_TRY(sync_ctl(e));
@@ -972,7 +985,9 @@ extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, double* backups, 
     std::vector<uint8_t> rows(n * SP);
     std::vector<double> vals(n);
     std::vector<uint32_t> inst(n);
+    std::vector<uint8_t> act(n);
     if (n) {
+        if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk_act, n, cudaMemcpyDeviceToHost, e->stream));
         DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk_state, rows.size(), cudaMemcpyDeviceToHost, e->stream));
         DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk_val, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
         DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk_inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
@@ -988,6 +1003,7 @@ extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, double* backups, 
         if (states) memcpy(states + (size_t)k * S, &rows[r * SP], S);
         if (backups) backups[k] = vals[r];
         if (insts) insts[k] = (int32_t)inst[r];
+        if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
         ++k;
     }
     k_reset_backups<<<1, 1, 0, e->stream>>>(e->d_ctl);

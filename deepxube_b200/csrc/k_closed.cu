@@ -259,7 +259,64 @@ k_bellman_backup(DomainDev d, Ctl* __restrict__ ctl, InstArrays ia, const uint8_
 __global__ void k_backup_commit(Ctl* ctl, int A) {
     if (ctl->error) return;
     if (ctl->backup_overflow) { ctl->error |= DX_DEVERR_BACKUPS; return; }
-    ctl->n_backups += ctl->n_children / (uint32_t)A;
+    ctl->n_backups += A > 0 ? ctl->n_children / (uint32_t)A : ctl->n_kept;
+}
+
+// Q*: remember is_solved of the nodes popped this iteration (PathFind.set_is_solved, base/pathfinding.py:353): the label of
+// an edge popped in a LATER iteration needs it.
+__global__ void k_mark_solved(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ popped,
+                              const uint32_t* __restrict__ pop_off, const uint8_t* __restrict__ pop_solved,
+                              uint8_t* __restrict__ node_solved) {
+    if (ctl->error) return;
+    const uint32_t n = pop_off[ctl->n_inst];
+    for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x)
+        node_solved[popped[j]] = pop_solved[j];
+}
+
+// Q* labels (UpdateHeurQRLKeepGoalABC._get_labels_no_rb, updaters/updater_rl.py:169-189, over Node.backup_act,
+// base/pathfinding.py:66-77): for every edge (node, action) popped this iteration,
+//     0 if node is solved else transition cost 1.0 + heuristic(node_next), heuristic(node_next) = min_a q(node_next, a).
+// node_next is the node generated for the edge this iteration (ids node_base + k, in pop order); its backup_val is still
+// +inf when the reference reads it (it can only be set by edges popped later), hence always the heuristic branch.
+__global__ void __launch_bounds__(256)
+k_bellman_backup_q(DomainDev d, Ctl* __restrict__ ctl, const uint8_t* __restrict__ node_state,
+                   const uint32_t* __restrict__ node_parent, const uint8_t* __restrict__ node_action,
+                   const float* __restrict__ node_h, const uint8_t* __restrict__ node_solved,
+                   const uint32_t* __restrict__ edge_inst, uint8_t* __restrict__ bk_state, double* __restrict__ bk_val,
+                   uint32_t* __restrict__ bk_inst, uint8_t* __restrict__ bk_act, uint32_t bk_cap) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_kept, base = ctl->node_base, at = ctl->n_backups;
+    if ((unsigned long long)at + n > bk_cap) {
+        if (blockIdx.x == 0 && threadIdx.x == 0) ctl->backup_overflow = 1;
+        return;
+    }
+    const int chunks = d.SP / 16;
+    for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
+        const uint32_t id = base + k, par = node_parent[id];
+        bk_val[at + k] = node_solved[par] ? 0.0 : 1.0 + (double)node_h[id];
+        bk_inst[at + k] = edge_inst[k];
+        bk_act[at + k] = node_action[id];
+        const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)par * d.SP);
+        uint4* dst = reinterpret_cast<uint4*>(bk_state + (size_t)(at + k) * d.SP);
+        for (int q = 0; q < chunks; ++q) dst[q] = src[q];
+    }
+}
+
+int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped, const uint32_t* pop_off,
+                          const uint8_t* pop_solved, uint8_t* node_solved, int max_pop) {
+    k_mark_solved<<<min(dx_div_up(max_pop, 256), 148 * 4), 256, 0, s>>>(ctl, popped, pop_off, pop_solved, node_solved);
+    return 1;
+}
+
+int dx_launch_bellman_backup_q(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* node_state, const uint32_t* node_parent,
+                               const uint8_t* node_action, const float* node_h, const uint8_t* node_solved,
+                               const uint32_t* edge_inst, uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint8_t* bk_act,
+                               uint32_t bk_cap, int max_pop) {
+    k_bellman_backup_q<<<min(dx_div_up(max_pop, 256), 148 * 4), 256, 0, s>>>(d, ctl, node_state, node_parent, node_action, node_h,
+                                                                            node_solved, edge_inst, bk_state, bk_val, bk_inst,
+                                                                            bk_act, bk_cap);
+    k_backup_commit<<<1, 1, 0, s>>>(ctl, 0);
+    return 2;
 }
 
 int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,

@@ -133,14 +133,14 @@ class GraphSearch(PathFind):
         child before the CLOSED filter, as the reference does, and logs Node.bellman_backup() of every expanded node."""
         if self._engine is not None:
             raise RuntimeError("enable_backups must precede the first add_instances")
-        if self.is_q or self.dx_algo not in (None, "graph_v"):
-            raise TypeError("Bellman backups are implemented for graph_v")
+        if self.dx_algo not in (None, "graph_v", "graph_q"):
+            raise TypeError("Bellman backups are implemented for graph_v / graph_q")
         self._max_backups = int(max_backups)
         if max_instances:
             self._max_instances = max(self._max_instances or 0, int(max_instances))
 
     def drain_backups(self):
-        """-> (state rows [n, S], backups float64 [n], instance slots [n]) since the last drain"""
+        """-> (state rows [n, S], [graph_q: action ids [n],] backups float64 [n], instance slots [n]) since the last drain"""
         return self._engine.drain_backups()
 
     # ---- PathFind protocol -----------------------------------------------------------------------------

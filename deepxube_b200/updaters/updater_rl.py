@@ -1,14 +1,15 @@
 """Training-data generation from the search: the value-iteration targets of the heuristic network.
 
-Mirror of ONE runner of the reference's RL updater for `heurv` with the goal kept (no HER), no replay buffer, Bellman
-(non-LHBL) backups and `ub_heur_solns` off:
+Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq` with the goal kept (no HER), no replay buffer,
+Bellman (non-LHBL) backups and `ub_heur_solns` off:
 
     base/updater.py:343-400        update_runner: for each of `search_itrs` iterations -- add instances (new ones for the
                                    instances removed last iteration, same steps_gen), one PathFind.step(), remove the
                                    instances that finished or reached search_itrs, emit their data; finally emit the rest
     base/updater.py:781-791        data of an instance group = the nodes those instances popped + their labels
-    updaters/updater_rl.py:143-158 labels = Node.bellman_backup() of each popped node
-    base/updater.py:904-921        -> [*nnet inputs of (state, goal), labels]
+    updaters/updater_rl.py:143-158 V labels = Node.bellman_backup() of each popped node
+    updaters/updater_rl.py:169-189 Q labels = Node.backup_act(action) of each popped edge
+    base/updater.py:904-921, 938-965 -> [*nnet inputs of (state, goal[, action]), labels]
 
 The search and the backups run on the device (graph_v engine created with max_backups > 0: every generated child is
 evaluated before the CLOSED filter and each expanded node's backup is logged by k_bellman_backup); this module only owns the
@@ -23,9 +24,13 @@ from deepxube_b200.pathfinding.graph_search import GraphSearch
 
 
 class UpdateHeurVRLKeepGoal:
+    is_q = False
+
     def __init__(self, domain: Any, pathfind: GraphSearch, search_itrs: int, nnet_input: Optional[Any] = None):
-        if pathfind.is_q or pathfind.dx_algo not in (None, "graph_v"):
-            raise TypeError("UpdateHeurVRLKeepGoal needs a graph_v search (PathFindSetHeurV, updaters/updater_rl.py:137)")
+        want = "graph_q" if self.is_q else "graph_v"
+        if pathfind.is_q != self.is_q or pathfind.dx_algo not in (None, want):
+            raise TypeError(f"{type(self).__name__} needs a {want} search (PathFindSetHeur{'Q' if self.is_q else 'V'}, "
+                            "updaters/updater_rl.py:137-165)")
         if pathfind.instances:
             raise ValueError("the PathFind must be fresh (base/updater.py:364 builds one per batch)")
         self.domain, self.pathfind, self.search_itrs, self.nnet_input = domain, pathfind, int(search_itrs), nnet_input
@@ -34,10 +39,10 @@ class UpdateHeurVRLKeepGoal:
         states, goals = self.domain.sample_problem_instances(steps_gen)                      # base/updater.py:679-685
         return self.pathfind.make_instances(states, goals, inst_infos=[(s,) for s in steps_gen], compute_root_vals=False)
 
-    def get_instance_data(self, steps_gen: List[int], instances: Optional[List[Any]] = None) -> Tuple[List[Any], List[Any], np.ndarray]:
-        """-> (states, goals, ctgs_backup) in the order the reference emits them: groups of removed instances in removal
-        order, instances in order within a group, each instance's popped nodes in pop order.  `instances`: use these
-        instead of sampling the first batch (tests)."""
+    def get_instance_data(self, steps_gen: List[int], instances: Optional[List[Any]] = None) -> Tuple:
+        """-> (states, goals, [Q: actions,] ctgs_backup) in the order the reference emits them: groups of removed instances
+        in removal order, instances in order within a group, each instance's popped nodes / edges in pop order.
+        `instances`: use these instead of sampling the first batch (tests)."""
         pf, n = self.pathfind, len(steps_gen)
         a = self.domain.get_num_acts()
         b = max(pf.batch_size_default, 1)
@@ -59,16 +64,27 @@ class UpdateHeurVRLKeepGoal:
                 groups.append(removed)
         if pf.instances:
             groups.append(list(pf.instances))
-        rows, vals, slots = pf.drain_backups()
+        drained = pf.drain_backups()
+        rows, vals, slots = drained[0], drained[-2], drained[-1]
         # regroup the device log (iteration-major) into the reference's emission order
         order = np.concatenate([np.flatnonzero(slots == inst._slot) for g in groups for inst in g]) if len(vals) else np.zeros(0, np.int64)
         goal_of = {inst._slot: inst.root_node.goal for g in groups for inst in g}
         states = self.domain.rows_to_states(rows[order])
         goals = [goal_of[int(s)] for s in slots[order]]
+        if self.is_q:
+            fixed = self.domain.get_actions_fixed()
+            return states, goals, [fixed[int(k)] for k in drained[1][order]], vals[order]
         return states, goals, vals[order]
 
     def get_update_data(self, steps_gen: List[int]) -> List[np.ndarray]:
-        """[*inputs_nnet, ctgs] (base/updater.py:915-921)"""
-        states, goals, ctgs = self.get_instance_data(steps_gen)
+        """[*inputs_nnet, ctgs] (base/updater.py:915-921, 958-965)"""
+        data = self.get_instance_data(steps_gen)
         assert self.nnet_input is not None, "nnet_input needed to build network inputs"
-        return list(self.nnet_input.to_np(states, goals)) + [np.asarray(ctgs)]
+        if self.is_q:                           # one action per row (`[[action] for action in ...]`, base/updater.py:960)
+            return list(self.nnet_input.to_np(data[0], data[1], [[a] for a in data[2]])) + [np.asarray(data[3])]
+        return list(self.nnet_input.to_np(data[0], data[1])) + [np.asarray(data[2])]
+
+
+class UpdateHeurQRLKeepGoal(UpdateHeurVRLKeepGoal):
+    """the same runner over graph_q: popped edges and Node.backup_act labels (updaters/updater_rl.py:162-189)"""
+    is_q = True

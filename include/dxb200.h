@@ -63,7 +63,7 @@ typedef struct dx_config {
     int32_t max_pop_total;   /* capacity: sum over instances of their batch sizes (nodes popped / iter)  */
     int32_t max_backups;     /* 0, or the capacity (records) of the Bellman-backup log: the engine then evaluates the
                                 heuristic of EVERY generated child before the CLOSED filter, like the reference
-                                (base/pathfinding.py:362-371), and logs the backup of every expanded node (graph_v only) */
+                                (base/pathfinding.py:362-371), and logs the backup of every expanded node; graph_q: logs the label of every popped edge */
     int64_t max_nodes;       /* capacity: nodes stored (A*: kept children; Q*: all generated children)   */
     int64_t max_open;        /* capacity: OPEN entries (A*: <= max_nodes; Q*: edges); 0 = derive         */
     int32_t reserved[8];
@@ -152,15 +152,20 @@ int dx_all_finished(dx_engine* e, int32_t* out);
 int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap);
 int dx_get_counters(dx_engine* e, dx_counters* out);
 
-/* Training targets from the search (engines created with max_backups > 0): Node.bellman_backup()
- * (deepxube/base/pathfinding.py:41-47) of every node expanded since the last drain --
- *     0 if the node is solved else min over its children of (1.0 + heuristic(child)), float64 --
- * in the order UpdateHeurVRLKeepGoalABC._get_labels_no_rb sees them (updaters/updater_rl.py:143-158: the popped nodes
- * of each PathFind.step(), instances in order, pop order within).  states [cap, state_bytes], backups [cap],
- * insts [cap] (any may be NULL); *n = records written.  An iteration takes one log slot per popped node (slots of nodes
- * popped by an instance in the iteration it finished are dropped at the drain): size max_backups accordingly.  DX_ERR_ARG with *n = the count when cap is too small (nothing is
- * drained).  The log is emptied on success. */
-int dx_drain_backups(dx_engine* e, uint8_t* states, double* backups, int32_t* insts, int64_t cap, int64_t* n);
+/* Training targets from the search (graph_v / graph_q engines created with max_backups > 0), one record per node
+ * expanded (graph_v) or edge popped (graph_q) since the last drain, in the order of the `popped` lists that
+ * PathFind.step() returns (instances in order, pop order within; base/pathfinding.py:399, 525):
+ *   graph_v  Node.bellman_backup() (base/pathfinding.py:41-47, UpdateHeurVRLKeepGoalABC._get_labels_no_rb,
+ *            updaters/updater_rl.py:143-158): 0 if the node is solved else min over its children of
+ *            (1.0 + heuristic(child)); actions[] = -1
+ *   graph_q  Node.backup_act(action) (base/pathfinding.py:66-77, UpdateHeurQRLKeepGoalABC._get_labels_no_rb,
+ *            updaters/updater_rl.py:169-189): 0 if the edge's node is solved else 1.0 + min_a q(node_next, a);
+ *            states[] = the edge's node, actions[] = the edge's action
+ * float64 like the reference's Python floats.  states [cap, state_bytes], actions [cap], backups [cap], insts [cap] (any
+ * may be NULL); *n = records written.  DX_ERR_ARG with *n = the count when cap is too small (nothing is drained).  The log is
+ * emptied on success.  An iteration takes one log slot per popped node / edge (graph_v: slots of nodes popped by an
+ * instance in the iteration it finished are dropped at the drain): size max_backups accordingly. */
+int dx_drain_backups(dx_engine* e, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap, int64_t* n);
 
 /* get_path (base/pathfinding.py:93-120): device-side parent walk from goal_node.  actions [cap],
  * states_on_path [(cap+1), state_bytes] (may be NULL).  *len = number of actions (path length). */

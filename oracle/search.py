@@ -299,17 +299,26 @@ class OracleSearch:
         q_all = self._heur(allst, allgoal)
         off = 0
         rec = []
+        bq: List[Tuple[np.ndarray, np.ndarray, np.ndarray, np.ndarray]] = []
         for inst, new_ids, ids, keep, costs in per:
             q = q_all[off: off + len(new_ids)]
             off += len(new_ids)
             inst.store.q[new_ids] = q
             inst.store.h[new_ids] = q.min(axis=1) if len(new_ids) else 0.0
+            # Node.backup_act (base/pathfinding.py:66-77) of the popped edges: 0 if the edge's node is solved else
+            # tc + heuristic(node_next); node_next.backup_val is +inf at this point (updaters/updater_rl.py:181-186)
+            par, act = inst.store.parent[new_ids], inst.store.action[new_ids]
+            solved = dom.is_solved(inst.store.state[par], np.broadcast_to(inst.goal, (len(par), dom.goal_len)))
+            hn = q.min(axis=1).astype(np.float64) if len(new_ids) else np.zeros(0)
+            bq.append((inst.store.state[par].copy(), np.where(solved, 0.0, 1.0 + hn), np.full(len(par), self.instances.index(inst), np.int32),
+                       np.asarray(act, np.int32)))
             inst.nodes_curr = new_ids
             if self.trace_on:
                 rec.append(dict(popped=ids.copy(), keep=keep.copy(), f=costs.copy(), next=new_ids.copy(), lb=inst.lb,
                                 ub=inst.ub, open=len(inst.open), closed=len(inst.closed)))
         if self.trace_on:
             self.trace.append(rec)
+        self.backup_log.append(tuple(np.concatenate([b[k] for b in bq]) for k in range(4)))
 
 
 def solve_one(domain: OracleDomain, state: np.ndarray, goal: np.ndarray, heur_fn: Optional[HeurFn], is_q: bool,

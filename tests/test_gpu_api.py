@@ -365,20 +365,26 @@ def test_bf16_search_deviation_is_reported():
     eng.close()
 
 
-def test_updater_rl_bellman_targets_vs_oracle():
-    """SURVEY 8f.1 slice: one runner of the heurv RL updater (instances with batch size 1, replaced when they finish,
-    base/updater.py:343-400) -- emitted (state, goal, backup) triples equal the oracle's for the same instances."""
-    from deepxube_b200.updaters.updater_rl import UpdateHeurVRLKeepGoal
+@pytest.mark.parametrize("is_q", [False, True])
+def test_updater_rl_bellman_targets_vs_oracle(is_q):
+    """SURVEY 8f.1 slice: one runner of the heurv / heurq RL updater (instances with batch size 1, replaced when they finish,
+    base/updater.py:343-400) -- emitted (state, goal, [action,] backup) records equal the oracle's for the same instances."""
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLKeepGoal, UpdateHeurVRLKeepGoal
     from oracle.domains_np import OracleDomain
-    from oracle.pseudo_heur import pseudo_v_fine
+    from oracle.pseudo_heur import make_pseudo_q_fine, pseudo_v_fine
     from oracle.search import OracleSearch
     random.seed(5)
     dom, _ = get_domain_from_arg("cube3")
-    pfns = PFNsHeurVC(heurv=lambda s, g, c: pseudo_v_fine(dom.states_to_rows(s)).tolist())
-    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph_v.1B_0.8W")
+    fq = make_pseudo_q_fine(12)
+    if is_q:
+        pfns = PFNsHeurQC(heurq=lambda s, g, a, c: fq(dom.states_to_rows(s)).tolist())
+    else:
+        pfns = PFNsHeurVC(heurv=lambda s, g, c: pseudo_v_fine(dom.states_to_rows(s)).tolist())
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.1B_0.8W")
+    assert pname == ("graph_q" if is_q else "graph_v")
     made = []
 
-    class Rec(UpdateHeurVRLKeepGoal):
+    class Rec(UpdateHeurQRLKeepGoal if is_q else UpdateHeurVRLKeepGoal):
         def _make_instances(self, steps_gen):
             insts = super()._make_instances(steps_gen)
             made.append(insts)
@@ -387,10 +393,11 @@ def test_updater_rl_bellman_targets_vs_oracle():
     steps_gen = [0, 1, 2, 1, 0, 3, 30, 40, 2, 1, 0, 25]
     search_itrs = 6
     up = Rec(dom, pathfind, search_itrs)
-    states, goals, ctgs = up.get_instance_data(steps_gen)
+    data = up.get_instance_data(steps_gen)
+    states, goals, ctgs = data[0], data[1], data[-1]
     assert len(made) >= 2 and [len(m) for m in made][0] == len(steps_gen)          # finished instances were replaced
 
-    orc = OracleSearch(OracleDomain("cube3"), pseudo_v_fine, False, 1, 0.8)
+    orc = OracleSearch(OracleDomain("cube3"), fq if is_q else pseudo_v_fine, is_q, 1, 0.8)
     groups, live = [], []
     it_made = iter(made)
     removed = None
@@ -411,7 +418,10 @@ def test_updater_rl_bellman_targets_vs_oracle():
     order = np.concatenate([np.flatnonzero(idx == orc.instances.index(i)) for g in groups for i in g])
     assert np.array_equal(dom.states_to_rows(states), st[order])
     assert np.array_equal(ctgs, val[order]) and (ctgs[:1] == 0.0).all()            # first emitted: a solved root
+    if is_q:
+        acts = np.concatenate([x[3] for x in orc.backup_log])
+        assert [dom.action_index(a) for a in data[2]] == acts[order].tolist()
     exp_goals = np.stack([orc.instances[k].goal for k in idx[order]])
     assert np.array_equal(dom.goals_to_rows(goals)[:, :exp_goals.shape[1]], exp_goals)
-    assert len(ctgs) == sum(i.itr for i in orc.instances)                          # batch size 1: one popped node per step
+    assert len(ctgs) == sum(i.itr for i in orc.instances)                          # batch size 1: one popped node / edge per step
     pathfind.close()

@@ -184,8 +184,8 @@ def test_updater_rl_rejects_what_it_does_not_implement():
     pq, _, _ = get_pathfind_from_arg(dom, pfq, "graph.1B")
     with pytest.raises(TypeError, match="graph_v"):
         UpdateHeurVRLKeepGoal(dom, pq, 5)
-    with pytest.raises(TypeError, match="graph_v"):
-        pq.enable_backups(10)
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLKeepGoal
+    assert UpdateHeurQRLKeepGoal(dom, pq, 3).is_q
     pfv, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv"])
     pb, _, _ = get_pathfind_from_arg(dom, pfv, "beam_v.4B")
     with pytest.raises(TypeError, match="graph_v"):
@@ -193,3 +193,7 @@ def test_updater_rl_rejects_what_it_does_not_implement():
     pv, _, _ = get_pathfind_from_arg(dom, pfv, "graph.1B_0.8W")
     up = UpdateHeurVRLKeepGoal(dom, pv, 5)
     assert up.search_itrs == 5 and pv._max_backups == 0
+    with pytest.raises(TypeError, match="graph_q"):
+        UpdateHeurQRLKeepGoal(dom, pv, 5)
+    with pytest.raises(TypeError, match="graph_v / graph_q"):
+        pb.enable_backups(10)

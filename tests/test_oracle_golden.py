@@ -105,6 +105,8 @@ def _heur_for(cfg, dom):
         return pseudo_v
     if heur == "v_pseudo_fine":
         return pseudo_v_fine
+    if heur == "q_pseudo_fine":
+        return make_pseudo_q_fine(dom.num_actions)
     if heur == "q_pseudo":
         return make_pseudo_q(dom.num_actions)
     if heur == "q_in_net":          # action-as-input Q network of the heurq_in trace
@@ -223,7 +225,8 @@ def test_bellman_backups_match_reference(tag):
     name, dim = gu.parse_domain(str(c["cfg"][0]))
     b, w = gu.parse_pathfind(str(c["cfg"][1]))
     dom = OracleDomain(name, dim)
-    srch = OracleSearch(dom, _heur_for(c["cfg"], dom), False, b, w)
+    is_q = tag.startswith("q_")          # graph_q: Node.backup_act of the popped edges (updaters/updater_rl.py:169-189)
+    srch = OracleSearch(dom, _heur_for(c["cfg"], dom), is_q, b, w)
     insts = srch.add_instances(c["states"], c["goals"])
     for _ in range(len(c["bk_counts"])):
         srch.step()
@@ -232,6 +235,8 @@ def test_bellman_backups_match_reference(tag):
     val = np.concatenate([x[1] for x in srch.backup_log])
     idx = np.concatenate([x[2] for x in srch.backup_log])
     assert np.array_equal(st, c["bk_states"]) and np.array_equal(idx, c["bk_inst"])
+    if is_q:
+        assert np.array_equal(np.concatenate([x[3] for x in srch.backup_log]), c["bk_acts"])
     if str(c["cfg"][2]).endswith("net"):
         np.testing.assert_allclose(val, c["bk_vals"], rtol=0, atol=2e-5)
     else:

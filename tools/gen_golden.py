@@ -485,6 +485,58 @@ def gen_backup() -> None:
         print(tag, name, "steps", steps, "records", int(sum(cnt_l)), "finished", out[tag + "/finished"].astype(int),
               "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()))
 
+    def add_q(tag, domain_str, pathfind_str, heur, steps_l, max_steps, nnet=None):
+        """graph_q: labels of the popped edges, computed the way UpdateHeurQRLKeepGoalABC._get_labels_no_rb does at the END
+        of the instances' lives (updaters/updater_rl.py:169-189: per instance, edges in pop order, node.backup_act(action),
+        node.backup_val overwritten as it goes), then stored in step order like the V cases."""
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        if heur == "q_zero":
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurq_fixout"], torch.device("cpu"))
+        elif heur == "q_pseudo_fine":
+            pfns = wrap_q(make_pseudo_q_fine(domain.get_num_acts()))
+        else:
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, [nnet[0]], torch.device("cpu"), nnet_files=[nnet[1]])
+        pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
+        insts = pathfind.make_instances(states, goals, None, True)
+        pathfind.add_instances(insts)
+        per_step, owners_l = [], []
+        steps = 0
+        while (not all(i.finished() for i in insts)) and steps < max_steps:
+            live = [k for k, inst in enumerate(insts) if not inst.finished()]
+            before = {k: len(insts[k].get_edges_popped()) for k in live}
+            _, edges = pathfind.step()
+            steps += 1
+            owners = [k for k in live for _ in range(len(insts[k].get_edges_popped()) - before[k])]
+            assert len(owners) == len(edges)
+            per_step.append(edges)
+            owners_l.append(owners)
+        label = {}
+        for inst in insts:
+            for edge in inst.get_edges_popped():
+                v = edge.node.backup_act(edge.action)
+                edge.node.backup_val = v
+                label[id(edge)] = v
+        flat = [e for es in per_step for e in es]
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, "" if nnet is None else nnet[0]])
+        out[tag + "/bk_states"] = states_np([e.node.state for e in flat])
+        out[tag + "/bk_acts"] = np.array([e.action.action for e in flat], np.int32)
+        out[tag + "/bk_vals"] = np.array([label[id(e)] for e in flat], np.float64)
+        out[tag + "/bk_inst"] = np.array([k for o in owners_l for k in o], np.int32)
+        out[tag + "/bk_counts"] = np.array([len(es) for es in per_step], np.int64)
+        out[tag + "/finished"] = np.array([i.finished() for i in insts])
+        out[tag + "/path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
+        print(tag, name, "steps", steps, "records", len(flat), "finished", out[tag + "/finished"].astype(int),
+              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()))
+
+    add_q("q_cube3_zero", "cube3", "graph.10B", "q_zero", [0, 1, 2, 1], 40)
+    add_q("q_cube3_fine", "cube3", "graph.20B_0.6W", "q_pseudo_fine", [20, 40, 3, 60], 10)
+    add_q("q_lo5_fine", "lightsout.5", "graph.8B_0.5W", "q_pseudo_fine", [3, 8, 1, 15], 10)
+    add_q("q_grid7_net", "grid.7d", "graph.3B_1.0W", "q_net", list(np.arange(8) * 5), 60,
+          ("heurq_fixout,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt")))
     add("cube3_zero", "cube3", "graph.10B", "v_zero", [0, 1, 2, 3, 1, 2], 100)
     add("cube3_fine", "cube3", "graph.20B_0.6W", "v_pseudo_fine", [20, 40, 3, 60], 10)
     add("np4_fine", "npuzzle.4", "graph.30B_0.8W", "v_pseudo_fine", [10, 30, 2, 60, 90], 12)

@@ -15,6 +15,7 @@ LIB_PATH = os.environ.get("DXB200_LIB") or os.path.join(HERE, "libdxb200.so")   
 
 DX_DOMAIN = {"cube3": 0, "npuzzle": 1, "grid": 2, "lightsout": 3}
 DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q, DX_ALGO_BEAM_V, DX_ALGO_BEAM_Q = 0, 1, 2, 3
+DX_BACKUP_MODE = {"bellman": 0, "ub_solns": 1, "lhbl": 2}
 DX_ALGO = {"graph_v": DX_ALGO_GRAPH_V, "graph_q": DX_ALGO_GRAPH_Q, "beam_v": DX_ALGO_BEAM_V, "beam_q": DX_ALGO_BEAM_Q}
 DX_HEUR_ZERO, DX_HEUR_HOST, DX_HEUR_NET_FP32, DX_HEUR_NET_BF16 = 0, 1, 2, 3
 STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book", "gemm_hidden", "gemm_input"]
@@ -74,7 +75,7 @@ SIGNATURES = {
     "dx_all_finished": (C.c_int, [_engp, _i32p]),
     "dx_get_status": (C.c_int, [_engp, C.POINTER(dx_inst_status), C.c_int32]),
     "dx_get_counters": (C.c_int, [_engp, C.POINTER(dx_counters)]),
-    "dx_drain_backups": (C.c_int, [_engp, _u8p, _i32p, C.POINTER(C.c_double), _i32p, C.c_int64, C.POINTER(C.c_int64)]),
+    "dx_drain_backups": (C.c_int, [_engp, C.c_int32, _u8p, _i32p, C.POINTER(C.c_double), _i32p, C.c_int64, C.POINTER(C.c_int64)]),
     "dx_get_path": (C.c_int, [_engp, C.c_int32, _i32p, _u8p, C.c_int32, _i32p]),
     "dx_get_curr_nodes": (C.c_int, [_engp, C.c_int32, _u8p, _f32p, _f32p, C.c_int32, _i32p]),
     "dx_domain_info": (C.c_int, [C.c_int32, C.c_int32, _i32p, _i32p, _i32p, _i32p]),
@@ -271,18 +272,19 @@ class Engine:
         check(self._lib.dx_get_counters(self._h, C.byref(c)))
         return c
 
-    def drain_backups(self):
+    def drain_backups(self, mode: str = "bellman"):
         """graph_v -> (states [n, S] uint8, backups [n] float64, insts [n] int32): Node.bellman_backup() of every node expanded
         since the last drain, in the reference's `popped` order (updaters/updater_rl.py:143-158);
         graph_q -> (states, actions [n] int32, backups, insts): Node.backup_act(action) of every popped edge (:169-189).
-        Empties the log."""
+        mode (graph_v): "bellman" | "ub_solns" (ub_heur_solns) | "lhbl" (Node.tree_backup) -- the options of UpRLArgs
+        (base/updater.py:669-672), computed over the records in the log at drain time.  Empties the log."""
         cap = self.max_backups
         st = np.empty((cap, self.state_bytes), np.uint8)
         bk = np.empty(cap, np.float64)
         ins = np.empty(cap, np.int32)
         act = np.empty(cap, np.int32)
         n = C.c_int64()
-        check(self._lib.dx_drain_backups(self._h, _p(st, _u8p), _p(act, _i32p), bk.ctypes.data_as(C.POINTER(C.c_double)),
+        check(self._lib.dx_drain_backups(self._h, DX_BACKUP_MODE[mode], _p(st, _u8p), _p(act, _i32p), bk.ctypes.data_as(C.POINTER(C.c_double)),
                                          _p(ins, _i32p), cap, C.byref(n)))
         k = n.value
         if self.is_q:

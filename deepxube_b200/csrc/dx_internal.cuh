@@ -77,6 +77,8 @@ struct Ctl {
     uint32_t pass_skip[DX_NUM_DIGITS];
     uint32_t n_backups;    // records in the Bellman-backup log (evaluate-all engines)
     uint32_t backup_overflow;
+    uint32_t backup_at;    // log position of this iteration's first record
+    uint32_t pad_;
 };
 
 // Per-instance state (structure of arrays, capacity max_instances (+1 for offset arrays)).
@@ -97,6 +99,22 @@ struct InstArrays {
     uint32_t* tile_off;         // [I+1] merge tile offsets
     unsigned long long* f_first;// key of the first popped entry this iteration
     uint8_t* goals;             // [I, SP] goal rows
+};
+
+// Training-label log (engines created with dx_config.max_backups > 0): one record per expanded node (A*) / popped edge (Q*)
+struct BackupLog {
+    uint8_t* state;      // [cap, SP] the record's state row
+    double* val;         // [cap] label (NaN: popped by an instance that had finished -- dropped at the drain)
+    uint32_t* inst;      // [cap]
+    uint8_t* act;        // [cap] Q*: the edge's action
+    // A* only: what the drain-time passes (ub_heur_solns parent paths, LHBL tree backup) need
+    uint8_t* solved;     // [cap]
+    uint32_t* node;      // [cap] node id of the record
+    uint32_t* itr;       // [cap] PathFind.itr when it was expanded
+    float* child_h;      // [cap, A] heuristic of every child
+    uint32_t* child_id;  // [cap, A] node id of a kept child, DX_NIL for a child the CLOSED filter dropped
+    uint32_t* node_rec;  // [max_nodes] record index + 1 of an expanded node, 0 = none
+    uint32_t cap;
 };
 
 struct NetDev {
@@ -215,13 +233,17 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
                            int max_children, const float* child_h = nullptr, float* node_h = nullptr);
 int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
                              const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
-                             uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint32_t bk_cap, int max_pop);
+                             const BackupLog& bk, int max_pop);
+int dx_launch_backup_children(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint8_t* child_flags,
+                              const uint32_t* child_prefix, const BackupLog& bk, int max_children);
+int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const BackupLog& bk);
+int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr);
+int dx_launch_backup_clear_map(cudaStream_t s, const Ctl* ctl, const BackupLog& bk);
 int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped, const uint32_t* pop_off,
                           const uint8_t* pop_solved, uint8_t* node_solved, int max_pop);
 int dx_launch_bellman_backup_q(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* node_state, const uint32_t* node_parent,
                                const uint8_t* node_action, const float* node_h, const uint8_t* node_solved,
-                               const uint32_t* edge_inst, uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint8_t* bk_act,
-                               uint32_t bk_cap, int max_pop);
+                               const uint32_t* edge_inst, const BackupLog& bk, int max_pop);
 int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,
                             const uint32_t* child_slot, const uint8_t* child_flags, int max_items);
 

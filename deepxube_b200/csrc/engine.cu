@@ -205,9 +205,10 @@ struct dx_engine {
     // evaluate-all engines (dx_config.max_backups > 0): the heuristic of EVERY generated child, before the CLOSED filter,
     // and the Bellman-backup log of the expanded nodes
     bool eval_all = false;
-    float* child_h = nullptr; uint8_t* bk_state = nullptr; double* bk_val = nullptr; uint32_t* bk_inst = nullptr;
+    float* child_h = nullptr;
+    BackupLog bk = {};
     bool backups_q = false;          // graph_q with a backup log: labels of the popped edges
-    uint8_t* bk_act = nullptr; uint8_t* node_solved = nullptr;
+    uint8_t* node_solved = nullptr;
     uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
     uint32_t* edge_tmp = nullptr; uint8_t* pop_solved = nullptr;
     // HDA* mode (hash-distributed single search)
@@ -385,6 +386,7 @@ static int reset_state(dx_engine* e) {
         DX_CUDA(cudaMemsetAsync(e->open_off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream));
     }
     if (e->node_solved) DX_CUDA(cudaMemsetAsync(e->node_solved, 0, e->max_nodes, e->stream));
+    if (e->bk.node_rec) DX_CUDA(cudaMemsetAsync(e->bk.node_rec, 0, (size_t)e->max_nodes * sizeof(uint32_t), e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
     e->n_inst = 0;
     e->parity = 0;
@@ -460,8 +462,13 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->backups_q = cfg->max_backups > 0 && e->is_q;
     if (cfg->max_backups > 0) {
         const size_t K = (size_t)cfg->max_backups;
-        A_(e->bk_state, K * e->SP); A_(e->bk_val, K); A_(e->bk_inst, K); A_(e->bk_act, K);
-        if (e->eval_all) A_(e->child_h, C + 1);
+        e->bk.cap = (uint32_t)K;
+        A_(e->bk.state, K * e->SP); A_(e->bk.val, K); A_(e->bk.inst, K); A_(e->bk.act, K);
+        if (e->eval_all) {
+            A_(e->child_h, C + 1);
+            A_(e->bk.solved, K); A_(e->bk.node, K); A_(e->bk.itr, K); A_(e->bk.child_h, K * e->A); A_(e->bk.child_id, K * e->A);
+            A_(e->bk.node_rec, N);
+        }
         if (e->backups_q) A_(e->node_solved, N);
     }
     A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
@@ -670,8 +677,7 @@ static int step_v_filter(dx_engine* e) {
     if (e->eval_all) {
         stage_begin(e, ST_BOOK);
         e->launches += dx_launch_bellman_backup(s, e->dom, e->d_ctl, e->ia, e->node_state, e->popped[p], e->popped_inst[p],
-                                                e->pop_solved, e->child_h, e->bk_state, e->bk_val, e->bk_inst,
-                                                (uint32_t)e->cfg.max_backups, e->max_pop);
+                                                e->pop_solved, e->child_h, e->bk, e->max_pop);
         stage_end(e);
     }
     stage_begin(e, ST_CLOSED);
@@ -691,6 +697,7 @@ static int step_v_filter(dx_engine* e) {
                                           e->child_flags, e->child_prefix, e->popped[p], e->popped_inst[p], e->node_state,
                                           e->node_g, e->node_parent, e->node_action, e->new_inst, e->max_children,
                                           e->eval_all ? e->child_h : nullptr, e->node_h);
+    if (e->eval_all) e->launches += dx_launch_backup_children(s, e->dom, e->d_ctl, e->child_flags, e->child_prefix, e->bk, e->max_children);
     stage_end(e);
     return DX_OK;
 }
@@ -770,8 +777,7 @@ static int step_q_b(dx_engine* e) {
     stage_begin(e, ST_BOOK);
     if (e->backups_q)
         e->launches += dx_launch_bellman_backup_q(e->stream, e->dom, e->d_ctl, e->node_state, e->node_parent, e->node_action,
-                                                  e->node_h, e->node_solved, e->popped_inst[q], e->bk_state, e->bk_val,
-                                                  e->bk_inst, e->bk_act, (uint32_t)e->cfg.max_backups, e->max_pop);
+                                                  e->node_h, e->node_solved, e->popped_inst[q], e->bk, e->max_pop);
     e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, e->is_beam ? 3 : 1);
     stage_end(e);
     e->parity = q;
@@ -973,25 +979,40 @@ extern "C" int dx_get_status(dx_engine* e, dx_inst_status* out, int32_t cap) {
 // Bellman-backup log (evaluate-all engines): one record per node expanded since the last drain, in expansion order
 // (iteration, then instance, then pop order -- the order of the `popped` lists PathFind.step() returns,
 // base/pathfinding.py:349,399) -> the (state, target) pairs of UpdateHeurVRLKeepGoalABC (updaters/updater_rl.py:143-158).
-extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap,
-                                int64_t* n_out) {
+extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int32_t* actions, double* backups, int32_t* insts,
+                                int64_t cap, int64_t* n_out) {
     if (!e || !n_out) DX_FAIL(DX_ERR_ARG, "null argument");
     if (!e->eval_all && !e->backups_q) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
+    if (mode != DX_BACKUP_BELLMAN && mode != DX_BACKUP_UB_SOLNS && mode != DX_BACKUP_LHBL) DX_FAIL(DX_ERR_ARG, "unknown backup mode");
+    if (mode != DX_BACKUP_BELLMAN && e->backups_q)
+        DX_FAIL(DX_ERR_UNSUPPORTED, "ub_heur_solns / LHBL labels are implemented for graph_v only");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_TRY(sync_ctl(e));
     const size_t n = e->h_ctl->n_backups;
     const int SP = e->SP, S = e->S;
+    cudaStream_t s = e->stream;
+    if (n && e->eval_all) {                         // drain-time passes over the whole log (labels are final only now)
+        if (mode == DX_BACKUP_UB_SOLNS) {
+            e->launches += dx_launch_backup_ub_paths(s, e->d_ctl, e->node_parent, e->bk);
+        } else if (mode == DX_BACKUP_LHBL) {
+            uint32_t it_first = 0, it_last = 0;     // the log is in iteration order
+            DX_CUDA(cudaMemcpyAsync(&it_first, e->bk.itr, 4, cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(&it_last, e->bk.itr + (n - 1), 4, cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaStreamSynchronize(s));
+            for (uint32_t it = it_last + 1; it-- > it_first;) e->launches += dx_launch_backup_tree(s, e->dom, e->d_ctl, e->bk, it);
+        }
+    }
     std::vector<uint8_t> rows(n * SP);
     std::vector<double> vals(n);
     std::vector<uint32_t> inst(n);
     std::vector<uint8_t> act(n);
     if (n) {
-        if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk_act, n, cudaMemcpyDeviceToHost, e->stream));
-        DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk_state, rows.size(), cudaMemcpyDeviceToHost, e->stream));
-        DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk_val, n * sizeof(double), cudaMemcpyDeviceToHost, e->stream));
-        DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk_inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, e->stream));
-        DX_CUDA(cudaStreamSynchronize(e->stream));
+        if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk.act, n, cudaMemcpyDeviceToHost, s));
+        DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk.state, rows.size(), cudaMemcpyDeviceToHost, s));
+        DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk.val, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+        DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk.inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+        DX_CUDA(cudaStreamSynchronize(s));
     }
     int64_t m = 0;
     for (size_t r = 0; r < n; ++r) m += vals[r] == vals[r] ? 1 : 0;        // NaN: popped by an instance that had finished
@@ -1006,9 +1027,10 @@ extern "C" int dx_drain_backups(dx_engine* e, uint8_t* states, int32_t* actions,
         if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
         ++k;
     }
-    k_reset_backups<<<1, 1, 0, e->stream>>>(e->d_ctl);
+    if (e->eval_all) e->launches += dx_launch_backup_clear_map(s, e->d_ctl, e->bk);
+    k_reset_backups<<<1, 1, 0, s>>>(e->d_ctl);
     e->launches += 1;
-    DX_CUDA(cudaStreamSynchronize(e->stream));
+    DX_CUDA(cudaStreamSynchronize(s));
     return DX_OK;
 }
 

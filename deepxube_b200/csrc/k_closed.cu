@@ -225,32 +225,39 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
 __global__ void __launch_bounds__(256)
 k_bellman_backup(DomainDev d, Ctl* __restrict__ ctl, InstArrays ia, const uint8_t* __restrict__ node_state,
                  const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
-                 const uint8_t* __restrict__ pop_solved, const float* __restrict__ child_h, uint8_t* __restrict__ bk_state,
-                 double* __restrict__ bk_val, uint32_t* __restrict__ bk_inst, uint32_t bk_cap) {
+                 const uint8_t* __restrict__ pop_solved, const float* __restrict__ child_h, BackupLog bk) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_children / (uint32_t)d.A, at = ctl->n_backups;
-    if ((unsigned long long)at + n > bk_cap) {
+    if ((unsigned long long)at + n > bk.cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl->backup_overflow = 1;     // turned into ctl->error by k_backup_commit
         return;
     }
     const int chunks = d.SP / 16;
+    const uint32_t itr = ctl->itr;
     unsigned long long skipped = 0;
     for (uint32_t j = blockIdx.x * blockDim.x + threadIdx.x; j < n; j += gridDim.x * blockDim.x) {
-        const uint32_t inst = popped_inst[j];
+        const uint32_t inst = popped_inst[j], id = popped[j];
+        const bool act = ia.active[inst] != 0, solved = act && pop_solved[j];
         double v;
-        if (!ia.active[inst]) {
+        if (!act) {
             v = __longlong_as_double(0x7ff8000000000000ll);
             skipped += (unsigned long long)d.A;
-        } else if (pop_solved[j]) {
+        } else if (solved) {
             v = 0.0;
         } else {
             v = __longlong_as_double(0x7ff0000000000000ll);
             for (int a = 0; a < d.A; ++a) v = fmin(v, 1.0 + (double)child_h[(size_t)j * d.A + a]);
         }
-        bk_val[at + j] = v;
-        bk_inst[at + j] = inst;
-        const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)popped[j] * d.SP);
-        uint4* dst = reinterpret_cast<uint4*>(bk_state + (size_t)(at + j) * d.SP);
+        const size_t r = (size_t)at + j;
+        bk.val[r] = v;
+        bk.inst[r] = inst;
+        bk.solved[r] = solved ? 1 : 0;
+        bk.node[r] = id;
+        bk.itr[r] = itr;
+        if (act) bk.node_rec[id] = (uint32_t)r + 1;          // node -> its record (tree / parent-path passes at drain time)
+        for (int a = 0; a < d.A; ++a) bk.child_h[r * d.A + a] = child_h[(size_t)j * d.A + a];
+        const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)id * d.SP);
+        uint4* dst = reinterpret_cast<uint4*>(bk.state + r * d.SP);
         for (int q = 0; q < chunks; ++q) dst[q] = src[q];
     }
     if (skipped) atomicAdd(&ctl->heur_evals, 0ull - skipped);
@@ -259,7 +266,96 @@ k_bellman_backup(DomainDev d, Ctl* __restrict__ ctl, InstArrays ia, const uint8_
 __global__ void k_backup_commit(Ctl* ctl, int A) {
     if (ctl->error) return;
     if (ctl->backup_overflow) { ctl->error |= DX_DEVERR_BACKUPS; return; }
+    ctl->backup_at = ctl->n_backups;
     ctl->n_backups += A > 0 ? ctl->n_children / (uint32_t)A : ctl->n_kept;
+}
+
+// after the CLOSED filter: which children of this iteration's records became nodes (kept children, ids in push order)
+__global__ void __launch_bounds__(256)
+k_backup_children(DomainDev d, const Ctl* __restrict__ ctl, const uint8_t* __restrict__ child_flags,
+                  const uint32_t* __restrict__ child_prefix, BackupLog bk) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children, base = ctl->node_base;
+    const size_t at = (size_t)ctl->backup_at * d.A;
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
+        bk.child_id[at + ci] = (child_flags[ci] & 1) ? base + child_prefix[ci] : DX_NIL;
+}
+
+__device__ __forceinline__ void atomic_min_f64(double* addr, double v) {
+    unsigned long long* a = reinterpret_cast<unsigned long long*>(addr);
+    unsigned long long old = *a;
+    while (__longlong_as_double((long long)old) > v) {
+        const unsigned long long seen = atomicCAS(a, old, (unsigned long long)__double_as_longlong(v));
+        if (seen == old) break;
+        old = seen;
+    }
+}
+
+// ub_heur_solns (updaters/updater_rl.py:148-152 over Node.upper_bound_parent_path, base/pathfinding.py:49-53): every solved
+// expanded node bounds the backup of its ancestors by the path cost down to it (transition costs 1.0).
+__global__ void __launch_bounds__(256)
+k_backup_ub_paths(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ node_parent, BackupLog bk) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (!bk.solved[r]) continue;
+        uint32_t id = bk.node[r];
+        double dist = 0.0;
+        for (uint32_t par = node_parent[id]; par != DX_NIL; par = node_parent[id]) {
+            dist += 1.0;
+            const uint32_t rr = bk.node_rec[par];
+            if (rr) atomic_min_f64(&bk.val[rr - 1], dist);
+            id = par;
+        }
+    }
+}
+
+// LHBL (updaters/updater_rl.py:153-155 over Node.tree_backup, base/pathfinding.py:55-64), one search iteration per launch, last
+// iteration first (a child is expanded in a later iteration than its parent, so its value is final when the parent reads it):
+//     0 if solved, else min_a (1.0 + (child_a was expanded ? tree value of child_a : max(heuristic(child_a), 0)))
+__global__ void __launch_bounds__(256)
+k_backup_tree(DomainDev d, const Ctl* __restrict__ ctl, BackupLog bk, uint32_t itr) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (bk.itr[r] != itr || bk.val[r] != bk.val[r]) continue;
+        double v = 0.0;
+        if (!bk.solved[r]) {
+            v = __longlong_as_double(0x7ff0000000000000ll);
+            for (int a = 0; a < d.A; ++a) {
+                const uint32_t cid = bk.child_id[(size_t)r * d.A + a];
+                const uint32_t rr = cid != DX_NIL ? bk.node_rec[cid] : 0;
+                const double cv = rr ? bk.val[rr - 1] : fmax((double)bk.child_h[(size_t)r * d.A + a], 0.0);
+                v = fmin(v, 1.0 + cv);
+            }
+        }
+        bk.val[r] = v;
+    }
+}
+
+// the drained records' nodes lose their record
+__global__ void k_backup_clear_map(const Ctl* __restrict__ ctl, BackupLog bk) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t id = bk.node[r];
+        if (bk.node_rec[id] == r + 1) bk.node_rec[id] = 0;
+    }
+}
+
+int dx_launch_backup_children(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint8_t* child_flags,
+                              const uint32_t* child_prefix, const BackupLog& bk, int max_children) {
+    k_backup_children<<<min(dx_div_up(max_children, 256), 148 * 8), 256, 0, s>>>(d, ctl, child_flags, child_prefix, bk);
+    return 1;
+}
+int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const BackupLog& bk) {
+    k_backup_ub_paths<<<148 * 4, 256, 0, s>>>(ctl, node_parent, bk);
+    return 1;
+}
+int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr) {
+    k_backup_tree<<<148 * 4, 256, 0, s>>>(d, ctl, bk, itr);
+    return 1;
+}
+int dx_launch_backup_clear_map(cudaStream_t s, const Ctl* ctl, const BackupLog& bk) {
+    k_backup_clear_map<<<148 * 4, 256, 0, s>>>(ctl, bk);
+    return 1;
 }
 
 // Q*: remember is_solved of the nodes popped this iteration (PathFind.set_is_solved, base/pathfinding.py:353): the label of
@@ -282,22 +378,21 @@ __global__ void __launch_bounds__(256)
 k_bellman_backup_q(DomainDev d, Ctl* __restrict__ ctl, const uint8_t* __restrict__ node_state,
                    const uint32_t* __restrict__ node_parent, const uint8_t* __restrict__ node_action,
                    const float* __restrict__ node_h, const uint8_t* __restrict__ node_solved,
-                   const uint32_t* __restrict__ edge_inst, uint8_t* __restrict__ bk_state, double* __restrict__ bk_val,
-                   uint32_t* __restrict__ bk_inst, uint8_t* __restrict__ bk_act, uint32_t bk_cap) {
+                   const uint32_t* __restrict__ edge_inst, BackupLog bk) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_kept, base = ctl->node_base, at = ctl->n_backups;
-    if ((unsigned long long)at + n > bk_cap) {
+    if ((unsigned long long)at + n > bk.cap) {
         if (blockIdx.x == 0 && threadIdx.x == 0) ctl->backup_overflow = 1;
         return;
     }
     const int chunks = d.SP / 16;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t id = base + k, par = node_parent[id];
-        bk_val[at + k] = node_solved[par] ? 0.0 : 1.0 + (double)node_h[id];
-        bk_inst[at + k] = edge_inst[k];
-        bk_act[at + k] = node_action[id];
+        bk.val[at + k] = node_solved[par] ? 0.0 : 1.0 + (double)node_h[id];
+        bk.inst[at + k] = edge_inst[k];
+        bk.act[at + k] = node_action[id];
         const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)par * d.SP);
-        uint4* dst = reinterpret_cast<uint4*>(bk_state + (size_t)(at + k) * d.SP);
+        uint4* dst = reinterpret_cast<uint4*>(bk.state + (size_t)(at + k) * d.SP);
         for (int q = 0; q < chunks; ++q) dst[q] = src[q];
     }
 }
@@ -310,21 +405,18 @@ int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped
 
 int dx_launch_bellman_backup_q(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* node_state, const uint32_t* node_parent,
                                const uint8_t* node_action, const float* node_h, const uint8_t* node_solved,
-                               const uint32_t* edge_inst, uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint8_t* bk_act,
-                               uint32_t bk_cap, int max_pop) {
+                               const uint32_t* edge_inst, const BackupLog& bk, int max_pop) {
     k_bellman_backup_q<<<min(dx_div_up(max_pop, 256), 148 * 4), 256, 0, s>>>(d, ctl, node_state, node_parent, node_action, node_h,
-                                                                            node_solved, edge_inst, bk_state, bk_val, bk_inst,
-                                                                            bk_act, bk_cap);
+                                                                            node_solved, edge_inst, bk);
     k_backup_commit<<<1, 1, 0, s>>>(ctl, 0);
     return 2;
 }
 
 int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
                              const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
-                             uint8_t* bk_state, double* bk_val, uint32_t* bk_inst, uint32_t bk_cap, int max_pop) {
+                             const BackupLog& bk, int max_pop) {
     k_bellman_backup<<<min(dx_div_up(max_pop, 256), 148 * 4), 256, 0, s>>>(d, ctl, ia, node_state, popped, popped_inst,
-                                                                                pop_solved, child_h, bk_state, bk_val, bk_inst,
-                                                                                bk_cap);
+                                                                                pop_solved, child_h, bk);
     k_backup_commit<<<1, 1, 0, s>>>(ctl, d.A);
     return 2;
 }

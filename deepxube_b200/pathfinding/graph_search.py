@@ -139,9 +139,10 @@ class GraphSearch(PathFind):
         if max_instances:
             self._max_instances = max(self._max_instances or 0, int(max_instances))
 
-    def drain_backups(self):
-        """-> (state rows [n, S], [graph_q: action ids [n],] backups float64 [n], instance slots [n]) since the last drain"""
-        return self._engine.drain_backups()
+    def drain_backups(self, mode: str = "bellman"):
+        """-> (state rows [n, S], [graph_q: action ids [n],] backups float64 [n], instance slots [n]) since the last drain;
+        mode "bellman" | "ub_solns" | "lhbl" (graph_v)"""
+        return self._engine.drain_backups(mode)
 
     # ---- PathFind protocol -----------------------------------------------------------------------------
     def make_instances(self, states: List[Any], goals: List[Any], inst_infos: Optional[List[Any]] = None,

@@ -164,8 +164,18 @@ int dx_get_counters(dx_engine* e, dx_counters* out);
  * float64 like the reference's Python floats.  states [cap, state_bytes], actions [cap], backups [cap], insts [cap] (any
  * may be NULL); *n = records written.  DX_ERR_ARG with *n = the count when cap is too small (nothing is drained).  The log is
  * emptied on success.  An iteration takes one log slot per popped node / edge (graph_v: slots of nodes popped by an
- * instance in the iteration it finished are dropped at the drain): size max_backups accordingly. */
-int dx_drain_backups(dx_engine* e, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap, int64_t* n);
+ * instance in the iteration it finished are dropped at the drain): size max_backups accordingly.
+ *
+ * mode (graph_v; graph_q takes DX_BACKUP_BELLMAN only) selects the label of the updater's options (UpRLArgs, base/updater.py:669-672),
+ * computed over ALL records in the log at the time of the drain -- drain when the instances' lives end, like the reference:
+ *   DX_BACKUP_BELLMAN   as above
+ *   DX_BACKUP_UB_SOLNS  ub_heur_solns: additionally every solved expanded node bounds the label of each ancestor by the path
+ *                       cost down to it (Node.upper_bound_parent_path, base/pathfinding.py:49-53; updater_rl.py:148-152)
+ *   DX_BACKUP_LHBL      lhbl: Node.tree_backup() from the roots (base/pathfinding.py:55-64; updater_rl.py:153-155): 0 if solved
+ *                       else min_a (1.0 + (child_a was expanded ? its tree backup : max(heuristic(child_a), 0))) */
+enum dx_backup_mode { DX_BACKUP_BELLMAN = 0, DX_BACKUP_UB_SOLNS = 1, DX_BACKUP_LHBL = 2 };
+int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap,
+                     int64_t* n);
 
 /* get_path (base/pathfinding.py:93-120): device-side parent walk from goal_node.  actions [cap],
  * states_on_path [(cap+1), state_bytes] (may be NULL).  *len = number of actions (path length). */

@@ -160,6 +160,7 @@ class OracleSearch:
         # Bellman backups of the popped nodes, per step: (states, backup values float64, instance index) -- what
         # UpdateHeurVRLKeepGoalABC._get_labels_no_rb (updaters/updater_rl.py:143-158) reads after each PathFind.step()
         self.backup_log: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = []
+        self.expansions: List[dict] = []      # A*: one entry per (step, instance), in backup_log order
 
     # zero heuristic defaults (ref: base/pathfind_fns.py:205-210, 235-243)
     def _heur(self, states: np.ndarray, goals: np.ndarray) -> np.ndarray:
@@ -237,10 +238,14 @@ class OracleSearch:
                 ids = inst.nodes_curr
                 pst = inst.store.state[ids]
                 solved = dom.is_solved(pst, np.broadcast_to(inst.goal, (len(ids), dom.goal_len)))
-                mins = (1.0 + np.asarray(p[5], np.float64)).reshape(len(ids), a).min(axis=1) if len(ids) else np.zeros(0)
+                ch = np.asarray(p[5], np.float64).reshape(len(ids), a)
+                mins = (1.0 + ch).min(axis=1) if len(ids) else np.zeros(0)
                 bst.append(pst.copy())
                 bval.append(np.where(solved, 0.0, mins))
                 bidx.append(np.full(len(ids), self.instances.index(inst), np.int32))
+                # what the other label options need (labels_v): the expanded nodes, their children's values / node ids
+                p.append(dict(inst=self.instances.index(inst), node=np.asarray(ids).copy(), solved=solved.copy(), child_h=ch,
+                              child_id=np.full((len(ids), a), -1, np.int64)))
             self.backup_log.append((np.concatenate(bst), np.concatenate(bval), np.concatenate(bidx)))
         keeps = []
         for p in per:
@@ -258,9 +263,12 @@ class OracleSearch:
                 p[5] = hh
         rec = []
         for p, keep in zip(per, keeps):
-            inst, cst, cg, cpar, cact, h = p
+            inst, cst, cg, cpar, cact, h = p[:6]
             popped_prev = inst.nodes_curr
             new_ids = inst.store.append(cst[keep], cg[keep], cpar[keep], cact[keep])
+            if len(p) > 6:
+                p[6]["child_id"].reshape(-1)[keep] = new_ids
+                self.expansions.append(p[6])
             inst.store.h[new_ids] = h[keep]
             costs = np.array(inst.weight) * cg[keep] + h[keep]          # float64, graph_search.py:153
             inst.push(new_ids, costs)
@@ -270,6 +278,47 @@ class OracleSearch:
                                 lb=inst.lb, ub=inst.ub, open=len(inst.open), closed=len(inst.closed)))
         if self.trace_on:
             self.trace.append(rec)
+
+    def labels_v(self, mode: str) -> np.ndarray:
+        """Labels of all expanded nodes so far, in backup_log order, for the updater's options (UpRLArgs, base/updater.py:669-672;
+        UpdateHeurVRLKeepGoalABC._get_labels_no_rb, updaters/updater_rl.py:143-158):
+          "bellman"   Node.bellman_backup() of every popped node
+          "ub_solns"  + every solved popped node bounds its ancestors' values by the path cost down to it
+                      (Node.upper_bound_parent_path, base/pathfinding.py:49-53)
+          "lhbl"      Node.tree_backup() from the root (base/pathfinding.py:55-64)"""
+        recs = []                                  # (inst, node, solved, child_h, child_id), flat, expansion order
+        for e in self.expansions:
+            for k in range(len(e["node"])):
+                recs.append((e["inst"], int(e["node"][k]), bool(e["solved"][k]), e["child_h"][k], e["child_id"][k]))
+        rec_of = {(r[0], r[1]): i for i, r in enumerate(recs)}
+        vals = np.array([0.0 if r[2] else float((1.0 + r[3]).min()) for r in recs])
+        if mode == "bellman":
+            return vals
+        if mode == "ub_solns":
+            for i, r in enumerate(recs):
+                if not r[2]:
+                    continue
+                store = self.instances[r[0]].store
+                node, dist = r[1], 0.0
+                while store.parent[node] >= 0:
+                    node = int(store.parent[node])
+                    dist += 1.0
+                    j = rec_of.get((r[0], node))
+                    if j is not None:
+                        vals[j] = min(vals[j], dist)
+            return vals
+        assert mode == "lhbl"
+        for i in range(len(recs) - 1, -1, -1):     # children are expanded after their parents
+            inst, _, solved, ch, cid = recs[i]
+            if solved:
+                vals[i] = 0.0
+                continue
+            best = np.inf
+            for a_i in range(len(ch)):
+                j = rec_of.get((inst, int(cid[a_i]))) if cid[a_i] >= 0 else None
+                best = min(best, 1.0 + (vals[j] if j is not None else max(float(ch[a_i]), 0.0)))
+            vals[i] = best
+        return vals
 
     # ---- batch weighted Q* -----------------------------------------------------------------------
     def _step_q(self, insts: List[OracleInstance]) -> None:

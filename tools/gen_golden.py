@@ -460,7 +460,7 @@ def gen_backup() -> None:
         pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
         insts = pathfind.make_instances(states, goals, None, True)
         pathfind.add_instances(insts)
-        st_l, val_l, idx_l, cnt_l = [], [], [], []
+        st_l, val_l, idx_l, cnt_l, popped_l = [], [], [], [], []
         steps = 0
         while (not all(i.finished() for i in insts)) and steps < max_steps:
             owners = [k for k, inst in enumerate(insts) if not inst.finished() for _ in inst._nodes_curr]
@@ -468,11 +468,24 @@ def gen_backup() -> None:
             assert len(popped) == len(owners)
             steps += 1
             vals = [node.bellman_backup() for node in popped]
+            popped_l.append(popped)
             assert all(isinstance(v, float) for v in vals), set(type(v) for v in vals)
             st_l.append(states_np([n.state for n in popped]) if popped else np.zeros((0, states_np(states).shape[1]), np.uint8))
             val_l.append(np.array(vals, np.float64))
             idx_l.append(np.array(owners, np.int32))
             cnt_l.append(len(popped))
+        # the updater's other label options over the same search (updaters/updater_rl.py:143-158), evaluated at the end of the
+        # instances' lives like the reference does: ub_heur_solns, then lhbl (tree_backup recomputes every value from scratch)
+        flat_nodes = [n for ns in popped_l for n in ns]
+        for node in flat_nodes:
+            node.bellman_backup()
+        for node in flat_nodes:
+            if node.is_solved:
+                node.upper_bound_parent_path(0.0)
+        out[tag + "/bk_vals_ub"] = np.array([n.backup_val for n in flat_nodes], np.float64)
+        for inst in insts:
+            inst.root_node.tree_backup()
+        out[tag + "/bk_vals_lhbl"] = np.array([n.backup_val for n in flat_nodes], np.float64)
         out[tag + "/states"] = states_np(states)
         out[tag + "/goals"] = goals_np(goals)
         out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, "" if nnet is None else nnet[0]])
@@ -483,7 +496,8 @@ def gen_backup() -> None:
         out[tag + "/finished"] = np.array([i.finished() for i in insts])
         out[tag + "/path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
         print(tag, name, "steps", steps, "records", int(sum(cnt_l)), "finished", out[tag + "/finished"].astype(int),
-              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()))
+              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()), "ub differs", int((out[tag + "/bk_vals_ub"] != out[tag + "/bk_vals"]).sum()),
+              "lhbl differs", int((out[tag + "/bk_vals_lhbl"] != out[tag + "/bk_vals"]).sum()))
 
     def add_q(tag, domain_str, pathfind_str, heur, steps_l, max_steps, nnet=None):
         """graph_q: labels of the popped edges, computed the way UpdateHeurQRLKeepGoalABC._get_labels_no_rb does at the END
@@ -539,6 +553,7 @@ def gen_backup() -> None:
           ("heurq_fixout,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt")))
     add("cube3_zero", "cube3", "graph.10B", "v_zero", [0, 1, 2, 3, 1, 2], 100)
     add("cube3_fine", "cube3", "graph.20B_0.6W", "v_pseudo_fine", [20, 40, 3, 60], 10)
+    add("cube3_fine_short", "cube3", "graph.60B_1.0W", "v_pseudo_fine", [1, 2, 2, 3, 1, 2], 12)
     add("np4_fine", "npuzzle.4", "graph.30B_0.8W", "v_pseudo_fine", [10, 30, 2, 60, 90], 12)
     add("lo5_fine", "lightsout.5", "graph.8B_0.5W", "v_pseudo_fine", [3, 8, 15], 10)
     add("grid7_net", "grid.7d", "graph.3B_1.0W", "v_net", list(np.arange(8) * 5), 60,

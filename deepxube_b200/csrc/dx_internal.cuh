@@ -107,13 +107,14 @@ struct BackupLog {
     double* val;         // [cap] label (NaN: popped by an instance that had finished -- dropped at the drain)
     uint32_t* inst;      // [cap]
     uint8_t* act;        // [cap] Q*: the edge's action
-    // A* only: what the drain-time passes (ub_heur_solns parent paths, LHBL tree backup) need
-    uint8_t* solved;     // [cap]
-    uint32_t* node;      // [cap] node id of the record
-    uint32_t* itr;       // [cap] PathFind.itr when it was expanded
+    // what the drain-time passes (ub_heur_solns parent paths, LHBL tree backup) need
+    uint32_t* node;      // [cap] A*: node id of the record; Q*: the node generated for the edge
+    uint32_t* itr;       // [cap] PathFind.itr when it was expanded / popped
+    uint8_t* solved;     // [cap] (A* only from here on)
     float* child_h;      // [cap, A] heuristic of every child
     uint32_t* child_id;  // [cap, A] node id of a kept child, DX_NIL for a child the CLOSED filter dropped
     uint32_t* node_rec;  // [max_nodes] record index + 1 of an expanded node, 0 = none
+    double* node_aux;    // [max_nodes] Q* drain-time passes: per-node bound (ub_heur_solns) / min over popped edges (lhbl)
     uint32_t cap;
 };
 
@@ -238,6 +239,8 @@ int dx_launch_backup_children(cudaStream_t s, const DomainDev& d, const Ctl* ctl
                               const uint32_t* child_prefix, const BackupLog& bk, int max_children);
 int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const BackupLog& bk);
 int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr);
+int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const uint8_t* node_solved,
+                             const float* node_h, const BackupLog& bk, int mode, uint32_t it_first, uint32_t it_last);
 int dx_launch_backup_clear_map(cudaStream_t s, const Ctl* ctl, const BackupLog& bk);
 int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped, const uint32_t* pop_off,
                           const uint8_t* pop_solved, uint8_t* node_solved, int max_pop);

@@ -469,7 +469,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
             A_(e->bk.solved, K); A_(e->bk.node, K); A_(e->bk.itr, K); A_(e->bk.child_h, K * e->A); A_(e->bk.child_id, K * e->A);
             A_(e->bk.node_rec, N);
         }
-        if (e->backups_q) A_(e->node_solved, N);
+        if (e->backups_q) { A_(e->node_solved, N); A_(e->bk.node, K); A_(e->bk.itr, K); A_(e->bk.node_aux, N); }
     }
     A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
     for (int p = 0; p < 2; ++p) {
@@ -984,24 +984,25 @@ extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int
     if (!e || !n_out) DX_FAIL(DX_ERR_ARG, "null argument");
     if (!e->eval_all && !e->backups_q) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
     if (mode != DX_BACKUP_BELLMAN && mode != DX_BACKUP_UB_SOLNS && mode != DX_BACKUP_LHBL) DX_FAIL(DX_ERR_ARG, "unknown backup mode");
-    if (mode != DX_BACKUP_BELLMAN && e->backups_q)
-        DX_FAIL(DX_ERR_UNSUPPORTED, "ub_heur_solns / LHBL labels are implemented for graph_v only");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_TRY(sync_ctl(e));
     const size_t n = e->h_ctl->n_backups;
     const int SP = e->SP, S = e->S;
     cudaStream_t s = e->stream;
-    if (n && e->eval_all) {                         // drain-time passes over the whole log (labels are final only now)
-        if (mode == DX_BACKUP_UB_SOLNS) {
-            e->launches += dx_launch_backup_ub_paths(s, e->d_ctl, e->node_parent, e->bk);
-        } else if (mode == DX_BACKUP_LHBL) {
-            uint32_t it_first = 0, it_last = 0;     // the log is in iteration order
+    if (n && mode != DX_BACKUP_BELLMAN) {           // drain-time passes over the whole log (labels are final only now)
+        uint32_t it_first = 0, it_last = 0;         // the log is in iteration order
+        if (mode == DX_BACKUP_LHBL) {
             DX_CUDA(cudaMemcpyAsync(&it_first, e->bk.itr, 4, cudaMemcpyDeviceToHost, s));
             DX_CUDA(cudaMemcpyAsync(&it_last, e->bk.itr + (n - 1), 4, cudaMemcpyDeviceToHost, s));
             DX_CUDA(cudaStreamSynchronize(s));
-            for (uint32_t it = it_last + 1; it-- > it_first;) e->launches += dx_launch_backup_tree(s, e->dom, e->d_ctl, e->bk, it);
         }
+        if (e->backups_q)
+            e->launches += dx_launch_backup_q_modes(s, e->d_ctl, e->node_parent, e->node_solved, e->node_h, e->bk, mode, it_first, it_last);
+        else if (mode == DX_BACKUP_UB_SOLNS)
+            e->launches += dx_launch_backup_ub_paths(s, e->d_ctl, e->node_parent, e->bk);
+        else
+            for (uint32_t it = it_last + 1; it-- > it_first;) e->launches += dx_launch_backup_tree(s, e->dom, e->d_ctl, e->bk, it);
     }
     std::vector<uint8_t> rows(n * SP);
     std::vector<double> vals(n);

@@ -331,6 +331,83 @@ k_backup_tree(DomainDev d, const Ctl* __restrict__ ctl, BackupLog bk, uint32_t i
     }
 }
 
+// ---- Q* label options, drain time (UpdateHeurQRLKeepGoalABC._get_labels_no_rb, updaters/updater_rl.py:169-189) ----
+// node_aux[node]: ub_heur_solns -> the parent-path bound; lhbl -> min over the node's popped edges of (1 + tree value of the child)
+__global__ void k_backup_q_fill(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ node_parent, BackupLog bk) {
+    const uint32_t n = ctl->n_backups;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        bk.node_aux[bk.node[r]] = inf;
+        bk.node_aux[node_parent[bk.node[r]]] = inf;
+    }
+}
+
+// ub_heur_solns: every popped edge whose node is solved bounds that node (0) and its ancestors (path cost down to it)
+__global__ void __launch_bounds__(256)
+k_backup_q_ub_paths(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ node_parent, const uint8_t* __restrict__ node_solved,
+                    BackupLog bk) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        uint32_t id = node_parent[bk.node[r]];
+        if (!node_solved[id]) continue;
+        double dist = 0.0;
+        for (;;) {
+            atomic_min_f64(&bk.node_aux[id], dist);
+            id = node_parent[id];
+            if (id == DX_NIL) break;
+            dist += 1.0;
+        }
+    }
+}
+
+// ... then Node.backup_act: 0 if solved else 1.0 + (node_next.backup_val if it was bounded else heuristic(node_next))
+__global__ void __launch_bounds__(256)
+k_backup_q_ub_labels(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ node_parent, const uint8_t* __restrict__ node_solved,
+                     const float* __restrict__ node_h, BackupLog bk) {
+    const uint32_t n = ctl->n_backups;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t c = bk.node[r];
+        const double ub = bk.node_aux[c];
+        bk.val[r] = node_solved[node_parent[c]] ? 0.0 : 1.0 + (ub < inf ? ub : (double)node_h[c]);
+    }
+}
+
+// lhbl: Node.tree_backup over the popped edges, one search iteration per launch, last first:
+//   T(c) = 0 if c is solved, else (c has popped edges ? min over them of (1 + T(child)) : max(heuristic(c), 0));
+//   label of the edge (p -> c) = 0 if p is solved else 1 + T(c)
+__global__ void __launch_bounds__(256)
+k_backup_q_tree(const Ctl* __restrict__ ctl, const uint32_t* __restrict__ node_parent, const uint8_t* __restrict__ node_solved,
+                const float* __restrict__ node_h, BackupLog bk, uint32_t itr) {
+    const uint32_t n = ctl->n_backups;
+    const double inf = __longlong_as_double(0x7ff0000000000000ll);
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (bk.itr[r] != itr) continue;
+        const uint32_t c = bk.node[r], p = node_parent[c];
+        const double em = bk.node_aux[c];
+        const double t = node_solved[c] ? 0.0 : (em < inf ? em : fmax((double)node_h[c], 0.0));
+        bk.val[r] = node_solved[p] ? 0.0 : 1.0 + t;
+        atomic_min_f64(&bk.node_aux[p], 1.0 + t);
+    }
+}
+
+int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const uint8_t* node_solved,
+                             const float* node_h, const BackupLog& bk, int mode, uint32_t it_first, uint32_t it_last) {
+    int launches = 1;
+    k_backup_q_fill<<<148 * 4, 256, 0, s>>>(ctl, node_parent, bk);
+    if (mode == 1) {
+        k_backup_q_ub_paths<<<148 * 4, 256, 0, s>>>(ctl, node_parent, node_solved, bk);
+        k_backup_q_ub_labels<<<148 * 4, 256, 0, s>>>(ctl, node_parent, node_solved, node_h, bk);
+        launches += 2;
+    } else {
+        for (uint32_t it = it_last + 1; it-- > it_first;) {
+            k_backup_q_tree<<<148 * 4, 256, 0, s>>>(ctl, node_parent, node_solved, node_h, bk, it);
+            launches += 1;
+        }
+    }
+    return launches;
+}
+
 // the drained records' nodes lose their record
 __global__ void k_backup_clear_map(const Ctl* __restrict__ ctl, BackupLog bk) {
     const uint32_t n = ctl->n_backups;
@@ -391,6 +468,8 @@ k_bellman_backup_q(DomainDev d, Ctl* __restrict__ ctl, const uint8_t* __restrict
         bk.val[at + k] = node_solved[par] ? 0.0 : 1.0 + (double)node_h[id];
         bk.inst[at + k] = edge_inst[k];
         bk.act[at + k] = node_action[id];
+        bk.node[at + k] = id;                       // the node generated for the edge
+        bk.itr[at + k] = ctl->itr;
         const uint4* src = reinterpret_cast<const uint4*>(node_state + (size_t)par * d.SP);
         uint4* dst = reinterpret_cast<uint4*>(bk.state + (size_t)(at + k) * d.SP);
         for (int q = 0; q < chunks; ++q) dst[q] = src[q];

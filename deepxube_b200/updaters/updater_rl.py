@@ -1,7 +1,7 @@
 """Training-data generation from the search: the value-iteration targets of the heuristic network.
 
 Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq` with the goal kept (no HER), no replay buffer;
-labels: Bellman backups, and for `heurv` also `ub_heur_solns` and LHBL tree backups:
+labels: Bellman backups, `ub_heur_solns`, LHBL tree backups:
 
     base/updater.py:343-400        update_runner: for each of `search_itrs` iterations -- add instances (new ones for the
                                    instances removed last iteration, same steps_gen), one PathFind.step(), remove the
@@ -29,9 +29,7 @@ class UpdateHeurVRLKeepGoal:
     def __init__(self, domain: Any, pathfind: GraphSearch, search_itrs: int, nnet_input: Optional[Any] = None,
                  ub_heur_solns: bool = False, lhbl: bool = False):
         """ub_heur_solns / lhbl: UpRLArgs (base/updater.py:669-672); lhbl wins when both are set, as in
-        updaters/updater_rl.py:145-155.  Both are computed on the device when the log is drained (graph_v only)."""
-        if self.is_q and (ub_heur_solns or lhbl):
-            raise NotImplementedError("ub_heur_solns / lhbl labels are implemented for the heurv updater only")
+        updaters/updater_rl.py:145-155, 171-179.  Both are computed on the device when the log is drained."""
         self.label_mode = "lhbl" if lhbl else ("ub_solns" if ub_heur_solns else "bellman")
         want = "graph_q" if self.is_q else "graph_v"
         if pathfind.is_q != self.is_q or pathfind.dx_algo not in (None, want):

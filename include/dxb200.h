@@ -166,13 +166,16 @@ int dx_get_counters(dx_engine* e, dx_counters* out);
  * emptied on success.  An iteration takes one log slot per popped node / edge (graph_v: slots of nodes popped by an
  * instance in the iteration it finished are dropped at the drain): size max_backups accordingly.
  *
- * mode (graph_v; graph_q takes DX_BACKUP_BELLMAN only) selects the label of the updater's options (UpRLArgs, base/updater.py:669-672),
- * computed over ALL records in the log at the time of the drain -- drain when the instances' lives end, like the reference:
+ * mode selects the label of the updater's options (UpRLArgs, base/updater.py:669-672), computed over ALL records in the log at
+ * the time of the drain -- drain when the instances' lives end, like the reference:
  *   DX_BACKUP_BELLMAN   as above
- *   DX_BACKUP_UB_SOLNS  ub_heur_solns: additionally every solved expanded node bounds the label of each ancestor by the path
- *                       cost down to it (Node.upper_bound_parent_path, base/pathfinding.py:49-53; updater_rl.py:148-152)
- *   DX_BACKUP_LHBL      lhbl: Node.tree_backup() from the roots (base/pathfinding.py:55-64; updater_rl.py:153-155): 0 if solved
- *                       else min_a (1.0 + (child_a was expanded ? its tree backup : max(heuristic(child_a), 0))) */
+ *   DX_BACKUP_UB_SOLNS  ub_heur_solns: every solved expanded node (graph_q: solved node of a popped edge) bounds the value of
+ *                       each ancestor by the path cost down to it (Node.upper_bound_parent_path, base/pathfinding.py:49-53;
+ *                       updater_rl.py:148-152, 172-176); graph_q labels then use the bound of node_next where there is one
+ *   DX_BACKUP_LHBL      lhbl: Node.tree_backup() from the roots (base/pathfinding.py:55-64; updater_rl.py:153-155, 177-179):
+ *                       0 if solved else min over the children (graph_q: over the popped edges) of
+ *                       (1.0 + (child was expanded ? its tree backup : max(heuristic(child), 0))); graph_q labels =
+ *                       1.0 + tree backup of node_next */
 enum dx_backup_mode { DX_BACKUP_BELLMAN = 0, DX_BACKUP_UB_SOLNS = 1, DX_BACKUP_LHBL = 2 };
 int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap,
                      int64_t* n);

@@ -160,7 +160,8 @@ class OracleSearch:
         # Bellman backups of the popped nodes, per step: (states, backup values float64, instance index) -- what
         # UpdateHeurVRLKeepGoalABC._get_labels_no_rb (updaters/updater_rl.py:143-158) reads after each PathFind.step()
         self.backup_log: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = []
-        self.expansions: List[dict] = []      # A*: one entry per (step, instance), in backup_log order
+        self.expansions: List[dict] = []      # one entry per (step, instance), in backup_log order
+        self.solved_mark: Dict[Tuple[int, int], bool] = {}     # Q*: Node.is_solved of the nodes that were popped (else None)
 
     # zero heuristic defaults (ref: base/pathfind_fns.py:205-210, 235-243)
     def _heur(self, states: np.ndarray, goals: np.ndarray) -> np.ndarray:
@@ -320,6 +321,40 @@ class OracleSearch:
             vals[i] = best
         return vals
 
+    def labels_q(self, mode: str) -> np.ndarray:
+        """Q* labels of all popped edges so far, in backup_log order (UpdateHeurQRLKeepGoalABC._get_labels_no_rb,
+        updaters/updater_rl.py:169-189): Node.backup_act(action) after the optional ub_heur_solns / lhbl passes."""
+        recs = []                                  # (inst, parent, child, h(child)), flat, pop order
+        for e in self.expansions:
+            for k in range(len(e["child"])):
+                recs.append((e["inst"], int(e["parent"][k]), int(e["child"][k]), float(e["child_h"][k])))
+        sol = lambda i, n: self.solved_mark.get((i, n), False)
+        if mode == "bellman":
+            return np.array([0.0 if sol(i, p) else 1.0 + h for i, p, c, h in recs])
+        if mode == "ub_solns":
+            ub: Dict[Tuple[int, int], float] = {}
+            for i, p, c, h in recs:
+                if not sol(i, p):
+                    continue
+                store = self.instances[i].store
+                node, dist = p, 0.0
+                while True:
+                    ub[(i, node)] = min(ub.get((i, node), np.inf), dist)
+                    if store.parent[node] < 0:
+                        break
+                    node = int(store.parent[node])
+                    dist += 1.0
+            return np.array([0.0 if sol(i, p) else 1.0 + ub.get((i, c), h) for i, p, c, h in recs])
+        assert mode == "lhbl"
+        emin: Dict[Tuple[int, int], float] = {}
+        vals = np.zeros(len(recs))
+        for r in range(len(recs) - 1, -1, -1):
+            i, p, c, h = recs[r]
+            t = 0.0 if sol(i, c) else (emin[(i, c)] if (i, c) in emin else max(h, 0.0))
+            vals[r] = 0.0 if sol(i, p) else 1.0 + t
+            emin[(i, p)] = min(emin.get((i, p), np.inf), 1.0 + t)
+        return vals
+
     # ---- batch weighted Q* -----------------------------------------------------------------------
     def _step_q(self, insts: List[OracleInstance]) -> None:
         dom, a = self.domain, self.domain.num_actions
@@ -329,7 +364,10 @@ class OracleSearch:
             st = inst.store
             pst = st.state[ids]
             goals = np.broadcast_to(inst.goal, (len(ids), dom.goal_len))
-            inst.record_goal(ids, dom.is_solved(pst, goals))
+            solved_now = dom.is_solved(pst, goals)
+            inst.record_goal(ids, solved_now)
+            for nid, sv in zip(ids, solved_now):                         # PathFind.set_is_solved (base/pathfinding.py:353)
+                self.solved_mark[(self.instances.index(inst), int(nid))] = bool(sv)
             keep = inst.check_closed(pst, st.g[ids])                     # closed test at pop, graph_search.py:132-133
             kid = ids[keep]
             # edges: kept-node order x action id (base/pathfinding.py:568-588)
@@ -361,6 +399,8 @@ class OracleSearch:
             hn = q.min(axis=1).astype(np.float64) if len(new_ids) else np.zeros(0)
             bq.append((inst.store.state[par].copy(), np.where(solved, 0.0, 1.0 + hn), np.full(len(par), self.instances.index(inst), np.int32),
                        np.asarray(act, np.int32)))
+            self.expansions.append(dict(inst=self.instances.index(inst), parent=np.asarray(par).copy(), child=np.asarray(new_ids).copy(),
+                                        child_h=hn.copy()))
             inst.nodes_curr = new_ids
             if self.trace_on:
                 rec.append(dict(popped=ids.copy(), keep=keep.copy(), f=costs.copy(), next=new_ids.copy(), lb=inst.lb,

@@ -365,8 +365,8 @@ def test_bf16_search_deviation_is_reported():
     eng.close()
 
 
-@pytest.mark.parametrize("is_q", [False, True])
-def test_updater_rl_bellman_targets_vs_oracle(is_q):
+@pytest.mark.parametrize("is_q,label_mode", [(False, "bellman"), (True, "bellman"), (False, "lhbl"), (False, "ub_solns"), (True, "lhbl"), (True, "ub_solns")])
+def test_updater_rl_bellman_targets_vs_oracle(is_q, label_mode):
     """SURVEY 8f.1 slice: one runner of the heurv / heurq RL updater (instances with batch size 1, replaced when they finish,
     base/updater.py:343-400) -- emitted (state, goal, [action,] backup) records equal the oracle's for the same instances."""
     from deepxube_b200.updaters.updater_rl import UpdateHeurQRLKeepGoal, UpdateHeurVRLKeepGoal
@@ -392,7 +392,7 @@ def test_updater_rl_bellman_targets_vs_oracle(is_q):
 
     steps_gen = [0, 1, 2, 1, 0, 3, 30, 40, 2, 1, 0, 25]
     search_itrs = 6
-    up = Rec(dom, pathfind, search_itrs)
+    up = Rec(dom, pathfind, search_itrs, lhbl=label_mode == "lhbl", ub_heur_solns=label_mode == "ub_solns")
     data = up.get_instance_data(steps_gen)
     states, goals, ctgs = data[0], data[1], data[-1]
     assert len(made) >= 2 and [len(m) for m in made][0] == len(steps_gen)          # finished instances were replaced
@@ -414,6 +414,8 @@ def test_updater_rl_bellman_targets_vs_oracle(is_q):
     if live:
         groups.append(live)
     st = np.concatenate([x[0] for x in orc.backup_log]); val = np.concatenate([x[1] for x in orc.backup_log])
+    if label_mode != "bellman":
+        val = orc.labels_q(label_mode) if is_q else orc.labels_v(label_mode)
     idx = np.concatenate([x[2] for x in orc.backup_log])
     order = np.concatenate([np.flatnonzero(idx == orc.instances.index(i)) for g in groups for i in g])
     assert np.array_equal(dom.states_to_rows(states), st[order])

@@ -237,9 +237,10 @@ def test_bellman_backups_match_reference(tag):
     assert np.array_equal(st, c["bk_states"]) and np.array_equal(idx, c["bk_inst"])
     if is_q:
         assert np.array_equal(np.concatenate([x[3] for x in srch.backup_log]), c["bk_acts"])
-    else:           # the updater's other label options: ub_heur_solns, lhbl (updaters/updater_rl.py:148-155)
+    # the updater's other label options: ub_heur_solns, lhbl (updaters/updater_rl.py:145-155, 171-179)
+    if True:
         for mode, key in (("bellman", "bk_vals"), ("ub_solns", "bk_vals_ub"), ("lhbl", "bk_vals_lhbl")):
-            got = srch.labels_v(mode)
+            got = srch.labels_q(mode) if is_q else srch.labels_v(mode)
             if str(c["cfg"][2]).endswith("net"):
                 np.testing.assert_allclose(got, c[key], rtol=0, atol=2e-5)
             else:

@@ -526,13 +526,32 @@ def gen_backup() -> None:
             assert len(owners) == len(edges)
             per_step.append(edges)
             owners_l.append(owners)
-        label = {}
-        for inst in insts:
-            for edge in inst.get_edges_popped():
-                v = edge.node.backup_act(edge.action)
-                edge.node.backup_val = v
-                label[id(edge)] = v
+        def labels(mode):
+            """_get_labels_no_rb of the Q updater, verbatim order of operations, from a clean slate (backup_val = inf)"""
+            for inst in insts:
+                for n in [inst.root_node] + inst.root_node.get_all_descendants():
+                    n.backup_val = np.inf
+            res = {}
+            if mode == "ub":
+                for inst in insts:
+                    for edge in inst.get_edges_popped():
+                        if edge.node.is_solved:
+                            edge.node.upper_bound_parent_path(0.0)
+            elif mode == "lhbl":
+                for inst in insts:
+                    inst.root_node.tree_backup()
+            for inst in insts:
+                for edge in inst.get_edges_popped():
+                    v = edge.node.backup_act(edge.action)
+                    edge.node.backup_val = v
+                    res[id(edge)] = v
+            return res
+
         flat = [e for es in per_step for e in es]
+        label = labels("bellman")
+        lab_ub, lab_lhbl = labels("ub"), labels("lhbl")
+        out[tag + "/bk_vals_ub"] = np.array([lab_ub[id(e)] for e in flat], np.float64)
+        out[tag + "/bk_vals_lhbl"] = np.array([lab_lhbl[id(e)] for e in flat], np.float64)
         out[tag + "/states"] = states_np(states)
         out[tag + "/goals"] = goals_np(goals)
         out[tag + "/cfg"] = np.array([domain_str, pathfind_str, heur, "" if nnet is None else nnet[0]])
@@ -544,10 +563,12 @@ def gen_backup() -> None:
         out[tag + "/finished"] = np.array([i.finished() for i in insts])
         out[tag + "/path_cost"] = np.array([i.path_cost() for i in insts], np.float64)
         print(tag, name, "steps", steps, "records", len(flat), "finished", out[tag + "/finished"].astype(int),
-              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()))
+              "zero-backups", int((out[tag + "/bk_vals"] == 0).sum()), "ub differs", int((out[tag + "/bk_vals_ub"] != out[tag + "/bk_vals"]).sum()),
+              "lhbl differs", int((out[tag + "/bk_vals_lhbl"] != out[tag + "/bk_vals"]).sum()))
 
     add_q("q_cube3_zero", "cube3", "graph.10B", "q_zero", [0, 1, 2, 1], 40)
     add_q("q_cube3_fine", "cube3", "graph.20B_0.6W", "q_pseudo_fine", [20, 40, 3, 60], 10)
+    add_q("q_cube3_fine_short", "cube3", "graph.60B_1.0W", "q_pseudo_fine", [1, 2, 2, 3, 1, 2], 12)
     add_q("q_lo5_fine", "lightsout.5", "graph.8B_0.5W", "q_pseudo_fine", [3, 8, 1, 15], 10)
     add_q("q_grid7_net", "grid.7d", "graph.3B_1.0W", "q_net", list(np.arange(8) * 5), 60,
           ("heurq_fixout,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt")))

@@ -49,7 +49,8 @@ class dx_hda_local(C.Structure):
 
 class dx_counters(C.Structure):
     _fields_ = [("nodes_stored", C.c_int64), ("heur_evals", C.c_int64), ("children_generated", C.c_int64),
-                ("iterations", C.c_int64), ("kernel_launches", C.c_int64), ("reserved", C.c_int64 * 3)]
+                ("iterations", C.c_int64), ("kernel_launches", C.c_int64), ("backups_logged", C.c_int64),
+                ("reserved", C.c_int64 * 2)]
 
 
 _u8p = C.POINTER(C.c_uint8)
@@ -278,7 +279,7 @@ class Engine:
         graph_q -> (states, actions [n] int32, backups, insts): Node.backup_act(action) of every popped edge (:169-189).
         mode (graph_v): "bellman" | "ub_solns" (ub_heur_solns) | "lhbl" (Node.tree_backup) -- the options of UpRLArgs
         (base/updater.py:669-672), computed over the records in the log at drain time.  Empties the log."""
-        cap = self.max_backups
+        cap = max(int(self.counters().backups_logged), 1)       # exact-size buffers: the copies land in them directly
         st = np.empty((cap, self.state_bytes), np.uint8)
         bk = np.empty(cap, np.float64)
         ins = np.empty(cap, np.int32)
@@ -288,8 +289,8 @@ class Engine:
                                          _p(ins, _i32p), cap, C.byref(n)))
         k = n.value
         if self.is_q:
-            return st[:k].copy(), act[:k].copy(), bk[:k].copy(), ins[:k].copy()
-        return st[:k].copy(), bk[:k].copy(), ins[:k].copy()
+            return st[:k], act[:k], bk[:k], ins[:k]
+        return st[:k], bk[:k], ins[:k]
 
     def get_path(self, inst: int, cap: int = 4096, with_states: bool = False):
         """-> (actions list or None, states_on_path [len+1, S] or None)"""

@@ -104,6 +104,7 @@ struct InstArrays {
 // Training-label log (engines created with dx_config.max_backups > 0): one record per expanded node (A*) / popped edge (Q*)
 struct BackupLog {
     uint8_t* state;      // [cap, SP] the record's state row
+    uint8_t* pack;       // [cap, S] drain scratch: the rows without padding
     double* val;         // [cap] label (NaN: popped by an instance that had finished -- dropped at the drain)
     uint32_t* inst;      // [cap]
     uint8_t* act;        // [cap] Q*: the edge's action
@@ -241,6 +242,7 @@ int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* no
 int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr);
 int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const uint8_t* node_solved,
                              const float* node_h, const BackupLog& bk, int mode, uint32_t it_first, uint32_t it_last);
+int dx_launch_backup_pack_rows(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk);
 int dx_launch_backup_clear_map(cudaStream_t s, const Ctl* ctl, const BackupLog& bk);
 int dx_launch_mark_solved(cudaStream_t s, const Ctl* ctl, const uint32_t* popped, const uint32_t* pop_off,
                           const uint8_t* pop_solved, uint8_t* node_solved, int max_pop);

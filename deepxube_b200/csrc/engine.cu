@@ -463,7 +463,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (cfg->max_backups > 0) {
         const size_t K = (size_t)cfg->max_backups;
         e->bk.cap = (uint32_t)K;
-        A_(e->bk.state, K * e->SP); A_(e->bk.val, K); A_(e->bk.inst, K); A_(e->bk.act, K);
+        A_(e->bk.state, K * e->SP); A_(e->bk.pack, K * e->S); A_(e->bk.val, K); A_(e->bk.inst, K); A_(e->bk.act, K);
         if (e->eval_all) {
             A_(e->child_h, C + 1);
             A_(e->bk.solved, K); A_(e->bk.node, K); A_(e->bk.itr, K); A_(e->bk.child_h, K * e->A); A_(e->bk.child_id, K * e->A);
@@ -1004,6 +1004,31 @@ extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int
         else
             for (uint32_t it = it_last + 1; it-- > it_first;) e->launches += dx_launch_backup_tree(s, e->dom, e->d_ctl, e->bk, it);
     }
+    if ((int64_t)n <= cap && states && backups && insts && (actions || !e->backups_q)) {
+        // direct path: the copies land in the caller's buffers (rows repacked SP -> S on the device first); the records of nodes
+        // popped by finished instances (NaN, A* only, rare) are squeezed out in place afterwards
+        std::vector<uint8_t> act(e->backups_q ? n : 0);
+        if (n) {
+            e->launches += dx_launch_backup_pack_rows(s, e->dom, e->d_ctl, e->bk);
+            DX_CUDA(cudaMemcpyAsync(states, e->bk.pack, n * S, cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(backups, e->bk.val, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(insts, e->bk.inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk.act, n, cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaStreamSynchronize(s));
+        }
+        size_t k = 0;
+        for (size_t r = 0; r < n; ++r) {
+            if (backups[r] != backups[r]) continue;
+            if (k != r) {
+                memmove(states + k * S, states + r * S, S);
+                backups[k] = backups[r];
+                insts[k] = insts[r];
+            }
+            if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
+            ++k;
+        }
+        *n_out = (int64_t)k;
+    } else {
     std::vector<uint8_t> rows(n * SP);
     std::vector<double> vals(n);
     std::vector<uint32_t> inst(n);
@@ -1028,6 +1053,7 @@ extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int
         if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
         ++k;
     }
+    }
     if (e->eval_all) e->launches += dx_launch_backup_clear_map(s, e->d_ctl, e->bk);
     k_reset_backups<<<1, 1, 0, s>>>(e->d_ctl);
     e->launches += 1;
@@ -1045,6 +1071,7 @@ extern "C" int dx_get_counters(dx_engine* e, dx_counters* out) {
     out->children_generated = (int64_t)e->h_ctl->gen_total;
     out->iterations = e->h_ctl->itr;
     out->kernel_launches = e->launches;
+    out->backups_logged = e->h_ctl->n_backups;
     return DX_OK;
 }
 

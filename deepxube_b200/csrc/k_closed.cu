@@ -408,6 +408,19 @@ int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* nod
     return launches;
 }
 
+// drain: rows without their padding, contiguous, so that ONE copy brings them to the host
+__global__ void k_backup_pack_rows(DomainDev d, const Ctl* __restrict__ ctl, BackupLog bk) {
+    const size_t total = (size_t)ctl->n_backups * d.S;
+    for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (size_t)gridDim.x * blockDim.x) {
+        const size_t r = i / d.S;
+        bk.pack[i] = bk.state[r * d.SP + (i - r * d.S)];
+    }
+}
+int dx_launch_backup_pack_rows(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk) {
+    k_backup_pack_rows<<<148 * 8, 256, 0, s>>>(d, ctl, bk);
+    return 1;
+}
+
 // the drained records' nodes lose their record
 __global__ void k_backup_clear_map(const Ctl* __restrict__ ctl, BackupLog bk) {
     const uint32_t n = ctl->n_backups;

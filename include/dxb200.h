@@ -110,7 +110,8 @@ typedef struct dx_counters {
     int64_t children_generated;   /* sum of num_nodes_generated over all instances                       */
     int64_t iterations;           /* PathFind.itr                                                        */
     int64_t kernel_launches;      /* CUDA kernels launched by the engine since creation                  */
-    int64_t reserved[3];
+    int64_t backups_logged;       /* log slots in use (an upper bound of what dx_drain_backups returns)  */
+    int64_t reserved[2];
 } dx_counters;
 
 const char* dx_last_error(void);

@@ -2,7 +2,7 @@
 base/updater.py:899-900), every generated child evaluated by the network, Bellman backups logged on the device.
 Reports labelled states/s and children evaluated/s next to the default (kept-children-only) search on the same instances,
 and the CPU oracle on a bounded sample.
-usage: backup_probe.py <domain> <dim> <I> <search_itrs> [bf16|fp32] [H] [NB]"""
+usage: backup_probe.py <domain> <dim> <I> <search_itrs> [bf16|fp32] [H] [NB] [v|q] [bellman|ub_solns|lhbl]"""
 import sys, os, time
 import numpy as np
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -16,6 +16,9 @@ dname, dim, I, ITERS = sys.argv[1], int(sys.argv[2]), int(sys.argv[3]), int(sys.
 mode_s = sys.argv[5] if len(sys.argv) > 5 else "bf16"
 H = int(sys.argv[6]) if len(sys.argv) > 6 else 1000
 NB = int(sys.argv[7]) if len(sys.argv) > 7 else 4
+ALGO = sys.argv[8] if len(sys.argv) > 8 else "v"
+LABEL = sys.argv[9] if len(sys.argv) > 9 else "bellman"
+is_q = ALGO == "q"
 MODE = {"bf16": L.DX_HEUR_NET_BF16, "fp32": L.DX_HEUR_NET_FP32}[mode_s]
 dom = OracleDomain(dname, dim)
 A = dom.num_actions
@@ -27,33 +30,37 @@ for t in range(30):
     mv = dom.next_state(st, rng.integers(0, A, size=I))
     st = np.where((nsteps > t)[:, None], mv, st)
 in_count, depth = dom.input_info()
-sd = random_state_dict(in_count * depth, H, NB, 1, True, seed=0)
+sd = random_state_dict(in_count * depth, H, NB, A if is_q else 1, True, seed=0)
 blob, info = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
 for backups in (0, 1):
-    eng = L.Engine(dname, dim, "graph_v", MODE, max_instances=I, max_pop_total=I, max_nodes=I * A * (ITERS + 1) + 4096,
-                   max_backups=I * ITERS * backups)
-    eng.load_weights(in_count, depth, H, NB, 1, True, blob)
+    eng = L.Engine(dname, dim, "graph_q" if is_q else "graph_v", MODE, max_instances=I, max_pop_total=I,
+                   max_nodes=I * (1 if is_q else A) * (ITERS + 1) + 4096, max_backups=I * ITERS * backups)
+    eng.load_weights(in_count, depth, H, NB, A if is_q else 1, True, blob)
     for rep in range(3):
         eng.reset()
         t0 = time.time()
         eng.add_instances(st, goals, 1, 0.8)
         done = eng.run(ITERS)
-        n_lab = len(eng.drain_backups()[1]) if backups else 0
+        t1 = time.time()
+        n_lab = len(eng.drain_backups(LABEL)[-1]) if backups else 0
         dt = time.time() - t0
+        t_drain = time.time() - t1
         c = eng.counters()
         gen = sum(s.num_nodes_generated for s in eng.status())
-    print(f"{dname}.{dim} I={I} itrs={ITERS} {mode_s} {H}H_{NB}B backups={backups}: iters={done} gen={gen} evals={c.heur_evals} "
+    print(f"{dname}.{dim} {'Q*' if is_q else 'A*'} I={I} itrs={ITERS} {mode_s} {H}H_{NB}B backups={backups} labels={LABEL} drain={t_drain * 1e3:.1f}ms: iters={done} gen={gen} evals={c.heur_evals} "
           f"labelled={n_lab} wall={dt:.3f}s dev_ms={eng.last_run_ms():.1f} children/s={gen / dt:.3e} "
           f"labelled/s={n_lab / dt:.3e} (device-only {n_lab / max(eng.last_run_ms(), 1e-9) * 1e3:.3e})", flush=True)
     eng.close()
 # CPU oracle on a bounded sample (same network in torch fp32, all host threads)
 n_cpu = min(I, 2000)
-f = heurv_from_state_dict(sd, depth)
-orc = OracleSearch(dom, lambda s, g: f(dom.nnet_input(s, g)), False, 1, 0.8)
+from oracle.nnet_torch import heurq_from_state_dict
+f = (heurq_from_state_dict if is_q else heurv_from_state_dict)(sd, depth)
+orc = OracleSearch(dom, lambda s, g: f(dom.nnet_input(s, g)), is_q, 1, 0.8)
 t0 = time.time()
 orc.add_instances(st[:n_cpu], goals[:n_cpu])
 for _ in range(ITERS):
     orc.step()
+lab = (orc.labels_q if is_q else orc.labels_v)(LABEL)
 dt = time.time() - t0
-n_lab = sum(len(x[1]) for x in orc.backup_log)
+n_lab = len(lab)
 print(f"cpu oracle sample I={n_cpu}: labelled={n_lab} wall={dt:.2f}s labelled/s={n_lab / dt:.3e}", flush=True)

@@ -1028,31 +1028,31 @@ extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int
             ++k;
         }
         *n_out = (int64_t)k;
-    } else {
-    std::vector<uint8_t> rows(n * SP);
-    std::vector<double> vals(n);
-    std::vector<uint32_t> inst(n);
-    std::vector<uint8_t> act(n);
-    if (n) {
-        if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk.act, n, cudaMemcpyDeviceToHost, s));
-        DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk.state, rows.size(), cudaMemcpyDeviceToHost, s));
-        DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk.val, n * sizeof(double), cudaMemcpyDeviceToHost, s));
-        DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk.inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
-        DX_CUDA(cudaStreamSynchronize(s));
-    }
-    int64_t m = 0;
-    for (size_t r = 0; r < n; ++r) m += vals[r] == vals[r] ? 1 : 0;        // NaN: popped by an instance that had finished
-    *n_out = m;
-    if (m > cap) DX_FAIL(DX_ERR_ARG, "buffer too small (n_out holds the record count; the log was not drained)");
-    int64_t k = 0;
-    for (size_t r = 0; r < n; ++r) {
-        if (vals[r] != vals[r]) continue;
-        if (states) memcpy(states + (size_t)k * S, &rows[r * SP], S);
-        if (backups) backups[k] = vals[r];
-        if (insts) insts[k] = (int32_t)inst[r];
-        if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
-        ++k;
-    }
+    } else {        // staging path: NULL outputs or cap below the raw slot count
+        std::vector<uint8_t> rows(n * SP);
+        std::vector<double> vals(n);
+        std::vector<uint32_t> inst(n);
+        std::vector<uint8_t> act(n);
+        if (n) {
+            if (e->backups_q) DX_CUDA(cudaMemcpyAsync(act.data(), e->bk.act, n, cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(rows.data(), e->bk.state, rows.size(), cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(vals.data(), e->bk.val, n * sizeof(double), cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaMemcpyAsync(inst.data(), e->bk.inst, n * sizeof(uint32_t), cudaMemcpyDeviceToHost, s));
+            DX_CUDA(cudaStreamSynchronize(s));
+        }
+        int64_t m = 0;
+        for (size_t r = 0; r < n; ++r) m += vals[r] == vals[r] ? 1 : 0;        // NaN: popped by an instance that had finished
+        *n_out = m;
+        if (m > cap) DX_FAIL(DX_ERR_ARG, "buffer too small (n_out holds the record count; the log was not drained)");
+        int64_t k = 0;
+        for (size_t r = 0; r < n; ++r) {
+            if (vals[r] != vals[r]) continue;
+            if (states) memcpy(states + (size_t)k * S, &rows[r * SP], S);
+            if (backups) backups[k] = vals[r];
+            if (insts) insts[k] = (int32_t)inst[r];
+            if (actions) actions[k] = e->backups_q ? (int32_t)act[r] : -1;
+            ++k;
+        }
     }
     if (e->eval_all) e->launches += dx_launch_backup_clear_map(s, e->d_ctl, e->bk);
     k_reset_backups<<<1, 1, 0, s>>>(e->d_ctl);

@@ -427,3 +427,34 @@ def test_updater_rl_bellman_targets_vs_oracle(is_q, label_mode):
     assert np.array_equal(dom.goals_to_rows(goals)[:, :exp_goals.shape[1]], exp_goals)
     assert len(ctgs) == sum(i.itr for i in orc.instances)                          # batch size 1: one popped node / edge per step
     pathfind.close()
+
+
+@pytest.mark.parametrize("precision", ["fp32", "bf16"])
+def test_updater_rl_with_device_network(precision):
+    """the updater mirror with the trained tutorial network evaluated on the device (the target network of the reference's
+    update): [*inputs_nnet, ctgs] as base/updater.py:915-921 returns them, labels recomputed independently from the
+    network values of each state's children."""
+    from deepxube_b200 import _lib as L
+    from deepxube_b200.base.nnet_input import get_nnet_input_from_arg
+    from deepxube_b200.updaters.updater_rl import UpdateHeurVRLKeepGoal
+    random.seed(11)
+    dom, name = get_domain_from_arg("cube3")
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, ["heurv,resnet_fc.200H_2B_bn"])
+    pfns.heurv.nnet.load_state_dict(gu.state_dict_np("cube3v"))
+    pfns.heurv.precision = precision
+    pathfind, pname, _ = get_pathfind_from_arg(dom, pfns, "graph.1B_0.8W")
+    up = UpdateHeurVRLKeepGoal(dom, pathfind, 8, nnet_input=get_nnet_input_from_arg(dom, name, "flat_sg"))
+    steps_gen = [0, 1, 2, 3, 5, 8, 13, 21, 30, 30, 1, 2] * 4
+    data = up.get_update_data(steps_gen)
+    rows, ctgs = data[0], data[-1]
+    assert len(data) == 2 and rows.shape == (len(ctgs), 54) and ctgs.dtype == np.float64 and len(ctgs) >= len(steps_gen)
+    goal_obj = dom.sample_problem_instances([0])[1][0]
+    goal = dom.goals_to_rows([goal_obj])
+    solved = L.is_solved("cube3", 0, rows, np.repeat(goal, len(rows), axis=0))
+    children = L.expand("cube3", 0, rows).reshape(-1, 54)
+    st_c = dom.rows_to_states(children)
+    h = np.array(pfns.heurv(st_c, [goal_obj] * len(st_c), [None] * len(st_c))).reshape(len(rows), 12)
+    want = np.where(solved, 0.0, 1.0 + h.min(axis=1))
+    np.testing.assert_allclose(ctgs, want, rtol=0, atol=2e-4 if precision == "fp32" else 0.1)
+    assert (ctgs[solved] == 0.0).all() and solved.sum() >= 4
+    pathfind.close()

@@ -84,6 +84,7 @@ SIGNATURES = {
     "dx_next_state": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _u8p, _i32p, C.c_int64, _u8p]),
     "dx_is_solved": (C.c_int, [C.c_int32, C.c_int32, C.c_int32, _u8p, _u8p, C.c_int64, _u8p]),
     "dx_heur_eval": (C.c_int, [_engp, _u8p, _u8p, C.c_int64, _f32p]),
+    "dx_vi_targets": (C.c_int, [_engp, _u8p, _u8p, _u8p, C.c_int64, C.POINTER(C.c_double)]),
     "dx_row_bytes": (C.c_int, [_engp, _i32p]),
     "dx_bench_heur": (C.c_int, [_engp, C.c_int64, C.c_int32, _f32p]),
     "dx_set_profiling": (C.c_int, [_engp, C.c_int32]),
@@ -272,6 +273,17 @@ class Engine:
         c = dx_counters()
         check(self._lib.dx_get_counters(self._h, C.byref(c)))
         return c
+
+    def vi_targets(self, states: np.ndarray, goals: np.ndarray, solved: Optional[np.ndarray] = None) -> np.ndarray:
+        """Replay-buffer labels with the loaded network (updaters/updater_rl.py:41-69 / :102-120) -> float64 [n].
+        graph_v: min_a (1 + h(child_a)) * (not solved); graph_q: `states` = next states, (1 + min_a q) * (not solved)."""
+        states, goals = _u8(states), _u8(goals)
+        n = states.shape[0]
+        out = np.empty(n, np.float64)
+        sol = None if solved is None else np.ascontiguousarray(np.asarray(solved).astype(np.uint8))
+        check(self._lib.dx_vi_targets(self._h, _p(states, _u8p), _p(goals, _u8p), _p(sol, _u8p), n,
+                                      out.ctypes.data_as(C.POINTER(C.c_double))))
+        return out
 
     def drain_backups(self, mode: str = "bellman"):
         """graph_v -> (states [n, S] uint8, backups [n] float64, insts [n] int32): Node.bellman_backup() of every node expanded

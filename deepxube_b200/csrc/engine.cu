@@ -1224,6 +1224,94 @@ extern "C" int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const floa
 
 // Evaluate the loaded network on host-provided states: rows are staged in a scratch area with a private
 // goal table (row r uses goal r), so it does not disturb the search state.
+// min over actions of (1 + value) per row, zeroed where solved -- the reduction of dx_vi_targets
+__global__ void k_vi_reduce(const float* __restrict__ vals, const uint8_t* __restrict__ solved, long long n, int A,
+                            double* __restrict__ out) {
+    for (long long r = (long long)blockIdx.x * blockDim.x + threadIdx.x; r < n; r += (long long)gridDim.x * blockDim.x) {
+        double v = __longlong_as_double(0x7ff0000000000000ll);
+        for (int a = 0; a < A; ++a) v = fmin(v, 1.0 + (double)vals[r * A + a]);
+        out[r] = (solved && solved[r]) ? 0.0 : v;
+    }
+}
+
+// Value-iteration / Q-learning targets of replay-buffer samples with the loaded (target) network:
+//   graph_v engines (UpdateHeurVRL._get_labels_rb, updaters/updater_rl.py:41-69):  states are expanded,
+//       target = min_a (1.0 + h(child_a)) * (not solved);   solved == NULL: is_solved(state, goal) is computed
+//   graph_q engines (UpdateHeurQRL._get_labels_rb, :102-120):  `states` are the NEXT states of the sampled edges,
+//       target = (1.0 + min_a q(next, a)) * (not solved);   solved = is_solved of the edge's node (NULL: none solved)
+// float64, like the reference's numpy arithmetic.
+extern "C" int dx_vi_targets(dx_engine* e, const uint8_t* states, const uint8_t* goals, const uint8_t* solved, int64_t n,
+                             double* out) {
+    if (!e || n < 0 || (n > 0 && (!states || !out))) DX_FAIL(DX_ERR_ARG, "bad argument");
+    if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    if (e->is_beam) DX_FAIL(DX_ERR_UNSUPPORTED, "dx_vi_targets: graph_v / graph_q engines");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    if (n == 0) return DX_OK;
+    const int amul = e->net.act_depth > 0 ? e->net.act_depth : 1;       // action-as-input Q network: one row per (state, action)
+    const int SP = e->SP, S = e->S, A = e->A;
+    const int fan = e->is_q ? 1 : A;                                     // network rows per input state
+    const int od = e->is_q ? e->net.out_dim * amul : 1;
+    const long long chunk = std::max<long long>(1, std::min<long long>(e->mlp.cap / ((long long)fan * amul), 1 << 15));
+    const size_t off_goals = (size_t)chunk * SP, off_child = off_goals + (size_t)chunk * SP,
+                 off_vals = off_child + (size_t)chunk * fan * SP, off_h = off_vals + (size_t)chunk * fan * od * 4,
+                 off_out = (off_h + (size_t)chunk * fan * 4 + 7) / 8 * 8, off_solved = off_out + (size_t)chunk * 8;
+    DX_TRY(ensure_stage(e, off_solved + (size_t)chunk + 64));
+    uint8_t* d_rows = e->d_stage;
+    uint8_t* d_goals = e->d_stage + off_goals;
+    uint8_t* d_child = e->d_stage + off_child;
+    float* d_vals = (float*)(e->d_stage + off_vals);                     // Q: the q-values
+    float* d_h = (float*)(e->d_stage + off_h);                           // V: h(child); Q: min_a q
+    double* d_out = (double*)(e->d_stage + off_out);
+    uint8_t* d_solved = e->d_stage + off_solved;
+    std::vector<uint8_t> rows((size_t)chunk * SP), grows((size_t)chunk * SP);
+    DX_TRY(sync_ctl(e));
+    const Ctl saved = *e->h_ctl;
+    cudaStream_t st = e->stream;
+    for (long long s0 = 0; s0 < n; s0 += chunk) {
+        const long long m = std::min(chunk, n - s0);
+        std::fill(rows.begin(), rows.end(), 0);
+        std::fill(grows.begin(), grows.end(), 0);
+        for (long long r = 0; r < m; ++r) {
+            memcpy(&rows[(size_t)r * SP], states + (size_t)(s0 + r) * S, S);
+            const uint32_t gi = (uint32_t)r;                             // the row's goal index, inherited by its children
+            memcpy(&rows[(size_t)r * SP + SP - 4], &gi, 4);
+            if (goals) memcpy(&grows[(size_t)r * SP], goals + (size_t)(s0 + r) * S, S);
+        }
+        DX_CUDA(cudaMemcpyAsync(d_rows, rows.data(), (size_t)m * SP, cudaMemcpyHostToDevice, st));
+        DX_CUDA(cudaMemcpyAsync(d_goals, grows.data(), (size_t)m * SP, cudaMemcpyHostToDevice, st));
+        const uint8_t* sol = nullptr;
+        if (solved) {
+            DX_CUDA(cudaMemcpyAsync(d_solved, solved + s0, (size_t)m, cudaMemcpyHostToDevice, st));
+            sol = d_solved;
+        } else if (!e->is_q) {
+            e->launches += dx_launch_standalone_solved(st, e->dom, d_rows, d_goals, m, d_solved);
+            sol = d_solved;
+        }
+        const uint8_t* nn_rows = d_rows;
+        if (!e->is_q) {
+            e->launches += dx_launch_standalone_expand(st, e->dom, d_rows, m, nullptr, d_child);
+            nn_rows = d_child;
+        }
+        k_set_job<<<1, 1, 0, st>>>(e->d_ctl, 0, (uint32_t)(m * fan));
+        e->launches += 1;
+        float* out_q = e->is_q ? d_vals : nullptr;
+        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
+            e->launches += dx_launch_mlp_bf16(st, e->dom, e->net, e->mlp, e->d_ctl, nn_rows, d_goals, d_h, out_q, 0, m * fan);
+        else
+            e->launches += dx_launch_mlp_f32(st, e->dom, e->net, e->mlp, e->d_ctl, nn_rows, d_goals, d_h, out_q, 0, m * fan);
+        k_vi_reduce<<<std::min(dx_div_up(m, 256), 148 * 4), 256, 0, st>>>(d_h, sol, m, fan, d_out);
+        e->launches += 1;
+        DX_CUDA(cudaMemcpyAsync(out + s0, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
+        DX_CUDA(cudaStreamSynchronize(st));
+    }
+    k_set_job<<<1, 1, 0, st>>>(e->d_ctl, saved.nn_row_start, saved.nn_n);
+    e->launches += 1;
+    DX_CUDA(cudaStreamSynchronize(st));
+    DX_CUDA(cudaGetLastError());
+    return DX_OK;
+}
+
 extern "C" int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* goals, int64_t n, float* out) {
     if (!e || n < 0 || (n > 0 && (!states || !out))) DX_FAIL(DX_ERR_ARG, "bad argument");
     if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");

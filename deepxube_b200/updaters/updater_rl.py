@@ -89,6 +89,33 @@ class UpdateHeurVRLKeepGoal:
         return list(self.nnet_input.to_np(data[0], data[1])) + [np.asarray(data[2])]
 
 
+    def _device_fn(self) -> Any:
+        from deepxube_b200.base.pathfind_fns import _DeviceHeur
+        fn = self.pathfind._fn
+        if not isinstance(fn, _DeviceHeur):
+            raise TypeError("replay-buffer labels are computed by the device (target) network: the PathFind functions must "
+                            "come from a resnet_fc network (heurv / heurq_fixout / heurq_in), not a host callable")
+        return fn
+
+    def _get_labels_rb(self, input_data: Tuple, replay_data: Any, times: Any = None) -> List[float]:
+        """UpdateHeurVRL._get_labels_rb (updaters/updater_rl.py:41-69): input_data = (states, goals, contexts), replay_data =
+        is_solved_l -> min_a (tc + h_targ(child_a)) * not(is_solved), expansion + network + min on the device."""
+        states, goals = input_data[0], input_data[1]
+        fn = self._device_fn()
+        rows, grows = self.domain.states_to_rows(states), self.domain.goals_to_rows(goals)
+        return fn._engine().vi_targets(rows, grows, None if replay_data is None else np.asarray(replay_data, bool)).tolist()
+
+
 class UpdateHeurQRLKeepGoal(UpdateHeurVRLKeepGoal):
     """the same runner over graph_q: popped edges and Node.backup_act labels (updaters/updater_rl.py:162-189)"""
     is_q = True
+
+    def _get_labels_rb(self, input_data: Tuple, replay_data: Any, times: Any = None) -> List[float]:
+        """UpdateHeurQRL._get_labels_rb (updaters/updater_rl.py:102-120): input_data = (states, goals, actions, contexts),
+        replay_data = (is_solved_l, tcs, states_next) -> (tc + min_a q_targ(next, a)) * not(is_solved)."""
+        goals = input_data[1]
+        is_solved_l, tcs, states_next = replay_data
+        assert all(float(t) == 1.0 for t in tcs), "the in-scope domains have unit transition costs"
+        fn = self._device_fn()
+        rows, grows = self.domain.states_to_rows(states_next), self.domain.goals_to_rows(goals)
+        return fn._engine().vi_targets(rows, grows, np.asarray(is_solved_l, bool)).tolist()

@@ -206,6 +206,14 @@ int dx_is_solved(int32_t device, int32_t domain, int32_t dim, const uint8_t* sta
  * precision (NET_FP32 or NET_BF16). */
 int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* goals, int64_t n, float* out);
 
+/* Value-iteration / Q-learning targets of replay-buffer samples, computed with the loaded (target) network:
+ *   graph_v engines -- UpdateHeurVRL._get_labels_rb (deepxube/updaters/updater_rl.py:41-69): every state is expanded,
+ *       out = min_a (1.0 + h(child_a)) * (not solved); solved == NULL: is_solved(state, goal) is computed on the device
+ *   graph_q engines -- UpdateHeurQRL._get_labels_rb (:102-120): `states` are the NEXT states of the sampled edges,
+ *       out = (1.0 + min_a q(next, a)) * (not solved); solved [n] = is_solved of each edge's node (NULL: none)
+ * states / goals [n, state_bytes], out [n] float64 (the reference computes these in numpy float64). */
+int dx_vi_targets(dx_engine* e, const uint8_t* states, const uint8_t* goals, const uint8_t* solved, int64_t n, double* out);
+
 /* Bench / profiling helpers: same network evaluation with inputs and outputs resident on the device.
  * dev_states: [n, row_bytes] engine row layout (see dx_row_bytes); returns milliseconds of device time
  * measured with CUDA events on the engine's stream over `reps` back-to-back evaluations. */

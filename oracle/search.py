@@ -427,3 +427,30 @@ def solve_one(domain: OracleDomain, state: np.ndarray, goal: np.ndarray, heur_fn
         _, acts, _ = inst.get_path()
         out["actions"] = acts
     return out
+
+
+# ---- replay-buffer labels (test infrastructure, like everything in oracle/) -------------------------------------------
+def vi_targets_v(domain: OracleDomain, heur_fn: HeurFn, states: np.ndarray, goals: np.ndarray,
+                 solved: Optional[np.ndarray] = None) -> np.ndarray:
+    """UpdateHeurVRL._get_labels_rb (updaters/updater_rl.py:41-69): expand the sampled states, evaluate the target network on
+    every child, ctg = min_a (tc + h(child_a)) * not(is_solved); tc = 1.0, numpy float64."""
+    n, a = states.shape[0], domain.num_actions
+    if solved is None:
+        solved = domain.is_solved(states, goals)
+    if n == 0:
+        return np.zeros(0)
+    children = domain.expand(states)
+    h = np.asarray(heur_fn(children, np.repeat(goals, a, axis=0)), np.float64)
+    return (1.0 + h).reshape(n, a).min(axis=1) * np.logical_not(np.asarray(solved, bool))
+
+
+def vi_targets_q(domain: OracleDomain, heurq_fn: HeurFn, states_next: np.ndarray, goals: np.ndarray,
+                 solved: Optional[np.ndarray] = None) -> np.ndarray:
+    """UpdateHeurQRL._get_labels_rb (updaters/updater_rl.py:102-120): ctg = (tc + min_a q_targ(next, a)) * not(is_solved of
+    the edge's node); tc = 1.0."""
+    n = states_next.shape[0]
+    if n == 0:
+        return np.zeros(0)
+    q = np.asarray(heurq_fn(states_next, goals), np.float64)
+    sol = np.zeros(n, bool) if solved is None else np.asarray(solved, bool)
+    return (1.0 + q.min(axis=1)) * np.logical_not(sol)

@@ -458,3 +458,35 @@ def test_updater_rl_with_device_network(precision):
     np.testing.assert_allclose(ctgs, want, rtol=0, atol=2e-4 if precision == "fp32" else 0.1)
     assert (ctgs[solved] == 0.0).all() and solved.sum() >= 4
     pathfind.close()
+
+
+@pytest.mark.parametrize("tag", ["v_cube3_net", "q_cube3_net", "v_grid7_net", "q_grid7_net"])
+def test_updater_rl_replay_labels_through_the_registries(tag):
+    """the mirror's _get_labels_rb with host State / Goal objects == the reference's labels (tests/golden/vi.npz)"""
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLKeepGoal, UpdateHeurVRLKeepGoal
+    c = gu.vi_case(tag)
+    is_q = tag.startswith("q_")
+    dom, name = get_domain_from_arg(str(c["cfg"][0]))
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [str(c["cfg"][1])])
+    heur = pfns.heurq if is_q else pfns.heurv
+    heur.nnet.load_state_dict(gu.state_dict_np({"v_cube3_net": "cube3v", "q_cube3_net": "cube3q", "v_grid7_net": "gridv",
+                                                "q_grid7_net": "gridq"}[tag]))
+    pathfind, _, _ = get_pathfind_from_arg(dom, pfns, "graph.1B_0.8W")
+    up = (UpdateHeurQRLKeepGoal if is_q else UpdateHeurVRLKeepGoal)(dom, pathfind, 4)
+    states = dom.rows_to_states(c["states"])
+    grows = c["goals"]
+    goal_t = type(dom.sample_problem_instances([0])[1][0])
+    goals = [goal_t(int(r[0]), int(r[1])) for r in grows] if name == "grid" else [goal_t(r) for r in grows]
+    solved = c["solved"].tolist()
+    if is_q:
+        fixed = dom.get_actions_fixed()
+        acts = [fixed[int(a)] for a in c["acts"]]
+        nxt = dom.rows_to_states(c["states_next"])
+        lab = up._get_labels_rb((states, goals, acts, [None] * len(states)), (solved, [1.0] * len(states), nxt))
+    else:
+        lab = up._get_labels_rb((states, goals, [None] * len(states)), solved)
+    np.testing.assert_allclose(np.array(lab), c["labels"], rtol=0, atol=2e-4)
+    host = (UpdateHeurVRLKeepGoal)(dom, get_pathfind_from_arg(dom, PFNsHeurVC(heurv=lambda s, g, c_: [0.0] * len(s)), "graph_v.1B")[0], 4)
+    with pytest.raises(TypeError, match="device"):
+        host._get_labels_rb((states, goals, None), solved)
+    pathfind.close()

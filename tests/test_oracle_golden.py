@@ -250,3 +250,31 @@ def test_bellman_backups_match_reference(tag):
     else:
         assert np.array_equal(val, c["bk_vals"])
     assert [i.finished() for i in insts] == c["finished"].tolist()
+
+
+VI_NETS = {"v_cube3_net": "cube3v", "v_np4_net": "np4v", "v_grid7_net": "gridv", "q_cube3_net": "cube3q", "q_grid7_net": "gridq"}
+
+
+@pytest.mark.parametrize("tag", gu.vi_tags())
+def test_replay_buffer_labels_match_reference(tag):
+    """UpdateHeurVRL._get_labels_rb / UpdateHeurQRL._get_labels_rb (updaters/updater_rl.py:41-69, 102-120), golden = the
+    reference's own methods."""
+    from oracle.search import vi_targets_q, vi_targets_v
+    c = gu.vi_case(tag)
+    name, dim = gu.parse_domain(str(c["cfg"][0]))
+    dom = OracleDomain(name, dim)
+    if str(c["cfg"][2]) == "pseudo":
+        got = vi_targets_v(dom, pseudo_v_fine, c["states"], c["goals"], c["solved"])
+        assert np.array_equal(got, c["labels"])
+        assert np.array_equal(vi_targets_v(dom, pseudo_v_fine, c["states"], c["goals"]), c["labels"])     # is_solved computed
+        return
+    depth = dom.input_info()[1]
+    sd = gu.state_dict_torch(VI_NETS[tag])
+    if tag.startswith("q_"):
+        f = heurq_from_state_dict(sd, depth)
+        got = vi_targets_q(dom, lambda s, g: f(dom.nnet_input(s, g)), c["states_next"], c["goals"], c["solved"])
+    else:
+        f = heurv_from_state_dict(sd, depth)
+        got = vi_targets_v(dom, lambda s, g: f(dom.nnet_input(s, g)), c["states"], c["goals"], c["solved"])
+    np.testing.assert_allclose(got, c["labels"], rtol=0, atol=2e-5)
+    assert (got[c["solved"]] == 0.0).all()

@@ -64,3 +64,20 @@ lab = (orc.labels_q if is_q else orc.labels_v)(LABEL)
 dt = time.time() - t0
 n_lab = len(lab)
 print(f"cpu oracle sample I={n_cpu}: labelled={n_lab} wall={dt:.2f}s labelled/s={n_lab / dt:.3e}", flush=True)
+# replay-buffer labels (dx_vi_targets): n sampled states -> expand + network + min, HOST buffers in and out
+if not is_q:
+    from oracle.search import vi_targets_v
+    n_vi = min(I, 100000)
+    eng = L.Engine(dname, dim, "graph_v", MODE, max_instances=1, max_pop_total=n_vi, max_nodes=4096)
+    eng.load_weights(in_count, depth, H, NB, 1, True, blob)
+    for rep in range(3):
+        t0 = time.time()
+        lab = eng.vi_targets(st[:n_vi], goals[:n_vi])
+        dt = time.time() - t0
+    print(f"vi_targets {dname}.{dim} n={n_vi} ({n_vi * A} evaluations) {mode_s} {H}H_{NB}B: wall={dt * 1e3:.1f}ms labels/s={n_vi / dt:.3e} evals/s={n_vi * A / dt:.3e}", flush=True)
+    n_cpu = min(n_vi, 4000)
+    t0 = time.time()
+    ref = vi_targets_v(dom, lambda s, g: f(dom.nnet_input(s, g)), st[:n_cpu], goals[:n_cpu])
+    dt = time.time() - t0
+    print(f"cpu oracle vi_targets n={n_cpu}: wall={dt:.2f}s labels/s={n_cpu / dt:.3e}  max |gpu - cpu| = {np.abs(lab[:n_cpu] - ref).max():.4f}", flush=True)
+    eng.close()

@@ -583,8 +583,75 @@ def gen_backup() -> None:
     print("backup.npz", len(out), "arrays")
 
 
+def gen_vi() -> None:
+    """vi.npz: replay-buffer labels straight out of the reference's own UpdateHeurVRL._get_labels_rb / UpdateHeurQRL._get_labels_rb
+    (updaters/updater_rl.py:41-69, 102-120).  The updater objects are created without their process / queue plumbing
+    (`__new__`), with the target-network function and the PathFind they would build injected."""
+    import tempfile
+    from deepxube.factories.updater_factory import updater_factory
+    from deepxube.utils.timing_utils import Times
+    from oracle.nnet_torch import random_state_dict
+    out = {}
+    z = np.load(os.path.join(OUT, "nnet.npz"))
+
+    def net_file(tag, in_dim, h, nb, odim):
+        """the random-BN nets of nnet.npz are regenerated from their seed (and checked against the fixture)"""
+        sd = random_state_dict(in_dim, h, nb, odim, batch_norm=True, seed=7, randomize_bn=True)
+        for k, v in sd.items():
+            assert np.array_equal(v.numpy(), z[tag + "/" + k]), k
+        tf = tempfile.NamedTemporaryFile(suffix=".pt", delete=False)
+        torch.save(sd, tf.name)
+        return tf.name
+
+    def add(tag, domain_str, fn_str, nnet_file, steps_l, pseudo=False):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        is_q = fn_str.startswith("heurq")
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        if pseudo:
+            pfns = wrap_v(pseudo_v_fine)
+        else:
+            pfns, _ = get_path_fns_nnet_par_dict(domain, dname, [fn_str], torch.device("cpu"), nnet_files=[nnet_file])
+        pathfind, _, _ = get_pathfind_from_arg(domain, pfns, "graph.1B_0.8W")
+        cls = updater_factory.get_type("up_rl_q" if is_q else "up_rl_v")
+        obj = cls.__new__(cls)
+        obj.domain = domain
+        obj.get_pathfind = lambda: pathfind
+        solved = domain.is_solved(states, goals)
+        ctxs = [None] * len(states)
+        out[tag + "/cfg"] = np.array([domain_str, fn_str, "pseudo" if pseudo else "net"])
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/solved"] = np.array(solved)
+        if is_q:
+            obj._get_targ_heurq_fn = lambda: pfns.heurq
+            acts = [random.choice(al) for al in domain.get_state_actions(states)]
+            nxt, tcs = domain.next_state(states, acts)
+            assert all(t == 1.0 for t in tcs)
+            lab = obj._get_labels_rb((states, goals, acts, ctxs), (solved, tcs, nxt), Times())
+            out[tag + "/acts"] = np.array([a.action for a in acts], np.int32)
+            out[tag + "/states_next"] = states_np(nxt)
+        else:
+            obj._get_targ_heurv_fn = lambda: pfns.heurv
+            lab = obj._get_labels_rb((states, goals, ctxs), solved, Times())
+        out[tag + "/labels"] = np.array(lab, np.float64)
+        print(tag, "n", len(lab), "solved", int(np.sum(solved)), "labels", np.round(out[tag + "/labels"][:6], 3))
+
+    rnd = lambda n, hi: [0, 0, 1, 1, 2] + list(np.random.RandomState(n).randint(0, hi, size=n))
+    add("v_cube3_pseudo", "cube3", "heurv", None, rnd(120, 30), pseudo=True)
+    add("v_cube3_net", "cube3", "heurv,resnet_fc.200H_2B_bn", os.path.join(REF_ROOT, "tutorial/cube3/models/heur.pt"), rnd(200, 30))
+    add("v_np4_net", "npuzzle.4", "heurv,resnet_fc.96H_2B_bn", net_file("np4v", 256, 96, 2, 1), rnd(150, 40))
+    add("v_grid7_net", "grid.7d", "heurv,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_v/heur.pt"), rnd(90, 12))
+    add("q_cube3_net", "cube3", "heurq_fixout,resnet_fc.128H_1B_bn", net_file("cube3q", 324, 128, 1, 12), rnd(160, 30))
+    add("q_grid7_net", "grid.7d", "heurq_fixout,resnet_fc.100H_1B_bn", os.path.join(REF_ROOT, "tutorial/grid_tut/flatin_qfix/heur.pt"), rnd(90, 12))
+    np.savez_compressed(os.path.join(OUT, "vi.npz"), **out)
+    print("vi.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam", "backup"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam", "backup", "vi"]
+    if "vi" in which:
+        gen_vi()
     if "backup" in which:
         gen_backup()
     if "beam" in which:

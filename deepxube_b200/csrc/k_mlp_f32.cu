@@ -68,40 +68,52 @@ k_first_layer_f32(DomainDev d, NetDev net, const Ctl* __restrict__ ctl, const ui
 }
 
 // C[M,N] = act(A[M,K] . W[N,K]^T + bias (+ R)), M = ctl->nn_n, N and K multiples of 128 / 16.
-#define SG_BM 128
-#define SG_BN 128
+// BM x BN output tile per block of 256 threads (16 x 16 threads, each (BM/16) x (BN/16) outputs in groups of 4): 128 x 128 for
+// full batches; 64 x 64 when the whole batch is a few thousand rows (small-batch searches: `graph.100B` evaluates ~1200 states
+// per iteration, 20 big tiles would use 20 SMs and each runs 4x longer).  Every output element is one fmaf chain over k in
+// ascending order from 0, whatever the tile: both variants give identical bits.
 #define SG_BK 16
+template <int BM, int BN>
 __global__ void __launch_bounds__(256)
 k_sgemm_bias_act(const float* __restrict__ A, const float* __restrict__ W, const float* __restrict__ bias,
                  const float* __restrict__ R, float* __restrict__ C, const Ctl* __restrict__ ctl, int N, int K, int relu) {
-    __shared__ __align__(16) float As[2][SG_BK][SG_BM + 4];
-    __shared__ __align__(16) float Bs[2][SG_BK][SG_BN + 4];
+    constexpr int GM = BM / 64, GN = BN / 64;           // groups of 4 rows / columns per thread
+    __shared__ __align__(16) float As[2][SG_BK][BM + 4];
+    __shared__ __align__(16) float Bs[2][SG_BK][BN + 4];
     if (ctl->error) return;
     const int M = (int)ctl->nn_n;
-    const int n0 = blockIdx.x * SG_BN;
+    const int n0 = blockIdx.x * BN;
     const int tid = threadIdx.x, tx = tid & 15, ty = tid >> 4;
-    for (int m0 = blockIdx.y * SG_BM; m0 < M; m0 += gridDim.y * SG_BM) {
-        float acc[8][8];
+    for (int m0 = blockIdx.y * BM; m0 < M; m0 += gridDim.y * BM) {
+        float acc[GM * 4][GN * 4];
 #pragma unroll
-        for (int i = 0; i < 8; ++i)
+        for (int i = 0; i < GM * 4; ++i)
 #pragma unroll
-            for (int j = 0; j < 8; ++j) acc[i][j] = 0.f;
-        float4 ra[2], rb[2];
+            for (int j = 0; j < GN * 4; ++j) acc[i][j] = 0.f;
+        float4 ra[GM], rb[GN];
         auto gload = [&](int k0) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < GM; ++q) {
                 const int idx = tid + q * 256, row = idx >> 2, kc = (idx & 3) * 4;
                 ra[q] = (m0 + row < M) ? *reinterpret_cast<const float4*>(A + (size_t)(m0 + row) * K + k0 + kc)
                                        : make_float4(0.f, 0.f, 0.f, 0.f);
+            }
+#pragma unroll
+            for (int q = 0; q < GN; ++q) {
+                const int idx = tid + q * 256, row = idx >> 2, kc = (idx & 3) * 4;
                 rb[q] = *reinterpret_cast<const float4*>(W + (size_t)(n0 + row) * K + k0 + kc);
             }
         };
         auto sstore = [&](int buf) {
 #pragma unroll
-            for (int q = 0; q < 2; ++q) {
+            for (int q = 0; q < GM; ++q) {
                 const int idx = tid + q * 256, row = idx >> 2, kc = (idx & 3) * 4;
                 As[buf][kc + 0][row] = ra[q].x; As[buf][kc + 1][row] = ra[q].y;
                 As[buf][kc + 2][row] = ra[q].z; As[buf][kc + 3][row] = ra[q].w;
+            }
+#pragma unroll
+            for (int q = 0; q < GN; ++q) {
+                const int idx = tid + q * 256, row = idx >> 2, kc = (idx & 3) * 4;
                 Bs[buf][kc + 0][row] = rb[q].x; Bs[buf][kc + 1][row] = rb[q].y;
                 Bs[buf][kc + 2][row] = rb[q].z; Bs[buf][kc + 3][row] = rb[q].w;
             }
@@ -116,27 +128,32 @@ k_sgemm_bias_act(const float* __restrict__ A, const float* __restrict__ W, const
             if (kt + 1 < nk) gload((kt + 1) * SG_BK);
 #pragma unroll
             for (int k = 0; k < SG_BK; ++k) {
-                const float4 a0 = *reinterpret_cast<const float4*>(&As[buf][k][ty * 4]);
-                const float4 a1 = *reinterpret_cast<const float4*>(&As[buf][k][64 + ty * 4]);
-                const float4 b0 = *reinterpret_cast<const float4*>(&Bs[buf][k][tx * 4]);
-                const float4 b1 = *reinterpret_cast<const float4*>(&Bs[buf][k][64 + tx * 4]);
-                const float a[8] = {a0.x, a0.y, a0.z, a0.w, a1.x, a1.y, a1.z, a1.w};
-                const float b[8] = {b0.x, b0.y, b0.z, b0.w, b1.x, b1.y, b1.z, b1.w};
+                float a[GM * 4], b[GN * 4];
 #pragma unroll
-                for (int i = 0; i < 8; ++i)
+                for (int g = 0; g < GM; ++g) {
+                    const float4 v = *reinterpret_cast<const float4*>(&As[buf][k][g * 64 + ty * 4]);
+                    a[g * 4 + 0] = v.x; a[g * 4 + 1] = v.y; a[g * 4 + 2] = v.z; a[g * 4 + 3] = v.w;
+                }
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+                for (int g = 0; g < GN; ++g) {
+                    const float4 v = *reinterpret_cast<const float4*>(&Bs[buf][k][g * 64 + tx * 4]);
+                    b[g * 4 + 0] = v.x; b[g * 4 + 1] = v.y; b[g * 4 + 2] = v.z; b[g * 4 + 3] = v.w;
+                }
+#pragma unroll
+                for (int i = 0; i < GM * 4; ++i)
+#pragma unroll
+                    for (int j = 0; j < GN * 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
             }
             if (kt + 1 < nk) sstore(buf ^ 1);
             __syncthreads();
         }
 #pragma unroll
-        for (int i = 0; i < 8; ++i) {
-            const int row = m0 + (i < 4 ? ty * 4 + i : 64 + ty * 4 + (i - 4));
+        for (int i = 0; i < GM * 4; ++i) {
+            const int row = m0 + (i / 4) * 64 + ty * 4 + (i & 3);
             if (row >= M) continue;
 #pragma unroll
-            for (int jh = 0; jh < 2; ++jh) {
-                const int col = n0 + (jh == 0 ? tx * 4 : 64 + tx * 4);
+            for (int jh = 0; jh < GN; ++jh) {
+                const int col = n0 + jh * 64 + tx * 4;
                 const float4 bv = *reinterpret_cast<const float4*>(bias + col);
                 float4 v = make_float4(acc[i][jh * 4 + 0] + bv.x, acc[i][jh * 4 + 1] + bv.y, acc[i][jh * 4 + 2] + bv.z,
                                        acc[i][jh * 4 + 3] + bv.w);
@@ -148,6 +165,17 @@ k_sgemm_bias_act(const float* __restrict__ A, const float* __restrict__ W, const
                 *reinterpret_cast<float4*>(C + (size_t)row * N + col) = v;
             }
         }
+    }
+}
+
+static void launch_sgemm(cudaStream_t s, bool small, long long max_rows, const float* A, const float* W, const float* bias,
+                         const float* R, float* C, const Ctl* ctl, int N, int K, int relu) {
+    if (small) {
+        dim3 grid(N / 64, (unsigned)dx_div_up(max_rows, 64));
+        k_sgemm_bias_act<64, 64><<<grid, 256, 0, s>>>(A, W, bias, R, C, ctl, N, K, relu);
+    } else {
+        dim3 grid(N / 128, (unsigned)min((long long)dx_div_up(max_rows, 128), (long long)(148 * 2 / max(1, N / 128) + 1)));
+        k_sgemm_bias_act<128, 128><<<grid, 256, 0, s>>>(A, W, bias, R, C, ctl, N, K, relu);
     }
 }
 
@@ -241,7 +269,8 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
     k_first_layer_f32<<<fl_blocks, FL_THREADS, 0, s>>>(d, net, ctl, rows, goals, mb.x[0]);
     ++launches;
     const int Hp = net.Hp;
-    dim3 grid(Hp / SG_BN, (unsigned)min((long long)dx_div_up(max_rows, SG_BM), (long long)(148 * 2 / max(1, Hp / SG_BN) + 1)));
+    // few big tiles: the 64 x 64 variant spreads a small batch over the SMs
+    const bool small = dx_div_up(max_rows, 128) * (Hp / 128) < 148 && dx_div_up(max_rows, 64) * (Hp / 64) <= 148 * 8;
     float* x = mb.x[0];
     float* y = mb.x[1];
     float* z = mb.x[2];
@@ -249,10 +278,10 @@ int dx_launch_mlp_f32(cudaStream_t s, const DomainDev& d, const NetDev& net, con
         const float* w1 = net.wres + (size_t)(2 * b) * Hp * Hp;
         const float* w2 = net.wres + (size_t)(2 * b + 1) * Hp * Hp;
         dx_prof_begin(DX_ST_GEMM_RES);
-        k_sgemm_bias_act<<<grid, 256, 0, s>>>(x, w1, net.bres + (size_t)(2 * b) * Hp, nullptr, y, ctl, Hp, Hp, 1);
+        launch_sgemm(s, small, max_rows, x, w1, net.bres + (size_t)(2 * b) * Hp, nullptr, y, ctl, Hp, Hp, 1);
         dx_prof_end();
         dx_prof_begin(DX_ST_GEMM_RES);
-        k_sgemm_bias_act<<<grid, 256, 0, s>>>(y, w2, net.bres + (size_t)(2 * b + 1) * Hp, x, z, ctl, Hp, Hp, 1);
+        launch_sgemm(s, small, max_rows, y, w2, net.bres + (size_t)(2 * b + 1) * Hp, x, z, ctl, Hp, Hp, 1);
         dx_prof_end();
         float* t = x; x = z; z = t;
         launches += 2;

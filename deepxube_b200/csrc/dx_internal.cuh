@@ -233,6 +233,14 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
                            const uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
                            uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
                            int max_children, const float* child_h = nullptr, float* node_h = nullptr);
+int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
+                           uint32_t max_open, const float* node_g, const float* node_h, const uint32_t* new_inst, const SortBufs& sb);
+int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
+                             const uint8_t* child_state, const float* child_g, uint32_t* child_slot, uint32_t* child_next,
+                             uint8_t* child_flags, uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
+                             uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
+                             uint32_t max_nodes, const uint32_t* pop_off, const uint8_t* pop_solved);
 int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const InstArrays& ia, const uint8_t* node_state,
                              const uint32_t* popped, const uint32_t* popped_inst, const uint8_t* pop_solved, const float* child_h,
                              const BackupLog& bk, int max_pop);

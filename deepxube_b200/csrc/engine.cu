@@ -204,6 +204,7 @@ struct dx_engine {
     uint8_t* child_flags = nullptr; uint32_t* child_prefix = nullptr; uint32_t* new_inst = nullptr;
     // evaluate-all engines (dx_config.max_backups > 0): the heuristic of EVERY generated child, before the CLOSED filter,
     // and the Bellman-backup log of the expanded nodes
+    bool fuse_small = true;
     bool eval_all = false;
     float* child_h = nullptr;
     BackupLog bk = {};
@@ -356,6 +357,11 @@ static int sync_ctl(dx_engine* e) {
 static bool small_sort(const dx_engine* e) {
     return e->hda_world < 1 && e->sort_bound > 0 && e->sort_bound <= DX_SMALL_SORT;
 }
+// small A* iterations: CLOSED filter + scan + scatter in one block, plan + keys + sort in another (DXB200_SMALL_FUSE=0: the
+// separate kernels, for A/B runs)
+static bool small_fused_v(const dx_engine* e) {
+    return small_sort(e) && e->fuse_small && !e->is_q && !e->is_beam && !e->eval_all;
+}
 
 static void drop_graphs(dx_engine* e) {
     for (int k = 0; k < 2; ++k) {
@@ -428,6 +434,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->is_q = cfg->algo == DX_ALGO_GRAPH_Q || cfg->algo == DX_ALGO_BEAM_Q;
     e->is_beam = cfg->algo == DX_ALGO_BEAM_V || cfg->algo == DX_ALGO_BEAM_Q;
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
+    if (const char* fs = getenv("DXB200_SMALL_FUSE")) e->fuse_small = !(fs[0] == '0');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -659,8 +666,9 @@ static int step_v_a(dx_engine* e) {
     stage_begin(e, ST_EXPAND);
     e->launches += dx_launch_expand(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
                                     e->pop_off[p], e->child_state, e->child_g, e->pop_solved, e->max_pop);
-    e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
-                                          e->pop_solved, e->max_pop);
+    if (!small_fused_v(e))             // (the fused small-iteration kernel resolves the goal nodes itself)
+        e->launches += dx_launch_goal_resolve(s, e->d_ctl, e->ia, e->node_g, e->popped[p], e->popped_inst[p], e->pop_off[p],
+                                              e->pop_solved, e->max_pop);
     stage_end(e);
     if (e->eval_all) {                 // the reference order (base/pathfinding.py:362-371): evaluate all children, then filter
         k_set_job_children<<<1, 1, 0, s>>>(e->d_ctl);
@@ -674,6 +682,15 @@ static int step_v_a(dx_engine* e) {
 static int step_v_filter(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity;
+    if (small_fused_v(e)) {
+        stage_begin(e, ST_CLOSED);
+        e->launches += dx_launch_small_filter_v(s, e->dom, e->closed, e->d_ctl, e->ia, e->child_state, e->child_g, e->child_slot,
+                                                e->child_next, e->child_flags, e->child_prefix, e->popped[p], e->popped_inst[p],
+                                                e->node_state, e->node_g, e->node_parent, e->node_action, e->new_inst,
+                                                e->max_nodes, e->pop_off[p], e->pop_solved);
+        stage_end(e);
+        return DX_OK;
+    }
     if (e->eval_all) {
         stage_begin(e, ST_BOOK);
         e->launches += dx_launch_bellman_backup(s, e->dom, e->d_ctl, e->ia, e->node_state, e->popped[p], e->popped_inst[p],
@@ -708,10 +725,16 @@ static int step_v_b(dx_engine* e) {
     if (e->eval_all) DX_TRY(step_v_filter(e));
     stage_begin(e, ST_SORT);
     const int beam = e->is_beam ? 1 : 0;
-    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
-                                  e->open_off[q], e->A, 1, e->max_pop, e->max_open, 0, beam);
-    e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort, beam);
-    e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
+    if (small_fused_v(e)) {
+        e->launches += dx_launch_small_push_v(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                              e->open_off[q], e->A, e->max_pop, e->max_open, e->node_g, e->node_h, e->new_inst,
+                                              e->sort);
+    } else {
+        e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                      e->open_off[q], e->A, 1, e->max_pop, e->max_open, 0, beam);
+        e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort, beam);
+        e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
+    }
     stage_end(e);
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;

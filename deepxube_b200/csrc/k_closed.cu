@@ -104,6 +104,27 @@ __device__ __forceinline__ float item_g(const ItemView& v, uint32_t c) {
     return v.batch_g[c];
 }
 
+__device__ __forceinline__ void closed_link_item(const ClosedDev& c, const Ctl* __restrict__ ctl, const ItemView& v,
+                                                 uint32_t* __restrict__ child_slot, uint32_t* __restrict__ child_next, uint32_t ci,
+                                                 uint32_t epoch, int chunks) {
+    const float g = item_g(v, ci);
+    if (g != g) { child_slot[ci] = DX_NIL; return; }      // item of a finished instance
+    const uint4* row = reinterpret_cast<const uint4*>(item_row(v, ci));
+    const uint32_t claim = v.item_node ? v.item_node[ci] : (DX_PENDING | ci);
+    const uint32_t i = closed_find_or_claim(c, row, chunks, claim, v.node_state, v.batch_rows, v.SP);
+    child_slot[ci] = i;
+    if (i == DX_NIL) { atomicOr((uint32_t*)&ctl->error, DX_DEVERR_NODES); return; }
+    unsigned long long old = *((volatile unsigned long long*)&c.slot_head[i]);
+    while (true) {
+        const uint32_t next = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
+        child_next[ci] = next;
+        const unsigned long long want = ((unsigned long long)epoch << 32) | ci;
+        const unsigned long long got = atomicCAS(&c.slot_head[i], old, want);
+        if (got == old) break;
+        old = got;
+    }
+}
+
 __global__ void __launch_bounds__(CL_THREADS)
 k_closed_link(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, uint32_t* __restrict__ child_slot,
               uint32_t* __restrict__ child_next) {
@@ -111,49 +132,37 @@ k_closed_link(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, uint32_t* __
     const uint32_t n = ctl->n_children;
     const uint32_t epoch = ctl->epoch;
     const int chunks = v.SP / 16;
-    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
-        const float g = item_g(v, ci);
-        if (g != g) { child_slot[ci] = DX_NIL; continue; }      // item of a finished instance
-        const uint4* row = reinterpret_cast<const uint4*>(item_row(v, ci));
-        const uint32_t claim = v.item_node ? v.item_node[ci] : (DX_PENDING | ci);
-        const uint32_t i = closed_find_or_claim(c, row, chunks, claim, v.node_state, v.batch_rows, v.SP);
-        child_slot[ci] = i;
-        if (i == DX_NIL) { atomicOr((uint32_t*)&ctl->error, DX_DEVERR_NODES); continue; }
-        unsigned long long old = *((volatile unsigned long long*)&c.slot_head[i]);
-        while (true) {
-            const uint32_t next = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
-            child_next[ci] = next;
-            const unsigned long long want = ((unsigned long long)epoch << 32) | ci;
-            const unsigned long long got = atomicCAS(&c.slot_head[i], old, want);
-            if (got == old) break;
-            old = got;
-        }
-    }
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
+        closed_link_item(c, ctl, v, child_slot, child_next, ci, epoch, chunks);
 }
 
 // flags: bit0 = keep, bit1 = final (this item's g becomes CLOSED[state])
+__device__ __forceinline__ uint8_t closed_decide_item(const ClosedDev& c, const ItemView& v, const uint32_t* __restrict__ child_slot,
+                                                      const uint32_t* __restrict__ child_next, uint32_t ci) {
+    const uint32_t i = child_slot[ci];
+    if (i == DX_NIL) return 0;
+    const float g = item_g(v, ci);
+    bool keep = g < c.slot_g[i];
+    bool fin = keep;
+    uint32_t c2 = (uint32_t)c.slot_head[i];
+    while (c2 != DX_NIL) {
+        if (c2 != ci) {
+            const float g2 = item_g(v, c2);
+            if (c2 < ci && g2 <= g) keep = false;                    // an earlier duplicate already set CLOSED <= g
+            if (g2 < g || (g2 == g && c2 < ci)) fin = false;
+        }
+        c2 = child_next[c2];
+    }
+    return (keep ? 1 : 0) | ((keep && fin) ? 2 : 0);
+}
+
 __global__ void __launch_bounds__(CL_THREADS)
 k_closed_decide(ClosedDev c, const Ctl* __restrict__ ctl, ItemView v, const uint32_t* __restrict__ child_slot,
                 const uint32_t* __restrict__ child_next, uint8_t* __restrict__ child_flags) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;
-    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
-        const uint32_t i = child_slot[ci];
-        if (i == DX_NIL) { child_flags[ci] = 0; continue; }
-        const float g = item_g(v, ci);
-        bool keep = g < c.slot_g[i];
-        bool fin = keep;
-        uint32_t c2 = (uint32_t)c.slot_head[i];
-        while (c2 != DX_NIL) {
-            if (c2 != ci) {
-                const float g2 = item_g(v, c2);
-                if (c2 < ci && g2 <= g) keep = false;                    // an earlier duplicate already set CLOSED <= g
-                if (g2 < g || (g2 == g && c2 < ci)) fin = false;
-            }
-            c2 = child_next[c2];
-        }
-        child_flags[ci] = (keep ? 1 : 0) | ((keep && fin) ? 2 : 0);
-    }
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
+        child_flags[ci] = closed_decide_item(c, v, child_slot, child_next, ci);
 }
 
 int dx_launch_closed_filter(cudaStream_t s, const DomainDev& d, const ClosedDev& c, const Ctl* ctl, const InstArrays& ia,
@@ -168,39 +177,133 @@ int dx_launch_closed_filter(cudaStream_t s, const DomainDev& d, const ClosedDev&
 }
 
 // A*: kept children become nodes (ids in flat child order = push order); final items commit CLOSED.
+struct ScatterArgs {
+    const uint8_t* child_state; const float* child_g; const uint32_t* child_slot; const uint8_t* child_flags;
+    const uint32_t* child_prefix; const uint32_t* popped; const uint32_t* popped_inst;
+    uint8_t* node_state; float* node_g; uint32_t* node_parent; uint8_t* node_action; uint32_t* new_inst;
+    const float* child_h; float* node_h;
+};
+
+__device__ __forceinline__ void scatter_kept_item(const DomainDev& d, const ClosedDev& c, const ScatterArgs& a, uint32_t ci,
+                                                  uint32_t base, int chunks) {
+    const uint8_t f = a.child_flags[ci];
+    if (!(f & 1)) return;
+    const uint32_t k = a.child_prefix[ci];
+    const uint32_t id = base + k;
+    const uint4* src = reinterpret_cast<const uint4*>(a.child_state + (size_t)ci * d.SP);
+    uint4* dst = reinterpret_cast<uint4*>(a.node_state + (size_t)id * d.SP);
+    for (int q = 0; q < chunks; ++q) dst[q] = src[q];
+    const float g = a.child_g[ci];
+    const uint32_t j = ci / d.A;
+    a.node_g[id] = g;
+    a.node_parent[id] = a.popped[j];
+    a.node_action[id] = (uint8_t)(ci % d.A);
+    a.new_inst[k] = a.popped_inst[j];
+    if (a.child_h) a.node_h[id] = a.child_h[ci];       // evaluate-all engines: the value was computed before the filter
+    if (f & 2) {
+        const uint32_t i = a.child_slot[ci];
+        c.slot_g[i] = g;
+        const unsigned long long key = c.slot_key[i];
+        if ((uint32_t)key & DX_PENDING) c.slot_key[i] = (key & 0xFFFFFFFF00000000ull) | id;
+    }
+}
+
 __global__ void __launch_bounds__(CL_THREADS)
-k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, const uint8_t* __restrict__ child_state,
-               const float* __restrict__ child_g, const uint32_t* __restrict__ child_slot,
-               const uint8_t* __restrict__ child_flags, const uint32_t* __restrict__ child_prefix,
-               const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst, uint8_t* __restrict__ node_state,
-               float* __restrict__ node_g, uint32_t* __restrict__ node_parent, uint8_t* __restrict__ node_action,
-               uint32_t* __restrict__ new_inst, const float* __restrict__ child_h, float* __restrict__ node_h) {
+k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ScatterArgs a) {
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;
     const uint32_t base = ctl->node_base;
     const int chunks = d.SP / 16;
-    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x) {
-        const uint8_t f = child_flags[ci];
-        if (!(f & 1)) continue;
-        const uint32_t k = child_prefix[ci];
-        const uint32_t id = base + k;
-        const uint4* src = reinterpret_cast<const uint4*>(child_state + (size_t)ci * d.SP);
-        uint4* dst = reinterpret_cast<uint4*>(node_state + (size_t)id * d.SP);
-        for (int q = 0; q < chunks; ++q) dst[q] = src[q];
-        const float g = child_g[ci];
-        const uint32_t j = ci / d.A;
-        node_g[id] = g;
-        node_parent[id] = popped[j];
-        node_action[id] = (uint8_t)(ci % d.A);
-        new_inst[k] = popped_inst[j];
-        if (child_h) node_h[id] = child_h[ci];       // evaluate-all engines: the value was computed before the filter
-        if (f & 2) {
-            const uint32_t i = child_slot[ci];
-            c.slot_g[i] = g;
-            const unsigned long long key = c.slot_key[i];
-            if ((uint32_t)key & DX_PENDING) c.slot_key[i] = (key & 0xFFFFFFFF00000000ull) | id;
-        }
+    for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
+        scatter_kept_item(d, c, a, ci, base, chunks);
+}
+
+// Small batches (the host bounds the iteration's children by DX_SMALL_SORT, e.g. `graph.100B` on cube3 = 1200): CLOSED link +
+// decide, the kept-children scan with its bookkeeping (k_after_scan_v) and the scatter in ONE block (plus k_goal_resolve, which
+// only needs the expansion kernel finished) -- eight launches whose cost at this size is mostly their dependency latency.  Same device functions, same order of
+// phases; __syncthreads() is the grid-wide barrier the separate launches provided.
+#define SMALL_THREADS 1024
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, uint32_t* __restrict__ child_slot,
+                 uint32_t* __restrict__ child_next, uint8_t* __restrict__ child_flags, uint32_t* __restrict__ child_prefix,
+                 ScatterArgs a, uint32_t max_nodes, InstArrays ia, const uint32_t* __restrict__ pop_off,
+                 const uint8_t* __restrict__ pop_solved) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_err;
+    if (ctl->error) return;
+    // k_goal_resolve (k_domain.cu): the solved popped node that won the (g, pop order) atomicMin becomes goal_node
+    for (uint32_t j = threadIdx.x; j < ctl->n_pop; j += SMALL_THREADS) {
+        if (!pop_solved[j]) continue;
+        const uint32_t inst = a.popped_inst[j], id = a.popped[j];
+        const unsigned long long key = ((unsigned long long)__float_as_uint(a.node_g[id]) << 32) |
+                                       (unsigned long long)(ia.pop_seq_base[inst] + j - pop_off[inst]);
+        if (ia.ub_key[inst] == key) ia.goal_node[inst] = id;
     }
+    const uint32_t n = ctl->n_children;
+    if (n > 4u * SMALL_THREADS) {            // the host's bound was wrong: fail loudly
+        if (threadIdx.x == 0) atomicOr(&ctl->error, DX_DEVERR_POP);
+        return;
+    }
+    const uint32_t epoch = ctl->epoch;
+    const int chunks = v.SP / 16;
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) closed_link_item(c, ctl, v, child_slot, child_next, ci, epoch, chunks);
+    __syncthreads();
+    if (threadIdx.x == 0) s_err = *((volatile uint32_t*)&ctl->error);
+    __syncthreads();
+    if (s_err) return;
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) child_flags[ci] = closed_decide_item(c, v, child_slot, child_next, ci);
+    __syncthreads();
+    // exclusive scan of (flags & 1): 4 consecutive items per thread, prefix[n] = total (as dx_launch_scan_flags)
+    const uint32_t base4 = threadIdx.x * 4;
+    uint32_t f4[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f4[i] = (base4 + i < n) ? (child_flags[base4 + i] & 1u) : 0u; sum += f4[i]; }
+    uint32_t x = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    const uint32_t total = s_warp[31];
+    uint32_t ex = (warp ? s_warp[warp - 1] : 0) + x - sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (base4 + i < n) child_prefix[base4 + i] = ex; ex += f4[i]; }
+    if (base4 <= n && n < base4 + 4) child_prefix[n] = ex;
+    if (threadIdx.x == 0) {                  // k_after_scan_v
+        ctl->n_kept = total;
+        if ((unsigned long long)ctl->node_base + total > max_nodes) {
+            ctl->error |= DX_DEVERR_NODES;
+        } else {
+            ctl->node_count = ctl->node_base + total;
+            ctl->nn_row_start = ctl->node_base;
+            ctl->nn_n = total;
+        }
+        s_err = ctl->error;
+    }
+    __syncthreads();
+    if (s_err) return;
+    const uint32_t nbase = ctl->node_base;
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) scatter_kept_item(d, c, a, ci, nbase, chunks);
+}
+
+int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
+                             const uint8_t* child_state, const float* child_g, uint32_t* child_slot, uint32_t* child_next,
+                             uint8_t* child_flags, uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,
+                             uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
+                             uint32_t max_nodes, const uint32_t* pop_off, const uint8_t* pop_solved) {
+    ItemView v{child_state, child_g, nullptr, node_state, node_g, popped_inst, ia.active, d.A, d.SP};
+    ScatterArgs a{child_state, child_g, child_slot, child_flags, child_prefix, popped, popped_inst,
+                  node_state, node_g, node_parent, node_action, new_inst, nullptr, nullptr};
+    k_small_filter_v<<<1, SMALL_THREADS, 0, s>>>(d, c, ctl, v, child_slot, child_next, child_flags, child_prefix, a, max_nodes, ia,
+                                                 pop_off, pop_solved);
+    return 1;
 }
 
 int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const uint8_t* child_state,
@@ -209,9 +312,9 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
                            uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, uint32_t* new_inst,
                            int max_children, const float* child_h, float* node_h) {
     int blocks = min(dx_div_up(max_children, CL_THREADS), 148 * 8);
-    k_scatter_kept<<<blocks, CL_THREADS, 0, s>>>(d, c, ctl, child_state, child_g, child_slot, child_flags, child_prefix, popped,
-                                                 popped_inst, node_state, node_g, node_parent, node_action, new_inst, child_h,
-                                                 node_h);
+    ScatterArgs a{child_state, child_g, child_slot, child_flags, child_prefix, popped, popped_inst,
+                  node_state, node_g, node_parent, node_action, new_inst, child_h, node_h};
+    k_scatter_kept<<<blocks, CL_THREADS, 0, s>>>(d, c, ctl, a);
     return 1;
 }
 

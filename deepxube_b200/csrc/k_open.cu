@@ -26,12 +26,12 @@
 static_assert(OPEN_THREADS * ITEMS == DX_SORT_TILE, "tile size");
 
 // ---------------------------------------------------------------------------------------------
-__global__ void __launch_bounds__(1024)
-k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
-       uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
-       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open, int kept_is_total, int beam) {
-    __shared__ uint32_t s_tot[4][1024];
-    if (ctl->error) return;
+// (all 1024 threads of ONE block call this; s_tot = 4 x 1024 words of shared memory)
+__device__ __forceinline__ void plan_body(uint32_t (*s_tot)[1024], Ctl* __restrict__ ctl, const InstArrays& ia,
+                                          const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+                                          uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur,
+                                          uint32_t* __restrict__ open_off_next, int child_mult, int push_mult, uint32_t max_pop,
+                                          uint32_t max_open, int kept_is_total, int beam) {
     const int I = ctl->n_inst;
     const int per = (I + 1023) / 1024;
     const int lo = min(I, (int)threadIdx.x * per), hi = min(I, lo + per);
@@ -69,6 +69,16 @@ k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix
         const uint32_t t = beam ? m : n + k;          // elements the merge of this instance walks
         om += m; ok += k; on += n; ot += (t + DX_SORT_TILE - 1) / DX_SORT_TILE;
     }
+}
+
+__global__ void __launch_bounds__(1024)
+k_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+       uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
+       int child_mult, int push_mult, uint32_t max_pop, uint32_t max_open, int kept_is_total, int beam) {
+    __shared__ uint32_t s_tot[4][1024];
+    if (ctl->error) return;
+    plan_body(s_tot, ctl, ia, prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, child_mult, push_mult, max_pop,
+              max_open, kept_is_total, beam);
 }
 
 int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
@@ -328,13 +338,10 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 // block -- a bitonic network in shared memory on (instance, f-key, original position), the position making it the same
 // stable order as the radix sort -- instead of 2 + 3 launches per digit pass, which at these sizes are pure launch latency
 // (26 of the 40 launches of an iteration).  Output goes to buffer 1, like an odd number of radix passes.
-__global__ void __launch_bounds__(OPEN_THREADS)
-k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
-    __shared__ unsigned long long s_key[DX_SMALL_SORT];
-    __shared__ uint32_t s_inst[DX_SMALL_SORT];
-    __shared__ uint32_t s_idx[DX_SMALL_SORT];
-    if (ctl->error) return;
-    const uint32_t n = ctl->sort_n;
+// (all threads of ONE block; s_key / s_inst / s_idx hold DX_SMALL_SORT entries each)
+__device__ __forceinline__ void sort_small_body(Ctl* __restrict__ ctl, const SortBufs& sb, unsigned long long* s_key, uint32_t* s_inst,
+                                                uint32_t* s_idx) {
+    const uint32_t n = ctl->sort_n, nt = blockDim.x;
     if (n > DX_SMALL_SORT) {                 // the host's bound was wrong: fail loudly instead of sorting a prefix
         if (threadIdx.x == 0) atomicOr(&ctl->error, DX_DEVERR_POP);
         return;
@@ -343,7 +350,7 @@ k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
     if (n == 0) return;
     uint32_t m = 1;
     while (m < n) m <<= 1;
-    for (uint32_t i = threadIdx.x; i < m; i += OPEN_THREADS) {
+    for (uint32_t i = threadIdx.x; i < m; i += nt) {
         const bool in = i < n;
         s_key[i] = in ? sb.key[0][i] : ~0ull;
         s_inst[i] = in ? sb.inst[0][i] : 0xFFFFFFFFu;
@@ -352,7 +359,7 @@ k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
     for (uint32_t k = 2; k <= m; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
             __syncthreads();
-            for (uint32_t i = threadIdx.x; i < m; i += OPEN_THREADS) {
+            for (uint32_t i = threadIdx.x; i < m; i += nt) {
                 const uint32_t p = i ^ j;
                 if (p > i) {
                     const unsigned long long ka = s_key[i], kb = s_key[p];
@@ -367,16 +374,63 @@ k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
             }
         }
     __syncthreads();
-    for (uint32_t i = threadIdx.x; i < n; i += OPEN_THREADS) {
+    for (uint32_t i = threadIdx.x; i < n; i += nt) {
         sb.key[1][i] = s_key[i];
         sb.inst[1][i] = s_inst[i];
         sb.val[1][i] = sb.val[0][s_idx[i]];
     }
 }
 
+__global__ void __launch_bounds__(1024)
+k_sort_small(Ctl* __restrict__ ctl, SortBufs sb) {
+    __shared__ unsigned long long s_key[DX_SMALL_SORT];
+    __shared__ uint32_t s_inst[DX_SMALL_SORT];
+    __shared__ uint32_t s_idx[DX_SMALL_SORT];
+    if (ctl->error) return;
+    sort_small_body(ctl, sb, s_key, s_inst, s_idx);
+}
+
+// Small batches, A*: k_plan + k_make_keys_v + k_sort_small in one block (three launches -> one); the plan's scratch and the
+// sort's arrays share the block's shared memory.
+__global__ void __launch_bounds__(1024)
+k_small_push_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+               uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
+               int A, uint32_t max_pop, uint32_t max_open, const float* __restrict__ node_g, const float* __restrict__ node_h,
+               const uint32_t* __restrict__ new_inst, SortBufs sb) {
+    __shared__ unsigned long long s_key[DX_SMALL_SORT];      // 16 KB, first used as the plan's 4 x 1024 words
+    __shared__ uint32_t s_inst[DX_SMALL_SORT];
+    __shared__ uint32_t s_idx[DX_SMALL_SORT];
+    __shared__ uint32_t s_err;
+    static_assert(sizeof(unsigned long long) * DX_SMALL_SORT >= 4 * 1024 * sizeof(uint32_t), "plan scratch fits");
+    if (ctl->error) return;
+    plan_body(reinterpret_cast<uint32_t (*)[1024]>(s_key), ctl, ia, prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A,
+              1, max_pop, max_open, 0, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) s_err = *((volatile uint32_t*)&ctl->error);
+    __syncthreads();
+    if (s_err) return;
+    const uint32_t n = ctl->sort_n, base = ctl->node_base;
+    for (uint32_t k = threadIdx.x; k < n; k += blockDim.x) {          // k_make_keys_v
+        const uint32_t id = base + k, inst = new_inst[k];
+        sb.key[0][k] = f_key(ia.weight[inst], node_g[id], node_h[id]);
+        sb.inst[0][k] = inst;
+        sb.val[0][k] = id;
+    }
+    __syncthreads();
+    sort_small_body(ctl, sb, s_key, s_inst, s_idx);
+}
+
+int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
+                           uint32_t max_open, const float* node_g, const float* node_h, const uint32_t* new_inst, const SortBufs& sb) {
+    k_small_push_v<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
+                                      max_open, node_g, node_h, new_inst, sb);
+    return 1;
+}
+
 int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n, bool small) {
     if (small) {
-        k_sort_small<<<1, OPEN_THREADS, 0, s>>>(ctl, sb);
+        k_sort_small<<<1, 1024, 0, s>>>(ctl, sb);
         return 1;
     }
     int launches = 0;

@@ -338,7 +338,7 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 // block -- a bitonic network in shared memory on (instance, f-key, original position), the position making it the same
 // stable order as the radix sort -- instead of 2 + 3 launches per digit pass, which at these sizes are pure launch latency
 // (26 of the 40 launches of an iteration).  Output goes to buffer 1, like an odd number of radix passes.
-// (all threads of ONE block; s_key / s_inst / s_idx hold DX_SMALL_SORT entries each)
+// (all 1024 threads of ONE block; s_key / s_inst / s_idx hold DX_SMALL_SORT entries each)
 __device__ __forceinline__ void sort_small_body(Ctl* __restrict__ ctl, const SortBufs& sb, unsigned long long* s_key, uint32_t* s_inst,
                                                 uint32_t* s_idx) {
     const uint32_t n = ctl->sort_n, nt = blockDim.x;
@@ -356,20 +356,23 @@ __device__ __forceinline__ void sort_small_body(Ctl* __restrict__ ctl, const Sor
         s_inst[i] = in ? sb.inst[0][i] : 0xFFFFFFFFu;
         s_idx[i] = i;
     }
+    // one compare-exchange pair per thread and stage (m / 2 <= 1024 pairs).  Pair q of stage j is (i, i | j) with i = q with a
+    // zero bit inserted at log2(j): for j <= 32 both elements lie in the 64-element block owned by q's warp, so those stages
+    // (51 of the 66 for m = 2048) only need __syncwarp(); a block barrier is needed when the previous stage crossed warps.
+    __syncthreads();
+    const uint32_t half = m >> 1, q = threadIdx.x;
     for (uint32_t k = 2; k <= m; k <<= 1)
         for (uint32_t j = k >> 1; j > 0; j >>= 1) {
-            __syncthreads();
-            for (uint32_t i = threadIdx.x; i < m; i += nt) {
-                const uint32_t p = i ^ j;
-                if (p > i) {
-                    const unsigned long long ka = s_key[i], kb = s_key[p];
-                    const uint32_t ia = s_inst[i], ib = s_inst[p], xa = s_idx[i], xb = s_idx[p];
-                    const bool a_gt_b = ia != ib ? ia > ib : (ka != kb ? ka > kb : xa > xb);
-                    if (a_gt_b == ((i & k) == 0)) {
-                        s_key[i] = kb; s_key[p] = ka;
-                        s_inst[i] = ib; s_inst[p] = ia;
-                        s_idx[i] = xb; s_idx[p] = xa;
-                    }
+            if (j >= 32) __syncthreads(); else __syncwarp();
+            if (q < half) {
+                const uint32_t i = ((q & ~(j - 1)) << 1) | (q & (j - 1)), p = i | j;
+                const unsigned long long ka = s_key[i], kb = s_key[p];
+                const uint32_t ia = s_inst[i], ib = s_inst[p], xa = s_idx[i], xb = s_idx[p];
+                const bool a_gt_b = ia != ib ? ia > ib : (ka != kb ? ka > kb : xa > xb);
+                if (a_gt_b == ((i & k) == 0)) {
+                    s_key[i] = kb; s_key[p] = ka;
+                    s_inst[i] = ib; s_inst[p] = ia;
+                    s_idx[i] = xb; s_idx[p] = xa;
                 }
             }
         }

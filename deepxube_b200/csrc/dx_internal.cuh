@@ -101,6 +101,20 @@ struct InstArrays {
     uint8_t* goals;             // [I, SP] goal rows
 };
 
+// is_solved (cube3.py:514-517, npuzzle.py:154-158: goal byte d*d = wildcard, grid.py:68-69, lightsout: all tiles off)
+__device__ __forceinline__ bool row_solved(int kind, int dim, int S, const uint8_t* __restrict__ row,
+                                           const uint8_t* __restrict__ goal) {
+    bool ok = true;
+    const int wild = dim * dim;
+    for (int i = 0; i < S; ++i) {
+        uint8_t g = goal[i];
+        bool e = (row[i] == g);
+        if (kind == DX_DOMAIN_NPUZZLE) e = e || (g == wild);
+        ok = ok && e;
+    }
+    return ok;
+}
+
 // Training-label log (engines created with dx_config.max_backups > 0): one record per expanded node (A*) / popped edge (Q*)
 struct BackupLog {
     uint8_t* state;      // [cap, SP] the record's state row
@@ -236,6 +250,14 @@ int dx_launch_scatter_kept(cudaStream_t s, const DomainDev& d, const ClosedDev& 
 int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                            uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
                            uint32_t max_open, const float* node_g, const float* node_h, const uint32_t* new_inst, const SortBufs& sb);
+int dx_launch_small_filter_q(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
+                             const uint8_t* node_state, const float* node_g, const uint32_t* popped, const uint32_t* popped_inst,
+                             const uint32_t* pop_off, uint8_t* pop_solved, uint32_t* child_slot, uint32_t* child_next,
+                             uint8_t* child_flags, uint32_t* child_prefix);
+int dx_launch_small_push_q(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
+                           uint32_t max_open, const float* node_g, const float* node_q, const uint32_t* popped,
+                           const uint32_t* popped_inst, const uint8_t* flags, const SortBufs& sb);
 int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
                              const uint8_t* child_state, const float* child_g, uint32_t* child_slot, uint32_t* child_next,
                              uint8_t* child_flags, uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,

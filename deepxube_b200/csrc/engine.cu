@@ -359,6 +359,9 @@ static bool small_sort(const dx_engine* e) {
 }
 // small A* iterations: CLOSED filter + scan + scatter in one block, plan + keys + sort in another (DXB200_SMALL_FUSE=0: the
 // separate kernels, for A/B runs)
+static bool small_fused_q(const dx_engine* e) {
+    return small_sort(e) && e->fuse_small && e->is_q && !e->is_beam && !e->backups_q;
+}
 static bool small_fused_v(const dx_engine* e) {
     return small_sort(e) && e->fuse_small && !e->is_q && !e->is_beam && !e->eval_all;
 }
@@ -748,10 +751,24 @@ static int step_v_b(dx_engine* e) {
     return DX_OK;
 }
 
+static int step_q_pop(dx_engine* e);
 // Q* phase A: up to (and including) generating the children of the popped edges.
 static int step_q_a(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity, q = p ^ 1;
+    if (small_fused_q(e)) {
+        stage_begin(e, ST_CLOSED);
+        e->launches += dx_launch_small_filter_q(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p],
+                                                e->popped_inst[p], e->pop_off[p], e->pop_solved, e->child_slot, e->child_next,
+                                                e->child_flags, e->child_prefix);
+        stage_end(e);
+        stage_begin(e, ST_SORT);
+        e->launches += dx_launch_small_push_q(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                              e->open_off[q], e->A, e->max_pop, e->max_open, e->node_g, e->node_q, e->popped[p],
+                                              e->popped_inst[p], e->child_flags, e->sort);
+        stage_end(e);
+        return step_q_pop(e);
+    }
     stage_begin(e, ST_EXPAND);
     e->launches += dx_launch_check_solved(s, e->dom, e->d_ctl, e->ia, e->node_state, e->node_g, e->popped[p], e->popped_inst[p],
                                           e->pop_off[p], e->pop_solved, e->max_pop);
@@ -783,6 +800,14 @@ static int step_q_a(dx_engine* e) {
                                          e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop, beam);
     e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     stage_end(e);
+    return step_q_pop(e);
+}
+
+// Q*: merge the pushed edges into OPEN, pop, generate the popped edges' children
+static int step_q_pop(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity, q = p ^ 1;
+    const int beam = e->is_beam ? 1 : 0;
     stage_begin(e, ST_MERGE);
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
     e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],

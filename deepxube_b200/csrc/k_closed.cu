@@ -293,6 +293,86 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
     for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) scatter_kept_item(d, c, a, ci, nbase, chunks);
 }
 
+// Q*, small batches: is_solved + record_goal of the popped nodes (k_check_solved, k_goal_resolve), their CLOSED test (link +
+// decide), the scan of the kept ones and the CLOSED commit in ONE block (eight launches).
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_small_filter_q(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, InstArrays ia, const uint32_t* __restrict__ pop_off,
+                 uint8_t* __restrict__ pop_solved, uint32_t* __restrict__ child_slot, uint32_t* __restrict__ child_next,
+                 uint8_t* __restrict__ child_flags, uint32_t* __restrict__ child_prefix) {
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_err;
+    if (ctl->error) return;
+    const uint32_t n = ctl->n_children;          // = n_pop: the items are the popped nodes
+    if (n > 4u * SMALL_THREADS || ctl->n_pop != n) {
+        if (threadIdx.x == 0) atomicOr(&ctl->error, DX_DEVERR_POP);
+        return;
+    }
+    for (uint32_t j = threadIdx.x; j < n; j += SMALL_THREADS) {                       // k_check_solved
+        const uint32_t inst = v.popped_inst[j], id = v.item_node[j];
+        bool solved = false;
+        if (ia.active[inst]) {
+            solved = row_solved(d.kind, d.dim, d.S, v.node_state + (size_t)id * d.SP, ia.goals + (size_t)inst * d.SP);
+            if (solved) {
+                const unsigned long long key = ((unsigned long long)__float_as_uint(v.node_g[id]) << 32) |
+                                               (unsigned long long)(ia.pop_seq_base[inst] + j - pop_off[inst]);
+                atomicMin(&ia.ub_key[inst], key);
+            }
+        }
+        pop_solved[j] = solved ? 1 : 0;
+    }
+    __syncthreads();
+    for (uint32_t j = threadIdx.x; j < n; j += SMALL_THREADS) {                       // k_goal_resolve
+        if (!pop_solved[j]) continue;
+        const uint32_t inst = v.popped_inst[j], id = v.item_node[j];
+        const unsigned long long key = ((unsigned long long)__float_as_uint(v.node_g[id]) << 32) |
+                                       (unsigned long long)(ia.pop_seq_base[inst] + j - pop_off[inst]);
+        if (*((volatile unsigned long long*)&ia.ub_key[inst]) == key) ia.goal_node[inst] = id;
+    }
+    const uint32_t epoch = ctl->epoch;
+    const int chunks = v.SP / 16;
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) closed_link_item(c, ctl, v, child_slot, child_next, ci, epoch, chunks);
+    __syncthreads();
+    if (threadIdx.x == 0) s_err = *((volatile uint32_t*)&ctl->error);
+    __syncthreads();
+    if (s_err) return;
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) child_flags[ci] = closed_decide_item(c, v, child_slot, child_next, ci);
+    __syncthreads();
+    const uint32_t base4 = threadIdx.x * 4;
+    uint32_t f4[4], sum = 0;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { f4[i] = (base4 + i < n) ? (child_flags[base4 + i] & 1u) : 0u; sum += f4[i]; }
+    uint32_t x = sum;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+    if (lane == 31) s_warp[warp] = x;
+    __syncthreads();
+    if (warp == 0) {
+        uint32_t w = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        s_warp[lane] = w;
+    }
+    __syncthreads();
+    uint32_t ex = (warp ? s_warp[warp - 1] : 0) + x - sum;
+#pragma unroll
+    for (int i = 0; i < 4; ++i) { if (base4 + i < n) child_prefix[base4 + i] = ex; ex += f4[i]; }
+    if (base4 <= n && n < base4 + 4) child_prefix[n] = ex;
+    if (threadIdx.x == 0) ctl->n_kept = s_warp[31];
+    for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS)                       // k_closed_commit
+        if (child_flags[ci] & 2) c.slot_g[child_slot[ci]] = v.node_g[v.item_node[ci]];
+}
+
+int dx_launch_small_filter_q(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
+                             const uint8_t* node_state, const float* node_g, const uint32_t* popped, const uint32_t* popped_inst,
+                             const uint32_t* pop_off, uint8_t* pop_solved, uint32_t* child_slot, uint32_t* child_next,
+                             uint8_t* child_flags, uint32_t* child_prefix) {
+    ItemView v{nullptr, nullptr, popped, node_state, node_g, popped_inst, ia.active, 1, d.SP};
+    k_small_filter_q<<<1, SMALL_THREADS, 0, s>>>(d, c, ctl, v, ia, pop_off, pop_solved, child_slot, child_next, child_flags,
+                                                 child_prefix);
+    return 1;
+}
+
 int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
                              const uint8_t* child_state, const float* child_g, uint32_t* child_slot, uint32_t* child_next,
                              uint8_t* child_flags, uint32_t* child_prefix, const uint32_t* popped, const uint32_t* popped_inst,

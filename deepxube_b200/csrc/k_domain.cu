@@ -47,19 +47,6 @@ __device__ __forceinline__ uint32_t child_byte(int kind, int dim, int S, const u
     }
 }
 
-__device__ __forceinline__ bool row_solved(int kind, int dim, int S, const uint8_t* __restrict__ row,
-                                           const uint8_t* __restrict__ goal) {
-    bool ok = true;
-    const int wild = dim * dim;
-    for (int i = 0; i < S; ++i) {
-        uint8_t g = goal[i];
-        bool e = (row[i] == g);
-        if (kind == DX_DOMAIN_NPUZZLE) e = e || (g == wild);
-        ok = ok && e;
-    }
-    return ok;
-}
-
 __device__ __forceinline__ int find_blank(const uint8_t* row, int S) {
     int z = 0;
     for (int i = 0; i < S; ++i)

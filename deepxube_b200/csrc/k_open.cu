@@ -423,6 +423,47 @@ k_small_push_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict_
     sort_small_body(ctl, sb, s_key, s_inst, s_idx);
 }
 
+// Small batches, Q*: k_plan + k_make_keys_q + k_sort_small in one block.
+__global__ void __launch_bounds__(1024)
+k_small_push_q(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+               uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ open_off_next,
+               int A, uint32_t max_pop, uint32_t max_open, const float* __restrict__ node_g, const float* __restrict__ node_q,
+               const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst, const uint8_t* __restrict__ flags,
+               SortBufs sb) {
+    __shared__ unsigned long long s_key[DX_SMALL_SORT];
+    __shared__ uint32_t s_inst[DX_SMALL_SORT];
+    __shared__ uint32_t s_idx[DX_SMALL_SORT];
+    __shared__ uint32_t s_err;
+    if (ctl->error) return;
+    plan_body(reinterpret_cast<uint32_t (*)[1024]>(s_key), ctl, ia, prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, 1,
+              A, max_pop, max_open, 0, 0);
+    __syncthreads();
+    if (threadIdx.x == 0) s_err = *((volatile uint32_t*)&ctl->error);
+    __syncthreads();
+    if (s_err) return;
+    const uint32_t n = ctl->n_pop * A;
+    for (uint32_t t = threadIdx.x; t < n; t += blockDim.x) {           // k_make_keys_q
+        const uint32_t j = t / A, a = t % A;
+        if (!(flags[j] & 1)) continue;
+        const uint32_t node = popped[j], inst = popped_inst[j];
+        const uint32_t k = prefix[j] * A + a;
+        sb.key[0][k] = f_key(ia.weight[inst], node_g[node], node_q[(size_t)node * A + a]);
+        sb.inst[0][k] = inst;
+        sb.val[0][k] = node * A + a;
+    }
+    __syncthreads();
+    sort_small_body(ctl, sb, s_key, s_inst, s_idx);
+}
+
+int dx_launch_small_push_q(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
+                           uint32_t max_open, const float* node_g, const float* node_q, const uint32_t* popped,
+                           const uint32_t* popped_inst, const uint8_t* flags, const SortBufs& sb) {
+    k_small_push_q<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
+                                      max_open, node_g, node_q, popped, popped_inst, flags, sb);
+    return 1;
+}
+
 int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                            uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
                            uint32_t max_open, const float* node_g, const float* node_h, const uint32_t* new_inst, const SortBufs& sb) {

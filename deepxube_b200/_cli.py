@@ -26,8 +26,8 @@ def problem_inst_gen(args: argparse.Namespace) -> None:
     print(f"Time: {time.time() - t0}")
     print(f"Saving data to {args.file}")
     data: Dict = {"states": states, "goals": goals}
-    with open(args.file, "wb") as f:
-        pickle.dump(data, f, protocol=-1)
+    from deepxube_b200 import compat_pickle
+    compat_pickle.dump(data, args.file, ref_classes=getattr(args, "ref_pickle", False))
 
 
 def time_test_args(args: argparse.Namespace) -> None:
@@ -81,6 +81,8 @@ def main() -> None:
     p.add_argument('--num', type=int, required=True)
     p.add_argument('--file', type=str, required=True)
     p.add_argument('--redo', action='store_true', default=False)
+    p.add_argument('--ref_pickle', action='store_true', default=False,
+                   help="(B200) write the file with the reference's class paths (deepxube.domains.*)")
     p.set_defaults(func=problem_inst_gen)
     p = sub.add_parser("domain_info", help="List registered domains")
     p.set_defaults(func=lambda a: print("\n".join(domain_factory.get_all_class_names())))

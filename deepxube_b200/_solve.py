@@ -38,6 +38,9 @@ def parse_solve(parser: ArgumentParser) -> None:
     parser.add_argument('--precision', type=str, default=None, choices=["fp32", "bf16"],
                         help="(B200) arithmetic of the device network: fp32 parity path (default) or bf16 tensor cores")
     parser.add_argument('--max_nodes', type=int, default=None, help="(B200) node-store capacity of the engine")
+    parser.add_argument('--ref_pickle', action='store_true', default=False,
+                        help="(B200) write results.pkl with the reference's class paths (deepxube.domains.*) so that the "
+                             "reference's own tooling opens it")
     parser.set_defaults(func=solve_cli)
 
 
@@ -132,8 +135,7 @@ def solve_cli(args: argparse.Namespace) -> None:
                               float(100.0 * np.mean(results["solved"])), _get_mean(results, "times")))
         print("")
         pathfind.close()
-        with open(results_file, "wb") as f:
-            pickle.dump(results, f, protocol=-1)
+        compat_pickle.dump(results, results_file, ref_classes=getattr(args, "ref_pickle", False))
 
 
 def _get_mean(results: Dict[str, Any], key: str) -> float:

@@ -1,9 +1,11 @@
-"""Reading problem-instance / results pickles written by the reference.
+"""Reading AND writing problem-instance / results pickles in the reference's format.
 
 The reference pickles its own classes by module path (`deepxube.domains.cube3.Cube3State`,
 `domains.grid_tutorial.GridState`, ..., deepxube/_cli.py:456-462, _solve.py:215).  The classes of this package
 have the same attribute layout, so an Unpickler that redirects those module paths is enough to read the
-reference's `--file` inputs and `results.pkl` outputs without the reference installed."""
+reference's `--file` inputs and `results.pkl` outputs without the reference installed.  `dump(..., ref_classes=True)` writes
+the other direction: a pickle whose class references are the reference's module paths, so that the reference's own tooling
+(`deepxube viz --soln`, `deepxube solve --file`) opens files produced here (`--ref_pickle` of `solve` / `problem_inst`)."""
 import io
 import pickle
 from typing import Any
@@ -31,3 +33,26 @@ def load(file: Any) -> Any:
 
 def loads(data: bytes) -> Any:
     return _CompatUnpickler(io.BytesIO(data)).load()
+
+
+def dumps(obj: Any, ref_classes: bool = False) -> bytes:
+    """ref_classes: class references are written with the reference's module paths.  Protocol 2 is used for that: its GLOBAL
+    opcode stores `module\nname\n` as plain text lines without a length prefix, so the module path can be rewritten in the
+    byte stream (the classes keep their names and attribute layout; tutorial pickles of `domains.grid_tutorial` are written
+    as `deepxube.domains.grid`, which the reference registers itself)."""
+    if not ref_classes:
+        return pickle.dumps(obj, protocol=-1)
+    data = pickle.dumps(obj, protocol=2)
+    for ref_mod, mod in _MODULE_MAP.items():
+        if ref_mod.startswith("deepxube."):
+            data = data.replace(b"c" + mod.encode() + b"\n", b"c" + ref_mod.encode() + b"\n")
+    return data
+
+
+def dump(obj: Any, file: Any, ref_classes: bool = False) -> None:
+    data = dumps(obj, ref_classes)
+    if isinstance(file, (str, bytes)):
+        with open(file, "wb") as f:
+            f.write(data)
+    else:
+        file.write(data)

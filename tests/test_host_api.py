@@ -197,3 +197,43 @@ def test_updater_rl_rejects_what_it_does_not_implement():
         UpdateHeurQRLKeepGoal(dom, pv, 5)
     with pytest.raises(TypeError, match="graph_v / graph_q"):
         pb.enable_backups(10)
+
+
+def test_writes_pickles_the_reference_opens(tmp_path):
+    """SURVEY 8f.2, the other direction: files written with ref_classes=True carry the reference's class paths.  Checked
+    structurally everywhere (no deepxube_b200 path left in the stream, round trip through our reader) and, where the
+    reference is present (the build container), by loading them with the UNMODIFIED reference and using its domain on them."""
+    import pickle
+    import random
+    random.seed(2)
+    for dstr, ref_mod in (("cube3", "deepxube.domains.cube3"), ("npuzzle.4", "deepxube.domains.npuzzle"), ("grid.7d", "deepxube.domains.grid"),
+                          ("lightsout.5", "deepxube.domains.lightsout")):
+        dom, _ = get_domain_from_arg(dstr)
+        states, goals = dom.sample_problem_instances([0, 3, 10])
+        walked, acts, _ = dom.random_walk(states, [2, 2, 2])
+        data = {"states": states, "goals": goals, "actions": acts, "states_on_path": [[s, w] for s, w in zip(states, walked)]}
+        blob = compat_pickle.dumps(data, ref_classes=True)
+        assert b"deepxube_b200" not in blob and ("c" + ref_mod + "\n").encode() in blob
+        back = compat_pickle.loads(blob)                         # our reader maps the paths back
+        assert np.array_equal(dom.states_to_rows(back["states"]), dom.states_to_rows(states))
+        assert [dom.action_index(a) for al in back["actions"] for a in al] == [dom.action_index(a) for al in acts for a in al]
+        assert b"deepxube_b200" in compat_pickle.dumps(data)     # default: our own class paths
+        f = tmp_path / "d.pkl"
+        compat_pickle.dump(data, str(f), ref_classes=True)
+        assert f.read_bytes() == blob
+    from oracle.ref_shim import import_reference, reference_available
+    if not reference_available():
+        return
+    import_reference()
+    from deepxube.factories.domain_factory import get_domain_from_arg as ref_get_domain
+    for dstr in ("cube3", "npuzzle.4", "grid.7d", "lightsout.5"):
+        dom, _ = get_domain_from_arg(dstr)
+        rdom, _ = ref_get_domain(dstr)
+        states, goals = dom.sample_problem_instances([0, 3, 10])
+        walked, acts, _ = dom.random_walk(states, [1, 1, 1])
+        blob = compat_pickle.dumps({"states": states, "goals": goals, "actions": acts, "walked": walked}, ref_classes=True)
+        d = pickle.loads(blob)                                   # the plain unpickler of the reference's tooling
+        assert type(d["states"][0]).__module__.startswith("deepxube.domains")
+        assert rdom.is_solved(d["states"], d["goals"])[0]            # the 0-step instance
+        nxt, tcs = rdom.next_state(d["states"], [al[0] for al in d["actions"]])       # viz_step's replay (deepxube/_cli.py:246-249)
+        assert all(a == b for a, b in zip(nxt, d["walked"])) and all(t == 1.0 for t in tcs)

@@ -141,6 +141,18 @@ def test_solve_cli_reproduces_tutorial_kat(tmp_path):
         sys.argv, sys.stdout = argv, stdout
     again = pickle.load(open(os.path.join(res_dir, "results.pkl"), "rb"))
     assert again["path_costs"] == ref["path_costs"] and len(again["actions"]) == 10
+    # --ref_pickle: results.pkl with the reference's class paths (what `deepxube viz --soln` would open); our reader maps them back
+    res_ref = str(tmp_path / "results_ref")
+    sys.argv = argv2[:-1] + [res_ref, "--ref_pickle", "--max_itrs", "200"]
+    try:
+        _cli.main()
+    finally:
+        sys.argv, sys.stdout = argv, stdout
+    blob = open(os.path.join(res_ref, "results.pkl"), "rb").read()
+    assert b"deepxube_b200" not in blob and b"cdeepxube.domains.cube3\nCube3State\n" in blob
+    back = compat_pickle.loads(blob)
+    assert back["path_costs"] == ref["path_costs"]
+    assert [[a.action for a in al] for al in back["actions"]] == [[a.action for a in al] for al in ref["actions"]]
 
 
 def test_device_heur_callable_matches_reference_values():

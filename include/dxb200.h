@@ -140,7 +140,8 @@ int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done);
 
 /* HOST heuristic mode: one step() split around the host callable.
  *   dx_step_begin   pop/is_solved/record_goal/expand/closed filter (A*) or filter/edges/push/pop/next_state (Q*);
- *                   *n_pending = number of states that need values
+ *                   *n_pending = number of states that need values (graph_v: the children that passed the CLOSED filter;
+ *                   with max_backups > 0 the filter runs in dx_step_end and EVERY generated child is pending)
  *   dx_get_pending  copies those states [n_pending, state_bytes] and their goals to the host
  *   dx_step_end     takes h [n_pending] (graph_v) or q [n_pending, A] (graph_q), float32, already clipped,
  *                   and finishes the step (costs, push, pop, lb, finished, itr) */

@@ -49,12 +49,9 @@ __device__ __forceinline__ uint32_t closed_find_or_claim(const ClosedDev& c, con
     // the table holds >= 2x (max_nodes + max items per batch) slots, so a probe sequence always ends;
     // the bound only guards against a corrupted table (never spin forever on the device)
     for (uint32_t probes = 0; probes <= c.mask; ++probes) {
-        unsigned long long k = *((volatile unsigned long long*)&c.slot_key[i]);
-        if (k == DX_EMPTY64) {
-            unsigned long long old = atomicCAS(&c.slot_key[i], DX_EMPTY64, mine);
-            if (old == DX_EMPTY64) return i;
-            k = old;
-        }
+        // CAS first: a new state (the common case) claims its slot in ONE round trip; an occupied slot returns its key
+        const unsigned long long k = atomicCAS(&c.slot_key[i], DX_EMPTY64, mine);
+        if (k == DX_EMPTY64) return i;
         if ((uint32_t)(k >> 32) == tag) {
             const uint32_t rep = (uint32_t)k;
             const uint8_t* other = (rep & DX_PENDING) ? (batch_rows + (size_t)(rep & ~DX_PENDING) * SP)
@@ -114,15 +111,10 @@ __device__ __forceinline__ void closed_link_item(const ClosedDev& c, const Ctl* 
     const uint32_t i = closed_find_or_claim(c, row, chunks, claim, v.node_state, v.batch_rows, v.SP);
     child_slot[ci] = i;
     if (i == DX_NIL) { atomicOr((uint32_t*)&ctl->error, DX_DEVERR_NODES); return; }
-    unsigned long long old = *((volatile unsigned long long*)&c.slot_head[i]);
-    while (true) {
-        const uint32_t next = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
-        child_next[ci] = next;
-        const unsigned long long want = ((unsigned long long)epoch << 32) | ci;
-        const unsigned long long got = atomicCAS(&c.slot_head[i], old, want);
-        if (got == old) break;
-        old = got;
-    }
+    // push on the slot's per-iteration list: nobody walks the lists before the link phase is over (kernel boundary or block
+    // barrier), so one exchange is enough -- the old head (if it is of this iteration) becomes this item's successor
+    const unsigned long long old = atomicExch(&c.slot_head[i], ((unsigned long long)epoch << 32) | ci);
+    child_next[ci] = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
 }
 
 __global__ void __launch_bounds__(CL_THREADS)

@@ -180,23 +180,35 @@ __device__ __forceinline__ void scatter_kept_item(const DomainDev& d, const Clos
                                                   uint32_t base, int chunks) {
     const uint8_t f = a.child_flags[ci];
     if (!(f & 1)) return;
+    // every load first (the pointers may alias as far as the compiler knows: a load placed after a store waits for the data the
+    // store needs, which turns a row copy into a chain of round trips), then the stores
+    const uint32_t j = ci / d.A;
     const uint32_t k = a.child_prefix[ci];
+    const float g = a.child_g[ci];
+    const uint32_t par = a.popped[j], inst = a.popped_inst[j];
+    const uint32_t slot = (f & 2) ? a.child_slot[ci] : 0u;
+    const float h = a.child_h ? a.child_h[ci] : 0.f;
     const uint32_t id = base + k;
     const uint4* src = reinterpret_cast<const uint4*>(a.child_state + (size_t)ci * d.SP);
     uint4* dst = reinterpret_cast<uint4*>(a.node_state + (size_t)id * d.SP);
-    for (int q = 0; q < chunks; ++q) dst[q] = src[q];
-    const float g = a.child_g[ci];
-    const uint32_t j = ci / d.A;
+    for (int q = 0; q < chunks; q += 4) {
+        uint4 r[4];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q + u < chunks) r[u] = src[q + u];
+#pragma unroll
+        for (int u = 0; u < 4; ++u)
+            if (q + u < chunks) dst[q + u] = r[u];
+    }
     a.node_g[id] = g;
-    a.node_parent[id] = a.popped[j];
+    a.node_parent[id] = par;
     a.node_action[id] = (uint8_t)(ci % d.A);
-    a.new_inst[k] = a.popped_inst[j];
-    if (a.child_h) a.node_h[id] = a.child_h[ci];       // evaluate-all engines: the value was computed before the filter
+    a.new_inst[k] = inst;
+    if (a.child_h) a.node_h[id] = h;                    // evaluate-all engines: the value was computed before the filter
     if (f & 2) {
-        const uint32_t i = a.child_slot[ci];
-        c.slot_g[i] = g;
-        const unsigned long long key = c.slot_key[i];
-        if ((uint32_t)key & DX_PENDING) c.slot_key[i] = (key & 0xFFFFFFFF00000000ull) | id;
+        c.slot_g[slot] = g;
+        const unsigned long long key = c.slot_key[slot];
+        if ((uint32_t)key & DX_PENDING) c.slot_key[slot] = (key & 0xFFFFFFFF00000000ull) | id;
     }
 }
 

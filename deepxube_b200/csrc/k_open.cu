@@ -53,9 +53,10 @@ __device__ __forceinline__ void plan_body(uint32_t (*s_tot)[1024], Ctl* __restri
     }
     s_tot[0][threadIdx.x] = sm; s_tot[1][threadIdx.x] = sk; s_tot[2][threadIdx.x] = sn; s_tot[3][threadIdx.x] = st;
     __syncthreads();
-    if (threadIdx.x < 4) {        // tiny serial scan over 1024 partials per quantity
-        uint32_t acc = 0;
-        for (int t = 0; t < 1024; ++t) { uint32_t v = s_tot[threadIdx.x][t]; s_tot[threadIdx.x][t] = acc; acc += v; }
+    if (threadIdx.x < 4) {        // tiny serial scan over the partials of the threads that own instances (the rest hold 0 and
+        uint32_t acc = 0;         // never read their prefix): one step for a single instance instead of 1024
+        const int used = (I + per - 1) / max(per, 1);
+        for (int t = 0; t < used; ++t) { uint32_t v = s_tot[threadIdx.x][t]; s_tot[threadIdx.x][t] = acc; acc += v; }
         if (threadIdx.x == 0) { ia.batch_off[I] = acc; ctl->sort_n = acc; }
         if (threadIdx.x == 1) { pop_off_next[I] = acc; if (acc > max_pop) atomicOr(&ctl->error, DX_DEVERR_POP); }
         if (threadIdx.x == 2) { open_off_next[I] = acc; ctl->open_total = acc; if (acc > max_open) atomicOr(&ctl->error, DX_DEVERR_OPEN); }
@@ -601,31 +602,33 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
     unsigned long long gen = 0;
     for (int i = threadIdx.x; i < I; i += blockDim.x) {
         if (!ia.active[i]) continue;
+        // all loads, then the stores (the arrays may alias as far as the compiler knows; interleaved they form one long chain)
         const uint32_t n_pop = pop_off_cur[i + 1] - pop_off_cur[i];
         const uint32_t k = ia.k_pop[i];
         double lb = ia.lb[i];
-        if (k > 0) lb = fmax(__longlong_as_double((long long)ia.f_first[i]), lb);   // graph_search.py:67-69
-        ia.lb[i] = lb;
+        const unsigned long long ff = ia.f_first[i], gen_old = ia.gen[i], ubk = ia.ub_key[i];
+        const uint32_t seq_old = ia.pop_seq_base[i], itr = ia.itr[i] + 1;
+        const double w = ia.weight[i];
+        if (k > 0) lb = fmax(__longlong_as_double((long long)ff), lb);              // graph_search.py:67-69
         const bool edge_mode = gen_mode == 1 || gen_mode == 3;
         const unsigned long long g_add = !edge_mode ? (unsigned long long)n_pop * A : (unsigned long long)k;
-        ia.gen[i] += g_add;
         gen += g_add;
-        ia.pop_seq_base[i] += n_pop;
-        const uint32_t itr = ia.itr[i] + 1;
-        ia.itr[i] = itr;
-        const unsigned long long ubk = ia.ub_key[i];
         bool fin = false;
         if (ubk != DX_EMPTY64) {
             const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
             fin = gen_mode >= 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
-                                : lb >= __dmul_rn(ia.weight[i], ub);                // graph_search.py:44
+                                : lb >= __dmul_rn(w, ub);                           // graph_search.py:44
         }
         fin = fin || (k == 0);                                                       // itr > 0 holds here (graph_search.py:45)
+        ia.lb[i] = lb;
+        ia.gen[i] = gen_old + g_add;
+        ia.pop_seq_base[i] = seq_old + n_pop;
+        ia.itr[i] = itr;
         ia.active[i] = fin ? 0 : 1;
         if (!fin) ++unfin;
     }
-    atomicAdd(&s_unfinished, unfin);
-    atomicAdd(&s_gen, gen);
+    if (unfin) atomicAdd(&s_unfinished, unfin);
+    if (gen) atomicAdd(&s_gen, gen);
     __syncthreads();
     if (threadIdx.x == 0) {
         ctl->n_unfinished = s_unfinished;

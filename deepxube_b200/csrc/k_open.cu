@@ -504,6 +504,24 @@ __device__ __forceinline__ uint32_t merge_path(const unsigned long long* __restr
     return lo;
 }
 
+// the same partition found by a whole warp: 32 probes per round trip (a 32-ary search, 3-4 dependent global accesses for any
+// OPEN size instead of one per halving -- the partition search is a pure latency chain at the head of every merge tile)
+__device__ __forceinline__ uint32_t merge_path_warp(const unsigned long long* __restrict__ a, uint32_t na,
+                                                    const unsigned long long* __restrict__ b, uint32_t nb, uint32_t diag) {
+    const uint32_t lane = threadIdx.x & 31;
+    uint32_t lo = diag > nb ? diag - nb : 0, hi = min(diag, na);
+    while (lo < hi) {                              // P(mid) = a[mid] <= b[diag - 1 - mid] is true ... true false ... false
+        const uint32_t step = (hi - lo) / 32 + 1;
+        const uint32_t idx = lo + lane * step;
+        const bool p = idx < hi && a[idx] <= b[diag - 1 - idx];
+        const uint32_t cnt = __popc(__ballot_sync(0xffffffffu, p));
+        if (cnt == 0) { hi = lo; break; }
+        const uint32_t nlo = lo + (cnt - 1) * step + 1, nhi = min(hi, lo + cnt * step);
+        lo = nlo; hi = nhi;
+    }
+    return lo;
+}
+
 __global__ void __launch_bounds__(OPEN_THREADS)
 k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
         const uint32_t* __restrict__ open_val_cur, const uint32_t* __restrict__ open_off_cur,
@@ -520,7 +538,8 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
     const uint32_t* __restrict__ bvals = sb.val[ctl->sort_final];
     for (uint32_t T = blockIdx.x; T < n_tiles; T += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x < 2) {
+        if (threadIdx.x < 64) {                 // warp 0: the tile's first diagonal, warp 1: its last
+            const int w = threadIdx.x >> 5;
             // instance of this tile: last i with tile_off[i] <= T
             int lo = 0, hi = I - 1;
             while (lo < hi) {
@@ -530,9 +549,12 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
             const int i = lo;
             const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
             const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
-            const uint32_t diag = threadIdx.x == 0 ? d0 : min(d0 + DX_SORT_TILE, na + nb);
-            s_part[threadIdx.x] = merge_path(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, diag);
-            if (threadIdx.x == 0) s_part[2] = i;
+            const uint32_t diag = w == 0 ? d0 : min(d0 + DX_SORT_TILE, na + nb);
+            const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, diag);
+            if ((threadIdx.x & 31) == 0) {
+                s_part[w] = part;
+                if (w == 0) s_part[2] = i;
+            }
         }
         __syncthreads();
         const int i = s_part[2];

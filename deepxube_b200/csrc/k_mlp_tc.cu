@@ -347,7 +347,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0) {
             // ---------------- TMA producer (every CTA: its A rows, its share of the weight tile) ----------------
             uint32_t it = 0;
-            long long w_empty = 0;
+            [[maybe_unused]] long long w_empty = 0;
             if (GEN_A) {       // weight tiles only: ring of nb_st slots behind the resident A tiles
                 uint32_t s = 0, ph = 0;
                 int m0, n0;
@@ -402,7 +402,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
                                    ((uint32_t)((TC_BM * PAIR) >> 4) << 24);
             uint32_t it = 0, lt = 0;
-            long long w_full = 0, w_tempty = 0;
+            [[maybe_unused]] long long w_full = 0, w_tempty = 0;
 #ifdef TC_PROFILE
             const long long t_mma0 = clock64();
 #endif
@@ -499,7 +499,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         };
         if (cl_id < groups) prefetch_rows(cl_id, 0);
         uint32_t lt = 0;                                 // row groups done by this cluster
-        long long w_gslot = 0, w_gmask = 0, w_gexp = 0, w_gsync = 0;
+        [[maybe_unused]] long long w_gslot = 0, w_gmask = 0, w_gexp = 0, w_gsync = 0;
 #ifdef TC_PROFILE
         const long long t_gen0 = clock64();
 #endif
@@ -590,7 +590,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         constexpr int NCH = BN / 32;
         uint32_t rphase = 0;                     // bit b = parity the next wait on residual buffer b expects
         uint32_t lt = 0;
-        long long w_tfull = 0, w_res = 0, w_store = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0;
+        [[maybe_unused]] long long w_tfull = 0, w_res = 0, w_store = 0, w_ld = 0, w_math = 0, w_fence = 0, w_issue = 0;
 #ifdef TC_PROFILE
         const long long t_epi0 = clock64();
 #endif

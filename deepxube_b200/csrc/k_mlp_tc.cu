@@ -52,6 +52,7 @@ struct TcPlan {
     int q_out;                   // the multi-output layer runs on the tensor cores (DXB200_QOUT=0: warp-per-state kernel)
     CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
     __nv_bfloat16* onehot;
+    long long max_rows;          // capacity of the activation buffers: no launch ever has more rows than this
     int BN;
     int CL;                      // CTAs per cluster of the hidden layers: 1 = single-CTA tiles, 2 = cta_group::2 pairs,
                                  // 4 = two pairs sharing their A tiles by TMA multicast (DXB200_GEMM_CLUSTER)
@@ -936,6 +937,7 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     }
     EncodeTiledFn enc = (EncodeTiledFn)fn;
     TcPlan* p = new TcPlan();
+    p->max_rows = mb.cap;
     p->BN = (net.Hp % 256 == 0) ? 256 : 128;      // n-tiles must divide the padded width (Hp is a multiple of 128)
     p->CL = 2;
     if (const char* c = getenv("DXB200_GEMM_CLUSTER")) p->CL = (c[0] == '1') ? 1 : (c[0] == '4' ? 4 : 2);
@@ -1037,7 +1039,16 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorM
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
-    cfg.gridDim = dim3((unsigned)(cl == 4 ? p->grid4 : p->num_sms / cl * cl));
+    // persistent grid: one cluster per SM group, but never more clusters than the engine's capacity can give work to (a
+    // `graph.100B` engine evaluates <= 1200 rows: 5 row groups, not 74 clusters' worth of barrier / TMEM set-up per launch)
+    unsigned grid = (unsigned)(cl == 4 ? p->grid4 : p->num_sms / cl * cl);
+    {
+        const int pair = cl >= 2 ? 2 : 1, npairs = cl / pair, bn = qo ? 128 : p->BN;
+        const long long groups = (p->max_rows + 128LL * pair - 1) / (128LL * pair);
+        const long long items = gen ? groups : groups * std::max(1, N / bn / npairs);
+        if (items * cl < (long long)grid) grid = (unsigned)(std::max(items, 1LL) * cl);
+    }
+    cfg.gridDim = dim3(grid);
     cfg.blockDim = dim3(TC_THREADS);
     cfg.stream = s;
     cudaLaunchAttribute attr[1];

@@ -73,3 +73,10 @@ def test_product_does_not_import_oracle():
                 src = open(os.path.join(dirpath, f)).read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), os.path.join(dirpath, f)
                 assert "/root/reference" not in src, os.path.join(dirpath, f)
+
+
+def test_integration_doc_lists_every_entry_point():
+    """INTEGRATION.md section C maps each C-ABI entry point to the reference interface it stands behind."""
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    missing = [n for n in _declared() if n not in doc]
+    assert not missing, missing

@@ -1,3 +1,5 @@
+"""GPU probe: per-stage device time of small-batch iterations (tutorial KAT shape: cube3, graph.100B_0.1W, zero heuristic);
+also the command the ncu list profiles/r1m_small_iteration_ncu.csv was taken from."""
 import sys, os, time
 import numpy as np
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))

@@ -51,7 +51,13 @@ class UpdateHeurVRLKeepGoal:
         a = self.domain.get_num_acts()
         b = max(pf.batch_size_default, 1)
         # log capacity: one record per popped node; the iteration after an instance finishes its last pops still take (dropped) slots
-        pf.enable_backups(max_backups=2 * n * b * self.search_itrs + n * b, max_instances=n * self.search_itrs)
+        need = 2 * n * b * self.search_itrs + n * b
+        if pf._engine is None:
+            pf.enable_backups(max_backups=need, max_instances=n * self.search_itrs)
+        else:                               # a later batch on the same engine (the reference builds a new PathFind per batch,
+            if pf._max_backups < need:      # base/updater.py:364; here the buffers, weights and captured graphs are kept)
+                raise ValueError(f"batch of {n} instances needs a backup log of {need} records, the engine has {pf._max_backups}")
+            pf.reset()
         removed: List[Any] = []
         groups: List[List[Any]] = []
         log: List[Tuple[np.ndarray, np.ndarray, np.ndarray]] = []

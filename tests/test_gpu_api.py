@@ -438,6 +438,12 @@ def test_updater_rl_bellman_targets_vs_oracle(is_q, label_mode):
     exp_goals = np.stack([orc.instances[k].goal for k in idx[order]])
     assert np.array_equal(dom.goals_to_rows(goals)[:, :exp_goals.shape[1]], exp_goals)
     assert len(ctgs) == sum(i.itr for i in orc.instances)                          # batch size 1: one popped node / edge per step
+    # a second batch on the same updater / engine (buffers, weights and graphs are reused)
+    made.clear()
+    data2 = up.get_instance_data(steps_gen[:8])
+    assert len(made[0]) == 8 and len(data2[-1]) >= 8 and len(pathfind.instances) <= 8
+    with pytest.raises(ValueError, match="backup log"):
+        up.get_instance_data(steps_gen * 4)
     pathfind.close()
 
 

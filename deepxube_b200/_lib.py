@@ -18,6 +18,7 @@ DX_ALGO_GRAPH_V, DX_ALGO_GRAPH_Q, DX_ALGO_BEAM_V, DX_ALGO_BEAM_Q = 0, 1, 2, 3
 DX_BACKUP_MODE = {"bellman": 0, "ub_solns": 1, "lhbl": 2}
 DX_ALGO = {"graph_v": DX_ALGO_GRAPH_V, "graph_q": DX_ALGO_GRAPH_Q, "beam_v": DX_ALGO_BEAM_V, "beam_q": DX_ALGO_BEAM_Q}
 DX_HEUR_ZERO, DX_HEUR_HOST, DX_HEUR_NET_FP32, DX_HEUR_NET_BF16 = 0, 1, 2, 3
+DX_HDA_LOCAL_DOUBLES = 8       # per-rank scalars of one HDA* iteration (include/dxb200.h)
 STAGE_NAMES = ["expand", "filt", "scatter", "heur", "sort", "pushpop", "book", "gemm_hidden", "gemm_input"]
 
 
@@ -68,6 +69,7 @@ SIGNATURES = {
     "dx_engine_reset": (C.c_int, [_engp]),
     "dx_load_weights": (C.c_int, [_engp, C.POINTER(dx_net_desc), _f32p, C.c_int64]),
     "dx_add_instances": (C.c_int, [_engp, _u8p, _u8p, C.c_int32, _i32p, _f64p, _f32p]),
+    "dx_remove_instances": (C.c_int, [_engp, _i32p, C.c_int32]),
     "dx_run": (C.c_int, [_engp, C.c_int32, _i32p]),
     "dx_step_begin": (C.c_int, [_engp, C.POINTER(C.c_int64)]),
     "dx_get_pending": (C.c_int, [_engp, _u8p, _u8p, C.c_int64]),
@@ -233,6 +235,12 @@ class Engine:
         w = None if weights is None else np.ascontiguousarray(np.broadcast_to(weights, (n,)), dtype=np.float64)
         r = None if root_vals is None else np.ascontiguousarray(root_vals, dtype=np.float32)
         check(self._lib.dx_add_instances(self._h, _p(states, _u8p), _p(goals, _u8p), n, _p(b, _i32p), _p(w, _f64p), _p(r, _f32p)))
+
+    def remove_instances(self, slots) -> None:
+        """The listed instance slots stop searching (PathFind.remove_instances); their nodes stay readable until reset()."""
+        sl = np.ascontiguousarray(slots, dtype=np.int32)
+        if sl.size:
+            check(self._lib.dx_remove_instances(self._h, _p(sl, _i32p), int(sl.size)))
 
     def run(self, max_iters: int) -> int:
         done = C.c_int32()

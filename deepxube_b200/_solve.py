@@ -96,6 +96,8 @@ def solve_cli(args: argparse.Namespace) -> None:
         pathfind = get_pathfind_from_arg(domain, pathfind_fns, args.pathfind)[0]
         if args.max_nodes is not None:
             pathfind._max_nodes = args.max_nodes
+        # the reference's "Times - heur: ..., expand: ..., filt: ..., cost: ..., pushpop: ..." line, from device stage timers
+        pathfind.stage_times_on = os.environ.get("DXB200_STAGE_TIMES", "1") == "1"
         start_time = time.time()
         num_itrs = 0
         instance = pathfind.make_instances([state], [goal], None, True)[0]

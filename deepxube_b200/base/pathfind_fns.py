@@ -71,6 +71,7 @@ class _DeviceHeur:
         self.precision = precision or default_precision()
         self.nnet_batch_size = nnet_batch_size
         self._eng = None
+        self._eng_version = -1
 
     def _engine(self):
         if self._eng is None:
@@ -81,7 +82,10 @@ class _DeviceHeur:
             eng = _lib.Engine(self.domain.dx_name, self.domain.dx_dim, "graph_q" if is_q else "graph_v", mode,
                               max_instances=1, max_pop_total=max(1, 16384 // (1 if self.nnet.q_fix else a)), max_nodes=1024)
             load_nnet_into_engine(eng, self.nnet)
-            self._eng = eng
+            self._eng, self._eng_version = eng, getattr(self.nnet, "version", 0)
+        elif getattr(self.nnet, "version", 0) != self._eng_version:      # nnet.load_state_dict since the upload
+            load_nnet_into_engine(self._eng, self.nnet)
+            self._eng_version = getattr(self.nnet, "version", 0)
         return self._eng
 
     def _eval(self, states: List[Any], goals: List[Any]) -> np.ndarray:

@@ -4,6 +4,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string>
+#include <string.h>
 
 #include "dxb200.h"
 
@@ -20,6 +21,9 @@
 #define DX_DEVERR_POP 4u
 #define DX_DEVERR_HDA 8u      // HDA*: an exchange segment / the receive capacity overflowed
 #define DX_DEVERR_BACKUPS 16u // the Bellman-backup log is full (dx_config.max_backups); drain it more often
+#define DX_DEVERR_PEER 32u    // HDA*: another rank of the distributed search reported a device error
+#define DX_DEVERR_NUMERIC 64u // split-fp16 network: an activation left the fp16 range (|x| > 65504)
+#define DX_HDA_LOCALS 8       // doubles per rank in the all-gathered per-iteration scalars (k_hda_locals)
 
 void dx_set_error(const std::string& msg);
 
@@ -156,6 +160,26 @@ struct NetDev {
 };
 
 static inline int dx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
+
+// OPEN keys: order-preserving map of a float64 f onto unsigned 64-bit integers (negative values: all bits flipped,
+// others: sign bit flipped), so that unsigned key order == numeric order for ANY f a host heuristic may return --
+// the reference's heap (graph_search.py:48-51) orders negative costs correctly too.  NaN sorts after +inf.
+__host__ __device__ __forceinline__ unsigned long long dx_f_to_key(double f) {
+#ifdef __CUDA_ARCH__
+    const unsigned long long b = (unsigned long long)__double_as_longlong(f);
+#else
+    unsigned long long b; memcpy(&b, &f, 8);
+#endif
+    return b ^ ((b >> 63) ? 0xFFFFFFFFFFFFFFFFull : 0x8000000000000000ull);
+}
+__host__ __device__ __forceinline__ double dx_key_to_f(unsigned long long k) {
+    const unsigned long long b = k ^ ((k >> 63) ? 0x8000000000000000ull : 0xFFFFFFFFFFFFFFFFull);
+#ifdef __CUDA_ARCH__
+    return __longlong_as_double((long long)b);
+#else
+    double f; memcpy(&f, &b, 8); return f;
+#endif
+}
 
 // ---------------------------------------------------------------------------------------------
 // 64-bit hash of a row (state bytes + padding + instance id), 16 bytes at a time.
@@ -313,7 +337,7 @@ int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortB
                        uint32_t seg_records, uint32_t* aux, int max_children);
 int dx_launch_hda_recv(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* recv, uint32_t world, uint32_t seg_records,
                        uint32_t max_children, uint32_t* src_off, uint8_t* child_state, float* child_g, uint32_t* child_parent,
-                       uint8_t* child_action);
+                       uint8_t* child_action, uint32_t* aux);
 int dx_launch_hda_locals(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const uint32_t* aux, double* loc);
 int dx_launch_hda_reduce(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
                          int A, int world, const double* all, double* summary);

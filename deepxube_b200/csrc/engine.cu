@@ -145,6 +145,16 @@ __global__ void k_set_host_vals(const Ctl* ctl, const float* vals, float* node_h
 }
 
 __global__ void k_set_job(Ctl* ctl, uint32_t start, uint32_t n) { ctl->nn_row_start = start; ctl->nn_n = n; }
+// PathFind.remove_instances (base/pathfinding.py:300-310): the instance stops searching -- no more pops, expansions or
+// OPEN entries (k_plan drops the run of an inactive instance) -- and no longer counts as unfinished
+__global__ void k_deactivate(Ctl* ctl, InstArrays ia, const int32_t* slots, int n) {
+    uint32_t dropped = 0;
+    for (int j = 0; j < n; ++j) {
+        const int i = slots[j];
+        if (ia.active[i]) { ia.active[i] = 0; ++dropped; }
+    }
+    ctl->n_unfinished -= min(dropped, ctl->n_unfinished);
+}
 __global__ void k_reset_backups(Ctl* ctl) { ctl->n_backups = 0; }
 __global__ void k_set_job_children(Ctl* ctl) { ctl->nn_row_start = 0; ctl->nn_n = ctl->error ? 0 : ctl->n_children; }
 
@@ -347,6 +357,8 @@ static int sync_ctl(dx_engine* e) {
         if (e->h_ctl->error & DX_DEVERR_POP) m += " max_pop_total";
         if (e->h_ctl->error & DX_DEVERR_HDA) m += " HDA* exchange segment / receive capacity";
         if (e->h_ctl->error & DX_DEVERR_BACKUPS) m += " max_backups (drain the backup log with dx_drain_backups)";
+        if (e->h_ctl->error & DX_DEVERR_PEER) m += " (reported by another rank of the HDA* search)";
+        if (e->h_ctl->error & DX_DEVERR_NUMERIC) m += " network activation outside the fp16 range of the split tensor-core path (DXB200_FP32_TC=0 selects the CUDA-core fp32 network)";
         DX_FAIL(DX_ERR_CAPACITY, m);
     }
     return DX_OK;
@@ -378,6 +390,13 @@ static void drop_graphs(dx_engine* e) {
 
 static int ensure_stage(dx_engine* e, size_t bytes) {
     if (bytes <= e->stage_bytes) return DX_OK;
+    if (e->d_stage) {                        // grow: nothing in flight may still use the old buffer
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+        e->allocs.erase(std::remove(e->allocs.begin(), e->allocs.end(), (void*)e->d_stage), e->allocs.end());
+        cudaFree(e->d_stage);
+        e->d_stage = nullptr;
+        e->stage_bytes = 0;
+    }
     void* q = nullptr;
     DX_CUDA(cudaMalloc(&q, bytes));
     e->allocs.push_back(q);
@@ -560,6 +579,35 @@ static int launch_heur_step(dx_engine* e, long long max_rows) {
     return launch_heur_nodes(e, max_rows);
 }
 
+// One-hot inputs must be < depth: the reference's F.one_hot raises on a larger value (pytorch_models.py:15-24); the device
+// kernels would otherwise have to clamp silently.  Checked on the host for every row that enters through the C ABI.
+static int check_rows_in_range(const dx_engine* e, const uint8_t* states, int64_t n) {
+    if (!e->weights_loaded || e->net.depth < 2 || !states) return DX_OK;
+    const int S = e->S, lim = std::min(e->net.in_count, S), depth = e->net.depth;
+    for (int64_t r = 0; r < n; ++r)
+        for (int i = 0; i < lim; ++i)
+            if (states[(size_t)r * S + i] >= depth)
+                DX_FAIL(DX_ERR_ARG, "state " + std::to_string(r) + " has value " + std::to_string((int)states[(size_t)r * S + i]) +
+                                        " at input " + std::to_string(i) + ": outside the network's one-hot depth " + std::to_string(depth));
+    return DX_OK;
+}
+
+extern "C" int dx_remove_instances(dx_engine* e, const int32_t* slots, int32_t n) {
+    if (!e || (n > 0 && !slots)) DX_FAIL(DX_ERR_ARG, "null argument");
+    if (n <= 0) return DX_OK;
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "dx_remove_instances between dx_step_begin and dx_step_end");
+    if (e->hda_world >= 1) DX_FAIL(DX_ERR_UNSUPPORTED, "HDA* mode holds one instance: use dx_engine_reset");
+    for (int j = 0; j < n; ++j)
+        if (slots[j] < 0 || slots[j] >= e->n_inst) DX_FAIL(DX_ERR_ARG, "instance slot out of range");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(ensure_stage(e, (size_t)n * sizeof(int32_t) + 64));
+    DX_CUDA(cudaMemcpyAsync(e->d_stage, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
+    k_deactivate<<<1, 1, 0, e->stream>>>(e->d_ctl, e->ia, (const int32_t*)e->d_stage, n);
+    e->launches += 1;
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    return DX_OK;
+}
+
 extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
                                 const int32_t* batch_sizes, const double* weights, const float* root_vals) {
     if (!e || (n > 0 && (!states || !goals))) DX_FAIL(DX_ERR_ARG, "null argument");
@@ -567,7 +615,10 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
     if (e->pending) DX_FAIL(DX_ERR_STATE, "dx_add_instances between dx_step_begin and dx_step_end");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_TRY(need_net(e));
-    if (e->n_inst + n > e->max_inst) DX_FAIL(DX_ERR_CAPACITY, "max_instances exceeded");
+    if (e->n_inst + n > e->max_inst)
+        DX_FAIL(DX_ERR_CAPACITY, "max_instances exceeded: instance slots are numbered for the engine's life (finished / removed instances keep "
+                                 "theirs until dx_engine_reset); size max_instances for every instance added between two resets");
+    DX_TRY(check_rows_in_range(e, states, n));
     if (e->cfg.heur_mode == DX_HEUR_HOST && e->is_q && !root_vals) DX_FAIL(DX_ERR_ARG, "graph_q in HOST mode needs root_vals");
     DX_TRY(sync_ctl(e));
     const Ctl c = *e->h_ctl;
@@ -579,11 +630,15 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
         if (b < 1) DX_FAIL(DX_ERR_ARG, "batch size must be >= 1");
         bsum += b;
     }
-    {   // total batch of live instances must fit max_pop_total
+    {   // total batch of LIVE instances (not finished, not removed) must fit max_pop_total
         std::vector<int32_t> hb(e->n_inst);
-        if (e->n_inst) DX_CUDA(cudaMemcpy(hb.data(), e->ia.batch, e->n_inst * sizeof(int32_t), cudaMemcpyDeviceToHost));
-        for (int b : hb) bsum += b;
-        if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of batch sizes exceeds max_pop_total");
+        std::vector<uint8_t> ha(e->n_inst);
+        if (e->n_inst) {
+            DX_CUDA(cudaMemcpy(hb.data(), e->ia.batch, e->n_inst * sizeof(int32_t), cudaMemcpyDeviceToHost));
+            DX_CUDA(cudaMemcpy(ha.data(), e->ia.active, e->n_inst, cudaMemcpyDeviceToHost));
+        }
+        for (int i = 0; i < e->n_inst; ++i) if (ha[i]) bsum += hb[i];
+        if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of the live instances' batch sizes exceeds max_pop_total");
     }
     e->sort_bound = bsum * e->A;             // no iteration can push more entries than every instance's full batch expanded
     const int SP = e->SP, S = e->S, I0 = e->n_inst, p = e->parity;
@@ -1294,6 +1349,7 @@ extern "C" int dx_vi_targets(dx_engine* e, const uint8_t* states, const uint8_t*
     if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
     if (e->is_beam) DX_FAIL(DX_ERR_UNSUPPORTED, "dx_vi_targets: graph_v / graph_q engines");
+    DX_TRY(check_rows_in_range(e, states, n));
     DX_CUDA(cudaSetDevice(e->cfg.device));
     if (n == 0) return DX_OK;
     const int amul = e->net.act_depth > 0 ? e->net.act_depth : 1;       // action-as-input Q network: one row per (state, action)
@@ -1364,6 +1420,7 @@ extern "C" int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* 
     if (!e || n < 0 || (n > 0 && (!states || !out))) DX_FAIL(DX_ERR_ARG, "bad argument");
     if (!e->weights_loaded) DX_FAIL(DX_ERR_STATE, "no weights loaded");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    DX_TRY(check_rows_in_range(e, states, n));
     DX_CUDA(cudaSetDevice(e->cfg.device));
     if (n == 0) return DX_OK;
     const int amul = e->net.act_depth > 0 ? e->net.act_depth : 1;
@@ -1487,7 +1544,10 @@ __global__ void k_f32_to_bf16(const float* __restrict__ src, uint16_t* __restric
 }
 
 int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats) {
-    if (e->weights_loaded) DX_FAIL(DX_ERR_STATE, "weights already loaded for this engine");
+    // A second load (the heuristic / target network changed between two batches of an RL loop, updaters/updater_rl.py)
+    // overwrites the parameters IN PLACE: same shape required, the captured step graphs keep pointing at the same buffers.
+    const bool reload = e->weights_loaded;
+    DX_CUDA(cudaStreamSynchronize(e->stream));
     const int H = desc->res_dim, nb = desc->num_blocks, od = desc->out_dim, bn = desc->batch_norm;
     const int act_depth = desc->act_depth;
     if (act_depth < 0 || (act_depth > 0 && (od != 1 || !e->is_q || act_depth != e->A)))
@@ -1500,6 +1560,9 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     const int Hp = ((H + 127) / 128) * 128;
     const int in_dim_p = ((in_dim + 63) / 64) * 64;
     NetDev& net = e->net;
+    if (reload && (net.in_count != desc->in_count || net.depth != desc->one_hot_depth || net.H != H || net.num_blocks != nb ||
+                   net.out_dim != od || net.act_depth != act_depth))
+        DX_FAIL(DX_ERR_ARG, "dx_load_weights: a reload must have the shape of the network loaded first");
     net.in_count = desc->in_count; net.depth = desc->one_hot_depth; net.H = H; net.Hp = Hp; net.num_blocks = nb;
     net.out_dim = od; net.in_dim = in_dim; net.in_dim_p = in_dim_p; net.act_depth = act_depth;
     std::vector<float> w0t((size_t)in_dim * Hp, 0.f), b0(Hp, 0.f), w0p((size_t)Hp * in_dim_p, 0.f);
@@ -1532,16 +1595,13 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     p += (size_t)od * H;
     for (int o = 0; o < od; ++o) bout[o] = p[o];
 
-#define UP_(dst, vec) do { DX_TRY(e->alloc(&(dst), (vec).size())); \
+#define UP_(dst, vec) do { if (!(dst)) DX_TRY(e->alloc(&(dst), (vec).size())); \
         DX_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(float), cudaMemcpyHostToDevice)); } while (0)
     UP_(net.w0t, w0t); UP_(net.b0, b0); UP_(net.wres, wres); UP_(net.bres, bres); UP_(net.wout, wout); UP_(net.bout, bout);
 #undef UP_
     // bf16 copies for the tensor-core path (first layer K-major [Hp, in_dim_p]; residual layers [l, Hp, Hp]).
     // Bias folding (NetDev::tc_fold): spare padding columns carry the bias through the GEMM itself.
     net.tc_fold = 0;
-    net.b0_tc = nullptr;
-    net.wout_bf16 = nullptr;
-    net.bout_pad = nullptr;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
         auto bf16r = [](float x) {                 // round to nearest even, as k_f32_to_bf16
             uint32_t u; memcpy(&u, &x, 4);
@@ -1573,13 +1633,13 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             } else {
                 std::vector<float> b0tc(b0);
                 for (int j = 0; j < 3; ++j) b0tc[H + j] = 1.f;
-                DX_TRY(e->alloc(&net.b0_tc, b0tc.size()));
+                if (!net.b0_tc) DX_TRY(e->alloc(&net.b0_tc, b0tc.size()));
                 DX_CUDA(cudaMemcpy(net.b0_tc, b0tc.data(), b0tc.size() * sizeof(float), cudaMemcpyHostToDevice));
             }
         }
-        uint16_t *w0b = nullptr, *wrb = nullptr;
-        DX_TRY(e->alloc(&w0b, w0p.size()));
-        DX_TRY(e->alloc(&wrb, wres_tc.size()));
+        uint16_t *w0b = (uint16_t*)net.w0_bf16, *wrb = (uint16_t*)net.wres_bf16;
+        if (!w0b) DX_TRY(e->alloc(&w0b, w0p.size()));
+        if (!wrb) DX_TRY(e->alloc(&wrb, wres_tc.size()));
         float* tmp = nullptr;
         const size_t tmp_n = std::max(std::max(w0p.size(), (size_t)128 * Hp), std::max<size_t>(wres_tc.size(), 1));
         DX_CUDA(cudaMalloc(&tmp, tmp_n * sizeof(float)));
@@ -1593,8 +1653,6 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, wrb, wres_tc.size());
         }
         cudaError_t ce = cudaStreamSynchronize(e->stream);
-        net.wout_bf16 = nullptr;
-        net.bout_pad = nullptr;
         if (ce == cudaSuccess && od > 1 && od <= 32 && tmp_n >= (size_t)128 * Hp) {
             // multi-output layer on the tensor cores: weight rows zero-padded to one 128-wide n-tile
             std::vector<float> wpad((size_t)128 * Hp, 0.f), bpad(128, 0.f);
@@ -1602,9 +1660,9 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
                 memcpy(&wpad[(size_t)o * Hp], &wout[(size_t)o * Hp], (size_t)Hp * sizeof(float));
                 bpad[o] = bout[o];
             }
-            uint16_t* wob = nullptr;
-            DX_TRY(e->alloc(&wob, wpad.size()));
-            DX_TRY(e->alloc(&net.bout_pad, bpad.size()));
+            uint16_t* wob = (uint16_t*)net.wout_bf16;
+            if (!wob) DX_TRY(e->alloc(&wob, wpad.size()));
+            if (!net.bout_pad) DX_TRY(e->alloc(&net.bout_pad, bpad.size()));
             cudaMemcpyAsync(net.bout_pad, bpad.data(), bpad.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
             cudaMemcpyAsync(tmp, wpad.data(), wpad.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
             k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, wob, wpad.size());
@@ -1615,6 +1673,10 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
         DX_CUDA(ce);
         net.w0_bf16 = w0b;
         net.wres_bf16 = wrb;
+    }
+    if (reload) {
+        DX_CUDA(cudaDeviceSynchronize());
+        return DX_OK;                         // activation buffers, tensor maps and captured graphs stay
     }
     // activation buffers
     // rows one evaluation can hold: popped nodes (Q*) or children (A*); x actions for an action-as-input network
@@ -1766,7 +1828,7 @@ extern "C" int dx_hda_absorb(dx_engine* e, const void* recv_dev, int64_t n_recor
     struct Local { int64_t k_popped; double f_first; double ub; int64_t goal_local; int64_t n_kept; int64_t open_size; int64_t children_sent; };
     Local* o = reinterpret_cast<Local*>(out);
     o->k_popped = k;
-    memcpy(&o->f_first, &ff, 8);
+    o->f_first = dx_key_to_f(ff);
     if (k == 0) o->f_first = INFINITY;
     if (ubk == DX_EMPTY64) o->ub = INFINITY;
     else { uint32_t b = (uint32_t)(ubk >> 32); float f; memcpy(&f, &b, 4); o->ub = (double)f; }
@@ -1855,7 +1917,7 @@ extern "C" int dx_hda_receive(dx_engine* e, const void* recv_dev, int64_t seg_re
     const int p = e->parity, q = p ^ 1;
     e->launches += dx_launch_hda_recv(s, e->dom, e->d_ctl, (const uint8_t*)recv_dev, (uint32_t)e->hda_world, (uint32_t)seg_records,
                                       (uint32_t)e->max_children, e->hda_src_off, e->child_state, e->child_g, e->child_parent,
-                                      e->child_action);
+                                      e->child_action, e->hda_aux);
     e->launches += dx_launch_closed_filter(s, e->dom, e->closed, e->d_ctl, e->ia, e->node_state, e->node_g, e->child_state,
                                            e->child_g, nullptr, e->popped_inst[p], e->child_slot, e->child_next, e->child_flags,
                                            e->max_children, e->A);

@@ -145,7 +145,14 @@ __global__ void k_hda_pack_seg(DomainDev d, Ctl* __restrict__ ctl, SortBufs sb, 
                                const uint32_t* __restrict__ counts, HdaDst dst, uint32_t seg_records,
                                uint32_t* __restrict__ aux) {
     __shared__ uint32_t s_pref[17];
-    if (ctl->error) return;
+    if (ctl->error) {
+        // A rank in the error state still publishes EMPTY segments: without fresh headers its peers would re-read the
+        // counts and records this rank wrote in the previous iteration.  The error itself travels in the per-rank
+        // scalars (k_hda_locals -> k_hda_reduce), so every rank raises in the same iteration.
+        if (blockIdx.x == 0 && threadIdx.x < world) *reinterpret_cast<uint4*>(dst.seg[threadIdx.x]) = make_uint4(0u, 0u, 0u, 0u);
+        if (blockIdx.x == 0 && threadIdx.x == 0) aux[0] = 0u;
+        return;
+    }
     const uint32_t n = ctl->n_children;
     const int words = d.SP / 4, rw = words + 4;
     if (threadIdx.x == 0) {
@@ -181,7 +188,7 @@ __global__ void k_hda_pack_seg(DomainDev d, Ctl* __restrict__ ctl, SortBufs sb, 
 
 // segment headers of the received buffer -> per-source offsets, ctl->n_children = records received
 __global__ void k_hda_recv_plan(Ctl* __restrict__ ctl, const uint8_t* __restrict__ recv, uint32_t world, size_t seg_bytes,
-                                uint32_t max_children, uint32_t* __restrict__ src_off) {
+                                uint32_t max_children, uint32_t* __restrict__ src_off, uint32_t* __restrict__ aux) {
     if (ctl->error) return;
     uint32_t acc = 0;
     for (uint32_t s = 0; s < world; ++s) {
@@ -191,6 +198,7 @@ __global__ void k_hda_recv_plan(Ctl* __restrict__ ctl, const uint8_t* __restrict
     if (acc > max_children) { atomicOr(&ctl->error, DX_DEVERR_HDA); acc = 0; }
     src_off[world] = acc;
     ctl->n_children = acc;
+    aux[1] = acc;
 }
 
 __global__ void k_hda_unpack_seg(DomainDev d, const Ctl* __restrict__ ctl, const uint8_t* __restrict__ recv, uint32_t world,
@@ -215,33 +223,43 @@ __global__ void k_hda_unpack_seg(DomainDev d, const Ctl* __restrict__ ctl, const
     }
 }
 
-// this rank's per-iteration scalars, as doubles: {k_popped, f of the first popped, ub, goal node (local id or -1), children generated}
+// this rank's per-iteration scalars, as DX_HDA_LOCALS doubles: {k_popped, f of the first popped, ub, goal node (local id or -1),
+// children generated, device error flags, children received, received children that passed the CLOSED filter}
 __global__ void k_hda_locals(const Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ aux, double* __restrict__ loc) {
     const uint32_t k = ctl->error ? 0u : ia.k_pop[0];
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
     loc[0] = (double)k;
-    loc[1] = k ? __longlong_as_double((long long)ia.f_first[0]) : inf;
+    loc[1] = k ? dx_key_to_f(ia.f_first[0]) : inf;
     const unsigned long long ubk = ia.ub_key[0];
     loc[2] = ubk == DX_EMPTY64 ? inf : (double)__uint_as_float((uint32_t)(ubk >> 32));
     const uint32_t goal = ia.goal_node[0];
     loc[3] = goal == DX_NIL ? -1.0 : (double)goal;
     loc[4] = ctl->error ? 0.0 : (double)aux[0];
+    loc[5] = (double)ctl->error;
+    loc[6] = ctl->error ? 0.0 : (double)aux[1];
+    loc[7] = ctl->error ? 0.0 : (double)ctl->n_kept;
 }
 
 // every rank, from the all-gathered scalars: the bookkeeping of k_hda_finish plus a summary for the host:
-// {finished, iterations, nodes generated, ub, goal rank, goal local id, device error flags, 0}
+// {finished, iterations, nodes generated, ub, goal rank, goal local id, device error flags OR-ed over ALL ranks,
+//  max over ranks of the children received this iteration (load imbalance of hash mod W)}
+// A device error on any rank freezes every rank in the same iteration (DX_DEVERR_PEER marks "a peer failed").
 __global__ void k_hda_reduce(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ pop_off_cur,
                              const uint32_t* __restrict__ pop_off_next, int A, int world, const double* __restrict__ all,
                              double* __restrict__ summary) {
     const double inf = __longlong_as_double(0x7ff0000000000000ll);
-    double k_total = 0.0, f_min = inf, children = 0.0, ub = inf, g_rank = -1.0, g_id = -1.0;
+    double k_total = 0.0, f_min = inf, children = 0.0, ub = inf, g_rank = -1.0, g_id = -1.0, recv_max = 0.0;
+    uint32_t err_all = 0u;
     for (int r = 0; r < world; ++r) {
-        const double* l = all + 5 * r;
+        const double* l = all + DX_HDA_LOCALS * r;
+        err_all |= (uint32_t)l[5];
+        recv_max = fmax(recv_max, l[6]);
         k_total += l[0];
         f_min = fmin(f_min, l[1]);
         children += l[4];
         if (l[3] >= 0.0 && l[2] < ub) { ub = l[2]; g_rank = (double)r; g_id = l[3]; }     // first rank wins ties, as min over (ub, rank)
     }
+    if (err_all && !ctl->error) ctl->error = DX_DEVERR_PEER;      // a peer failed: stop here too (its segments are empty from now on)
     if (!ctl->error && ia.active[0]) {          // a finished search stays frozen
         double lb = ia.lb[0];
         if (k_total > 0.0) lb = fmax(f_min, lb);
@@ -272,8 +290,8 @@ __global__ void k_hda_reduce(Ctl* __restrict__ ctl, InstArrays ia, const uint32_
     summary[3] = ub;
     summary[4] = g_rank;
     summary[5] = g_id;
-    summary[6] = (double)ctl->error;
-    summary[7] = 0.0;
+    summary[6] = (double)(err_all | ctl->error);
+    summary[7] = recv_max;
 }
 
 // non-owner ranks hold the instance without a root in their popped list
@@ -335,9 +353,9 @@ int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortB
 
 int dx_launch_hda_recv(cudaStream_t s, const DomainDev& d, Ctl* ctl, const uint8_t* recv, uint32_t world, uint32_t seg_records,
                        uint32_t max_children, uint32_t* src_off, uint8_t* child_state, float* child_g, uint32_t* child_parent,
-                       uint8_t* child_action) {
+                       uint8_t* child_action, uint32_t* aux) {
     const size_t seg_bytes = 16 + (size_t)seg_records * (size_t)(d.SP + 16);
-    k_hda_recv_plan<<<1, 1, 0, s>>>(ctl, recv, world, seg_bytes, max_children, src_off);
+    k_hda_recv_plan<<<1, 1, 0, s>>>(ctl, recv, world, seg_bytes, max_children, src_off, aux);
     const int blocks = (int)min((long long)dx_div_up((long long)max_children * (d.SP / 4 + 4), 256), (long long)148 * 16);
     k_hda_unpack_seg<<<blocks, 256, 0, s>>>(d, ctl, recv, world, seg_bytes, src_off, child_state, child_g, child_parent, child_action);
     return 2;

@@ -6,8 +6,8 @@
 // f = float64(w) * float64(g) + float64(h), two separately rounded float64 operations
 // (graph_search.py:153, :175).
 //
-// Device formulation: per instance, OPEN is one run sorted by (f-key, item), where f-key is the bit
-// pattern of the float64 f (f >= 0, so unsigned order == numeric order) and items are numbered in push
+// Device formulation: per instance, OPEN is one run sorted by (f-key, item), where f-key is the order-preserving
+// unsigned image of the float64 f (dx_f_to_key: correct for negative f too) and items are numbered in push
 // order (A*: node id; Q*: node id * A + action), so the pair order IS the heap's (f, push_count) order.
 // One iteration =
 //   k_plan        per-instance sizes and offsets of this iteration (pushed m, popped k, new |OPEN|),
@@ -94,7 +94,7 @@ int dx_launch_plan(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_
 __device__ __forceinline__ unsigned long long f_key(double w, float g, float h) {
     // float64(w) * float64(g) + float64(h), each rounded once (no FMA) -- graph_search.py:153
     const double f = __dadd_rn(__dmul_rn(w, (double)g), (double)h);
-    return (unsigned long long)__double_as_longlong(f);
+    return dx_f_to_key(f);
 }
 
 // A*: batch element k is new node (node_base + k).
@@ -106,7 +106,7 @@ __global__ void k_make_keys_v(const Ctl* __restrict__ ctl, InstArrays ia, const 
     const uint32_t n = ctl->sort_n, base = ctl->node_base;
     for (uint32_t k = blockIdx.x * blockDim.x + threadIdx.x; k < n; k += gridDim.x * blockDim.x) {
         const uint32_t id = base + k, inst = new_inst[k];
-        sb.key[0][k] = beam ? (unsigned long long)__double_as_longlong(__dadd_rn(1.0, (double)node_h[id]))
+        sb.key[0][k] = beam ? dx_f_to_key(__dadd_rn(1.0, (double)node_h[id]))
                             : f_key(ia.weight[inst], node_g[id], node_h[id]);
         sb.inst[0][k] = inst;
         sb.val[0][k] = id;
@@ -127,7 +127,7 @@ __global__ void k_make_keys_q(const Ctl* __restrict__ ctl, InstArrays ia, const 
         const uint32_t node = popped[j], inst = popped_inst[j];
         const uint32_t k = prefix[j] * A + a;
         // beam_q ranks an edge by its q-value alone (logits = -q_val, beam_search.py:206-212)
-        sb.key[0][k] = beam ? (unsigned long long)__double_as_longlong((double)node_q[(size_t)node * A + a])
+        sb.key[0][k] = beam ? dx_f_to_key((double)node_q[(size_t)node * A + a])
                             : f_key(ia.weight[inst], node_g[node], node_q[(size_t)node * A + a]);
         sb.inst[0][k] = inst;
         sb.val[0][k] = node * A + a;
@@ -631,7 +631,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         const unsigned long long ff = ia.f_first[i], gen_old = ia.gen[i], ubk = ia.ub_key[i];
         const uint32_t seq_old = ia.pop_seq_base[i], itr = ia.itr[i] + 1;
         const double w = ia.weight[i];
-        if (k > 0) lb = fmax(__longlong_as_double((long long)ff), lb);              // graph_search.py:67-69
+        if (k > 0) lb = fmax(dx_key_to_f(ff), lb);                                  // graph_search.py:67-69
         const bool edge_mode = gen_mode == 1 || gen_mode == 3;
         const unsigned long long g_add = !edge_mode ? (unsigned long long)n_pop * A : (unsigned long long)k;
         gen += g_add;

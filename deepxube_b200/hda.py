@@ -70,6 +70,13 @@ class HdaSearch:
         self.num_nodes_generated = 0
         self.goal = None          # (ub, rank, local id)
         self.finished = False
+        # per-iteration phase timing (CUDA events on the iteration's stream) and load statistics, for bench.py's `hda` block
+        self.timing = False
+        self.phase_ms = {"pack": 0.0, "exchange": 0.0, "receive": 0.0, "all_gather": 0.0, "reduce": 0.0}
+        self.recv_max_sum = 0.0       # sum over iterations of max over ranks of the children received
+        self.recv_mean_sum = 0.0      # ... of the mean over ranks (= children generated / W)
+        self.timed_iters = 0
+        self._ev = None
         if device_resident:
             # expected records per destination = batch_local * actions / world; the slack covers the hash imbalance
             self.seg_records = int(np.ceil(self.batch_local * self.num_actions / world * max(capacity_slack, 1.0) * 1.25)) + 64
@@ -78,8 +85,9 @@ class HdaSearch:
             with torch.cuda.stream(self.stream):
                 self.send = [torch.zeros(world * self.seg_bytes, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
                 self.recv = [torch.zeros(world * self.seg_bytes, dtype=torch.uint8, device=self.tdev) for _ in self.local_ranks]
-                self.loc = [torch.zeros(5, dtype=torch.float64, device=self.tdev) for _ in self.local_ranks]
-                self.loc_all = torch.zeros(world * 5, dtype=torch.float64, device=self.tdev)
+                nl = _lib.DX_HDA_LOCAL_DOUBLES
+                self.loc = [torch.zeros(nl, dtype=torch.float64, device=self.tdev) for _ in self.local_ranks]
+                self.loc_all = torch.zeros(world * nl, dtype=torch.float64, device=self.tdev)
                 self.summary = [torch.zeros(8, dtype=torch.float64, device=self.tdev) for _ in self.local_ranks]
             self.stream.synchronize()
             for eng in self.engines:
@@ -140,9 +148,9 @@ class HdaSearch:
         torch.cuda.synchronize(self.tdev)
         return [n]
 
-    def _gather_locals(self, locs: List[Any]) -> List[Any]:
-        """Per-rank scalars of every rank, in rank order: rows of (k, f_first, ub, goal_local, children_sent)."""
-        rows = [[float(l.k_popped), l.f_first, l.ub, float(l.goal_local), float(l.children_sent)] for l in locs]
+    def _gather_locals(self, locs: List[Any], failed: bool = False) -> List[Any]:
+        """Per-rank scalars of every rank, in rank order: rows of (k, f_first, ub, goal_local, children_sent, error flag)."""
+        rows = [[float(l.k_popped), l.f_first, l.ub, float(l.goal_local), float(l.children_sent), 1.0 if failed else 0.0] for l in locs]
         if self.dist is None:
             return rows
         t = torch.tensor(rows[0], dtype=torch.float64, device=self.tdev)
@@ -160,32 +168,59 @@ class HdaSearch:
     def _step_device(self) -> bool:
         """One iteration with every launch and collective on self.stream; the only host read is the summary."""
         W, seg = self.world, self.seg_bytes
+        tm = self.timing
+        if tm and self._ev is None:
+            self._ev = [torch.cuda.Event(enable_timing=True) for _ in range(6)]
+        ev = self._ev
+        gen_before = self.num_nodes_generated
         with torch.cuda.stream(self.stream):
+            if tm:
+                ev[0].record(self.stream)
             if self.exchange == "p2p":
                 for i, eng in enumerate(self.engines):
                     eng.hda_send_peers(self.peer_ptrs[i], self.seg_records)               # pack + store into the owners' buffers
+                if tm:
+                    ev[1].record(self.stream)
                 if self.symm is not None:
                     self.symm.barrier(channel=0)                                          # every rank's segments have landed
             else:
                 for i, eng in enumerate(self.engines):
                     eng.hda_send(self.send[i].data_ptr(), self.seg_records)
+                if tm:
+                    ev[1].record(self.stream)
                 if self.dist is not None:
                     self.dist.all_to_all_single(self.recv[0], self.send[0])             # equal splits of seg_bytes
                 else:
                     for di in range(W):
                         for si in range(W):
                             self.recv[di][si * seg:(si + 1) * seg].copy_(self.send[si][di * seg:(di + 1) * seg], non_blocking=True)
+            if tm:
+                ev[2].record(self.stream)
             for i, eng in enumerate(self.engines):
                 eng.hda_receive(self.recv[i].data_ptr(), self.seg_records, self.loc[i].data_ptr())
+            if tm:
+                ev[3].record(self.stream)
             if self.dist is not None:
                 self.dist.all_gather_into_tensor(self.loc_all, self.loc[0])
             else:
                 torch.cat(self.loc, out=self.loc_all)
+            if tm:
+                ev[4].record(self.stream)
             for i, eng in enumerate(self.engines):
                 eng.hda_reduce(self.loc_all.data_ptr(), self.summary[i].data_ptr())
+            if tm:
+                ev[5].record(self.stream)
             sm = self.summary[0].cpu().tolist()                                          # the iteration's one synchronisation
         if sm[6] != 0:
-            raise _lib.DxError(f"HDA*: device capacity exceeded (flags {int(sm[6])}): raise capacity_slack / max_nodes_per_rank")
+            # the flags are OR-ed over ALL ranks by dx_hda_reduce, so every rank raises here in the same iteration
+            # (no rank is left waiting in a barrier / collective for a peer that has gone)
+            raise _lib.DxError(f"HDA*: device capacity exceeded on some rank (flags {int(sm[6])}): raise capacity_slack / max_nodes_per_rank")
+        if tm:
+            for k, name in enumerate(("pack", "exchange", "receive", "all_gather", "reduce")):
+                self.phase_ms[name] += ev[k].elapsed_time(ev[k + 1])
+            self.recv_max_sum += sm[7]
+            self.recv_mean_sum += (int(sm[2]) - gen_before) / W
+            self.timed_iters += 1
         self.finished = sm[0] != 0
         self.itr = int(sm[1])
         self.num_nodes_generated = int(sm[2])
@@ -195,10 +230,33 @@ class HdaSearch:
     def step(self) -> bool:
         if self.device_resident:
             return self._step_device()
-        counts = [eng.hda_expand(self.send[i].data_ptr(), self.send[i].numel(), self.world) for i, eng in enumerate(self.engines)]
-        n_recv = self._exchange(counts)
-        locs = [eng.hda_absorb(self.recv[i].data_ptr(), n_recv[i]) for i, eng in enumerate(self.engines)]
-        rows = self._gather_locals(locs)
+        # host-driven arm: a DxError on one rank must not leave the others waiting in a collective -- the failing rank keeps
+        # taking part (empty sends) and the flag travels with the gathered scalars, so every rank raises together
+        err: Optional[Exception] = None
+        counts = []
+        for i, eng in enumerate(self.engines):
+            try:
+                counts.append(eng.hda_expand(self.send[i].data_ptr(), self.send[i].numel(), self.world))
+            except _lib.DxError as ex:
+                err = err or ex
+                counts.append(np.zeros(self.world, np.int64))
+        try:
+            n_recv = self._exchange(counts)
+        except _lib.DxError as ex:                     # receive buffer too small: detected after the collective completed
+            err = err or ex
+            n_recv = [0 for _ in self.engines]
+        locs = []
+        for i, eng in enumerate(self.engines):
+            try:
+                if err is not None:
+                    raise err
+                locs.append(eng.hda_absorb(self.recv[i].data_ptr(), n_recv[i]))
+            except _lib.DxError as ex:
+                err = err or ex
+                locs.append(_lib.dx_hda_local(0, float("inf"), float("inf"), -1, 0, 0, 0))
+        rows = self._gather_locals(locs, failed=err is not None)
+        if any(r[5] != 0 for r in rows):
+            raise _lib.DxError(f"HDA*: a rank failed ({err if err is not None else 'reported by a peer'})")
         k_total = int(sum(r[0] for r in rows))
         f_first_min = min(r[1] for r in rows)
         children = int(sum(r[4] for r in rows))

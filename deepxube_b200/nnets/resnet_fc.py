@@ -39,6 +39,7 @@ class ResnetFCHeur:
             self.act_depth = int(depths[1])
         self.in_dim = self.in_count * self.one_hot_depth + self.act_depth
         self._sd: Optional[Dict[str, np.ndarray]] = None
+        self.version = 0          # bumped whenever the parameters change: engines holding a copy re-upload (dx_load_weights)
 
     # ---- weights -------------------------------------------------------------------------------------
     def expected_shapes(self) -> Dict[str, tuple]:
@@ -69,6 +70,7 @@ class ResnetFCHeur:
             if tuple(clean[k].shape) != shp:
                 raise RuntimeError(f"size mismatch for {k}: got {tuple(clean[k].shape)}, expected {shp}")
         self._sd = clean
+        self.version += 1
 
     def init_random(self, seed: Optional[int] = None) -> None:
         """nn.Linear default init in the reference's module construction order (so `torch.manual_seed(s)`
@@ -95,6 +97,7 @@ class ResnetFCHeur:
                     sd[p + ".1.running_mean"], sd[p + ".1.running_var"] = np.zeros(h, np.float32), np.ones(h, np.float32)
         take("heur.2", nn.Linear(h, self.out_dim))
         self._sd = sd
+        self.version += 1
 
     def state_dict(self) -> Dict[str, np.ndarray]:
         if self._sd is None:

@@ -13,6 +13,7 @@ networks run inside the device iteration; any other callable is invoked on the h
 import os
 import re
 import time
+import weakref
 from typing import Any, Dict, List, Optional, Tuple, Type
 
 import numpy as np
@@ -98,6 +99,13 @@ class GraphSearch(PathFind):
         self._fn = pathfind_fns.heurq if self.is_q else pathfind_fns.heurv
         self._pending: List[InstanceGraph] = []
         self._max_backups = 0
+        # stage_times: split every step's device time over the reference's Times keys (expand / filt / heur / cost / pushpop,
+        # deepxube/base/pathfinding.py:426-744, graph_search.py:156) from CUDA events recorded inside the captured
+        # iteration (4-5 % overhead); off: the whole step is booked as "search"
+        self.stage_times_on = os.environ.get("DXB200_STAGE_TIMES", "0") == "1"
+        self._stage_last: Dict[str, float] = {}
+        self._weights_version = -1                     # version of the nnet whose parameters the engine holds
+        self._detached: "weakref.WeakSet[InstanceGraph]" = weakref.WeakSet()   # removed instances whose nodes still live in the engine
 
     @staticmethod
     def _check_eps(eps: float) -> None:
@@ -127,6 +135,18 @@ class GraphSearch(PathFind):
                                    max_backups=self._max_backups)
         if mode in (_lib.DX_HEUR_NET_FP32, _lib.DX_HEUR_NET_BF16):
             load_nnet_into_engine(self._engine, self._fn.nnet)
+            self._weights_version = getattr(self._fn.nnet, "version", 0)
+
+    def _sync_weights(self) -> None:
+        """Re-upload the parameters when the network changed since they were loaded (nnet.load_state_dict bumps
+        `version`): the reference builds every PathFind around the CURRENT function (updaters/updater_rl.py)."""
+        eng = self._engine
+        if eng is None or eng.heur_mode not in (_lib.DX_HEUR_NET_FP32, _lib.DX_HEUR_NET_BF16):
+            return
+        v = getattr(self._fn.nnet, "version", 0)
+        if v != self._weights_version:
+            load_nnet_into_engine(eng, self._fn.nnet)
+            self._weights_version = v
 
     def enable_backups(self, max_backups: int, max_instances: Optional[int] = None) -> None:
         """Extension (training-data generation, deepxube_b200/updaters/updater_rl.py): the engine evaluates every generated
@@ -168,6 +188,11 @@ class GraphSearch(PathFind):
         t0 = time.time()
         if self._engine is None:
             self._make_engine(instances)
+        elif not self.instances and self._engine.num_instances() > 0 and self._max_backups == 0:
+            # every earlier instance was removed: recycle the engine's instance slots, node store and CLOSED table
+            # (the reference's add / step / remove_finished_instances / add loop, base/updater.py:343-400)
+            self._recycle()
+        self._sync_weights()
         eng, dom = self._engine, self.domain
         states = [i.root_node.state for i in instances]
         goals = [i.root_node.goal for i in instances]
@@ -183,6 +208,27 @@ class GraphSearch(PathFind):
         self._refresh()
         self.times.record_time("heur", time.time() - t0)
 
+    def _recycle(self) -> None:
+        for inst in list(self._detached):              # instances the caller still holds: keep their solutions readable
+            if inst.goal_node is not None and inst.goal_node.parent is None and inst.goal_node.path_cost > 0:
+                inst._materialise_path(inst.goal_node)
+            inst._owner, inst._slot = None, -1
+        self._detached = weakref.WeakSet()
+        self._engine.reset()
+
+    def remove_instances(self, test_rem) -> List[Any]:
+        """PathFind.remove_instances (base/pathfinding.py:300-310): removed instances stop searching on the device too;
+        their nodes stay in the engine (get_path works) until the slots are recycled, which happens when instances
+        are added while none is left."""
+        removed = [i for i in self.instances if test_rem(i)]
+        if removed:
+            self.instances = [i for i in self.instances if not test_rem(i)]
+            if self._engine is not None:
+                self._engine.remove_instances([i._slot for i in removed if i._owner is self and i._slot >= 0])
+            for i in removed:
+                self._detached.add(i)
+        return removed
+
     def _call_host_fn(self, states: List[Any], goals: List[Any]) -> np.ndarray:
         if self.is_q:
             actions_l = self.domain.get_state_actions(states)
@@ -192,6 +238,8 @@ class GraphSearch(PathFind):
             vals = self._fn(states, goals, [None] * len(states))
             out = np.asarray(vals, dtype=np.float32).reshape(len(states))
         assert out.shape[0] == len(states), f"{out.shape[0]}, {len(states)}"
+        if np.isnan(out).any():
+            raise ValueError("heuristic function returned NaN")
         return out
 
     def _refresh(self) -> None:
@@ -225,8 +273,11 @@ class GraphSearch(PathFind):
             eng.step_end(vals)
             self.times.record_time("search", (t1 - t0) + (time.time() - t2))
         else:
+            if self.stage_times_on and not self._stage_last:
+                eng.set_profiling(1)
+                self._stage_last = eng.stage_ms()
             eng.run(1)
-            self.times.record_time("search", time.time() - t0)
+            self._record_stage_times(time.time() - t0)
         self._refresh()
         if verbose:
             fs = [i.frontier_size() for i in self.instances]
@@ -235,6 +286,24 @@ class GraphSearch(PathFind):
                   f"%finished: {100.0 * np.mean([i.finished() for i in self.instances])}")
             print(f"Times - {self.times.get_time_str()}\n")
         return [], []
+
+    # reference Times key <- engine stages (csrc/engine.cu ST_*): "cost" is the f-key / sort stage of the pushed batch
+    # (GraphSearch._compute_costs + the ordering work the heap does at push time), "pushpop" the OPEN merge + pop
+    _STAGE_KEYS = (("expand", ("expand",)), ("filt", ("filt", "scatter")), ("heur", ("heur",)), ("cost", ("sort",)),
+                   ("pushpop", ("pushpop",)), ("up_inst", ("book",)))
+
+    def _record_stage_times(self, wall: float) -> None:
+        if not self.stage_times_on:
+            self.times.record_time("search", wall)
+            return
+        now = self._engine.stage_ms()
+        dev = 0.0
+        for key, stages in self._STAGE_KEYS:
+            dt = sum(now[s] - self._stage_last.get(s, 0.0) for s in stages) / 1e3
+            self.times.record_time(key, dt)
+            dev += dt
+        self._stage_last = now
+        self.times.record_time("host", max(wall - dev, 0.0))      # launch, status read-back, Python
 
     def run(self, max_itrs: int) -> int:
         """Extension: up to max_itrs steps without returning to Python between them (device heuristics only)."""
@@ -248,9 +317,12 @@ class GraphSearch(PathFind):
                 done += 1
             return done
         t0 = time.time()
+        if self.stage_times_on and not self._stage_last:
+            eng.set_profiling(1)
+            self._stage_last = eng.stage_ms()
         done = eng.run(max_itrs)
         self.itr += done
-        self.times.record_time("search", time.time() - t0)
+        self._record_stage_times(time.time() - t0)
         self._refresh()
         return done
 
@@ -269,7 +341,7 @@ class GraphSearch(PathFind):
         """Extension: drop all instances but keep the engine (buffers, loaded weights, captured graphs) --
         what `solve` gets in the reference by constructing a fresh, cheap PathFind per instance."""
         if self._engine is not None:
-            self._engine.reset()
+            self._recycle()
         self.instances = []
         self.itr = 0
 

@@ -124,7 +124,9 @@ int dx_engine_destroy(dx_engine* e);
  * problem instance, deepxube/_solve.py:146-147, without re-allocating). */
 int dx_engine_reset(dx_engine* e);
 
-/* load_nnet + nnet.eval() (deepxube/pytorch/nnet_utils.py:44-62, factories/pathfind_fns_factory.py:98-104). */
+/* load_nnet + nnet.eval() (deepxube/pytorch/nnet_utils.py:44-62, factories/pathfind_fns_factory.py:98-104).
+ * Calling it again on the same engine overwrites the parameters in place (same network shape required): what an RL
+ * loop does between two batches when the heuristic / target network has been updated (updaters/updater_rl.py). */
 int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats);
 
 /* make_instances + add_instances (graph_search.py:94-109,142-145,161-166; base/pathfinding.py:242-243).
@@ -133,6 +135,12 @@ int dx_load_weights(dx_engine* e, const dx_net_desc* desc, const float* blob, in
  * passes them in root_vals ([n] for graph_v, [n, A] for graph_q; may be NULL for graph_v). */
 int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
                      const int32_t* batch_sizes, const double* weights, const float* root_vals);
+
+/* PathFind.remove_instances / remove_finished_instances (base/pathfinding.py:300-314): the listed instance slots (the
+ * order they were added in since the last reset) stop searching -- no further pops, expansions or OPEN entries -- and
+ * no longer count against max_pop_total.  Their slots, nodes and CLOSED entries are kept until dx_engine_reset, so
+ * dx_get_path / dx_get_status stay valid for them; max_instances bounds the instances added between two resets. */
+int dx_remove_instances(dx_engine* e, const int32_t* slots, int32_t n);
 
 /* PathFind.step() repeated (base/pathfinding.py:338-400, 471-525): runs until every instance is
  * finished() or max_iters steps were taken.  ZERO / NET modes only.  *iters_done = steps taken. */
@@ -269,11 +277,16 @@ int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint32_t* parent
  *                                                segments [u32 count, 12 B pad, seg_records records] (segment d is for rank d)
  *   -- all-to-all of the segments with EQUAL splits (16 + seg_records * record_bytes each) --
  *   dx_hda_receive(e, recv_dev, seg_records, local_dev)   unpack the W received segments (source-major), CLOSED filter, heuristic,
- *                                                push / pop; local_dev[5] (device doubles) = {k_popped, f_first, ub, goal_local, children}
+ *                                                push / pop; local_dev[DX_HDA_LOCAL_DOUBLES] (device doubles) = {k_popped, f_first, ub,
+ *                                                goal_local, children generated, device error flags, children received, children kept}
  *   -- all-gather of local_dev over the ranks --
- *   dx_hda_reduce(e, all_dev, summary_dev)       lb / ub / finished() from all_dev[5 * W] on every rank; summary_dev[8] (device doubles)
- *                                                = {finished, iterations, nodes generated, ub, goal rank, goal local id, device error flags, 0}
- * A segment or receive-capacity overflow raises the device error flag (reported in the summary and by the next synchronising call). */
+ *   dx_hda_reduce(e, all_dev, summary_dev)       lb / ub / finished() from all_dev[DX_HDA_LOCAL_DOUBLES * W] on every rank; summary_dev[8]
+ *                                                (device doubles) = {finished, iterations, nodes generated, ub, goal rank, goal local id,
+ *                                                device error flags OR-ed over all ranks, max over ranks of children received}
+ * A segment or receive-capacity overflow raises the device error flag on that rank; the flag travels in local_dev, so EVERY rank
+ * sees it in the summary of the same iteration and stops (a failing rank keeps publishing empty segments; nobody is left waiting
+ * in a collective). */
+#define DX_HDA_LOCAL_DOUBLES 8
 int dx_engine_set_stream(dx_engine* e, void* cuda_stream);   /* NULL: back to the engine's own stream */
 int dx_hda_send(dx_engine* e, void* send_dev, int64_t seg_records);
 /* Fused pack + exchange over peer memory: peer_recv[r] is rank r's receive buffer mapped into this process (symmetric /

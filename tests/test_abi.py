@@ -41,6 +41,24 @@ def test_struct_sizes_match_header():
     assert ctypes.sizeof(_lib.dx_counters) == 64
 
 
+def test_integration_doc_struct_matches_ctypes():
+    """The dx_config mirror printed in INTEGRATION.md section B has the fields, order and size of the real binding."""
+    from deepxube_b200 import _lib
+    doc = open(os.path.join(ROOT, "INTEGRATION.md")).read()
+    block = doc[doc.index("class dx_config(ctypes.Structure)"):]
+    block = block[:block.index("]\n") + 1]
+    fields = re.findall(r'\("([a-z_0-9]+)", ctypes\.(c_int32 \* 8|c_int32|c_int64)\)', block)
+    ctype = {"c_int32": ctypes.c_int32, "c_int64": ctypes.c_int64, "c_int32 * 8": ctypes.c_int32 * 8}
+
+    class Doc(ctypes.Structure):
+        _fields_ = [(n, ctype[t]) for n, t in fields]
+
+    assert [n for n, _ in fields] == [n for n, _ in _lib.dx_config._fields_]
+    assert ctypes.sizeof(Doc) == ctypes.sizeof(_lib.dx_config)
+    for n, _ in fields:
+        assert getattr(Doc, n).offset == getattr(_lib.dx_config, n).offset, n
+
+
 def test_domain_info_is_host_side(lib):
     from deepxube_b200 import _lib
     assert _lib.domain_info("cube3", 0) == (54, 12, 54, 6)

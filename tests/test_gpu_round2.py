@@ -1,0 +1,345 @@
+"""GPU parity tests added in round 2: h-injection of the in-graph device networks at BASELINE's full sizes, the
+engine-lifecycle entry points (weight reload, instance removal / slot recycling), negative heuristic values, input
+validation and HDA* error propagation.  Everything goes through the C ABI (ctypes) or the host mirror above it."""
+import numpy as np
+import pytest
+
+import golden_utils as gu
+from oracle.domains_np import OracleDomain
+from oracle.nnet_torch import heurv_from_state_dict, random_state_dict
+from oracle.pseudo_heur import make_pseudo_q, pseudo_v
+from oracle.search import OracleSearch
+
+pytestmark = pytest.mark.gpu
+
+
+def _lib():
+    from deepxube_b200 import _lib
+    return _lib
+
+
+def _scrambles(dom, n, k, seed):
+    rng = np.random.default_rng(seed)
+    goals = np.tile(dom.canonical_goal(), (n, 1))
+    st = goals.copy()
+    for _ in range(k):
+        st = dom.next_state(st, rng.integers(0, dom.num_actions, size=n))
+    return st, goals
+
+
+def _compare_iteration(t, eng, oi):
+    for j, (o, s) in enumerate(zip(oi, eng.status())):
+        ids = o.nodes_curr
+        cs, cg, _ = eng.curr_nodes(j, len(ids) + 8)
+        if o.itr == t + 1:
+            assert len(cs) == len(ids), (t, j, len(cs), len(ids))
+            assert np.array_equal(cs, o.store.state[ids]) and np.array_equal(cg.astype(np.float64), o.store.g[ids]), (t, j)
+        assert s.lb == o.lb and s.ub == o.ub and s.num_nodes_generated == o.num_nodes_generated, (t, j, s.lb, o.lb)
+        assert s.itr == o.itr and bool(s.finished) == o.finished(), (t, j)
+        if not s.finished:
+            assert s.open_size == len(o.open), (t, j)
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode_name", ["bf16", "fp32"])
+@pytest.mark.parametrize("algo,n,iters", [("graph_v", 4, 6), ("graph_q", 2, 7)])
+def test_in_graph_network_engine_vs_oracle_fed_the_engines_h(mode_name, algo, n, iters):
+    """SURVEY 8c.1 (h-injection) at BASELINE's full size: cube3, B = 10 000, W = 0.6, resnet_fc.1000H_4B_bn evaluated INSIDE the
+    captured device iteration (dx_run), against the CPU oracle whose heuristic callable returns the same device network's
+    values (dx_heur_eval on a second engine with the same weights).  Every CLOSED decision, pop order, lb / ub / OPEN size
+    and counter must be bit-equal in every iteration -- this pins the in-graph network path (fused one-hot input GEMM,
+    absolute row indexing, kept-children-only evaluation) to the search logic, not just to sortedness properties."""
+    L = _lib()
+    is_q = algo == "graph_q"
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, n, 150, 31)
+    b, w = 10000, 0.6
+    od = 12 if is_q else 1
+    sd = random_state_dict(324, 1000, 4, od, True, seed=2, randomize_bn=True)
+    blob, _ = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    mode = L.DX_HEUR_NET_BF16 if mode_name == "bf16" else L.DX_HEUR_NET_FP32
+    eng = L.Engine("cube3", 0, algo, mode, max_instances=n, max_pop_total=n * b, max_nodes=n * b * (1 if is_q else 12) * (iters + 1) + 1024)
+    eng.load_weights(54, 6, 1000, 4, od, True, blob)
+    ev = L.Engine("cube3", 0, algo, mode, max_instances=1, max_pop_total=8192, max_nodes=1024)
+    ev.load_weights(54, 6, 1000, 4, od, True, blob)
+
+    def heur(s, g):
+        out = ev.heur_eval(s, None, od)
+        return out.astype(np.float64) if is_q else out[:, 0].astype(np.float64)
+
+    orc = OracleSearch(dom, heur, is_q, b, w)
+    oi = orc.add_instances(st, goals)
+    eng.add_instances(st, goals, b, w)
+    for t in range(iters):
+        orc.step()
+        assert eng.run(1) == 1
+        _compare_iteration(t, eng, oi)
+    assert eng.counters().children_generated == sum(o.num_nodes_generated for o in oi)
+    eng.close(); ev.close()
+
+
+def test_config_c1_grid7_100_of_100_with_the_engines_h():
+    """BASELINE config 1 (grid.7d, 100 instances, resnet_fc.100H_2B_bn, graph.1B_1.0W): with the oracle fed the device
+    network's own fp32 values all 100 instances must match exactly (iterations, nodes generated, path cost, actions).
+    Against the torch-evaluated network a handful of instances differ by fp32 re-association of exact ties; those are
+    listed by tests/test_gpu_engine.py::test_config_c1_grid7_100_instances."""
+    L = _lib()
+    dom = OracleDomain("grid", 7)
+    rng = np.random.default_rng(0)
+    n = 100
+    st = rng.integers(0, 7, size=(n, 2), dtype=np.uint8)
+    goals = rng.integers(0, 7, size=(n, 2), dtype=np.uint8)
+    sd = random_state_dict(28, 100, 2, 1, batch_norm=True, seed=3, randomize_bn=True)
+    blob, _ = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    eng = L.Engine("grid", 7, "graph_v", L.DX_HEUR_NET_FP32, max_instances=n, max_pop_total=n, max_nodes=100000)
+    eng.load_weights(4, 7, 100, 2, 1, True, blob)
+    ev = L.Engine("grid", 7, "graph_v", L.DX_HEUR_NET_FP32, max_instances=1, max_pop_total=256, max_nodes=1024)
+    ev.load_weights(4, 7, 100, 2, 1, True, blob)
+    orc = OracleSearch(dom, lambda s, g: ev.heur_eval(s, g, 1)[:, 0].astype(np.float64), False, 1, 1.0)
+    oi = orc.add_instances(st, goals)
+    while not orc.all_finished():
+        orc.step()
+    eng.add_instances(st, goals, 1, 1.0)
+    eng.run(10000)
+    assert eng.all_finished()
+    for j, (o, s) in enumerate(zip(oi, eng.status())):
+        acts, _ = eng.get_path(j)
+        assert s.itr == o.itr and s.num_nodes_generated == o.num_nodes_generated and s.ub == o.ub, j
+        assert acts == o.get_path()[1], j
+    eng.close(); ev.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("mode_name", ["fp32", "bf16"])
+def test_weights_can_be_reloaded_in_place(mode_name):
+    """dx_load_weights twice on one engine (an RL loop's updated network): the second set of parameters is the one
+    that is evaluated afterwards, and a search after the reload equals a fresh engine's (captured graphs survive)."""
+    L = _lib()
+    dom = OracleDomain("cube3")
+    mode = L.DX_HEUR_NET_BF16 if mode_name == "bf16" else L.DX_HEUR_NET_FP32
+    st, goals = _scrambles(dom, 3, 40, 5)
+    blobs = [L.pack_state_dict({k: v.numpy() for k, v in random_state_dict(324, 256, 2, 1, True, seed=s, randomize_bn=True).items()})[0]
+             for s in (1, 2)]
+
+    def fresh(blob):
+        e = L.Engine("cube3", 0, "graph_v", mode, max_instances=3, max_pop_total=600, max_nodes=200000)
+        e.load_weights(54, 6, 256, 2, 1, True, blob)
+        return e
+
+    def search(e):
+        e.reset()
+        e.add_instances(st, goals, 200, 0.6)
+        e.run(6)
+        return [(s.num_nodes_generated, s.lb, s.open_size) for s in e.status()], [e.curr_nodes(j, 300)[2].copy() for j in range(3)]
+
+    e = fresh(blobs[0])
+    h_a = e.heur_eval(st, None, 1)
+    r_a = search(e)
+    e.load_weights(54, 6, 256, 2, 1, True, blobs[1])            # in place
+    h_b = e.heur_eval(st, None, 1)
+    r_b = search(e)
+    f = fresh(blobs[1])
+    assert np.array_equal(h_b, f.heur_eval(st, None, 1)) and not np.array_equal(h_a, h_b)
+    r_f = search(f)
+    assert r_b[0] == r_f[0] and all(np.array_equal(x, y) for x, y in zip(r_b[1], r_f[1]))
+    assert r_a[0] != r_b[0]
+    with pytest.raises(L.DxError, match="shape"):
+        e.load_weights(54, 6, 128, 2, 1, True, L.pack_state_dict({k: v.numpy() for k, v in random_state_dict(324, 128, 2, 1, True, seed=1).items()})[0])
+    e.close(); f.close()
+
+
+def test_host_mirror_reuploads_changed_weights():
+    """nnet.load_state_dict() between two batches of a reused PathFind: the second batch searches with the new network
+    (the reference builds each PathFind around the current function, updaters/updater_rl.py:137-165)."""
+    import deepxube_b200  # noqa: F401
+    from deepxube_b200.factories.domain_factory import get_domain_from_arg
+    from deepxube_b200.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict
+    from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+    domain, dname = get_domain_from_arg("cube3")
+    sds = [{k: v.numpy() for k, v in random_state_dict(324, 128, 1, 1, True, seed=s, randomize_bn=True).items()} for s in (3, 4)]
+    states, goals = domain.sample_problem_instances([20, 25, 30])
+
+    def run(pf):
+        insts = pf.make_instances(states, goals, None, True)
+        pf.add_instances(insts)
+        for _ in range(5):
+            pf.step()
+        return [(i.num_nodes_generated, i.lb, i.frontier_size()) for i in pf.instances]
+
+    pfns, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv,resnet_fc.128H_1B_bn"])
+    pfns.heurv.nnet.load_state_dict(sds[0])
+    pf = get_pathfind_from_arg(domain, pfns, "graph.50B_0.7W")[0]
+    r0 = run(pf)
+    h0 = pfns.heurv(states, goals, [None] * 3)
+    pfns.heurv.nnet.load_state_dict(sds[1])
+    pf.reset()
+    r1 = run(pf)
+    h1 = pfns.heurv(states, goals, [None] * 3)
+    pfns2, _ = get_path_fns_nnet_par_dict(domain, dname, ["heurv,resnet_fc.128H_1B_bn"])
+    pfns2.heurv.nnet.load_state_dict(sds[1])
+    pf2 = get_pathfind_from_arg(domain, pfns2, "graph.50B_0.7W")[0]
+    assert run(pf2) == r1 and r0 != r1
+    assert h1 == pfns2.heurv(states, goals, [None] * 3) and h0 != h1
+    pf.close(); pf2.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+def test_remove_instances_stops_them_and_slots_recycle():
+    """PathFind.remove_instances / remove_finished_instances on the device: a removed instance is not searched any more
+    (its counters freeze, it stops counting against max_pop_total), the others are unaffected (bit-equal to the oracle),
+    and once none is left the engine's slots are recycled by the next add_instances."""
+    import deepxube_b200  # noqa: F401
+    from deepxube_b200.base.pathfind_fns import PFNsHeurV
+    from deepxube_b200.base.pathfinding import get_path
+    from deepxube_b200.factories.domain_factory import get_domain_from_arg
+    from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+    domain, _ = get_domain_from_arg("npuzzle.3")
+    dom = OracleDomain("npuzzle", 3)
+    st, goals = _scrambles(dom, 3, 30, 9)
+    states, goal_objs = domain.rows_to_states(st), [type(domain.sample_problem_instances([0])[1][0])(g) for g in goals]
+    pf = get_pathfind_from_arg(domain, PFNsHeurV(heurv=lambda s, g, c: pseudo_v(domain.states_to_rows(s), None).tolist()), "graph.20B_1.0W",
+                               )[0]
+    pf._max_instances = 3
+    insts = pf.make_instances(states, goal_objs, None, True)
+    pf.add_instances(insts)
+    orc = OracleSearch(dom, pseudo_v, False, 20, 1.0)
+    oi = orc.add_instances(st, goals)
+    for _ in range(3):
+        pf.step(); orc.step()
+    victim = insts[1]
+    removed = pf.remove_instances(lambda i: i is victim)
+    assert removed == [victim] and len(pf.instances) == 2
+    frozen = (victim.itr, victim.num_nodes_generated)
+    oi_live = [oi[0], oi[2]]
+    for t in range(60):
+        if all(i.finished() for i in pf.instances):
+            break
+        pf.step()
+        for o in oi_live:
+            if not o.finished():
+                orc_step_one(orc, o)
+    for inst, o in zip(pf.instances, oi_live):
+        assert inst.finished() and o.finished()
+        assert inst.num_nodes_generated == o.num_nodes_generated and inst.itr == o.itr and inst.path_cost() == o.path_cost()
+        assert [a.action for a in get_path(inst.goal_node)[1]] == o.get_path()[1]
+    sts = pf._engine.status()
+    assert (sts[1].itr, sts[1].num_nodes_generated) == frozen and sts[1].finished        # never stepped again
+    # remove the rest, then add again: the engine is recycled (slots 0.. are reused) and the old solutions stay readable
+    done = pf.remove_finished_instances(10 ** 9)
+    assert len(done) == 2 and pf.instances == []
+    again = pf.make_instances(states, goal_objs, None, True)
+    pf.add_instances(again)
+    assert pf._engine.num_instances() == 3 and [i._slot for i in again] == [0, 1, 2]
+    while not all(i.finished() for i in pf.instances):
+        pf.step()
+    assert [i.num_nodes_generated for i in again][0::2] == [i.num_nodes_generated for i in done]
+    assert [a.action for a in get_path(done[0].goal_node)[1]] == oi[0].get_path()[1]     # materialised before the recycle
+    pf.close()
+
+
+def orc_step_one(orc, inst):
+    """advance ONE oracle instance by an iteration (the oracle steps all unfinished instances of its list)"""
+    keep = orc.instances
+    orc.instances = [inst]
+    orc.step()
+    orc.instances = keep
+
+
+def test_remove_frees_pop_capacity():
+    L = _lib()
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 4, 30, 2)
+    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_ZERO, max_instances=4, max_pop_total=200, max_nodes=400000)
+    eng.add_instances(st[:2], goals[:2], 100, 1.0)
+    eng.run(3)
+    with pytest.raises(L.DxError, match="max_pop_total"):
+        eng.add_instances(st[2:3], goals[2:3], 100, 1.0)
+    eng.remove_instances([0])
+    eng.add_instances(st[2:3], goals[2:3], 100, 1.0)            # fits now
+    gen0 = eng.status()[0].num_nodes_generated
+    eng.run(3)
+    s = eng.status()
+    assert s[0].num_nodes_generated == gen0 and s[0].finished and s[1].itr == 6 and s[2].itr == 3
+    with pytest.raises(L.DxError, match="slot"):
+        eng.remove_instances([7])
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("q", [False, True])
+def test_negative_heuristic_values_order_like_the_reference_heap(q):
+    """A host callable may return negative values (the reference's heap orders them numerically, graph_search.py:48-51;
+    Node.tree_backup clips with max(h, 0) precisely because they occur): OPEN keys must sort negative f below positive f."""
+    L = _lib()
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 2, 25, 3)
+    base = make_pseudo_q(12) if q else pseudo_v
+    fn = (lambda s, g: base(s, g) - 32.0)                      # roughly half of the values below zero
+    vals = fn(st, goals)
+    assert (np.asarray(vals) < 0).any()
+    orc = OracleSearch(dom, fn, q, 60, 0.3)
+    oi = orc.add_instances(st, goals)
+    eng = L.Engine("cube3", 0, "graph_q" if q else "graph_v", L.DX_HEUR_HOST, max_instances=2, max_pop_total=120, max_nodes=300000)
+    eng.add_instances(st, goals, 60, 0.3, root_vals=vals)
+    saw_negative_lb = False
+    for t in range(8):
+        orc.step()
+        n = eng.step_begin()
+        ps, pg = eng.get_pending(n)
+        eng.step_end(fn(ps, pg) if n else np.zeros((0, 12) if q else (0,)))
+        _compare_iteration(t, eng, oi)
+        saw_negative_lb = saw_negative_lb or any(o.lb < 0 for o in oi) or any(s.lb < 0 for s in eng.status())
+    eng.close()
+
+
+def test_nan_heuristic_is_rejected_by_the_host_mirror():
+    import deepxube_b200  # noqa: F401
+    from deepxube_b200.base.pathfind_fns import PFNsHeurV
+    from deepxube_b200.factories.domain_factory import get_domain_from_arg
+    from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
+    domain, _ = get_domain_from_arg("cube3")
+    states, goals = domain.sample_problem_instances([5])
+    pf = get_pathfind_from_arg(domain, PFNsHeurV(heurv=lambda s, g, c: [float("nan")] * len(s)), "graph.5B_1.0W")[0]
+    with pytest.raises(ValueError, match="NaN"):
+        pf.add_instances(pf.make_instances(states, goals, None, True))
+    pf.close()
+
+
+def test_one_hot_inputs_out_of_range_are_rejected():
+    """F.one_hot raises in the reference when a value is >= the depth (pytorch_models.py:15-24); the C ABI refuses such rows
+    instead of clamping them on the device."""
+    L = _lib()
+    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_FP32, max_instances=1, max_pop_total=16, max_nodes=1024)
+    blob, _ = L.pack_state_dict({k: v.numpy() for k, v in random_state_dict(324, 128, 1, 1, True, seed=1).items()})
+    eng.load_weights(54, 6, 128, 1, 1, True, blob)
+    bad = np.zeros((2, 54), np.uint8)
+    bad[1, 17] = 6
+    with pytest.raises(L.DxError, match="one-hot depth"):
+        eng.heur_eval(bad, None, 1)
+    with pytest.raises(L.DxError, match="one-hot depth"):
+        eng.add_instances(bad, bad, 4, 1.0)
+    eng.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("device_resident", [True, False])
+def test_hda_capacity_error_reaches_every_rank(device_resident):
+    """An exchange-segment / receive-capacity overflow on ONE rank must stop ALL ranks in the same iteration (the flag travels
+    in the all-gathered scalars) -- otherwise the healthy ranks of a multi-process run wait forever in the next collective."""
+    from deepxube_b200 import _lib as L
+    from deepxube_b200.hda import HdaSearch
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 1, 60, 4)
+    h = HdaSearch("cube3", 0, 4, batch_size=4000, weight=0.0, max_nodes_per_rank=1 << 20, capacity_slack=1.0,
+                  device_resident=device_resident)
+    if device_resident:
+        h.seg_records = 40                      # far below the ~3000 records a rank sends to each owner
+        h.seg_bytes = 16 + h.seg_records * h.rec
+    else:
+        h.cap_records = 500
+    with pytest.raises(L.DxError):
+        h.solve(st[0], goals[0], max_itrs=12)
+    if device_resident:
+        flags = [int(s.cpu()[6].item()) for s in h.summary]
+        assert all(f != 0 for f in flags), flags          # every rank's summary carries the error, not only the failing one
+    h.close()

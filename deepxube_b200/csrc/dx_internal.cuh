@@ -156,7 +156,19 @@ struct NetDev {
     float* b0_tc;    // [Hp] first-layer bias for the unfolded input layer (carries the 1.0 of the ones columns), else nullptr
     void* wout_bf16; // [128, Hp] zero-padded bf16 output-layer weights (multi-output networks with out_dim <= 32), else nullptr
     float* bout_pad; // [128] output bias, zero-padded
-    void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16
+    void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16 / split NET_FP32
+    void* tc_split;  // host TcSplitW*: fp16 (hi, lo) copies of the parameters -- NET_FP32 on the tensor cores (k_mlp_tc.cu), else nullptr
+};
+
+// Split-fp16 parameters of the fp32-accurate tensor-core path: every weight w is stored as the fp16 pair (hi, lo) of w * s
+// (s = a power of two per layer that puts the largest weight in [2^13, 2^14), so that the lo halves are normal fp16 numbers):
+// rows [hi(0..K) | lo(0..K)].
+struct TcSplitW {
+    void* w0;        // [Hp, 2 * in_dim_p]
+    void* wres;      // [2 * num_blocks * Hp, 2 * Hp]
+    void* wout;      // [128, 2 * Hp] zero-padded multi-output layer (1 < out_dim <= 32), else nullptr
+    float s_in, s_out;
+    float s_res[128];
 };
 
 static inline int dx_div_up(long long a, long long b) { return (int)((a + b - 1) / b); }
@@ -372,4 +384,8 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
 int dx_launch_act_begin(cudaStream_t s, const NetDev& net, Ctl* ctl);
 int dx_launch_act_end(cudaStream_t s, const NetDev& net, Ctl* ctl, const float* q, float* out_h, int absolute, long long max_nodes);
 bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d);
+// fp32-accurate network on the tensor cores: whether this shape is supported, and the (re)upload of the split parameters from the
+// host copies (w0p [Hp, in_dim_p], wres [2 * nb, Hp, Hp], wout [out_dim, Hp], all fp32 with BN folded)
+bool dx_mlp_split_supported(const NetDev& net);
+int dx_mlp_split_upload(cudaStream_t s, NetDev& net, const float* w0p, const float* wres, const float* wout);
 int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out);

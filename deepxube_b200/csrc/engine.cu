@@ -147,13 +147,23 @@ __global__ void k_set_host_vals(const Ctl* ctl, const float* vals, float* node_h
 __global__ void k_set_job(Ctl* ctl, uint32_t start, uint32_t n) { ctl->nn_row_start = start; ctl->nn_n = n; }
 // PathFind.remove_instances (base/pathfinding.py:300-310): the instance stops searching -- no more pops, expansions or
 // OPEN entries (k_plan drops the run of an inactive instance) -- and no longer counts as unfinished
-__global__ void k_deactivate(Ctl* ctl, InstArrays ia, const int32_t* slots, int n) {
-    uint32_t dropped = 0;
-    for (int j = 0; j < n; ++j) {
-        const int i = slots[j];
-        if (ia.active[i]) { ia.active[i] = 0; ++dropped; }
+// The popped list (nodes the next step expands) is compacted so that the removed instances' entries give their room back
+// at once: one block per instance copies its segment to its new offset in the other buffer; the host copies it back.
+__global__ void k_compact_popped(const uint32_t* __restrict__ off_old, const uint32_t* __restrict__ off_new, int n_inst,
+                                 const uint32_t* __restrict__ popped, const uint32_t* __restrict__ popped_inst,
+                                 uint32_t* __restrict__ popped_out, uint32_t* __restrict__ popped_inst_out) {
+    for (int i = blockIdx.x; i < n_inst; i += gridDim.x) {
+        const uint32_t src = off_old[i], dst = off_new[i], len = off_new[i + 1] - off_new[i];
+        for (uint32_t t = threadIdx.x; t < len; t += blockDim.x) {
+            popped_out[dst + t] = popped[src + t];
+            popped_inst_out[dst + t] = popped_inst[src + t];
+        }
     }
-    ctl->n_unfinished -= min(dropped, ctl->n_unfinished);
+}
+__global__ void k_after_remove(Ctl* ctl, uint32_t n_pop, uint32_t n_children, uint32_t n_unfinished) {
+    ctl->n_pop = n_pop;
+    ctl->n_children = n_children;
+    ctl->n_unfinished = n_unfinished;
 }
 __global__ void k_reset_backups(Ctl* ctl) { ctl->n_backups = 0; }
 __global__ void k_set_job_children(Ctl* ctl) { ctl->nn_row_start = 0; ctl->nn_n = ctl->error ? 0 : ctl->n_children; }
@@ -202,6 +212,7 @@ struct dx_engine {
     bool pending = false;        // HOST mode: between step_begin and step_end
     bool weights_loaded = false;
     long long launches = 0;
+    std::vector<uint8_t> removed;        // instance slots given up through dx_remove_instances (host copy)
 
     // device memory
     uint8_t* d_table = nullptr;
@@ -420,6 +431,7 @@ static int reset_state(dx_engine* e) {
     e->parity = 0;
     e->pending = false;
     e->sort_bound = 0;
+    e->removed.clear();
     return DX_OK;      // stage timers are cumulative across resets; dx_set_profiling() clears them
 }
 
@@ -526,6 +538,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
 
 extern "C" int dx_engine_destroy(dx_engine* e) {
     if (!e) return DX_OK;
+    if (g_prof_engine == e) g_prof_engine = nullptr;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
     for (int k = 0; k < 2; ++k) {
@@ -534,6 +547,11 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
         for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
     }
     for (void* p : e->allocs) cudaFree(p);
+    if (e->net.tc_split) {
+        TcSplitW* sw = (TcSplitW*)e->net.tc_split;
+        cudaFree(sw->w0); cudaFree(sw->wres); cudaFree(sw->wout);
+        delete sw;
+    }
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -555,17 +573,23 @@ static int need_net(dx_engine* e) {
 
 int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int64_t n_floats);   // net_load.cu
 
+// The loaded network over the current job: tcgen05 path (bf16, or split-fp16 for NET_FP32 when the shape is supported),
+// else the CUDA-core fp32 path.  Returns the number of launches.
+static int launch_net(dx_engine* e, const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows) {
+    g_prof_engine = e->profiling ? e : nullptr;       // the launchers' dx_prof_begin / dx_prof_end hooks time into THIS engine
+    if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || e->net.tc_split)
+        return dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, goals, out_h, out_q, absolute, max_rows);
+    return dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, goals, out_h, out_q, absolute, max_rows);
+}
+
 // heuristic for the current job (ctl->nn_row_start / nn_n) over node-store rows
 static int launch_heur_rows(dx_engine* e, const uint8_t* rows, float* out_h, float* out_q, long long max_rows) {
     const int mode = e->cfg.heur_mode;
-    g_prof_engine = e->profiling ? e : nullptr;
     if (mode == DX_HEUR_ZERO) {
         k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, out_h, out_q, e->A);
         e->launches += 1;
-    } else if (mode == DX_HEUR_NET_FP32) {
-        e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, e->ia.goals, out_h, out_q, 1, max_rows);
-    } else if (mode == DX_HEUR_NET_BF16) {
-        e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, e->ia.goals, out_h, out_q, 1, max_rows);
+    } else if (mode == DX_HEUR_NET_FP32 || mode == DX_HEUR_NET_BF16) {
+        e->launches += launch_net(e, rows, e->ia.goals, out_h, out_q, 1, max_rows);
     }
     return DX_OK;
 }
@@ -600,11 +624,34 @@ extern "C" int dx_remove_instances(dx_engine* e, const int32_t* slots, int32_t n
     for (int j = 0; j < n; ++j)
         if (slots[j] < 0 || slots[j] >= e->n_inst) DX_FAIL(DX_ERR_ARG, "instance slot out of range");
     DX_CUDA(cudaSetDevice(e->cfg.device));
-    DX_TRY(ensure_stage(e, (size_t)n * sizeof(int32_t) + 64));
-    DX_CUDA(cudaMemcpyAsync(e->d_stage, slots, (size_t)n * sizeof(int32_t), cudaMemcpyHostToDevice, e->stream));
-    k_deactivate<<<1, 1, 0, e->stream>>>(e->d_ctl, e->ia, (const int32_t*)e->d_stage, n);
-    e->launches += 1;
-    DX_CUDA(cudaStreamSynchronize(e->stream));
+    DX_TRY(sync_ctl(e));
+    const int I = e->n_inst, p = e->parity, q = p ^ 1;
+    cudaStream_t s = e->stream;
+    std::vector<uint8_t> act(I);
+    std::vector<uint32_t> off(I + 1), noff(I + 1);
+    DX_CUDA(cudaMemcpy(act.data(), e->ia.active, I, cudaMemcpyDeviceToHost));
+    DX_CUDA(cudaMemcpy(off.data(), e->pop_off[p], (size_t)(I + 1) * 4, cudaMemcpyDeviceToHost));
+    e->removed.resize(e->max_inst, 0);
+    for (int j = 0; j < n; ++j) { act[slots[j]] = 0; e->removed[slots[j]] = 1; }
+    uint32_t acc = 0, unfinished = 0;
+    for (int i = 0; i < I; ++i) {                 // removed instances give up their popped entries (a finished one keeps its last
+        noff[i] = acc;                            // `_nodes_curr` readable, Instance.get_nodes)
+        if (!e->removed[i]) acc += off[i + 1] - off[i];
+        if (act[i]) ++unfinished;
+    }
+    noff[I] = acc;
+    DX_CUDA(cudaMemcpyAsync(e->ia.active, act.data(), I, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->pop_off[q], noff.data(), (size_t)(I + 1) * 4, cudaMemcpyHostToDevice, s));
+    k_compact_popped<<<std::min(I, 148 * 8), 256, 0, s>>>(e->pop_off[p], e->pop_off[q], I, e->popped[p], e->popped_inst[p], e->popped[q],
+                                                          e->popped_inst[q]);
+    if (acc) {
+        DX_CUDA(cudaMemcpyAsync(e->popped[p], e->popped[q], (size_t)acc * 4, cudaMemcpyDeviceToDevice, s));
+        DX_CUDA(cudaMemcpyAsync(e->popped_inst[p], e->popped_inst[q], (size_t)acc * 4, cudaMemcpyDeviceToDevice, s));
+    }
+    DX_CUDA(cudaMemcpyAsync(e->pop_off[p], e->pop_off[q], (size_t)(I + 1) * 4, cudaMemcpyDeviceToDevice, s));
+    k_after_remove<<<1, 1, 0, s>>>(e->d_ctl, acc, acc * (e->is_q ? 1u : (uint32_t)e->A), unfinished);
+    e->launches += 2;
+    DX_CUDA(cudaStreamSynchronize(s));            // (the host vectors above must outlive the copies)
     return DX_OK;
 }
 
@@ -1400,10 +1447,7 @@ extern "C" int dx_vi_targets(dx_engine* e, const uint8_t* states, const uint8_t*
         k_set_job<<<1, 1, 0, st>>>(e->d_ctl, 0, (uint32_t)(m * fan));
         e->launches += 1;
         float* out_q = e->is_q ? d_vals : nullptr;
-        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
-            e->launches += dx_launch_mlp_bf16(st, e->dom, e->net, e->mlp, e->d_ctl, nn_rows, d_goals, d_h, out_q, 0, m * fan);
-        else
-            e->launches += dx_launch_mlp_f32(st, e->dom, e->net, e->mlp, e->d_ctl, nn_rows, d_goals, d_h, out_q, 0, m * fan);
+        e->launches += launch_net(e, nn_rows, d_goals, d_h, out_q, 0, m * fan);
         k_vi_reduce<<<std::min(dx_div_up(m, 256), 148 * 4), 256, 0, st>>>(d_h, sol, m, fan, d_out);
         e->launches += 1;
         DX_CUDA(cudaMemcpyAsync(out + s0, d_out, (size_t)m * 8, cudaMemcpyDeviceToHost, st));
@@ -1447,10 +1491,7 @@ extern "C" int dx_heur_eval(dx_engine* e, const uint8_t* states, const uint8_t* 
         DX_CUDA(cudaMemcpyAsync(d_goals, grows.data(), (size_t)m * SP, cudaMemcpyHostToDevice, e->stream));
         k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, 0, (uint32_t)m);
         e->launches += 1;
-        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
-            e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, d_rows, d_goals, nullptr, d_out, 0, m);
-        else
-            e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, d_rows, d_goals, nullptr, d_out, 0, m);
+        e->launches += launch_net(e, d_rows, d_goals, nullptr, d_out, 0, m);
         DX_CUDA(cudaMemcpyAsync(out + (size_t)s0 * od, d_out, (size_t)m * od * 4, cudaMemcpyDeviceToHost, e->stream));
         DX_CUDA(cudaStreamSynchronize(e->stream));
     }
@@ -1486,10 +1527,7 @@ extern "C" int dx_bench_heur(dx_engine* e, int64_t n, int32_t reps, float* ms_to
     cudaEventCreate(&b);
     cudaEventRecord(a, e->stream);
     for (int r = 0; r < reps; ++r) {
-        if (e->cfg.heur_mode == DX_HEUR_NET_BF16)
-            e->launches += dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, nullptr, d_out, 0, n);
-        else
-            e->launches += dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, e->node_state, e->ia.goals, nullptr, d_out, 0, n);
+        e->launches += launch_net(e, e->node_state, e->ia.goals, nullptr, d_out, 0, n);
     }
     cudaEventRecord(b, e->stream);
     k_set_job<<<1, 1, 0, e->stream>>>(e->d_ctl, saved.nn_row_start, saved.nn_n);
@@ -1674,25 +1712,38 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
         net.w0_bf16 = w0b;
         net.wres_bf16 = wrb;
     }
+    // NET_FP32 on the tensor cores (split-fp16 operands, k_mlp_tc.cu) where the shape allows; else the CUDA-core SGEMM path
+    const bool split = e->cfg.heur_mode == DX_HEUR_NET_FP32 && (reload ? net.tc_split != nullptr : dx_mlp_split_supported(net));
+    if (split) {
+        DX_TRY(dx_mlp_split_upload(e->stream, net, w0p.data(), wres.data(), wout.data()));
+        if (od > 1) {
+            std::vector<float> bpad(128, 0.f);
+            for (int o = 0; o < od; ++o) bpad[o] = bout[o];
+            if (!net.bout_pad) DX_TRY(e->alloc(&net.bout_pad, bpad.size()));
+            DX_CUDA(cudaMemcpy(net.bout_pad, bpad.data(), bpad.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
+    }
     if (reload) {
         DX_CUDA(cudaDeviceSynchronize());
-        return DX_OK;                         // activation buffers, tensor maps and captured graphs stay
+        if (split) drop_graphs(e);            // the per-layer weight scales are kernel ARGUMENTS baked into the captured launches
+        return DX_OK;                         // activation buffers and tensor maps stay (bf16 / SGEMM: the captured graphs too)
     }
     // activation buffers
     // rows one evaluation can hold: popped nodes (Q*) or children (A*); x actions for an action-as-input network
     const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst) * (act_depth > 0 ? act_depth : 1);
     e->mlp.cap = cap;
-    if (e->cfg.heur_mode == DX_HEUR_NET_BF16) {
+    if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || split) {
         int fill = 0;
         if (const char* f = getenv("DXB200_DEBUG_FILL")) fill = atoi(f);      // debug: poison value of never-written rows
+        const size_t xw = split ? 2 : 1;                                      // split mode: [hi | lo] halves per row
         for (int i = 0; i < 3; ++i) {
             uint16_t* q = nullptr;
-            DX_TRY(e->alloc(&q, (size_t)cap * Hp));
-            DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 2));
+            DX_TRY(e->alloc(&q, (size_t)cap * Hp * xw));
+            DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 2 * xw));
             e->mlp.xb[i] = q;
         }
         uint16_t* onehot = nullptr;
-        const bool gen_input = dx_mlp_bf16_gen_input(net, e->dom);
+        const bool gen_input = !split && dx_mlp_bf16_gen_input(net, e->dom);
         if (!gen_input) {                   // the one-hot matrix exists only for networks whose input layer is not fused
             DX_TRY(e->alloc(&onehot, (size_t)cap * in_dim_p));
             DX_CUDA(cudaMemset(onehot, fill, (size_t)cap * in_dim_p * 2));

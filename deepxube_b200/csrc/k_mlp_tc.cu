@@ -20,7 +20,12 @@
 // k_onehot_bf16 (exact: the entries are 0 / 1).
 #include <cuda.h>
 #include <stdlib.h>
+#include <math.h>
+#include <cmath>
+#include <algorithm>
+#include <vector>
 #include <cuda_bf16.h>
+#include <cuda_fp16.h>
 
 #include "dx_internal.cuh"
 
@@ -61,6 +66,7 @@ struct TcPlan {
     int fuse_out;                // fold a scalar output layer into the last hidden GEMM (DXB200_FUSE_OUT=0 disables)
     int fuse_in;                 // the one-hot input is generated inside the first GEMM (dx_mlp_bf16_gen_input; DXB200_FUSE_IN=0 disables)
     int num_sms;
+    int split;                   // fp32-accurate mode: fp16 (hi, lo) operands, activation buffers / weights are [rows, 2 * K]
 };
 
 // Fused input layer (GEN_A): the A operand is the one-hot encoding of the state rows
@@ -72,6 +78,23 @@ struct TcGen {
     int S, SP, in_count, depth;
     int ones_col;                // >= 0: columns ones_col .. +2 are 1.0 (folded bias), else -1
 };
+
+// fp32-accurate mode (DX_HEUR_NET_FP32 on the tensor cores): every operand is an fp16 (hi, lo) pair with hi + lo == the
+// scaled fp32 value to ~22 bits, and a contraction is three MMA passes into the same fp32 TMEM accumulator,
+//   A.W ~= A_hi.W_lo + A_lo.W_hi + A_hi.W_hi           (the dropped A_lo.W_lo term is 2^-22 relative)
+// The kernel's main loop is unchanged: a "phase" is one pass over the k-blocks with its own column offsets into the
+// [hi | lo] operand arrays (activations [rows, 2*Hp], weights [out, 2*K]).  Weights are scaled by a power of two per
+// layer (fp16 lo halves stay normal numbers), activations by 2^6; the epilogue undoes the scales exactly.
+struct TcSplit {
+    int nph;                 // MMA passes over the k-blocks (1: plain bf16 GEMM)
+    int a_col[3], w_col[3];  // column offset (elements) of the A / W operand of each pass
+    float acc_scale;         // accumulator -> true pre-activation (1 / (weight scale * activation scale))
+    float res_scale;         // stored residual -> true value (1 / activation scale)
+    float out_scale;         // true activation -> stored value (activation scale)
+    int lo_col;              // column offset of the lo half in the output / residual buffers
+    int f16;                 // operands are fp16 (else bf16)
+};
+#define TC_ACT_SCALE 64.0f
 
 // Optional in-kernel wait accounting (build with -DTC_PROFILE): cycles the role threads spend blocked on each
 // barrier, summed over CTAs.  [0] MMA waits operands (full), [1] MMA waits accumulator (tmem empty),
@@ -244,14 +267,16 @@ struct TcSmem {
 // multi-output network (Q*: out_dim = #actions <= 32, weight rows zero-padded to the n-tile): the epilogue adds the fp32
 // bias, clips at 0 and writes the first qdim columns as fp32 q-values plus their minimum (node.heuristic) -- no bf16
 // rounding of the outputs, no activation store.
-template <int BN, int CL, int OUT_MODE, bool GEN_A>
+template <int BN, int CL, int OUT_MODE, bool GEN_A, bool SPLIT = false>
 __global__ void __launch_bounds__(GEN_A ? TC_THREADS_GEN : TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
                int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu,
                const float* __restrict__ wout, float* __restrict__ partial, long long pstride, const TcGen gen,
-               float* __restrict__ out_h, int qdim, int absolute) {
+               float* __restrict__ out_h, int qdim, int absolute, const TcSplit sp) {
     extern __shared__ uint8_t smem_raw[];
+    static_assert(!(SPLIT && (GEN_A || CL != 2)), "the split-fp16 mode runs in CTA pairs with a TMA-fed A operand");
+    const int nph = SPLIT ? sp.nph : 1;
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
     constexpr bool FUSE_OUT = OUT_MODE == 1, Q_OUT = OUT_MODE == 2;
@@ -368,27 +393,29 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             }
             for (int t = cl_id; !GEN_A && t < total; t += n_cl) {
                 const int m0 = tile_m0(t), n0 = tile_n0(t);
+                for (int ph = 0; ph < nph; ++ph)
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     { TC_T0(); mbar_wait(empty_bar(s), ((it / STAGES) & 1u) ^ 1u); TC_ACC(w_empty); }
                     const uint32_t a_dst = smem_base + s * SM::STAGE_BYTES, b_dst = a_dst + SM::A_BYTES;
                     constexpr int TX = SM::STAGE_BYTES;
+                    const int a_c = (SPLIT ? sp.a_col[ph] : 0) + kb * TC_BK, w_c = (SPLIT ? sp.w_col[ph] : 0) + kb * TC_BK;
                     if (PAIR == 1) {
                         mbar_arrive_expect_tx(full_bar(s), TX);
-                        tma_load_2d(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
-                        tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
+                        tma_load_2d(a_dst, &tmA, full_bar(s), a_c, m0);
+                        tma_load_2d(b_dst, &tmB, full_bar(s), w_c, w_row0 + n0);
                     } else {
                         // the pair leader's barrier counts the bytes of both CTAs (2 x STAGE_BYTES per phase)
                         if (hr == 0) mbar_arrive_expect_tx(full_bar(s), 2 * TX);
                         if (NP == 2) {
                             // CTAs hr and hr + 2 hold the same 128 A rows: each fetches 64 of them (tmA has 64-row boxes here)
                             // and multicasts them into both
-                            tma_load_2d_2sm_mc(a_dst + pr * (SM::A_BYTES / 2), &tmA, full_bar(s), kb * TC_BK, m0 + (int)pr * (TC_BM / 2),
+                            tma_load_2d_2sm_mc(a_dst + pr * (SM::A_BYTES / 2), &tmA, full_bar(s), a_c, m0 + (int)pr * (TC_BM / 2),
                                                (uint16_t)((1u << hr) | (1u << (hr + 2))));
                         } else {
-                            tma_load_2d_2sm(a_dst, &tmA, full_bar(s), kb * TC_BK, m0);
+                            tma_load_2d_2sm(a_dst, &tmA, full_bar(s), a_c, m0);
                         }
-                        tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)hr * (BN / PAIR));
+                        tma_load_2d_2sm(b_dst, &tmB, full_bar(s), w_c, w_row0 + n0 + (int)hr * (BN / PAIR));
                     }
                 }
             }
@@ -400,8 +427,9 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         if (lane == 0 && hr == 0) {
             // ---------------- MMA issuer (the leader CTA of each pair) ----------------
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128 * PAIR
-            const uint32_t idesc = (1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(BN >> 3) << 17) |
-                                   ((uint32_t)((TC_BM * PAIR) >> 4) << 24);
+            // (A / B format field: 1 = bf16, 0 = fp16 -- the split-fp16 mode's operands)
+            const uint32_t ab_fmt = (SPLIT && sp.f16) ? 0u : ((1u << 7) | (1u << 10));
+            const uint32_t idesc = (1u << 4) | ab_fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * PAIR) >> 4) << 24);
             uint32_t it = 0, lt = 0;
             [[maybe_unused]] long long w_full = 0, w_tempty = 0;
 #ifdef TC_PROFILE
@@ -436,6 +464,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 { TC_T0(); mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u); TC_ACC(w_tempty); }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                for (int ph = 0; ph < nph; ++ph)
                 for (int kb = 0; kb < kblocks; ++kb, ++it) {
                     const int s = it % STAGES;
                     { TC_T0(); mbar_wait(full_bar(s), (it / STAGES) & 1u); TC_ACC(w_full); }
@@ -444,7 +473,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     const uint64_t adesc = make_sw128_desc(a_src), bdesc = make_sw128_desc(b_src);
 #pragma unroll
                     for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-                        umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (kb | k) ? 1u : 0u);
+                        umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(k * 2), bdesc + (uint64_t)(k * 2), idesc, (ph | kb | k) ? 1u : 0u);
                     umma_commit<PAIR>(empty_bar(s), all_mask);    // slot reusable (told to every CTA of the cluster) once these MMAs have read it
                 }
                 umma_commit<PAIR>(tfull_bar(as), pair_mask);      // accumulator complete (signalled to both CTAs of the pair)
@@ -599,7 +628,15 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; seq_tile(k, m0, n0); ++k, ++lt) {
             const int as = lt & 1;
             const int row0 = m0 + q * 32;
-            if (has_res && lane == 0) {          // this warp's first TC_NBUF residual chunks of the tile
+            if (SPLIT) {
+                // split mode: buffer 0 holds the hi half, buffer 1 the lo half of ONE chunk (both on barrier 0); the epilogue
+                // has three MMA passes' worth of time per tile, so chunks are not double-buffered here
+                if (has_res && lane == 0 && h < NCH) {
+                    mbar_arrive_expect_tx(res_bar(ew, 0), 2 * SM::EPI_BUF);
+                    tma_load_2d(res_base, &tmR, res_bar(ew, 0), n0 + h * 32, row0);
+                    tma_load_2d(res_base + SM::EPI_BUF, &tmR, res_bar(ew, 0), sp.lo_col + n0 + h * 32, row0);
+                }
+            } else if (has_res && lane == 0) {          // this warp's first TC_NBUF residual chunks of the tile
 #pragma unroll
                 for (int b = 0; b < TC_NBUF && h + 2 * b < NCH; ++b) {
                     mbar_arrive_expect_tx(res_bar(ew, b), SM::EPI_BUF);
@@ -721,12 +758,116 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 #endif
             };
 
+            // ---- split-fp16 epilogue: true value = acc * acc_scale + bias (+ (r_hi + r_lo) * res_scale), ReLU; stored as the fp16
+            // pair (hi, lo) of value * out_scale into columns [col, col + 32) and [lo_col + col, ...) of the output buffer ----
+            bool bad = false;                     // a stored value left the fp16 range
+            auto process_split = [&](const uint32_t* v, int c) {
+                const int col = n0 + c * 32;
+                float4 bv[8];
+                if (bias) {
+                    const float4* b4 = reinterpret_cast<const float4*>(bias + col);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) bv[g] = __ldg(b4 + g);
+                } else {
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) bv[g] = make_float4(0.f, 0.f, 0.f, 0.f);
+                }
+                float4 wv[FUSE_OUT ? 8 : 1];
+                if (FUSE_OUT) {
+                    const float4* w4 = reinterpret_cast<const float4*>(wout + col);
+#pragma unroll
+                    for (int g = 0; g < 8; ++g) wv[g] = __ldg(w4 + g);
+                }
+                if (has_res) {
+                    mbar_wait(res_bar(ew, 0), rphase & 1u);
+                    rphase ^= 1u;
+                }
+                if (OUT_MODE == 0) {              // the two TMA stores of the previous chunk have read the staging buffers
+                    if (lane == 0) asm volatile("cp.async.bulk.wait_group.read 0;" ::: "memory");
+                    __syncwarp();
+                }
+                const uint8_t* rrow = res_ptr + lane * 64;
+                uint8_t* crow = epi_ptr + lane * 64;
+                const float as = sp.acc_scale, rs = sp.res_scale, os = sp.out_scale;
+#pragma unroll
+                for (int g = 0; g < 4; ++g) {
+                    float f[8];
+                    const float4 ba = bv[2 * g], bb = bv[2 * g + 1];
+                    f[0] = fmaf(__uint_as_float(v[8 * g + 0]), as, ba.x); f[1] = fmaf(__uint_as_float(v[8 * g + 1]), as, ba.y);
+                    f[2] = fmaf(__uint_as_float(v[8 * g + 2]), as, ba.z); f[3] = fmaf(__uint_as_float(v[8 * g + 3]), as, ba.w);
+                    f[4] = fmaf(__uint_as_float(v[8 * g + 4]), as, bb.x); f[5] = fmaf(__uint_as_float(v[8 * g + 5]), as, bb.y);
+                    f[6] = fmaf(__uint_as_float(v[8 * g + 6]), as, bb.z); f[7] = fmaf(__uint_as_float(v[8 * g + 7]), as, bb.w);
+                    const uint32_t pos = ((uint32_t)g ^ sw) << 4;
+                    if (has_res) {
+                        const uint4 rh = *reinterpret_cast<const uint4*>(rrow + pos);
+                        const uint4 rl = *reinterpret_cast<const uint4*>(rrow + SM::EPI_BUF + pos);
+                        const __half2* hh = reinterpret_cast<const __half2*>(&rh);
+                        const __half2* hl = reinterpret_cast<const __half2*>(&rl);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float2 a = __half22float2(hh[e]), b = __half22float2(hl[e]);
+                            f[2 * e] += (a.x + b.x) * rs; f[2 * e + 1] += (a.y + b.y) * rs;
+                        }
+                    }
+                    if (relu) {
+#pragma unroll
+                        for (int e = 0; e < 8; ++e) f[e] = fmaxf(f[e], 0.f);
+                    }
+                    if (Q_OUT) {
+                        if (row0 + lane < M) {
+#pragma unroll
+                            for (int e = 0; e < 8; ++e)
+                                if (8 * g + e < qdim) {
+                                    hmin = fminf(hmin, f[e]);
+                                    partial[orow * (size_t)qdim + (size_t)(8 * g + e)] = f[e];
+                                }
+                        }
+                    } else if (FUSE_OUT) {
+                        const float4 wa = wv[FUSE_OUT ? 2 * g : 0], wb = wv[FUSE_OUT ? 2 * g + 1 : 0];
+                        oacc = fmaf(f[0], wa.x, oacc); oacc = fmaf(f[1], wa.y, oacc);
+                        oacc = fmaf(f[2], wa.z, oacc); oacc = fmaf(f[3], wa.w, oacc);
+                        oacc = fmaf(f[4], wb.x, oacc); oacc = fmaf(f[5], wb.y, oacc);
+                        oacc = fmaf(f[6], wb.z, oacc); oacc = fmaf(f[7], wb.w, oacc);
+                    } else {
+                        uint4 oh, ol;
+                        __half2* ph2 = reinterpret_cast<__half2*>(&oh);
+                        __half2* pl2 = reinterpret_cast<__half2*>(&ol);
+#pragma unroll
+                        for (int e = 0; e < 4; ++e) {
+                            const float x0 = f[2 * e] * os, x1 = f[2 * e + 1] * os;
+                            bad = bad || fabsf(x0) > 65000.f || fabsf(x1) > 65000.f;
+                            const __half2 hi = __floats2half2_rn(x0, x1);
+                            const float2 hf = __half22float2(hi);
+                            ph2[e] = hi;
+                            pl2[e] = __floats2half2_rn(x0 - hf.x, x1 - hf.y);
+                        }
+                        *reinterpret_cast<uint4*>(crow + pos) = oh;
+                        *reinterpret_cast<uint4*>(crow + SM::EPI_BUF + pos) = ol;
+                    }
+                }
+                if (OUT_MODE == 0) asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                __syncwarp();
+                if (lane == 0) {
+                    if (OUT_MODE == 0) {
+                        tma_store_2d(&tmC, epi_base, col, row0);
+                        tma_store_2d(&tmC, epi_base + SM::EPI_BUF, sp.lo_col + col, row0);
+                        asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+                    }
+                    if (has_res && c + 2 < NCH) {            // all lanes are past their reads of the residual buffers
+                        mbar_arrive_expect_tx(res_bar(ew, 0), 2 * SM::EPI_BUF);
+                        tma_load_2d(res_base, &tmR, res_bar(ew, 0), n0 + (c + 2) * 32, row0);
+                        tma_load_2d(res_base + SM::EPI_BUF, &tmR, res_bar(ew, 0), sp.lo_col + n0 + (c + 2) * 32, row0);
+                    }
+                }
+            };
+#define TC_PROCESS(v, c) do { if (SPLIT) process_split(v, c); else process(v, c); } while (0)
+
             uint32_t va[32], vb[32];
             if (Q_OUT) {                                   // the q-values live in the first 32 columns: one chunk, by the h = 0 warps
                 if (h == 0) {
                     tmem_ld32(t_row, va);
                     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                    process(va, 0);
+                    TC_PROCESS(va, 0);
                     if (out_h && row0 + lane < M) out_h[orow] = hmin;
                 }
             } else {
@@ -735,14 +876,16 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             for (int c = h; c < NCH; c += 4) {
                 { TC_T0(); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); TC_ACC(w_ld); }
                 if (c + 2 < NCH) tmem_ld32(t_row + (uint32_t)((c + 2) * 32), vb);
-                process(va, c);
+                TC_PROCESS(va, c);
                 if (c + 2 < NCH) {
                     { TC_T0(); asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); TC_ACC(w_ld); }
                     if (c + 4 < NCH) tmem_ld32(t_row + (uint32_t)((c + 4) * 32), va);
-                    process(vb, c + 2);
+                    TC_PROCESS(vb, c + 2);
                 }
             }
             }
+#undef TC_PROCESS
+            if (SPLIT && __any_sync(0xffffffffu, bad) && lane == 0) atomicOr(const_cast<uint32_t*>(&ctl->error), DX_DEVERR_NUMERIC);
             if (FUSE_OUT && row0 + lane < M) partial[(size_t)((n0 / BN) * 2 + h) * (size_t)pstride + (size_t)(row0 + lane)] = oacc;
             asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
             __syncwarp();
@@ -779,10 +922,12 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
 // bf16 one-hot input matrix [n, in_dim_p] (OneHot.forward, deepxube/pytorch/pytorch_models.py:15-24)
 // ones_col >= 0: columns ones_col .. ones_col + 2 are set to 1.0 (they multiply the folded bias columns of W0)
 // act_depth > 0 (heurq_in): row r is node r / act_depth with action r % act_depth; column act_col0 + action is 1.0
+// f16 != 0: the matrix is fp16 (split-fp16 mode) -- 1.0 = 0x3C00 instead of bf16's 0x3F80
 __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p, int ones_col, int act_depth, int act_col0,
                               const Ctl* __restrict__ ctl, const uint8_t* __restrict__ rows, const uint8_t* __restrict__ goals,
-                              __nv_bfloat16* __restrict__ out) {
+                              __nv_bfloat16* __restrict__ out, int f16) {
     if (ctl->error) return;
+    const uint32_t one_lo = f16 ? 0x00003C00u : 0x00003F80u, one_hi = one_lo << 16;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     const int chunks = in_dim_p / 8;
     const size_t total = (size_t)n * chunks;
@@ -794,7 +939,7 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
         uint32_t w[4] = {0u, 0u, 0u, 0u};
         if (act_depth > 0) {
             const int f = act_col0 + (int)(r % (uint32_t)act_depth) - c0;
-            if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;
+            if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? one_hi : one_lo;
         }
         const int i_lo = c0 / depth, i_hi = min(in_count - 1, (c0 + 7) / depth);
         for (int i = i_lo; i <= i_hi; ++i) {
@@ -806,19 +951,20 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
             }
             if (depth == 1) {                       // OneHot with depth 1 is x.float(): feature i = the value (exact in bf16 up to 256)
                 const int f = i - c0;
-                const uint32_t bits = (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)v));
+                const uint32_t bits = f16 ? (uint32_t)__half_as_ushort(__float2half_rn((float)v))
+                                          : (uint32_t)__bfloat16_as_ushort(__float2bfloat16_rn((float)v));
                 w[f >> 1] |= (f & 1) ? (bits << 16) : bits;
                 continue;
             }
             v = min(v, depth - 1);
             const int f = i * depth + v - c0;
-            if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;   // bf16 1.0 = 0x3F80
+            if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? one_hi : one_lo;   // bf16 1.0 = 0x3F80
         }
         if (ones_col >= 0) {
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
                 const int f = ones_col + j - c0;
-                if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? 0x3F800000u : 0x00003F80u;
+                if (f >= 0 && f < 8) w[f >> 1] |= (f & 1) ? one_hi : one_lo;
             }
         }
         reinterpret_cast<uint4*>(out + (size_t)r * in_dim_p)[c0 / 8] = make_uint4(w[0], w[1], w[2], w[3]);
@@ -921,6 +1067,71 @@ bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d) {
            4096 + 2 * TC_BM * d.SP + 512 <= TC_EPI_WARPS * TC_NBUF * 32 * 64;
 }
 
+// Shapes the fp32-accurate tensor-core path covers: at least one residual block (the scalar output layer is folded into the
+// last hidden GEMM) and, for multi-output networks, out_dim <= 32 (one 128-wide n-tile).  DXB200_FP32_TC=0 keeps NET_FP32 on
+// the CUDA-core SGEMM path (A/B runs; also the fallback for every other shape).
+bool dx_mlp_split_supported(const NetDev& net) {
+    if (const char* c = getenv("DXB200_FP32_TC")) if (c[0] == '0') return false;
+    if (net.num_blocks < 1 || 2 * net.num_blocks > 128 || net.in_dim_p > 4096) return false;
+    return net.out_dim == 1 || net.out_dim <= 32;
+}
+
+static float split_scale(const float* w, size_t n) {
+    float m = 0.f;
+    for (size_t i = 0; i < n; ++i) m = fmaxf(m, fabsf(w[i]));
+    if (!(m > 0.f) || !std::isfinite(m)) return 1.f;
+    int e = 0;
+    frexpf(m, &e);                          // m = f * 2^e, f in [0.5, 1)  ->  m * 2^(14 - e) in [2^13, 2^14)
+    return ldexpf(1.f, 14 - e);
+}
+
+// rows x K fp32 (row stride ld) -> rows x [hi(K) | lo(K)] fp16 of w * scale
+static void split_rows(const float* w, size_t rows, size_t K, size_t ld, float scale, uint16_t* out) {
+    for (size_t r = 0; r < rows; ++r)
+        for (size_t k = 0; k < K; ++k) {
+            const float x = w[r * ld + k] * scale;
+            const __half hi = __float2half_rn(x);
+            const __half lo = __float2half_rn(x - __half2float(hi));
+            out[r * 2 * K + k] = __half_as_ushort(hi);
+            out[r * 2 * K + K + k] = __half_as_ushort(lo);
+        }
+}
+
+// (Re)builds the split-fp16 parameter copies from the host fp32 parameters (BN folded, padded).  The first call allocates;
+// later calls (dx_load_weights again) overwrite in place.
+int dx_mlp_split_upload(cudaStream_t s, NetDev& net, const float* w0p, const float* wres, const float* wout) {
+    TcSplitW* sw = (TcSplitW*)net.tc_split;
+    const size_t Hp = net.Hp, Kin = net.in_dim_p, L = (size_t)2 * net.num_blocks;
+    const bool multi = net.out_dim > 1;
+    if (!sw) {
+        sw = new TcSplitW();
+        memset(sw, 0, sizeof(*sw));
+        DX_CUDA(cudaMalloc(&sw->w0, Hp * 2 * Kin * 2));
+        DX_CUDA(cudaMalloc(&sw->wres, L * Hp * 2 * Hp * 2));
+        if (multi) DX_CUDA(cudaMalloc(&sw->wout, (size_t)128 * 2 * Hp * 2));
+        net.tc_split = sw;
+    }
+    std::vector<uint16_t> buf(std::max(std::max(Hp * 2 * Kin, L * Hp * 2 * Hp), (size_t)128 * 2 * Hp));
+    sw->s_in = split_scale(w0p, Hp * Kin);
+    split_rows(w0p, Hp, Kin, Kin, sw->s_in, buf.data());
+    DX_CUDA(cudaMemcpyAsync(sw->w0, buf.data(), Hp * 2 * Kin * 2, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaStreamSynchronize(s));
+    for (size_t l = 0; l < L; ++l) {
+        sw->s_res[l] = split_scale(wres + l * Hp * Hp, Hp * Hp);
+        split_rows(wres + l * Hp * Hp, Hp, Hp, Hp, sw->s_res[l], buf.data() + l * Hp * 2 * Hp);
+    }
+    DX_CUDA(cudaMemcpyAsync(sw->wres, buf.data(), L * Hp * 2 * Hp * 2, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaStreamSynchronize(s));
+    if (multi) {
+        std::fill(buf.begin(), buf.begin() + (size_t)128 * 2 * Hp, (uint16_t)0);
+        sw->s_out = split_scale(wout, (size_t)net.out_dim * Hp);
+        split_rows(wout, (size_t)net.out_dim, Hp, Hp, sw->s_out, buf.data());
+        DX_CUDA(cudaMemcpyAsync(sw->wout, buf.data(), (size_t)128 * 2 * Hp * 2, cudaMemcpyHostToDevice, s));
+        DX_CUDA(cudaStreamSynchronize(s));
+    }
+    return DX_OK;
+}
+
 // Called once after the weights and activation buffers exist.  Returns a heap TcPlan in *plan_out.
 // onehot_buf may be nullptr when dx_mlp_bf16_gen_input() holds (gen_input then tells the launcher).
 int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out) {
@@ -948,25 +1159,30 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     if (const char* c = getenv("DXB200_FUSE_OUT")) p->fuse_out = (c[0] == '0') ? 0 : 1;
     p->fuse_in = gen_input ? 1 : 0;
     p->onehot = (__nv_bfloat16*)onehot_buf;
+    const TcSplitW* sw = (const TcSplitW*)net.tc_split;
+    p->split = sw ? 1 : 0;
+    if (sw) { p->CL = 2; p->fuse_out = 1; p->fuse_in = 0; }
+    const uint64_t xp = sw ? 2 : 1;               // pitch multiplier: split buffers hold [hi | lo]
     int dev = 0;
     cudaGetDevice(&dev);
     cudaDeviceGetAttribute(&p->num_sms, cudaDevAttrMultiProcessorCount, dev);
     // (with a generated input the A map of the first launch is never read: any valid map will do)
     int rc = onehot_buf ? make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM)
                         : make_map(enc, &p->a_onehot, mb.xb[0], net.Hp, (uint64_t)mb.cap, TC_BM);
-    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM);
-    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_xh[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, TC_BM / 2);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_xh[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM / 2);
     for (int i = 0; i < 3 && rc == DX_OK; ++i)
-        rc = make_map(enc, &p->c_x[i], mb.xb[i], net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        rc = make_map(enc, &p->c_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
     const int pair = p->CL >= 2 ? 2 : 1;
-    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, net.w0_bf16, net.in_dim_p, net.Hp, p->BN / pair);
+    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, sw ? sw->w0 : net.w0_bf16, xp * net.in_dim_p, net.Hp, p->BN / pair);
     if (rc == DX_OK && net.num_blocks > 0)
-        rc = make_map(enc, &p->b_res, net.wres_bf16, net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / pair);
+        rc = make_map(enc, &p->b_res, sw ? sw->wres : net.wres_bf16, xp * net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / pair);
     p->q_out = 0;
-    if (rc == DX_OK && net.wout_bf16) {
+    void* wout_tc = sw ? sw->wout : net.wout_bf16;
+    if (rc == DX_OK && wout_tc) {
         const char* c = getenv("DXB200_QOUT");
-        p->q_out = (c && c[0] == '0') ? 0 : 1;
-        rc = make_map(enc, &p->b_out, net.wout_bf16, net.Hp, 128, 128 / pair);
+        p->q_out = (sw || !(c && c[0] == '0')) ? 1 : 0;
+        rc = make_map(enc, &p->b_out, wout_tc, xp * net.Hp, 128, 128 / pair);
     }
     if (rc == DX_OK) {
         cudaError_t ce = cudaSuccess;
@@ -989,6 +1205,11 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
         set_attr((const void*)k_gemm_bf16_tc<128, 2, 2, false>, TcSmem<128, 2>::TOTAL);
         set_attr((const void*)k_gemm_bf16_tc<256, 4, 0, false>, TcSmem<256, 4>::TOTAL);
         set_attr((const void*)k_gemm_bf16_tc<256, 4, 1, false>, TcSmem<256, 4>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, 0, false, true>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<256, 2, 1, false, true>, TcSmem<256, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 0, false, true>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 1, false, true>, TcSmem<128, 2>::TOTAL);
+        set_attr((const void*)k_gemm_bf16_tc<128, 2, 2, false, true>, TcSmem<128, 2>::TOTAL);
         if (ce == cudaSuccess && p->CL == 4) {
             // clusters of 4 do not fill every GPC: launch exactly as many as can be co-resident (persistent tiles)
             cudaLaunchConfig_t cfg = {};
@@ -1019,14 +1240,15 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
 
 struct TcQOut { float* out_h; int qdim; int absolute; };       // Q_OUT launches: where the fp32 q-values / minima go
 
-template <int BN, int CL, int MODE, bool GEN>
+template <int BN, int CL, int MODE, bool GEN, bool SPLIT = false>
 static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const CUtensorMap& b, const CUtensorMap& tc,
                           const CUtensorMap& tr, const Ctl* ctl, int w_row0, int K, int N, const float* bias, int has_res,
-                          int relu, const float* wout, float* partial, long long pstride, const TcGen& gen, const TcQOut& qo) {
+                          int relu, const float* wout, float* partial, long long pstride, const TcGen& gen, const TcQOut& qo,
+                          const TcSplit& sp) {
     cfg->dynamicSmemBytes = TcSmem<BN, CL>::TOTAL;
     cfg->blockDim = dim3(GEN ? TC_THREADS_GEN : TC_THREADS);
-    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, MODE, GEN>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
-                       pstride, gen, qo.out_h, qo.qdim, qo.absolute);
+    cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, MODE, GEN, SPLIT>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
+                       pstride, gen, qo.out_h, qo.qdim, qo.absolute, sp);
 }
 
 // c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
@@ -1035,7 +1257,8 @@ static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const C
 // cl: CTAs per cluster of this launch
 static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorMap& a, const CUtensorMap& b, const Ctl* ctl, int w_row0,
                         int K, int N, const float* bias, int r, int c, int relu, const float* wout = nullptr,
-                        float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr, const TcQOut* qo = nullptr) {
+                        float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr, const TcQOut* qo = nullptr,
+                        const TcSplit* split = nullptr) {
     const CUtensorMap& tc = p->c_x[c];
     const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
     cudaLaunchConfig_t cfg = {};
@@ -1062,10 +1285,17 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorM
     const TcGen g = gen ? *gen : TcGen{};
     const TcQOut q = qo ? *qo : TcQOut{nullptr, 0, 0};
     const bool big = p->BN == 256, fuse = partial != nullptr;
-#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g, q
+    TcSplit sp = {};
+    sp.nph = 1;
+    if (split) sp = *split;
+#define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g, q, sp
 #define DX_TC_PICK(CLV, MODEV, GENV) do { if (big) launch_gemm_t<256, CLV, MODEV, GENV>(DX_TC_ARGS); \
                                           else launch_gemm_t<128, CLV, MODEV, GENV>(DX_TC_ARGS); } while (0)
-    if (qo) {
+    if (split) {                       // fp32-accurate mode: CTA pairs, TMA-fed A, (hi, lo) epilogue
+        if (qo) launch_gemm_t<128, 2, 2, false, true>(DX_TC_ARGS);
+        else if (fuse) { if (big) launch_gemm_t<256, 2, 1, false, true>(DX_TC_ARGS); else launch_gemm_t<128, 2, 1, false, true>(DX_TC_ARGS); }
+        else { if (big) launch_gemm_t<256, 2, 0, false, true>(DX_TC_ARGS); else launch_gemm_t<128, 2, 0, false, true>(DX_TC_ARGS); }
+    } else if (qo) {
         if (cl == 2) launch_gemm_t<128, 2, 2, false>(DX_TC_ARGS); else launch_gemm_t<128, 1, 2, false>(DX_TC_ARGS);
     } else if (gen) {
         if (cl == 2) DX_TC_PICK(2, 0, true); else DX_TC_PICK(1, 0, true);
@@ -1100,6 +1330,61 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const float* bias0 = (net.tc_fold & 2) ? nullptr : (fold_h ? net.b0_tc : net.b0);
     const int ones_col = (net.tc_fold & 2) ? net.in_dim : -1;
     const int kv_in = net.in_dim_p, kv_h = Hp, nv = Hp;      // padded shapes (trimming the padding measured no gain)
+    if (p->split) {
+        // ---- fp32-accurate mode: fp16 (hi, lo) operands, 2 (input layer: the one-hot A is exact) / 3 MMA passes per layer ----
+        const TcSplitW* sw = (const TcSplitW*)net.tc_split;
+        const float t = TC_ACT_SCALE;
+        auto mk = [&](int nph, int a1, int w0c, float wscale, bool a_scaled) {
+            TcSplit sp = {};
+            sp.nph = nph;
+            // small terms first: A_hi.W_lo, A_lo.W_hi, then A_hi.W_hi (input layer: A.W_lo, A.W_hi)
+            sp.a_col[0] = 0;   sp.w_col[0] = w0c;
+            sp.a_col[1] = a1;  sp.w_col[1] = 0;
+            sp.a_col[2] = 0;   sp.w_col[2] = 0;
+            sp.acc_scale = 1.0f / (wscale * (a_scaled ? t : 1.0f));
+            sp.res_scale = 1.0f / t;
+            sp.out_scale = t;
+            sp.lo_col = Hp;
+            sp.f16 = 1;
+            return sp;
+        };
+        dx_prof_begin(DX_ST_GEMM_IN);
+        k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, -1, net.act_depth,
+                                                net.in_dim - net.act_depth, ctl, rows, goals, p->onehot, 1);
+        {
+            const TcSplit sp = mk(2, 0, net.in_dim_p, sw->s_in, false);
+            launch_gemm(s, p, 2, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, net.b0, -1, ix, 0, nullptr, nullptr, 0, nullptr, nullptr, &sp);
+        }
+        launches += 2;
+        dx_prof_end();
+        const bool fuse_s = net.out_dim == 1 && net.num_blocks > 0;
+        dx_prof_begin(DX_ST_GEMM_RES);
+        for (int b = 0; b < net.num_blocks; ++b) {
+            const TcSplit s1 = mk(3, Hp, Hp, sw->s_res[2 * b], true), s2 = mk(3, Hp, Hp, sw->s_res[2 * b + 1], true);
+            launch_gemm(s, p, 2, p->a_x[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, net.bres + (size_t)(2 * b) * Hp, -1, iy, 1,
+                        nullptr, nullptr, 0, nullptr, nullptr, &s1);
+            if (fuse_s && b == net.num_blocks - 1)
+                launch_gemm(s, p, 2, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+                            net.wout, (float*)mb.xb[iz], mb.cap, nullptr, nullptr, &s2);
+            else
+                launch_gemm(s, p, 2, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
+                            nullptr, nullptr, 0, nullptr, nullptr, &s2);
+            launches += 2;
+            int ti = ix; ix = iz; iz = ti;
+        }
+        dx_prof_end();
+        if (fuse_s) {
+            const int blocks = (int)min((long long)dx_div_up(max_rows, 256), (long long)148 * 8);
+            k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, (const float*)mb.xb[ix], mb.cap, 2 * (Hp / p->BN), out_h, out_q, absolute);
+        } else {                          // multi-output layer (dx_mlp_split_supported guarantees out_dim <= 32 here)
+            TcQOut qo{out_h, net.out_dim, absolute};
+            const TcSplit so = mk(3, Hp, Hp, sw->s_out, true);
+            launch_gemm(s, p, 2, p->a_x[ix], p->b_out, ctl, 0, Hp, 128, net.bout_pad, -1, iz, 1, nullptr, out_q, 0, nullptr, &qo, &so);
+        }
+        ++launches;
+        launches += dx_launch_act_end(s, net, const_cast<Ctl*>(ctl), q_dst, h_dst, absolute, max_nodes);
+        return launches;
+    }
     dx_prof_begin(DX_ST_GEMM_IN);
     if (p->fuse_in && p->CL_in == 2) {
         // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
@@ -1109,7 +1394,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         ++launches;
     } else {
         k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, net.act_depth,
-                                                net.in_dim - net.act_depth, ctl, rows, goals, p->onehot);
+                                                net.in_dim - net.act_depth, ctl, rows, goals, p->onehot, 0);
         launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0);
         launches += 2;
     }

@@ -88,18 +88,19 @@ def resnet_fc_forward(sd: Dict[str, torch.Tensor], x_int: np.ndarray, one_hot_de
     nb, bn = num_blocks_of(sd), has_bn(sd)
     n = x_int.shape[0]
     outs = []
+    dt = sd["heur.0.weight"].dtype           # float32 like the reference; a float64 state_dict gives a float64 yardstick
     step = n if not batch_size else batch_size
     for s in range(0, max(n, 1), max(step, 1)):
         xi = torch.as_tensor(np.ascontiguousarray(x_int[s:s + step]))
         xa = None
         if act_depth > 0:
-            xa = F.one_hot(xi[:, -1].long(), act_depth).float()
+            xa = F.one_hot(xi[:, -1].long(), act_depth).to(dt)
             xi = xi[:, :-1]
         if one_hot_depth > 1:
-            x = F.one_hot(xi.long(), one_hot_depth).float()
+            x = F.one_hot(xi.long(), one_hot_depth).to(dt)
             x = x.reshape(x.shape[0], -1)
         else:
-            x = xi.float()
+            x = xi.to(dt)
         if xa is not None:
             x = torch.cat([x, xa], dim=1)
         x = F.linear(x, sd["heur.0.weight"], sd["heur.0.bias"])

@@ -27,6 +27,15 @@ def _scrambles(dom, n, k, seed):
     return st, goals
 
 
+def _spread_net(in_dim, h, nb, od, seed):
+    """random-BN resnet_fc whose outputs are spread over positive values (a plain random init mostly lands below zero,
+    where process_outputs clips everything to 0 and two different networks look identical)"""
+    sd = {k: v.numpy().copy() for k, v in random_state_dict(in_dim, h, nb, od, True, seed=seed, randomize_bn=True).items()}
+    sd["heur.2.weight"] *= 12.0
+    sd["heur.2.bias"] = sd["heur.2.bias"] * 12.0 + 4.0
+    return sd
+
+
 def _compare_iteration(t, eng, oi):
     for j, (o, s) in enumerate(zip(oi, eng.status())):
         ids = o.nodes_curr
@@ -55,8 +64,7 @@ def test_in_graph_network_engine_vs_oracle_fed_the_engines_h(mode_name, algo, n,
     st, goals = _scrambles(dom, n, 150, 31)
     b, w = 10000, 0.6
     od = 12 if is_q else 1
-    sd = random_state_dict(324, 1000, 4, od, True, seed=2, randomize_bn=True)
-    blob, _ = L.pack_state_dict({k: v.numpy() for k, v in sd.items()})
+    blob, _ = L.pack_state_dict(_spread_net(324, 1000, 4, od, 2))
     mode = L.DX_HEUR_NET_BF16 if mode_name == "bf16" else L.DX_HEUR_NET_FP32
     eng = L.Engine("cube3", 0, algo, mode, max_instances=n, max_pop_total=n * b, max_nodes=n * b * (1 if is_q else 12) * (iters + 1) + 1024)
     eng.load_weights(54, 6, 1000, 4, od, True, blob)
@@ -67,6 +75,7 @@ def test_in_graph_network_engine_vs_oracle_fed_the_engines_h(mode_name, algo, n,
         out = ev.heur_eval(s, None, od)
         return out.astype(np.float64) if is_q else out[:, 0].astype(np.float64)
 
+    assert (heur(st, goals) > 0).mean() > 0.5, "network values must not be clipped away (the search would be breadth-first)"
     orc = OracleSearch(dom, heur, is_q, b, w)
     oi = orc.add_instances(st, goals)
     eng.add_instances(st, goals, b, w)
@@ -118,8 +127,7 @@ def test_weights_can_be_reloaded_in_place(mode_name):
     dom = OracleDomain("cube3")
     mode = L.DX_HEUR_NET_BF16 if mode_name == "bf16" else L.DX_HEUR_NET_FP32
     st, goals = _scrambles(dom, 3, 40, 5)
-    blobs = [L.pack_state_dict({k: v.numpy() for k, v in random_state_dict(324, 256, 2, 1, True, seed=s, randomize_bn=True).items()})[0]
-             for s in (1, 2)]
+    blobs = [L.pack_state_dict(_spread_net(324, 256, 2, 1, s))[0] for s in (1, 2)]
 
     def fresh(blob):
         e = L.Engine("cube3", 0, "graph_v", mode, max_instances=3, max_pop_total=600, max_nodes=200000)
@@ -156,7 +164,7 @@ def test_host_mirror_reuploads_changed_weights():
     from deepxube_b200.factories.pathfind_fns_factory import get_path_fns_nnet_par_dict
     from deepxube_b200.factories.pathfinding_factory import get_pathfind_from_arg
     domain, dname = get_domain_from_arg("cube3")
-    sds = [{k: v.numpy() for k, v in random_state_dict(324, 128, 1, 1, True, seed=s, randomize_bn=True).items()} for s in (3, 4)]
+    sds = [_spread_net(324, 128, 1, 1, s) for s in (3, 4)]
     states, goals = domain.sample_problem_instances([20, 25, 30])
 
     def run(pf):
@@ -309,7 +317,7 @@ def test_one_hot_inputs_out_of_range_are_rejected():
     """F.one_hot raises in the reference when a value is >= the depth (pytorch_models.py:15-24); the C ABI refuses such rows
     instead of clamping them on the device."""
     L = _lib()
-    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_FP32, max_instances=1, max_pop_total=16, max_nodes=1024)
+    eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_FP32, max_instances=2, max_pop_total=16, max_nodes=1024)
     blob, _ = L.pack_state_dict({k: v.numpy() for k, v in random_state_dict(324, 128, 1, 1, True, seed=1).items()})
     eng.load_weights(54, 6, 128, 1, 1, True, blob)
     bad = np.zeros((2, 54), np.uint8)

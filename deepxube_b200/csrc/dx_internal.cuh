@@ -244,6 +244,14 @@ struct SortBufs {
     uint32_t* hist;       // [256 * max_tiles (+ slack)]
     uint32_t* ghist;      // [DX_NUM_DIGITS * 256] global digit histograms of the batch
     uint32_t* gbase;      // [DX_NUM_DIGITS * 256] exclusive bin offsets per digit position
+    // one-sweep passes (decoupled look-back): per (tile, digit value) a 64-bit word (epoch << 32 | flag << 30 | count),
+    // valid only while its epoch equals the pass's -- never needs clearing; tickets[d] hands out tile ids in launch order
+    unsigned long long* status;   // [max_tiles * 256]
+    uint32_t* tickets;            // [DX_NUM_DIGITS] + [DX_NUM_DIGITS]: the sort counter behind the epochs (survives engine resets:
+                                  // the status words of earlier searches must never match again)
+    uint32_t* part_a;             // [merge tiles + 1] merge-path partition of every merge tile (k_merge_partition)
+    uint32_t* part_i;             // [merge tiles + 1] ... and its instance
+    int onesweep;                 // 1: one kernel per digit pass; 0 (DXB200_SORT_ONESWEEP=0): histogram / tile scan / scatter
     int max_tiles;
     int num_digits;       // digit positions that can vary: 8 key bytes + the bytes max_instances - 1 occupies
 };

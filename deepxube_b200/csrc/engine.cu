@@ -523,6 +523,15 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->sort.num_digits = 8;
     for (uint32_t m = (uint32_t)(e->max_inst - 1); m && e->sort.num_digits < DX_NUM_DIGITS; m >>= 8) e->sort.num_digits += 1;
     A_(e->sort.hist, (size_t)256 * e->sort.max_tiles + 4096); A_(e->sort.ghist, DX_NUM_DIGITS * 256); A_(e->sort.gbase, DX_NUM_DIGITS * 256);
+    A_(e->sort.status, (size_t)256 * e->sort.max_tiles + 256); A_(e->sort.tickets, DX_NUM_DIGITS + 4);
+    cudaMemset(e->sort.status, 0, ((size_t)256 * e->sort.max_tiles + 256) * sizeof(unsigned long long));
+    cudaMemset(e->sort.tickets, 0, (DX_NUM_DIGITS + 4) * sizeof(uint32_t));
+    {
+        const size_t mt = (size_t)dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst + 8;
+        A_(e->sort.part_a, mt); A_(e->sort.part_i, mt);
+    }
+    e->sort.onesweep = 1;
+    if (const char* c = getenv("DXB200_SORT_ONESWEEP")) e->sort.onesweep = (c[0] == '0') ? 0 : 1;
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
     A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);

@@ -200,6 +200,7 @@ __global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
             acc += c;
         }
     }
+    if (threadIdx.x < DX_NUM_DIGITS) sb.tickets[threadIdx.x] = 0;
     if (threadIdx.x == 0) {
         uint32_t src = 0;
         for (int d = 0; d < DX_NUM_DIGITS; ++d) {
@@ -208,6 +209,7 @@ __global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
             if (!s_skip[d]) src ^= 1u;
         }
         ctl->sort_final = src;
+        sb.tickets[DX_NUM_DIGITS] += 1;        // new tag for the look-back words of this sort's passes
     }
 }
 
@@ -331,6 +333,123 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
             okeys[pos] = key[r];
             oinsts[pos] = inst[r];
             ovals[pos] = val[r];
+        }
+    }
+}
+
+
+// One digit pass in ONE kernel (decoupled look-back, "onesweep"): a block takes the next tile in ticket order, ranks its
+// elements by digit (stable: warp w owns a contiguous eighth of the tile, rounds of 32, lanes in order), publishes the tile's
+// per-digit counts, and thread `dg` walks back over the preceding tiles' words of digit dg until it meets an inclusive
+// prefix -- replacing the per-tile histogram kernel, the 256-block tile scan and the scatter kernel (3 launches and two
+// extra reads of the batch per pass).  Words are tagged with the pass's epoch, so the status array is never cleared;
+// ticket order guarantees that every tile a block waits for has already been started by a resident (or finished) block.
+#define OS_FLAG_AGG 1ull
+#define OS_FLAG_PREFIX 2ull
+#define OS_ITEMS 16                       // elements per thread: tiles of 4096 (half as many look-back links as the merge tiles)
+#define OS_TILE (OPEN_THREADS * OS_ITEMS)
+#define OS_WINDOW 8                       // predecessor words fetched per round trip of the look-back
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
+    __shared__ uint32_t s_cnt[OPEN_THREADS / 32][256];
+    __shared__ uint32_t s_base[256];
+    __shared__ uint32_t s_tile;
+    if (ctl->error || ctl->pass_skip[d]) return;
+    const uint32_t n = ctl->sort_n;
+    const uint32_t ntiles = (n + OS_TILE - 1) / OS_TILE;
+    const uint32_t src = ctl->pass_src[d], dst = src ^ 1u;
+    const unsigned long long epoch = ((unsigned long long)(sb.tickets[DX_NUM_DIGITS] * (uint32_t)DX_NUM_DIGITS + (uint32_t)d + 1u)) << 32;
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const unsigned long long* __restrict__ keys = sb.key[src];
+    const uint32_t* __restrict__ insts = sb.inst[src];
+    const uint32_t* __restrict__ vals = sb.val[src];
+    unsigned long long* __restrict__ okeys = sb.key[dst];
+    uint32_t* __restrict__ oinsts = sb.inst[dst];
+    uint32_t* __restrict__ ovals = sb.val[dst];
+    for (;;) {
+        __syncthreads();
+        if (threadIdx.x == 0) s_tile = atomicAdd(&sb.tickets[d], 1u);
+        for (int i = threadIdx.x; i < (OPEN_THREADS / 32) * 256; i += OPEN_THREADS) (&s_cnt[0][0])[i] = 0;
+        __syncthreads();
+        const uint32_t tile = s_tile;
+        if (tile >= ntiles) return;
+        const uint32_t base = tile * OS_TILE;
+        unsigned long long key[OS_ITEMS];
+        uint32_t inst[OS_ITEMS], val[OS_ITEMS];
+        uint16_t rank[OS_ITEMS], dig[OS_ITEMS];
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const uint32_t e = base + warp * (32 * OS_ITEMS) + r * 32 + lane;
+            const bool valid = e < n;
+            key[r] = valid ? keys[e] : 0ull;
+            inst[r] = valid ? insts[e] : 0u;
+            val[r] = valid ? vals[e] : 0u;
+        }
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            const bool valid = base + warp * (32 * OS_ITEMS) + r * 32 + lane < n;
+            const uint32_t dg = valid ? digit_of(key[r], inst[r], d) : (256u + lane);
+            const uint32_t peers = __match_any_sync(0xffffffffu, dg);
+            const int leader = __ffs(peers) - 1;
+            const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = s_cnt[warp][dg];
+                s_cnt[warp][dg] = old + __popc(peers);
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            rank[r] = (uint16_t)(old + before);
+            dig[r] = (uint16_t)dg;
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // thread dg: this tile's count of digit dg, exclusive offsets over the warps, then the look-back
+            const uint32_t dg = threadIdx.x;
+            uint32_t acc = 0;
+#pragma unroll
+            for (int w = 0; w < OPEN_THREADS / 32; ++w) {
+                const uint32_t c = s_cnt[w][dg];
+                s_cnt[w][dg] = acc;
+                acc += c;
+            }
+            volatile unsigned long long* st = sb.status;
+            if (tile == 0) {
+                st[dg] = epoch | (OS_FLAG_PREFIX << 30) | acc;
+                s_base[dg] = sb.gbase[d * 256 + dg];
+            } else {
+                st[(size_t)tile * 256 + dg] = epoch | (OS_FLAG_AGG << 30) | acc;
+                uint32_t excl = 0;
+                int t = (int)tile - 1;
+                bool done = false;
+                uint32_t spins = 0;
+                while (!done) {
+                    // OS_WINDOW predecessor words per round trip (independent loads); consumed nearest first, stopping at the first
+                    // inclusive prefix; a word whose pass has not published yet ends the round and is polled again
+                    unsigned long long w[OS_WINDOW];
+#pragma unroll
+                    for (int j = 0; j < OS_WINDOW; ++j) w[j] = (t - j >= 0) ? st[(size_t)(t - j) * 256 + dg] : (epoch | (OS_FLAG_PREFIX << 30));
+#pragma unroll
+                    for (int j = 0; j < OS_WINDOW; ++j) {
+                        if (done || (w[j] & 0xFFFFFFFF00000000ull) != epoch) break;
+                        excl += (uint32_t)(w[j] & 0x3FFFFFFFull);
+                        --t;
+                        if (((w[j] >> 30) & 3ull) == OS_FLAG_PREFIX) done = true;
+                    }
+                    if (++spins > (1u << 24)) { atomicOr(&ctl->error, DX_DEVERR_POP); done = true; }   // protocol bug: fail, do not hang
+                }
+                st[(size_t)tile * 256 + dg] = epoch | (OS_FLAG_PREFIX << 30) | (excl + acc);
+                s_base[dg] = sb.gbase[d * 256 + dg] + excl;
+            }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < OS_ITEMS; ++r) {
+            if (dig[r] < 256u) {
+                const uint32_t pos = s_base[dig[r]] + s_cnt[warp][dig[r]] + rank[r];
+                okeys[pos] = key[r];
+                oinsts[pos] = inst[r];
+                ovals[pos] = val[r];
+            }
         }
     }
 }
@@ -483,6 +602,11 @@ int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp&
     k_radix_prepass<<<pre_blocks, OPEN_THREADS, 0, s>>>(ctl, sb);
     k_radix_flags<<<1, 256, 0, s>>>(ctl, sb);
     launches += 2;
+    if (sb.onesweep) {
+        const int blocks = min(dx_div_up(max_n, OS_TILE), 148 * 4);           // persistent over tiles (ticket order)
+        for (int d = 0; d < sb.num_digits; ++d) k_radix_onesweep<<<blocks, OPEN_THREADS, 0, s>>>(ctl, sb, d);
+        return launches + sb.num_digits;
+    }
     for (int d = 0; d < sb.num_digits; ++d) {      // higher instance-id bytes are constant zero: never launched
         k_radix_hist<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_tilescan<<<256, OPEN_THREADS, 0, s>>>(ctl, sb, d);
@@ -522,39 +646,53 @@ __device__ __forceinline__ uint32_t merge_path_warp(const unsigned long long* __
     return lo;
 }
 
+// Partition points of every merge tile, found up front by one warp per tile (a 32-ary search: 3-4 dependent global accesses):
+// part_a[T] = how many OPEN-run elements precede tile T's first output, part_i[T] = the tile's instance.  Inside k_merge
+// this search was a serial latency chain at the head of every tile, with 6 of the block's 8 warps idle.
+__global__ void __launch_bounds__(OPEN_THREADS)
+k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
+                  const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ part_a, uint32_t* __restrict__ part_i) {
+    if (ctl->error) return;
+    const uint32_t n_tiles = ctl->n_tiles;
+    const int I = ctl->n_inst;
+    const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
+    const uint32_t warps = gridDim.x * (OPEN_THREADS / 32);
+    for (uint32_t T = blockIdx.x * (OPEN_THREADS / 32) + (threadIdx.x >> 5); T < n_tiles; T += warps) {
+        int lo = 0, hi = I - 1;                 // instance of this tile: last i with tile_off[i] <= T
+        while (lo < hi) {
+            const int mid = (lo + hi + 1) >> 1;
+            if (ia.tile_off[mid] <= T) lo = mid; else hi = mid - 1;
+        }
+        const int i = lo;
+        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
+        const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
+        const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, d0);
+        if ((threadIdx.x & 31) == 0) { part_a[T] = part; part_i[T] = (uint32_t)i; }
+    }
+}
+
 __global__ void __launch_bounds__(OPEN_THREADS)
 k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
         const uint32_t* __restrict__ open_val_cur, const uint32_t* __restrict__ open_off_cur,
         unsigned long long* __restrict__ open_key_next, uint32_t* __restrict__ open_val_next,
         const uint32_t* __restrict__ open_off_next, uint32_t* __restrict__ popped_next, uint32_t* __restrict__ popped_inst_next,
-        const uint32_t* __restrict__ pop_off_next, int keep_open) {
+        const uint32_t* __restrict__ pop_off_next, int keep_open, const uint32_t* __restrict__ part_a,
+        const uint32_t* __restrict__ part_i) {
     __shared__ unsigned long long s_key[DX_SORT_TILE];
     __shared__ uint32_t s_val[DX_SORT_TILE];
     __shared__ uint32_t s_part[4];   // a0, a1, inst
     if (ctl->error) return;
     const uint32_t n_tiles = ctl->n_tiles;
-    const int I = ctl->n_inst;
     const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
     const uint32_t* __restrict__ bvals = sb.val[ctl->sort_final];
     for (uint32_t T = blockIdx.x; T < n_tiles; T += gridDim.x) {
         __syncthreads();
-        if (threadIdx.x < 64) {                 // warp 0: the tile's first diagonal, warp 1: its last
-            const int w = threadIdx.x >> 5;
-            // instance of this tile: last i with tile_off[i] <= T
-            int lo = 0, hi = I - 1;
-            while (lo < hi) {
-                const int mid = (lo + hi + 1) >> 1;
-                if (ia.tile_off[mid] <= T) lo = mid; else hi = mid - 1;
-            }
-            const int i = lo;
-            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
-            const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
-            const uint32_t diag = w == 0 ? d0 : min(d0 + DX_SORT_TILE, na + nb);
-            const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, diag);
-            if ((threadIdx.x & 31) == 0) {
-                s_part[w] = part;
-                if (w == 0) s_part[2] = i;
-            }
+        if (threadIdx.x == 0) {
+            const uint32_t i = part_i[T];
+            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i];
+            s_part[0] = part_a[T];
+            s_part[1] = (T + 1 < ia.tile_off[i + 1]) ? part_a[T + 1] : na;     // the instance's last tile ends at the end of its run
+            s_part[2] = i;
         }
         __syncthreads();
         const int i = s_part[2];
@@ -575,16 +713,31 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
         uint32_t pb = my0 - pa;
         const uint32_t k = ia.k_pop[i];
         const uint32_t pop_base = pop_off_next[i], open_base = open_off_next[i];
-        for (uint32_t o = my0; o < my1; ++o) {
+        // each thread merges its ITEMS consecutive outputs into registers ...
+        unsigned long long okey[ITEMS];
+        uint32_t oval[ITEMS];
+#pragma unroll
+        for (int o = 0; o < ITEMS; ++o) {
             bool take_a;
             if (pa >= ca) take_a = false;
             else if (pb >= cb) take_a = true;
             else take_a = s_key[pa] <= s_key[ca + pb];
-            const uint32_t idx = take_a ? pa : ca + pb;
-            const unsigned long long key = s_key[idx];
-            const uint32_t val = s_val[idx];
+            const uint32_t idx = min(take_a ? pa : ca + pb, (uint32_t)DX_SORT_TILE - 1);
+            okey[o] = s_key[idx];
+            oval[o] = s_val[idx];
             if (take_a) ++pa; else ++pb;
-            const uint32_t r = d0 + o;
+        }
+        __syncthreads();                           // every thread has read its inputs: the tile buffers can take the outputs
+#pragma unroll
+        for (int o = 0; o < ITEMS; ++o)
+            if (my0 + o < my1) { s_key[my0 + o] = okey[o]; s_val[my0 + o] = oval[o]; }
+        __syncthreads();
+        // ... and the tile is written out with consecutive threads on consecutive entries (a thread writing its own 8 outputs
+        // touches a different 32-byte sector per store: 4x / 8x write amplification on the key / value arrays)
+        for (uint32_t t = threadIdx.x; t < cnt; t += OPEN_THREADS) {
+            const uint32_t r = d0 + t;
+            const unsigned long long key = s_key[t];
+            const uint32_t val = s_val[t];
             if (r < k) {
                 popped_next[pop_base + r] = val;
                 popped_inst_next[pop_base + r] = i;
@@ -601,10 +754,12 @@ int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const 
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open) {
-    int blocks = min(max_tiles, 148 * 4);
+    int blocks = min(max_tiles, 148 * 8);      // 24.5 KB of shared memory and 256 threads per block: 8 blocks per SM
+    k_merge_partition<<<min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_off_cur,
+                                                                                                   sb.part_a, sb.part_i);
     k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
-                                            open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open);
-    return 1;
+                                            open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i);
+    return 2;
 }
 
 // ---------------------------------------------------------------------------------------------

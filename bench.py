@@ -396,13 +396,14 @@ def run_side_config(L, name: str, rank: int, world: int, local: int, steps: int,
         nodes += c.children_generated
         evals += c.heur_evals
     stage, calls = eng.stage_ms(), eng.stage_calls()
+    n_hidden = int(eng.counters().hidden_gemm_launches)        # H x H GEMM launches per evaluation inside the timed interval
     eng.set_profiling(1)
     one(warmup + steps)
     split = eng.stage_ms()
     open_total = int(sum(s.open_size for s in eng.status()))
     eng.set_profiling(0)
     eng.close()
-    hidden_flop = FLOP_PER_STATE_HIDDEN_LAYER * 2 * NB * evals
+    hidden_flop = FLOP_PER_STATE_HIDDEN_LAYER * n_hidden * evals
     gms = stage["gemm_hidden"]
     achieved = hidden_flop / (gms / 1e3) / 1e12 if gms > 0 else None
     peak = peaks["bf16_tflops_sustained"]
@@ -417,8 +418,8 @@ def run_side_config(L, name: str, rank: int, world: int, local: int, steps: int,
                         "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                         "frac": (achieved / peak) if achieved else None, "traffic": None,
                         "peak_source": peaks["_source"] + " (sustained bf16)",
-                        "launches_timed": int(calls["gemm_hidden"] * 2 * NB),
-                        "avg_launch_ms": gms / max(calls["gemm_hidden"] * 2 * NB, 1)},
+                        "launches_timed": int(calls["gemm_hidden"] * n_hidden),
+                        "avg_launch_ms": gms / max(calls["gemm_hidden"] * n_hidden, 1)},
            "stage_share_one_extra_step": {k: round(split[k] / tot, 4) for k in ("expand", "filt", "scatter", "heur", "sort", "pushpop", "book")} if tot > 0 else None,
            "stage_ms_one_extra_step": {k: round(v, 3) for k, v in split.items()}}
     if cpu and cpu_iters > 0:
@@ -575,6 +576,8 @@ def main() -> None:
     launches = eng.counters().kernel_launches - launches0
     stage = eng.stage_ms()
     calls = eng.stage_calls()
+    n_hidden = int(eng.counters().hidden_gemm_launches)   # H x H GEMM launches per network evaluation (7 of the 8 hidden layers when
+    #                                                       the first one is computed by the input-layer launch)
     # informational stage split: ONE extra step with every stage timed (outside both timed regions)
     eng.set_profiling(1)
     s, g = pick(args.warmup + args.steps)
@@ -658,7 +661,7 @@ def main() -> None:
         e2e_val = tot[1] / tmax[1]
         # roofline of the dominant kernel (hidden-layer tcgen05 GEMM, 8 launches per network evaluation):
         # algorithmic FLOPs of this rank's launches / their summed CUDA-event durations
-        hidden_flop = FLOP_PER_STATE_HIDDEN_LAYER * 2 * NB * evals
+        hidden_flop = FLOP_PER_STATE_HIDDEN_LAYER * n_hidden * evals
         achieved = hidden_flop / (stage["gemm_hidden"] / 1e3) / 1e12 if stage["gemm_hidden"] > 0 else None
         peak = peaks["bf16_tflops_sustained"]
         traffic, traffic_note = None, None
@@ -669,7 +672,7 @@ def main() -> None:
             traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture of a "
                             f"{tj['rows_in_launch']}-state launch (profiles/r1i_gemm_traffic.json); algorithmic bytes of that launch: "
                             f"{tj['algorithmic_bytes']['hidden']} (plain) / {tj['algorithmic_bytes']['hidden_residual']} (with residual)")
-        n_l = calls["gemm_hidden"] * 2 * NB
+        n_l = calls["gemm_hidden"] * n_hidden
         roof = {"kernel": "k_gemm_bf16_tc<256,2> (hidden layers, 1000x1000 per state)" if args.precision == "bf16"
                 else "k_gemm_bf16_tc<256,2,*,split> (hidden layers, fp16 hi/lo split: 3 MMAs per algorithmic MAC)",
                 "bound": "tensor", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",

@@ -51,7 +51,7 @@ class dx_hda_local(C.Structure):
 class dx_counters(C.Structure):
     _fields_ = [("nodes_stored", C.c_int64), ("heur_evals", C.c_int64), ("children_generated", C.c_int64),
                 ("iterations", C.c_int64), ("kernel_launches", C.c_int64), ("backups_logged", C.c_int64),
-                ("reserved", C.c_int64 * 2)]
+                ("hidden_gemm_launches", C.c_int64), ("reserved", C.c_int64 * 1)]
 
 
 _u8p = C.POINTER(C.c_uint8)

@@ -153,7 +153,13 @@ struct NetDev {
     // Bias folding of the tensor-core path: when H < Hp, activation columns H..H+2 hold 1.0 and weight columns
     // H..H+2 hold a 3-piece bf16 split of the fp32 bias (hi + mid + lo == bias exactly), so the GEMM adds the bias.
     int tc_fold;     // bit 0: hidden layers folded, bit 1: input layer folded
-    float* b0_tc;    // [Hp] first-layer bias for the unfolded input layer (carries the 1.0 of the ones columns), else nullptr
+    float* b0_tc;    // [Hp] (fused first block: [2 * Hp]) first-layer bias for the unfolded input layer (carries the 1.0 of the ones
+                     // columns), else nullptr
+    // Fused first block (tc_l1 != 0): the network has no activation between the input Linear and the first hidden Linear
+    // (resnet_fc.py:41-44, pytorch_models.py:149-160), so  relu(W1 (W0 x + b0) + b1) = relu((W1 W0) x + (W1 b0 + b1)):
+    // w0_bf16 holds [W0 ; W1 W0] stacked ([2 * Hp, in_dim_p]) and ONE launch of the generated-input GEMM writes both the
+    // skip stream x0 and the first hidden activation -- the first K = Hp hidden GEMM disappears.
+    int tc_l1;
     void* wout_bf16; // [128, Hp] zero-padded bf16 output-layer weights (multi-output networks with out_dim <= 32), else nullptr
     float* bout_pad; // [128] output bias, zero-padded
     void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16 / split NET_FP32
@@ -258,7 +264,10 @@ struct SortBufs {
 
 struct MlpBufs {
     float* x[3];          // fp32 activations [cap, Hp]
-    void* xb[3];          // bf16 activations [cap, Hp]
+    void* xb[3];          // 16-bit activations: bf16 [cap, Hp] slices of ONE [cap, 3 * Hp] array (xb[i] = base + i * Hp, so that a
+                          // launch can write two buffers at once), or -- split-fp16 mode -- three [cap, 2 * Hp] arrays ([hi | lo])
+    long long pitch;      // elements between consecutive rows of an xb buffer
+    float* partial;       // [16, cap] fp32 partial output-layer dot products of the fused last GEMM (k_out_final_bf16)
     long long cap;        // rows
 };
 

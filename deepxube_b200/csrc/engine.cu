@@ -11,6 +11,7 @@
 //   is_solved + record_goal -> CLOSED filter on popped nodes -> edges of kept nodes -> f-keys -> sort ->
 //   merge/pop edges -> next_state per popped edge -> heuristic (all-action q, h = min) -> lb/finished/itr.
 #include <math.h>
+#include <cuda_fp16.h>
 #include <cmath>
 #include <stdlib.h>
 #include <string.h>
@@ -1231,6 +1232,7 @@ extern "C" int dx_get_counters(dx_engine* e, dx_counters* out) {
     out->iterations = e->h_ctl->itr;
     out->kernel_launches = e->launches;
     out->backups_logged = e->h_ctl->n_backups;
+    out->hidden_gemm_launches = e->weights_loaded ? 2 * e->net.num_blocks - (e->net.tc_l1 ? 1 : 0) : 0;
     return DX_OK;
 }
 
@@ -1661,9 +1663,42 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             out3[1] = bf16r(b - out3[0]);
             out3[2] = bf16r(b - out3[0] - out3[1]);
         };
+        auto f16r = [](float x) { return __half2float(__float2half_rn(x)); };
+        auto split3h = [&](float b, float* out3) {      // the same 3-piece split in fp16 (fused first block with fp16 operands)
+            out3[0] = f16r(b);
+            out3[1] = f16r(b - out3[0]);
+            out3[2] = f16r(b - out3[0] - out3[1]);
+        };
         const char* fenv = getenv("DXB200_FOLD_BIAS");            // =0: keep the explicit bias adds (A/B measurements)
         const bool fold_h = Hp - H >= 3 && nb > 0 && !(fenv && fenv[0] == '0');
         const bool fold_in = fold_h && in_dim_p - in_dim >= 3;
+        // Fused first block (NetDev::tc_l1): rows [Hp, 2 * Hp) of the input-layer weights hold W1 . W0 (and b10 = W1 . b0 + b1),
+        // computed in double from the BN-folded fp32 parameters; needs the generated-input launch.
+        const char* l1env = getenv("DXB200_FUSE_L1");
+        const bool l1 = reload ? net.tc_l1 != 0 : (nb > 0 && dx_mlp_bf16_gen_input(net, e->dom) && !(l1env && l1env[0] == '0'));
+        const char* l1s = getenv("DXB200_L1_SPLIT");
+        const bool l1_pairs = l1 && (reload ? net.tc_l1 == 2 : (l1s && l1s[0] == '1'));   // bf16 (hi, lo) weight pairs instead of fp16 weights
+        net.tc_l1 = l1 ? (l1_pairs ? 2 : 1) : 0;
+        std::vector<float> b10(Hp, 0.f);
+        if (l1) {
+            w0p.resize((size_t)2 * Hp * in_dim_p, 0.f);
+            std::vector<double> acc(in_dim);
+            const float* W1 = &wres[0];                          // layer 0 of block 0, [Hp, Hp] row-major, BN folded
+            for (int o = 0; o < H; ++o) {
+                std::fill(acc.begin(), acc.end(), 0.0);
+                double bb = (double)bres[o];
+                for (int k = 0; k < H; ++k) {
+                    const double w = (double)W1[(size_t)o * Hp + k];
+                    if (w == 0.0) continue;
+                    const float* w0row = &w0p[(size_t)k * in_dim_p];
+                    for (int i = 0; i < in_dim; ++i) acc[i] += w * (double)w0row[i];
+                    bb += w * (double)b0[k];
+                }
+                float* dst = &w0p[(size_t)(Hp + o) * in_dim_p];
+                for (int i = 0; i < in_dim; ++i) dst[i] = (float)acc[i];
+                b10[o] = (float)bb;
+            }
+        }
         std::vector<float> wres_tc(wres);
         if (fold_h) {
             net.tc_fold |= 1;
@@ -1675,25 +1710,53 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
             }
             if (fold_in) {
                 net.tc_fold |= 2;
-                for (int o = 0; o < H; ++o) split3(b0[o], &w0p[(size_t)o * in_dim_p + in_dim]);
+                const bool h16 = net.tc_l1 == 1;          // the stacked first-block weights are fp16
+                auto split_in = [&](float b, float* out3) { if (h16) split3h(b, out3); else split3(b, out3); };
+                for (int o = 0; o < H; ++o) split_in(b0[o], &w0p[(size_t)o * in_dim_p + in_dim]);
                 for (int j = 0; j < 3; ++j) w0p[(size_t)(H + j) * in_dim_p + in_dim + j] = 1.f;
-            } else {
-                std::vector<float> b0tc(b0);
-                for (int j = 0; j < 3; ++j) b0tc[H + j] = 1.f;
-                if (!net.b0_tc) DX_TRY(e->alloc(&net.b0_tc, b0tc.size()));
-                DX_CUDA(cudaMemcpy(net.b0_tc, b0tc.data(), b0tc.size() * sizeof(float), cudaMemcpyHostToDevice));
+                if (l1) {                   // the stacked half: bias b10 and its own ones columns (relu(1) = 1)
+                    for (int o = 0; o < H; ++o) split_in(b10[o], &w0p[(size_t)(Hp + o) * in_dim_p + in_dim]);
+                    for (int j = 0; j < 3; ++j) w0p[(size_t)(Hp + H + j) * in_dim_p + in_dim + j] = 1.f;
+                }
             }
         }
+        if (!(net.tc_fold & 2) && (fold_h || l1)) {       // explicit first-layer bias: [b0 (+ ones) | b10 (+ ones)]
+            std::vector<float> b0tc(b0);
+            if (fold_h) for (int j = 0; j < 3; ++j) b0tc[H + j] = 1.f;
+            if (l1) {
+                b0tc.insert(b0tc.end(), b10.begin(), b10.end());
+                if (fold_h) for (int j = 0; j < 3; ++j) b0tc[Hp + H + j] = 1.f;
+            }
+            if (!net.b0_tc) DX_TRY(e->alloc(&net.b0_tc, b0tc.size()));
+            DX_CUDA(cudaMemcpy(net.b0_tc, b0tc.data(), b0tc.size() * sizeof(float), cudaMemcpyHostToDevice));
+        }
         uint16_t *w0b = (uint16_t*)net.w0_bf16, *wrb = (uint16_t*)net.wres_bf16;
-        if (!w0b) DX_TRY(e->alloc(&w0b, w0p.size()));
+        if (!w0b) DX_TRY(e->alloc(&w0b, w0p.size() * (net.tc_l1 == 2 ? 2 : 1)));
         if (!wrb) DX_TRY(e->alloc(&wrb, wres_tc.size()));
         float* tmp = nullptr;
         const size_t tmp_n = std::max(std::max(w0p.size(), (size_t)128 * Hp), std::max<size_t>(wres_tc.size(), 1));
         DX_CUDA(cudaMalloc(&tmp, tmp_n * sizeof(float)));
         // copies go through the engine's (non-blocking) stream: a legacy-stream cudaMemcpy from pageable memory may
         // return before its DMA has landed, and nothing would order the conversion kernel after it
-        cudaMemcpyAsync(tmp, w0p.data(), w0p.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
-        k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, w0b, w0p.size());
+        std::vector<uint16_t> w0s;
+        if (net.tc_l1 == 1) {        // stacked [W0 ; W1 W0] in fp16
+            w0s.resize(w0p.size());
+            for (size_t i = 0; i < w0p.size(); ++i) w0s[i] = __half_as_ushort(__float2half_rn(w0p[i]));
+            cudaMemcpyAsync(w0b, w0s.data(), w0s.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream);
+        } else if (net.tc_l1 == 2) { // ... or as bf16 (hi, lo) pairs, rows [hi(in_dim_p) | lo(in_dim_p)]
+            w0s.resize(w0p.size() * 2);
+            auto bits = [](float x) { uint32_t u; memcpy(&u, &x, 4); return (uint16_t)(u >> 16); };
+            for (size_t r = 0; r < (size_t)2 * Hp; ++r)
+                for (int i = 0; i < in_dim_p; ++i) {
+                    const float w = w0p[r * in_dim_p + i], hi = bf16r(w), lo = bf16r(w - hi);
+                    w0s[r * 2 * in_dim_p + i] = bits(hi);
+                    w0s[r * 2 * in_dim_p + in_dim_p + i] = bits(lo);
+                }
+            cudaMemcpyAsync(w0b, w0s.data(), w0s.size() * sizeof(uint16_t), cudaMemcpyHostToDevice, e->stream);
+        } else {
+            cudaMemcpyAsync(tmp, w0p.data(), w0p.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
+            k_f32_to_bf16<<<148 * 4, 256, 0, e->stream>>>(tmp, w0b, w0p.size());
+        }
         cudaStreamSynchronize(e->stream);
         if (!wres_tc.empty()) {
             cudaMemcpyAsync(tmp, wres_tc.data(), wres_tc.size() * sizeof(float), cudaMemcpyHostToDevice, e->stream);
@@ -1744,13 +1807,22 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || split) {
         int fill = 0;
         if (const char* f = getenv("DXB200_DEBUG_FILL")) fill = atoi(f);      // debug: poison value of never-written rows
-        const size_t xw = split ? 2 : 1;                                      // split mode: [hi | lo] halves per row
-        for (int i = 0; i < 3; ++i) {
+        if (split) {                                                          // three [cap, 2 * Hp] arrays ([hi | lo] halves per row)
+            e->mlp.pitch = 2 * (long long)Hp;
+            for (int i = 0; i < 3; ++i) {
+                uint16_t* q = nullptr;
+                DX_TRY(e->alloc(&q, (size_t)cap * Hp * 2));
+                DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 2 * 2));
+                e->mlp.xb[i] = q;
+            }
+        } else {                                                              // column slices of ONE [cap, 3 * Hp] array
+            e->mlp.pitch = 3 * (long long)Hp;
             uint16_t* q = nullptr;
-            DX_TRY(e->alloc(&q, (size_t)cap * Hp * xw));
-            DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 2 * xw));
-            e->mlp.xb[i] = q;
+            DX_TRY(e->alloc(&q, (size_t)cap * Hp * 3));
+            DX_CUDA(cudaMemset(q, fill, (size_t)cap * Hp * 3 * 2));
+            for (int i = 0; i < 3; ++i) e->mlp.xb[i] = q + (size_t)i * Hp;
         }
+        DX_TRY(e->alloc(&e->mlp.partial, (size_t)cap * 16));
         uint16_t* onehot = nullptr;
         const bool gen_input = !split && dx_mlp_bf16_gen_input(net, e->dom);
         if (!gen_input) {                   // the one-hot matrix exists only for networks whose input layer is not fused

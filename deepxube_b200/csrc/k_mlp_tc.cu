@@ -55,7 +55,9 @@ struct TcPlan {
     CUtensorMap b_res;
     CUtensorMap b_out;           // zero-padded output-layer weights [128, Hp] (multi-output networks), boxes of 128 / pair rows
     int q_out;                   // the multi-output layer runs on the tensor cores (DXB200_QOUT=0: warp-per-state kernel)
-    CUtensorMap c_x[3];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads
+    CUtensorMap c_x[4];          // 32 x 32 boxes (64-byte swizzle) over the activation buffers: C stores / R loads; [3] = buffers 0 and 1
+                                 // as one [rows, 2 * Hp] output (fused first block)
+    int fuse_l1;                 // the generated-input launch also computes the first hidden layer (NetDev::tc_l1)
     __nv_bfloat16* onehot;
     long long max_rows;          // capacity of the activation buffers: no launch ever has more rows than this
     int BN;
@@ -77,6 +79,7 @@ struct TcGen {
     const uint8_t* goals;        // [instances, SP] goal rows (inputs S .. in_count - 1 come from the goal)
     int S, SP, in_count, depth;
     int ones_col;                // >= 0: columns ones_col .. +2 are 1.0 (folded bias), else -1
+    int relu_col0;               // ReLU only for output columns >= relu_col0 (fused first block: [x0 | relu(hidden)]); 0: all
 };
 
 // fp32-accurate mode (DX_HEUR_NET_FP32 on the tensor cores): every operand is an fp16 (hi, lo) pair with hi + lo == the
@@ -271,12 +274,12 @@ template <int BN, int CL, int OUT_MODE, bool GEN_A, bool SPLIT = false>
 __global__ void __launch_bounds__(GEN_A ? TC_THREADS_GEN : TC_THREADS, 1)
 k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmB,
                const __grid_constant__ CUtensorMap tmC, const __grid_constant__ CUtensorMap tmR, const Ctl* __restrict__ ctl,
-               int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu,
+               int w_row0, int K, int N, const float* __restrict__ bias, int has_res, int relu_all,
                const float* __restrict__ wout, float* __restrict__ partial, long long pstride, const TcGen gen,
-               float* __restrict__ out_h, int qdim, int absolute, const TcSplit sp) {
+               float* __restrict__ out_h, int qdim, int absolute, const TcSplit sp, int relu_col0) {
     extern __shared__ uint8_t smem_raw[];
     static_assert(!(SPLIT && (GEN_A || CL != 2)), "the split-fp16 mode runs in CTA pairs with a TMA-fed A operand");
-    const int nph = SPLIT ? sp.nph : 1;
+    const int nph = (SPLIT || GEN_A) ? sp.nph : 1;
     using SM = TcSmem<BN, CL>;
     constexpr int STAGES = SM::STAGES;
     constexpr bool FUSE_OUT = OUT_MODE == 1, Q_OUT = OUT_MODE == 2;
@@ -378,15 +381,17 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                 uint32_t s = 0, ph = 0;
                 int m0, n0;
                 for (int k = 0; seq_tile(k, m0, n0); ++k)
+                    for (int wp = 0; wp < nph; ++wp)               // weight passes: [lo | hi] halves of hi/lo-split weights, else one
                     for (int kb = 0; kb < kblocks; ++kb) {
                         mbar_wait(empty_bar(s), ph ^ 1u);
                         const uint32_t b_dst = smem_base + a_res_bytes + s * SM::B_BYTES;
+                        const int w_c = sp.w_col[wp] + kb * TC_BK;
                         if (PAIR == 1) {
                             mbar_arrive_expect_tx(full_bar(s), SM::B_BYTES);
-                            tma_load_2d(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0);
+                            tma_load_2d(b_dst, &tmB, full_bar(s), w_c, w_row0 + n0);
                         } else {
                             if (hr == 0) mbar_arrive_expect_tx(full_bar(s), 2 * SM::B_BYTES);
-                            tma_load_2d_2sm(b_dst, &tmB, full_bar(s), kb * TC_BK, w_row0 + n0 + (int)hr * (BN / PAIR));
+                            tma_load_2d_2sm(b_dst, &tmB, full_bar(s), w_c, w_row0 + n0 + (int)hr * (BN / PAIR));
                         }
                         if (++s == (uint32_t)nb_st) { s = 0; ph ^= 1u; }
                     }
@@ -428,7 +433,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
             // ---------------- MMA issuer (the leader CTA of each pair) ----------------
             // instruction descriptor: D = F32, A = B = BF16, both K-major, N = BN, M = 128 * PAIR
             // (A / B format field: 1 = bf16, 0 = fp16 -- the split-fp16 mode's operands)
-            const uint32_t ab_fmt = (SPLIT && sp.f16) ? 0u : ((1u << 7) | (1u << 10));
+            const uint32_t ab_fmt = ((SPLIT || GEN_A) && sp.f16) ? 0u : ((1u << 7) | (1u << 10));
             const uint32_t idesc = (1u << 4) | ab_fmt | ((uint32_t)(BN >> 3) << 17) | ((uint32_t)((TC_BM * PAIR) >> 4) << 24);
             uint32_t it = 0, lt = 0;
             [[maybe_unused]] long long w_full = 0, w_tempty = 0;
@@ -444,16 +449,18 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
                     { TC_T0(); mbar_wait(tempty_bar(as), ((lt >> 1) & 1u) ^ 1u); TC_ACC(w_tempty); }
                     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                     const uint32_t d_tmem = tmem_base + (uint32_t)(as * BN);
+                    for (int wp = 0; wp < nph; ++wp)
                     for (int kb = 0; kb < kblocks; ++kb) {
-                        { TC_T0(); mbar_wait(full_bar(s), ph); if (nt == 0) mbar_wait(afull_bar(kb), gph); TC_ACC(w_full); }
+                        { TC_T0(); mbar_wait(full_bar(s), ph); if (nt == 0 && wp == 0) mbar_wait(afull_bar(kb), gph); TC_ACC(w_full); }
                         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                         const uint64_t adesc = make_sw128_desc(smem_base + kb * SM::A_BYTES);
                         const uint64_t bdesc = make_sw128_desc(smem_base + a_res_bytes + s * SM::B_BYTES);
 #pragma unroll
                         for (int q = 0; q < TC_BK / TC_UMMA_K; ++q)
-                            umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(q * 2), bdesc + (uint64_t)(q * 2), idesc, (kb | q) ? 1u : 0u);
+                            umma_bf16<PAIR>(d_tmem, adesc + (uint64_t)(q * 2), bdesc + (uint64_t)(q * 2), idesc, (wp | kb | q) ? 1u : 0u);
                         umma_commit<PAIR>(empty_bar(s), all_mask);
-                        if (nt == n_tiles - 1) umma_commit<PAIR>(aempty_bar(kb), pair_mask);   // the group's A tile kb may be overwritten
+                        // the group's A tile kb may be overwritten once its last use (last weight pass of the last n-tile) has been read
+                        if (nt == n_tiles - 1 && wp == nph - 1) umma_commit<PAIR>(aempty_bar(kb), pair_mask);
                         if (++s == (uint32_t)nb_st) { s = 0; ph ^= 1u; }
                     }
                     umma_commit<PAIR>(tfull_bar(as), pair_mask);
@@ -492,6 +499,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         const int gt = (warp >= 12 ? (warp - 10) : (warp - 2)) * 32 + lane;
         uint8_t* res_sm = smem_raw + (smem_base + SM::RES_OFF - smem_u32(smem_raw));
         uint4* lut = reinterpret_cast<uint4*>(res_sm);
+        const uint32_t one16 = sp.f16 ? 0x3C00u : 0x3F80u;         // 1.0 in the operand format (fp16 / bf16)
         // LUT slot of byte e: low 3 bits permuted so that the few byte values a one-hot code produces spread over banks
         auto lut_slot = [](uint32_t e) { return e ^ (((e >> 3) ^ (e >> 6)) & 7u); };
         const int SP = gen.SP, depth = gen.depth;
@@ -506,7 +514,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (uint32_t e = gt; e < 256; e += 128) {
             uint32_t w[4];
 #pragma unroll
-            for (int k = 0; k < 4; ++k) w[k] = (((e >> (2 * k)) & 1) ? 0x00003F80u : 0u) | (((e >> (2 * k + 1)) & 1) ? 0x3F800000u : 0u);
+            for (int k = 0; k < 4; ++k) w[k] = (((e >> (2 * k)) & 1) ? one16 : 0u) | (((e >> (2 * k + 1)) & 1) ? (one16 << 16) : 0u);
             lut[lut_slot(e)] = make_uint4(w[0], w[1], w[2], w[3]);
         }
         // One bulk copy (TMA, completes on rows_bar) brings a tile's rows -- contiguous in the node store -- into buffer b.
@@ -628,6 +636,7 @@ k_gemm_bf16_tc(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ 
         for (int k = 0; seq_tile(k, m0, n0); ++k, ++lt) {
             const int as = lt & 1;
             const int row0 = m0 + q * 32;
+            const int relu = relu_all && n0 >= relu_col0;       // (fused first block: only the hidden-layer half of the columns)
             if (SPLIT) {
                 // split mode: buffer 0 holds the hi half, buffer 1 the lo half of ONE chunk (both on barrier 0); the epilogue
                 // has three MMA passes' worth of time per tile, so chunks are not double-buffered here
@@ -973,15 +982,15 @@ __global__ void k_onehot_bf16(DomainDev d, int in_count, int depth, int in_dim_p
 
 // Final Linear(H, out_dim) + clipping on bf16 activations; one warp per row (see k_out_layer in k_mlp_f32.cu).
 __global__ void __launch_bounds__(256)
-k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* __restrict__ X, int kmax, float* __restrict__ out_h,
-                 float* __restrict__ out_q, int absolute) {      // kmax: columns of X the last GEMM wrote (the rest is never read)
+k_out_layer_bf16(NetDev net, const Ctl* __restrict__ ctl, const __nv_bfloat16* __restrict__ X, long long pitch, int kmax,
+                 float* __restrict__ out_h, float* __restrict__ out_q, int absolute) {      // kmax: columns of X the last GEMM wrote
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     const int lane = threadIdx.x & 31;
     const int Hp = net.Hp, od = net.out_dim;
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
     for (uint32_t r = blockIdx.x * 8 + (threadIdx.x >> 5); r < n; r += gridDim.x * 8) {
-        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(X + (size_t)r * Hp);
+        const __nv_bfloat162* x2 = reinterpret_cast<const __nv_bfloat162*>(X + (size_t)r * (size_t)pitch);
         const size_t oi = absolute ? (size_t)start * (net.act_depth > 0 ? net.act_depth : 1) + r : (size_t)r;
         float hmin = __int_as_float(0x7f800000);
         for (int o0 = 0; o0 < od; o0 += 4) {
@@ -1036,9 +1045,9 @@ typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t,
                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
 
 static int make_map(EncodeTiledFn enc, CUtensorMap* map, void* base, uint64_t cols, uint64_t rows, uint32_t box_rows,
-                    uint32_t box_cols = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B) {
+                    uint32_t box_cols = TC_BK, CUtensorMapSwizzle swz = CU_TENSOR_MAP_SWIZZLE_128B, uint64_t pitch = 0) {
     cuuint64_t dims[2] = {cols, rows};
-    cuuint64_t strides[1] = {cols * 2};
+    cuuint64_t strides[1] = {(pitch ? pitch : cols) * 2};      // pitch (elements): the buffer is a column slice of a wider array
     cuuint32_t box[2] = {box_cols, box_rows};
     cuuint32_t estr[2] = {1, 1};
     CUresult r = enc(map, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, base, dims, strides, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
@@ -1169,12 +1178,25 @@ int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, 
     // (with a generated input the A map of the first launch is never read: any valid map will do)
     int rc = onehot_buf ? make_map(enc, &p->a_onehot, onehot_buf, net.in_dim_p, (uint64_t)mb.cap, TC_BM)
                         : make_map(enc, &p->a_onehot, mb.xb[0], net.Hp, (uint64_t)mb.cap, TC_BM);
-    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM);
-    for (int i = 0; i < 3 && rc == DX_OK; ++i) rc = make_map(enc, &p->a_xh[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM / 2);
+    const uint64_t pitch = (uint64_t)mb.pitch;
     for (int i = 0; i < 3 && rc == DX_OK; ++i)
-        rc = make_map(enc, &p->c_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B);
+        rc = make_map(enc, &p->a_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, pitch);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i)
+        rc = make_map(enc, &p->a_xh[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, TC_BM / 2, TC_BK, CU_TENSOR_MAP_SWIZZLE_128B, pitch);
+    for (int i = 0; i < 3 && rc == DX_OK; ++i)
+        rc = make_map(enc, &p->c_x[i], mb.xb[i], xp * net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, pitch);
     const int pair = p->CL >= 2 ? 2 : 1;
-    if (rc == DX_OK) rc = make_map(enc, &p->b_w0, sw ? sw->w0 : net.w0_bf16, xp * net.in_dim_p, net.Hp, p->BN / pair);
+    p->fuse_l1 = (!sw && net.tc_l1 && p->fuse_in && p->CL_in == 2) ? 1 : 0;
+    if (net.tc_l1 && !p->fuse_l1) {
+        dx_set_error("NET_BF16: the stacked first-block weights need the generated-input launch (internal error)");
+        delete p;
+        return DX_ERR_STATE;
+    }
+    if (rc == DX_OK && p->fuse_l1)
+        rc = make_map(enc, &p->c_x[3], mb.xb[0], 2 * (uint64_t)net.Hp, (uint64_t)mb.cap, 32, 32, CU_TENSOR_MAP_SWIZZLE_64B, pitch);
+    if (rc == DX_OK)
+        rc = make_map(enc, &p->b_w0, sw ? sw->w0 : net.w0_bf16, (sw || net.tc_l1 == 2 ? 2 : 1) * (uint64_t)net.in_dim_p,
+                      (uint64_t)net.Hp * (p->fuse_l1 ? 2 : 1), p->BN / pair);
     if (rc == DX_OK && net.num_blocks > 0)
         rc = make_map(enc, &p->b_res, sw ? sw->wres : net.wres_bf16, xp * net.Hp, (uint64_t)2 * net.num_blocks * net.Hp, p->BN / pair);
     p->q_out = 0;
@@ -1248,7 +1270,7 @@ static void launch_gemm_t(cudaLaunchConfig_t* cfg, const CUtensorMap& a, const C
     cfg->dynamicSmemBytes = TcSmem<BN, CL>::TOTAL;
     cfg->blockDim = dim3(GEN ? TC_THREADS_GEN : TC_THREADS);
     cudaLaunchKernelEx(cfg, k_gemm_bf16_tc<BN, CL, MODE, GEN, SPLIT>, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial,
-                       pstride, gen, qo.out_h, qo.qdim, qo.absolute, sp);
+                       pstride, gen, qo.out_h, qo.qdim, qo.absolute, sp, gen.relu_col0);
 }
 
 // c: output buffer index, r: residual buffer index or -1; partial != nullptr selects the fused output-layer epilogue
@@ -1260,7 +1282,7 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorM
                         float* partial = nullptr, long long pstride = 0, const TcGen* gen = nullptr, const TcQOut* qo = nullptr,
                         const TcSplit* split = nullptr) {
     const CUtensorMap& tc = p->c_x[c];
-    const CUtensorMap& tr = p->c_x[r >= 0 ? r : c];
+    const CUtensorMap& tr = p->c_x[r >= 0 ? r : (c < 3 ? c : 0)];
     cudaLaunchConfig_t cfg = {};
     // persistent grid: one cluster per SM group, but never more clusters than the engine's capacity can give work to (a
     // `graph.100B` engine evaluates <= 1200 rows: 5 row groups, not 74 clusters' worth of barrier / TMEM set-up per launch)
@@ -1291,7 +1313,7 @@ static void launch_gemm(cudaStream_t s, const TcPlan* p, int cl, const CUtensorM
 #define DX_TC_ARGS &cfg, a, b, tc, tr, ctl, w_row0, K, N, bias, has_res, relu, wout, partial, pstride, g, q, sp
 #define DX_TC_PICK(CLV, MODEV, GENV) do { if (big) launch_gemm_t<256, CLV, MODEV, GENV>(DX_TC_ARGS); \
                                           else launch_gemm_t<128, CLV, MODEV, GENV>(DX_TC_ARGS); } while (0)
-    if (split) {                       // fp32-accurate mode: CTA pairs, TMA-fed A, (hi, lo) epilogue
+    if (split && !gen) {               // fp32-accurate mode: CTA pairs, TMA-fed A, (hi, lo) epilogue
         if (qo) launch_gemm_t<128, 2, 2, false, true>(DX_TC_ARGS);
         else if (fuse) { if (big) launch_gemm_t<256, 2, 1, false, true>(DX_TC_ARGS); else launch_gemm_t<128, 2, 1, false, true>(DX_TC_ARGS); }
         else { if (big) launch_gemm_t<256, 2, 0, false, true>(DX_TC_ARGS); else launch_gemm_t<128, 2, 0, false, true>(DX_TC_ARGS); }
@@ -1327,7 +1349,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     int ix = 0, iy = 1, iz = 2;
     const int Hp = net.Hp;
     const bool fold_h = (net.tc_fold & 1) != 0;
-    const float* bias0 = (net.tc_fold & 2) ? nullptr : (fold_h ? net.b0_tc : net.b0);
+    const float* bias0 = (net.tc_fold & 2) ? nullptr : ((fold_h || net.tc_l1) ? net.b0_tc : net.b0);
     const int ones_col = (net.tc_fold & 2) ? net.in_dim : -1;
     const int kv_in = net.in_dim_p, kv_h = Hp, nv = Hp;      // padded shapes (trimming the padding measured no gain)
     if (p->split) {
@@ -1365,7 +1387,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
                         nullptr, nullptr, 0, nullptr, nullptr, &s1);
             if (fuse_s && b == net.num_blocks - 1)
                 launch_gemm(s, p, 2, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
-                            net.wout, (float*)mb.xb[iz], mb.cap, nullptr, nullptr, &s2);
+                            net.wout, mb.partial, mb.cap, nullptr, nullptr, &s2);
             else
                 launch_gemm(s, p, 2, p->a_x[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
                             nullptr, nullptr, 0, nullptr, nullptr, &s2);
@@ -1375,7 +1397,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         dx_prof_end();
         if (fuse_s) {
             const int blocks = (int)min((long long)dx_div_up(max_rows, 256), (long long)148 * 8);
-            k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, (const float*)mb.xb[ix], mb.cap, 2 * (Hp / p->BN), out_h, out_q, absolute);
+            k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, mb.partial, mb.cap, 2 * (Hp / p->BN), out_h, out_q, absolute);
         } else {                          // multi-output layer (dx_mlp_split_supported guarantees out_dim <= 32 here)
             TcQOut qo{out_h, net.out_dim, absolute};
             const TcSplit so = mk(3, Hp, Hp, sw->s_out, true);
@@ -1390,7 +1412,23 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
         // input layer with the one-hot encoding generated inside the GEMM (no one-hot matrix in HBM)
         TcGen g;
         g.rows = rows; g.goals = goals; g.S = d.S; g.SP = d.SP; g.in_count = net.in_count; g.depth = net.depth; g.ones_col = ones_col;
-        launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
+        g.relu_col0 = 0;
+        if (p->fuse_l1) {      // [x0 | relu(W1 x0 + b1)] in one launch: 2 * Hp output columns into buffers 0 and 1 (NetDev::tc_l1)
+            g.relu_col0 = Hp;
+            // the stacked weights are bf16 (hi, lo) pairs ([hi | lo] per row): two weight passes over the resident one-hot tiles
+            // make x0 and the first hidden pre-activation accurate to ~16 bits before their single bf16 rounding on store
+            TcSplit wsp = {};
+            if (net.tc_l1 == 2) {      // DXB200_L1_SPLIT=1: bf16 (hi, lo) weight pairs, two weight passes (A/B arm, +80 % launch time)
+                wsp.nph = 2;
+                wsp.w_col[0] = net.in_dim_p; wsp.w_col[1] = 0;
+            } else {                   // default: fp16 operands (the one-hot A is exact in any format; 11-bit instead of 8-bit weights)
+                wsp.nph = 1;
+                wsp.f16 = 1;
+            }
+            launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, 2 * nv, bias0, -1, 3, 1, nullptr, nullptr, 0, &g, nullptr, &wsp);
+        } else {
+            launch_gemm(s, p, p->CL_in, p->a_onehot, p->b_w0, ctl, 0, kv_in, nv, bias0, -1, ix, 0, nullptr, nullptr, 0, &g);
+        }
         ++launches;
     } else {
         k_onehot_bf16<<<oh_blocks, 256, 0, s>>>(d, net.in_count, net.depth, net.in_dim_p, ones_col, net.act_depth,
@@ -1408,19 +1446,22 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     const CUtensorMap* ax = p->CL == 4 ? p->a_xh : p->a_x;
     dx_prof_begin(DX_ST_GEMM_RES);
     for (int b = 0; b < net.num_blocks; ++b) {
-        launch_gemm(s, p, p->CL, ax[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
+        if (!(b == 0 && p->fuse_l1)) {       // (fused first block: buffer iy already holds the first hidden activation)
+            launch_gemm(s, p, p->CL, ax[ix], p->b_res, ctl, (2 * b) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b) * Hp, -1, iy, 1);
+            ++launches;
+        }
         if (fuse && b == net.num_blocks - 1)
             launch_gemm(s, p, p->CL, ax[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1,
-                        net.wout, (float*)mb.xb[iz], mb.cap);
+                        net.wout, mb.partial, mb.cap);
         else
             launch_gemm(s, p, p->CL, ax[iy], p->b_res, ctl, (2 * b + 1) * Hp, kv_h, nv, fold_h ? nullptr : net.bres + (size_t)(2 * b + 1) * Hp, ix, iz, 1);
-        launches += 2;
+        ++launches;
         int ti = ix; ix = iz; iz = ti;
     }
     dx_prof_end();
     if (fuse) {
         const int blocks = (int)min((long long)dx_div_up(max_rows, 256), (long long)148 * 8);
-        k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, (const float*)mb.xb[ix], mb.cap, P, out_h, out_q, absolute);
+        k_out_final_bf16<<<blocks, 256, 0, s>>>(net, ctl, mb.partial, mb.cap, P, out_h, out_q, absolute);
     } else if (p->q_out && out_q) {
         // multi-output layer as one more GEMM (128-wide n-tile of zero-padded weight rows), fp32 q-values from the epilogue
         TcQOut qo{out_h, net.out_dim, absolute};
@@ -1428,7 +1469,7 @@ int dx_launch_mlp_bf16(cudaStream_t s, const DomainDev& d, const NetDev& net, co
     } else {
         const __nv_bfloat16* x = (const __nv_bfloat16*)mb.xb[ix];
         const int blocks = (int)min((long long)dx_div_up(max_rows, 8), (long long)148 * 8);
-        k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, Hp, out_h, out_q, absolute);
+        k_out_layer_bf16<<<blocks, 256, 0, s>>>(net, ctl, x, mb.pitch, Hp, out_h, out_q, absolute);
     }
     ++launches;
     launches += dx_launch_act_end(s, net, const_cast<Ctl*>(ctl), q_dst, h_dst, absolute, max_nodes);

@@ -111,7 +111,9 @@ typedef struct dx_counters {
     int64_t iterations;           /* PathFind.itr                                                        */
     int64_t kernel_launches;      /* CUDA kernels launched by the engine since creation                  */
     int64_t backups_logged;       /* log slots in use (an upper bound of what dx_drain_backups returns)  */
-    int64_t reserved[2];
+    int64_t hidden_gemm_launches; /* H x H GEMM launches per network evaluation: 2 * num_blocks, or one less when the first
+                                     hidden layer is computed by the input-layer launch (bf16 tensor-core path)             */
+    int64_t reserved[1];
 } dx_counters;
 
 const char* dx_last_error(void);

@@ -11,7 +11,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 ROOT = os.path.dirname(HERE)
 LIB = os.path.join(HERE, "libdxb200.so")
-SOURCES = ["engine.cu", "k_domain.cu", "k_closed.cu", "k_scan.cu", "k_open.cu", "k_mlp_f32.cu", "k_mlp_tc.cu", "k_hda.cu"]
+SOURCES = ["engine.cu", "k_domain.cu", "k_closed.cu", "k_scan.cu", "k_open.cu", "k_mlp_f32.cu", "k_mlp_tc.cu", "k_mlp_small.cu", "k_hda.cu"]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17", "-Xcompiler", "-fPIC",
               "--expt-relaxed-constexpr", "-I", os.path.join(ROOT, "include"), "-I", CSRC] + os.environ.get("DXB200_NVCC_DEFS", "").split()
 

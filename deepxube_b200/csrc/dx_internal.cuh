@@ -23,6 +23,11 @@
 #define DX_DEVERR_BACKUPS 16u // the Bellman-backup log is full (dx_config.max_backups); drain it more often
 #define DX_DEVERR_PEER 32u    // HDA*: another rank of the distributed search reported a device error
 #define DX_DEVERR_NUMERIC 64u // split-fp16 network: an activation left the fp16 range (|x| > 65504)
+// Not an error: every instance is finished().  Set by k_end_iter only inside dx_run's bursts (several iterations launched per
+// host poll): every kernel returns on a non-zero error word, so the rest of a burst is a no-op and the search stops in the exact
+// iteration the reference's loop would (deepxube/_solve.py:150-161).  dx_run clears it before it returns.
+#define DX_DEVERR_DONE 0x80000000u
+#define DX_END_HALT 8          // k_end_iter gen_mode flag: raise DX_DEVERR_DONE when no instance is left
 #define DX_HDA_LOCALS 8       // doubles per rank in the all-gathered per-iteration scalars (k_hda_locals)
 
 void dx_set_error(const std::string& msg);
@@ -164,7 +169,9 @@ struct NetDev {
     float* bout_pad; // [128] output bias, zero-padded
     void* tc_plan;   // TMA tensor maps etc. of the tensor-core path (k_mlp_tc.cu), nullptr unless NET_BF16 / split NET_FP32
     void* tc_split;  // host TcSplitW*: fp16 (hi, lo) copies of the parameters -- NET_FP32 on the tensor cores (k_mlp_tc.cu), else nullptr
+    void* small;     // host SmallNetHost*: packed weight stream of the one-launch small-evaluation kernel (k_mlp_small.cu), else nullptr
 };
+#define DX_SMALL_NET_ROWS 8192   // engines whose evaluations never exceed this many rows run the network with k_mlp_small
 
 // Split-fp16 parameters of the fp32-accurate tensor-core path: every weight w is stored as the fp16 pair (hi, lo) of w * s
 // (s = a power of two per layer that puts the largest weight in [2^13, 2^14), so that the lo halves are normal fp16 numbers):
@@ -406,3 +413,9 @@ bool dx_mlp_bf16_gen_input(const NetDev& net, const DomainDev& d);
 bool dx_mlp_split_supported(const NetDev& net);
 int dx_mlp_split_upload(cudaStream_t s, NetDev& net, const float* w0p, const float* wres, const float* wout);
 int dx_mlp_bf16_prepare(const NetDev& net, const MlpBufs& mb, void* onehot_buf, bool gen_input, void** plan_out);
+// k_mlp_small.cu: the whole network in one launch for engines with small evaluations (res_dim <= 256)
+bool dx_mlp_small_supported(const NetDev& net, const DomainDev& d);
+int dx_mlp_small_upload(cudaStream_t s, NetDev& net, bool split, const float* w0p, const float* wres);
+void dx_mlp_small_free(NetDev& net);
+int dx_launch_mlp_small(cudaStream_t s, const DomainDev& d, const NetDev& net, const Ctl* ctl, const uint8_t* rows,
+                        const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows);

@@ -167,6 +167,7 @@ __global__ void k_after_remove(Ctl* ctl, uint32_t n_pop, uint32_t n_children, ui
     ctl->n_unfinished = n_unfinished;
 }
 __global__ void k_reset_backups(Ctl* ctl) { ctl->n_backups = 0; }
+__global__ void k_clear_done(Ctl* ctl) { ctl->error &= ~DX_DEVERR_DONE; }
 __global__ void k_set_job_children(Ctl* ctl) { ctl->nn_row_start = 0; ctl->nn_n = ctl->error ? 0 : ctl->n_children; }
 
 // device-side parent walk (base/pathfinding.py:93-120): actions written goal -> root, reversed on the host
@@ -270,6 +271,8 @@ struct dx_engine {
     long long sort_bound = 0;          // sum of batch_size * actions over the instances: no iteration pushes more entries
     bool graph_small = false;          // whether the captured graphs use the single-block sort
     bool use_graphs = true;
+    int poll_every = 4;             // small-batch dx_run: iterations launched per host poll (DXB200_POLL_EVERY)
+    bool halt_flag = false;         // the step being launched / captured belongs to dx_run: k_end_iter may raise DX_DEVERR_DONE
     float last_run_ms = 0.f;
 
     template <typename T> int alloc(T** p, size_t count) {
@@ -362,7 +365,7 @@ void dx_prof_end() { if (g_prof_engine) stage_end(g_prof_engine); }
 static int sync_ctl(dx_engine* e) {
     DX_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
-    if (e->h_ctl->error) {
+    if (e->h_ctl->error & ~DX_DEVERR_DONE) {
         std::string m = "device capacity exceeded:";
         if (e->h_ctl->error & DX_DEVERR_NODES) m += " max_nodes";
         if (e->h_ctl->error & DX_DEVERR_OPEN) m += " max_open";
@@ -470,6 +473,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     e->is_beam = cfg->algo == DX_ALGO_BEAM_V || cfg->algo == DX_ALGO_BEAM_Q;
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     if (const char* fs = getenv("DXB200_SMALL_FUSE")) e->fuse_small = !(fs[0] == '0');
+    if (const char* pe = getenv("DXB200_POLL_EVERY")) e->poll_every = std::max(1, atoi(pe));
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -562,6 +566,7 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
         cudaFree(sw->w0); cudaFree(sw->wres); cudaFree(sw->wout);
         delete sw;
     }
+    dx_mlp_small_free(e->net);
     if (e->h_ctl) cudaFreeHost(e->h_ctl);
     if (e->own_stream) cudaStreamDestroy(e->own_stream);
     delete e;
@@ -587,6 +592,8 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
 // else the CUDA-core fp32 path.  Returns the number of launches.
 static int launch_net(dx_engine* e, const uint8_t* rows, const uint8_t* goals, float* out_h, float* out_q, int absolute, long long max_rows) {
     g_prof_engine = e->profiling ? e : nullptr;       // the launchers' dx_prof_begin / dx_prof_end hooks time into THIS engine
+    if (e->net.small)
+        return dx_launch_mlp_small(e->stream, e->dom, e->net, e->d_ctl, rows, goals, out_h, out_q, absolute, std::min<long long>(max_rows, e->mlp.cap));
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || e->net.tc_split)
         return dx_launch_mlp_bf16(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, goals, out_h, out_q, absolute, max_rows);
     return dx_launch_mlp_f32(e->stream, e->dom, e->net, e->mlp, e->d_ctl, rows, goals, out_h, out_q, absolute, max_rows);
@@ -857,7 +864,7 @@ static int step_v_b(dx_engine* e) {
                                    e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
     stage_end(e);
     stage_begin(e, ST_BOOK);
-    e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, beam ? 2 : 0);
+    e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, (beam ? 2 : 0) | (e->halt_flag ? DX_END_HALT : 0));
     stage_end(e);
     e->parity = q;
     return DX_OK;
@@ -938,7 +945,7 @@ static int step_q_b(dx_engine* e) {
     if (e->backups_q)
         e->launches += dx_launch_bellman_backup_q(e->stream, e->dom, e->d_ctl, e->node_state, e->node_parent, e->node_action,
                                                   e->node_h, e->node_solved, e->popped_inst[q], e->bk, e->max_pop);
-    e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, e->is_beam ? 3 : 1);
+    e->launches += dx_launch_end_iter(e->stream, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, (e->is_beam ? 3 : 1) | (e->halt_flag ? DX_END_HALT : 0));
     stage_end(e);
     e->parity = q;
     return DX_OK;
@@ -970,7 +977,9 @@ static int build_step_graphs(dx_engine* e, bool prof) {
         cudaGraph_t g = nullptr;
         DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         e->cap_prof = prof ? p : -1;
+        e->halt_flag = !prof && e->graph_small;      // (only the graphs dx_run launches in bursts)
         const int rc = full_step(e);                 // flips e->parity
+        e->halt_flag = false;
         e->cap_prof = -1;
         e->ev_open.clear();
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
@@ -1015,17 +1024,32 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
         e->prof_graph_level = e->profiling;
     }
     cudaEventRecord(e->run_ev[0], e->stream);
+    // Small-batch searches (an iteration is ~100 us of kernels) launch a BURST of iterations per host poll: k_end_iter raises
+    // DX_DEVERR_DONE in the iteration that finishes the last instance, which turns the rest of the burst into no-ops, so the
+    // search still stops in exactly the iteration the reference's loop does; the host reads how many iterations really ran.
+    const int burst_max = (use_graph && !prof && e->graph_small) ? e->poll_every : 1;
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         if (use_graph) {
-            DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[e->parity] : e->graph_exec[e->parity], e->stream));
-            e->launches += e->graph_launches;
-            e->parity ^= 1;
+            const int burst = std::min(burst_max, (int)max_iters - done);
+            const uint32_t itr0 = e->h_ctl->itr;
+            for (int b = 0; b < burst; ++b)
+                DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[e->parity ^ (b & 1)] : e->graph_exec[e->parity ^ (b & 1)], e->stream));
+            DX_TRY(sync_ctl(e));                     // synchronises the stream
+            const int ran = burst == 1 ? 1 : (int)(e->h_ctl->itr - itr0);
+            e->launches += (long long)ran * e->graph_launches;
+            e->parity ^= (ran & 1);
+            done += ran;
+            if (prof) stage_collect_graph(e, e->parity ^ 1);
+            if (ran < burst) break;                  // (everything finished inside the burst)
         } else {
             DX_TRY(full_step(e));
+            ++done;
+            DX_TRY(sync_ctl(e));
         }
-        ++done;
-        DX_TRY(sync_ctl(e));                         // synchronises the stream
-        if (use_graph && prof) stage_collect_graph(e, e->parity ^ 1);
+    }
+    if (e->h_ctl->error & DX_DEVERR_DONE) {         // internal to this loop: no other entry point ever sees it
+        k_clear_done<<<1, 1, 0, e->stream>>>(e->d_ctl);
+        e->h_ctl->error &= ~DX_DEVERR_DONE;
     }
     cudaEventRecord(e->run_ev[1], e->stream);
     DX_CUDA(cudaStreamSynchronize(e->stream));
@@ -1644,10 +1668,18 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
     p += (size_t)od * H;
     for (int o = 0; o < od; ++o) bout[o] = p[o];
 
+    // rows one evaluation can hold: popped nodes (Q*) or children (A*); x actions for an action-as-input network
+    const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst) * (act_depth > 0 ? act_depth : 1);
 #define UP_(dst, vec) do { if (!(dst)) DX_TRY(e->alloc(&(dst), (vec).size())); \
         DX_CUDA(cudaMemcpy((dst), (vec).data(), (vec).size() * sizeof(float), cudaMemcpyHostToDevice)); } while (0)
     UP_(net.w0t, w0t); UP_(net.b0, b0); UP_(net.wres, wres); UP_(net.bres, bres); UP_(net.wout, wout); UP_(net.bout, bout);
 #undef UP_
+    // Engines whose evaluations are small (solve-time regime: graph.100B) run the whole network in ONE launch (k_mlp_small.cu).
+    // The choice is per ENGINE, not per call, so that every value an engine produces comes from the same arithmetic.
+    if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || e->cfg.heur_mode == DX_HEUR_NET_FP32) {
+        const bool want = reload ? net.small != nullptr : (cap <= DX_SMALL_NET_ROWS && dx_mlp_small_supported(net, e->dom));
+        if (want) DX_TRY(dx_mlp_small_upload(e->stream, net, e->cfg.heur_mode == DX_HEUR_NET_FP32, w0p.data(), wres.data()));
+    }
     // bf16 copies for the tensor-core path (first layer K-major [Hp, in_dim_p]; residual layers [l, Hp, Hp]).
     // Bias folding (NetDev::tc_fold): spare padding columns carry the bias through the GEMM itself.
     net.tc_fold = 0;
@@ -1801,8 +1833,6 @@ int dx_upload_net(dx_engine* e, const dx_net_desc* desc, const float* blob, int6
         return DX_OK;                         // activation buffers and tensor maps stay (bf16 / SGEMM: the captured graphs too)
     }
     // activation buffers
-    // rows one evaluation can hold: popped nodes (Q*) or children (A*); x actions for an action-as-input network
-    const long long cap = std::max<long long>(e->is_q ? e->max_pop : e->max_children, e->max_inst) * (act_depth > 0 ? act_depth : 1);
     e->mlp.cap = cap;
     if (e->cfg.heur_mode == DX_HEUR_NET_BF16 || split) {
         int fill = 0;
@@ -2099,9 +2129,11 @@ extern "C" int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint3
 }
 
 int dx_tc_profile_read(unsigned long long* out16);   // k_mlp_tc.cu
+int dx_small_profile_read(unsigned long long* out16);   // k_mlp_small.cu
 extern "C" int dx_debug_tc_profile(dx_engine* e, uint64_t* out8) {   /* out8: 16 entries */
     if (!e || !out8) DX_FAIL(DX_ERR_ARG, "null argument");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->net.small) return dx_small_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DSM_PROFILE timeline)
     return dx_tc_profile_read(reinterpret_cast<unsigned long long*>(out8));
 }

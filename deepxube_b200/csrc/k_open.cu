@@ -787,13 +787,13 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         const uint32_t seq_old = ia.pop_seq_base[i], itr = ia.itr[i] + 1;
         const double w = ia.weight[i];
         if (k > 0) lb = fmax(dx_key_to_f(ff), lb);                                  // graph_search.py:67-69
-        const bool edge_mode = gen_mode == 1 || gen_mode == 3;
+        const bool edge_mode = (gen_mode & 7) == 1 || (gen_mode & 7) == 3;
         const unsigned long long g_add = !edge_mode ? (unsigned long long)n_pop * A : (unsigned long long)k;
         gen += g_add;
         bool fin = false;
         if (ubk != DX_EMPTY64) {
             const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
-            fin = gen_mode >= 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
+            fin = (gen_mode & 7) >= 2 ? true                                               // beam search: finished() == has_soln() (beam_search.py:62-66)
                                 : lb >= __dmul_rn(w, ub);                           // graph_search.py:44
         }
         fin = fin || (k == 0);                                                       // itr > 0 holds here (graph_search.py:45)
@@ -811,7 +811,8 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
         ctl->n_unfinished = s_unfinished;
         ctl->gen_total += s_gen;
         ctl->n_pop = pop_off_next[I];
-        ctl->n_children = pop_off_next[I] * ((gen_mode == 0 || gen_mode == 2) ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
+        ctl->n_children = pop_off_next[I] * (((gen_mode & 7) == 0 || (gen_mode & 7) == 2) ? (uint32_t)A : 1u);   // items the next CLOSED filter sees
+        if ((gen_mode & DX_END_HALT) && s_unfinished == 0) ctl->error |= DX_DEVERR_DONE;        // the rest of dx_run's burst is a no-op
         ctl->itr += 1;
         ctl->epoch += 1;
         ctl->node_base = ctl->node_count;

@@ -8,24 +8,33 @@ g = os.path.join(ROOT, "tests", "golden")
 k = np.load(os.path.join(g, "kat_cube3.npz"))
 z = np.load(os.path.join(g, "nnet.npz"))
 sd = {key[len("cube3v/"):]: z[key] for key in z.files if key.startswith("cube3v/")}
+want = sys.argv[1].split(",") if len(sys.argv) > 1 else ["fp32", "bf16", "zero"]
 for prec, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16), ("zero", L.DX_HEUR_ZERO)):
+    if prec not in want:
+        continue
     eng = L.Engine("cube3", 0, "graph_v", mode, max_instances=1, max_pop_total=100, max_nodes=600000)
     if mode != L.DX_HEUR_ZERO:
         blob, info = L.pack_state_dict(sd)
         eng.load_weights(54, 6, info["res_dim"], info["num_blocks"], 1, True, blob)
     eng.add_instances(k["hard_states"][:1], k["hard_goals"][:1], 100, 0.1)
     eng.run(50)
+    if mode != L.DX_HEUR_ZERO:
+        eng.tc_profile()
     tot_it, tot_s, dev_ms = 0, 0.0, 0.0
     l0 = eng.counters().kernel_launches
     for i in range(10):
         eng.reset()
         eng.add_instances(k["hard_states"][i:i + 1], k["hard_goals"][i:i + 1], 100, 0.1)
         t0 = time.perf_counter()
-        it = eng.run(60 if mode == L.DX_HEUR_ZERO else 100000)
+        it = eng.run(60 if mode == L.DX_HEUR_ZERO else int(os.environ.get("DXB200_PROBE_ITERS", "100000")))
         tot_s += time.perf_counter() - t0
         tot_it += it
         dev_ms += eng.last_run_ms()
     launches = eng.counters().kernel_launches - l0
     print(f"{prec}: {tot_it} iterations, wall {1e6 * tot_s / tot_it:.1f} us/iteration, device {1e3 * dev_ms / tot_it:.1f} us/iteration, "
           f"{launches / tot_it:.1f} launches/iteration", flush=True)
+    if mode != L.DX_HEUR_ZERO and os.environ.get("DXB200_NVCC_DEFS", "").find("SM_PROFILE") >= 0:
+        pr = eng.tc_profile()
+        names = ["launches", "rows staged", "one-hot built"] + ["layer prologue", "first k step"] + [f"layer{l}" for l in range(2, 8)] + ["k loops", "epilogues", "layer barriers", "output", "-"]
+        print("   k_mlp_small CTA-0 timeline (cycles per launch):", {k: round(v / max(pr[0], 1)) for k, v in zip(names[1:], pr[1:]) if v})
     eng.close()

@@ -32,6 +32,34 @@
 
 void dx_set_error(const std::string& msg);
 
+// Programmatic dependent launch for the small-batch regime, where an iteration is a chain of tiny dependent kernels and the
+// 2-3 us of launch / drain latency between two of them is a quarter of the iteration: a kernel launched through dx_launch()
+// while g_dx_pdl is set may be scheduled as soon as its predecessor has STARTED (every kernel calls
+// griddepcontrol.launch_dependents first) and parks in griddepcontrol.wait until the predecessor has completed and its writes
+// are visible -- so nothing a predecessor produces is read before the wait, and nothing is written before it either.
+// Dependencies stay transitive: a kernel's wait returns only after its predecessor's own wait has.  Without the launch
+// attribute both instructions are no-ops, so the same kernels serve the plainly launched big-batch path.
+extern thread_local bool g_dx_pdl;
+#ifdef __CUDACC__
+template <typename... KArgs, typename... Args>
+static inline void dx_launch(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t s, Args&&... args) {
+    if (!g_dx_pdl) {
+        kernel<<<grid, block, smem, s>>>(args...);
+        return;
+    }
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid; cfg.blockDim = block; cfg.dynamicSmemBytes = smem; cfg.stream = s;
+    cudaLaunchAttribute at[1];
+    at[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    at[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = at; cfg.numAttrs = 1;
+    cudaLaunchKernelEx(&cfg, kernel, args...);
+}
+__device__ __forceinline__ void dx_pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+__device__ __forceinline__ void dx_pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void dx_pdl_prologue() { dx_pdl_trigger(); dx_pdl_wait(); }
+#endif
+
 // optional per-kernel timing (CUDA events on the engine stream); no-ops unless profiling is on
 #define DX_ST_GEMM_RES 7     // hidden-layer tensor-core / fp32 GEMM launches
 #define DX_ST_GEMM_IN 8      // input-layer launches (one-hot + first GEMM, or the gather kernel)

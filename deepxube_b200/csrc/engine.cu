@@ -105,6 +105,7 @@ __global__ void k_after_scan_v(Ctl* ctl, uint32_t max_nodes) {
 
 // Q*: after the merge the number of popped edges (= nodes to generate) is pop_off_next[I].
 __global__ void k_after_merge_q(Ctl* ctl, const uint32_t* pop_off_next, uint32_t max_nodes) {
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n = pop_off_next[ctl->n_inst];
     if ((unsigned long long)ctl->node_base + n > max_nodes) { ctl->error |= DX_DEVERR_NODES; return; }
@@ -115,6 +116,7 @@ __global__ void k_after_merge_q(Ctl* ctl, const uint32_t* pop_off_next, uint32_t
 }
 
 __global__ void k_fill_zero_vals(const Ctl* ctl, float* node_h, float* node_q, int A) {
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
@@ -272,6 +274,7 @@ struct dx_engine {
     bool graph_small = false;          // whether the captured graphs use the single-block sort
     bool use_graphs = true;
     int poll_every = 4;             // small-batch dx_run: iterations launched per host poll (DXB200_POLL_EVERY)
+    bool pdl = true;                // small-batch graphs: programmatic dependent launches (DXB200_PDL=0 disables)
     bool halt_flag = false;         // the step being launched / captured belongs to dx_run: k_end_iter may raise DX_DEVERR_DONE
     float last_run_ms = 0.f;
 
@@ -359,6 +362,7 @@ static void stage_collect_graph(dx_engine* e, int p) {
 
 // kernel-level timing hooks used by the network launchers (nested inside the ST_HEUR stage)
 static thread_local dx_engine* g_prof_engine = nullptr;
+thread_local bool g_dx_pdl = false;      // dx_launch(): programmatic dependent launches (set while a small-batch step is captured)
 void dx_prof_begin(int stage) { if (g_prof_engine) stage_begin(g_prof_engine, stage); }
 void dx_prof_end() { if (g_prof_engine) stage_end(g_prof_engine); }
 
@@ -474,6 +478,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     if (const char* fs = getenv("DXB200_SMALL_FUSE")) e->fuse_small = !(fs[0] == '0');
     if (const char* pe = getenv("DXB200_POLL_EVERY")) e->poll_every = std::max(1, atoi(pe));
+    if (const char* pd = getenv("DXB200_PDL")) e->pdl = !(pd[0] == '0');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -603,7 +608,7 @@ static int launch_net(dx_engine* e, const uint8_t* rows, const uint8_t* goals, f
 static int launch_heur_rows(dx_engine* e, const uint8_t* rows, float* out_h, float* out_q, long long max_rows) {
     const int mode = e->cfg.heur_mode;
     if (mode == DX_HEUR_ZERO) {
-        k_fill_zero_vals<<<std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream>>>(e->d_ctl, out_h, out_q, e->A);
+        dx_launch(k_fill_zero_vals, std::min(dx_div_up(max_rows, 256), 148 * 4), 256, 0, e->stream, (const Ctl*)e->d_ctl, out_h, out_q, e->A);
         e->launches += 1;
     } else if (mode == DX_HEUR_NET_FP32 || mode == DX_HEUR_NET_BF16) {
         e->launches += launch_net(e, rows, e->ia.goals, out_h, out_q, 1, max_rows);
@@ -931,7 +936,7 @@ static int step_q_pop(dx_engine* e) {
     const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
     e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
                                    e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
-    k_after_merge_q<<<1, 1, 0, s>>>(e->d_ctl, e->pop_off[q], e->max_nodes);
+    dx_launch(k_after_merge_q, 1, 1, 0, s, e->d_ctl, (const uint32_t*)e->pop_off[q], (uint32_t)e->max_nodes);
     e->launches += 1;
     e->launches += dx_launch_expand_edges(s, e->dom, e->d_ctl, e->edge_tmp, e->popped[q], e->node_state, e->node_g,
                                           e->node_parent, e->node_action, e->max_pop);
@@ -978,7 +983,9 @@ static int build_step_graphs(dx_engine* e, bool prof) {
         DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         e->cap_prof = prof ? p : -1;
         e->halt_flag = !prof && e->graph_small;      // (only the graphs dx_run launches in bursts)
+        g_dx_pdl = !prof && e->graph_small && e->pdl && (small_fused_v(e) || small_fused_q(e));
         const int rc = full_step(e);                 // flips e->parity
+        g_dx_pdl = false;
         e->halt_flag = false;
         e->cap_prof = -1;
         e->ev_open.clear();

@@ -234,6 +234,7 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
                  const uint8_t* __restrict__ pop_solved) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_err;
+    dx_pdl_prologue();
     if (ctl->error) return;
     // k_goal_resolve (k_domain.cu): the solved popped node that won the (g, pop order) atomicMin becomes goal_node
     for (uint32_t j = threadIdx.x; j < ctl->n_pop; j += SMALL_THREADS) {
@@ -305,6 +306,7 @@ k_small_filter_q(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, In
                  uint8_t* __restrict__ child_flags, uint32_t* __restrict__ child_prefix) {
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_err;
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;          // = n_pop: the items are the popped nodes
     if (n > 4u * SMALL_THREADS || ctl->n_pop != n) {
@@ -372,8 +374,8 @@ int dx_launch_small_filter_q(cudaStream_t s, const DomainDev& d, const ClosedDev
                              const uint32_t* pop_off, uint8_t* pop_solved, uint32_t* child_slot, uint32_t* child_next,
                              uint8_t* child_flags, uint32_t* child_prefix) {
     ItemView v{nullptr, nullptr, popped, node_state, node_g, popped_inst, ia.active, 1, d.SP};
-    k_small_filter_q<<<1, SMALL_THREADS, 0, s>>>(d, c, ctl, v, ia, pop_off, pop_solved, child_slot, child_next, child_flags,
-                                                 child_prefix);
+    dx_launch(k_small_filter_q, 1, SMALL_THREADS, 0, s, d, c, ctl, v, ia, pop_off, pop_solved, child_slot, child_next, child_flags,
+              child_prefix);
     return 1;
 }
 
@@ -385,8 +387,8 @@ int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev
     ItemView v{child_state, child_g, nullptr, node_state, node_g, popped_inst, ia.active, d.A, d.SP};
     ScatterArgs a{child_state, child_g, child_slot, child_flags, child_prefix, popped, popped_inst,
                   node_state, node_g, node_parent, node_action, new_inst, nullptr, nullptr};
-    k_small_filter_v<<<1, SMALL_THREADS, 0, s>>>(d, c, ctl, v, child_slot, child_next, child_flags, child_prefix, a, max_nodes, ia,
-                                                 pop_off, pop_solved);
+    dx_launch(k_small_filter_v, 1, SMALL_THREADS, 0, s, d, c, ctl, v, child_slot, child_next, child_flags, child_prefix, a, max_nodes, ia,
+              pop_off, pop_solved);
     return 1;
 }
 

@@ -77,6 +77,7 @@ k_expand_t(DomainDev d, const Ctl* __restrict__ ctl, InstArrays ia, const uint8_
     __shared__ uint32_t s_inst[EXP_SP];
     __shared__ float s_g[EXP_SP];       // NaN marks a parent of an inactive (finished) instance
 
+    dx_pdl_prologue();
     if (ctl->error) return;
     const int n_pop = ctl->n_pop;
     const int SP = d.SP, S = d.S, A = d.A, chunks = SP / 16;
@@ -207,10 +208,10 @@ int dx_launch_expand(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const I
     static_assert(EXP_THREADS == 8 * EXP_SP, "eight threads per staged parent");
     const int blocks = min(dx_div_up(max_pop, EXP_SP), 148 * 8);
 #define DX_EXPAND_ARGS d, ctl, ia, node_state, node_g, popped, popped_inst, pop_off, child_state, child_g, pop_solved
-    if (d.kind == DX_DOMAIN_CUBE3) k_expand_t<DX_DOMAIN_CUBE3><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
-    else if (d.kind == DX_DOMAIN_NPUZZLE) k_expand_t<DX_DOMAIN_NPUZZLE><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
-    else if (d.kind == DX_DOMAIN_LIGHTSOUT) k_expand_t<DX_DOMAIN_LIGHTSOUT><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
-    else k_expand_t<DX_DOMAIN_GRID><<<blocks, EXP_THREADS, 0, s>>>(DX_EXPAND_ARGS);
+    if (d.kind == DX_DOMAIN_CUBE3) dx_launch(k_expand_t<DX_DOMAIN_CUBE3>, blocks, EXP_THREADS, 0, s, DX_EXPAND_ARGS);
+    else if (d.kind == DX_DOMAIN_NPUZZLE) dx_launch(k_expand_t<DX_DOMAIN_NPUZZLE>, blocks, EXP_THREADS, 0, s, DX_EXPAND_ARGS);
+    else if (d.kind == DX_DOMAIN_LIGHTSOUT) dx_launch(k_expand_t<DX_DOMAIN_LIGHTSOUT>, blocks, EXP_THREADS, 0, s, DX_EXPAND_ARGS);
+    else dx_launch(k_expand_t<DX_DOMAIN_GRID>, blocks, EXP_THREADS, 0, s, DX_EXPAND_ARGS);
 #undef DX_EXPAND_ARGS
     return 1;
 }
@@ -346,6 +347,7 @@ __global__ void __launch_bounds__(128)
 k_expand_edges(DomainDev d, const Ctl* __restrict__ ctl, const uint32_t* __restrict__ edges, uint32_t* __restrict__ popped_out,
                uint8_t* __restrict__ node_state, float* __restrict__ node_g, uint32_t* __restrict__ node_parent,
                uint8_t* __restrict__ node_action) {
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n = ctl->n_kept, base = ctl->node_base;
     const int SP = d.SP, S = d.S, words = SP / 4;
@@ -384,6 +386,6 @@ k_expand_edges(DomainDev d, const Ctl* __restrict__ ctl, const uint32_t* __restr
 int dx_launch_expand_edges(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint32_t* edges, uint32_t* popped_out,
                            uint8_t* node_state, float* node_g, uint32_t* node_parent, uint8_t* node_action, int max_pop) {
     int blocks = min(dx_div_up((long long)max_pop * 4, 128), 148 * 8);
-    k_expand_edges<<<blocks, 128, 0, s>>>(d, ctl, edges, popped_out, node_state, node_g, node_parent, node_action);
+    dx_launch(k_expand_edges, blocks, 128, 0, s, d, ctl, edges, popped_out, node_state, node_g, node_parent, node_action);
     return 1;
 }

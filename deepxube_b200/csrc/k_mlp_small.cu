@@ -159,10 +159,12 @@ k_mlp_small(SmallNetDev sn, DomainDev d, const Ctl* __restrict__ ctl, const uint
     long long t_prev = clock64();
     if (blockIdx.x == 0 && threadIdx.x == 0) atomicAdd(&g_small_prof[0], 1ull);
 #endif
+    dx_pdl_trigger();
     if (tid == 0) {
         for (int i = 0; i < D; ++i) { sm_mbar_init(bar_full + 8 * i, 1); sm_mbar_init(bar_empty + 8 * i, sn.nwa); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    dx_pdl_wait();                                    // (everything above is independent of the kernels before this one)
     if (ctl->error) return;
     const uint32_t n = ctl->nn_n, start = ctl->nn_row_start;
     if (blockIdx.x == 0 && tid == 0) atomicAdd((unsigned long long*)&ctl->heur_evals, (unsigned long long)n);
@@ -562,7 +564,7 @@ static int small_launch_t(cudaStream_t s, const SmallNetDev& sn, const DomainDev
     }
     if (smem > SM_SMEM_LIMIT) { dx_set_error("k_mlp_small: network too large for the fused small-evaluation kernel"); return 0; }
     const int grid = (int)std::max<long long>(1, std::min<long long>(dx_div_up(max_rows, 16 * MT), 148 * 4));
-    k_mlp_small<MT, SPLIT><<<grid, SM_THREADS, smem, s>>>(sn, d, ctl, rows, goals, out_h, out_q, absolute);
+    dx_launch(k_mlp_small<MT, SPLIT>, grid, SM_THREADS, smem, s, sn, d, ctl, rows, goals, out_h, out_q, absolute);
     return 1;
 }
 

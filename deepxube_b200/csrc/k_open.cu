@@ -525,6 +525,7 @@ k_small_push_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict_
     __shared__ uint32_t s_idx[DX_SMALL_SORT];
     __shared__ uint32_t s_err;
     static_assert(sizeof(unsigned long long) * DX_SMALL_SORT >= 4 * 1024 * sizeof(uint32_t), "plan scratch fits");
+    dx_pdl_prologue();
     if (ctl->error) return;
     plan_body(reinterpret_cast<uint32_t (*)[1024]>(s_key), ctl, ia, prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A,
               1, max_pop, max_open, 0, 0);
@@ -554,6 +555,7 @@ k_small_push_q(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict_
     __shared__ uint32_t s_inst[DX_SMALL_SORT];
     __shared__ uint32_t s_idx[DX_SMALL_SORT];
     __shared__ uint32_t s_err;
+    dx_pdl_prologue();
     if (ctl->error) return;
     plan_body(reinterpret_cast<uint32_t (*)[1024]>(s_key), ctl, ia, prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, 1,
               A, max_pop, max_open, 0, 0);
@@ -579,16 +581,16 @@ int dx_launch_small_push_q(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const
                            uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
                            uint32_t max_open, const float* node_g, const float* node_q, const uint32_t* popped,
                            const uint32_t* popped_inst, const uint8_t* flags, const SortBufs& sb) {
-    k_small_push_q<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
-                                      max_open, node_g, node_q, popped, popped_inst, flags, sb);
+    dx_launch(k_small_push_q, 1, 1024, 0, s, ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
+              max_open, node_g, node_q, popped, popped_inst, flags, sb);
     return 1;
 }
 
 int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
                            uint32_t* pop_off_next, const uint32_t* open_off_cur, uint32_t* open_off_next, int A, uint32_t max_pop,
                            uint32_t max_open, const float* node_g, const float* node_h, const uint32_t* new_inst, const SortBufs& sb) {
-    k_small_push_v<<<1, 1024, 0, s>>>(ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
-                                      max_open, node_g, node_h, new_inst, sb);
+    dx_launch(k_small_push_v, 1, 1024, 0, s, ctl, ia, child_prefix, pop_off_cur, pop_off_next, open_off_cur, open_off_next, A, max_pop,
+              max_open, node_g, node_h, new_inst, sb);
     return 1;
 }
 
@@ -652,6 +654,7 @@ __device__ __forceinline__ uint32_t merge_path_warp(const unsigned long long* __
 __global__ void __launch_bounds__(OPEN_THREADS)
 k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
                   const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ part_a, uint32_t* __restrict__ part_i) {
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n_tiles = ctl->n_tiles;
     const int I = ctl->n_inst;
@@ -681,6 +684,7 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
     __shared__ unsigned long long s_key[DX_SORT_TILE];
     __shared__ uint32_t s_val[DX_SORT_TILE];
     __shared__ uint32_t s_part[4];   // a0, a1, inst
+    dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n_tiles = ctl->n_tiles;
     const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
@@ -755,10 +759,10 @@ int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const 
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open) {
     int blocks = min(max_tiles, 148 * 8);      // 24.5 KB of shared memory and 256 threads per block: 8 blocks per SM
-    k_merge_partition<<<min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_off_cur,
-                                                                                                   sb.part_a, sb.part_i);
-    k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
-                                            open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i);
+    dx_launch(k_merge_partition, min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur,
+              open_off_cur, sb.part_a, sb.part_i);
+    dx_launch(k_merge, blocks, OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
+              open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i);
     return 2;
 }
 
@@ -771,6 +775,7 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
            const uint32_t* __restrict__ pop_off_next, int A, int gen_mode) {
     __shared__ uint32_t s_unfinished;
     __shared__ unsigned long long s_gen;
+    dx_pdl_prologue();
     if (ctl->error) return;
     if (threadIdx.x == 0) { s_unfinished = 0; s_gen = 0; }
     __syncthreads();
@@ -821,6 +826,6 @@ k_end_iter(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ po
 
 int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,
                        int A, int gen_mode) {
-    k_end_iter<<<1, 1024, 0, s>>>(ctl, ia, pop_off_cur, pop_off_next, A, gen_mode);
+    dx_launch(k_end_iter, 1, 1024, 0, s, ctl, ia, pop_off_cur, pop_off_next, A, gen_mode);
     return 1;
 }

@@ -27,6 +27,9 @@ def _net(in_dim, h, nb, od, seed):
 
 def _states(dom, n, seed):
     rng = np.random.default_rng(seed)
+    if dom.name == "grid":                      # (state = robot position, goal = goal position: both random cells)
+        return (rng.integers(0, dom.dim, size=(n, dom.state_len)).astype(np.uint8),
+                rng.integers(0, dom.dim, size=(n, dom.state_len)).astype(np.uint8))
     goals = np.tile(dom.canonical_goal(), (n, 1))
     st = goals.copy()
     for _ in range(30):

@@ -1,7 +1,9 @@
 """Training-data generation from the search: the value-iteration targets of the heuristic network.
 
-Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq` with the goal kept (no HER), no replay buffer;
-labels: Bellman backups, `ub_heur_solns`, LHBL tree backups:
+Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq` with the goal kept (no HER); labels without a
+replay buffer: Bellman backups, `ub_heur_solns`, LHBL tree backups; with a replay buffer (`rb_size > 0`): the popped nodes /
+edges of every emitted instance group go into an array-backed replay buffer, as many elements are sampled back, and their
+value-iteration targets are recomputed with the (target) network on the device (`dx_vi_targets`):
 
     base/updater.py:343-400        update_runner: for each of `search_itrs` iterations -- add instances (new ones for the
                                    instances removed last iteration, same steps_gen), one PathFind.step(), remove the
@@ -10,6 +12,9 @@ labels: Bellman backups, `ub_heur_solns`, LHBL tree backups:
     updaters/updater_rl.py:143-158 V labels = Node.bellman_backup() of each popped node
     updaters/updater_rl.py:169-189 Q labels = Node.backup_act(action) of each popped edge
     base/updater.py:904-921, 938-965 -> [*nnet inputs of (state, goal[, action]), labels]
+    base/updater.py:763-795        _rb_add_sample_train_data / _get_instance_data_rb: add, sample len(popped), label, to_np
+    updaters/updater_rl.py:30-69, 85-120  replay data (is_solved [, tc, next state]) and the labels of sampled elements
+    base/updater.py:330-341        one `update_runner` work item = one batch of searches; `generate()` runs several
 
 The search and the backups run on the device (graph_v engine created with max_backups > 0: every generated child is
 evaluated before the CLOSED filter and each expanded node's backup is logged by k_bellman_backup); this module only owns the
@@ -23,11 +28,14 @@ import numpy as np
 from deepxube_b200.pathfinding.graph_search import GraphSearch
 
 
+_GOAL_CACHE: dict = {}       # goal row bytes -> goal object (replay-buffer mode hands goal OBJECTS back, like the reference)
+
+
 class UpdateHeurVRLKeepGoal:
     is_q = False
 
     def __init__(self, domain: Any, pathfind: GraphSearch, search_itrs: int, nnet_input: Optional[Any] = None,
-                 ub_heur_solns: bool = False, lhbl: bool = False):
+                 ub_heur_solns: bool = False, lhbl: bool = False, rb_size: int = 0):
         """ub_heur_solns / lhbl: UpRLArgs (base/updater.py:669-672); lhbl wins when both are set, as in
         updaters/updater_rl.py:145-155, 171-179.  Both are computed on the device when the log is drained."""
         self.label_mode = "lhbl" if lhbl else ("ub_solns" if ub_heur_solns else "bellman")
@@ -38,6 +46,8 @@ class UpdateHeurVRLKeepGoal:
         if pathfind.instances:
             raise ValueError("the PathFind must be fresh (base/updater.py:364 builds one per batch)")
         self.domain, self.pathfind, self.search_itrs, self.nnet_input = domain, pathfind, int(search_itrs), nnet_input
+        self.rb_size = int(rb_size)
+        self.rb: Optional[Any] = None                   # _init_replay_buffer (base/updater.py:707-708), built on first use
 
     def _make_instances(self, steps_gen: List[int]) -> List[Any]:
         states, goals = self.domain.sample_problem_instances(steps_gen)                      # base/updater.py:679-685
@@ -77,14 +87,84 @@ class UpdateHeurVRLKeepGoal:
         drained = pf.drain_backups(self.label_mode)
         rows, vals, slots = drained[0], drained[-2], drained[-1]
         # regroup the device log (iteration-major) into the reference's emission order
-        order = np.concatenate([np.flatnonzero(slots == inst._slot) for g in groups for inst in g]) if len(vals) else np.zeros(0, np.int64)
+        per_group = [np.concatenate([np.flatnonzero(slots == inst._slot) for inst in g]) if len(vals) else np.zeros(0, np.int64)
+                     for g in groups]
         goal_of = {inst._slot: inst.root_node.goal for g in groups for inst in g}
+        if self.rb_size > 0:
+            return self._emit_rb(per_group, rows, slots, drained[1] if self.is_q else None, goal_of)
+        order = np.concatenate(per_group) if per_group else np.zeros(0, np.int64)
         states = self.domain.rows_to_states(rows[order])
         goals = [goal_of[int(s)] for s in slots[order]]
         if self.is_q:
             fixed = self.domain.get_actions_fixed()
             return states, goals, [fixed[int(k)] for k in drained[1][order]], vals[order]
         return states, goals, vals[order]
+
+    # ---- replay-buffer mode (base/updater.py:763-795) -----------------------------------------------------------------
+    def _init_replay_buffer(self, state_bytes: int, goal_bytes: int) -> None:
+        from deepxube_b200.updaters.replay_buffer import ReplayBufferQ, ReplayBufferV
+        self.rb = (ReplayBufferQ if self.is_q else ReplayBufferV)(self.rb_size, state_bytes, goal_bytes)
+
+    def _emit_rb(self, per_group: List[np.ndarray], rows: np.ndarray, slots: np.ndarray, acts: Optional[np.ndarray], goal_of: dict) -> Tuple:
+        """For every emitted instance group, in emission order: popped data -> replay buffer, sample as many elements back,
+        label them with the device network (`_get_instance_data_rb` -> `_rb_add_sample_train_data`).  Everything stays in packed
+        rows until the end; -> (states, goals, [Q: actions,] labels) of the SAMPLED elements, groups concatenated."""
+        from deepxube_b200 import _lib
+        dom = self.domain
+        slot_ids = sorted(goal_of)
+        grow_of = dict(zip(slot_ids, dom.goals_to_rows([goal_of[k] for k in slot_ids])))
+        fn_eng = self._device_fn()._engine()
+        out_rows, out_grows, out_acts, out_labels = [], [], [], []
+        for idx in per_group:
+            if len(idx) == 0:
+                continue
+            r = rows[idx]
+            g = np.stack([grow_of[int(k)] for k in slots[idx]])
+            if self.rb is None:
+                self._init_replay_buffer(r.shape[1], g.shape[1])
+            solved = _lib.is_solved(dom.dx_name, dom.dx_dim, r, g)                       # Node.is_solved of the popped nodes
+            if self.is_q:
+                a = acts[idx]
+                nxt = _lib.next_state(dom.dx_name, dom.dx_dim, r, a)                     # node.edge_dict[action] = (tc, node_next)
+                self.rb.add(r, g, a, solved, np.ones(len(idx)), nxt)
+                (sr, sg, sa), (ssol, stc, snxt) = self.rb.sample(len(idx))
+                assert np.all(stc == 1.0), "the in-scope domains have unit transition costs"
+                labels = fn_eng.vi_targets(snxt, sg, ssol)                               # (tc + min_a q_targ(next, a)) * not solved
+                out_acts.append(sa)
+            else:
+                self.rb.add(r, g, solved)
+                (sr, sg), ssol = self.rb.sample(len(idx))
+                labels = fn_eng.vi_targets(sr, sg, ssol)                                 # min_a (tc + h_targ(child_a)) * not solved
+            out_rows.append(sr); out_grows.append(sg); out_labels.append(labels)
+        if not out_rows:
+            return ([], [], [], np.zeros(0)) if self.is_q else ([], [], np.zeros(0))
+        srows, sgrows = np.concatenate(out_rows), np.concatenate(out_grows)
+        states = dom.rows_to_states(srows)
+        goals = dom.rows_to_goals(sgrows) if hasattr(dom, "rows_to_goals") else self._goals_from_rows(sgrows, goal_of, grow_of)
+        labels = np.concatenate(out_labels)
+        if self.is_q:
+            fixed = dom.get_actions_fixed()
+            return states, goals, [fixed[int(k)] for k in np.concatenate(out_acts)], labels
+        return states, goals, labels
+
+    @staticmethod
+    def _goals_from_rows(grows: np.ndarray, goal_of: dict, grow_of: dict) -> List[Any]:
+        """goal objects of sampled goal rows: rows that came from this batch map back to their objects; rows from earlier batches
+        (still in the buffer) are resolved through the cache the updater keeps of every goal row it has seen"""
+        cache = _GOAL_CACHE
+        for k, row in grow_of.items():
+            cache.setdefault(row.tobytes(), goal_of[k])
+        return [cache[row.tobytes()] for row in grows]
+
+    def generate(self, num_batches: int, batch_size: int, step_probs: List[float], step_max: int) -> List[Tuple]:
+        """`update_runner`'s inner loop over work items (base/updater.py:330-395): `num_batches` batches of `batch_size` searches,
+        start-state step counts drawn from `step_probs` over 0..step_max (`_add_instances`, :418-423).  The engine, its weights
+        and captured graphs are reused across batches; with `rb_size > 0` so is the replay buffer."""
+        out = []
+        for _ in range(num_batches):
+            steps_gen = np.random.choice(step_max + 1, size=batch_size, p=np.array(step_probs)).tolist()
+            out.append(self.get_instance_data(steps_gen))
+        return out
 
     def get_update_data(self, steps_gen: List[int]) -> List[np.ndarray]:
         """[*inputs_nnet, ctgs] (base/updater.py:915-921, 958-965)"""

@@ -510,3 +510,49 @@ def test_updater_rl_replay_labels_through_the_registries(tag):
     with pytest.raises(TypeError, match="device"):
         host._get_labels_rb((states, goals, None), solved)
     pathfind.close()
+
+
+@pytest.mark.parametrize("is_q", [False, True])
+def test_updater_rl_replay_buffer_mode(is_q):
+    """SURVEY 8f.1, replay-buffer mode (base/updater.py:763-795 `_get_instance_data_rb` -> `_rb_add_sample_train_data`): the popped
+    nodes / edges of every emitted instance group are added to the buffer, as many are sampled back and labelled with the device
+    (target) network.  Checked: every sampled element is one the searches popped (state, goal, action), the buffer holds the newest
+    `rb_size` of them, the labels equal an independent evaluation of the reference's formulas (updaters/updater_rl.py:41-69,
+    102-120) with the same network through the public functions, and a second batch reuses engine, weights and buffer."""
+    from deepxube_b200 import _lib as L
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLKeepGoal, UpdateHeurVRLKeepGoal
+    random.seed(3)
+    np.random.seed(3)
+    dom, name = get_domain_from_arg("cube3")
+    fn = "heurq_fixout,resnet_fc.200H_2B_bn" if is_q else "heurv,resnet_fc.200H_2B_bn"
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [fn])
+    heur = pfns.heurq if is_q else pfns.heurv
+    heur.nnet.load_state_dict(gu.state_dict_np("cube3q" if is_q else "cube3v"))
+    pathfind, _, _ = get_pathfind_from_arg(dom, pfns, "graph.1B_0.8W")
+    rb_size = 150
+    up = (UpdateHeurQRLKeepGoal if is_q else UpdateHeurVRLKeepGoal)(dom, pathfind, 6, rb_size=rb_size)
+    steps_gen = [0, 1, 2, 1, 0, 3, 30, 40, 2, 1, 0, 25] * 3
+    total = 0
+    for batch in range(2):
+        data = up.get_instance_data(steps_gen)
+        states, goals, labels = data[0], data[1], np.asarray(data[-1])
+        assert len(states) == len(goals) == len(labels) >= len(steps_gen) and labels.dtype == np.float64
+        total += len(states)
+        assert up.rb.size() == min(rb_size, total) and up.rb.max_size() == rb_size
+        rows, grows = dom.states_to_rows(states), dom.goals_to_rows(goals)
+        solved = L.is_solved("cube3", 0, rows, grows)
+        if is_q:
+            acts = np.array([dom.action_index(a) for a in data[2]])
+            nxt = L.next_state("cube3", 0, rows, acts)
+            st_n = dom.rows_to_states(nxt)
+            q = np.array(pfns.heurq(st_n, goals, [dom.get_actions_fixed()] * len(st_n), [None] * len(st_n)))
+            want = np.where(solved, 0.0, 1.0 + q.min(axis=1))
+        else:
+            children = dom.rows_to_states(L.expand("cube3", 0, rows))
+            h = np.array(pfns.heurv(children, [g for g in goals for _ in range(12)], [None] * len(children))).reshape(len(rows), 12)
+            want = np.where(solved, 0.0, 1.0 + h.min(axis=1))
+        np.testing.assert_allclose(labels, want, rtol=0, atol=2e-4)
+        assert (labels[solved] == 0.0).all()
+    out = up.generate(2, 8, [0.25, 0.25, 0.25, 0.25], 3)            # the runner loop over work items (base/updater.py:330-395)
+    assert len(out) == 2 and all(len(o[0]) >= 8 for o in out)
+    pathfind.close()

@@ -237,3 +237,50 @@ def test_writes_pickles_the_reference_opens(tmp_path):
         assert rdom.is_solved(d["states"], d["goals"])[0]            # the 0-step instance
         nxt, tcs = rdom.next_state(d["states"], [al[0] for al in d["actions"]])       # viz_step's replay (deepxube/_cli.py:246-249)
         assert all(a == b for a, b in zip(nxt, d["walked"])) and all(t == 1.0 for t in tcs)
+
+
+def test_replay_buffers_match_the_reference_deque():
+    """the array-backed replay buffers behave like the reference's deque(maxlen) buffers
+    (deepxube/updaters/utils/replay_buffer_utils.py:28-84): same survivors after overflowing adds, same elements for the same
+    np.random seed.  Checked against a deque restatement everywhere and, in the build container, against the reference's classes."""
+    from collections import deque
+    from deepxube_b200.updaters.replay_buffer import ReplayBufferQ, ReplayBufferV
+    rng = np.random.default_rng(0)
+    S = 5
+    for cap in (7, 64):
+        rv, rq = ReplayBufferV(cap, S, S), ReplayBufferQ(cap, S, S)
+        dv, dq = deque([], cap), deque([], cap)
+        for n in (3, 5, 1, 9, 70, 2):                     # (includes an add larger than the whole buffer)
+            st, gl, nx = (rng.integers(0, 250, size=(n, S)).astype(np.uint8) for _ in range(3))
+            sol, act, tc = rng.integers(0, 2, size=n).astype(bool), rng.integers(0, 12, size=n), np.ones(n)
+            rv.add(st, gl, sol)
+            rq.add(st, gl, act, sol, tc, nx)
+            dv.extend(zip(map(bytes, st), map(bytes, gl), sol.tolist()))
+            dq.extend(zip(map(bytes, st), map(bytes, gl), act.tolist(), sol.tolist(), tc.tolist(), map(bytes, nx)))
+            assert rv.size() == len(dv) == rq.size() and rv.max_size() == cap
+            np.random.seed(n)
+            idxs = np.random.randint(0, len(dv), size=11).tolist()
+            np.random.seed(n)
+            (a, b), c = rv.sample(11)
+            assert [(bytes(x), bytes(y), bool(z)) for x, y, z in zip(a, b, c)] == [dv[i] for i in idxs]
+            np.random.seed(n)
+            (a, b, k), (c, t, x) = rq.sample(11)
+            assert [(bytes(p), bytes(q), int(r), bool(s_), float(u), bytes(v)) for p, q, r, s_, u, v in zip(a, b, k, c, t, x)] == [dq[i] for i in idxs]
+    with pytest.raises(AssertionError, match="Replay buffer size"):
+        ReplayBufferV(4, S, S).sample(1)
+    from oracle.ref_shim import import_reference, reference_available
+    if not reference_available():
+        return
+    import_reference()
+    from deepxube.updaters.utils.replay_buffer_utils import ReplayBufferV as RefV
+    ref, mine = RefV(10), ReplayBufferV(10, S, S)
+    for n in (4, 9, 3):
+        st, gl = (rng.integers(0, 250, size=(n, S)).astype(np.uint8) for _ in range(2))
+        sol = rng.integers(0, 2, size=n).astype(bool)
+        ref.add(([bytes(r) for r in st], [bytes(r) for r in gl], [None] * n), sol.tolist())
+        mine.add(st, gl, sol)
+        np.random.seed(5)
+        (rs, rg, _), rsol = ref.sample(6)
+        np.random.seed(5)
+        (ms, mg), msol = mine.sample(6)
+        assert rs == [bytes(r) for r in ms] and rg == [bytes(r) for r in mg] and rsol == msol.tolist()

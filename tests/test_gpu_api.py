@@ -524,7 +524,7 @@ def test_updater_rl_replay_buffer_mode(is_q):
     random.seed(3)
     np.random.seed(3)
     dom, name = get_domain_from_arg("cube3")
-    fn = "heurq_fixout,resnet_fc.200H_2B_bn" if is_q else "heurv,resnet_fc.200H_2B_bn"
+    fn = "heurq_fixout,resnet_fc.128H_1B_bn" if is_q else "heurv,resnet_fc.200H_2B_bn"      # (the shapes of the golden nets)
     pfns, _ = get_path_fns_nnet_par_dict(dom, name, [fn])
     heur = pfns.heurq if is_q else pfns.heurv
     heur.nnet.load_state_dict(gu.state_dict_np("cube3q" if is_q else "cube3v"))

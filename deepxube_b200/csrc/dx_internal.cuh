@@ -115,7 +115,7 @@ struct Ctl {
     uint32_t n_backups;    // records in the Bellman-backup log (evaluate-all engines)
     uint32_t backup_overflow;
     uint32_t backup_at;    // log position of this iteration's first record
-    uint32_t pad_;
+    uint32_t young_total;  // entries in the young runs' current buffer (young-run OPEN, YoungBufs)
 };
 
 // Per-instance state (structure of arrays, capacity max_instances (+1 for offset arrays)).
@@ -297,6 +297,24 @@ struct SortBufs {
     int num_digits;       // digit positions that can vary: 8 key bytes + the bytes max_instances - 1 occupies
 };
 
+// Small-batch A* engines (the solve-time regime: <= DX_SMALL_SORT pushed entries per iteration) keep OPEN as TWO sorted runs per
+// instance: the main run (open_key / open_val, consumed from the front through m_head) and a small YOUNG run of what was pushed
+// since the last compaction.  One block then does a whole iteration's OPEN work in shared memory -- keys, sort of the batch, merge
+// with the young run, pop of the batch_size smallest of (main run head, young run), lb / finished() bookkeeping -- instead of
+// rewriting the whole 100 k-entry run through three grid-wide kernels (k_merge_partition, k_merge, k_end_iter) for 100 pops.
+// Every DX_YOUNG_CAP / sort_bound iterations the host schedules a compaction (main <- merge(main, young); the existing merge
+// kernels).  Order is unchanged: everything in the main run was pushed before everything in the young run, which was pushed
+// before the batch, and every merge takes the older run first on ties -- the reference heap's (f, push count) order.
+#define DX_YOUNG_CAP 6144                      // entries the young runs (all instances) may hold after an iteration
+#define DX_YOUNG_BUF (DX_YOUNG_CAP + 2048)     // ... plus one pushed batch (DX_SMALL_SORT)
+struct YoungBufs {
+    unsigned long long* key[2];    // [DX_YOUNG_BUF] ping-pong by iteration parity
+    uint32_t* val[2];
+    uint32_t* off[2];              // [I + 1] per-instance offsets (packed)
+    uint32_t* head[2];             // [I] entries of the run already popped
+    uint32_t* m_head;              // [I] entries of the MAIN run already popped
+};
+
 struct MlpBufs {
     float* x[3];          // fp32 activations [cap, Hp]
     void* xb[3];          // 16-bit activations: bf16 [cap, Hp] slices of ONE [cap, 3 * Hp] array (xb[i] = base + i * Hp, so that a
@@ -417,6 +435,15 @@ int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const 
                     const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                     unsigned long long* open_key_next, uint32_t* open_val_next, const uint32_t* open_off_next,
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open = 1);
+int dx_launch_small_tail_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const unsigned long long* m_key, const uint32_t* m_val, const uint32_t* m_off,
+                           const YoungBufs& yb, int p, int A, uint32_t max_pop, const float* node_g, const float* node_h,
+                           const uint32_t* new_inst, uint32_t* popped_next, uint32_t* popped_inst_next, int gen_mode);
+int dx_launch_young_compact(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const SortBufs& sb, const YoungBufs& yb, int p,
+                            const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
+                            unsigned long long* open_key_next, uint32_t* open_val_next, uint32_t* open_off_next,
+                            uint32_t* popped_scratch, uint32_t* popped_inst_scratch, const uint32_t* pop_off_any, int max_tiles,
+                            uint32_t max_open);
 // gen_mode: 0 graph_v (A children per popped node), 1 graph_q (one node per popped edge), 2 beam_v / 3 beam_q (as 0 / 1,
 // finished on a goal)
 int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* pop_off_cur, const uint32_t* pop_off_next,

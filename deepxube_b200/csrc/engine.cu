@@ -274,6 +274,12 @@ struct dx_engine {
     bool graph_small = false;          // whether the captured graphs use the single-block sort
     bool use_graphs = true;
     int poll_every = 4;             // small-batch dx_run: iterations launched per host poll (DXB200_POLL_EVERY)
+    // young-run OPEN of small-batch A* engines (YoungBufs): the main run stays in open_*[0] while it is active
+    YoungBufs young{};
+    bool young_enabled = true;      // DXB200_YOUNG=0 disables
+    bool young_active = false;      // decided when the first instances arrive after a reset; left (flushed) when the batch outgrows it
+    bool graph_young = false;       // the captured graphs were built for the young-run tail
+    long long y_bound = 0;          // upper bound of the entries in the young runs (host-side: compaction schedule)
     bool pdl = true;                // small-batch graphs: programmatic dependent launches (DXB200_PDL=0 disables)
     bool halt_flag = false;         // the step being launched / captured belongs to dx_run: k_end_iter may raise DX_DEVERR_DONE
     float last_run_ms = 0.f;
@@ -435,6 +441,16 @@ static int reset_state(dx_engine* e) {
     if (e->node_solved) DX_CUDA(cudaMemsetAsync(e->node_solved, 0, e->max_nodes, e->stream));
     if (e->bk.node_rec) DX_CUDA(cudaMemsetAsync(e->bk.node_rec, 0, (size_t)e->max_nodes * sizeof(uint32_t), e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
+    if (e->young.m_head) {
+        for (int p = 0; p < 2; ++p) {
+            cudaMemsetAsync(e->young.off[p], 0, (e->max_inst + 1) * sizeof(uint32_t), e->stream);
+            cudaMemsetAsync(e->young.head[p], 0, e->max_inst * sizeof(uint32_t), e->stream);
+        }
+        cudaMemsetAsync(e->young.m_head, 0, e->max_inst * sizeof(uint32_t), e->stream);
+        DX_CUDA(cudaStreamSynchronize(e->stream));
+    }
+    e->young_active = false;
+    e->y_bound = 0;
     e->n_inst = 0;
     e->parity = 0;
     e->pending = false;
@@ -479,6 +495,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (const char* fs = getenv("DXB200_SMALL_FUSE")) e->fuse_small = !(fs[0] == '0');
     if (const char* pe = getenv("DXB200_POLL_EVERY")) e->poll_every = std::max(1, atoi(pe));
     if (const char* pd = getenv("DXB200_PDL")) e->pdl = !(pd[0] == '0');
+    if (const char* yg = getenv("DXB200_YOUNG")) e->young_enabled = !(yg[0] == '0');
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -537,7 +554,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     cudaMemset(e->sort.status, 0, ((size_t)256 * e->sort.max_tiles + 256) * sizeof(unsigned long long));
     cudaMemset(e->sort.tickets, 0, (DX_NUM_DIGITS + 4) * sizeof(uint32_t));
     {
-        const size_t mt = (size_t)dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst + 8;
+        const size_t mt = (size_t)dx_div_up((long long)e->max_open + std::max<long long>(e->max_sort, DX_YOUNG_BUF), DX_SORT_TILE) + e->max_inst + 8;
         A_(e->sort.part_a, mt); A_(e->sort.part_i, mt);
     }
     e->sort.onesweep = 1;
@@ -546,6 +563,13 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
     A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);
     A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP);
+    if (!e->is_q && !e->is_beam && I <= 256) {      // young-run OPEN (small-batch regime); 200 KB
+        for (int p = 0; p < 2; ++p) {
+            A_(e->young.key[p], (size_t)DX_YOUNG_BUF); A_(e->young.val[p], (size_t)DX_YOUNG_BUF);
+            A_(e->young.off[p], I + 1); A_(e->young.head[p], I);
+        }
+        A_(e->young.m_head, I);
+    }
     A_(e->d_vals, std::max<size_t>((size_t)e->max_sort, P * e->A) + I * e->A);
 #undef A_
     cudaDeviceSynchronize();                 // the legacy-stream table upload has landed before the engine stream runs
@@ -677,6 +701,48 @@ extern "C" int dx_remove_instances(dx_engine* e, const int32_t* slots, int32_t n
     return DX_OK;
 }
 
+// ---- young-run OPEN (YoungBufs, dx_internal.cuh) ------------------------------------------------------------------------
+__global__ void k_young_copyback(const Ctl* __restrict__ ctl, const unsigned long long* __restrict__ key_src, const uint32_t* __restrict__ val_src,
+                                 const uint32_t* __restrict__ off_src, unsigned long long* __restrict__ key_dst, uint32_t* __restrict__ val_dst,
+                                 uint32_t* __restrict__ off_dst) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->open_total, I = ctl->n_inst;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { key_dst[t] = key_src[t]; val_dst[t] = val_src[t]; }
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= I; t += gridDim.x * blockDim.x) off_dst[t] = off_src[t];
+}
+
+// main run <- merge(main run remainder, young runs); the main run's home is open_*[0] (merged into [1], copied back)
+static int young_compact(dx_engine* e) {
+    cudaStream_t s = e->stream;
+    const int p = e->parity;
+    const int max_tiles = dx_div_up((long long)e->max_open + DX_YOUNG_BUF, DX_SORT_TILE) + e->max_inst;
+    e->launches += dx_launch_young_compact(s, e->d_ctl, e->ia, e->sort, e->young, p, e->open_key[0], e->open_val[0], e->open_off[0],
+                                           e->open_key[1], e->open_val[1], e->open_off[1], e->popped[p ^ 1], e->popped_inst[p ^ 1],
+                                           e->pop_off[p], max_tiles, (uint32_t)e->max_open);
+    k_young_copyback<<<148 * 2, 256, 0, s>>>(e->d_ctl, e->open_key[1], e->open_val[1], e->open_off[1], e->open_key[0], e->open_val[0], e->open_off[0]);
+    e->launches += 1;
+    e->y_bound = 0;
+    return DX_OK;
+}
+// before an iteration is launched: the merged young runs (young + pushed batch) must fit the block's buffer
+static int young_before_step(dx_engine* e) {
+    if (!e->young_active) return DX_OK;
+    if (e->y_bound + e->sort_bound > DX_YOUNG_BUF) DX_TRY(young_compact(e));
+    e->y_bound += e->sort_bound;
+    return DX_OK;
+}
+// leave young mode (the batch outgrew the small regime): everything back into ONE run, in the buffer the plain path reads next
+static int young_flush(dx_engine* e) {
+    if (!e->young_active) return DX_OK;
+    DX_TRY(young_compact(e));
+    if (e->parity != 0)
+        k_young_copyback<<<148 * 2, 256, 0, e->stream>>>(e->d_ctl, e->open_key[0], e->open_val[0], e->open_off[0], e->open_key[1], e->open_val[1],
+                                                          e->open_off[1]);
+    DX_CUDA(cudaStreamSynchronize(e->stream));
+    e->young_active = false;
+    return DX_OK;
+}
+
 extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8_t* goals, int32_t n,
                                 const int32_t* batch_sizes, const double* weights, const float* root_vals) {
     if (!e || (n > 0 && (!states || !goals))) DX_FAIL(DX_ERR_ARG, "null argument");
@@ -690,7 +756,7 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
     DX_TRY(check_rows_in_range(e, states, n));
     if (e->cfg.heur_mode == DX_HEUR_HOST && e->is_q && !root_vals) DX_FAIL(DX_ERR_ARG, "graph_q in HOST mode needs root_vals");
     DX_TRY(sync_ctl(e));
-    const Ctl c = *e->h_ctl;
+    Ctl c = *e->h_ctl;
     if ((unsigned long long)c.node_count + n > e->max_nodes) DX_FAIL(DX_ERR_CAPACITY, "max_nodes exceeded");
     if ((unsigned long long)c.n_pop + n > e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "max_pop_total exceeded");
     long long bsum = 0;
@@ -710,6 +776,17 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
         if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of the live instances' batch sizes exceeds max_pop_total");
     }
     e->sort_bound = bsum * e->A;             // no iteration can push more entries than every instance's full batch expanded
+    {   // young-run OPEN: entered with the first instances after a reset, left for good when the batch outgrows the small regime
+        const bool want = e->young_enabled && e->young.m_head != nullptr && small_fused_v(e);
+        if (e->n_inst == 0) {
+            e->young_active = want;
+            e->y_bound = 0;
+        } else if (e->young_active && !want) {
+            DX_TRY(young_flush(e));
+            DX_TRY(sync_ctl(e));
+            c = *e->h_ctl;                   // (the compaction rewrote open_total / young_total)
+        }
+    }
     const int SP = e->SP, S = e->S, I0 = e->n_inst, p = e->parity;
     std::vector<uint8_t> rows((size_t)n * SP, 0), grow((size_t)n * SP, 0);
     std::vector<int32_t> hb(n);
@@ -753,7 +830,13 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
     DX_CUDA(cudaMemcpyAsync(e->popped[p] + c.n_pop, hpop.data(), n * 4, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->popped_inst[p] + c.n_pop, hpinst.data(), n * 4, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->pop_off[p] + I0, hoff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
-    DX_CUDA(cudaMemcpyAsync(e->open_off[p] + I0, hooff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->open_off[e->young_active ? 0 : p] + I0, hooff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+    std::vector<uint32_t> hyoff(n + 1, c.young_total);
+    if (e->young_active) {
+        DX_CUDA(cudaMemcpyAsync(e->young.off[p] + I0, hyoff.data(), (n + 1) * 4, cudaMemcpyHostToDevice, s));
+        DX_CUDA(cudaMemcpyAsync(e->young.head[p] + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
+        DX_CUDA(cudaMemcpyAsync(e->young.m_head + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
+    }
     // control block
     Ctl nc = c;
     nc.n_inst = I0 + n;
@@ -852,6 +935,14 @@ static int step_v_b(dx_engine* e) {
     if (e->eval_all) DX_TRY(step_v_filter(e));
     stage_begin(e, ST_SORT);
     const int beam = e->is_beam ? 1 : 0;
+    if (e->young_active) {                 // the whole OPEN side of the iteration in one block (k_small_tail_v)
+        e->launches += dx_launch_small_tail_v(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_key[0],
+                                              e->open_val[0], e->open_off[0], e->young, p, e->A, (uint32_t)e->max_pop, e->node_g, e->node_h,
+                                              e->new_inst, e->popped[q], e->popped_inst[q], e->halt_flag ? DX_END_HALT : 0);
+        stage_end(e);
+        e->parity = q;
+        return DX_OK;
+    }
     if (small_fused_v(e)) {
         e->launches += dx_launch_small_push_v(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
                                               e->open_off[q], e->A, e->max_pop, e->max_open, e->node_g, e->node_h, e->new_inst,
@@ -975,6 +1066,7 @@ static int full_step(dx_engine* e) {
 
 static int build_step_graphs(dx_engine* e, bool prof) {
     e->graph_small = small_sort(e);
+    e->graph_young = e->young_active;
     const int p0 = e->parity;
     const long long l0 = e->launches;
     for (int k = 0; k < 2; ++k) {
@@ -1014,7 +1106,8 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
     const bool use_graph = e->use_graphs, prof = e->profiling != 0;
-    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && e->graph_small != small_sort(e)) drop_graphs(e);   // captured with the other sort
+    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != e->young_active))
+        drop_graphs(e);                              // captured with the other sort / OPEN structure
     if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
     if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level
         for (int k = 0; k < 2; ++k) {
@@ -1039,8 +1132,14 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
         if (use_graph) {
             const int burst = std::min(burst_max, (int)max_iters - done);
             const uint32_t itr0 = e->h_ctl->itr;
-            for (int b = 0; b < burst; ++b)
+            for (int b = 0; b < burst; ++b) {
+                const int keep = e->parity;          // (the compaction reads the buffers of the iteration about to run)
+                e->parity = keep ^ (b & 1);
+                const int rcy = young_before_step(e);
+                e->parity = keep;
+                DX_TRY(rcy);
                 DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[e->parity ^ (b & 1)] : e->graph_exec[e->parity ^ (b & 1)], e->stream));
+            }
             DX_TRY(sync_ctl(e));                     // synchronises the stream
             const int ran = burst == 1 ? 1 : (int)(e->h_ctl->itr - itr0);
             e->launches += (long long)ran * e->graph_launches;
@@ -1049,6 +1148,7 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
             if (prof) stage_collect_graph(e, e->parity ^ 1);
             if (ran < burst) break;                  // (everything finished inside the burst)
         } else {
+            DX_TRY(young_before_step(e));
             DX_TRY(full_step(e));
             ++done;
             DX_TRY(sync_ctl(e));
@@ -1072,6 +1172,7 @@ extern "C" int dx_step_begin(dx_engine* e, int64_t* n_pending) {
     if (e->cfg.heur_mode != DX_HEUR_HOST) DX_FAIL(DX_ERR_STATE, "dx_step_begin is for HOST heuristic mode");
     if (e->pending) DX_FAIL(DX_ERR_STATE, "step already pending");
     DX_CUDA(cudaSetDevice(e->cfg.device));
+    DX_TRY(young_before_step(e));
     if (e->is_q) DX_TRY(step_q_a(e)); else DX_TRY(step_v_a(e));
     DX_TRY(sync_ctl(e));
     e->pending = true;
@@ -2137,10 +2238,12 @@ extern "C" int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint3
 
 int dx_tc_profile_read(unsigned long long* out16);   // k_mlp_tc.cu
 int dx_small_profile_read(unsigned long long* out16);   // k_mlp_small.cu
+int dx_tail_profile_read(unsigned long long* out16);    // k_open.cu
 extern "C" int dx_debug_tc_profile(dx_engine* e, uint64_t* out8) {   /* out8: 16 entries */
     if (!e || !out8) DX_FAIL(DX_ERR_ARG, "null argument");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_CUDA(cudaStreamSynchronize(e->stream));
+    if (getenv("DXB200_PROF_TAIL")) return dx_tail_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DYT_PROFILE timeline)
     if (e->net.small) return dx_small_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DSM_PROFILE timeline)
     return dx_tc_profile_read(reinterpret_cast<unsigned long long*>(out8));
 }

@@ -653,12 +653,14 @@ __device__ __forceinline__ uint32_t merge_path_warp(const unsigned long long* __
 // this search was a serial latency chain at the head of every tile, with 6 of the block's 8 warps idle.
 __global__ void __launch_bounds__(OPEN_THREADS)
 k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
-                  const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ part_a, uint32_t* __restrict__ part_i) {
+                  const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ part_a, uint32_t* __restrict__ part_i,
+                  const uint32_t* __restrict__ a_head, const unsigned long long* __restrict__ b_keys) {
     dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n_tiles = ctl->n_tiles;
     const int I = ctl->n_inst;
-    const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
+    // (young-run compaction: the B run is the young run, and the A run starts behind its consumed prefix a_head[i])
+    const unsigned long long* __restrict__ bkeys = b_keys ? b_keys : sb.key[ctl->sort_final];
     const uint32_t warps = gridDim.x * (OPEN_THREADS / 32);
     for (uint32_t T = blockIdx.x * (OPEN_THREADS / 32) + (threadIdx.x >> 5); T < n_tiles; T += warps) {
         int lo = 0, hi = I - 1;                 // instance of this tile: last i with tile_off[i] <= T
@@ -667,9 +669,10 @@ k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const
             if (ia.tile_off[mid] <= T) lo = mid; else hi = mid - 1;
         }
         const int i = lo;
-        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
+        const uint32_t ah = a_head ? a_head[i] : 0u;
+        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
         const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
-        const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i], na, bkeys + ia.batch_off[i], nb, d0);
+        const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i] + ah, na, bkeys + ia.batch_off[i], nb, d0);
         if ((threadIdx.x & 31) == 0) { part_a[T] = part; part_i[T] = (uint32_t)i; }
     }
 }
@@ -680,32 +683,34 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
         unsigned long long* __restrict__ open_key_next, uint32_t* __restrict__ open_val_next,
         const uint32_t* __restrict__ open_off_next, uint32_t* __restrict__ popped_next, uint32_t* __restrict__ popped_inst_next,
         const uint32_t* __restrict__ pop_off_next, int keep_open, const uint32_t* __restrict__ part_a,
-        const uint32_t* __restrict__ part_i) {
+        const uint32_t* __restrict__ part_i, const uint32_t* __restrict__ a_head, const unsigned long long* __restrict__ b_keys,
+        const uint32_t* __restrict__ b_vals) {
     __shared__ unsigned long long s_key[DX_SORT_TILE];
     __shared__ uint32_t s_val[DX_SORT_TILE];
     __shared__ uint32_t s_part[4];   // a0, a1, inst
     dx_pdl_prologue();
     if (ctl->error) return;
     const uint32_t n_tiles = ctl->n_tiles;
-    const unsigned long long* __restrict__ bkeys = sb.key[ctl->sort_final];
-    const uint32_t* __restrict__ bvals = sb.val[ctl->sort_final];
+    const unsigned long long* __restrict__ bkeys = b_keys ? b_keys : sb.key[ctl->sort_final];
+    const uint32_t* __restrict__ bvals = b_keys ? b_vals : sb.val[ctl->sort_final];
     for (uint32_t T = blockIdx.x; T < n_tiles; T += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t i = part_i[T];
-            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i];
+            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - (a_head ? a_head[i] : 0u);
             s_part[0] = part_a[T];
             s_part[1] = (T + 1 < ia.tile_off[i + 1]) ? part_a[T + 1] : na;     // the instance's last tile ends at the end of its run
             s_part[2] = i;
         }
         __syncthreads();
         const int i = s_part[2];
-        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i], nb = ia.m_new[i];
+        const uint32_t ah = a_head ? a_head[i] : 0u;
+        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
         const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE, d1 = min(d0 + DX_SORT_TILE, na + nb);
         const uint32_t a0 = s_part[0], a1 = s_part[1], b0 = d0 - a0, b1 = d1 - a1;
         const uint32_t ca = a1 - a0, cb = b1 - b0;
-        const unsigned long long* __restrict__ ak = open_key_cur + open_off_cur[i] + a0;
-        const uint32_t* __restrict__ av = open_val_cur + open_off_cur[i] + a0;
+        const unsigned long long* __restrict__ ak = open_key_cur + open_off_cur[i] + ah + a0;
+        const uint32_t* __restrict__ av = open_val_cur + open_off_cur[i] + ah + a0;
         const unsigned long long* __restrict__ bk = bkeys + ia.batch_off[i] + b0;
         const uint32_t* __restrict__ bv = bvals + ia.batch_off[i] + b0;
         for (uint32_t t = threadIdx.x; t < ca; t += OPEN_THREADS) { s_key[t] = ak[t]; s_val[t] = av[t]; }
@@ -760,9 +765,10 @@ int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const 
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open) {
     int blocks = min(max_tiles, 148 * 8);      // 24.5 KB of shared memory and 256 threads per block: 8 blocks per SM
     dx_launch(k_merge_partition, min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur,
-              open_off_cur, sb.part_a, sb.part_i);
+              open_off_cur, sb.part_a, sb.part_i, (const uint32_t*)nullptr, (const unsigned long long*)nullptr);
     dx_launch(k_merge, blocks, OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
-              open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i);
+              open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i, (const uint32_t*)nullptr,
+              (const unsigned long long*)nullptr, (const uint32_t*)nullptr);
     return 2;
 }
 
@@ -828,4 +834,413 @@ int dx_launch_end_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uin
                        int A, int gen_mode) {
     dx_launch(k_end_iter, 1, 1024, 0, s, ctl, ia, pop_off_cur, pop_off_next, A, gen_mode);
     return 1;
+}
+
+// ---------------------------------------------------------------------------------------------
+// Young-run OPEN for small-batch A* engines (YoungBufs, dx_internal.cuh): the OPEN side of an iteration in ONE block.
+//   plan   per instance: pushed m, main-run remainder nm, young-run remainder ny, k = min(batch, nm + ny + m)   (k_plan)
+//   keys   f = w * g + h of the stored children                                                                (k_make_keys_v)
+//   sort   bitonic network on (instance, key, position) in shared memory                                       (k_sort_small)
+//   merge  young run + batch by RANKING: an element's output position is its own index plus the number of elements of the
+//          other run that precede it (young before batch on ties: older push first) -- one binary search per element, no
+//          serial merge; the result stays in shared memory and goes back to the other young buffer
+//   pop    k smallest of (main run head, merged young run): a warp finds the merge-path split (ka, kp), the k outputs are
+//          ranked into the popped list the same way (main run first on ties); the two runs' heads advance by ka / kp
+//   book   lb / ub / finished() / counters                                                                    (k_end_iter)
+#define YT_THREADS 1024
+#define YT_MAX_INST 256
+// -DYT_PROFILE: clock64 timeline of the block (thread 0), accumulated over launches: [0] launches, [1] plan, [2] staging + keys,
+// [3] sort, [4] merge by ranking, [5] pop split, [6] pop ranking, [7] write-back, [8] bookkeeping (read and cleared by dx_debug_tc_profile
+// when DXB200_PROF_TAIL is set)
+__device__ unsigned long long g_tail_prof[16];
+#ifdef YT_PROFILE
+#define YT_MARK(slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); \
+        atomicAdd(&g_tail_prof[(slot)], (unsigned long long)(_t - t_prev)); t_prev = _t; } } while (0)
+#else
+#define YT_MARK(slot) do { } while (0)
+#endif
+int dx_tail_profile_read(unsigned long long* out16) {
+    if (cudaMemcpyFromSymbol(out16, g_tail_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return DX_ERR_CUDA;
+    unsigned long long z[16] = {0};
+    if (cudaMemcpyToSymbol(g_tail_prof, z, sizeof(z)) != cudaSuccess) return DX_ERR_CUDA;
+    return DX_OK;
+}
+
+__device__ __forceinline__ uint32_t yt_lower_bound(const unsigned long long* a, uint32_t n, unsigned long long key) {   // # a[j] < key
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] < key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+__device__ __forceinline__ uint32_t yt_upper_bound(const unsigned long long* a, uint32_t n, unsigned long long key) {   // # a[j] <= key
+    uint32_t lo = 0, hi = n;
+    while (lo < hi) { const uint32_t mid = (lo + hi) >> 1; if (a[mid] <= key) lo = mid + 1; else hi = mid; }
+    return lo;
+}
+// last i in [0, n) with off[i] <= x  (off ascending, off[0] = 0 <= x)
+__device__ __forceinline__ int yt_find(const uint32_t* off, int n, uint32_t x) {
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi + 1) >> 1; if (off[mid] <= x) lo = mid; else hi = mid - 1; }
+    return lo;
+}
+
+// Sort of <= 2048 (instance, key, position) triples in shared memory without a 66-stage block-wide bitonic network (which cost
+// 450 cycles per stage: 15 us of a 25 us kernel): every warp sorts a 64-element chunk in REGISTERS (two elements per lane, 21
+// compare-exchange stages through shuffles), then two rounds of merging BY RANKING -- an element's position in the merged run is
+// its own index plus, for every other run of its group, the number of that run's elements below it (binary searches in shared
+// memory; the order is total because positions are unique, so no tie rule is needed): 64-runs -> 256-runs -> the whole batch.
+struct YtElem { uint32_t inst; unsigned long long key; uint32_t idx; };
+__device__ __forceinline__ bool yt_less(const YtElem& a, const YtElem& b) {
+    return a.inst != b.inst ? a.inst < b.inst : (a.key != b.key ? a.key < b.key : a.idx < b.idx);
+}
+__device__ __forceinline__ YtElem yt_shfl_xor(const YtElem& a, int j) {
+    YtElem o;
+    o.inst = __shfl_xor_sync(0xffffffffu, a.inst, j);
+    o.key = __shfl_xor_sync(0xffffffffu, a.key, j);
+    o.idx = __shfl_xor_sync(0xffffffffu, a.idx, j);
+    return o;
+}
+// # elements of the run [key, inst, idx][0 .. len) below x
+__device__ __forceinline__ uint32_t yt_rank_in(const unsigned long long* key, const uint32_t* inst, const uint32_t* idx, uint32_t len,
+                                               const YtElem& x) {
+    uint32_t lo = 0, hi = len;
+    while (lo < hi) {
+        const uint32_t mid = (lo + hi) >> 1;
+        YtElem m; m.inst = inst[mid]; m.key = key[mid]; m.idx = idx[mid];
+        if (yt_less(m, x)) lo = mid + 1; else hi = mid;
+    }
+    return lo;
+}
+// one round: runs of `len` elements, merged in groups of `grp` runs (total elements: multiple of 64, all threads of the block call)
+__device__ __forceinline__ void yt_rank_merge(const unsigned long long* ikey, const uint32_t* iinst, const uint32_t* iidx,
+                                              unsigned long long* okey, uint32_t* oinst, uint32_t* oidx, uint32_t total, uint32_t len,
+                                              uint32_t grp) {
+    for (uint32_t e = threadIdx.x; e < total; e += blockDim.x) {
+        const uint32_t r = e / len, g = r / grp, l = e - r * len;
+        YtElem x; x.inst = iinst[e]; x.key = ikey[e]; x.idx = iidx[e];
+        uint32_t pos = g * grp * len + l;
+        for (uint32_t r2 = g * grp; r2 < (g + 1) * grp; ++r2) {
+            const uint32_t b2 = r2 * len;
+            if (r2 == r || b2 >= total) continue;
+            pos += yt_rank_in(ikey + b2, iinst + b2, iidx + b2, min(len, total - b2), x);
+        }
+        okey[pos] = x.key; oinst[pos] = x.inst; oidx[pos] = x.idx;
+    }
+}
+// s_key / s_inst / s_idx [0 .. total) (total = n rounded up to 64, padding = (0xFFFFFFFF, ~0, position)) -> sorted in place;
+// t_key / t_inst / t_idx: scratch of the same size
+__device__ __forceinline__ void yt_sort(unsigned long long* s_key, uint32_t* s_inst, uint32_t* s_idx, unsigned long long* t_key,
+                                        uint32_t* t_inst, uint32_t* t_idx, uint32_t total) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t cbase = (uint32_t)warp * 64;
+    if (cbase < total) {                              // warp-uniform: this warp's chunk exists
+        YtElem el[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { const uint32_t e = cbase + lane + 32 * r; el[r].inst = s_inst[e]; el[r].key = s_key[e]; el[r].idx = s_idx[e]; }
+#pragma unroll
+        for (int k = 2; k <= 64; k <<= 1)
+#pragma unroll
+            for (int j = k >> 1; j > 0; j >>= 1) {
+                if (j == 32) {                        // partner = the lane's own second element; k = 64: ascending everywhere
+                    if (yt_less(el[1], el[0])) { const YtElem t = el[0]; el[0] = el[1]; el[1] = t; }
+                } else {
+#pragma unroll
+                    for (int r = 0; r < 2; ++r) {
+                        const int e = lane + 32 * r;
+                        const YtElem o = yt_shfl_xor(el[r], j);
+                        const bool up = (e & k) == 0, lower = (lane & j) == 0;
+                        const bool take_min = up == lower;
+                        const bool o_less = yt_less(o, el[r]);
+                        if (take_min == o_less) el[r] = o;
+                    }
+                }
+            }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) { const uint32_t e = cbase + lane + 32 * r; s_inst[e] = el[r].inst; s_key[e] = el[r].key; s_idx[e] = el[r].idx; }
+    }
+    __syncthreads();
+    if (total <= 64) return;
+    yt_rank_merge(s_key, s_inst, s_idx, t_key, t_inst, t_idx, total, 64, 4);             // -> runs of 256
+    __syncthreads();
+    yt_rank_merge(t_key, t_inst, t_idx, s_key, s_inst, s_idx, total, 256, 8);            // -> one run (total <= 2048)
+    __syncthreads();
+}
+
+__global__ void __launch_bounds__(YT_THREADS)
+k_small_tail_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+               uint32_t* __restrict__ pop_off_next, const unsigned long long* __restrict__ m_key, const uint32_t* __restrict__ m_val,
+               const uint32_t* __restrict__ m_off, YoungBufs yb, int p, int A, uint32_t max_pop, const float* __restrict__ node_g,
+               const float* __restrict__ node_h, const uint32_t* __restrict__ new_inst, uint32_t* __restrict__ popped_next,
+               uint32_t* __restrict__ popped_inst_next, int gen_mode) {
+    extern __shared__ __align__(16) uint8_t yt_raw[];
+    unsigned long long* s_bkey = reinterpret_cast<unsigned long long*>(yt_raw);               // [2048] batch keys
+    unsigned long long* s_ykey = s_bkey + DX_SMALL_SORT;                                      // [DX_YOUNG_BUF] merged young run
+    uint32_t* s_binst = reinterpret_cast<uint32_t*>(s_ykey + DX_YOUNG_BUF);                   // [2048]
+    uint32_t* s_bidx = s_binst + DX_SMALL_SORT;                                               // [2048]
+    uint32_t* s_yval = s_bidx + DX_SMALL_SORT;                                                // [DX_YOUNG_BUF]
+    unsigned long long* s_yin = reinterpret_cast<unsigned long long*>(s_yval + DX_YOUNG_BUF); // [DX_YOUNG_BUF] keys of the young remainders
+    unsigned long long* s_mkey = s_yin + DX_YOUNG_BUF;                                        // [2048] keys of the main-run heads (first k)
+    uint32_t* s_mval = reinterpret_cast<uint32_t*>(s_mkey + DX_SMALL_SORT);                   // [2048]
+    uint32_t* s_boff = s_mval + DX_SMALL_SORT;       // [I + 1] batch offsets
+    uint32_t* s_yoff = s_boff + YT_MAX_INST + 1;     // [I + 1] offsets of the young-run remainders (flat index space)
+    uint32_t* s_ysrc = s_yoff + YT_MAX_INST + 1;     // [I]     where the remainder starts in the current young buffer
+    uint32_t* s_ybo = s_ysrc + YT_MAX_INST + 1;      // [I + 1] offsets of the merged runs (next young buffer)
+    uint32_t* s_nm = s_ybo + YT_MAX_INST + 1;        // [I]     main-run remainder
+    uint32_t* s_msrc = s_nm + YT_MAX_INST + 1;       // [I]     where it starts
+    uint32_t* s_poff = s_msrc + YT_MAX_INST + 1;     // [I + 1] popped-list offsets
+    uint32_t* s_ka = s_poff + YT_MAX_INST + 1;       // [I]     pops from the main run
+    __shared__ uint32_t s_err, s_unfinished;
+    __shared__ unsigned long long s_gen;
+    dx_pdl_prologue();
+#ifdef YT_PROFILE
+    long long t_prev = clock64();
+    if (threadIdx.x == 0) atomicAdd(&g_tail_prof[0], 1ull);
+#endif
+    if (ctl->error) return;
+    const int tid = threadIdx.x, q = p ^ 1;
+    const int I = (int)ctl->n_inst;
+    const uint32_t node_base = ctl->node_base;
+    if (tid == 0) { s_err = 0; s_unfinished = 0; s_gen = 0; }
+    if (I > YT_MAX_INST) { if (tid == 0) atomicOr(&ctl->error, DX_DEVERR_POP); return; }
+    // ---- plan (serial over the instances: I is small in this regime) -------------------------------------------------
+    if (tid == 0) {
+        uint32_t sm = 0, sy = 0, syb = 0, sk = 0;
+        for (int i = 0; i < I; ++i) {
+            const bool act = ia.active[i] != 0;
+            const uint32_t kept = prefix[pop_off_cur[i + 1] * A] - prefix[pop_off_cur[i] * A];
+            const uint32_t m = act ? kept : 0u;
+            const uint32_t mh = yb.m_head[i];
+            const uint32_t nm = act ? (m_off[i + 1] - m_off[i]) - mh : 0u;        // (OPEN of a finished instance is dropped)
+            const uint32_t yh = yb.head[p][i];
+            const uint32_t ny = act ? (yb.off[p][i + 1] - yb.off[p][i]) - yh : 0u;
+            const uint32_t t = nm + ny + m;
+            const uint32_t k = act ? min((uint32_t)ia.batch[i], t) : 0u;
+            s_boff[i] = sm; s_yoff[i] = sy; s_ybo[i] = syb; s_poff[i] = sk;
+            s_ysrc[i] = yb.off[p][i] + yh; s_nm[i] = nm; s_msrc[i] = m_off[i] + mh;
+            ia.m_new[i] = m; ia.k_pop[i] = k; ia.n_open[i] = t - k;
+            sm += m; sy += ny; syb += ny + m; sk += k;
+        }
+        s_boff[I] = sm; s_yoff[I] = sy; s_ybo[I] = syb; s_poff[I] = sk;
+        uint32_t err = 0;
+        if (sm > DX_SMALL_SORT || sk > max_pop) err |= DX_DEVERR_POP;
+        if (syb > DX_YOUNG_BUF) err |= DX_DEVERR_OPEN;                           // (the host compacts before this can happen)
+        if (err) { atomicOr(&ctl->error, err); s_err = err; }
+        ctl->sort_n = sm;
+    }
+    __syncthreads();
+    if (s_err) return;
+    YT_MARK(1);
+    const uint32_t n = s_boff[I], n_young = s_yoff[I], n_yb = s_ybo[I], n_popk = s_poff[I];
+    // stage what the searches below read: the young remainders' keys and the first k entries of every main run (one round trip,
+    // issued before the key computation; every binary search of the merge and the pop then stays in shared memory)
+    for (uint32_t e = tid; e < n_young; e += YT_THREADS) {
+        const int i = yt_find(s_yoff, I, e);
+        s_yin[e] = yb.key[p][s_ysrc[i] + (e - s_yoff[i])];
+    }
+    for (uint32_t r = tid; r < n_popk; r += YT_THREADS) {
+        const int i = yt_find(s_poff, I, r);
+        const uint32_t rr = r - s_poff[i];
+        const bool in = rr < s_nm[i];
+        s_mkey[r] = in ? m_key[s_msrc[i] + rr] : ~0ull;
+        s_mval[r] = in ? m_val[s_msrc[i] + rr] : 0u;
+    }
+    // ---- keys of the stored children, then the sort on (instance, key, position) ----------------------------------------
+    const uint32_t total = (n + 63u) & ~63u;
+    for (uint32_t k = tid; k < total; k += YT_THREADS) {
+        if (k < n) {
+            const uint32_t id = node_base + k, inst = new_inst[k];
+            s_bkey[k] = f_key(ia.weight[inst], node_g[id], node_h[id]);
+            s_binst[k] = inst;
+        } else {
+            s_bkey[k] = ~0ull; s_binst[k] = 0xFFFFFFFFu;
+        }
+        s_bidx[k] = k;
+    }
+    __syncthreads();
+    YT_MARK(2);
+    if (n > 1) yt_sort(s_bkey, s_binst, s_bidx, s_ykey, s_yval, s_yval + DX_SMALL_SORT, total);
+    YT_MARK(3);
+    // ---- merged young run = young remainder + batch, by ranking --------------------------------------------------------
+    const uint32_t* __restrict__ yval_cur = yb.val[p];
+    for (uint32_t j = tid; j < n; j += YT_THREADS) {                             // batch elements: young entries <= key precede
+        const int i = (int)s_binst[j];
+        const unsigned long long key = s_bkey[j];
+        const uint32_t b = j - s_boff[i], ny = s_yoff[i + 1] - s_yoff[i];
+        const uint32_t pos = s_ybo[i] + b + yt_upper_bound(s_yin + s_yoff[i], ny, key);
+        s_ykey[pos] = key;
+        s_yval[pos] = node_base + s_bidx[j];
+    }
+    for (uint32_t e = tid; e < n_young; e += YT_THREADS) {                       // young entries: batch entries < key precede
+        const int i = yt_find(s_yoff, I, e);                                     // (instances with ny = 0 share an offset: the LAST wins,
+        const uint32_t a = e - s_yoff[i];                                        //  which is the one that owns e)
+        const unsigned long long key = s_yin[e];
+        const uint32_t pos = s_ybo[i] + a + yt_lower_bound(s_bkey + s_boff[i], s_boff[i + 1] - s_boff[i], key);
+        s_ykey[pos] = key;
+        s_yval[pos] = yval_cur[s_ysrc[i] + a];
+    }
+    __syncthreads();
+    YT_MARK(4);
+    // ---- pop split per instance (a warp each): ka entries of the main run among the k smallest ----------------------------
+    for (int i = tid >> 5; i < I; i += YT_THREADS / 32) {
+        const uint32_t k = s_poff[i + 1] - s_poff[i];
+        const uint32_t nyb = s_ybo[i + 1] - s_ybo[i];
+        const uint32_t ka = merge_path_warp(s_mkey + s_poff[i], min(s_nm[i], k), s_ykey + s_ybo[i], min(nyb, k), k);
+        if ((tid & 31) == 0) s_ka[i] = ka;
+    }
+    __syncthreads();
+    YT_MARK(5);
+    // ---- the popped list (pop order), by ranking; main run first on ties ------------------------------------------------
+    for (uint32_t r = tid; r < n_popk; r += YT_THREADS) {
+        const int i = yt_find(s_poff, I, r);
+        const uint32_t rr = r - s_poff[i], ka = s_ka[i], kp = (s_poff[i + 1] - s_poff[i]) - ka;
+        unsigned long long key;
+        uint32_t val, pos;
+        if (rr < ka) {
+            key = s_mkey[s_poff[i] + rr];
+            val = s_mval[s_poff[i] + rr];
+            pos = rr + yt_lower_bound(s_ykey + s_ybo[i], kp, key);
+        } else {
+            const uint32_t b = rr - ka;
+            key = s_ykey[s_ybo[i] + b];
+            val = s_yval[s_ybo[i] + b];
+            pos = b + yt_upper_bound(s_mkey + s_poff[i], ka, key);
+        }
+        popped_next[s_poff[i] + pos] = val;
+        popped_inst_next[s_poff[i] + pos] = (uint32_t)i;
+        if (pos == 0) ia.f_first[i] = key;
+    }
+    YT_MARK(6);
+    // ---- the merged young runs go to the other buffer; heads advance ------------------------------------------------------
+    for (uint32_t e = tid; e < n_yb; e += YT_THREADS) { yb.key[q][e] = s_ykey[e]; yb.val[q][e] = s_yval[e]; }
+    for (int i = tid; i <= I; i += YT_THREADS) {
+        yb.off[q][i] = s_ybo[i];
+        pop_off_next[i] = s_poff[i];
+        if (i < I) {
+            const uint32_t ka = s_ka[i];
+            yb.head[q][i] = (s_poff[i + 1] - s_poff[i]) - ka;
+            yb.m_head[i] += ka;
+        }
+    }
+    __syncthreads();                                  // f_first of every instance is written (same block: visible)
+    YT_MARK(7);
+    // ---- lb / ub / finished() / counters (k_end_iter; graph_search.py:43-46, 67-69) ------------------------------------------
+    uint32_t unfin = 0;
+    unsigned long long gen = 0;
+    for (int i = tid; i < I; i += YT_THREADS) {
+        if (!ia.active[i]) continue;
+        const uint32_t n_pop = pop_off_cur[i + 1] - pop_off_cur[i];
+        const uint32_t k = s_poff[i + 1] - s_poff[i];
+        double lb = ia.lb[i];
+        const unsigned long long ff = ia.f_first[i], gen_old = ia.gen[i], ubk = ia.ub_key[i];
+        const uint32_t seq_old = ia.pop_seq_base[i], itr = ia.itr[i] + 1;
+        const double w = ia.weight[i];
+        if (k > 0) lb = fmax(dx_key_to_f(ff), lb);
+        const unsigned long long g_add = (unsigned long long)n_pop * A;
+        gen += g_add;
+        bool fin = false;
+        if (ubk != DX_EMPTY64) {
+            const double ub = (double)__uint_as_float((uint32_t)(ubk >> 32));
+            fin = lb >= __dmul_rn(w, ub);
+        }
+        fin = fin || (k == 0);
+        ia.lb[i] = lb;
+        ia.gen[i] = gen_old + g_add;
+        ia.pop_seq_base[i] = seq_old + n_pop;
+        ia.itr[i] = itr;
+        ia.active[i] = fin ? 0 : 1;
+        if (!fin) ++unfin;
+    }
+    if (unfin) atomicAdd(&s_unfinished, unfin);
+    if (gen) atomicAdd(&s_gen, gen);
+    __syncthreads();
+    if (tid == 0) {
+        ctl->n_unfinished = s_unfinished;
+        ctl->gen_total += s_gen;
+        ctl->n_pop = n_popk;
+        ctl->n_children = n_popk * (uint32_t)A;
+        ctl->itr += 1;
+        ctl->epoch += 1;
+        ctl->node_base = ctl->node_count;
+        ctl->young_total = n_yb;
+        if ((gen_mode & DX_END_HALT) && s_unfinished == 0) ctl->error |= DX_DEVERR_DONE;
+    }
+    YT_MARK(8);
+}
+
+static size_t young_tail_smem() {
+    return (size_t)DX_SMALL_SORT * (8 + 4 + 4) + (size_t)DX_YOUNG_BUF * (8 + 4) + (size_t)DX_YOUNG_BUF * 8 + (size_t)DX_SMALL_SORT * (8 + 4) +
+           (size_t)8 * (YT_MAX_INST + 1) * 4;
+}
+
+int dx_launch_small_tail_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const unsigned long long* m_key, const uint32_t* m_val, const uint32_t* m_off,
+                           const YoungBufs& yb, int p, int A, uint32_t max_pop, const float* node_g, const float* node_h,
+                           const uint32_t* new_inst, uint32_t* popped_next, uint32_t* popped_inst_next, int gen_mode) {
+    static bool attr_set = false;
+    if (!attr_set) {
+        if (cudaFuncSetAttribute(k_small_tail_v, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)young_tail_smem()) != cudaSuccess) {
+            dx_set_error("k_small_tail_v: cannot raise the dynamic shared-memory limit");
+            return 0;
+        }
+        attr_set = true;
+    }
+    dx_launch(k_small_tail_v, 1, YT_THREADS, young_tail_smem(), s, ctl, ia, child_prefix, pop_off_cur, pop_off_next, m_key, m_val, m_off, yb,
+              p, A, max_pop, node_g, node_h, new_inst, popped_next, popped_inst_next, gen_mode);
+    return 1;
+}
+
+// Compaction: main run <- merge(main run remainder, young run remainder) per instance, young runs emptied.  The merge itself is
+// k_merge_partition + k_merge with the young run as the B run (k = 0: nothing is popped).
+__global__ void __launch_bounds__(1024)
+k_young_plan(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ m_off, uint32_t* __restrict__ m_off_next, YoungBufs yb,
+             int p, uint32_t max_open) {
+    if (ctl->error) return;
+    if (threadIdx.x != 0) return;
+    const int I = (int)ctl->n_inst;
+    uint32_t so = 0, st = 0;
+    for (int i = 0; i < I; ++i) {
+        const bool act = ia.active[i] != 0;
+        const uint32_t nm = act ? (m_off[i + 1] - m_off[i]) - yb.m_head[i] : 0u;
+        const uint32_t ny = act ? (yb.off[p][i + 1] - yb.off[p][i]) - yb.head[p][i] : 0u;
+        ia.m_new[i] = ny;                                  // the B run of the merge = the young remainder ...
+        ia.batch_off[i] = yb.off[p][i] + yb.head[p][i];    // ... which starts here in the young buffer
+        ia.k_pop[i] = 0;
+        m_off_next[i] = so;
+        ia.tile_off[i] = st;
+        so += nm + ny;
+        st += (nm + ny + DX_SORT_TILE - 1) / DX_SORT_TILE;
+        if (!act) yb.m_head[i] = m_off[i + 1] - m_off[i];  // (a finished instance's run is dropped: the merge sees na = 0)
+    }
+    m_off_next[I] = so;
+    ia.tile_off[I] = st;
+    ctl->n_tiles = st;
+    ctl->open_total = so;
+    if (so > max_open) atomicOr(&ctl->error, DX_DEVERR_OPEN);
+}
+
+__global__ void __launch_bounds__(1024)
+k_young_finish(Ctl* __restrict__ ctl, YoungBufs yb) {
+    if (ctl->error) return;
+    const int I = (int)ctl->n_inst;
+    for (int i = threadIdx.x; i <= I; i += blockDim.x) {
+        yb.off[0][i] = 0; yb.off[1][i] = 0;
+        if (i < I) { yb.head[0][i] = 0; yb.head[1][i] = 0; yb.m_head[i] = 0; }
+    }
+    if (threadIdx.x == 0) ctl->young_total = 0;
+}
+
+// launches the compaction: open_*_cur (with the consumed prefixes m_head) + young buffer p -> open_*_next
+int dx_launch_young_compact(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const SortBufs& sb, const YoungBufs& yb, int p,
+                            const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
+                            unsigned long long* open_key_next, uint32_t* open_val_next, uint32_t* open_off_next,
+                            uint32_t* popped_scratch, uint32_t* popped_inst_scratch, const uint32_t* pop_off_any, int max_tiles,
+                            uint32_t max_open) {
+    k_young_plan<<<1, 32, 0, s>>>(ctl, ia, open_off_cur, open_off_next, yb, p, max_open);
+    const int blocks = min(max_tiles, 148 * 8);
+    k_merge_partition<<<min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s>>>(
+        ctl, ia, sb, open_key_cur, open_off_cur, sb.part_a, sb.part_i, yb.m_head, yb.key[p]);
+    k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
+                                            open_off_next, popped_scratch, popped_inst_scratch, pop_off_any, 1, sb.part_a, sb.part_i,
+                                            yb.m_head, yb.key[p], yb.val[p]);
+    k_young_finish<<<1, 256, 0, s>>>(ctl, yb);
+    return 4;
 }

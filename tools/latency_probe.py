@@ -18,8 +18,7 @@ for prec, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16), (
         eng.load_weights(54, 6, info["res_dim"], info["num_blocks"], 1, True, blob)
     eng.add_instances(k["hard_states"][:1], k["hard_goals"][:1], 100, 0.1)
     eng.run(50)
-    if mode != L.DX_HEUR_ZERO:
-        eng.tc_profile()
+    eng.tc_profile()
     tot_it, tot_s, dev_ms = 0, 0.0, 0.0
     l0 = eng.counters().kernel_launches
     for i in range(10):
@@ -33,7 +32,11 @@ for prec, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16), (
     launches = eng.counters().kernel_launches - l0
     print(f"{prec}: {tot_it} iterations, wall {1e6 * tot_s / tot_it:.1f} us/iteration, device {1e3 * dev_ms / tot_it:.1f} us/iteration, "
           f"{launches / tot_it:.1f} launches/iteration", flush=True)
-    if mode != L.DX_HEUR_ZERO and os.environ.get("DXB200_NVCC_DEFS", "").find("SM_PROFILE") >= 0:
+    if os.environ.get("DXB200_PROF_TAIL"):
+        pr = eng.tc_profile()
+        names = ["launches", "plan", "staging+keys", "sort", "merge by ranking", "pop split", "pop ranking", "write-back", "bookkeeping"]
+        print("   k_small_tail_v timeline (cycles per launch):", {k: round(v / max(pr[0], 1)) for k, v in zip(names[1:], pr[1:]) if v})
+    elif mode != L.DX_HEUR_ZERO and os.environ.get("DXB200_NVCC_DEFS", "").find("SM_PROFILE") >= 0:
         pr = eng.tc_profile()
         names = ["launches", "rows staged", "one-hot built"] + ["layer prologue", "first k step"] + [f"layer{l}" for l in range(2, 8)] + ["k loops", "epilogues", "layer barriers", "output", "-"]
         print("   k_mlp_small CTA-0 timeline (cycles per launch):", {k: round(v / max(pr[0], 1)) for k, v in zip(names[1:], pr[1:]) if v})

@@ -271,10 +271,17 @@ struct ScanTemp {
     uint32_t* block_sums;   // [>= ceil(n_max / 4096) + 1]
 };
 
+// One CLOSED slot = one 32-byte DRAM sector: the key CAS, the per-iteration list head and the stored path cost of a state are
+// touched by the same item within a few hundred cycles (link -> decide -> commit), so they share a sector instead of living in
+// three arrays (three random sectors per item: round 1 measured 297 MB of DRAM traffic for 144 MB of algorithmic bytes).
+struct __align__(32) ClosedSlot {
+    unsigned long long key;    // (tag << 32) | rep ; DX_EMPTY64 when free
+    unsigned long long head;   // (epoch << 32) | first item of this state in the current batch
+    float g;                   // CLOSED[state] (inf when new)
+    uint32_t pad_[3];
+};
 struct ClosedDev {
-    unsigned long long* slot_key;   // (tag << 32) | rep ; DX_EMPTY64 when free
-    float* slot_g;                  // CLOSED[state] (inf when new)
-    unsigned long long* slot_head;  // (epoch << 32) | first item of this state in the current batch
+    ClosedSlot* slots;
     uint32_t mask;                  // capacity - 1
 };
 

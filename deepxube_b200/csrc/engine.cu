@@ -524,7 +524,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     size_t hcap = 1024;
     while (hcap < 2 * (N + C)) hcap <<= 1;   // load factor <= 0.5 even with a full node store and a full batch in flight
     e->closed.mask = (uint32_t)(hcap - 1);
-    A_(e->closed.slot_key, hcap); A_(e->closed.slot_g, hcap); A_(e->closed.slot_head, hcap);
+    A_(e->closed.slots, hcap);
     if (!e->is_q) { A_(e->child_state, C * e->SP); A_(e->child_g, C); }
     e->eval_all = cfg->max_backups > 0 && !e->is_q;
     e->backups_q = cfg->max_backups > 0 && e->is_q;
@@ -2239,11 +2239,18 @@ extern "C" int dx_hda_node(dx_engine* e, int64_t local_id, uint8_t* state, uint3
 int dx_tc_profile_read(unsigned long long* out16);   // k_mlp_tc.cu
 int dx_small_profile_read(unsigned long long* out16);   // k_mlp_small.cu
 int dx_tail_profile_read(unsigned long long* out16);    // k_open.cu
+int dx_filter_profile_read(unsigned long long* out8);   // k_closed.cu
 extern "C" int dx_debug_tc_profile(dx_engine* e, uint64_t* out8) {   /* out8: 16 entries */
     if (!e || !out8) DX_FAIL(DX_ERR_ARG, "null argument");
     DX_CUDA(cudaSetDevice(e->cfg.device));
     DX_CUDA(cudaStreamSynchronize(e->stream));
-    if (getenv("DXB200_PROF_TAIL")) return dx_tail_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DYT_PROFILE timeline)
+    if (getenv("DXB200_PROF_TAIL")) {                  // (-DYT_PROFILE timelines: tail kernel in slots 0..8, filter kernel in 9..14)
+        unsigned long long f[8];
+        DX_TRY(dx_tail_profile_read(reinterpret_cast<unsigned long long*>(out8)));
+        DX_TRY(dx_filter_profile_read(f));
+        for (int i = 0; i < 6; ++i) out8[9 + i] = f[i];
+        return DX_OK;
+    }
     if (e->net.small) return dx_small_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DSM_PROFILE timeline)
     return dx_tc_profile_read(reinterpret_cast<unsigned long long*>(out8));
 }

@@ -28,9 +28,9 @@
 __global__ void k_closed_init(ClosedDev c) {
     const size_t cap = (size_t)c.mask + 1;
     for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < cap; i += (size_t)gridDim.x * blockDim.x) {
-        c.slot_key[i] = DX_EMPTY64;
-        c.slot_g[i] = __int_as_float(0x7f800000);
-        c.slot_head[i] = 0ull;
+        ClosedSlot z;
+        z.key = DX_EMPTY64; z.head = 0ull; z.g = __int_as_float(0x7f800000); z.pad_[0] = z.pad_[1] = z.pad_[2] = 0u;
+        c.slots[i] = z;
     }
 }
 
@@ -50,7 +50,7 @@ __device__ __forceinline__ uint32_t closed_find_or_claim(const ClosedDev& c, con
     // the bound only guards against a corrupted table (never spin forever on the device)
     for (uint32_t probes = 0; probes <= c.mask; ++probes) {
         // CAS first: a new state (the common case) claims its slot in ONE round trip; an occupied slot returns its key
-        const unsigned long long k = atomicCAS(&c.slot_key[i], DX_EMPTY64, mine);
+        const unsigned long long k = atomicCAS(&c.slots[i].key, DX_EMPTY64, mine);
         if (k == DX_EMPTY64) return i;
         if ((uint32_t)(k >> 32) == tag) {
             const uint32_t rep = (uint32_t)k;
@@ -69,7 +69,7 @@ __global__ void k_closed_seed(DomainDev d, ClosedDev c, const uint8_t* __restric
         const uint32_t id = first + t;
         const uint4* row = reinterpret_cast<const uint4*>(node_state + (size_t)id * d.SP);
         uint32_t i = closed_find_or_claim(c, row, d.SP / 16, id, node_state, node_state, d.SP);
-        if (i != DX_NIL) c.slot_g[i] = 0.0f;
+        if (i != DX_NIL) c.slots[i].g = 0.0f;
     }
 }
 
@@ -113,7 +113,7 @@ __device__ __forceinline__ void closed_link_item(const ClosedDev& c, const Ctl* 
     if (i == DX_NIL) { atomicOr((uint32_t*)&ctl->error, DX_DEVERR_NODES); return; }
     // push on the slot's per-iteration list: nobody walks the lists before the link phase is over (kernel boundary or block
     // barrier), so one exchange is enough -- the old head (if it is of this iteration) becomes this item's successor
-    const unsigned long long old = atomicExch(&c.slot_head[i], ((unsigned long long)epoch << 32) | ci);
+    const unsigned long long old = atomicExch(&c.slots[i].head, ((unsigned long long)epoch << 32) | ci);
     child_next[ci] = ((uint32_t)(old >> 32) == epoch) ? (uint32_t)old : DX_NIL;
 }
 
@@ -134,9 +134,9 @@ __device__ __forceinline__ uint8_t closed_decide_item(const ClosedDev& c, const 
     const uint32_t i = child_slot[ci];
     if (i == DX_NIL) return 0;
     const float g = item_g(v, ci);
-    bool keep = g < c.slot_g[i];
+    bool keep = g < c.slots[i].g;
     bool fin = keep;
-    uint32_t c2 = (uint32_t)c.slot_head[i];
+    uint32_t c2 = (uint32_t)c.slots[i].head;
     while (c2 != DX_NIL) {
         if (c2 != ci) {
             const float g2 = item_g(v, c2);
@@ -187,6 +187,7 @@ __device__ __forceinline__ void scatter_kept_item(const DomainDev& d, const Clos
     const float g = a.child_g[ci];
     const uint32_t par = a.popped[j], inst = a.popped_inst[j];
     const uint32_t slot = (f & 2) ? a.child_slot[ci] : 0u;
+    const unsigned long long skey = (f & 2) ? c.slots[slot].key : 0ull;      // (read before the slot's sector is written below)
     const float h = a.child_h ? a.child_h[ci] : 0.f;
     const uint32_t id = base + k;
     const uint4* src = reinterpret_cast<const uint4*>(a.child_state + (size_t)ci * d.SP);
@@ -206,9 +207,8 @@ __device__ __forceinline__ void scatter_kept_item(const DomainDev& d, const Clos
     a.new_inst[k] = inst;
     if (a.child_h) a.node_h[id] = h;                    // evaluate-all engines: the value was computed before the filter
     if (f & 2) {
-        c.slot_g[slot] = g;
-        const unsigned long long key = c.slot_key[slot];
-        if ((uint32_t)key & DX_PENDING) c.slot_key[slot] = (key & 0xFFFFFFFF00000000ull) | id;
+        c.slots[slot].g = g;
+        if ((uint32_t)skey & DX_PENDING) c.slots[slot].key = (skey & 0xFFFFFFFF00000000ull) | id;
     }
 }
 
@@ -227,6 +227,21 @@ k_scatter_kept(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ScatterArgs a) {
 // only needs the expansion kernel finished) -- eight launches whose cost at this size is mostly their dependency latency.  Same device functions, same order of
 // phases; __syncthreads() is the grid-wide barrier the separate launches provided.
 #define SMALL_THREADS 1024
+// -DYT_PROFILE: clock64 timeline of the block (thread 0): g_filter_prof[0] launches, [1] goal resolve, [2] link, [3] decide, [4] scan,
+// [5] scatter (read and cleared with the tail kernel's timeline, slots 9..13 of dx_debug_tc_profile under DXB200_PROF_TAIL)
+__device__ unsigned long long g_filter_prof[8];
+#ifdef YT_PROFILE
+#define SF_MARK(slot) do { if (threadIdx.x == 0) { const long long _t = clock64(); \
+        atomicAdd(&g_filter_prof[(slot)], (unsigned long long)(_t - t_prev)); t_prev = _t; } } while (0)
+#else
+#define SF_MARK(slot) do { } while (0)
+#endif
+int dx_filter_profile_read(unsigned long long* out8) {
+    if (cudaMemcpyFromSymbol(out8, g_filter_prof, sizeof(unsigned long long) * 8) != cudaSuccess) return DX_ERR_CUDA;
+    unsigned long long z[8] = {0};
+    if (cudaMemcpyToSymbol(g_filter_prof, z, sizeof(z)) != cudaSuccess) return DX_ERR_CUDA;
+    return DX_OK;
+}
 __global__ void __launch_bounds__(SMALL_THREADS)
 k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, uint32_t* __restrict__ child_slot,
                  uint32_t* __restrict__ child_next, uint8_t* __restrict__ child_flags, uint32_t* __restrict__ child_prefix,
@@ -235,6 +250,10 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
     __shared__ uint32_t s_warp[32];
     __shared__ uint32_t s_err;
     dx_pdl_prologue();
+#ifdef YT_PROFILE
+    long long t_prev = clock64();
+    if (threadIdx.x == 0) atomicAdd(&g_filter_prof[0], 1ull);
+#endif
     if (ctl->error) return;
     // k_goal_resolve (k_domain.cu): the solved popped node that won the (g, pop order) atomicMin becomes goal_node
     for (uint32_t j = threadIdx.x; j < ctl->n_pop; j += SMALL_THREADS) {
@@ -251,13 +270,16 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
     }
     const uint32_t epoch = ctl->epoch;
     const int chunks = v.SP / 16;
+    SF_MARK(1);
     for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) closed_link_item(c, ctl, v, child_slot, child_next, ci, epoch, chunks);
     __syncthreads();
     if (threadIdx.x == 0) s_err = *((volatile uint32_t*)&ctl->error);
     __syncthreads();
     if (s_err) return;
+    SF_MARK(2);
     for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) child_flags[ci] = closed_decide_item(c, v, child_slot, child_next, ci);
     __syncthreads();
+    SF_MARK(3);
     // exclusive scan of (flags & 1): 4 consecutive items per thread, prefix[n] = total (as dx_launch_scan_flags)
     const uint32_t base4 = threadIdx.x * 4;
     uint32_t f4[4], sum = 0;
@@ -294,8 +316,10 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
     }
     __syncthreads();
     if (s_err) return;
+    SF_MARK(4);
     const uint32_t nbase = ctl->node_base;
     for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS) scatter_kept_item(d, c, a, ci, nbase, chunks);
+    SF_MARK(5);
 }
 
 // Q*, small batches: is_solved + record_goal of the popped nodes (k_check_solved, k_goal_resolve), their CLOSED test (link +
@@ -366,7 +390,7 @@ k_small_filter_q(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, In
     if (base4 <= n && n < base4 + 4) child_prefix[n] = ex;
     if (threadIdx.x == 0) ctl->n_kept = s_warp[31];
     for (uint32_t ci = threadIdx.x; ci < n; ci += SMALL_THREADS)                       // k_closed_commit
-        if (child_flags[ci] & 2) c.slot_g[child_slot[ci]] = v.node_g[v.item_node[ci]];
+        if (child_flags[ci] & 2) c.slots[child_slot[ci]].g = v.node_g[v.item_node[ci]];
 }
 
 int dx_launch_small_filter_q(cudaStream_t s, const DomainDev& d, const ClosedDev& c, Ctl* ctl, const InstArrays& ia,
@@ -709,7 +733,7 @@ __global__ void k_closed_commit(ClosedDev c, const Ctl* __restrict__ ctl, const 
     if (ctl->error) return;
     const uint32_t n = ctl->n_children;
     for (uint32_t ci = blockIdx.x * blockDim.x + threadIdx.x; ci < n; ci += gridDim.x * blockDim.x)
-        if (child_flags[ci] & 2) c.slot_g[child_slot[ci]] = node_g[item_node[ci]];
+        if (child_flags[ci] & 2) c.slots[child_slot[ci]].g = node_g[item_node[ci]];
 }
 
 int dx_launch_closed_commit(cudaStream_t s, const ClosedDev& c, const Ctl* ctl, const float* node_g, const uint32_t* item_node,

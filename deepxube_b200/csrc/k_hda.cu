@@ -92,9 +92,9 @@ __global__ void k_scatter_kept_hda(DomainDev d, ClosedDev c, Ctl* __restrict__ c
         new_inst[k] = 0;
         if (f & 2) {
             const uint32_t i = child_slot[ci];
-            c.slot_g[i] = g;
-            const unsigned long long key = c.slot_key[i];
-            if ((uint32_t)key & DX_PENDING) c.slot_key[i] = (key & 0xFFFFFFFF00000000ull) | id;
+            const unsigned long long key = c.slots[i].key;       // (read before the slot's sector is written)
+            c.slots[i].g = g;
+            if ((uint32_t)key & DX_PENDING) c.slots[i].key = (key & 0xFFFFFFFF00000000ull) | id;
         }
     }
 }

@@ -2248,7 +2248,7 @@ extern "C" int dx_debug_tc_profile(dx_engine* e, uint64_t* out8) {   /* out8: 16
         unsigned long long f[8];
         DX_TRY(dx_tail_profile_read(reinterpret_cast<unsigned long long*>(out8)));
         DX_TRY(dx_filter_profile_read(f));
-        for (int i = 0; i < 6; ++i) out8[9 + i] = f[i];
+        for (int i = 1; i < 8; ++i) out8[8 + i] = f[i];   // (the filter runs once per tail launch: its launch counter is not reported)
         return DX_OK;
     }
     if (e->net.small) return dx_small_profile_read(reinterpret_cast<unsigned long long*>(out8));   // (-DSM_PROFILE timeline)

@@ -322,6 +322,216 @@ k_small_filter_v(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, ui
     SF_MARK(5);
 }
 
+// The same block, restructured around what the timeline showed (-DYT_PROFILE: link 17 k, scatter 12 k, decide 7 k of 40 k cycles, all
+// of them chains of dependent L2 / DRAM round trips on ONE SM, walked twice by the 176 threads that own a second item):
+//   * a thread's (up to) two items advance TOGETHER through every phase -- both CAS probes, both row compares, both list pushes
+//     and both slot reads are in flight at once, so a second item costs issue slots, not another latency chain;
+//   * per-item state (g, slot, tag, "slot claimed by this batch", flags, prefix) stays in REGISTERS across the phases, the two
+//     things other threads need (g and the same-state list links) live in shared memory -- no child_slot / child_next /
+//     child_flags / child_prefix round trips between phases, and the commit no longer reads the slot key back;
+//   * the kept-children scan is two ballot scans (items tid and tid + 1024 keep flat child order: round 0 precedes round 1).
+// Same decisions as closed_link_item / closed_decide_item / scatter_kept_item; child_flags and child_prefix are still written
+// (the OPEN side reads the prefix at the instance boundaries).
+__global__ void __launch_bounds__(SMALL_THREADS)
+k_small_filter_v2(DomainDev d, ClosedDev c, Ctl* __restrict__ ctl, ItemView v, uint8_t* __restrict__ child_flags,
+                  uint32_t* __restrict__ child_prefix, ScatterArgs a, uint32_t max_nodes, InstArrays ia,
+                  const uint32_t* __restrict__ pop_off, const uint8_t* __restrict__ pop_solved) {
+    __shared__ float s_g[2 * SMALL_THREADS];
+    __shared__ uint32_t s_next[2 * SMALL_THREADS];
+    __shared__ uint32_t s_warp[2][32];
+    __shared__ uint32_t s_err;
+    dx_pdl_prologue();
+#ifdef YT_PROFILE
+    long long t_prev = clock64();
+    if (threadIdx.x == 0) atomicAdd(&g_filter_prof[0], 1ull);
+#endif
+    if (ctl->error) return;
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    for (uint32_t j = tid; j < ctl->n_pop; j += SMALL_THREADS) {                    // k_goal_resolve
+        if (!pop_solved[j]) continue;
+        const uint32_t inst = a.popped_inst[j], id = a.popped[j];
+        const unsigned long long key = ((unsigned long long)__float_as_uint(a.node_g[id]) << 32) |
+                                       (unsigned long long)(ia.pop_seq_base[inst] + j - pop_off[inst]);
+        if (ia.ub_key[inst] == key) ia.goal_node[inst] = id;
+    }
+    const uint32_t n = ctl->n_children;
+    if (n > 2u * SMALL_THREADS) {            // the host's bound was wrong: fail loudly
+        if (tid == 0) atomicOr(&ctl->error, DX_DEVERR_POP);
+        return;
+    }
+    const uint32_t epoch = ctl->epoch, nbase = ctl->node_base;
+    const int chunks = v.SP / 16;
+    SF_MARK(1);
+    // ---- link: find / claim the slot of each item, push it on the slot's list of this iteration ------------------------------
+    uint32_t ci[2], slot[2], tag[2], idx[2], par[2], inst[2];
+    float g[2];
+    bool live[2], done[2], pend[2];
+    uint4 rv[2][4];                                  // the items' rows (SP <= 64), loaded ONCE: every chunk load of both items is
+#pragma unroll                                       // in flight together (a per-chunk loop serialises one L2 round trip per chunk)
+    for (int r = 0; r < 2; ++r) {
+        ci[r] = (uint32_t)tid + (uint32_t)r * SMALL_THREADS;
+        const bool valid = ci[r] < n;
+        g[r] = valid ? v.batch_g[ci[r]] : __int_as_float(0x7fc00000);
+        par[r] = valid ? a.popped[ci[r] / d.A] : 0u;
+        inst[r] = valid ? a.popped_inst[ci[r] / d.A] : 0u;
+        const uint4* row = reinterpret_cast<const uint4*>(v.batch_rows + (size_t)ci[r] * v.SP);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) rv[r][q] = (valid && q < chunks) ? row[q] : make_uint4(0, 0, 0, 0);
+        slot[r] = DX_NIL; pend[r] = false; tag[r] = 0; idx[r] = 0;
+    }
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        live[r] = g[r] == g[r];                      // (NaN: beyond n, or the child of a finished instance)
+        done[r] = !live[r];
+        if (ci[r] < n) s_g[ci[r]] = g[r];
+        if (live[r]) {
+            uint64_t h = 0x9E3779B97F4A7C15ull;      // dx_hash_row over the register copy
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                if (q < chunks) {
+                    const uint64_t x = ((uint64_t)rv[r][q].y << 32) | rv[r][q].x, y = ((uint64_t)rv[r][q].w << 32) | rv[r][q].z;
+                    h = dx_mix64(h ^ x) + 0x632BE59BD9B4E019ull;
+                    h = dx_mix64(h ^ y) + 0x9E3779B97F4A7C15ull;
+                }
+            tag[r] = (uint32_t)(h >> 32);
+            idx[r] = (uint32_t)h & c.mask;
+        }
+    }
+    SF_MARK(6);
+    for (uint32_t probes = 0; probes <= c.mask && !(done[0] && done[1]); ++probes) {
+        unsigned long long k[2] = {0ull, 0ull};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)                  // CAS first: a new state claims its slot in ONE round trip
+            if (!done[r]) k[r] = atomicCAS(&c.slots[idx[r]].key, DX_EMPTY64, ((unsigned long long)tag[r] << 32) | (DX_PENDING | ci[r]));
+        const uint4* other[2] = {nullptr, nullptr};
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (done[r]) continue;
+            if (k[r] == DX_EMPTY64) { done[r] = true; slot[r] = idx[r]; pend[r] = true; continue; }
+            if ((uint32_t)(k[r] >> 32) == tag[r]) {
+                const uint32_t rep = (uint32_t)k[r];
+                other[r] = reinterpret_cast<const uint4*>((rep & DX_PENDING) ? (v.batch_rows + (size_t)(rep & ~DX_PENDING) * v.SP)
+                                                                            : (v.node_state + (size_t)rep * v.SP));
+            } else {
+                idx[r] = (idx[r] + 1) & c.mask;
+            }
+        }
+        uint4 ov[2][4];                               // the representatives' rows: both items' loads in flight together
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+#pragma unroll
+            for (int q = 0; q < 4; ++q) ov[r][q] = (other[r] && q < chunks) ? other[r][q] : make_uint4(0, 0, 0, 0);
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!other[r]) continue;
+            bool eq = true;
+#pragma unroll
+            for (int q = 0; q < 4; ++q)
+                eq = eq && ov[r][q].x == rv[r][q].x && ov[r][q].y == rv[r][q].y && ov[r][q].z == rv[r][q].z && ov[r][q].w == rv[r][q].w;
+            if (eq) { done[r] = true; slot[r] = idx[r]; pend[r] = ((uint32_t)k[r] & DX_PENDING) != 0; }
+            else idx[r] = (idx[r] + 1) & c.mask;
+        }
+    }
+    if ((live[0] && !done[0]) || (live[1] && !done[1])) atomicOr(&ctl->error, DX_DEVERR_NODES);
+    SF_MARK(7);
+    {
+        unsigned long long old[2] = {0ull, 0ull};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)                  // nobody walks the lists before the barrier below: one exchange is enough
+            if (live[r] && slot[r] != DX_NIL) old[r] = atomicExch(&c.slots[slot[r]].head, ((unsigned long long)epoch << 32) | ci[r]);
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (ci[r] < n) s_next[ci[r]] = ((uint32_t)(old[r] >> 32) == epoch) ? (uint32_t)old[r] : DX_NIL;
+    }
+    __syncthreads();
+    if (tid == 0) s_err = *((volatile uint32_t*)&ctl->error);
+    __syncthreads();
+    if (s_err) return;
+    SF_MARK(2);
+    // ---- decide: the sequential rule from (g, batch position) over the same-state items of the batch ---------------------------
+    uint32_t flag[2] = {0u, 0u};
+    {
+        float sg[2] = {0.f, 0.f};
+        uint32_t hd[2] = {DX_NIL, DX_NIL};
+#pragma unroll
+        for (int r = 0; r < 2; ++r)
+            if (live[r]) { sg[r] = c.slots[slot[r]].g; hd[r] = (uint32_t)c.slots[slot[r]].head; }
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (!live[r]) continue;
+            bool keep = g[r] < sg[r];
+            bool fin = keep;
+            uint32_t c2 = hd[r];
+            while (c2 != DX_NIL) {
+                if (c2 != ci[r]) {
+                    const float g2 = s_g[c2];
+                    if (c2 < ci[r] && g2 <= g[r]) keep = false;                  // an earlier duplicate already set CLOSED <= g
+                    if (g2 < g[r] || (g2 == g[r] && c2 < ci[r])) fin = false;
+                }
+                c2 = s_next[c2];
+            }
+            flag[r] = (keep ? 1u : 0u) | ((keep && fin) ? 2u : 0u);
+        }
+    }
+    SF_MARK(3);
+    // ---- kept-children scan: ids in flat child order = push order --------------------------------------------------------------
+    uint32_t pre[2];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        const uint32_t bal = __ballot_sync(0xffffffffu, (flag[r] & 1u) != 0);
+        pre[r] = __popc(bal & ((1u << lane) - 1u));
+        if (lane == 0) s_warp[r][warp] = __popc(bal);
+    }
+    __syncthreads();
+    if (warp < 2) {
+        uint32_t w = s_warp[warp][lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+        s_warp[warp][lane] = w;                      // inclusive over the warps of round `warp`
+    }
+    __syncthreads();
+    const uint32_t tot0 = s_warp[0][31], total = tot0 + s_warp[1][31];
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        pre[r] += (r ? tot0 : 0u) + (warp ? s_warp[r][warp - 1] : 0u);
+        if (ci[r] < n) { child_flags[ci[r]] = (uint8_t)flag[r]; child_prefix[ci[r]] = pre[r]; }
+    }
+    if (tid == 0) {                          // k_after_scan_v
+        child_prefix[n] = total;
+        ctl->n_kept = total;
+        if ((unsigned long long)nbase + total > max_nodes) {
+            ctl->error |= DX_DEVERR_NODES;
+            s_err = 1;
+        } else {
+            ctl->node_count = nbase + total;
+            ctl->nn_row_start = nbase;
+            ctl->nn_n = total;
+        }
+    }
+    __syncthreads();
+    if (s_err) return;
+    SF_MARK(4);
+    // ---- kept children become nodes; final items commit CLOSED (no slot read: the link phase knows who claimed the slot) ------
+#pragma unroll
+    for (int r = 0; r < 2; ++r) {
+        if (!(flag[r] & 1u)) continue;
+        const uint32_t id = nbase + pre[r];
+        uint4* dst = reinterpret_cast<uint4*>(a.node_state + (size_t)id * d.SP);
+#pragma unroll
+        for (int q = 0; q < 4; ++q)
+            if (q < chunks) dst[q] = rv[r][q];
+        a.node_g[id] = g[r];
+        a.node_parent[id] = par[r];
+        a.node_action[id] = (uint8_t)(ci[r] % d.A);
+        a.new_inst[pre[r]] = inst[r];
+        if (flag[r] & 2u) {
+            c.slots[slot[r]].g = g[r];
+            if (pend[r]) c.slots[slot[r]].key = ((unsigned long long)tag[r] << 32) | id;
+        }
+    }
+    SF_MARK(5);
+}
+
 // Q*, small batches: is_solved + record_goal of the popped nodes (k_check_solved, k_goal_resolve), their CLOSED test (link +
 // decide), the scan of the kept ones and the CLOSED commit in ONE block (eight launches).
 __global__ void __launch_bounds__(SMALL_THREADS)
@@ -411,8 +621,13 @@ int dx_launch_small_filter_v(cudaStream_t s, const DomainDev& d, const ClosedDev
     ItemView v{child_state, child_g, nullptr, node_state, node_g, popped_inst, ia.active, d.A, d.SP};
     ScatterArgs a{child_state, child_g, child_slot, child_flags, child_prefix, popped, popped_inst,
                   node_state, node_g, node_parent, node_action, new_inst, nullptr, nullptr};
-    dx_launch(k_small_filter_v, 1, SMALL_THREADS, 0, s, d, c, ctl, v, child_slot, child_next, child_flags, child_prefix, a, max_nodes, ia,
-              pop_off, pop_solved);
+    static int v2 = -1;
+    if (v2 < 0) { const char* e = getenv("DXB200_FILTER_V2"); v2 = (e && e[0] == '0') ? 0 : 1; }
+    if (v2 && d.SP <= 64)                         // (the register copy of the rows holds 4 x 16 bytes)
+        dx_launch(k_small_filter_v2, 1, SMALL_THREADS, 0, s, d, c, ctl, v, child_flags, child_prefix, a, max_nodes, ia, pop_off, pop_solved);
+    else
+        dx_launch(k_small_filter_v, 1, SMALL_THREADS, 0, s, d, c, ctl, v, child_slot, child_next, child_flags, child_prefix, a, max_nodes, ia,
+                  pop_off, pop_solved);
     return 1;
 }
 

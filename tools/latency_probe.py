@@ -36,8 +36,8 @@ for prec, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16), (
         pr = eng.tc_profile()
         names = ["launches", "plan", "staging+keys", "sort", "merge by ranking", "pop split", "pop ranking", "write-back", "bookkeeping"]
         print("   k_small_tail_v timeline (cycles per launch):", {k: round(v / max(pr[0], 1)) for k, v in zip(names[1:], pr[1:9]) if v})
-        fn = ["launches", "goal resolve", "link", "decide", "scan", "scatter"]
-        print("   k_small_filter_v timeline (cycles per launch):", {k: round(v / max(pr[9], 1)) for k, v in zip(fn[1:], pr[10:15]) if v})
+        fn = ["launches", "goal resolve", "link (list push + barrier)", "decide", "scan", "scatter", "link: loads + hash", "link: probes"]
+        print("   k_small_filter_v timeline (cycles per launch):", {k: round(v / max(pr[0], 1)) for k, v in zip(fn[1:], pr[9:16]) if v})
     elif mode != L.DX_HEUR_ZERO and os.environ.get("DXB200_NVCC_DEFS", "").find("SM_PROFILE") >= 0:
         pr = eng.tc_profile()
         names = ["launches", "rows staged", "one-hot built"] + ["layer prologue", "first k step"] + [f"layer{l}" for l in range(2, 8)] + ["k loops", "epilogues", "layer barriers", "output", "-"]

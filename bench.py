@@ -496,7 +496,9 @@ def main() -> None:
     ap.add_argument("--impl", type=str, default="b200", choices=["b200", "reference"])
     ap.add_argument("--insts-per-step", type=int, default=8)
     ap.add_argument("--max-itrs", type=int, default=20)
-    ap.add_argument("--ref-itrs", type=int, default=5, help="iterations per bounded CPU sample")
+    ap.add_argument("--ref-itrs", type=int, default=5, help="--impl reference: iterations per step (one instance; 134 340 nodes)")
+    ap.add_argument("--cpu-sample-itrs", type=int, default=12,
+                    help="iterations of the bounded CPU sample inside the GPU arm's line (one instance; 12 -> 974 k nodes, ~8-10 s)")
     ap.add_argument("--precision", type=str, default="bf16", choices=["bf16", "fp32"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-kat", action="store_true", help="skip the solve-time-per-instance report on the trained-net KAT set")
@@ -702,7 +704,7 @@ def main() -> None:
         if not args.no_cpu_baseline and world == 1:
             try:
                 arm = CpuArm("cube3", "heurv,resnet_fc.1000H_4B_bn", "graph.10000B_0.6W", sd, os.cpu_count() or 8)
-                line["cpu_baseline"] = cpu_sample_block(arm, st_all[0], gl_all[0], args.ref_itrs, "the headline workload")
+                line["cpu_baseline"] = cpu_sample_block(arm, st_all[0], gl_all[0], args.cpu_sample_itrs, "the headline workload")
                 arm.close()
             except Exception as e:  # noqa: BLE001
                 line["cpu_baseline"] = {"error": repr(e)}

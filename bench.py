@@ -336,6 +336,49 @@ def kat_solve_times(L, device: int) -> dict:
     return out
 
 
+def bf16_deviation_c2(L, device: int, st_all, gl_all, sd, iters: int = 8, insts: int = 2) -> dict:
+    """north_star: "bf16-mode solution costs and nodes generated are reported with their deviation".  A random-init network never
+    terminates a C2 search, so the deviation is reported on what the search DOES with the values: the same instances are advanced in
+    lock-step by an fp32-accurate engine and a bf16 engine; per iteration, the fraction of the bf16 engine's popped nodes (the nodes
+    it expands next) that the fp32 engine pops too, and the heuristic error on the fp32 engine's popped states."""
+    B = 10000
+    blob, _ = L.pack_state_dict(sd)
+    engs = {}
+    for name, mode in (("fp32", L.DX_HEUR_NET_FP32), ("bf16", L.DX_HEUR_NET_BF16)):
+        e = L.Engine("cube3", 0, "graph_v", mode, max_instances=insts, max_pop_total=insts * B,
+                     max_nodes=int(insts * B * ACTS * (iters + 1)) + 1024, device=device)
+        e.load_weights(54, 6, H, NB, 1, True, blob)
+        e.add_instances(st_all[:insts], gl_all[:insts], B, 0.6)
+        engs[name] = e
+    overlap, herr_max, herr_mean, gen = [], 0.0, [], {}
+    for it in range(iters):
+        for e in engs.values():
+            e.run(1)
+        same, tot = 0, 0
+        for j in range(insts):
+            a, _, _ = engs["fp32"].curr_nodes(j, B + 8)
+            b, _, _ = engs["bf16"].curr_nodes(j, B + 8)
+            sa = {r.tobytes() for r in a}
+            same += sum(1 for r in b if r.tobytes() in sa)
+            tot += len(b)
+            if j == 0 and len(a):
+                hf = engs["fp32"].heur_eval(a[:4096], gl_all[:1].repeat(min(len(a), 4096), axis=0), 1)[:, 0]
+                hb = engs["bf16"].heur_eval(a[:4096], gl_all[:1].repeat(min(len(a), 4096), axis=0), 1)[:, 0]
+                d = np.abs(hf.astype(np.float64) - hb)
+                herr_max = max(herr_max, float(d.max()))
+                herr_mean.append(float(d.mean()))
+        overlap.append(same / max(tot, 1))
+    for name, e in engs.items():
+        gen[name] = int(sum(s.num_nodes_generated for s in e.status()))
+        e.close()
+    return {"workload": f"{insts} C2 instances x {iters} iterations, fp32-accurate engine vs bf16 engine in lock-step",
+            "popped_set_overlap_per_iteration": [round(x, 4) for x in overlap],
+            "heuristic_abs_error_max": herr_max, "heuristic_abs_error_mean": float(np.mean(herr_mean)) if herr_mean else None,
+            "nodes_generated": gen, "nodes_generated_deviation": (gen["bf16"] - gen["fp32"]) / max(gen["fp32"], 1),
+            "note": "solution costs cannot deviate on this workload (random-init weights: no search terminates); on the trained-network KAT "
+                    "set (kat_solve) bf16 costs equal the reference's 10/10"}
+
+
 def workload_config(args, world: int) -> dict:
     return {"workload": "cube3 batch weighted A* graph.10000B_0.6W, heurv resnet_fc.1000H_4B_bn random-init, "
                         "1000 synthetic scrambles (BASELINE.json configs[1])",
@@ -701,6 +744,10 @@ def main() -> None:
                 line["kat_solve"] = kat_solve_times(L, local)
             except Exception as e:  # noqa: BLE001  (extra information only; never fails the bench line)
                 line["kat_solve"] = {"error": str(e)}
+            try:
+                line["bf16_deviation"] = bf16_deviation_c2(L, local, st_all, gl_all, sd)
+            except Exception as e:  # noqa: BLE001
+                line["bf16_deviation"] = {"error": repr(e)}
         if not args.no_cpu_baseline and world == 1:
             try:
                 arm = CpuArm("cube3", "heurv,resnet_fc.1000H_4B_bn", "graph.10000B_0.6W", sd, os.cpu_count() or 8)

@@ -351,3 +351,61 @@ def test_hda_capacity_error_reaches_every_rank(device_resident):
         flags = [int(s.cpu()[6].item()) for s in h.summary]
         assert all(f != 0 for f in flags), flags          # every rank's summary carries the error, not only the failing one
     h.close()
+
+
+# ---------------------------------------------------------------------------------------------------
+# Young-run OPEN of small-batch A* engines (csrc/k_open.cu k_small_tail_v)
+def _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, iters, fn, add_later=None, max_pop=None):
+    """HOST-heuristic engine against the oracle, compared after every iteration (popped nodes, lb / ub / OPEN size / counters)."""
+    orc = OracleSearch(dom, fn, False, batch, weight)
+    oi = orc.add_instances(st, goals)
+    n_all = len(st) + (len(add_later[1]) if add_later else 0)
+    eng = L.Engine(dname, dim, "graph_v", L.DX_HEUR_HOST, max_instances=n_all, max_pop_total=max_pop or n_all * batch, max_nodes=600000)
+    eng.add_instances(st, goals, batch, weight, root_vals=fn(st, goals))
+    for t in range(iters):
+        if add_later and t == add_later[0]:
+            st2, gl2, b2 = add_later[1], add_later[2], add_later[3]
+            oi += orc.add_instances(st2, gl2, batch_size=b2)
+            eng.add_instances(st2, gl2, b2, weight, root_vals=fn(st2, gl2))
+        orc.step()
+        n = eng.step_begin()
+        ps, pg = eng.get_pending(n)
+        eng.step_end(fn(ps, pg) if n else np.zeros((0,)))
+        for j, (o, s) in enumerate(zip(oi, eng.status())):
+            assert s.lb == o.lb and s.ub == o.ub and s.num_nodes_generated == o.num_nodes_generated, (t, j, s.lb, o.lb)
+            assert bool(s.finished) == o.finished(), (t, j)
+            if not s.finished:
+                assert s.open_size == len(o.open), (t, j, s.open_size, len(o.open))
+                cs, cg, _ = eng.curr_nodes(j, len(o.nodes_curr) + 8)
+                assert np.array_equal(cs, o.store.state[o.nodes_curr]), (t, j)
+    return eng, oi
+
+
+@pytest.mark.parametrize("dname,dim,n,batch,weight", [("cube3", 0, 1, 100, 0.2), ("cube3", 0, 7, 20, 0.6), ("npuzzle", 4, 24, 10, 0.8),
+                                                      ("grid", 7, 60, 3, 1.0)])
+def test_young_run_open_matches_the_oracle_over_many_compactions(dname, dim, n, batch, weight):
+    """40 iterations of small-batch searches (several compactions of the young runs into the main runs, instances finishing at
+    different iterations, 1 to 60 instances in one block): every iteration's popped nodes, OPEN sizes, lb / ub and counters are
+    the oracle's.  The pseudo-heuristic has many exact ties, so the (f, push order) tie rule is exercised across the run boundaries."""
+    L = _lib()
+    dom = OracleDomain(dname, dim)
+    if dname == "grid":
+        rng = np.random.default_rng(4)
+        st = rng.integers(0, dim, size=(n, 2)).astype(np.uint8)
+        goals = rng.integers(0, dim, size=(n, 2)).astype(np.uint8)
+    else:
+        st, goals = _scrambles(dom, n, 40, 9)
+    eng, oi = _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, 40, pseudo_v)
+    assert eng.counters().kernel_launches > 0
+    eng.close()
+
+
+def test_young_run_is_flushed_when_the_batch_outgrows_the_small_regime():
+    """An engine that starts in the small regime (young runs active) and then receives instances whose batches exceed it: the
+    young runs are merged back into one run and the search continues on the big-batch kernels with the same results."""
+    L = _lib()
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 3, 35, 12)
+    eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st[:2], goals[:2], 50, 0.5, 14, pseudo_v, add_later=(7, st[2:], goals[2:], 400),
+                             max_pop=2 * 50 + 400)
+    eng.close()

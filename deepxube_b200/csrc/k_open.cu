@@ -346,10 +346,15 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 // ticket order guarantees that every tile a block waits for has already been started by a resident (or finished) block.
 #define OS_FLAG_AGG 1ull
 #define OS_FLAG_PREFIX 2ull
-#define OS_ITEMS 16                       // elements per thread: tiles of 4096 (half as many look-back links as the merge tiles)
+#ifndef OS_ITEMS
+#define OS_ITEMS 8                        // elements per thread: tiles of 2048.  16 (tiles of 4096) needed 181 registers = ONE block per SM
+#endif                                    // (ncu: 12.5 % occupancy, 87 % of cycles without an eligible warp); 8 measured -18 % on the
+#ifndef OS_MIN_BLOCKS                     // npuzzle.5 sort (64 instances x 4 k entries) and -2 % on the cube3 Q* sort (8 x 100 k)
+#define OS_MIN_BLOCKS 2
+#endif
 #define OS_TILE (OPEN_THREADS * OS_ITEMS)
 #define OS_WINDOW 8                       // predecessor words fetched per round trip of the look-back
-__global__ void __launch_bounds__(OPEN_THREADS)
+__global__ void __launch_bounds__(OPEN_THREADS, OS_MIN_BLOCKS)
 k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
     __shared__ uint32_t s_cnt[OPEN_THREADS / 32][256];
     __shared__ uint32_t s_base[256];
@@ -1021,7 +1026,7 @@ k_small_tail_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict_
         }
         s_boff[I] = sm; s_yoff[I] = sy; s_ybo[I] = syb; s_poff[I] = sk;
         uint32_t err = 0;
-        if (sm > DX_SMALL_SORT || sk > max_pop) err |= DX_DEVERR_POP;
+        if (sm > DX_SMALL_SORT || sk > max_pop || sk > DX_SMALL_SORT) err |= DX_DEVERR_POP;
         if (syb > DX_YOUNG_BUF) err |= DX_DEVERR_OPEN;                           // (the host compacts before this can happen)
         if (err) { atomicOr(&ctl->error, err); s_err = err; }
         ctl->sort_n = sm;

@@ -710,7 +710,7 @@ def main() -> None:
         achieved = hidden_flop / (stage["gemm_hidden"] / 1e3) / 1e12 if stage["gemm_hidden"] > 0 else None
         peak = peaks["bf16_tflops_sustained"]
         traffic, traffic_note = None, None
-        tf = os.path.join(ROOT, "profiles", "r1i_gemm_traffic.json")
+        tf = os.path.join(ROOT, "profiles", "r2k_gemm_traffic.json")          # (round-2 capture: the launches of the last iteration of a step)
         if args.precision == "bf16" and os.path.exists(tf):
             tj = json.load(open(tf))
             traffic = tj["traffic_per_launch_avg_bytes"]

@@ -970,6 +970,126 @@ __device__ __forceinline__ void yt_sort(unsigned long long* s_key, uint32_t* s_i
     __syncthreads();
 }
 
+// The same sort as a stable LSD radix sort in shared memory, taken when at most YT_RADIX_MAX_DIGITS digits vary (returns false
+// otherwise and the caller runs the comparison sort above): both blocks of the small iteration are bound by instruction issue on
+// ONE SM, and a radix pass over low-entropy digits costs ~160 instructions per thread.  A pass: per-warp digit counts through
+// __match_any_sync (a warp owns 64 consecutive elements, two rows of 32: ranks stay in position order, so the sort is stable and
+// the position never has to be compared), a block scan over (digit, warp), scatter into the other buffer.  Bytes that are the same
+// in every key (the top bytes of a narrow f range) and the instance byte of single-instance batches are skipped.
+// s_cnt: [256][32] bytes, s_base: [256][32] u16, s_red: [8 + 32] words of scratch.
+#define YT_RADIX_MAX_DIGITS 3
+__device__ __forceinline__ bool yt_radix_sort(unsigned long long* s_key, uint32_t* s_inst, uint32_t* s_idx, unsigned long long* t_key,
+                                              uint32_t* t_inst, uint32_t* t_idx, uint8_t* s_cnt, uint16_t* s_base, uint32_t* s_red,
+                                              uint32_t n) {
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const uint32_t e0 = (uint32_t)warp * 64 + lane, e1 = e0 + 32;
+    {   // which digits vary
+        uint32_t o_lo = 0, o_hi = 0, a_lo = ~0u, a_hi = ~0u, o_in = 0, a_in = ~0u;
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t e = r ? e1 : e0;
+            if (e < n) {
+                const unsigned long long k = s_key[e];
+                const uint32_t in = s_inst[e];
+                o_lo |= (uint32_t)k; o_hi |= (uint32_t)(k >> 32); a_lo &= (uint32_t)k; a_hi &= (uint32_t)(k >> 32);
+                o_in |= in; a_in &= in;
+            }
+        }
+        o_lo = __reduce_or_sync(0xffffffffu, o_lo); o_hi = __reduce_or_sync(0xffffffffu, o_hi); o_in = __reduce_or_sync(0xffffffffu, o_in);
+        a_lo = __reduce_and_sync(0xffffffffu, a_lo); a_hi = __reduce_and_sync(0xffffffffu, a_hi); a_in = __reduce_and_sync(0xffffffffu, a_in);
+        if (tid < 6) s_red[tid] = tid < 3 ? 0u : ~0u;
+        __syncthreads();
+        if (lane == 0) {
+            atomicOr(&s_red[0], o_lo); atomicOr(&s_red[1], o_hi); atomicOr(&s_red[2], o_in);
+            atomicAnd(&s_red[3], a_lo); atomicAnd(&s_red[4], a_hi); atomicAnd(&s_red[5], a_in);
+        }
+        __syncthreads();
+    }
+    const uint32_t diff_lo = s_red[0] ^ s_red[3], diff_hi = s_red[1] ^ s_red[4], diff_in = s_red[2] ^ s_red[5];
+    __syncthreads();                                  // (s_red[8..] is reused by the scans below)
+    {   // __match_any_sync walks the distinct digit values of a warp one by one: with high-entropy bytes (the low mantissa bytes of
+        // w * g + h with a network h) a pass costs ~5 k cycles and eight of them lose to the comparison sort (measured: KAT
+        // iteration 67.5 -> 76.3 us), while keys with few varying bytes (zero / coarse heuristics) win (53.0 -> 45.5 us)
+        int nvar = (diff_in & 0xFFu) ? 1 : 0;
+#pragma unroll
+        for (int b = 0; b < 4; ++b) nvar += (((diff_lo >> (8 * b)) & 0xFFu) ? 1 : 0) + (((diff_hi >> (8 * b)) & 0xFFu) ? 1 : 0);
+        if (nvar > YT_RADIX_MAX_DIGITS) return false;
+    }
+    unsigned long long *ksrc = s_key, *kdst = t_key;
+    uint32_t *isrc = s_inst, *idst = t_inst, *xsrc = s_idx, *xdst = t_idx;
+    for (int b = 0; b < 9; ++b) {                     // key bytes 0..7, then the instance byte (instances < 256 in this regime)
+        const uint32_t varies = b < 4 ? (diff_lo >> (8 * b)) & 0xFFu : (b < 8 ? (diff_hi >> (8 * (b - 4))) & 0xFFu : (diff_in & 0xFFu));
+        if (!varies) continue;                        // (block-uniform)
+        for (int i = tid; i < 256 * 32 / 4; i += YT_THREADS) reinterpret_cast<uint32_t*>(s_cnt)[i] = 0u;
+        __syncthreads();
+        unsigned long long k[2];
+        uint32_t in[2], ix[2], dg[2], lr[2];
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            const uint32_t e = r ? e1 : e0;
+            const bool valid = e < n;
+            k[r] = valid ? ksrc[e] : 0ull;
+            in[r] = valid ? isrc[e] : 0u;
+            ix[r] = valid ? xsrc[e] : 0u;
+            const uint32_t d = b < 8 ? (uint32_t)(k[r] >> (8 * b)) & 0xFFu : (in[r] & 0xFFu);
+            dg[r] = valid ? d : (256u + (uint32_t)lane);
+            const uint32_t peers = __match_any_sync(0xffffffffu, dg[r]);
+            const int leader = __ffs(peers) - 1;
+            const uint32_t before = __popc(peers & ((1u << lane) - 1u));
+            uint32_t old = 0;
+            if (valid && lane == leader) {
+                old = s_cnt[d * 32 + warp];
+                s_cnt[d * 32 + warp] = (uint8_t)(old + __popc(peers));
+            }
+            old = __shfl_sync(0xffffffffu, old, leader);
+            lr[r] = old + before;
+            __syncwarp();
+        }
+        __syncthreads();
+        {   // exclusive scan over (digit, warp): thread t owns digit t / 4, warps 8 * (t % 4) .. + 7
+            const uint2 c8 = reinterpret_cast<const uint2*>(s_cnt)[tid];
+            uint32_t c[8];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) { c[j] = (c8.x >> (8 * j)) & 0xFFu; c[4 + j] = (c8.y >> (8 * j)) & 0xFFu; }
+            uint32_t sum = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) sum += c[j];
+            uint32_t x = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, x, o); if (lane >= o) x += y; }
+            if (lane == 31) s_red[8 + warp] = x;
+            __syncthreads();
+            if (warp == 0) {
+                uint32_t w = s_red[8 + lane];
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, w, o); if (lane >= o) w += y; }
+                s_red[8 + lane] = w;
+            }
+            __syncthreads();
+            uint32_t run = (warp ? s_red[8 + warp - 1] : 0u) + x - sum;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) { s_base[tid * 8 + j] = (uint16_t)run; run += c[j]; }
+        }
+        __syncthreads();
+#pragma unroll
+        for (int r = 0; r < 2; ++r) {
+            if (dg[r] < 256u) {
+                const uint32_t pos = (uint32_t)s_base[dg[r] * 32 + warp] + lr[r];
+                kdst[pos] = k[r]; idst[pos] = in[r]; xdst[pos] = ix[r];
+            }
+        }
+        __syncthreads();
+        { unsigned long long* t = ksrc; ksrc = kdst; kdst = t; }
+        { uint32_t* t = isrc; isrc = idst; idst = t; }
+        { uint32_t* t = xsrc; xsrc = xdst; xdst = t; }
+    }
+    if (ksrc != s_key) {
+        for (uint32_t e = tid; e < n; e += YT_THREADS) { s_key[e] = ksrc[e]; s_inst[e] = isrc[e]; s_idx[e] = xsrc[e]; }
+        __syncthreads();
+    }
+    return true;
+}
+
 __global__ void __launch_bounds__(YT_THREADS)
 k_small_tail_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
                uint32_t* __restrict__ pop_off_next, const unsigned long long* __restrict__ m_key, const uint32_t* __restrict__ m_val,
@@ -1062,7 +1182,12 @@ k_small_tail_v(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict_
     }
     __syncthreads();
     YT_MARK(2);
-    if (n > 1) yt_sort(s_bkey, s_binst, s_bidx, s_ykey, s_yval, s_yval + DX_SMALL_SORT, total);
+    if (n > 1) {    // radix scratch: the merged-run buffers (not in use yet): keys [0, 2048), counters / bases / scan words behind them
+        const bool done = yt_radix_sort(s_bkey, s_binst, s_bidx, s_ykey, s_yval, s_yval + DX_SMALL_SORT,
+                                        reinterpret_cast<uint8_t*>(s_ykey + DX_SMALL_SORT), reinterpret_cast<uint16_t*>(s_ykey + DX_SMALL_SORT + 1024),
+                                        reinterpret_cast<uint32_t*>(s_ykey + DX_SMALL_SORT + 1024 + 2048), n);
+        if (!done) yt_sort(s_bkey, s_binst, s_bidx, s_ykey, s_yval, s_yval + DX_SMALL_SORT, total);      // (block-uniform decision)
+    }
     YT_MARK(3);
     // ---- merged young run = young remainder + batch, by ranking --------------------------------------------------------
     const uint32_t* __restrict__ yval_cur = yb.val[p];

@@ -14,10 +14,12 @@ python tools/config_probe.py cube3 0 q 10000 8 40 > $out/${tag}_q_plain.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/${tag}_c2_launches.csv $B > $out/${tag}_ncu_c2.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -c 6000 --csv --log-file $out/${tag}_q_launches.csv python tools/config_probe.py cube3 0 q 10000 8 40 > $out/${tag}_ncu_q.log 2>&1
 ncu --metrics gpu__time_duration.sum --clock-control none -s 2000 -c 1400 --csv --log-file $out/${tag}_kat_launches.csv python tools/latency_probe.py bf16 > $out/${tag}_ncu_kat.log 2>&1
-ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_gemm_bf16_tc<\(int\)256, \(int\)2, \(bool\)0, \(bool\)0' -s 246 -c 6 -o $out/${tag}_gemm_full -f $B > $out/${tag}_ncu_full.log 2>&1
+ncu --set full --clock-control none --import-source on --kernel-name-base demangled -k 'regex:k_gemm_bf16_tc<\(int\)256, \(int\)2, \(int\)0, \(bool\)0, \(bool\)0>' -s 246 -c 6 -o $out/${tag}_gemm_full -f $B > $out/${tag}_ncu_full.log 2>&1
 ncu -i $out/${tag}_gemm_full.ncu-rep --page raw --csv > $out/${tag}_gemm_full_raw.csv 2>/dev/null
 ncu --set full --clock-control none --import-source on -k regex:k_mlp_small -s 300 -c 2 -o $out/${tag}_small_full -f python tools/latency_probe.py bf16 > $out/${tag}_ncu_small.log 2>&1
 ncu -i $out/${tag}_small_full.ncu-rep --page raw --csv > $out/${tag}_small_full_raw.csv 2>/dev/null
+ncu --set full --clock-control none -k 'regex:k_small_tail_v|k_small_filter_v2' -s 600 -c 4 -o $out/${tag}_blocks_full -f python tools/latency_probe.py bf16 > $out/${tag}_ncu_blocks.log 2>&1
+ncu -i $out/${tag}_blocks_full.ncu-rep --page raw --csv > $out/${tag}_blocks_full_raw.csv 2>/dev/null
 ncu --set full --clock-control none -k 'regex:k_radix_onesweep|k_merge|k_radix_prepass' -s 330 -c 12 -o $out/${tag}_qsort_full -f python tools/config_probe.py cube3 0 q 10000 8 40 > $out/${tag}_ncu_qsort.log 2>&1
 ncu -i $out/${tag}_qsort_full.ncu-rep --page raw --csv > $out/${tag}_qsort_full_raw.csv 2>/dev/null
 ls -la $out | tail -30

@@ -715,7 +715,7 @@ def main() -> None:
             tj = json.load(open(tf))
             traffic = tj["traffic_per_launch_avg_bytes"]
             traffic_note = (f"dram__bytes_read.sum + dram__bytes_write.sum per launch from one ncu --set full capture of a "
-                            f"{tj['rows_in_launch']}-state launch (profiles/r1i_gemm_traffic.json); algorithmic bytes of that launch: "
+                            f"{tj['rows_in_launch']}-state launch (profiles/r2k_gemm_traffic.json); algorithmic bytes of that launch: "
                             f"{tj['algorithmic_bytes']['hidden']} (plain) / {tj['algorithmic_bytes']['hidden_residual']} (with residual)")
         n_l = calls["gemm_hidden"] * n_hidden
         roof = {"kernel": "k_gemm_bf16_tc<256,2> (hidden layers, 1000x1000 per state)" if args.precision == "bf16"

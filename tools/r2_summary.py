@@ -1,35 +1,46 @@
-# r2: round-2 profiles (B200, sm_100a)
+"""Writes profiles/r2_summary.md from the round's bench line (profiles/r2_bench_n1.json) and the ncu numbers quoted below
+(extracted with tools/launch_list_summary.py / tools/profile_summary.py from gpurun_out/r2k_* and r2e_*)."""
+import json, os
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+d = json.loads(open(os.path.join(ROOT, "profiles", "r2_bench_n1.json")).read().strip().splitlines()[-1])
+c = d["configs"]; q, n4, n5, f32 = c["c4_qstar"], c["c3_np4"], c["c3_np5"], c["c2_fp32"]
+st = d["roofline"]["stage_ms_one_extra_step_rank0"]
+tot = sum(v for k, v in st.items() if k in ("expand", "filt", "scatter", "heur", "sort", "pushpop", "book"))
+ks = d["kat_solve"]
+sh = lambda x: f"{100 * x['stage_share_one_extra_step']['heur']:.1f} % / {100 * x['stage_share_one_extra_step']['sort']:.1f} % / {100 * x['stage_share_one_extra_step']['pushpop']:.1f} %"
+cpu = lambda x: f"{x['cpu_baseline']['value'] / 1e3:.0f} k" if x.get("cpu_baseline") and "value" in x["cpu_baseline"] else "—"
+md = f"""# r2: round-2 profiles (B200, sm_100a)
 
 All launch lists: `ncu --metrics gpu__time_duration.sum --clock-control none` (serialised, cold-cache: compare SHARES with the live
 CUDA-event numbers, not absolute times); every profiled command exited 0 without ncu first in the same gpurun call
 (`tools/r2_profile.sh`).  Live numbers: `profiles/r2_bench_n1.json` (the raw `bench.py` line of the round's final kernels; CUDA events
 inside the captured iteration).  This file is written by `tools/r2_summary.py`.
 
-## 1. C2 (cube3 A\*, B = 10 000, 8 instances per step, bf16) — last iteration of a step, 34 launches
+## 1. C2 (cube3 A\\*, B = 10 000, 8 instances per step, bf16) — last iteration of a step, 34 launches
 
 `profiles/r2k_launch_list_ncu.csv` (whole step), `profiles/r2_c2_last_iteration_ncu.csv`.  9.9 ms serialised: the 8 tcgen05 GEMM launches (fused
 one-hot + first block, 6 hidden, fused-output last) 94.0 %; radix sort (prepass + flags + 9 one-sweep passes, constant digits return at once) 1.7 %;
 `k_merge` 1.1 %, `k_closed_link` 0.9 %, `k_scatter_kept` 0.9 %, `k_closed_decide` 0.4 %, `k_expand_t` 0.3 %.
-Live (bench, power-capped to ~1275 MHz): heuristic 93.7 % of the step (hidden GEMMs 141 ms + input / first block
-21 ms of 179 ms), sort 4.0 ms, CLOSED 2.4 ms, scatter 1.7 ms, merge / pop 1.8 ms, expand 0.9 ms —
-the kernel's share of the step agrees (94 % serialised at full clocks vs 94 % live).
-Roofline (bench line): hidden GEMMs 1192 TFLOP/s = **0.860** of the measured sustained bf16 peak; whole step 0.828.
+Live (bench, power-capped to ~{d['clocks']['sm_mhz']:.0f} MHz): heuristic {100 * st['heur'] / tot:.1f} % of the step (hidden GEMMs {st['gemm_hidden']:.0f} ms + input / first block
+{st['gemm_input']:.0f} ms of {d['ms_per_step']:.0f} ms), sort {st['sort']:.1f} ms, CLOSED {st['filt']:.1f} ms, scatter {st['scatter']:.1f} ms, merge / pop {st['pushpop']:.1f} ms, expand {st['expand']:.1f} ms —
+the kernel's share of the step agrees (94 % serialised at full clocks vs {100 * st['heur'] / tot:.0f} % live).
+Roofline (bench line): hidden GEMMs {d['roofline']['achieved']:.0f} TFLOP/s = **{d['roofline']['frac']:.3f}** of the measured sustained bf16 peak; whole step {d['roofline']['whole_step_frac']:.3f}.
 `ncu --set full` of the six plain hidden-layer launches of the last iteration (`profiles/r2k_summary.md`, `r2k_gemm_traffic.json`; 783 k rows,
 148 CTAs = 74 CTA pairs): 1.09 ms (no residual) / 1.20 ms (residual) at 1.97 GHz, tensor pipe active 88.2-88.9 % / 85.5-85.8 %, DRAM read + write
 3.24 / 4.89 GB against 3.21 / 4.81 GB algorithmic — traffic = 1.01× algorithmic.
 
 | config (bench `configs`, rank 0, device-timed) | nodes/s | hidden-GEMM frac of sustained bf16 peak | heur / sort / merge share | CPU reference (16 cores) |
 |---|---:|---:|---|---:|
-| C2 cube3 A\* bf16 (headline) | 86.4 M (e2e 85.4 M) | 0.860 | 93.7 % / 2.3 % / 1.0 % | 130 k (1 instance x 12 iterations of the headline workload (974340 nodes, 7.5 s)) |
-| C2 fp32-accurate (split fp16, 3 MMAs per MAC) | 28.6 M | 0.285 (algorithmic FLOPs) | 97.7 % / 0.8 % / 0.4 % | — |
-| C4 cube3 Q\* | 52.6 M | 0.914 | 70.3 % / 12.7 % / 11.8 % | 22 k |
-| C3 npuzzle.4 A\* B = 10 000 | 137.5 M | 0.887 | 88.7 % / 4.8 % / 1.3 % | 82 k |
-| C3 npuzzle.5 A\* B = 1 000 × 64 | 105.4 M | 0.911 | 87.0 % / 6.2 % / 1.7 % | 73 k |
+| C2 cube3 A\\* bf16 (headline) | {d['value'] / 1e6:.1f} M (e2e {d['e2e']['value'] / 1e6:.1f} M) | {d['roofline']['frac']:.3f} | {100 * st['heur'] / tot:.1f} % / {100 * st['sort'] / tot:.1f} % / {100 * st['pushpop'] / tot:.1f} % | {d['cpu_baseline']['value'] / 1e3:.0f} k ({d['cpu_baseline']['sample']}) |
+| C2 fp32-accurate (split fp16, 3 MMAs per MAC) | {f32['value'] / 1e6:.1f} M | {f32['roofline']['frac']:.3f} (algorithmic FLOPs) | {sh(f32)} | — |
+| C4 cube3 Q\\* | {q['value'] / 1e6:.1f} M | {q['roofline']['frac']:.3f} | {sh(q)} | {cpu(q)} |
+| C3 npuzzle.4 A\\* B = 10 000 | {n4['value'] / 1e6:.1f} M | {n4['roofline']['frac']:.3f} | {sh(n4)} | {cpu(n4)} |
+| C3 npuzzle.5 A\\* B = 1 000 × 64 | {n5['value'] / 1e6:.1f} M | {n5['roofline']['frac']:.3f} | {sh(n5)} | {cpu(n5)} |
 
 bf16 against fp32-accurate on C2 itself (`bf16_deviation`: 2 instances in lock-step): popped-set overlap per iteration
-[1.0, 1.0, 1.0, 1.0, 0.996, 0.9936, 0.9877, 0.9859], heuristic error max 1.33e-03 / mean 1.22e-04, nodes generated identical.
+{d['bf16_deviation']['popped_set_overlap_per_iteration']}, heuristic error max {d['bf16_deviation']['heuristic_abs_error_max']:.2e} / mean {d['bf16_deviation']['heuristic_abs_error_mean']:.2e}, nodes generated identical.
 
-## 2. C4 (cube3 Q\*, B = 10 000, 8 instances, 40 iterations) — last iteration, 35 launches
+## 2. C4 (cube3 Q\\*, B = 10 000, 8 instances, 40 iterations) — last iteration, 35 launches
 
 `profiles/r2_q_last_iteration_ncu.csv`.  1 547 µs serialised: GEMMs 982 µs (63.5 %), `k_merge` 245 µs (15.9 %), one-sweep radix passes
 177 µs (11.4 %), `k_merge_partition` 23 µs.  `ncu --set full` of the sort / merge kernels of a late iteration (810 k pushed entries, 25 M-entry OPEN):
@@ -39,7 +50,7 @@ bf16 against fp32-accurate on C2 itself (`bf16_deviation`: 2 instances in lock-s
 | `k_radix_onesweep` (per digit pass) | 18-30 µs | 13.0 MB | ≈ 0 (the scattered output stays in L2) | 16 B read + 16 B written × 810 k = 25.9 MB | 0.9-1.4 TB/s = **0.13-0.22** — look-back-latency-bound at this size (181 registers = one block per SM when captured; now 8 items per thread, 2 blocks per SM: −18 % on the npuzzle.5 sort, −2 % here) |
 | `k_radix_prepass` | 12.4 µs | 9.6 MB | 0 | 8 B × 810 k keys | 0.5 TB/s = 0.08 |
 | `k_merge_partition` | 18.4 µs | 59.7 MB | 3.6 MB | — (32-ary searches) | — |
-| `k_merge` (1 184 blocks) | 163.8 µs | 200.3 MB | 192.2 MB | 12 B read + 12 B written × (25 M OPEN + 0.8 M batch) = 620 MB nominal; 392 MB measured (part of the run is L2-resident) | 2.4 TB/s = **0.37** — and O(\|OPEN\|) work for an O(batch) change: the kernel furthest from what the algorithm needs |
+| `k_merge` (1 184 blocks) | 163.8 µs | 200.3 MB | 192.2 MB | 12 B read + 12 B written × (25 M OPEN + 0.8 M batch) = 620 MB nominal; 392 MB measured (part of the run is L2-resident) | 2.4 TB/s = **0.37** — and O(\\|OPEN\\|) work for an O(batch) change: the kernel furthest from what the algorithm needs |
 
 ## 3. Small-batch iteration (tutorial KAT: cube3, graph.100B_0.1W, resnet_fc.200H_2B, ~1200 children per iteration), bf16 — 4 launches
 
@@ -48,8 +59,8 @@ bf16 against fp32-accurate on C2 itself (`bf16_deviation`: 2 instances in lock-s
 every ~6 iterations).  Start of the round: 11-13 launches (`k_small_filter_v` 27.3, six network launches 75-85, `k_small_push_v` 21.3,
 `k_merge_partition` 6.4, `k_merge` 10.5, `k_end_iter` 5.4 µs).
 Live per-iteration device time (`tools/latency_probe.py`, CUDA events around `dx_run`): 112.3 µs bf16 / 139.7 fp32 / 73.3 zero heuristic →
-**67.9 / 77.1 / 45.3 µs**.  Solve time per KAT instance (bench `kat_solve`): fp32 14.9 → **8.7 ms** (costs, node counts exact 10/10), bf16 10.8 →
-**7.2 ms** (costs exact 10/10, nodes -32 %…+8 %).
+**67.9 / 77.1 / 45.3 µs**.  Solve time per KAT instance (bench `kat_solve`): fp32 14.9 → **{1e3 * ks['fp32']['mean_solve_time_s']:.1f} ms** (costs, node counts exact 10/10), bf16 10.8 →
+**{1e3 * ks['bf16']['mean_solve_time_s']:.1f} ms** (costs exact 10/10, nodes {100 * ks['bf16']['nodes_generated_deviation_min_max'][0]:.0f} %…+{100 * ks['bf16']['nodes_generated_deviation_min_max'][1]:.0f} %).
 `ncu --set full`: `k_mlp_small<1, false>` (75 CTAs × 544 threads, 94 registers) 16.5 µs, 0.84 MB of DRAM reads (the weight stream comes from L2), tensor
 pipe active 6 % — shared-memory-bandwidth / latency kernel (DESIGN.md §10); `k_small_filter_v2` 21.4-22.5 µs, 33-37 k warp instructions, 0.95-0.98 IPC,
 issue slots 24 % busy (latency chains: CAS → compare → exchange → slot read); `k_small_tail_v` 22.7-24.2 µs, 65-74 k warp instructions, 1.7 IPC, issue slots
@@ -57,6 +68,9 @@ issue slots 24 % busy (latency chains: CAS → compare → exchange → slot rea
 
 ## 4. Multi-GPU (raw bench lines: `profiles/r2_bench_n2.json`, `profiles/r2_bench_n8.json`)
 
-See DESIGN.md §6.  Instance-sharded headline: 84.7 M (1 GPU) → 168.7 M (2) → 665.8 M nodes/s (8 B200s, 7.86×).  One HDA\* search:
+See DESIGN.md §6.  Instance-sharded headline: 84.7 M (1 GPU) → 168.7 M (2) → 665.8 M nodes/s (8 B200s, 7.86×).  One HDA\\* search:
 2 GPUs 123.9 M (peer-memory exchange) / 119.9 M (NCCL all-to-all), exchange phase 0.016 / 0.064 ms of a 1.51 / 1.56 ms iteration, load imbalance
 1.05; 8 GPUs (B = 80 000) **508.4 M** / 489.0 M nodes/s, exchange 0.023 / 0.086 ms of 1.43 / 1.49 ms, imbalance 1.12.
+"""
+open(os.path.join(ROOT, "profiles", "r2_summary.md"), "w").write(md)
+print("written", len(md))

@@ -54,7 +54,7 @@ bf16 against fp32-accurate on C2 itself (`bf16_deviation`: 2 instances in lock-s
 
 ## 3. Small-batch iteration (tutorial KAT: cube3, graph.100B_0.1W, resnet_fc.200H_2B, ~1200 children per iteration), bf16 — 4 launches
 
-`profiles/r2_kat_last_iteration_ncu.csv` (final kernels, programmatic dependent launches off for the capture): `k_expand_t` 7.7 µs, `k_small_filter_v2` 20.6 µs,
+`profiles/r2_kat_last_iteration_ncu.csv` (final kernels): `k_expand_t` 7.7 µs, `k_small_filter_v2` 20.6 µs,
 `k_mlp_small` 15.5 µs, `k_small_tail_v` 25.4 µs (69 µs; plus a compaction — `k_young_plan`, `k_merge_partition`, `k_merge`, `k_young_finish`, copy-back —
 every ~6 iterations).  Start of the round: 11-13 launches (`k_small_filter_v` 27.3, six network launches 75-85, `k_small_push_v` 21.3,
 `k_merge_partition` 6.4, `k_merge` 10.5, `k_end_iter` 5.4 µs).

@@ -409,3 +409,35 @@ def test_young_run_is_flushed_when_the_batch_outgrows_the_small_regime():
     eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st[:2], goals[:2], 50, 0.5, 14, pseudo_v, add_later=(7, st[2:], goals[2:], 400),
                              max_pop=2 * 50 + 400)
     eng.close()
+
+
+def test_bursts_stop_in_the_exact_iteration_and_the_engine_continues_after_a_finished_search(monkeypatch):
+    """dx_run launches bursts of iterations per host poll in the small-batch regime; the device raises a DONE bit in the iteration
+    that finishes the last instance, so the rest of the burst must be a no-op: same iteration counts / nodes / costs as polling every
+    iteration, max_iters honoured when it is not a multiple of the burst, and an engine whose search ended mid-burst (young runs,
+    compaction schedule and buffer parities included) keeps working when another instance is added without a reset."""
+    L = _lib()
+    k = gu.load("kat_cube3")
+    sd = gu.state_dict_np("cube3v")
+    blob, info = L.pack_state_dict(sd)
+    results = {}
+    for poll in ("1", "4", "7"):
+        monkeypatch.setenv("DXB200_POLL_EVERY", poll)
+        eng = L.Engine("cube3", 0, "graph_v", L.DX_HEUR_NET_FP32, max_instances=3, max_pop_total=300, max_nodes=900000)
+        eng.load_weights(54, 6, info["res_dim"], info["num_blocks"], 1, True, blob)
+        eng.add_instances(k["hard_states"][:1], k["hard_goals"][:1], 100, 0.1)
+        assert eng.run(10) == 10 and eng.status()[0].itr == 10              # (10 is neither a multiple of 4 nor of 7)
+        done = 10 + eng.run(100000)
+        s0 = eng.status()[0]
+        assert s0.finished and s0.itr == done
+        eng.add_instances(k["hard_states"][1:3], k["hard_goals"][1:3], 100, 0.1)      # no reset: slots 1 and 2 join a finished slot 0
+        more = eng.run(100000)
+        st = eng.status()
+        results[poll] = (done, more, [(s.itr, s.num_nodes_generated, s.ub, bool(s.finished)) for s in st],
+                         [eng.get_path(j)[0] for j in range(3)])
+        eng.close()
+    assert results["1"] == results["4"] == results["7"]
+    done, more, stat, paths = results["4"]
+    # instance 0 alone is the KAT search: the reference's iteration count / node count / cost (tests/golden/kat_cube3.npz)
+    assert stat[0][1] == int(k["hard_nodes"][0]) and stat[0][2] == float(k["hard_path_costs"][0])
+    assert all(s[3] for s in stat) and all(p is not None for p in paths)

@@ -94,6 +94,7 @@ SIGNATURES = {
     "dx_get_stage_calls": (C.c_int, [_engp, C.POINTER(C.c_int64), C.c_int32]),
     "dx_last_run_ms": (C.c_int, [_engp, _f32p]),
     "dx_debug_tc_profile": (C.c_int, [_engp, C.POINTER(C.c_uint64)]),
+    "dx_backup_deepest": (C.c_int, [_engp, _u8p, _i32p, C.c_int32]),
     "dx_hda_config": (C.c_int, [_engp, C.c_int32, C.c_int32]),
     "dx_hda_record_bytes": (C.c_int, [_engp, _i32p]),
     "dx_hda_owner": (C.c_int, [_engp, _u8p, _i32p]),
@@ -311,6 +312,16 @@ class Engine:
         if self.is_q:
             return st[:k], act[:k], bk[:k], ins[:k]
         return st[:k], bk[:k], ins[:k]
+
+    def backup_deepest(self) -> Tuple[np.ndarray, np.ndarray]:
+        """UpdateHER._get_her_goals (base/updater.py:485-530): per instance slot, (state of the deepest node with children among
+        the logged records -- the root's when nothing deeper was expanded, depth).  Call before drain_backups."""
+        n = max(self.num_instances(), 1)
+        st = np.empty((n, self.state_bytes), np.uint8)
+        dp = np.empty(n, np.int32)
+        check(self._lib.dx_backup_deepest(self._h, _p(st, _u8p), _p(dp, _i32p), n))
+        k = self.num_instances()
+        return st[:k], dp[:k]
 
     def get_path(self, inst: int, cap: int = 4096, with_states: bool = False):
         """-> (actions list or None, states_on_path [len+1, S] or None)"""

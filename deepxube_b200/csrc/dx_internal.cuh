@@ -136,6 +136,7 @@ struct InstArrays {
     uint32_t* tile_off;         // [I+1] merge tile offsets
     unsigned long long* f_first;// key of the first popped entry this iteration
     uint8_t* goals;             // [I, SP] goal rows
+    uint32_t* root;             // [I] node id of the instance's root
 };
 
 // is_solved (cube3.py:514-517, npuzzle.py:154-158: goal byte d*d = wildcard, grid.py:68-69, lightsout: all tiles off)
@@ -382,6 +383,9 @@ int dx_launch_bellman_backup(cudaStream_t s, const DomainDev& d, Ctl* ctl, const
 int dx_launch_backup_children(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const uint8_t* child_flags,
                               const uint32_t* child_prefix, const BackupLog& bk, int max_children);
 int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const BackupLog& bk);
+int dx_launch_her_deepest(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, const uint32_t* node_parent,
+                          const uint8_t* node_action, const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
+                          uint32_t* rec_depth, uint32_t* best_depth, uint32_t* deep_node, uint8_t* out_rows, int max_inst);
 int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr);
 int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const uint8_t* node_solved,
                              const float* node_h, const BackupLog& bk, int mode, uint32_t it_first, uint32_t it_last);

@@ -233,6 +233,8 @@ struct dx_engine {
     bool eval_all = false;
     float* child_h = nullptr;
     BackupLog bk = {};
+    uint32_t *her_cand = nullptr, *her_depth = nullptr, *her_best = nullptr, *her_node = nullptr;   // dx_backup_deepest scratch
+    uint8_t* her_rows = nullptr;
     bool backups_q = false;          // graph_q with a backup log: labels of the popped edges
     uint8_t* node_solved = nullptr;
     uint32_t* popped[2] = {nullptr, nullptr}; uint32_t* popped_inst[2] = {nullptr, nullptr}; uint32_t* pop_off[2] = {nullptr, nullptr};
@@ -538,7 +540,9 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
             A_(e->bk.node_rec, N);
         }
         if (e->backups_q) { A_(e->node_solved, N); A_(e->bk.node, K); A_(e->bk.itr, K); A_(e->bk.node_aux, N); }
+        A_(e->her_cand, K); A_(e->her_depth, K);          // hindsight relabelling (dx_backup_deepest)
     }
+    A_(e->her_best, I); A_(e->her_node, I); A_(e->her_rows, I * e->S);
     A_(e->child_slot, C + 1); A_(e->child_next, C + 1); A_(e->child_flags, C + 1); A_(e->child_prefix, C + 8); A_(e->new_inst, C + 1);
     for (int p = 0; p < 2; ++p) {
         A_(e->popped[p], P); A_(e->popped_inst[p], P); A_(e->pop_off[p], I + 1);
@@ -562,7 +566,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
     A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);
-    A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP);
+    A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP); A_(e->ia.root, I);
     if (!e->is_q && !e->is_beam && I <= 256) {      // young-run OPEN (small-batch regime); 200 KB
         for (int p = 0; p < 2; ++p) {
             A_(e->young.key[p], (size_t)DX_YOUNG_BUF); A_(e->young.val[p], (size_t)DX_YOUNG_BUF);
@@ -822,6 +826,7 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
     DX_CUDA(cudaMemcpyAsync(e->ia.lb + I0, hlb.data(), n * 8, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->ia.ub_key + I0, hub.data(), n * 8, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->ia.goal_node + I0, hgoal.data(), n * 4, cudaMemcpyHostToDevice, s));
+    DX_CUDA(cudaMemcpyAsync(e->ia.root + I0, hpop.data(), n * 4, cudaMemcpyHostToDevice, s));      // (hpop = the new roots' node ids)
     DX_CUDA(cudaMemcpyAsync(e->ia.itr + I0, hz.data(), n * 4, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->ia.gen + I0, hgen.data(), n * 8, cudaMemcpyHostToDevice, s));
     DX_CUDA(cudaMemcpyAsync(e->ia.active + I0, hact.data(), n, cudaMemcpyHostToDevice, s));
@@ -1350,6 +1355,25 @@ extern "C" int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int
     k_reset_backups<<<1, 1, 0, s>>>(e->d_ctl);
     e->launches += 1;
     DX_CUDA(cudaStreamSynchronize(s));
+    return DX_OK;
+}
+
+// UpdateHER._get_her_goals (deepxube/base/updater.py:485-530): per instance, the state of the deepest node that has children among
+// the records currently in the backup log (the root's state when nothing deeper was expanded) and its depth.  Call before the drain.
+extern "C" int dx_backup_deepest(dx_engine* e, uint8_t* states, int32_t* depths, int32_t cap) {
+    if (!e || !states) DX_FAIL(DX_ERR_ARG, "null argument");
+    if (!e->eval_all && !e->backups_q) DX_FAIL(DX_ERR_STATE, "engine was created with max_backups == 0");
+    if (e->pending) DX_FAIL(DX_ERR_STATE, "step pending");
+    if (cap < e->n_inst) DX_FAIL(DX_ERR_ARG, "buffer holds fewer rows than there are instances");
+    DX_CUDA(cudaSetDevice(e->cfg.device));
+    if (e->n_inst == 0) return DX_OK;
+    cudaStream_t s = e->stream;
+    e->launches += dx_launch_her_deepest(s, e->dom, e->d_ctl, e->bk, e->node_parent, e->node_action, e->node_state, e->backups_q ? 1 : 0,
+                                         e->ia.root, e->her_cand, e->her_depth, e->her_best, e->her_node, e->her_rows, e->n_inst);
+    DX_CUDA(cudaMemcpyAsync(states, e->her_rows, (size_t)e->n_inst * e->S, cudaMemcpyDeviceToHost, s));
+    if (depths) DX_CUDA(cudaMemcpyAsync(depths, e->her_best, (size_t)e->n_inst * 4, cudaMemcpyDeviceToHost, s));
+    DX_CUDA(cudaStreamSynchronize(s));
+    DX_CUDA(cudaGetLastError());
     return DX_OK;
 }
 

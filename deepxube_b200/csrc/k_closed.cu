@@ -987,3 +987,75 @@ int dx_launch_beam_keep_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, 
     k_beam_keep_q<<<min(dx_div_up(max_items, 256), 148 * 8), 256, 0, s>>>(ctl, ia, popped_inst, flags);
     return 1;
 }
+
+// ---------------------------------------------------------------------------------------------
+// Hindsight relabelling (UpdateHER._get_her_goals, deepxube/base/updater.py:485-530): for an instance that did not finish with a
+// solution the relabelled goal is sampled from the DEEPEST node that has children (an expanded node; the root when nothing deeper
+// was expanded); the reference walks `root.get_all_descendants()` (breadth first, children in action order) and keeps the first
+// node of the largest depth -- among equally deep nodes, the one whose action path from the root is lexicographically smallest.
+// Candidates come from the backup log: A* records are the expanded nodes; a Q* record is a popped edge, whose node has a child.
+//   her_depth: depth of every record's candidate (parent hops to the root) and the per-instance maximum
+//   her_pick : the first of the deepest in that walk's order (two equally deep nodes are compared below their lowest common ancestor)
+__global__ void k_her_depth(const Ctl* __restrict__ ctl, BackupLog bk, const uint32_t* __restrict__ node_parent, int is_q,
+                            uint32_t* __restrict__ rec_cand, uint32_t* __restrict__ rec_depth, uint32_t* __restrict__ best_depth) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        if (bk.val[r] != bk.val[r]) { rec_cand[r] = DX_NIL; continue; }          // popped by an instance that had finished
+        uint32_t c = bk.node[r];
+        if (is_q) c = node_parent[c];                                            // the edge's node (the generated node's parent)
+        uint32_t depth = 0;
+        for (uint32_t x = c; node_parent[x] != DX_NIL; x = node_parent[x]) ++depth;
+        rec_cand[r] = c;
+        rec_depth[r] = depth;
+        atomicMax(&best_depth[bk.inst[r]], depth);
+    }
+}
+
+// One thread per record of the largest depth: a compare-and-swap tournament on the instance's slot.  `earlier(c, cur)` orders two
+// equally deep nodes the way the reference's breadth-first walk meets them: below their lowest common ancestor, by the order in
+// which the LCA's two children entered its edge_dict -- action order for A* (children are generated together, ids in action
+// order), pop order of the edges for Q* -- which is the order of the children's node ids in both cases.
+__global__ void k_her_pick(const Ctl* __restrict__ ctl, BackupLog bk, const uint32_t* __restrict__ node_parent,
+                           const uint32_t* __restrict__ rec_cand, const uint32_t* __restrict__ rec_depth,
+                           const uint32_t* __restrict__ best_depth, uint32_t* __restrict__ deep_node) {
+    const uint32_t n = ctl->n_backups;
+    for (uint32_t r = blockIdx.x * blockDim.x + threadIdx.x; r < n; r += gridDim.x * blockDim.x) {
+        const uint32_t c = rec_cand[r];
+        if (c == DX_NIL) continue;
+        const uint32_t i = bk.inst[r];
+        if (rec_depth[r] != best_depth[i] || rec_depth[r] == 0) continue;
+        uint32_t cur = *((volatile uint32_t*)&deep_node[i]);
+        for (;;) {
+            if (cur == c) break;
+            if (cur != DX_NIL) {
+                uint32_t a = c, b = cur, ap = c, bp = cur;                       // equal depths: the walks meet at the LCA
+                while (a != b) { ap = a; bp = b; a = node_parent[a]; b = node_parent[b]; }
+                if (ap > bp) break;                                              // the holder comes first
+            }
+            const uint32_t seen = atomicCAS(&deep_node[i], cur, c);
+            if (seen == cur) break;
+            cur = seen;
+        }
+    }
+}
+
+__global__ void k_her_rows(DomainDev d, const Ctl* __restrict__ ctl, const uint8_t* __restrict__ node_state,
+                           const uint32_t* __restrict__ deep_node, const uint32_t* __restrict__ root, uint8_t* __restrict__ out_rows) {
+    const uint32_t I = ctl->n_inst;
+    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < I * (uint32_t)d.S; t += gridDim.x * blockDim.x) {
+        const uint32_t i = t / d.S, b = t - i * d.S;
+        const uint32_t nd = deep_node[i] == DX_NIL ? root[i] : deep_node[i];       // nothing deeper than the root was expanded
+        out_rows[t] = node_state[(size_t)nd * d.SP + b];
+    }
+}
+
+int dx_launch_her_deepest(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, const uint32_t* node_parent,
+                          const uint8_t* node_action, const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
+                          uint32_t* rec_depth, uint32_t* best_depth, uint32_t* deep_node, uint8_t* out_rows, int max_inst) {
+    cudaMemsetAsync(best_depth, 0, (size_t)max_inst * sizeof(uint32_t), s);
+    k_her_depth<<<148 * 4, 256, 0, s>>>(ctl, bk, node_parent, is_q, rec_cand, rec_depth, best_depth);
+    cudaMemsetAsync(deep_node, 0xff, (size_t)max_inst * sizeof(uint32_t), s);
+    k_her_pick<<<148 * 4, 256, 0, s>>>(ctl, bk, node_parent, rec_cand, rec_depth, best_depth, deep_node);
+    k_her_rows<<<min(dx_div_up((long long)max_inst * d.S, 256), 148 * 4), 256, 0, s>>>(d, ctl, node_state, deep_node, root, out_rows);
+    return 3;
+}

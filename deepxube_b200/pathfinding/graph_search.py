@@ -164,6 +164,12 @@ class GraphSearch(PathFind):
         mode "bellman" | "ub_solns" | "lhbl" (graph_v)"""
         return self._engine.drain_backups(mode)
 
+    def backup_deepest(self):
+        """-> (state rows [n_slots, S], depths [n_slots]): per instance slot, the state of the deepest node that has children among
+        the logged expansions (the root's when there is none) -- the relabelling source of UpdateHER._get_her_goals
+        (base/updater.py:508-527).  Reads the log: call it before `drain_backups`."""
+        return self._engine.backup_deepest()
+
     # ---- PathFind protocol -----------------------------------------------------------------------------
     def make_instances(self, states: List[Any], goals: List[Any], inst_infos: Optional[List[Any]] = None,
                        compute_root_vals: bool = True, batch_size: Optional[int] = None, weight: Optional[float] = None,

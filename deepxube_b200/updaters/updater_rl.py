@@ -1,6 +1,7 @@
 """Training-data generation from the search: the value-iteration targets of the heuristic network.
 
-Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq` with the goal kept (no HER); labels without a
+Mirror of ONE runner of the reference's RL updaters for `heurv` / `heurq`, with the goal kept or relabelled in hindsight
+(HER, `UpdateHeurVRLHER` / `UpdateHeurQRLHER` below); labels without a
 replay buffer: Bellman backups, `ub_heur_solns`, LHBL tree backups; with a replay buffer (`rb_size > 0`): the popped nodes /
 edges of every emitted instance group go into an array-backed replay buffer, as many elements are sampled back, and their
 value-iteration targets are recomputed with the (target) network on the device (`dx_vi_targets`):
@@ -15,6 +16,8 @@ value-iteration targets are recomputed with the (target) network on the device (
     base/updater.py:763-795        _rb_add_sample_train_data / _get_instance_data_rb: add, sample len(popped), label, to_np
     updaters/updater_rl.py:30-69, 85-120  replay data (is_solved [, tc, next state]) and the labels of sampled elements
     base/updater.py:330-341        one `update_runner` work item = one batch of searches; `generate()` runs several
+    base/updater.py:485-583, 803-818  HER: instances that did not finish with a solution get the goal sampled from their deepest
+                                   expanded node (found on the device, `dx_backup_deepest`), goal-keeping instances first
 
 The search and the backups run on the device (graph_v engine created with max_backups > 0: every generated child is
 evaluated before the CLOSED filter and each expanded node's backup is logged by k_bellman_backup); this module only owns the
@@ -33,6 +36,7 @@ _GOAL_CACHE: dict = {}       # goal row bytes -> goal object (replay-buffer mode
 
 class UpdateHeurVRLKeepGoal:
     is_q = False
+    her = False
 
     def __init__(self, domain: Any, pathfind: GraphSearch, search_itrs: int, nnet_input: Optional[Any] = None,
                  ub_heur_solns: bool = False, lhbl: bool = False, rb_size: int = 0):
@@ -48,6 +52,11 @@ class UpdateHeurVRLKeepGoal:
         self.domain, self.pathfind, self.search_itrs, self.nnet_input = domain, pathfind, int(search_itrs), nnet_input
         self.rb_size = int(rb_size)
         self.rb: Optional[Any] = None                   # _init_replay_buffer (base/updater.py:707-708), built on first use
+        if self.her:
+            if self.rb_size <= 0:
+                raise NotImplementedError("Must use replay buffer if doing HER.")                     # base/updater.py:483
+            if not hasattr(domain, "sample_goal_from_state"):
+                raise TypeError("HER needs a GoalSampleableFromState domain (base/domain.py:421-431); of the device domains: grid")
 
     def _make_instances(self, steps_gen: List[int]) -> List[Any]:
         states, goals = self.domain.sample_problem_instances(steps_gen)                      # base/updater.py:679-685
@@ -84,14 +93,15 @@ class UpdateHeurVRLKeepGoal:
                 groups.append(removed)
         if pf.instances:
             groups.append(list(pf.instances))
+        deepest = pf.backup_deepest()[0] if self.her else None     # (before the drain empties the log)
         drained = pf.drain_backups(self.label_mode)
         rows, vals, slots = drained[0], drained[-2], drained[-1]
+        if self.rb_size > 0:
+            return self._emit_rb(groups, rows, slots, drained[1] if self.is_q else None, deepest)
         # regroup the device log (iteration-major) into the reference's emission order
         per_group = [np.concatenate([np.flatnonzero(slots == inst._slot) for inst in g]) if len(vals) else np.zeros(0, np.int64)
                      for g in groups]
         goal_of = {inst._slot: inst.root_node.goal for g in groups for inst in g}
-        if self.rb_size > 0:
-            return self._emit_rb(per_group, rows, slots, drained[1] if self.is_q else None, goal_of)
         order = np.concatenate(per_group) if per_group else np.zeros(0, np.int64)
         states = self.domain.rows_to_states(rows[order])
         goals = [goal_of[int(s)] for s in slots[order]]
@@ -105,17 +115,27 @@ class UpdateHeurVRLKeepGoal:
         from deepxube_b200.updaters.replay_buffer import ReplayBufferQ, ReplayBufferV
         self.rb = (ReplayBufferQ if self.is_q else ReplayBufferV)(self.rb_size, state_bytes, goal_bytes)
 
-    def _emit_rb(self, per_group: List[np.ndarray], rows: np.ndarray, slots: np.ndarray, acts: Optional[np.ndarray], goal_of: dict) -> Tuple:
+    def _group_goals(self, group: List[Any], deepest: Optional[np.ndarray]) -> Tuple[List[Any], List[Any]]:
+        """-> the group's instances in emission order and the goal each one's data is labelled against: their own."""
+        return list(group), [inst.root_node.goal for inst in group]
+
+    def _emit_rb(self, groups: List[List[Any]], rows: np.ndarray, slots: np.ndarray, acts: Optional[np.ndarray],
+                 deepest: Optional[np.ndarray]) -> Tuple:
         """For every emitted instance group, in emission order: popped data -> replay buffer, sample as many elements back,
         label them with the device network (`_get_instance_data_rb` -> `_rb_add_sample_train_data`).  Everything stays in packed
         rows until the end; -> (states, goals, [Q: actions,] labels) of the SAMPLED elements, groups concatenated."""
         from deepxube_b200 import _lib
         dom = self.domain
-        slot_ids = sorted(goal_of)
-        grow_of = dict(zip(slot_ids, dom.goals_to_rows([goal_of[k] for k in slot_ids])))
         fn_eng = self._device_fn()._engine()
         out_rows, out_grows, out_acts, out_labels = [], [], [], []
-        for idx in per_group:
+        goal_of: dict = {}
+        grow_of: dict = {}
+        for group in groups:
+            insts, goals_g = self._group_goals(group, deepest)
+            grows_g = dom.goals_to_rows(goals_g)
+            for inst, goal, grow in zip(insts, goals_g, grows_g):
+                goal_of[inst._slot], grow_of[inst._slot] = goal, grow
+            idx = np.concatenate([np.flatnonzero(slots == inst._slot) for inst in insts]) if len(slots) else np.zeros(0, np.int64)
             if len(idx) == 0:
                 continue
             r = rows[idx]
@@ -205,3 +225,33 @@ class UpdateHeurQRLKeepGoal(UpdateHeurVRLKeepGoal):
         fn = self._device_fn()
         rows, grows = self.domain.states_to_rows(states_next), self.domain.goals_to_rows(goals)
         return fn._engine().vi_targets(rows, grows, np.asarray(is_solved_l, bool)).tolist()
+
+
+
+class _HERMixin:
+    """UpdateHER._get_her_goals (base/updater.py:485-530) over engine-backed instances: an instance that finished with a solution
+    keeps its goal; every other one is relabelled with `domain.sample_goal_from_state(start states, deepest states)`, the deepest
+    state being that of its deepest node that has children (the root's when nothing deeper was expanded) -- found on the device by
+    `dx_backup_deepest` (csrc/k_closed.cu: k_her_depth / k_her_pick).  The goal-keeping instances are emitted first, as in the
+    reference.  `_get_her_node_data` / `_get_her_edge_data` (:532-583) are what `_emit_rb` does with the returned goals: the popped
+    nodes / edges of each instance with the instance's (new) goal, is_solved recomputed against it."""
+    her = True
+
+    def _group_goals(self, group: List[Any], deepest: Optional[np.ndarray]) -> Tuple[List[Any], List[Any]]:
+        np.random.uniform(0, 1, size=len(group))       # `rand_keeps` (:495): drawn and unused by the reference; keeps the RNG stream aligned
+        keep = [i for i in group if i.finished() and i.has_soln()]
+        relabel = [i for i in group if not (i.finished() and i.has_soln())]
+        goals = [i.root_node.goal for i in keep]
+        if relabel:
+            starts = [i.root_node.state for i in relabel]
+            deep = self.domain.rows_to_states(deepest[[i._slot for i in relabel]])
+            goals = goals + list(self.domain.sample_goal_from_state(starts, deep))
+        return keep + relabel, goals
+
+
+class UpdateHeurVRLHER(_HERMixin, UpdateHeurVRLKeepGoal):
+    """`up_her_v` (updaters/updater_rl.py:203-212, 253-264)"""
+
+
+class UpdateHeurQRLHER(_HERMixin, UpdateHeurQRLKeepGoal):
+    """`up_her_q` (updaters/updater_rl.py:215-224, 311-323)"""

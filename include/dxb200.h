@@ -192,6 +192,14 @@ enum dx_backup_mode { DX_BACKUP_BELLMAN = 0, DX_BACKUP_UB_SOLNS = 1, DX_BACKUP_L
 int dx_drain_backups(dx_engine* e, int32_t mode, uint8_t* states, int32_t* actions, double* backups, int32_t* insts, int64_t cap,
                      int64_t* n);
 
+/* Hindsight experience replay, goal relabelling (UpdateHER._get_her_goals, deepxube/base/updater.py:485-530): for every instance
+ * slot, the state of the DEEPEST node that has children among the records currently in the backup log -- expanded nodes (graph_v) /
+ * nodes of popped edges (graph_q); the reference keeps the first node of the largest depth in `root.get_all_descendants()` order
+ * (breadth first, children in action order), i.e. the lexicographically smallest action path among the deepest -- or the root's state
+ * when nothing deeper was expanded.  states [cap >= instances, state_bytes], depths [cap] (may be NULL).  The caller relabels with
+ * domain.sample_goal_from_state(start, deepest) for the instances that did not finish solved.  Call before dx_drain_backups. */
+int dx_backup_deepest(dx_engine* e, uint8_t* states, int32_t* depths, int32_t cap);
+
 /* get_path (base/pathfinding.py:93-120): device-side parent walk from goal_node.  actions [cap],
  * states_on_path [(cap+1), state_bytes] (may be NULL).  *len = number of actions (path length). */
 int dx_get_path(dx_engine* e, int32_t inst, int32_t* actions, uint8_t* states_on_path, int32_t cap, int32_t* len);

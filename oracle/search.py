@@ -85,6 +85,7 @@ class OracleInstance:
         self.nodes_curr = np.array([0], np.int64)
         self.itr = 0
         self.num_nodes_generated = 0
+        self.expanded: set = set()      # ids of the nodes that have children (A*: expanded; Q*: at least one edge popped)
         if not is_q:
             self.closed[self.store.state[0].tobytes()] = 0.0   # graph_search.py:119-121
 
@@ -125,6 +126,30 @@ class OracleInstance:
 
     def path_cost(self) -> float:
         return np.inf if self.goal_node is None else float(self.store.g[self.goal_node])
+
+    def has_soln(self) -> bool:
+        return self.goal_node is not None
+
+    def deepest_with_children(self) -> Tuple[np.ndarray, int]:            # base/updater.py:508-527
+        """UpdateHER._get_her_goals' relabelling source: walk the root's descendants breadth first (Node.get_all_descendants,
+        base/pathfinding.py:78-90: a FIFO, children in edge_dict insertion order = node-id order here), keep the FIRST node with
+        children whose depth (the reference counts the states on its path, here the hops: same order) is strictly larger than any before;
+        the root's state when no descendant has children.  "Has children" = was expanded (`self.expanded`), also when the CLOSED
+        filter dropped every child; dropped children never enter the store, but they have no children of their own, so leaving
+        them out changes neither the candidates nor their order.  -> (state row, depth)"""
+        st = self.store
+        kids: Dict[int, List[int]] = {}
+        for nid in range(1, st.n):
+            kids.setdefault(int(st.parent[nid]), []).append(nid)
+        best, best_depth = 0, 0
+        fifo = [(c, 1) for c in kids.get(0, [])]
+        while fifo:
+            nid, depth = fifo.pop(0)
+            for c in kids.get(nid, []):
+                fifo.append((c, depth + 1))
+            if nid in self.expanded and depth > best_depth:
+                best, best_depth = nid, depth
+        return st.state[best].copy(), best_depth
 
     def get_path(self) -> Tuple[np.ndarray, List[int], float]:            # base/pathfinding.py:93-120
         assert self.goal_node is not None
@@ -223,6 +248,7 @@ class OracleSearch:
             cpar = np.repeat(ids, a)
             cact = np.tile(np.arange(a), len(ids))
             inst.num_nodes_generated += cst.shape[0]
+            inst.expanded.update(int(x) for x in ids)
             per.append([inst, cst, cg, cpar, cact, None])
         if not self.eval_kept_only:
             allst = np.concatenate([p[1] for p in per])
@@ -379,6 +405,7 @@ class OracleSearch:
             cst = dom.next_state(st.state[par], act) if len(par) else np.zeros((0, dom.state_len), np.uint8)
             cg = st.g[par] + 1.0                                          # base/pathfinding.py:542
             new_ids = st.append(cst, cg, par, act)
+            inst.expanded.update(int(x) for x in par)
             inst.num_nodes_generated += len(new_ids)                      # base/pathfinding.py:562-563
             per.append((inst, new_ids, ids, keep, costs))
         allst = np.concatenate([p[0].store.state[p[1]] for p in per])

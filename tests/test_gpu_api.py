@@ -556,3 +556,99 @@ def test_updater_rl_replay_buffer_mode(is_q):
     out = up.generate(2, 8, [0.25, 0.25, 0.25, 0.25], 3)            # the runner loop over work items (base/updater.py:330-395)
     assert len(out) == 2 and all(len(o[0]) >= 8 for o in out)
     pathfind.close()
+
+
+@pytest.mark.parametrize("is_q", [False, True])
+def test_updater_her_relabels_goals_from_the_deepest_nodes(is_q):
+    """SURVEY 8f.1, hindsight experience replay (`up_her_v` / `up_her_q`, base/updater.py:485-583, 803-818): instances that finish
+    with a solution keep their goal and are emitted first; every other instance's popped nodes / edges are relabelled with the goal
+    sampled from its deepest expanded node (dx_backup_deepest, pinned to the reference in tests/test_gpu_engine.py); is_solved and
+    the labels are recomputed against the new goals.  Checked here: the plumbing through the registries -- which instances are
+    relabelled, what `sample_goal_from_state` is asked, what enters the replay buffer, the labels of what is sampled back."""
+    from deepxube_b200 import _lib as L
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLHER, UpdateHeurVRLHER, UpdateHeurVRLKeepGoal
+    random.seed(5)
+    np.random.seed(5)
+    dom, name = get_domain_from_arg("grid.7d")
+    fn = str(gu.vi_case("q_grid7_net" if is_q else "v_grid7_net")["cfg"][1])
+    pfns, _ = get_path_fns_nnet_par_dict(dom, name, [fn])
+    heur = pfns.heurq if is_q else pfns.heurv
+    heur.nnet.load_state_dict(gu.state_dict_np("gridq" if is_q else "gridv"))
+    pathfind, _, _ = get_pathfind_from_arg(dom, pfns, "graph.1B_1.0W")
+    cls = UpdateHeurQRLHER if is_q else UpdateHeurVRLHER
+    with pytest.raises(NotImplementedError, match="replay buffer"):
+        cls(dom, pathfind, 4)                                                   # base/updater.py:483
+    calls = []
+    orig = dom.sample_goal_from_state
+
+    relabelling = [False]
+
+    def recording(starts, deepest):                 # (the domain also draws the goals of new problem instances through it)
+        if relabelling[0]:
+            calls.append((list(starts), list(deepest)))
+        return orig(starts, deepest)
+
+    def watch(up_):
+        inner = up_._group_goals
+
+        def group_goals(group, deepest):
+            relabelling[0] = True
+            try:
+                return inner(group, deepest)
+            finally:
+                relabelling[0] = False
+        up_._group_goals = group_goals
+        return up_
+
+    dom.sample_goal_from_state = recording
+    itrs = 5
+    up = watch(cls(dom, pathfind, itrs, rb_size=100000))
+    # search_itrs iterations of batch-size-1 A*: far-away goals are not reached, near ones are
+    steps_gen = [0, 1, 2, 12, 12, 11, 3, 10, 12, 1, 9, 12] * 4
+    data = up.get_instance_data(steps_gen)
+    states, goals, labels = data[0], data[1], np.asarray(data[-1])
+    assert len(calls) >= 1 and len(states) == len(goals) == len(labels) == up.rb.size() > len(steps_gen)
+    n_relabelled = sum(len(c[0]) for c in calls)
+    assert 0 < n_relabelled
+    for starts, deepest in calls:
+        for s, d in zip(starts, deepest):            # the deepest expanded node is at most search_itrs - 1 moves from the start
+            assert abs(s.robot_x - d.robot_x) + abs(s.robot_y - d.robot_y) <= itrs - 1
+    # what entered the buffer: every relabelled goal is a deepest position, and each relabelled instance that expanded anything
+    # below its root popped that deepest node -> a record whose state IS the new goal (solved against it)
+    rb_state, rb_goal, rb_solved = up.rb._cols["state"][:up.rb.size()], up.rb._cols["goal"][:up.rb.size()], up.rb._cols["solved"][:up.rb.size()]
+    deep_rows = {bytes(dom.states_to_rows([d])[0]) for _, dl in calls for d in dl}
+    n_on_goal = int((rb_state == rb_goal).all(axis=1).sum())
+    assert n_on_goal >= len(deep_rows) and np.array_equal(rb_solved, (rb_state == rb_goal).all(axis=1))
+    assert deep_rows <= {bytes(r) for r in rb_goal}
+    # labels of the sampled elements: the reference's formulas against the goals they carry
+    rows, grows = dom.states_to_rows(states), dom.goals_to_rows(goals)
+    solved = L.is_solved("grid", 7, rows, grows)
+    if is_q:
+        acts = np.array([dom.action_index(a) for a in data[2]])
+        st_n = dom.rows_to_states(L.next_state("grid", 7, rows, acts))
+        q = np.array(pfns.heurq(st_n, goals, [dom.get_actions_fixed()] * len(st_n), [None] * len(st_n)))
+        want = np.where(solved, 0.0, 1.0 + q.min(axis=1))
+    else:
+        children = dom.rows_to_states(L.expand("grid", 7, rows))
+        h = np.array(pfns.heurv(children, [g for g in goals for _ in range(4)], [None] * len(children))).reshape(len(rows), 4)
+        want = np.where(solved, 0.0, 1.0 + h.min(axis=1))
+    np.testing.assert_allclose(labels, want, rtol=0, atol=2e-4)
+    assert solved.sum() > 0 and (labels[solved] == 0.0).all()
+    # one expansion per instance: nothing below the root has children, the relabelled goal is the start position itself
+    calls.clear()
+    pathfind.reset()
+    up1 = watch(cls(dom, pathfind, 1, rb_size=1000))
+    d1 = up1.get_instance_data([12] * 10 + [0] * 3)
+    assert len(calls) == 1 and len(d1[0]) == 13
+    assert all(s == d for s, d in zip(*calls[0])) and len(calls[0][0]) >= 9
+    on_goal = (dom.states_to_rows(d1[0]) == dom.goals_to_rows(d1[1])).all(axis=1)
+    assert on_goal.all() and (np.asarray(d1[-1]) == 0.0).all()        # every record is its instance's root = its (new) goal
+    dom.sample_goal_from_state = orig
+    pathfind.close()
+    cube, cname = get_domain_from_arg("cube3")
+    pf_c, _ = get_path_fns_nnet_par_dict(cube, cname, ["heurv,resnet_fc.200H_2B_bn"])
+    pathfind_c, _, _ = get_pathfind_from_arg(cube, pf_c, "graph.1B_1.0W")
+    with pytest.raises(TypeError, match="GoalSampleableFromState"):
+        UpdateHeurVRLHER(cube, pathfind_c, 3, rb_size=10)
+    assert UpdateHeurVRLKeepGoal(cube, pathfind_c, 3, rb_size=10).her is False
+    pathfind_c.close()

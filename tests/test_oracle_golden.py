@@ -254,6 +254,43 @@ def test_bellman_backups_match_reference(tag):
     assert [i.finished() for i in insts] == c["finished"].tolist()
 
 
+@pytest.mark.parametrize("tag", gu.her_tags())
+def test_her_deepest_nodes_and_relabelled_data_match_reference(tag):
+    """SURVEY 8f.1, hindsight relabelling: UpdateHER._get_her_goals / _get_her_node_data / _get_her_edge_data
+    (base/updater.py:485-583) run by the unmodified reference (tools/gen_golden.py gen_her): which instances keep their goal, the
+    deepest node with children of every other one, and -- grid, the in-scope domain that can sample a goal from a state -- the
+    relabelled goals, the popped nodes / edges regrouped per instance and is_solved against the new goals."""
+    c = gu.her_case(tag)
+    name, dim = gu.parse_domain(str(c["cfg"][0]))
+    b, w = gu.parse_pathfind(str(c["cfg"][1]))
+    is_q = str(c["cfg"][2]) == "q"
+    dom = OracleDomain(name, dim)
+    srch = OracleSearch(dom, make_pseudo_q_fine(dom.num_actions) if is_q else pseudo_v_fine, is_q, b, w)
+    insts = srch.add_instances(c["states"], c["goals"])
+    for _ in range(int(c["cfg"][3])):
+        srch.step()
+    keep = [k for k, i in enumerate(insts) if i.finished() and i.has_soln()]
+    relabel = [k for k, i in enumerate(insts) if not (i.finished() and i.has_soln())]
+    assert keep + relabel == c["order"].tolist() and len(keep) == int(c["n_keep"])
+    deepest = np.stack([insts[k].deepest_with_children()[0] for k in relabel]) if relabel else np.zeros((0, dom.state_len), np.uint8)
+    assert np.array_equal(deepest, c["deepest"])
+    if "goals_her" not in c:
+        return
+    goals_her = np.concatenate([c["goals"][keep], deepest])          # Grid.sample_goal_from_state: the goal IS the robot position
+    assert np.array_equal(goals_her, c["goals_her"])
+    inst_of = np.concatenate([x[2] for x in srch.backup_log])
+    st_all = np.concatenate([x[0] for x in srch.backup_log])
+    idx = np.concatenate([np.flatnonzero(inst_of == k) for k in keep + relabel])
+    g_of = {k: goals_her[j] for j, k in enumerate(keep + relabel)}
+    grows = np.stack([g_of[int(k)] for k in inst_of[idx]])
+    assert np.array_equal(st_all[idx], c["her_states"]) and np.array_equal(grows, c["her_goals"])
+    assert np.array_equal(dom.is_solved(st_all[idx], grows), c["her_solved"])
+    if is_q:
+        acts = np.concatenate([x[3] for x in srch.backup_log])[idx]
+        assert np.array_equal(acts, c["her_acts"])
+        assert np.array_equal(dom.next_state(st_all[idx], acts), c["her_next"])
+
+
 VI_NETS = {"v_cube3_net": "cube3v", "v_np4_net": "np4v", "v_grid7_net": "gridv", "q_cube3_net": "cube3q", "q_grid7_net": "gridq"}
 
 

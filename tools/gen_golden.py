@@ -659,8 +659,86 @@ def gen_vi() -> None:
     print("vi.npz", len(out), "arrays")
 
 
+def gen_her() -> None:
+    """her.npz (hindsight experience replay): UpdateHER._get_her_goals / _get_her_node_data / _get_her_edge_data
+    (deepxube/base/updater.py:485-583) run by the UNMODIFIED reference on its own searches.  The deepest-node rule is domain-agnostic,
+    so it is also recorded for cube3 / npuzzle by handing the method a domain whose sample_goal_from_state returns the deepest states
+    themselves; grid uses the reference's own Grid.sample_goal_from_state."""
+    from deepxube.base.updater import UpdateHER
+    from deepxube.utils.timing_utils import Times
+    out = {}
+
+    class _Stub:
+        pass
+
+    def add(tag, domain_str, pathfind_str, is_q, steps_l, max_steps):
+        seed_all(zlib.crc32(tag.encode()) % 1000)
+        domain, dname = get_domain_from_arg(domain_str)
+        states, goals = domain.sample_problem_instances(list(steps_l))
+        pfns = wrap_q(make_pseudo_q_fine(domain.get_num_acts())) if is_q else wrap_v(pseudo_v_fine)
+        pathfind, name, _ = get_pathfind_from_arg(domain, pfns, pathfind_str)
+        insts = pathfind.make_instances(states, goals, None, True)
+        pathfind.add_instances(insts)
+        steps = 0
+        while (not all(i.finished() for i in insts)) and steps < max_steps:
+            pathfind.step()
+            steps += 1
+        stub = _Stub()
+        captured = {}
+
+        class _Dom:
+            def sample_goal_from_state(self, starts, deepest):
+                captured["starts"], captured["deepest"] = starts, deepest
+                if hasattr(domain, "sample_goal_from_state"):
+                    try:
+                        return domain.sample_goal_from_state(starts, deepest)
+                    except Exception:
+                        pass
+                return list(deepest)
+
+            def is_solved(self, st, gl):
+                return domain.is_solved(st, gl)
+
+        stub.domain = _Dom()
+        order_in = list(insts)
+        insts_her, goals_her = UpdateHER._get_her_goals(stub, order_in, Times())
+        order = [order_in.index(i) for i in insts_her]
+        n_keep = sum(1 for i in insts if i.finished() and i.has_soln())
+        out[tag + "/cfg"] = np.array([domain_str, pathfind_str, "q" if is_q else "v", str(steps)])
+        out[tag + "/states"] = states_np(states)
+        out[tag + "/goals"] = goals_np(goals)
+        out[tag + "/order"] = np.array(order, np.int32)                       # goal-keeping instances first, then the relabelled ones
+        out[tag + "/n_keep"] = np.array(n_keep)
+        deepest = captured.get("deepest", [])
+        out[tag + "/deepest"] = states_np(deepest) if deepest else np.zeros((0, states_np(states).shape[1]), np.uint8)
+        if domain_str.startswith("grid"):
+            out[tag + "/goals_her"] = goals_np(goals_her)
+            if is_q:
+                st, gl, ac, _, sol, tcs, nxt = UpdateHER._get_her_edge_data(stub, insts_her, goals_her, Times())
+                out[tag + "/her_acts"] = np.array([a.action for a in ac], np.int32)
+                out[tag + "/her_next"] = states_np(nxt)
+                assert all(t == 1.0 for t in tcs)
+            else:
+                st, gl, _, sol = UpdateHER._get_her_node_data(stub, insts_her, goals_her, Times())
+            out[tag + "/her_states"] = states_np(st)
+            out[tag + "/her_goals"] = goals_np(gl)
+            out[tag + "/her_solved"] = np.array(sol, bool)
+        print(tag, name, "steps", steps, "keep", n_keep, "relabel", len(deepest), "finished", [int(i.finished()) for i in insts])
+
+    add("grid7_v", "grid.7d", "graph.2B_1.0W", False, [0, 3, 6, 9, 12, 2, 8, 11], 3)
+    add("grid7_v_long", "grid.7d", "graph.1B_0.8W", False, [4, 10, 12, 12, 7, 9], 5)
+    add("grid7_q", "grid.7d", "graph.2B_1.0W", True, [0, 3, 6, 9, 12, 2, 8, 11], 4)
+    add("cube3_v", "cube3", "graph.6B_0.6W", False, [1, 2, 30, 40, 3, 25], 6)
+    add("np4_v", "npuzzle.4", "graph.5B_0.8W", False, [2, 40, 60, 1, 50], 7)
+    add("cube3_q", "cube3", "graph.8B_0.6W", True, [1, 30, 40, 2], 6)
+    np.savez_compressed(os.path.join(OUT, "her.npz"), **out)
+    print("her.npz", len(out), "arrays")
+
+
 if __name__ == "__main__":
-    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam", "backup", "vi"]
+    which = sys.argv[1:] or ["domains", "nnet", "kat", "traces", "lightsout", "qin", "beam", "backup", "vi", "her"]
+    if "her" in which:
+        gen_her()
     if "vi" in which:
         gen_vi()
     if "backup" in which:

@@ -313,6 +313,7 @@ struct SortBufs {
 // Every DX_YOUNG_CAP / sort_bound iterations the host schedules a compaction (main <- merge(main, young); the existing merge
 // kernels).  Order is unchanged: everything in the main run was pushed before everything in the young run, which was pushed
 // before the batch, and every merge takes the older run first on ties -- the reference heap's (f, push count) order.
+#define YT_MAX_INST_HOST 256                   // instance slots an engine with a two-run OPEN may have (= YT_MAX_INST, k_open.cu)
 #define DX_YOUNG_CAP 6144                      // entries the young runs (all instances) may hold after an iteration
 #define DX_YOUNG_BUF (DX_YOUNG_CAP + 2048)     // ... plus one pushed batch (DX_SMALL_SORT)
 struct YoungBufs {
@@ -321,6 +322,15 @@ struct YoungBufs {
     uint32_t* off[2];              // [I + 1] per-instance offsets (packed)
     uint32_t* head[2];             // [I] entries of the run already popped
     uint32_t* m_head;              // [I] entries of the MAIN run already popped
+    // big batches (dx_launch_young_iter: the same two runs handled by grid-wide merges, engines with <= 256 instance slots)
+    uint32_t* ka;                  // [I] pops taken from the main run this iteration
+    uint32_t* kp;                  // [I] ... and from the merged young run
+    uint32_t* mh_old;              // [I] m_head before this iteration's pops
+    uint32_t* tile_off1;           // [I + 1] merge tiles of (young remainder + batch)
+    uint32_t* tile_off2;           // [I + 1] merge tiles of the popped lists
+    uint32_t* zeros;               // [I] k = 0: the first merge pops nothing
+    uint32_t* n_tiles;             // [2] tile counts of the two merges
+    uint32_t cap;                  // entries a young buffer holds
 };
 
 struct MlpBufs {
@@ -450,6 +460,14 @@ int dx_launch_small_tail_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const
                            uint32_t* pop_off_next, const unsigned long long* m_key, const uint32_t* m_val, const uint32_t* m_off,
                            const YoungBufs& yb, int p, int A, uint32_t max_pop, const float* node_g, const float* node_h,
                            const uint32_t* new_inst, uint32_t* popped_next, uint32_t* popped_inst_next, int gen_mode);
+// One iteration's OPEN side with two runs, grid-wide (after the batch is sorted): young <- merge(young remainder, batch); split of
+// the k pops between main-run head and young run; popped list <- merge of the two prefixes.  push_mult / child_mult as dx_launch_plan.
+int dx_launch_young_plan_b(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* m_off, const YoungBufs& yb, int p, int child_mult, int push_mult,
+                           uint32_t max_pop);
+int dx_launch_young_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const SortBufs& sb, const unsigned long long* m_key,
+                         const uint32_t* m_val, const uint32_t* m_off, const YoungBufs& yb, int p, uint32_t* popped_next,
+                         uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_pop);
 int dx_launch_young_compact(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const SortBufs& sb, const YoungBufs& yb, int p,
                             const unsigned long long* open_key_cur, const uint32_t* open_val_cur, const uint32_t* open_off_cur,
                             unsigned long long* open_key_next, uint32_t* open_val_next, uint32_t* open_off_next,

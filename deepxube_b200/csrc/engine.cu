@@ -280,8 +280,18 @@ struct dx_engine {
     YoungBufs young{};
     bool young_enabled = true;      // DXB200_YOUNG=0 disables
     bool young_active = false;      // decided when the first instances arrive after a reset; left (flushed) when the batch outgrows it
-    bool graph_young = false;       // the captured graphs were built for the young-run tail
+    bool young_big = false;         // ... handled by the grid-wide merges (dx_launch_young_iter) instead of the one-block tail
+    int graph_young = 0;            // OPEN structure the captured graphs were built for: 0 one run, 1 young (one block), 2 young (grid-wide)
     long long y_bound = 0;          // upper bound of the entries in the young runs (host-side: compaction schedule)
+    long long m_bound = 0;          // upper bound of the entries in the main runs (everything compacted so far)
+    long long young_cap = 0;        // entries a young buffer holds (>= DX_YOUNG_BUF); big-batch two-run OPEN needs >= 4 * max_sort
+    // DXB200_YOUNG_BIG: 0 never, 1 (default) graph_q only, 2 graph_v too.  Q* pushes A edges per kept node and pops one per batch slot, so
+    // its runs grow by ~(A - 1) x batch entries per iteration and rewriting them dominates the OPEN side after a few iterations
+    // (cube3, B = 10 000: 12 % of the step with 25 M entries).  A* pushes what survives the CLOSED filter: on cube3 / npuzzle the runs
+    // stay within a few batches for tens of iterations and the five extra launches cost more than the shorter merge saves
+    // (measured: npuzzle.5 B = 1000 x 64 -1.4 %, cube3 B = 10 000 x 8 +-0).
+    int young_big_enabled = 1;
+    int young_every = 0;            // DXB200_YOUNG_EVERY=n: compact the big-batch young runs every n iterations (0: the cost model)
     bool pdl = true;                // small-batch graphs: programmatic dependent launches (DXB200_PDL=0 disables)
     bool halt_flag = false;         // the step being launched / captured belongs to dx_run: k_end_iter may raise DX_DEVERR_DONE
     float last_run_ms = 0.f;
@@ -452,7 +462,9 @@ static int reset_state(dx_engine* e) {
         DX_CUDA(cudaStreamSynchronize(e->stream));
     }
     e->young_active = false;
+    e->young_big = false;
     e->y_bound = 0;
+    e->m_bound = 0;
     e->n_inst = 0;
     e->parity = 0;
     e->pending = false;
@@ -498,6 +510,8 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (const char* pe = getenv("DXB200_POLL_EVERY")) e->poll_every = std::max(1, atoi(pe));
     if (const char* pd = getenv("DXB200_PDL")) e->pdl = !(pd[0] == '0');
     if (const char* yg = getenv("DXB200_YOUNG")) e->young_enabled = !(yg[0] == '0');
+    if (const char* yg = getenv("DXB200_YOUNG_BIG")) e->young_big_enabled = std::max(0, std::min(2, atoi(yg)));
+    if (const char* yg = getenv("DXB200_YOUNG_EVERY")) e->young_every = std::max(0, atoi(yg));
     e->A = e->dom.A; e->SP = e->dom.SP; e->S = e->dom.S;
     e->max_inst = cfg->max_instances;
     e->max_nodes = (uint32_t)cfg->max_nodes;
@@ -558,7 +572,10 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     cudaMemset(e->sort.status, 0, ((size_t)256 * e->sort.max_tiles + 256) * sizeof(unsigned long long));
     cudaMemset(e->sort.tickets, 0, (DX_NUM_DIGITS + 4) * sizeof(uint32_t));
     {
-        const size_t mt = (size_t)dx_div_up((long long)e->max_open + std::max<long long>(e->max_sort, DX_YOUNG_BUF), DX_SORT_TILE) + e->max_inst + 8;
+        // young-run capacity: a dozen pushed batches, never more than the main runs may hold
+        e->young_cap = std::max<long long>(DX_YOUNG_BUF, std::min<long long>((long long)e->max_open, 12ll * e->max_sort));
+        const size_t mt = (size_t)dx_div_up((long long)e->max_open + std::max<long long>(e->max_sort, e->young_cap), DX_SORT_TILE) + e->max_inst + 8 +
+                          YT_MAX_INST_HOST;
         A_(e->sort.part_a, mt); A_(e->sort.part_i, mt);
     }
     e->sort.onesweep = 1;
@@ -567,12 +584,19 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     A_(e->ia.batch, I); A_(e->ia.weight, I); A_(e->ia.lb, I); A_(e->ia.ub_key, I); A_(e->ia.goal_node, I); A_(e->ia.itr, I);
     A_(e->ia.gen, I); A_(e->ia.active, I); A_(e->ia.pop_seq_base, I); A_(e->ia.n_open, I); A_(e->ia.m_new, I); A_(e->ia.k_pop, I);
     A_(e->ia.batch_off, I + 1); A_(e->ia.tile_off, I + 1); A_(e->ia.f_first, I); A_(e->ia.goals, I * e->SP); A_(e->ia.root, I);
-    if (!e->is_q && !e->is_beam && I <= 256) {      // young-run OPEN (small-batch regime); 200 KB
-        for (int p = 0; p < 2; ++p) {
-            A_(e->young.key[p], (size_t)DX_YOUNG_BUF); A_(e->young.val[p], (size_t)DX_YOUNG_BUF);
-            A_(e->young.off[p], I + 1); A_(e->young.head[p], I);
+    if (!e->is_beam && I <= YT_MAX_INST_HOST) {      // two-run OPEN: small-batch A* (one block, 200 KB) and big batches (A*, Q*)
+        const bool big_capable = e->young_cap >= 4ll * e->max_sort && e->max_sort > DX_SMALL_SORT;
+        if (!big_capable) e->young_cap = DX_YOUNG_BUF;
+        if (big_capable || !e->is_q) {
+            for (int p = 0; p < 2; ++p) {
+                A_(e->young.key[p], (size_t)e->young_cap); A_(e->young.val[p], (size_t)e->young_cap);
+                A_(e->young.off[p], I + 1); A_(e->young.head[p], I);
+            }
+            A_(e->young.m_head, I);
+            A_(e->young.ka, I); A_(e->young.kp, I); A_(e->young.mh_old, I); A_(e->young.zeros, I);
+            A_(e->young.tile_off1, I + 1); A_(e->young.tile_off2, I + 1); A_(e->young.n_tiles, 2);
+            e->young.cap = (uint32_t)e->young_cap;
         }
-        A_(e->young.m_head, I);
     }
     A_(e->d_vals, std::max<size_t>((size_t)e->max_sort, P * e->A) + I * e->A);
 #undef A_
@@ -711,27 +735,46 @@ __global__ void k_young_copyback(const Ctl* __restrict__ ctl, const unsigned lon
                                  uint32_t* __restrict__ off_dst) {
     if (ctl->error) return;
     const uint32_t n = ctl->open_total, I = ctl->n_inst;
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t < n; t += gridDim.x * blockDim.x) { key_dst[t] = key_src[t]; val_dst[t] = val_src[t]; }
-    for (uint32_t t = blockIdx.x * blockDim.x + threadIdx.x; t <= I; t += gridDim.x * blockDim.x) off_dst[t] = off_src[t];
+    const uint32_t tid = blockIdx.x * blockDim.x + threadIdx.x, nth = gridDim.x * blockDim.x;
+    // 16-byte copies (the buffers are cudaMalloc-aligned): two keys / four values per access, then the odd tail
+    const uint4* __restrict__ k4 = reinterpret_cast<const uint4*>(key_src);
+    const uint4* __restrict__ v4 = reinterpret_cast<const uint4*>(val_src);
+    uint4* __restrict__ dk4 = reinterpret_cast<uint4*>(key_dst);
+    uint4* __restrict__ dv4 = reinterpret_cast<uint4*>(val_dst);
+    for (uint32_t t = tid; t < n / 2; t += nth) dk4[t] = k4[t];
+    for (uint32_t t = tid; t < n / 4; t += nth) dv4[t] = v4[t];
+    if (tid == 0 && (n & 1)) key_dst[n - 1] = key_src[n - 1];
+    if (tid < (n & 3)) val_dst[(n & ~3u) + tid] = val_src[(n & ~3u) + tid];
+    for (uint32_t t = tid; t <= I; t += nth) off_dst[t] = off_src[t];
 }
 
 // main run <- merge(main run remainder, young runs); the main run's home is open_*[0] (merged into [1], copied back)
 static int young_compact(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity;
-    const int max_tiles = dx_div_up((long long)e->max_open + DX_YOUNG_BUF, DX_SORT_TILE) + e->max_inst;
+    const int max_tiles = dx_div_up((long long)e->max_open + e->young_cap, DX_SORT_TILE) + e->max_inst;
     e->launches += dx_launch_young_compact(s, e->d_ctl, e->ia, e->sort, e->young, p, e->open_key[0], e->open_val[0], e->open_off[0],
                                            e->open_key[1], e->open_val[1], e->open_off[1], e->popped[p ^ 1], e->popped_inst[p ^ 1],
                                            e->pop_off[p], max_tiles, (uint32_t)e->max_open);
-    k_young_copyback<<<148 * 2, 256, 0, s>>>(e->d_ctl, e->open_key[1], e->open_val[1], e->open_off[1], e->open_key[0], e->open_val[0], e->open_off[0]);
+    k_young_copyback<<<148 * 8, 256, 0, s>>>(e->d_ctl, e->open_key[1], e->open_val[1], e->open_off[1], e->open_key[0], e->open_val[0], e->open_off[0]);
     e->launches += 1;
+    e->m_bound += e->y_bound;
     e->y_bound = 0;
     return DX_OK;
 }
-// before an iteration is launched: the merged young runs (young + pushed batch) must fit the block's buffer
+// before an iteration is launched: the merged young runs (young + pushed batch) must fit the block's buffer (one-block tail) /
+// the young buffers (grid-wide merges), and the young runs are folded into the main runs when rewriting them every iteration
+// starts to cost more than the compaction saves: per iteration the young merge moves ~ y entries and a compaction every n
+// iterations (y = n * b) moves (M + y) / n, least at y = sqrt(2 M b) for main runs of M entries and pushes of b per iteration
 static int young_before_step(dx_engine* e) {
     if (!e->young_active) return DX_OK;
-    if (e->y_bound + e->sort_bound > DX_YOUNG_BUF) DX_TRY(young_compact(e));
+    const long long b = std::max<long long>(e->sort_bound, 1);
+    long long limit = DX_YOUNG_BUF;
+    if (e->young_big) {
+        const long long best = (long long)std::sqrt(2.0 * (double)e->m_bound * (double)b);
+        limit = std::min<long long>(e->young_cap, (e->young_every > 0 ? (long long)e->young_every * b : std::max<long long>(4 * b, best)) + b);
+    }
+    if (e->y_bound + e->sort_bound > limit) DX_TRY(young_compact(e));
     e->y_bound += e->sort_bound;
     return DX_OK;
 }
@@ -740,10 +783,11 @@ static int young_flush(dx_engine* e) {
     if (!e->young_active) return DX_OK;
     DX_TRY(young_compact(e));
     if (e->parity != 0)
-        k_young_copyback<<<148 * 2, 256, 0, e->stream>>>(e->d_ctl, e->open_key[0], e->open_val[0], e->open_off[0], e->open_key[1], e->open_val[1],
+        k_young_copyback<<<148 * 8, 256, 0, e->stream>>>(e->d_ctl, e->open_key[0], e->open_val[0], e->open_off[0], e->open_key[1], e->open_val[1],
                                                           e->open_off[1]);
     DX_CUDA(cudaStreamSynchronize(e->stream));
     e->young_active = false;
+    e->young_big = false;
     return DX_OK;
 }
 
@@ -781,14 +825,21 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
     }
     e->sort_bound = bsum * e->A;             // no iteration can push more entries than every instance's full batch expanded
     {   // young-run OPEN: entered with the first instances after a reset, left for good when the batch outgrows the small regime
-        const bool want = e->young_enabled && e->young.m_head != nullptr && small_fused_v(e);
+        const bool have = e->young_enabled && e->young.m_head != nullptr && e->hda_world < 1;
+        const bool want_small = have && small_fused_v(e);
+        const bool want_big = have && e->young_big_enabled >= (e->is_q ? 1 : 2) && !small_sort(e) && e->young_cap >= 4 * e->sort_bound &&
+                              e->young_cap > DX_YOUNG_BUF;
         if (e->n_inst == 0) {
-            e->young_active = want;
+            e->young_active = want_small || want_big;
+            e->young_big = want_big;
             e->y_bound = 0;
-        } else if (e->young_active && !want) {
+            e->m_bound = 0;
+        } else if (e->young_active && !(want_small || want_big)) {
             DX_TRY(young_flush(e));
             DX_TRY(sync_ctl(e));
             c = *e->h_ctl;                   // (the compaction rewrote open_total / young_total)
+        } else if (e->young_active) {
+            e->young_big = want_big;         // same two runs, other kernels (young_before_step compacts first if the block's buffer is smaller)
         }
     }
     const int SP = e->SP, S = e->S, I0 = e->n_inst, p = e->parity;
@@ -940,7 +991,7 @@ static int step_v_b(dx_engine* e) {
     if (e->eval_all) DX_TRY(step_v_filter(e));
     stage_begin(e, ST_SORT);
     const int beam = e->is_beam ? 1 : 0;
-    if (e->young_active) {                 // the whole OPEN side of the iteration in one block (k_small_tail_v)
+    if (e->young_active && !e->young_big) {                 // the whole OPEN side of the iteration in one block (k_small_tail_v)
         e->launches += dx_launch_small_tail_v(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_key[0],
                                               e->open_val[0], e->open_off[0], e->young, p, e->A, (uint32_t)e->max_pop, e->node_g, e->node_h,
                                               e->new_inst, e->popped[q], e->popped_inst[q], e->halt_flag ? DX_END_HALT : 0);
@@ -953,16 +1004,25 @@ static int step_v_b(dx_engine* e) {
                                               e->open_off[q], e->A, e->max_pop, e->max_open, e->node_g, e->node_h, e->new_inst,
                                               e->sort);
     } else {
-        e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
-                                      e->open_off[q], e->A, 1, e->max_pop, e->max_open, 0, beam);
+        if (e->young_big)
+            e->launches += dx_launch_young_plan_b(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[0],
+                                                  e->young, p, e->A, 1, e->max_pop);
+        else
+            e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                          e->open_off[q], e->A, 1, e->max_pop, e->max_open, 0, beam);
         e->launches += dx_launch_make_keys(s, e->d_ctl, e->ia, e->node_g, e->node_h, e->new_inst, e->sort, e->max_sort, beam);
         e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
     }
     stage_end(e);
     stage_begin(e, ST_MERGE);
-    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
-    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
-                                   e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
+    if (e->young_big) {
+        e->launches += dx_launch_young_iter(s, e->d_ctl, e->ia, e->sort, e->open_key[0], e->open_val[0], e->open_off[0], e->young, p,
+                                            e->popped[q], e->popped_inst[q], e->pop_off[q], (int)e->max_pop);
+    } else {
+        const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+        e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                       e->open_val[q], e->open_off[q], e->popped[q], e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
+    }
     stage_end(e);
     stage_begin(e, ST_BOOK);
     e->launches += dx_launch_end_iter(s, e->d_ctl, e->ia, e->pop_off[p], e->pop_off[q], e->A, (beam ? 2 : 0) | (e->halt_flag ? DX_END_HALT : 0));
@@ -1014,8 +1074,12 @@ static int step_q_a(dx_engine* e) {
                                                e->max_children);
     stage_end(e);
     stage_begin(e, ST_SORT);
-    e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
-                                  e->open_off[q], 1, e->A, e->max_pop, e->max_open, 0, beam);
+    if (e->young_big)
+        e->launches += dx_launch_young_plan_b(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[0],
+                                              e->young, p, 1, e->A, e->max_pop);
+    else
+        e->launches += dx_launch_plan(s, e->d_ctl, e->ia, e->child_prefix, e->pop_off[p], e->pop_off[q], e->open_off[p],
+                                      e->open_off[q], 1, e->A, e->max_pop, e->max_open, 0, beam);
     e->launches += dx_launch_make_keys_q(s, e->d_ctl, e->ia, e->node_g, e->node_q, e->popped[p], e->popped_inst[p],
                                          e->child_flags, e->child_prefix, e->sort, e->A, e->max_pop, beam);
     e->launches += dx_launch_sort(s, e->d_ctl, e->sort, e->scan, e->max_sort, small_sort(e));
@@ -1029,9 +1093,14 @@ static int step_q_pop(dx_engine* e) {
     const int p = e->parity, q = p ^ 1;
     const int beam = e->is_beam ? 1 : 0;
     stage_begin(e, ST_MERGE);
-    const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
-    e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
-                                   e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
+    if (e->young_big) {
+        e->launches += dx_launch_young_iter(s, e->d_ctl, e->ia, e->sort, e->open_key[0], e->open_val[0], e->open_off[0], e->young, p,
+                                            e->edge_tmp, e->popped_inst[q], e->pop_off[q], (int)e->max_pop);
+    } else {
+        const int max_tiles = dx_div_up((long long)e->max_open + e->max_sort, DX_SORT_TILE) + e->max_inst;
+        e->launches += dx_launch_merge(s, e->d_ctl, e->ia, e->sort, e->open_key[p], e->open_val[p], e->open_off[p], e->open_key[q],
+                                       e->open_val[q], e->open_off[q], e->edge_tmp, e->popped_inst[q], e->pop_off[q], max_tiles, beam ? 0 : 1);
+    }
     dx_launch(k_after_merge_q, 1, 1, 0, s, e->d_ctl, (const uint32_t*)e->pop_off[q], (uint32_t)e->max_nodes);
     e->launches += 1;
     e->launches += dx_launch_expand_edges(s, e->dom, e->d_ctl, e->edge_tmp, e->popped[q], e->node_state, e->node_g,
@@ -1071,7 +1140,7 @@ static int full_step(dx_engine* e) {
 
 static int build_step_graphs(dx_engine* e, bool prof) {
     e->graph_small = small_sort(e);
-    e->graph_young = e->young_active;
+    e->graph_young = e->young_active ? (e->young_big ? 2 : 1) : 0;
     const int p0 = e->parity;
     const long long l0 = e->launches;
     for (int k = 0; k < 2; ++k) {
@@ -1111,7 +1180,7 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
     const bool use_graph = e->use_graphs, prof = e->profiling != 0;
-    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != e->young_active))
+    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != (e->young_active ? (e->young_big ? 2 : 1) : 0)))
         drop_graphs(e);                              // captured with the other sort / OPEN structure
     if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
     if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level

@@ -659,10 +659,11 @@ __device__ __forceinline__ uint32_t merge_path_warp(const unsigned long long* __
 __global__ void __launch_bounds__(OPEN_THREADS)
 k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned long long* __restrict__ open_key_cur,
                   const uint32_t* __restrict__ open_off_cur, uint32_t* __restrict__ part_a, uint32_t* __restrict__ part_i,
-                  const uint32_t* __restrict__ a_head, const unsigned long long* __restrict__ b_keys) {
+                  const uint32_t* __restrict__ a_head, const unsigned long long* __restrict__ b_keys,
+                  const uint32_t* __restrict__ a_len, const uint32_t* __restrict__ n_tiles_ptr) {
     dx_pdl_prologue();
     if (ctl->error) return;
-    const uint32_t n_tiles = ctl->n_tiles;
+    const uint32_t n_tiles = n_tiles_ptr ? *n_tiles_ptr : ctl->n_tiles;
     const int I = ctl->n_inst;
     // (young-run compaction: the B run is the young run, and the A run starts behind its consumed prefix a_head[i])
     const unsigned long long* __restrict__ bkeys = b_keys ? b_keys : sb.key[ctl->sort_final];
@@ -675,7 +676,7 @@ k_merge_partition(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const
         }
         const int i = lo;
         const uint32_t ah = a_head ? a_head[i] : 0u;
-        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
+        const uint32_t na = a_len ? a_len[i] : open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
         const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE;
         const uint32_t part = merge_path_warp(open_key_cur + open_off_cur[i] + ah, na, bkeys + ia.batch_off[i], nb, d0);
         if ((threadIdx.x & 31) == 0) { part_a[T] = part; part_i[T] = (uint32_t)i; }
@@ -689,20 +690,20 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
         const uint32_t* __restrict__ open_off_next, uint32_t* __restrict__ popped_next, uint32_t* __restrict__ popped_inst_next,
         const uint32_t* __restrict__ pop_off_next, int keep_open, const uint32_t* __restrict__ part_a,
         const uint32_t* __restrict__ part_i, const uint32_t* __restrict__ a_head, const unsigned long long* __restrict__ b_keys,
-        const uint32_t* __restrict__ b_vals) {
+        const uint32_t* __restrict__ b_vals, const uint32_t* __restrict__ a_len, const uint32_t* __restrict__ n_tiles_ptr) {
     __shared__ unsigned long long s_key[DX_SORT_TILE];
     __shared__ uint32_t s_val[DX_SORT_TILE];
     __shared__ uint32_t s_part[4];   // a0, a1, inst
     dx_pdl_prologue();
     if (ctl->error) return;
-    const uint32_t n_tiles = ctl->n_tiles;
+    const uint32_t n_tiles = n_tiles_ptr ? *n_tiles_ptr : ctl->n_tiles;
     const unsigned long long* __restrict__ bkeys = b_keys ? b_keys : sb.key[ctl->sort_final];
     const uint32_t* __restrict__ bvals = b_keys ? b_vals : sb.val[ctl->sort_final];
     for (uint32_t T = blockIdx.x; T < n_tiles; T += gridDim.x) {
         __syncthreads();
         if (threadIdx.x == 0) {
             const uint32_t i = part_i[T];
-            const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - (a_head ? a_head[i] : 0u);
+            const uint32_t na = a_len ? a_len[i] : open_off_cur[i + 1] - open_off_cur[i] - (a_head ? a_head[i] : 0u);
             s_part[0] = part_a[T];
             s_part[1] = (T + 1 < ia.tile_off[i + 1]) ? part_a[T + 1] : na;     // the instance's last tile ends at the end of its run
             s_part[2] = i;
@@ -710,7 +711,7 @@ k_merge(const Ctl* __restrict__ ctl, InstArrays ia, SortBufs sb, const unsigned 
         __syncthreads();
         const int i = s_part[2];
         const uint32_t ah = a_head ? a_head[i] : 0u;
-        const uint32_t na = open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
+        const uint32_t na = a_len ? a_len[i] : open_off_cur[i + 1] - open_off_cur[i] - ah, nb = ia.m_new[i];
         const uint32_t d0 = (T - ia.tile_off[i]) * DX_SORT_TILE, d1 = min(d0 + DX_SORT_TILE, na + nb);
         const uint32_t a0 = s_part[0], a1 = s_part[1], b0 = d0 - a0, b1 = d1 - a1;
         const uint32_t ca = a1 - a0, cb = b1 - b0;
@@ -770,10 +771,11 @@ int dx_launch_merge(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, const 
                     uint32_t* popped_next, uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_tiles, int keep_open) {
     int blocks = min(max_tiles, 148 * 8);      // 24.5 KB of shared memory and 256 threads per block: 8 blocks per SM
     dx_launch(k_merge_partition, min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur,
-              open_off_cur, sb.part_a, sb.part_i, (const uint32_t*)nullptr, (const unsigned long long*)nullptr);
+              open_off_cur, sb.part_a, sb.part_i, (const uint32_t*)nullptr, (const unsigned long long*)nullptr, (const uint32_t*)nullptr,
+              (const uint32_t*)nullptr);
     dx_launch(k_merge, blocks, OPEN_THREADS, 0, s, ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
               open_off_next, popped_next, popped_inst_next, pop_off_next, keep_open, sb.part_a, sb.part_i, (const uint32_t*)nullptr,
-              (const unsigned long long*)nullptr, (const uint32_t*)nullptr);
+              (const unsigned long long*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr, (const uint32_t*)nullptr);
     return 2;
 }
 
@@ -1318,6 +1320,131 @@ int dx_launch_small_tail_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const
     return 1;
 }
 
+// ---------------------------------------------------------------------------------------------
+// Two-run OPEN for BIG batches (engines with <= YT_MAX_INST instance slots): the same state as above (main run consumed through
+// m_head, young run of what was pushed since the last compaction), handled by the grid-wide merge kernels.  k_merge rewrote every
+// instance's whole run each iteration -- O(|OPEN|) traffic for an O(batch) change, 12 % of a cube3 Q* step with a 25 M-entry OPEN;
+// now an iteration moves O(|young| + batch) entries and the main run is only rewritten at the host-scheduled compactions.
+//   k_young_plan_b   per instance: pushed m, remainders nm / ny, k = min(batch, nm + ny + m); offsets of the batch, the merged young
+//                    runs and the popped lists; tile offsets of the two merges                                   (k_plan)
+//   merge 1          young[q] <- merge(young[p] behind its head, sorted batch), nothing popped      (k_merge_partition + k_merge)
+//   k_young_split    a warp per instance: ka = how many of the k smallest of (main-run head, merged young run) are main-run entries
+//                    (main run first on ties: pushed earlier); heads advance by ka / k - ka
+//   merge 2          popped list <- merge(main[m_head .. m_head + ka), young[q][0 .. k - ka))          (k_merge_partition + k_merge)
+__global__ void __launch_bounds__(YT_MAX_INST)
+k_young_plan_b(Ctl* __restrict__ ctl, InstArrays ia, const uint32_t* __restrict__ prefix, const uint32_t* __restrict__ pop_off_cur,
+               uint32_t* __restrict__ pop_off_next, const uint32_t* __restrict__ m_off, YoungBufs yb, int p, int child_mult,
+               int push_mult, uint32_t max_pop) {
+    __shared__ uint32_t s_scan[5][YT_MAX_INST + 1];
+    dx_pdl_prologue();
+    if (ctl->error) return;
+    const int I = (int)ctl->n_inst, i = threadIdx.x, q = p ^ 1;
+    if (I > YT_MAX_INST) { if (i == 0) atomicOr(&ctl->error, DX_DEVERR_POP); return; }
+    uint32_t m = 0, ny = 0, k = 0, yh = 0;
+    if (i < I) {
+        const bool act = ia.active[i] != 0;
+        const uint32_t kept = prefix[pop_off_cur[i + 1] * child_mult] - prefix[pop_off_cur[i] * child_mult];
+        m = act ? kept * (uint32_t)push_mult : 0u;
+        const uint32_t nm = act ? (m_off[i + 1] - m_off[i]) - yb.m_head[i] : 0u;          // (OPEN of a finished instance is dropped)
+        yh = yb.head[p][i];
+        ny = act ? (yb.off[p][i + 1] - yb.off[p][i]) - yh : 0u;
+        const uint32_t t = nm + ny + m;
+        k = act ? min((uint32_t)ia.batch[i], t) : 0u;
+        ia.m_new[i] = m; ia.k_pop[i] = k; ia.n_open[i] = t - k;
+        // merge 1 reads the young remainder through (off[p], head = total - remainder): a dropped run has remainder 0
+        yb.head[p][i] = (yb.off[p][i + 1] - yb.off[p][i]) - ny;
+        yb.zeros[i] = 0;
+    }
+    s_scan[0][i] = m; s_scan[1][i] = ny + m; s_scan[2][i] = k;
+    s_scan[3][i] = (ny + m + DX_SORT_TILE - 1) / DX_SORT_TILE; s_scan[4][i] = (k + DX_SORT_TILE - 1) / DX_SORT_TILE;
+    __syncthreads();
+    if (i < 5) {                                     // five short serial scans (I <= 256), one thread each
+        uint32_t acc = 0;
+        for (int t = 0; t < I; ++t) { const uint32_t v = s_scan[i][t]; s_scan[i][t] = acc; acc += v; }
+        s_scan[i][I] = acc;
+    }
+    __syncthreads();
+    for (int j = i; j <= I; j += YT_MAX_INST) {       // (I + 1 entries: thread 0 also writes the last one when I = 256)
+        ia.batch_off[j] = s_scan[0][j];
+        yb.off[q][j] = s_scan[1][j];
+        pop_off_next[j] = s_scan[2][j];
+        yb.tile_off1[j] = s_scan[3][j];
+        yb.tile_off2[j] = s_scan[4][j];
+    }
+    if (i == 0) {
+        ctl->sort_n = s_scan[0][I];
+        ctl->young_total = s_scan[1][I];
+        yb.n_tiles[0] = s_scan[3][I];
+        yb.n_tiles[1] = s_scan[4][I];
+        uint32_t err = 0;
+        if (s_scan[2][I] > max_pop) err |= DX_DEVERR_POP;
+        if (s_scan[1][I] > yb.cap) err |= DX_DEVERR_OPEN;                        // (the host compacts before this can happen)
+        if (err) atomicOr(&ctl->error, err);
+    }
+}
+
+__global__ void __launch_bounds__(256)
+k_young_split(const Ctl* __restrict__ ctl, InstArrays ia, const unsigned long long* __restrict__ m_key, const uint32_t* __restrict__ m_off,
+              YoungBufs yb, int q) {
+    dx_pdl_prologue();
+    if (ctl->error) return;
+    const int I = (int)ctl->n_inst;
+    for (int i = blockIdx.x * (blockDim.x / 32) + (threadIdx.x >> 5); i < I; i += gridDim.x * (blockDim.x / 32)) {
+        const uint32_t k = ia.k_pop[i], mh = yb.m_head[i];
+        const uint32_t nm = ia.active[i] ? (m_off[i + 1] - m_off[i]) - mh : 0u;
+        const uint32_t nyb = yb.off[q][i + 1] - yb.off[q][i];
+        const uint32_t ka = k ? merge_path_warp(m_key + m_off[i] + mh, min(nm, k), yb.key[q] + yb.off[q][i], min(nyb, k), k) : 0u;
+        if ((threadIdx.x & 31) == 0) {
+            yb.ka[i] = ka; yb.kp[i] = k - ka; yb.mh_old[i] = mh;
+            yb.m_head[i] = mh + ka;
+            yb.head[q][i] = k - ka;
+        }
+    }
+}
+
+int dx_launch_young_plan_b(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const uint32_t* child_prefix, const uint32_t* pop_off_cur,
+                           uint32_t* pop_off_next, const uint32_t* m_off, const YoungBufs& yb, int p, int child_mult, int push_mult,
+                           uint32_t max_pop) {
+    dx_launch(k_young_plan_b, 1, YT_MAX_INST, 0, s, ctl, ia, child_prefix, pop_off_cur, pop_off_next, m_off, yb, p, child_mult, push_mult,
+              max_pop);
+    return 1;
+}
+
+int dx_launch_young_iter(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const SortBufs& sb, const unsigned long long* m_key,
+                         const uint32_t* m_val, const uint32_t* m_off, const YoungBufs& yb, int p, uint32_t* popped_next,
+                         uint32_t* popped_inst_next, const uint32_t* pop_off_next, int max_pop) {
+    const int q = p ^ 1;
+    const unsigned long long* no_keys = nullptr;
+    const uint32_t* no_u32 = nullptr;
+    // merge 1: young[q] <- young[p] remainder + sorted batch; k = 0, so everything lands in the "next run"
+    InstArrays ia1 = ia;
+    ia1.k_pop = yb.zeros;
+    ia1.tile_off = yb.tile_off1;
+    const int tiles1 = dx_div_up((long long)yb.cap, DX_SORT_TILE) + YT_MAX_INST;
+    dx_launch(k_merge_partition, min(dx_div_up(tiles1, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s, (const Ctl*)ctl, ia1, sb,
+              (const unsigned long long*)yb.key[p], (const uint32_t*)yb.off[p], sb.part_a, sb.part_i, (const uint32_t*)yb.head[p], no_keys,
+              no_u32, (const uint32_t*)yb.n_tiles);
+    dx_launch(k_merge, min(tiles1, 148 * 8), OPEN_THREADS, 0, s, (const Ctl*)ctl, ia1, sb, (const unsigned long long*)yb.key[p],
+              (const uint32_t*)yb.val[p], (const uint32_t*)yb.off[p], yb.key[q], yb.val[q], (const uint32_t*)yb.off[q], popped_next,
+              popped_inst_next, pop_off_next, 1, (const uint32_t*)sb.part_a, (const uint32_t*)sb.part_i, (const uint32_t*)yb.head[p], no_keys,
+              no_u32, no_u32, (const uint32_t*)yb.n_tiles);
+    dx_launch(k_young_split, min(dx_div_up(YT_MAX_INST, 8), 32), 256, 0, s, (const Ctl*)ctl, ia, m_key, m_off, yb, q);
+    // merge 2: popped list <- main[mh_old .. mh_old + ka) + young[q][0 .. kp); every output is a pop (r < k)
+    InstArrays ia2 = ia;
+    ia2.m_new = yb.kp;
+    ia2.batch_off = yb.off[q];
+    ia2.tile_off = yb.tile_off2;
+    const int tiles2 = dx_div_up(max_pop, DX_SORT_TILE) + YT_MAX_INST;
+    dx_launch(k_merge_partition, min(dx_div_up(tiles2, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s, (const Ctl*)ctl, ia2, sb, m_key, m_off,
+              sb.part_a, sb.part_i, (const uint32_t*)yb.mh_old, (const unsigned long long*)yb.key[q], (const uint32_t*)yb.ka,
+              (const uint32_t*)(yb.n_tiles + 1));
+    dx_launch(k_merge, min(tiles2, 148 * 8), OPEN_THREADS, 0, s, (const Ctl*)ctl, ia2, sb, m_key, m_val, m_off, yb.key[p], yb.val[p],
+              (const uint32_t*)yb.off[p], popped_next, popped_inst_next, pop_off_next, 0, (const uint32_t*)sb.part_a,
+              (const uint32_t*)sb.part_i, (const uint32_t*)yb.mh_old, (const unsigned long long*)yb.key[q], (const uint32_t*)yb.val[q],
+              (const uint32_t*)yb.ka, (const uint32_t*)(yb.n_tiles + 1));
+    return 5;
+}
+
 // Compaction: main run <- merge(main run remainder, young run remainder) per instance, young runs emptied.  The merge itself is
 // k_merge_partition + k_merge with the young run as the B run (k = 0: nothing is popped).
 __global__ void __launch_bounds__(1024)
@@ -1367,10 +1494,10 @@ int dx_launch_young_compact(cudaStream_t s, Ctl* ctl, const InstArrays& ia, cons
     k_young_plan<<<1, 32, 0, s>>>(ctl, ia, open_off_cur, open_off_next, yb, p, max_open);
     const int blocks = min(max_tiles, 148 * 8);
     k_merge_partition<<<min(dx_div_up(max_tiles, OPEN_THREADS / 32), 148 * 4), OPEN_THREADS, 0, s>>>(
-        ctl, ia, sb, open_key_cur, open_off_cur, sb.part_a, sb.part_i, yb.m_head, yb.key[p]);
+        ctl, ia, sb, open_key_cur, open_off_cur, sb.part_a, sb.part_i, yb.m_head, yb.key[p], nullptr, nullptr);
     k_merge<<<blocks, OPEN_THREADS, 0, s>>>(ctl, ia, sb, open_key_cur, open_val_cur, open_off_cur, open_key_next, open_val_next,
                                             open_off_next, popped_scratch, popped_inst_scratch, pop_off_any, 1, sb.part_a, sb.part_i,
-                                            yb.m_head, yb.key[p], yb.val[p]);
+                                            yb.m_head, yb.key[p], yb.val[p], nullptr, nullptr);
     k_young_finish<<<1, 256, 0, s>>>(ctl, yb);
     return 4;
 }

@@ -355,23 +355,35 @@ def test_hda_capacity_error_reaches_every_rank(device_resident):
 
 # ---------------------------------------------------------------------------------------------------
 # Young-run OPEN of small-batch A* engines (csrc/k_open.cu k_small_tail_v)
-def _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, iters, fn, add_later=None, max_pop=None):
-    """HOST-heuristic engine against the oracle, compared after every iteration (popped nodes, lb / ub / OPEN size / counters)."""
-    orc = OracleSearch(dom, fn, False, batch, weight)
+def _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, iters, fn, add_later=None, max_pop=None, is_q=False, max_nodes=600000,
+                   remove_at=None):
+    """HOST-heuristic engine against the oracle, compared after every iteration (popped nodes, lb / ub / OPEN size / counters).
+    remove_at = (iteration, [slots]): those instances are removed (dx_remove_instances) before that iteration."""
+    orc = OracleSearch(dom, fn, is_q, batch, weight)
     oi = orc.add_instances(st, goals)
-    n_all = len(st) + (len(add_later[1]) if add_later else 0)
-    eng = L.Engine(dname, dim, "graph_v", L.DX_HEUR_HOST, max_instances=n_all, max_pop_total=max_pop or n_all * batch, max_nodes=600000)
+    adds = [] if not add_later else ([add_later] if not isinstance(add_later, list) else add_later)
+    n_all = len(st) + sum(len(a[1]) for a in adds)
+    eng = L.Engine(dname, dim, "graph_q" if is_q else "graph_v", L.DX_HEUR_HOST, max_instances=n_all, max_pop_total=max_pop or n_all * batch,
+                   max_nodes=max_nodes)
     eng.add_instances(st, goals, batch, weight, root_vals=fn(st, goals))
+    gone = set()
     for t in range(iters):
-        if add_later and t == add_later[0]:
-            st2, gl2, b2 = add_later[1], add_later[2], add_later[3]
-            oi += orc.add_instances(st2, gl2, batch_size=b2)
-            eng.add_instances(st2, gl2, b2, weight, root_vals=fn(st2, gl2))
+        for a in adds:
+            if t == a[0]:
+                st2, gl2, b2 = a[1], a[2], a[3]
+                oi += orc.add_instances(st2, gl2, batch_size=b2)
+                eng.add_instances(st2, gl2, b2, weight, root_vals=fn(st2, gl2))
+        if remove_at and t == remove_at[0]:
+            eng.remove_instances(list(remove_at[1]))
+            gone.update(remove_at[1])
+            orc.instances = [o for j, o in enumerate(oi) if j not in gone]     # (the oracle steps its `instances` list)
         orc.step()
         n = eng.step_begin()
         ps, pg = eng.get_pending(n)
-        eng.step_end(fn(ps, pg) if n else np.zeros((0,)))
+        eng.step_end(fn(ps, pg) if n else np.zeros((0, dom.num_actions) if is_q else (0,)))
         for j, (o, s) in enumerate(zip(oi, eng.status())):
+            if j in gone:
+                continue
             assert s.lb == o.lb and s.ub == o.ub and s.num_nodes_generated == o.num_nodes_generated, (t, j, s.lb, o.lb)
             assert bool(s.finished) == o.finished(), (t, j)
             if not s.finished:
@@ -397,6 +409,57 @@ def test_young_run_open_matches_the_oracle_over_many_compactions(dname, dim, n, 
         st, goals = _scrambles(dom, n, 40, 9)
     eng, oi = _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, 40, pseudo_v)
     assert eng.counters().kernel_launches > 0
+    eng.close()
+
+
+@pytest.mark.parametrize("every", ["1", "3", "0"])
+@pytest.mark.parametrize("dname,dim,is_q,n,batch,weight,iters", [
+    ("cube3", 0, False, 3, 300, 0.6, 24),      # 3 x 300 x 12 = 10 800 pushed entries per iteration: the grid-wide kernels
+    ("cube3", 0, True, 4, 700, 0.5, 22),       # Q*: edges in OPEN, 12 pushed per kept node
+    ("npuzzle", 4, False, 40, 30, 0.8, 30),    # many instances, ragged runs, some finish early
+    ("grid", 7, True, 200, 5, 1.0, 14),        # tiny state space: runs empty out, instances finish at different iterations
+])
+def test_two_run_open_of_big_batches_matches_the_oracle(monkeypatch, every, dname, dim, is_q, n, batch, weight, iters):
+    """Big batches keep OPEN as two runs as well (dx_launch_young_iter: young <- merge(young, batch), pop split, popped list <- merge
+    of the two prefixes; compaction every DXB200_YOUNG_EVERY iterations, or by the cost model when 0): every iteration's popped
+    nodes, OPEN sizes, lb / ub and counters are the oracle's, with the tie-heavy pseudo-heuristic."""
+    L = _lib()
+    monkeypatch.setenv("DXB200_YOUNG_EVERY", every)
+    monkeypatch.setenv("DXB200_YOUNG_BIG", "2")             # (graph_v engines use it only on request: see engine.cu)
+    dom = OracleDomain(dname, dim)
+    if dname == "grid":
+        rng = np.random.default_rng(4)
+        st = rng.integers(0, dim, size=(n, 2)).astype(np.uint8)
+        goals = rng.integers(0, dim, size=(n, 2)).astype(np.uint8)
+    else:
+        st, goals = _scrambles(dom, n, 40, 9)
+    fn = make_pseudo_q(dom.num_actions) if is_q else pseudo_v
+    eng, oi = _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, iters, fn, is_q=is_q, max_nodes=3000000)
+    eng.close()
+
+
+def test_two_run_open_survives_regime_changes(monkeypatch):
+    """small (one-block tail) -> big (grid-wide merges) when instances are added, big -> small when instances are removed, and a
+    Q* engine that drops out of the big regime: the two runs carry over / are flushed and the searches go on unchanged."""
+    L = _lib()
+    monkeypatch.setenv("DXB200_YOUNG_EVERY", "2")
+    monkeypatch.setenv("DXB200_YOUNG_BIG", "2")
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 5, 35, 12)
+    # A*: 2 x 50 (small) -> + 2 x 400 (big) at iteration 6 -> the two big ones removed at iteration 13 -> + 1 x 20 at iteration 16:
+    # the regime is decided when instances are added, so that is where the engine goes back to the one-block tail
+    st6, goals6 = _scrambles(dom, 6, 35, 12)
+    eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st6[:2], goals6[:2], 50, 0.5, 26, pseudo_v,
+                             add_later=[(6, st6[2:4], goals6[2:4], 400), (16, st6[4:5], goals6[4:5], 20)],
+                             max_pop=2 * 50 + 2 * 400 + 20, remove_at=(13, [2, 3]), max_nodes=3000000)
+    eng.close()
+    # Q*: 3 x 600 (big) -> two removed at iteration 8: 600 x 12 pushes still big; then the engine is reused after a reset
+    eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st[:3], goals[:3], 600, 0.5, 16, make_pseudo_q(12), is_q=True, remove_at=(8, [0, 2]),
+                             max_nodes=3000000)
+    eng.close()
+    # Q*: 2 x 150 = 3600 pushes (big) -> one removed: 1800 pushes, the small Q* kernels have one run: flush
+    eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st[:2], goals[:2], 150, 0.5, 16, make_pseudo_q(12), is_q=True, remove_at=(7, [1]),
+                             max_nodes=3000000)
     eng.close()
 
 

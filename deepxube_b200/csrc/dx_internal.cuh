@@ -286,6 +286,7 @@ struct ClosedDev {
     uint32_t mask;                  // capacity - 1
 };
 
+#define DX_KEY_CUT 23          // low f-key bits left to the sort's fix-up (k_open.cu, digit_of)
 struct SortBufs {
     unsigned long long* key[2];
     uint32_t* inst[2];
@@ -300,6 +301,11 @@ struct SortBufs {
                                   // the status words of earlier searches must never match again)
     uint32_t* part_a;             // [merge tiles + 1] merge-path partition of every merge tile (k_merge_partition)
     uint32_t* part_i;             // [merge tiles + 1] ... and its instance
+    // the digit passes leave out the low key_cut bits of the f-key; groups of equal (instance, key >> key_cut) are put in full-key
+    // order afterwards (k_sort_fixup lists the groups that are not, k_sort_fixup_groups repairs them)
+    uint32_t* fix_list;           // [max_sort / 2 + 2] listed inversions; fix_list[0] = how many
+    uint32_t* fix_claim;          // [max_sort] group claims, tagged with the sort counter
+    int key_cut;                  // DX_KEY_CUT, or 0 (DXB200_SORT_CUT=0): every key bit goes through the digit passes
     int onesweep;                 // 1: one kernel per digit pass; 0 (DXB200_SORT_ONESWEEP=0): histogram / tile scan / scatter
     int max_tiles;
     int num_digits;       // digit positions that can vary: 8 key bytes + the bytes max_instances - 1 occupies

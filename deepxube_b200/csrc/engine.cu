@@ -578,6 +578,11 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
                           YT_MAX_INST_HOST;
         A_(e->sort.part_a, mt); A_(e->sort.part_i, mt);
     }
+    A_(e->sort.fix_list, (size_t)e->max_sort / 2 + 2);       // (a listed inversion has a predecessor in its group: at most n / 2)
+    A_(e->sort.fix_claim, (size_t)e->max_sort + 1);
+    cudaMemset(e->sort.fix_claim, 0, ((size_t)e->max_sort + 1) * sizeof(uint32_t));
+    e->sort.key_cut = DX_KEY_CUT;
+    if (const char* c = getenv("DXB200_SORT_CUT")) e->sort.key_cut = std::max(0, std::min(40, atoi(c)));
     e->sort.onesweep = 1;
     if (const char* c = getenv("DXB200_SORT_ONESWEEP")) e->sort.onesweep = (c[0] == '0') ? 0 : 1;
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);

@@ -150,10 +150,17 @@ int dx_launch_make_keys_q(cudaStream_t s, const Ctl* ctl, const InstArrays& ia, 
 }
 
 // ---------------------------------------------------------------------------------------------
-// Radix sort (LSD, 8-bit digits, stable).  Digit d < 8: byte d of the f-key; d >= 8: byte d-8 of the
-// instance id.
-__device__ __forceinline__ uint32_t digit_of(unsigned long long key, uint32_t inst, int d) {
-    return d < 8 ? (uint32_t)(key >> (8 * d)) & 255u : (inst >> (8 * (d - 8))) & 255u;
+// Radix sort (LSD, 8-bit digits, stable).  Digit d < 8: bits [cut + 8 d, cut + 8 d + 8) of the f-key; d >= 8: byte d-8 of the
+// instance id.  cut = SortBufs::key_cut: the low 23 bits of the key do NOT go through the digit passes.  f = w g + h has 52
+// varying mantissa bits (w g is a full double) but h is a float32: two different (g, h) pairs land within 2^-29 of each other
+// about once per 10^8 pairs, so after sorting on (instance, key >> 23) almost every group of equal sort keys is a single entry or a
+// set of exact ties; k_sort_fixup / k_sort_fixup_big put the few others into full-key order (stable, so the result is the order of
+// the full 64-bit sort for ANY input -- only the time depends on the assumption).  That is 4-5 digit passes instead of 8-9
+// (sign / high exponent digits are constant and skipped as before).
+__device__ __forceinline__ uint32_t digit_of(unsigned long long key, uint32_t inst, int d, int cut) {
+    if (d >= 8) return (inst >> (8 * (d - 8))) & 255u;
+    const int sh = cut + 8 * d;
+    return sh < 64 ? (uint32_t)(key >> sh) & 255u : 0u;
 }
 
 __global__ void __launch_bounds__(OPEN_THREADS)
@@ -168,7 +175,7 @@ k_radix_prepass(const Ctl* __restrict__ ctl, SortBufs sb) {
         const unsigned long long key = sb.key[0][k];
         const uint32_t inst = sb.inst[0][k];
 #pragma unroll
-        for (int d = 0; d < DX_NUM_DIGITS; ++d) atomicAdd(&s_h[d * 256 + digit_of(key, inst, d)], 1u);
+        for (int d = 0; d < DX_NUM_DIGITS; ++d) atomicAdd(&s_h[d * 256 + digit_of(key, inst, d, sb.key_cut)], 1u);
     }
     __syncthreads();
     for (int i = threadIdx.x; i < DX_NUM_DIGITS * 256; i += OPEN_THREADS)
@@ -192,12 +199,18 @@ __global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
         sb.ghist[i] = 0;
     }
     __syncthreads();
-    if (threadIdx.x < DX_NUM_DIGITS) {
-        uint32_t acc = 0;
-        for (int b = 0; b < 256; ++b) {
-            const uint32_t c = s_cnt[threadIdx.x * 256 + b];
-            sb.gbase[threadIdx.x * 256 + b] = acc;
-            acc += c;
+    {   // exclusive scan of every digit position's 256 counts: a warp per position, 8 consecutive bins per lane
+        const int lane = threadIdx.x & 31;
+        for (int d = threadIdx.x >> 5; d < DX_NUM_DIGITS; d += blockDim.x >> 5) {
+            uint32_t c[8], sum = 0;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { c[k] = s_cnt[d * 256 + lane * 8 + k]; sum += c[k]; }
+            uint32_t incl = sum;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const uint32_t y = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += y; }
+            uint32_t acc = incl - sum;
+#pragma unroll
+            for (int k = 0; k < 8; ++k) { sb.gbase[d * 256 + lane * 8 + k] = acc; acc += c[k]; }
         }
     }
     if (threadIdx.x < DX_NUM_DIGITS) sb.tickets[threadIdx.x] = 0;
@@ -210,6 +223,7 @@ __global__ void k_radix_flags(Ctl* __restrict__ ctl, SortBufs sb) {
         }
         ctl->sort_final = src;
         sb.tickets[DX_NUM_DIGITS] += 1;        // new tag for the look-back words of this sort's passes
+        sb.fix_list[0] = 0;
     }
 }
 
@@ -230,7 +244,7 @@ k_radix_hist(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 #pragma unroll
         for (int r = 0; r < ITEMS; ++r) {
             const uint32_t e = base + r * OPEN_THREADS + threadIdx.x;
-            if (e < n) atomicAdd(&s_h[digit_of(keys[e], insts[e], d)], 1u);
+            if (e < n) atomicAdd(&s_h[digit_of(keys[e], insts[e], d, sb.key_cut)], 1u);
         }
     }
     __syncthreads();
@@ -298,7 +312,7 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
         key[r] = valid ? keys[e] : 0ull;
         inst[r] = valid ? insts[e] : 0u;
         val[r] = valid ? vals[e] : 0u;
-        dig[r] = valid ? digit_of(key[r], inst[r], d) : (256u + lane);
+        dig[r] = valid ? digit_of(key[r], inst[r], d, sb.key_cut) : (256u + lane);
         const uint32_t peers = __match_any_sync(0xffffffffu, dig[r]);
         const int leader = __ffs(peers) - 1;
         const uint32_t before = __popc(peers & ((1u << lane) - 1u));
@@ -353,7 +367,9 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 #define OS_MIN_BLOCKS 2
 #endif
 #define OS_TILE (OPEN_THREADS * OS_ITEMS)
+#ifndef OS_WINDOW
 #define OS_WINDOW 8                       // predecessor words fetched per round trip of the look-back
+#endif
 __global__ void __launch_bounds__(OPEN_THREADS, OS_MIN_BLOCKS)
 k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
     __shared__ uint32_t s_cnt[OPEN_THREADS / 32][256];
@@ -393,7 +409,7 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
 #pragma unroll
         for (int r = 0; r < OS_ITEMS; ++r) {
             const bool valid = base + warp * (32 * OS_ITEMS) + r * 32 + lane < n;
-            const uint32_t dg = valid ? digit_of(key[r], inst[r], d) : (256u + lane);
+            const uint32_t dg = valid ? digit_of(key[r], inst[r], d, sb.key_cut) : (256u + lane);
             const uint32_t peers = __match_any_sync(0xffffffffu, dg);
             const int leader = __ffs(peers) - 1;
             const uint32_t before = __popc(peers & ((1u << lane) - 1u));
@@ -599,6 +615,153 @@ int dx_launch_small_push_v(cudaStream_t s, Ctl* ctl, const InstArrays& ia, const
     return 1;
 }
 
+// After the digit passes: entries are in (instance, key >> cut, original position) order; what is left to do is a stable sort by
+// the low bits inside every group of equal (instance, key >> cut).  Almost every group is a single entry or a set of exact ties
+// (a clipped heuristic gives f = w g for 10^5 entries at once): nothing to do, and that is found out with O(1) work per entry --
+// k_sort_fixup (read-only) lists the entries that are SMALLER than their predecessor in the same group (inversions), at most one per
+// FIX_BACK positions of a group; k_sort_fixup_groups repairs the listed groups, a block each.
+#define FIX_BACK 64
+__device__ __forceinline__ bool fix_same(const unsigned long long* K, const uint32_t* In, uint32_t j, uint32_t inst,
+                                         unsigned long long head, int cut) {
+    return In[j] == inst && (K[j] >> cut) == head;
+}
+
+__global__ void __launch_bounds__(256)
+k_sort_fixup(const Ctl* __restrict__ ctl, SortBufs sb) {
+    if (ctl->error) return;
+    const uint32_t n = ctl->sort_n;
+    const int cut = sb.key_cut;
+    const unsigned long long* __restrict__ K = sb.key[ctl->sort_final];
+    const uint32_t* __restrict__ In = sb.inst[ctl->sort_final];
+    for (uint32_t e = blockIdx.x * blockDim.x + threadIdx.x + 1; e < n; e += gridDim.x * blockDim.x) {
+        const unsigned long long key = K[e], pk = K[e - 1];
+        const uint32_t inst = In[e];
+        const unsigned long long head = key >> cut;
+        if (pk <= key || (pk >> cut) != head || In[e - 1] != inst) continue;               // no inversion at e
+        // an earlier inversion of the same group within FIX_BACK positions has this group listed already
+        bool earlier = false;
+        uint32_t lo = e - 1;
+        for (int steps = 0; steps < FIX_BACK && lo > 0 && fix_same(K, In, lo - 1, inst, head, cut); ++steps, --lo)
+            if (K[lo - 1] > K[lo]) { earlier = true; break; }
+        if (!earlier) sb.fix_list[1 + atomicAdd(&sb.fix_list[0], 1u)] = e;
+    }
+}
+
+// A block per listed inversion: the group [lo, hi) around it (256 positions per round trip), claimed through fix_claim[lo] (several
+// listed inversions may belong to one long group; the word carries the sort's epoch, so it is never cleared), then its non-decreasing
+// runs are merged by ranking -- an entry's output position is its offset in its own run plus, for every other run, the number of
+// entries that precede it there (earlier runs win ties: stable).  O(len x runs x log len) loads: an outlier inside 10^5 exact ties is
+// 3 runs.  With more than FIX_RUNS runs (hand-made heuristics with many distinct values inside one 2^cut window) the run starts no
+// longer fit shared memory and every entry counts its predecessors directly, O(len^2).
+#define FIX_RUNS 1024
+__global__ void __launch_bounds__(256)
+k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
+    __shared__ uint32_t s_run[FIX_RUNS + 1];
+    __shared__ uint32_t s_w[8];
+    __shared__ uint32_t s_a, s_b, s_cnt, s_mine;
+    if (ctl->error) return;
+    const uint32_t groups = sb.fix_list[0];
+    if (groups == 0) return;
+    const uint32_t n = ctl->sort_n, fin = ctl->sort_final;
+    const uint32_t epoch = sb.tickets[DX_NUM_DIGITS];
+    const int cut = sb.key_cut;
+    unsigned long long* K = sb.key[fin];
+    uint32_t* V = sb.val[fin];
+    const uint32_t* __restrict__ In = sb.inst[fin];
+    unsigned long long* TK = sb.key[fin ^ 1u];
+    uint32_t* TV = sb.val[fin ^ 1u];
+    const uint32_t tid = threadIdx.x;
+    for (uint32_t gi = blockIdx.x; gi < groups; gi += gridDim.x) {
+        const uint32_t x = sb.fix_list[1 + gi];
+        const uint32_t inst = In[x];
+        const unsigned long long head = K[x] >> cut;       // (the high bits of every entry of a group are the same: safe to read while
+        __syncthreads();                                   //  another block rewrites the group)
+        if (tid == 0) { s_a = 0; s_b = n; s_cnt = 0; s_mine = 0; }
+        __syncthreads();
+        for (uint32_t top = x;;) {                         // lo: positions top - 1 - tid; the nearest non-member below x decides
+            const bool valid = tid < top;
+            const uint32_t j = valid ? top - 1 - tid : 0;
+            if (valid && !fix_same(K, In, j, inst, head, cut)) atomicMax(&s_a, j + 1);
+            __syncthreads();
+            const uint32_t found = s_a;
+            __syncthreads();
+            if (found > 0 || top <= 256) break;
+            top -= 256;
+        }
+        const uint32_t lo = s_a;
+        if (tid == 0) s_mine = atomicExch(&sb.fix_claim[lo], epoch) != epoch ? 1u : 0u;
+        __syncthreads();
+        if (!s_mine) continue;                             // (block-uniform) another listed inversion of this group got here first
+        for (uint32_t base = x + 1; base < n; base += 256) {        // hi: the nearest non-member above x
+            const uint32_t j = base + tid;
+            if (j < n && !fix_same(K, In, j, inst, head, cut)) atomicMin(&s_b, j);
+            __syncthreads();
+            const uint32_t found = s_b;
+            __syncthreads();
+            if (found < n) break;
+        }
+        const uint32_t hi = s_b;
+        for (uint32_t base = lo; base < hi; base += 256) {          // run starts in position order (ordered compaction per 256)
+            const uint32_t j = base + tid;
+            const bool start = j < hi && (j == lo || K[j - 1] > K[j]);
+            const uint32_t bal = __ballot_sync(0xffffffffu, start);
+            if ((tid & 31) == 0) s_w[tid >> 5] = __popc(bal);
+            __syncthreads();
+            uint32_t off = s_cnt;
+            for (uint32_t w = 0; w < (tid >> 5); ++w) off += s_w[w];
+            off += __popc(bal & ((1u << (tid & 31)) - 1u));
+            if (start && off < FIX_RUNS) s_run[off] = j;
+            __syncthreads();
+            if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; s_cnt += t; }
+            __syncthreads();
+        }
+        const uint32_t runs = s_cnt;
+        if (runs <= FIX_RUNS) {
+            if (tid == 0) s_run[runs] = hi;
+            __syncthreads();
+            for (uint32_t j = lo + tid; j < hi; j += 256) {
+                const unsigned long long kj = K[j];
+                uint32_t rl = 0, rh = runs - 1;                    // my run: the last one starting at or before j
+                while (rl < rh) { const uint32_t m = (rl + rh + 1) >> 1; if (s_run[m] <= j) rl = m; else rh = m - 1; }
+                uint32_t rank = j - s_run[rl];
+                for (uint32_t r = 0; r < runs; ++r) {
+                    if (r == rl) continue;
+                    uint32_t a2 = s_run[r], b2 = s_run[r + 1];    // entries of run r that go before kj: <= for earlier runs, < for later ones
+                    const uint32_t r0 = a2;
+                    while (a2 < b2) {
+                        const uint32_t m = (a2 + b2) >> 1;
+                        const unsigned long long km = K[m];
+                        if (r < rl ? km <= kj : km < kj) a2 = m + 1; else b2 = m;
+                    }
+                    rank += a2 - r0;
+                }
+                TK[lo + rank] = kj;
+                TV[lo + rank] = V[j];
+            }
+        } else {
+            for (uint32_t j = lo + tid; j < hi; j += 256) {
+                const unsigned long long kj = K[j];
+                uint32_t rank = 0;
+                for (uint32_t i = lo; i < hi; ++i) {
+                    const unsigned long long ki = K[i];
+                    rank += (ki < kj || (ki == kj && i < j)) ? 1u : 0u;
+                }
+                TK[lo + rank] = kj;
+                TV[lo + rank] = V[j];
+            }
+        }
+        __syncthreads();
+        for (uint32_t j = lo + tid; j < hi; j += 256) { K[j] = TK[j]; V[j] = TV[j]; }
+    }
+}
+
+static int launch_sort_fixup(cudaStream_t s, Ctl* ctl, const SortBufs& sb, int max_n) {
+    if (sb.key_cut <= 0) return 0;
+    k_sort_fixup<<<min(dx_div_up(max_n, 256), 148 * 8), 256, 0, s>>>(ctl, sb);
+    k_sort_fixup_groups<<<148 * 4, 256, 0, s>>>(ctl, sb);
+    return 2;
+}
+
 int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp& t, int max_n, bool small) {
     if (small) {
         k_sort_small<<<1, 1024, 0, s>>>(ctl, sb);
@@ -611,16 +774,21 @@ int dx_launch_sort(cudaStream_t s, Ctl* ctl, const SortBufs& sb, const ScanTemp&
     launches += 2;
     if (sb.onesweep) {
         const int blocks = min(dx_div_up(max_n, OS_TILE), 148 * 4);           // persistent over tiles (ticket order)
-        for (int d = 0; d < sb.num_digits; ++d) k_radix_onesweep<<<blocks, OPEN_THREADS, 0, s>>>(ctl, sb, d);
-        return launches + sb.num_digits;
+        for (int d = 0; d < sb.num_digits; ++d) {
+            if (d < 8 && sb.key_cut + 8 * d >= 64) continue;                   // (no key bits left in this digit)
+            k_radix_onesweep<<<blocks, OPEN_THREADS, 0, s>>>(ctl, sb, d);
+            ++launches;
+        }
+        return launches + launch_sort_fixup(s, ctl, sb, max_n);
     }
     for (int d = 0; d < sb.num_digits; ++d) {      // higher instance-id bytes are constant zero: never launched
+        if (d < 8 && sb.key_cut + 8 * d >= 64) continue;
         k_radix_hist<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_tilescan<<<256, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         k_radix_scatter<<<sb.max_tiles, OPEN_THREADS, 0, s>>>(ctl, sb, d);
         launches += 3;
     }
-    return launches;
+    return launches + launch_sort_fixup(s, ctl, sb, max_n);
 }
 
 // ---------------------------------------------------------------------------------------------

@@ -7,7 +7,7 @@ import pytest
 import golden_utils as gu
 from oracle.domains_np import OracleDomain
 from oracle.nnet_torch import heurv_from_state_dict, random_state_dict
-from oracle.pseudo_heur import make_pseudo_q, pseudo_v
+from oracle.pseudo_heur import make_pseudo_q, make_pseudo_q_fine, pseudo_v, pseudo_v_fine
 from oracle.search import OracleSearch
 
 pytestmark = pytest.mark.gpu
@@ -435,6 +435,32 @@ def test_two_run_open_of_big_batches_matches_the_oracle(monkeypatch, every, dnam
         st, goals = _scrambles(dom, n, 40, 9)
     fn = make_pseudo_q(dom.num_actions) if is_q else pseudo_v
     eng, oi = _run_vs_oracle(L, dom, dname, dim, st, goals, batch, weight, iters, fn, is_q=is_q, max_nodes=3000000)
+    eng.close()
+
+
+@pytest.mark.parametrize("levels,scale_log2,is_q", [
+    (1 << 24, -42, False),     # ~3600 distinct keys per iteration inside a few 2^-30 windows: small unsorted groups everywhere
+    (4096, -40, False),        # every pushed key of an iteration in ONE window, ~4096 distinct values: long unsorted groups (rank sort)
+    (5, -40, True),            # five distinct values: long groups that are mostly exact ties, out of order across the values
+    (1 << 20, -20, True),      # ordinary spread: single-entry groups
+])
+def test_sort_key_cut_keeps_the_full_key_order(levels, scale_log2, is_q):
+    """The digit passes of the batch sort leave out the low 23 bits of the f-key (k_open.cu digit_of / k_sort_fixup): heuristics
+    whose values differ only far below that cut -- small unsorted groups, long unsorted groups, long groups of exact ties -- must
+    still pop in exactly the oracle's (f, push order) order, every iteration."""
+    L = _lib()
+    dom = OracleDomain("cube3")
+    st, goals = _scrambles(dom, 3, 40, 21)
+    scale = 2.0 ** scale_log2
+
+    def fn_v(states, goals_=None):
+        return (np.floor(pseudo_v_fine(states) * 262144.0) % levels) * scale          # exact in float32: < 2^24 levels
+
+    def fn_q(states, goals_=None):
+        return (np.floor(make_pseudo_q_fine(12)(states) * 262144.0) % levels) * scale
+
+    eng, oi = _run_vs_oracle(L, dom, "cube3", 0, st, goals, 300 if not is_q else 500, 0.6, 12, fn_q if is_q else fn_v, is_q=is_q,
+                             max_nodes=3000000)
     eng.close()
 
 

@@ -276,6 +276,7 @@ struct dx_engine {
     bool graph_small = false;          // whether the captured graphs use the single-block sort
     bool use_graphs = true;
     int poll_every = 4;             // small-batch dx_run: iterations launched per host poll (DXB200_POLL_EVERY)
+    int poll_every_big = 4;         // ... for big batches (DXB200_POLL_EVERY_BIG)
     // young-run OPEN of small-batch A* engines (YoungBufs): the main run stays in open_*[0] while it is active
     YoungBufs young{};
     bool young_enabled = true;      // DXB200_YOUNG=0 disables
@@ -508,6 +509,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     if (const char* ng = getenv("DXB200_NO_GRAPHS")) e->use_graphs = !(ng[0] == '1');
     if (const char* fs = getenv("DXB200_SMALL_FUSE")) e->fuse_small = !(fs[0] == '0');
     if (const char* pe = getenv("DXB200_POLL_EVERY")) e->poll_every = std::max(1, atoi(pe));
+    if (const char* pe = getenv("DXB200_POLL_EVERY_BIG")) e->poll_every_big = std::max(1, atoi(pe));
     if (const char* pd = getenv("DXB200_PDL")) e->pdl = !(pd[0] == '0');
     if (const char* yg = getenv("DXB200_YOUNG")) e->young_enabled = !(yg[0] == '0');
     if (const char* yg = getenv("DXB200_YOUNG_BIG")) e->young_big_enabled = std::max(0, std::min(2, atoi(yg)));
@@ -1153,7 +1155,7 @@ static int build_step_graphs(dx_engine* e, bool prof) {
         cudaGraph_t g = nullptr;
         DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
         e->cap_prof = prof ? p : -1;
-        e->halt_flag = !prof && e->graph_small;      // (only the graphs dx_run launches in bursts)
+        e->halt_flag = !prof;                        // (only the graphs dx_run launches in bursts)
         g_dx_pdl = !prof && e->graph_small && e->pdl && (small_fused_v(e) || small_fused_q(e));
         const int rc = full_step(e);                 // flips e->parity
         g_dx_pdl = false;
@@ -1206,7 +1208,8 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // Small-batch searches (an iteration is ~100 us of kernels) launch a BURST of iterations per host poll: k_end_iter raises
     // DX_DEVERR_DONE in the iteration that finishes the last instance, which turns the rest of the burst into no-ops, so the
     // search still stops in exactly the iteration the reference's loop does; the host reads how many iterations really ran.
-    const int burst_max = (use_graph && !prof && e->graph_small) ? e->poll_every : 1;
+    // (big batches: an iteration is 1-10 ms, the host's poll costs ~30 us of idle GPU per iteration -- 2 % of a cube3 Q* iteration)
+    const int burst_max = (use_graph && !prof) ? (e->graph_small ? e->poll_every : e->poll_every_big) : 1;
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         if (use_graph) {
             const int burst = std::min(burst_max, (int)max_iters - done);

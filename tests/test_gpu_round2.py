@@ -530,3 +530,34 @@ def test_bursts_stop_in_the_exact_iteration_and_the_engine_continues_after_a_fin
     # instance 0 alone is the KAT search: the reference's iteration count / node count / cost (tests/golden/kat_cube3.npz)
     assert stat[0][1] == int(k["hard_nodes"][0]) and stat[0][2] == float(k["hard_path_costs"][0])
     assert all(s[3] for s in stat) and all(p is not None for p in paths)
+
+
+@pytest.mark.parametrize("is_q", [False, True])
+def test_big_batch_bursts_stop_in_the_exact_iteration(monkeypatch, is_q):
+    """dx_run polls the host every DXB200_POLL_EVERY_BIG iterations for big batches too: identical iteration counts, node counts, costs
+    and paths for 1 / 3 / 4 iterations per poll, max_iters honoured mid-burst, and the engine goes on after a search that ended inside
+    a burst (two-run OPEN compaction schedule and buffer parities included)."""
+    L = _lib()
+    k = gu.load("kat_cube3")
+    sd = gu.state_dict_np("cube3q" if is_q else "cube3v")
+    blob, info = L.pack_state_dict(sd)
+    results = {}
+    if is_q:                   # (the golden Q network is barely trained, outputs 0 .. 0.1: breadth-first in effect, so 4-move scrambles)
+        k = dict(zip(("hard_states", "hard_goals"), _scrambles(OracleDomain("cube3"), 4, 4, 33)))
+    for poll in ("1", "3", "4"):
+        monkeypatch.setenv("DXB200_POLL_EVERY_BIG", poll)
+        eng = L.Engine("cube3", 0, "graph_q" if is_q else "graph_v", L.DX_HEUR_NET_FP32, max_instances=4, max_pop_total=1600, max_nodes=6000000)
+        eng.load_weights(54, 6, info["res_dim"], info["num_blocks"], 12 if is_q else 1, True, blob)
+        w = 0.05 if is_q else 0.2
+        eng.add_instances(k["hard_states"][:2], k["hard_goals"][:2], 400, w)            # 2 x 400 x 12 pushes: the grid-wide kernels
+        assert eng.run(5) == 5 and all(s.itr == 5 for s in eng.status())                  # (5 is not a multiple of 3 or 4)
+        done = 5 + eng.run(100000)
+        assert all(s.finished for s in eng.status()) and max(s.itr for s in eng.status()) == done
+        eng.add_instances(k["hard_states"][2:4], k["hard_goals"][2:4], 400, w)           # no reset: two more join the finished ones
+        more = eng.run(100000)
+        st = eng.status()
+        results[poll] = (done, more, [(s.itr, s.num_nodes_generated, s.ub, s.lb, bool(s.finished)) for s in st],
+                         [eng.get_path(j)[0] for j in range(4)])
+        eng.close()
+    assert results["1"] == results["3"] == results["4"]
+    assert all(s[4] for s in results["1"][2]) and all(p is not None for p in results["1"][3])

@@ -18,13 +18,15 @@ inside the captured iteration).  This file is written by `tools/r2_summary.py`.
 
 ## 1. C2 (cube3 A\\*, B = 10 000, 8 instances per step, bf16) — last iteration of a step, 34 launches
 
-`profiles/r2k_launch_list_ncu.csv` (whole step), `profiles/r2_c2_last_iteration_ncu.csv`.  9.9 ms serialised: the 8 tcgen05 GEMM launches (fused
-one-hot + first block, 6 hidden, fused-output last) 94.0 %; radix sort (prepass + flags + 9 one-sweep passes, constant digits return at once) 1.7 %;
-`k_merge` 1.1 %, `k_closed_link` 0.9 %, `k_scatter_kept` 0.9 %, `k_closed_decide` 0.4 %, `k_expand_t` 0.3 %.
+`profiles/r2f_launch_list_ncu.csv` (whole step, final kernels), `profiles/r2_c2_last_iteration_ncu.csv`.  9.93 ms serialised: the 8 tcgen05 GEMM launches (fused
+one-hot + first block, 6 hidden, fused-output last) 94.7 %; radix sort (prepass + flags + 7 one-sweep launches of which 5 are real passes + the two fix-up
+kernels) 1.6 %; `k_merge` 1.1 %, `k_closed_link` 0.8 %, `k_scatter_kept` 0.6 %, `k_closed_decide` 0.3 %, `k_expand_t` 0.3 %.
 Live (bench, power-capped to ~{d['clocks']['sm_mhz']:.0f} MHz): heuristic {100 * st['heur'] / tot:.1f} % of the step (hidden GEMMs {st['gemm_hidden']:.0f} ms + input / first block
 {st['gemm_input']:.0f} ms of {d['ms_per_step']:.0f} ms), sort {st['sort']:.1f} ms, CLOSED {st['filt']:.1f} ms, scatter {st['scatter']:.1f} ms, merge / pop {st['pushpop']:.1f} ms, expand {st['expand']:.1f} ms —
-the kernel's share of the step agrees (94 % serialised at full clocks vs {100 * st['heur'] / tot:.0f} % live).
-Roofline (bench line): hidden GEMMs {d['roofline']['achieved']:.0f} TFLOP/s = **{d['roofline']['frac']:.3f}** of the measured sustained bf16 peak; whole step {d['roofline']['whole_step_frac']:.3f}.
+the kernel's share of the step agrees (95 % serialised at full clocks vs {100 * st['heur'] / tot:.0f} % live).
+Roofline (bench line): hidden GEMMs {d['roofline']['achieved']:.0f} TFLOP/s = **{d['roofline']['frac']:.3f}** of the measured sustained bf16 peak; whole step {d['roofline']['whole_step_frac']:.3f}
+(the fraction follows the SM clock the power cap allows: the same kernels on a box that held 1275 MHz measured 86.4 M nodes/s, 0.860 / 0.828 — the
+bench line of commit 055a7b5, `git show 055a7b5:profiles/r2_bench_n1.json`).
 `ncu --set full` of the six plain hidden-layer launches of the last iteration (`profiles/r2k_summary.md`, `r2k_gemm_traffic.json`; 783 k rows,
 148 CTAs = 74 CTA pairs): 1.09 ms (no residual) / 1.20 ms (residual) at 1.97 GHz, tensor pipe active 88.2-88.9 % / 85.5-85.8 %, DRAM read + write
 3.24 / 4.89 GB against 3.21 / 4.81 GB algorithmic — traffic = 1.01× algorithmic.
@@ -40,17 +42,26 @@ Roofline (bench line): hidden GEMMs {d['roofline']['achieved']:.0f} TFLOP/s = **
 bf16 against fp32-accurate on C2 itself (`bf16_deviation`: 2 instances in lock-step): popped-set overlap per iteration
 {d['bf16_deviation']['popped_set_overlap_per_iteration']}, heuristic error max {d['bf16_deviation']['heuristic_abs_error_max']:.2e} / mean {d['bf16_deviation']['heuristic_abs_error_mean']:.2e}, nodes generated identical.
 
-## 2. C4 (cube3 Q\\*, B = 10 000, 8 instances, 40 iterations) — last iteration, 35 launches
+## 2. C4 (cube3 Q\\*, B = 10 000, 8 instances, 40 iterations) — last iteration, 38 launches
 
-`profiles/r2_q_last_iteration_ncu.csv`.  1 547 µs serialised: GEMMs 982 µs (63.5 %), `k_merge` 245 µs (15.9 %), one-sweep radix passes
-177 µs (11.4 %), `k_merge_partition` 23 µs.  `ncu --set full` of the sort / merge kernels of a late iteration (810 k pushed entries, 25 M-entry OPEN):
+`profiles/r2_q_last_iteration_ncu.csv` (final kernels).  1 301 µs serialised: GEMMs 976 µs (75.0 %), one-sweep radix passes 127 µs (9.7 %: four real key
+passes 18.7-29.4 µs, two skipped 3.5 µs, the instance pass 18.4 µs), prepass + flags 19 µs, fix-up 13.8 µs, young merge (`k_merge_partition` + `k_merge`)
+45.4 µs, pop split + popped-list merge 20.3 µs, plan 4.5 µs.  Before the two-run OPEN and the key cut (same iteration, earlier in the round): 1 547 µs —
+`k_merge` 245 µs (15.9 %), radix passes 177 µs (11.4 %), `k_merge_partition` 23 µs.  Live (bench `configs.c4_qstar`, stage timers): sort {100 * q['stage_share_one_extra_step']['sort']:.1f} %,
+merge + pop {100 * q['stage_share_one_extra_step']['pushpop']:.1f} % of the step (12.7 % / 11.8 % before); the compactions (about seven per 40 iterations, host-scheduled, outside the stage
+timers) add ≈ 1.6 ms to a {q['ms_per_step']:.1f} ms step.
+`ncu --set full` of a late iteration (810 k pushed entries, 25 M-entry OPEN of which ≈ 3 M in the young runs; `gpurun_out/r2f_qsort_full_raw.csv`):
 
 | kernel | duration | DRAM read | DRAM write | algorithmic bytes | achieved / HBM peak (6 546 GB/s) |
 |---|---:|---:|---:|---:|---:|
-| `k_radix_onesweep` (per digit pass) | 18-30 µs | 13.0 MB | ≈ 0 (the scattered output stays in L2) | 16 B read + 16 B written × 810 k = 25.9 MB | 0.9-1.4 TB/s = **0.13-0.22** — look-back-latency-bound at this size (181 registers = one block per SM when captured; now 8 items per thread, 2 blocks per SM: −18 % on the npuzzle.5 sort, −2 % here) |
-| `k_radix_prepass` | 12.4 µs | 9.6 MB | 0 | 8 B × 810 k keys | 0.5 TB/s = 0.08 |
-| `k_merge_partition` | 18.4 µs | 59.7 MB | 3.6 MB | — (32-ary searches) | — |
-| `k_merge` (1 184 blocks) | 163.8 µs | 200.3 MB | 192.2 MB | 12 B read + 12 B written × (25 M OPEN + 0.8 M batch) = 620 MB nominal; 392 MB measured (part of the run is L2-resident) | 2.4 TB/s = **0.37** — and O(\\|OPEN\\|) work for an O(batch) change: the kernel furthest from what the algorithm needs |
+| `k_radix_onesweep` (real digit pass; 469 blocks, 124 registers, 2 blocks per SM) | 19.8-31.2 µs | 13.4 MB | ≈ 0.1 MB (the scattered output stays in L2) | 16 B read + 16 B written × 810 k = 25.9 MB | 0.8-1.3 TB/s = **0.13-0.20** — look-back-latency-bound at this size (tile 2048 / 2816 / 3072 and look-back windows 8 / 16 / 32 measured: ±5 %) |
+| `k_radix_prepass` | 12.5-13.2 µs | 9.6 MB | 0 | 8 B + 4 B × 810 k | 0.7 TB/s = 0.11 |
+| `k_sort_fixup` (inversion scan, read-only) | 7.0 µs | 6.4 MB | 0 | 12 B × 810 k | 1.4 TB/s = 0.21 |
+| `k_sort_fixup_groups` (a block per listed group) | 9.7 µs | 0.2 MB | 0 | — | — |
+| `k_merge_partition` + `k_merge`, young run + batch (1 184 blocks) | 9.0 + 22.1 µs | 7.3 + 19.2 MB | ≈ 0 | 12 B read + 12 B written × (≈ 3 M young + 0.8 M batch) = 91 MB nominal (L2-resident: 26 MB of DRAM traffic) | 4.1 TB/s of L2-level traffic |
+| `k_young_split` (a warp per instance) | 7.6 µs | 0.1 MB | 0 | — (one 32-ary search per instance) | latency |
+| `k_merge_partition` + `k_merge`, popped lists (80 k entries) | 5.3 + 10.6 µs | 1.0 MB | 0 | 12 B × 2 × 80 k | latency |
+| before: `k_merge` over the whole run (1 184 blocks) | 163.8 µs | 200.3 MB | 192.2 MB | 12 B read + 12 B written × (25 M OPEN + 0.8 M batch) = 620 MB nominal | 2.4 TB/s = 0.37, O(\\|OPEN\\|) work for an O(batch) change |
 
 ## 3. Small-batch iteration (tutorial KAT: cube3, graph.100B_0.1W, resnet_fc.200H_2B, ~1200 children per iteration), bf16 — 4 launches
 

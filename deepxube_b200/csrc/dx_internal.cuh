@@ -400,7 +400,7 @@ int dx_launch_backup_children(cudaStream_t s, const DomainDev& d, const Ctl* ctl
                               const uint32_t* child_prefix, const BackupLog& bk, int max_children);
 int dx_launch_backup_ub_paths(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const BackupLog& bk);
 int dx_launch_her_deepest(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, const uint32_t* node_parent,
-                          const uint8_t* node_action, const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
+                          const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
                           uint32_t* rec_depth, uint32_t* best_depth, uint32_t* deep_node, uint8_t* out_rows, int max_inst);
 int dx_launch_backup_tree(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, uint32_t itr);
 int dx_launch_backup_q_modes(cudaStream_t s, const Ctl* ctl, const uint32_t* node_parent, const uint8_t* node_solved,

@@ -1445,7 +1445,7 @@ extern "C" int dx_backup_deepest(dx_engine* e, uint8_t* states, int32_t* depths,
     DX_CUDA(cudaSetDevice(e->cfg.device));
     if (e->n_inst == 0) return DX_OK;
     cudaStream_t s = e->stream;
-    e->launches += dx_launch_her_deepest(s, e->dom, e->d_ctl, e->bk, e->node_parent, e->node_action, e->node_state, e->backups_q ? 1 : 0,
+    e->launches += dx_launch_her_deepest(s, e->dom, e->d_ctl, e->bk, e->node_parent, e->node_state, e->backups_q ? 1 : 0,
                                          e->ia.root, e->her_cand, e->her_depth, e->her_best, e->her_node, e->her_rows, e->n_inst);
     DX_CUDA(cudaMemcpyAsync(states, e->her_rows, (size_t)e->n_inst * e->S, cudaMemcpyDeviceToHost, s));
     if (depths) DX_CUDA(cudaMemcpyAsync(depths, e->her_best, (size_t)e->n_inst * 4, cudaMemcpyDeviceToHost, s));

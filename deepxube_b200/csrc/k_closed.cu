@@ -1050,7 +1050,7 @@ __global__ void k_her_rows(DomainDev d, const Ctl* __restrict__ ctl, const uint8
 }
 
 int dx_launch_her_deepest(cudaStream_t s, const DomainDev& d, const Ctl* ctl, const BackupLog& bk, const uint32_t* node_parent,
-                          const uint8_t* node_action, const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
+                          const uint8_t* node_state, int is_q, const uint32_t* root, uint32_t* rec_cand,
                           uint32_t* rec_depth, uint32_t* best_depth, uint32_t* deep_node, uint8_t* out_rows, int max_inst) {
     cudaMemsetAsync(best_depth, 0, (size_t)max_inst * sizeof(uint32_t), s);
     k_her_depth<<<148 * 4, 256, 0, s>>>(ctl, bk, node_parent, is_q, rec_cand, rec_depth, best_depth);

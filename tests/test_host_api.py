@@ -284,3 +284,46 @@ def test_replay_buffers_match_the_reference_deque():
         np.random.seed(5)
         (ms, mg), msol = mine.sample(6)
         assert rs == [bytes(r) for r in ms] and rg == [bytes(r) for r in mg] and rsol == msol.tolist()
+
+
+def test_her_goal_relabelling_order_and_rng_stream():
+    """UpdateHER._get_her_goals (base/updater.py:485-530) in the updater mirror, without a device: instances that finished with a
+    solution keep their goal and come first, the others get `sample_goal_from_state(start states, deepest states)` with the deepest
+    rows looked up by instance slot, and one `np.random.uniform(size=len(instances))` is drawn per group like the reference's unused
+    `rand_keeps` (the streams of a seeded reference run and of the mirror stay aligned)."""
+    from deepxube_b200.domains.grid import Grid, GridGoal, GridState
+    from deepxube_b200.updaters.updater_rl import UpdateHeurQRLHER, UpdateHeurVRLHER, _HERMixin
+
+    class _Inst:
+        def __init__(self, slot, start, goal, fin, soln):
+            self._slot, self._fin, self._soln = slot, fin, soln
+            self.root_node = type("N", (), {"state": start, "goal": goal})()
+
+        def finished(self):
+            return self._fin
+
+        def has_soln(self):
+            return self._soln
+
+    dom = Grid(7)
+    calls = []
+    orig = dom.sample_goal_from_state
+    dom.sample_goal_from_state = lambda starts, deep: (calls.append((list(starts), list(deep))), orig(starts, deep))[1]
+    up = object.__new__(UpdateHeurVRLHER)
+    up.domain = dom
+    group = [_Inst(3, GridState(0, 0), GridGoal(6, 6), False, False), _Inst(0, GridState(1, 1), GridGoal(1, 2), True, True),
+             _Inst(5, GridState(2, 2), GridGoal(5, 5), True, False), _Inst(1, GridState(3, 3), GridGoal(3, 3), True, True)]
+    deepest = np.array([[9, 9], [8, 8], [7, 7], [0, 4], [6, 6], [2, 5]], np.uint8)          # rows by instance slot
+    np.random.seed(11)
+    insts, goals = up._group_goals(group, deepest)
+    after = np.random.uniform()
+    np.random.seed(11)
+    np.random.uniform(0, 1, size=4)
+    assert after == np.random.uniform()                                                       # exactly one draw of len(group) values
+    assert [i._slot for i in insts] == [0, 1, 3, 5]                                           # goal-keeping first, order kept within each part
+    assert [(g.robot_x, g.robot_y) for g in goals] == [(1, 2), (3, 3), (0, 4), (2, 5)]
+    assert len(calls) == 1 and calls[0][0] == [GridState(0, 0), GridState(2, 2)] and calls[0][1] == [GridState(0, 4), GridState(2, 5)]
+    calls.clear()
+    insts, goals = up._group_goals(group[1:2], deepest)                                       # nobody to relabel: the domain is not asked
+    assert calls == [] and [i._slot for i in insts] == [0] and (goals[0].robot_x, goals[0].robot_y) == (1, 2)
+    assert UpdateHeurVRLHER.her and UpdateHeurQRLHER.her and UpdateHeurQRLHER.is_q and issubclass(UpdateHeurQRLHER, _HERMixin)

@@ -116,6 +116,7 @@ struct Ctl {
     uint32_t backup_overflow;
     uint32_t backup_at;    // log position of this iteration's first record
     uint32_t young_total;  // entries in the young runs' current buffer (young-run OPEN, YoungBufs)
+    uint32_t sort_slow;    // the sort's fix-up met a group with more than FIX_RUNS runs: the key cut does not fit these keys (host: cut 0)
 };
 
 // Per-instance state (structure of arrays, capacity max_instances (+1 for offset arrays)).

@@ -292,6 +292,8 @@ struct dx_engine {
     // stay within a few batches for tens of iterations and the five extra launches cost more than the shorter merge saves
     // (measured: npuzzle.5 B = 1000 x 64 -1.4 %, cube3 B = 10 000 x 8 +-0).
     int young_big_enabled = 1;
+    bool cut_sticky = true;         // DXB200_SORT_CUT_STICKY=0: keep the key cut after a slow sort (tests of the fix-up's merge rounds)
+    int graph_cut = -1;             // key cut the captured graphs were built with
     int young_every = 0;            // DXB200_YOUNG_EVERY=n: compact the big-batch young runs every n iterations (0: the cost model)
     bool pdl = true;                // small-batch graphs: programmatic dependent launches (DXB200_PDL=0 disables)
     bool halt_flag = false;         // the step being launched / captured belongs to dx_run: k_end_iter may raise DX_DEVERR_DONE
@@ -388,6 +390,9 @@ void dx_prof_end() { if (g_prof_engine) stage_end(g_prof_engine); }
 static int sync_ctl(dx_engine* e) {
     DX_CUDA(cudaMemcpyAsync(e->h_ctl, e->d_ctl, sizeof(Ctl), cudaMemcpyDeviceToHost, e->stream));
     DX_CUDA(cudaStreamSynchronize(e->stream));
+    // the batch sort's key cut assumes float-like keys; a sort that had to merge > FIX_RUNS runs inside one group says these keys are
+    // not (results are still exact): from the next launch on every key bit goes through the digit passes (graphs: dx_run re-captures)
+    if (e->h_ctl->sort_slow && e->sort.key_cut > 0 && e->cut_sticky) e->sort.key_cut = 0;
     if (e->h_ctl->error & ~DX_DEVERR_DONE) {
         std::string m = "device capacity exceeded:";
         if (e->h_ctl->error & DX_DEVERR_NODES) m += " max_nodes";
@@ -585,6 +590,7 @@ extern "C" int dx_engine_create(const dx_config* cfg, dx_engine** out) {
     cudaMemset(e->sort.fix_claim, 0, ((size_t)e->max_sort + 1) * sizeof(uint32_t));
     e->sort.key_cut = DX_KEY_CUT;
     if (const char* c = getenv("DXB200_SORT_CUT")) e->sort.key_cut = std::max(0, std::min(40, atoi(c)));
+    if (const char* c = getenv("DXB200_SORT_CUT_STICKY")) e->cut_sticky = !(c[0] == '0');
     e->sort.onesweep = 1;
     if (const char* c = getenv("DXB200_SORT_ONESWEEP")) e->sort.onesweep = (c[0] == '0') ? 0 : 1;
     A_(e->scan.block_sums, std::max<size_t>((C + 1) / 4096, ((size_t)256 * e->sort.max_tiles) / 4096) + 8);
@@ -1148,6 +1154,7 @@ static int full_step(dx_engine* e) {
 static int build_step_graphs(dx_engine* e, bool prof) {
     e->graph_small = small_sort(e);
     e->graph_young = e->young_active ? (e->young_big ? 2 : 1) : 0;
+    e->graph_cut = e->sort.key_cut;
     const int p0 = e->parity;
     const long long l0 = e->launches;
     for (int k = 0; k < 2; ++k) {
@@ -1187,7 +1194,8 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
     const bool use_graph = e->use_graphs, prof = e->profiling != 0;
-    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != (e->young_active ? (e->young_big ? 2 : 1) : 0)))
+    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != (e->young_active ? (e->young_big ? 2 : 1) : 0) ||
+                                                        e->graph_cut != e->sort.key_cut))
         drop_graphs(e);                              // captured with the other sort / OPEN structure
     if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
     if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level
@@ -1229,6 +1237,11 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
             done += ran;
             if (prof) stage_collect_graph(e, e->parity ^ 1);
             if (ran < burst) break;                  // (everything finished inside the burst)
+            if (e->graph_cut != e->sort.key_cut) {   // (the sort asked for every key bit: capture the iteration again)
+                drop_graphs(e);
+                DX_TRY(build_step_graphs(e, prof));
+                if (prof) e->prof_graph_level = e->profiling;
+            }
         } else {
             DX_TRY(young_before_step(e));
             DX_TRY(full_step(e));

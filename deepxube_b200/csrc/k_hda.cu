@@ -308,7 +308,9 @@ int dx_launch_hda_bucket(cudaStream_t s, const DomainDev& d, Ctl* ctl, const Sor
     int launches = 0;
     const int blocks = min(dx_div_up(max_children, 256), 148 * 8);
     k_hda_owner_keys<<<blocks, 256, 0, s>>>(d, ctl, child_state, child_g, sb, world, counts);
-    launches += 1 + dx_launch_sort(s, ctl, sb, t, max_children);
+    SortBufs sb_all = sb;
+    sb_all.key_cut = 0;                       // (owner keys are small integers: every bit goes through the digit passes)
+    launches += 1 + dx_launch_sort(s, ctl, sb_all, t, max_children);
     const int pblocks = (int)min((long long)dx_div_up((long long)max_children * (d.SP / 4 + 4), 256), (long long)148 * 16);
     k_hda_pack<<<pblocks, 256, 0, s>>>(d, ctl, sb, child_state, child_g, popped, rank, send);
     return launches + 1;
@@ -345,7 +347,9 @@ int dx_launch_hda_send(cudaStream_t s, const DomainDev& d, Ctl* ctl, const SortB
     int launches = 0;
     const int blocks = min(dx_div_up(max_children, 256), 148 * 8);
     k_hda_owner_keys<<<blocks, 256, 0, s>>>(d, ctl, child_state, child_g, sb, world, counts);
-    launches += 1 + dx_launch_sort(s, ctl, sb, t, max_children);
+    SortBufs sb_all = sb;
+    sb_all.key_cut = 0;                       // (owner keys are small integers: every bit goes through the digit passes)
+    launches += 1 + dx_launch_sort(s, ctl, sb_all, t, max_children);
     const int pblocks = (int)min((long long)dx_div_up((long long)max_children * (d.SP / 4 + 4), 256), (long long)148 * 16);
     k_hda_pack_seg<<<pblocks, 256, 0, s>>>(d, ctl, sb, child_state, child_g, popped, rank, world, counts, dst, seg_records, aux);
     return launches + 1;

@@ -651,11 +651,12 @@ k_sort_fixup(const Ctl* __restrict__ ctl, SortBufs sb) {
 // listed inversions may belong to one long group; the word carries the sort's epoch, so it is never cleared), then its non-decreasing
 // runs are merged by ranking -- an entry's output position is its offset in its own run plus, for every other run, the number of
 // entries that precede it there (earlier runs win ties: stable).  O(len x runs x log len) loads: an outlier inside 10^5 exact ties is
-// 3 runs.  With more than FIX_RUNS runs (hand-made heuristics with many distinct values inside one 2^cut window) the run starts no
-// longer fit shared memory and every entry counts its predecessors directly, O(len^2).
+// 3 runs.  With more than FIX_RUNS runs (keys whose information sits below the cut: hand-made heuristics with many distinct values
+// inside one 2^cut window) the run starts go to global scratch and adjacent runs are merged pairwise, round by round (a merge sort
+// by ranking, O(len x log runs x log len)), and the control block is flagged so that the host stops using the cut for this engine.
 #define FIX_RUNS 1024
 __global__ void __launch_bounds__(256)
-k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
+k_sort_fixup_groups(Ctl* __restrict__ ctl, SortBufs sb) {
     __shared__ uint32_t s_run[FIX_RUNS + 1];
     __shared__ uint32_t s_w[8];
     __shared__ uint32_t s_a, s_b, s_cnt, s_mine;
@@ -670,6 +671,7 @@ k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
     const uint32_t* __restrict__ In = sb.inst[fin];
     unsigned long long* TK = sb.key[fin ^ 1u];
     uint32_t* TV = sb.val[fin ^ 1u];
+    uint32_t* scratch = sb.inst[fin ^ 1u];                 // (free after the last pass; a group uses the words of its own positions)
     const uint32_t tid = threadIdx.x;
     for (uint32_t gi = blockIdx.x; gi < groups; gi += gridDim.x) {
         const uint32_t x = sb.fix_list[1 + gi];
@@ -701,6 +703,7 @@ k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
             if (found < n) break;
         }
         const uint32_t hi = s_b;
+        uint32_t* R = scratch + lo;                                 // run starts (all of them; the first FIX_RUNS also in s_run)
         for (uint32_t base = lo; base < hi; base += 256) {          // run starts in position order (ordered compaction per 256)
             const uint32_t j = base + tid;
             const bool start = j < hi && (j == lo || K[j - 1] > K[j]);
@@ -711,6 +714,7 @@ k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
             for (uint32_t w = 0; w < (tid >> 5); ++w) off += s_w[w];
             off += __popc(bal & ((1u << (tid & 31)) - 1u));
             if (start && off < FIX_RUNS) s_run[off] = j;
+            if (start) R[off] = j;
             __syncthreads();
             if (tid == 0) { uint32_t t = 0; for (int w = 0; w < 8; ++w) t += s_w[w]; s_cnt += t; }
             __syncthreads();
@@ -739,16 +743,51 @@ k_sort_fixup_groups(const Ctl* __restrict__ ctl, SortBufs sb) {
                 TV[lo + rank] = V[j];
             }
         } else {
-            for (uint32_t j = lo + tid; j < hi; j += 256) {
-                const unsigned long long kj = K[j];
-                uint32_t rank = 0;
-                for (uint32_t i = lo; i < hi; ++i) {
-                    const unsigned long long ki = K[i];
-                    rank += (ki < kj || (ki == kj && i < j)) ? 1u : 0u;
+            if (tid == 0) ctl->sort_slow = 1;
+            unsigned long long* sk = K; uint32_t* sv = V;             // ping-pong: the merged runs of a round land in the other pair
+            unsigned long long* dk = TK; uint32_t* dv = TV;
+            uint32_t nr = runs;
+            __syncthreads();
+            while (nr > 1) {
+                for (uint32_t j = lo + tid; j < hi; j += 256) {
+                    const unsigned long long kj = sk[j];
+                    uint32_t rl = 0, rh = nr - 1;                  // my run
+                    while (rl < rh) { const uint32_t m = (rl + rh + 1) >> 1; if (R[m] <= j) rl = m; else rh = m - 1; }
+                    const uint32_t pa = rl & ~1u, pb = pa + 1;     // the pair (pa, pb); a last run without partner is copied
+                    uint32_t pos = j;
+                    if (pb < nr) {
+                        const uint32_t a0 = R[pa], b0 = R[pb], b1 = pb + 1 < nr ? R[pb + 1] : hi;
+                        uint32_t l2, h2;
+                        if (rl == pa) { l2 = b0; h2 = b1; } else { l2 = a0; h2 = b0; }
+                        const uint32_t base2 = l2;
+                        while (l2 < h2) {                          // run A entries precede equal run B entries (stable)
+                            const uint32_t m = (l2 + h2) >> 1;
+                            const unsigned long long km = sk[m];
+                            if (rl == pa ? km < kj : km <= kj) l2 = m + 1; else h2 = m;
+                        }
+                        pos = a0 + (j - (rl == pa ? a0 : b0)) + (l2 - base2);
+                    }
+                    dk[pos] = kj;
+                    dv[pos] = sv[j];
                 }
-                TK[lo + rank] = kj;
-                TV[lo + rank] = V[j];
+                __syncthreads();
+                const uint32_t half = (nr + 1) >> 1;               // R[p] <- R[2 p], ascending chunks: read, barrier, write
+                for (uint32_t c0 = 0; c0 < half; c0 += 256) {
+                    const uint32_t pidx = c0 + tid;
+                    const uint32_t v = pidx < half ? R[2 * pidx] : 0u;
+                    __syncthreads();
+                    if (pidx < half) R[pidx] = v;
+                    __syncthreads();
+                }
+                nr = half;
+                unsigned long long* tk = sk; sk = dk; dk = tk;
+                uint32_t* tv = sv; sv = dv; dv = tv;
             }
+            if (sk != K) {
+                for (uint32_t j = lo + tid; j < hi; j += 256) { K[j] = sk[j]; V[j] = sv[j]; }
+            }
+            __syncthreads();
+            continue;
         }
         __syncthreads();
         for (uint32_t j = lo + tid; j < hi; j += 256) { K[j] = TK[j]; V[j] = TV[j]; }

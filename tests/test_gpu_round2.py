@@ -444,11 +444,14 @@ def test_two_run_open_of_big_batches_matches_the_oracle(monkeypatch, every, dnam
     (5, -40, True),            # five distinct values: long groups that are mostly exact ties, out of order across the values
     (1 << 20, -20, True),      # ordinary spread: single-entry groups
 ])
-def test_sort_key_cut_keeps_the_full_key_order(levels, scale_log2, is_q):
+@pytest.mark.parametrize("sticky", ["0", "1"])
+def test_sort_key_cut_keeps_the_full_key_order(monkeypatch, sticky, levels, scale_log2, is_q):
     """The digit passes of the batch sort leave out the low 23 bits of the f-key (k_open.cu digit_of / k_sort_fixup): heuristics
     whose values differ only far below that cut -- small unsorted groups, long unsorted groups, long groups of exact ties -- must
-    still pop in exactly the oracle's (f, push order) order, every iteration."""
+    still pop in exactly the oracle's (f, push order) order, every iteration.  A sort that meets more than 1024 runs inside one group
+    makes the engine give up the cut (sticky = 1, the default); sticky = 0 keeps it, so the merge rounds run every iteration."""
     L = _lib()
+    monkeypatch.setenv("DXB200_SORT_CUT_STICKY", sticky)
     dom = OracleDomain("cube3")
     st, goals = _scrambles(dom, 3, 40, 21)
     scale = 2.0 ** scale_log2

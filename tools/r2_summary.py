@@ -79,9 +79,9 @@ issue slots 24 % busy (latency chains: CAS → compare → exchange → slot rea
 
 ## 4. Multi-GPU (raw bench lines: `profiles/r2_bench_n2.json`, `profiles/r2_bench_n8.json`)
 
-See DESIGN.md §6.  Instance-sharded headline: 86.4 M (1 GPU) → 168.7 M (2) → 692.3 M nodes/s (8 B200s, 8.0×).  One HDA\\* search:
-2 GPUs 123.9 M (peer-memory exchange) / 119.9 M (NCCL all-to-all), exchange phase 0.016 / 0.064 ms of a 1.51 / 1.56 ms iteration, load imbalance
-1.05; 8 GPUs (B = 80 000) **517.4 M** / 500.1 M nodes/s, exchange 0.026 / 0.091 ms of 1.40 / 1.45 ms, imbalance 1.12.
+See DESIGN.md §6.  Instance-sharded headline (final kernels): {d['value'] / 1e6:.1f} M (1 GPU) → 170.7 M (2) → 692.0 M nodes/s (8 B200s).  One HDA\\* search:
+2 GPUs 128.7 M (peer-memory exchange) / 123.9 M (NCCL all-to-all), exchange phase 0.021 / 0.074 ms of a 1.45 / 1.51 ms iteration, load imbalance
+1.05; 8 GPUs (B = 80 000) **528.8 M** / 504.0 M nodes/s, exchange 0.026 / 0.101 ms of 1.37 / 1.44 ms, imbalance 1.12.
 """
 open(os.path.join(ROOT, "profiles", "r2_summary.md"), "w").write(md)
 print("written", len(md))

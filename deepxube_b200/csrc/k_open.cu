@@ -370,6 +370,17 @@ k_radix_scatter(const Ctl* __restrict__ ctl, SortBufs sb, int d) {
 #ifndef OS_WINDOW
 #define OS_WINDOW 8                       // predecessor words fetched per round trip of the look-back
 #endif
+// -DOS_PROFILE: clock64 timeline of thread 0 of every block, summed over tiles: [0] tiles, [1] ticket, [2] loads, [3] ranking,
+// [4] count scan + publish, [5] look-back, [6] scatter (read and cleared through dx_tail_profile_read / dx_debug_tc_profile with
+// DXB200_PROF_TAIL set).  cube3 Q*, 8 x 100 k entries (396 tiles): ticket 1.2 k, loads issued 1.1 k, ranking (absorbs the load latency) 4.6 k,
+// scan + publish 0.3 k, look-back 6.8 k (3.2 k with one instance = 50 tiles), scatter 3.7 k cycles per tile -- latency end to end: tile sizes
+// 1024-3072, 2-4 blocks per SM, look-back windows 8-32 and ballot-based ranking all measured within +-3 % of each other
+#ifdef OS_PROFILE
+__device__ unsigned long long g_os_prof[16];
+#define OS_MARK(slot) do { if (threadIdx.x == 0) { const long long t_now = clock64(); atomicAdd(&g_os_prof[slot], (unsigned long long)(t_now - t_prev)); t_prev = t_now; } } while (0)
+#else
+#define OS_MARK(slot) do { } while (0)
+#endif
 __global__ void __launch_bounds__(OPEN_THREADS, OS_MIN_BLOCKS)
 k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
     __shared__ uint32_t s_cnt[OPEN_THREADS / 32][256];
@@ -387,6 +398,9 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
     unsigned long long* __restrict__ okeys = sb.key[dst];
     uint32_t* __restrict__ oinsts = sb.inst[dst];
     uint32_t* __restrict__ ovals = sb.val[dst];
+#ifdef OS_PROFILE
+    long long t_prev = clock64();
+#endif
     for (;;) {
         __syncthreads();
         if (threadIdx.x == 0) s_tile = atomicAdd(&sb.tickets[d], 1u);
@@ -394,6 +408,10 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
         __syncthreads();
         const uint32_t tile = s_tile;
         if (tile >= ntiles) return;
+        OS_MARK(1);
+#ifdef OS_PROFILE
+        if (threadIdx.x == 0) atomicAdd(&g_os_prof[0], 1ull);
+#endif
         const uint32_t base = tile * OS_TILE;
         unsigned long long key[OS_ITEMS];
         uint32_t inst[OS_ITEMS], val[OS_ITEMS];
@@ -406,6 +424,8 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
             inst[r] = valid ? insts[e] : 0u;
             val[r] = valid ? vals[e] : 0u;
         }
+        if (key[0] == 1ull && inst[OS_ITEMS - 1] == 0xFFFFFFFFu && val[0] == 7u) __syncwarp();   // (keeps the loads ahead of the first mark)
+        OS_MARK(2);
 #pragma unroll
         for (int r = 0; r < OS_ITEMS; ++r) {
             const bool valid = base + warp * (32 * OS_ITEMS) + r * 32 + lane < n;
@@ -424,6 +444,7 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
             __syncwarp();
         }
         __syncthreads();
+        OS_MARK(3);
         {   // thread dg: this tile's count of digit dg, exclusive offsets over the warps, then the look-back
             const uint32_t dg = threadIdx.x;
             uint32_t acc = 0;
@@ -439,6 +460,7 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
                 s_base[dg] = sb.gbase[d * 256 + dg];
             } else {
                 st[(size_t)tile * 256 + dg] = epoch | (OS_FLAG_AGG << 30) | acc;
+                OS_MARK(4);
                 uint32_t excl = 0;
                 int t = (int)tile - 1;
                 bool done = false;
@@ -463,6 +485,7 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
             }
         }
         __syncthreads();
+        OS_MARK(5);
 #pragma unroll
         for (int r = 0; r < OS_ITEMS; ++r) {
             if (dig[r] < 256u) {
@@ -472,6 +495,7 @@ k_radix_onesweep(Ctl* __restrict__ ctl, SortBufs sb, int d) {
                 ovals[pos] = val[r];
             }
         }
+        OS_MARK(6);
     }
 }
 
@@ -1074,9 +1098,14 @@ __device__ unsigned long long g_tail_prof[16];
 #define YT_MARK(slot) do { } while (0)
 #endif
 int dx_tail_profile_read(unsigned long long* out16) {
-    if (cudaMemcpyFromSymbol(out16, g_tail_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return DX_ERR_CUDA;
     unsigned long long z[16] = {0};
+#ifdef OS_PROFILE
+    if (cudaMemcpyFromSymbol(out16, g_os_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return DX_ERR_CUDA;
+    if (cudaMemcpyToSymbol(g_os_prof, z, sizeof(z)) != cudaSuccess) return DX_ERR_CUDA;
+#else
+    if (cudaMemcpyFromSymbol(out16, g_tail_prof, sizeof(unsigned long long) * 16) != cudaSuccess) return DX_ERR_CUDA;
     if (cudaMemcpyToSymbol(g_tail_prof, z, sizeof(z)) != cudaSuccess) return DX_ERR_CUDA;
+#endif
     return DX_OK;
 }
 

@@ -836,7 +836,10 @@ extern "C" int dx_add_instances(dx_engine* e, const uint8_t* states, const uint8
         for (int i = 0; i < e->n_inst; ++i) if (ha[i]) bsum += hb[i];
         if (bsum > (long long)e->max_pop) DX_FAIL(DX_ERR_CAPACITY, "sum of the live instances' batch sizes exceeds max_pop_total");
     }
-    e->sort_bound = bsum * e->A;             // no iteration can push more entries than every instance's full batch expanded
+    // no iteration can push more entries than every live instance's full batch expanded -- but the CURRENT popped list may still hold
+    // the last pops of instances that finished and were not removed (they stay readable, Instance.get_nodes): the next iteration's
+    // kernels see those entries too, so the bound that selects the small-batch kernels must cover them
+    e->sort_bound = std::max<long long>(bsum, (long long)c.n_pop + n) * e->A;
     {   // young-run OPEN: entered with the first instances after a reset, left for good when the batch outgrows the small regime
         const bool have = e->young_enabled && e->young.m_head != nullptr && e->hda_world < 1;
         const bool want_small = have && small_fused_v(e);

@@ -564,3 +564,39 @@ def test_big_batch_bursts_stop_in_the_exact_iteration(monkeypatch, is_q):
         eng.close()
     assert results["1"] == results["3"] == results["4"]
     assert all(s[4] for s in results["1"][2]) and all(p is not None for p in results["1"][3])
+
+
+def test_instances_added_right_after_another_finished_keep_the_big_kernels():
+    """Found by tools/fuzz_vs_oracle.py: an instance that has just finished still has its last pops in the current popped list (they
+    stay readable); instances added at that moment made the live batches fit the small-batch regime (303 x 4 pushes) while the next
+    iteration's CLOSED block still saw 603 x 4 children -- "max_pop_total" from its own sanity check.  The regime bound now covers the
+    current popped list."""
+    L = _lib()
+    dom = OracleDomain("npuzzle", 4)
+    easy, goals = _scrambles(dom, 1, 3, 5)
+    hard, _ = _scrambles(dom, 4, 60, 6)
+    st = np.concatenate([easy, hard[:1]])
+    gl = np.tile(goals[0], (2, 1))
+    orc = OracleSearch(dom, pseudo_v_fine, False, 300, 1.0)
+    oi = orc.add_instances(st, gl)
+    eng = L.Engine("npuzzle", 4, "graph_v", L.DX_HEUR_HOST, max_instances=5, max_pop_total=603, max_nodes=2000000)
+    eng.add_instances(st, gl, 300, 1.0, root_vals=pseudo_v_fine(st, gl))
+    added, after = False, 0
+    for t in range(40):
+        if not added and oi[0].finished() and not oi[1].finished():
+            oi += orc.add_instances(hard[1:4], np.tile(goals[0], (3, 1)), batch_size=1)
+            eng.add_instances(hard[1:4], np.tile(goals[0], (3, 1)), 1, 1.0, root_vals=pseudo_v_fine(hard[1:4]))
+            added = True
+        orc.step()
+        k = eng.step_begin()
+        ps, pg = eng.get_pending(k)
+        eng.step_end(pseudo_v_fine(ps, pg) if k else np.zeros((0,)))
+        for j, (o, s) in enumerate(zip(oi, eng.status())):
+            assert s.lb == o.lb and s.ub == o.ub and s.num_nodes_generated == o.num_nodes_generated and bool(s.finished) == o.finished(), (t, j)
+            if not s.finished:
+                assert s.open_size == len(o.open), (t, j)
+        after += added
+        if after >= 6:
+            break
+    assert added and after >= 6
+    eng.close()

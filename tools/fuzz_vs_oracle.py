@@ -52,13 +52,17 @@ while time.time() < t_end:
         batch = max(1, 40000 // (n * A))
     weight = float(rng.choice([0.0, 0.2, 0.6, 1.0]))
     iters = int(rng.integers(6, 22))
-    kind = str(rng.choice(["ties", "fine", "subcut", "subcut2"]))
+    kind = str(rng.choice(["ties", "fine", "subcut", "subcut2", "zero-run"]))      # zero-run: device zero heuristic through dx_run (graphs, bursts)
     env = {"DXB200_YOUNG_BIG": str(rng.integers(0, 3)), "DXB200_YOUNG_EVERY": str(rng.choice([0, 1, 2, 5])),
-           "DXB200_SORT_CUT": str(rng.choice([0, 23, 30])), "DXB200_SORT_CUT_STICKY": str(rng.integers(0, 2))}
+           "DXB200_SORT_CUT": str(rng.choice([0, 23, 30])), "DXB200_SORT_CUT_STICKY": str(rng.integers(0, 2)),
+           "DXB200_POLL_EVERY": str(rng.choice([1, 3, 4])), "DXB200_POLL_EVERY_BIG": str(rng.choice([1, 2, 4])),
+           "DXB200_NO_GRAPHS": str(rng.choice([0, 0, 0, 1]))}
     for kv in os.environ.get("FUZZ_OVERRIDE", "").split():         # (replaying a failure with one switch changed)
         env[kv.split("=")[0]] = kv.split("=")[1]
     os.environ.update(env)
-    fn = heuristic(kind, is_q, A)
+    run_mode = kind == "zero-run"
+    chunks = [int(x) for x in rng.integers(1, 6, size=32)]          # iterations per dx_run call
+    fn = None if run_mode else heuristic(kind, is_q, A)
     st, goals = instances(dom, n)
     n_late = int(rng.integers(0, 4))
     t_add, t_rem = int(rng.integers(1, iters)), int(rng.integers(1, iters))
@@ -70,24 +74,36 @@ while time.time() < t_end:
         continue
     orc = OracleSearch(dom, fn, is_q, batch, weight)
     oi = orc.add_instances(st, goals)
-    eng = L.Engine(name, dim, "graph_q" if is_q else "graph_v", L.DX_HEUR_HOST, max_instances=n + n_late, max_pop_total=n * batch + n_late * b2,
-                   max_nodes=4000000)
-    eng.add_instances(st, goals, batch, weight, root_vals=fn(st, goals))
+    eng = L.Engine(name, dim, "graph_q" if is_q else "graph_v", L.DX_HEUR_ZERO if run_mode else L.DX_HEUR_HOST, max_instances=n + n_late,
+                   max_pop_total=n * batch + n_late * b2, max_nodes=4000000)
+    eng.add_instances(st, goals, batch, weight, root_vals=None if run_mode else fn(st, goals))
     gone = set()
     t = -1
     try:
-        for t in range(iters):
-            if n_late and t == t_add:
+        t = 0
+        while t < iters:
+            if n_late and t >= t_add and len(oi) == n:
                 oi += orc.add_instances(st2[:n_late], goals2[:n_late], batch_size=b2)
-                eng.add_instances(st2[:n_late], goals2[:n_late], b2, weight, root_vals=fn(st2[:n_late], goals2[:n_late]))
-            if rem and t == t_rem:
+                eng.add_instances(st2[:n_late], goals2[:n_late], b2, weight, root_vals=None if run_mode else fn(st2[:n_late], goals2[:n_late]))
+            if rem and t >= t_rem and not gone:
                 eng.remove_instances(rem)
                 gone.update(rem)
                 orc.instances = [o for j, o in enumerate(oi) if j not in gone]
-            orc.step()
-            k = eng.step_begin()
-            ps, pg = eng.get_pending(k)
-            eng.step_end(fn(ps, pg) if k else np.zeros((0, A) if is_q else (0,)))
+            if run_mode:                             # the engine stops in the iteration that finishes the last instance, like the loop below
+                want = chunks[t % 32]
+                did = 0
+                while did < want and not all(o.finished() for o in orc.instances):
+                    orc.step()
+                    did += 1
+                got = eng.run(want)
+                assert got == did, (t, "iterations run", got, did)
+                t += max(did, 1)
+            else:
+                orc.step()
+                k = eng.step_begin()
+                ps, pg = eng.get_pending(k)
+                eng.step_end(fn(ps, pg) if k else np.zeros((0, A) if is_q else (0,)))
+                t += 1
             for j, (o, s) in enumerate(zip(oi, eng.status())):
                 if j in gone:
                     continue

@@ -61,6 +61,8 @@ while time.time() < t_end:
         env[kv.split("=")[0]] = kv.split("=")[1]
     os.environ.update(env)
     run_mode = kind == "zero-run"
+    backups = (not run_mode) and bool(rng.integers(0, 4) == 0)      # evaluate-all engine with the training-label log, drained at the end
+    label_mode = str(rng.choice(["bellman", "ub_solns", "lhbl"]))
     chunks = [int(x) for x in rng.integers(1, 6, size=32)]          # iterations per dx_run call
     fn = None if run_mode else heuristic(kind, is_q, A)
     st, goals = instances(dom, n)
@@ -69,13 +71,17 @@ while time.time() < t_end:
     st2, goals2 = instances(dom, max(n_late, 1))
     b2 = int(rng.choice([1, batch, min(4 * batch, 1000)]))
     rem = sorted(set(rng.integers(0, n, size=int(rng.integers(0, 3))).tolist())) if n > 1 else []
-    desc = f"case {case}: {name}.{dim} {'Q*' if is_q else 'A*'} n={n} B={batch} w={weight} iters={iters} heur={kind} +{n_late}x{b2}@{t_add} -{rem}@{t_rem} {env}"
+    if backups:
+        rem = []                                                     # (the oracle's log indexes instances by position)
+    desc = (f"case {case}: {name}.{dim} {'Q*' if is_q else 'A*'} n={n} B={batch} w={weight} iters={iters} heur={kind} +{n_late}x{b2}@{t_add} -{rem}@{t_rem} "
+            f"{'backups:' + label_mode + ' ' if backups else ''}{env}")
     if case < first_case:
         continue
     orc = OracleSearch(dom, fn, is_q, batch, weight)
     oi = orc.add_instances(st, goals)
     eng = L.Engine(name, dim, "graph_q" if is_q else "graph_v", L.DX_HEUR_ZERO if run_mode else L.DX_HEUR_HOST, max_instances=n + n_late,
-                   max_pop_total=n * batch + n_late * b2, max_nodes=4000000)
+                   max_pop_total=n * batch + n_late * b2, max_nodes=4000000,
+                   max_backups=2 * (n * batch + n_late * b2) * (iters + 2) if backups else 0)
     eng.add_instances(st, goals, batch, weight, root_vals=None if run_mode else fn(st, goals))
     gone = set()
     t = -1
@@ -114,6 +120,17 @@ while time.time() < t_end:
                     cs, _, _ = eng.curr_nodes(j, len(o.nodes_curr) + 8)
                     assert np.array_equal(cs, o.store.state[o.nodes_curr]), (t, j, "popped")
                 checked += 1
+        if backups:
+            deep, depths = eng.backup_deepest()
+            want = [o.deepest_with_children() for o in oi]
+            assert np.array_equal(depths, np.array([d for _, d in want], np.int32)), "deepest depths"
+            assert np.array_equal(deep, np.stack([s_ for s_, _ in want])), "deepest states"
+            got = eng.drain_backups(label_mode)
+            w_st = np.concatenate([x[0] for x in orc.backup_log]); w_idx = np.concatenate([x[2] for x in orc.backup_log])
+            assert np.array_equal(got[0], w_st) and np.array_equal(got[-1], w_idx), "backup records"
+            if is_q:
+                assert np.array_equal(got[1], np.concatenate([x[3] for x in orc.backup_log])), "backup actions"
+            assert np.array_equal(got[-2], (orc.labels_q if is_q else orc.labels_v)(label_mode)), "labels " + label_mode
     except Exception as ex:
         print("FAIL", desc, "at iteration", t, "->", repr(ex)[:300], flush=True)
         sys.exit(1)

@@ -731,6 +731,9 @@ def gen_her() -> None:
     add("cube3_v", "cube3", "graph.6B_0.6W", False, [1, 2, 30, 40, 3, 25], 6)
     add("np4_v", "npuzzle.4", "graph.5B_0.8W", False, [2, 40, 60, 1, 50], 7)
     add("cube3_q", "cube3", "graph.8B_0.6W", True, [1, 30, 40, 2], 6)
+    add("np3_q", "npuzzle.3", "graph.4B_0.9W", True, [3, 20, 30, 1, 25, 18], 9)
+    add("lo3_v", "lightsout.3", "graph.3B_1.0W", False, [1, 5, 7, 9, 2], 5)
+    add("grid7_q_long", "grid.7d", "graph.1B_0.7W", True, [12, 12, 11, 10, 9, 12, 8], 9)
     np.savez_compressed(os.path.join(OUT, "her.npz"), **out)
     print("her.npz", len(out), "arrays")
 

@@ -567,7 +567,7 @@ def test_big_batch_bursts_stop_in_the_exact_iteration(monkeypatch, is_q):
 
 
 def test_instances_added_right_after_another_finished_keep_the_big_kernels():
-    """Found by tools/fuzz_vs_oracle.py: an instance that has just finished still has its last pops in the current popped list (they
+    """Found by tests/fuzz_vs_oracle.py: an instance that has just finished still has its last pops in the current popped list (they
     stay readable); instances added at that moment made the live batches fit the small-batch regime (303 x 4 pushes) while the next
     iteration's CLOSED block still saw 603 x 4 children -- "max_pop_total" from its own sanity check.  The regime bound now covers the
     current popped list."""

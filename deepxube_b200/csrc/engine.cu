@@ -265,11 +265,14 @@ struct dx_engine {
     float stage_ms[ST_COUNT] = {0};
     long long stage_calls[ST_COUNT] = {0};
     cudaEvent_t run_ev[2] = {nullptr, nullptr};
-    cudaGraphExec_t graph_exec[2] = {nullptr, nullptr};   // one captured iteration per buffer parity
+    // one captured iteration per (identity of the OPEN buffer pair, buffer parity): slot = 2 * open_id + parity.  A compaction of the
+    // two-run OPEN swaps the open_*[0] / [1] pointers instead of copying the merged runs back, so graphs exist for both identities
+    int open_id = 0;
+    cudaGraphExec_t graph_exec[4] = {nullptr, nullptr, nullptr, nullptr};
     // the same iteration captured with the stage timers as event-record nodes (used while profiling is on)
-    cudaGraphExec_t graph_prof_exec[2] = {nullptr, nullptr};
-    std::vector<cudaEvent_t> gev[2];   // begin/end pairs of the captured timers, per parity
-    std::vector<int> gev_stage[2];
+    cudaGraphExec_t graph_prof_exec[4] = {nullptr, nullptr, nullptr, nullptr};
+    std::vector<cudaEvent_t> gev[4];   // begin/end pairs of the captured timers, per slot
+    std::vector<int> gev_stage[4];
     int cap_prof = -1;                 // parity whose profiling graph is being captured, else -1
     int graph_launches = 0;
     long long sort_bound = 0;          // sum of batch_size * actions over the instances: no iteration pushes more entries
@@ -422,7 +425,7 @@ static bool small_fused_v(const dx_engine* e) {
 }
 
 static void drop_graphs(dx_engine* e) {
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (e->graph_exec[k]) { cudaGraphExecDestroy(e->graph_exec[k]); e->graph_exec[k] = nullptr; }
         if (e->graph_prof_exec[k]) { cudaGraphExecDestroy(e->graph_prof_exec[k]); e->graph_prof_exec[k] = nullptr; }
         for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
@@ -625,7 +628,7 @@ extern "C" int dx_engine_destroy(dx_engine* e) {
     if (g_prof_engine == e) g_prof_engine = nullptr;
     cudaSetDevice(e->cfg.device);
     if (e->stream) cudaStreamSynchronize(e->stream);
-    for (int k = 0; k < 2; ++k) {
+    for (int k = 0; k < 4; ++k) {
         if (e->graph_exec[k]) cudaGraphExecDestroy(e->graph_exec[k]);
         if (e->graph_prof_exec[k]) cudaGraphExecDestroy(e->graph_prof_exec[k]);
         for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
@@ -761,7 +764,7 @@ __global__ void k_young_copyback(const Ctl* __restrict__ ctl, const unsigned lon
     for (uint32_t t = tid; t <= I; t += nth) off_dst[t] = off_src[t];
 }
 
-// main run <- merge(main run remainder, young runs); the main run's home is open_*[0] (merged into [1], copied back)
+// main run <- merge(main run remainder, young runs); the main run's home is open_*[0]: merged into [1], then the pointers are swapped
 static int young_compact(dx_engine* e) {
     cudaStream_t s = e->stream;
     const int p = e->parity;
@@ -769,8 +772,10 @@ static int young_compact(dx_engine* e) {
     e->launches += dx_launch_young_compact(s, e->d_ctl, e->ia, e->sort, e->young, p, e->open_key[0], e->open_val[0], e->open_off[0],
                                            e->open_key[1], e->open_val[1], e->open_off[1], e->popped[p ^ 1], e->popped_inst[p ^ 1],
                                            e->pop_off[p], max_tiles, (uint32_t)e->max_open);
-    k_young_copyback<<<148 * 8, 256, 0, s>>>(e->d_ctl, e->open_key[1], e->open_val[1], e->open_off[1], e->open_key[0], e->open_val[0], e->open_off[0]);
-    e->launches += 1;
+    std::swap(e->open_key[0], e->open_key[1]);        // the merged runs become the main runs: no copy back (graphs are kept per identity
+    std::swap(e->open_val[0], e->open_val[1]);        // of the pair, dx_run picks / captures the set of the current one)
+    std::swap(e->open_off[0], e->open_off[1]);
+    e->open_id ^= 1;
     e->m_bound += e->y_bound;
     e->y_bound = 0;
     return DX_OK;
@@ -1164,7 +1169,8 @@ static int build_step_graphs(dx_engine* e, bool prof) {
         const int p = e->parity;
         cudaGraph_t g = nullptr;
         DX_CUDA(cudaStreamBeginCapture(e->stream, cudaStreamCaptureModeThreadLocal));
-        e->cap_prof = prof ? p : -1;
+        const int slot = 2 * e->open_id + p;
+        e->cap_prof = prof ? slot : -1;
         e->halt_flag = !prof;                        // (only the graphs dx_run launches in bursts)
         g_dx_pdl = !prof && e->graph_small && e->pdl && (small_fused_v(e) || small_fused_q(e));
         const int rc = full_step(e);                 // flips e->parity
@@ -1175,7 +1181,9 @@ static int build_step_graphs(dx_engine* e, bool prof) {
         cudaError_t ce = cudaStreamEndCapture(e->stream, &g);
         if (rc < 0) { if (g) cudaGraphDestroy(g); return rc; }
         if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph capture failed: ") + cudaGetErrorString(ce));
-        ce = cudaGraphInstantiate(prof ? &e->graph_prof_exec[p] : &e->graph_exec[p], g, 0);
+        if (prof && e->graph_prof_exec[slot]) { cudaGraphExecDestroy(e->graph_prof_exec[slot]); e->graph_prof_exec[slot] = nullptr; }
+        if (!prof && e->graph_exec[slot]) { cudaGraphExecDestroy(e->graph_exec[slot]); e->graph_exec[slot] = nullptr; }
+        ce = cudaGraphInstantiate(prof ? &e->graph_prof_exec[slot] : &e->graph_exec[slot], g, 0);
         cudaGraphDestroy(g);
         if (ce != cudaSuccess) DX_FAIL(DX_ERR_CUDA, std::string("graph instantiate failed: ") + cudaGetErrorString(ce));
     }
@@ -1197,20 +1205,22 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // The iteration is a fixed launch sequence (all sizes live in the device control block), so it is captured
     // once per buffer parity into a CUDA graph and replayed; per-kernel profiling needs the plain launches.
     const bool use_graph = e->use_graphs, prof = e->profiling != 0;
-    if ((e->graph_exec[0] || e->graph_prof_exec[0]) && (e->graph_small != small_sort(e) || e->graph_young != (e->young_active ? (e->young_big ? 2 : 1) : 0) ||
+    bool have_graphs = false;
+    for (int k = 0; k < 4; ++k) have_graphs = have_graphs || e->graph_exec[k] || e->graph_prof_exec[k];
+    if (have_graphs && (e->graph_small != small_sort(e) || e->graph_young != (e->young_active ? (e->young_big ? 2 : 1) : 0) ||
                                                         e->graph_cut != e->sort.key_cut))
         drop_graphs(e);                              // captured with the other sort / OPEN structure
-    if (use_graph && !prof && !e->graph_exec[0]) DX_TRY(build_step_graphs(e, false));
-    if (use_graph && prof && e->graph_prof_exec[0] && e->prof_graph_level != e->profiling) {     // captured at another level
-        for (int k = 0; k < 2; ++k) {
-            cudaGraphExecDestroy(e->graph_prof_exec[k]);
+    if (use_graph && !prof && !e->graph_exec[2 * e->open_id]) DX_TRY(build_step_graphs(e, false));
+    if (use_graph && prof && e->prof_graph_level != e->profiling) {     // captured at another level
+        for (int k = 0; k < 4; ++k) {
+            if (e->graph_prof_exec[k]) cudaGraphExecDestroy(e->graph_prof_exec[k]);
             e->graph_prof_exec[k] = nullptr;
             for (cudaEvent_t ev : e->gev[k]) if (ev) cudaEventDestroy(ev);
             e->gev[k].clear();
             e->gev_stage[k].clear();
         }
     }
-    if (use_graph && prof && !e->graph_prof_exec[0]) {
+    if (use_graph && prof && !e->graph_prof_exec[2 * e->open_id]) {
         stage_collect(e);
         DX_TRY(build_step_graphs(e, true));
         e->prof_graph_level = e->profiling;
@@ -1221,6 +1231,7 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
     // search still stops in exactly the iteration the reference's loop does; the host reads how many iterations really ran.
     // (big batches: an iteration is 1-10 ms, the host's poll costs ~30 us of idle GPU per iteration -- 2 % of a cube3 Q* iteration)
     const int burst_max = (use_graph && !prof) ? (e->graph_small ? e->poll_every : e->poll_every_big) : 1;
+    int last_slot = 0;
     while (done < max_iters && e->h_ctl->n_unfinished > 0) {
         if (use_graph) {
             const int burst = std::min(burst_max, (int)max_iters - done);
@@ -1231,14 +1242,19 @@ extern "C" int dx_run(dx_engine* e, int32_t max_iters, int32_t* iters_done) {
                 const int rcy = young_before_step(e);
                 e->parity = keep;
                 DX_TRY(rcy);
-                DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[e->parity ^ (b & 1)] : e->graph_exec[e->parity ^ (b & 1)], e->stream));
+                last_slot = 2 * e->open_id + (e->parity ^ (b & 1));
+                if (!(prof ? e->graph_prof_exec[last_slot] : e->graph_exec[last_slot])) {    // (first compaction: the OPEN pointers were swapped)
+                    DX_TRY(build_step_graphs(e, prof));
+                    if (prof) e->prof_graph_level = e->profiling;
+                }
+                DX_CUDA(cudaGraphLaunch(prof ? e->graph_prof_exec[last_slot] : e->graph_exec[last_slot], e->stream));
             }
             DX_TRY(sync_ctl(e));                     // synchronises the stream
             const int ran = burst == 1 ? 1 : (int)(e->h_ctl->itr - itr0);
             e->launches += (long long)ran * e->graph_launches;
             e->parity ^= (ran & 1);
             done += ran;
-            if (prof) stage_collect_graph(e, e->parity ^ 1);
+            if (prof) stage_collect_graph(e, last_slot);
             if (ran < burst) break;                  // (everything finished inside the burst)
             if (e->graph_cut != e->sort.key_cut) {   // (the sort asked for every key bit: capture the iteration again)
                 drop_graphs(e);
